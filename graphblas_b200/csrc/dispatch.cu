@@ -1,0 +1,40 @@
+// dispatch.cu -- run-time (xy type) -> compiled launcher table.  Each inst_<type>.cu translation
+// unit instantiates the semiring-templated kernels for one operand type, so they build in parallel.
+#include "engine.cuh"
+#include "kernels.cuh"
+
+namespace gb200 {
+
+#define GB200_DECL(NAME) bool launch_##NAME (int family, int z_code, int add, int mult, \
+    const void *args, LaunchCfg cfg) ;
+GB200_DECL (bool)   GB200_DECL (int8)   GB200_DECL (uint8)  GB200_DECL (int16)
+GB200_DECL (uint16) GB200_DECL (int32)  GB200_DECL (uint32) GB200_DECL (int64)
+GB200_DECL (uint64) GB200_DECL (fp32)   GB200_DECL (fp64)
+#undef GB200_DECL
+
+bool launch_typed (int xy_code, int family, int z_code, int add, int mult, const void *args,
+    int grid, int block)
+{
+    LaunchCfg cfg ;
+    cfg.grid = grid ; cfg.block = block ; cfg.stream = ctx ().stream ;
+    bool ok = false ;
+    switch (xy_code)
+    {
+        case GB200_BOOL   : ok = launch_bool   (family, z_code, add, mult, args, cfg) ; break ;
+        case GB200_INT8   : ok = launch_int8   (family, z_code, add, mult, args, cfg) ; break ;
+        case GB200_UINT8  : ok = launch_uint8  (family, z_code, add, mult, args, cfg) ; break ;
+        case GB200_INT16  : ok = launch_int16  (family, z_code, add, mult, args, cfg) ; break ;
+        case GB200_UINT16 : ok = launch_uint16 (family, z_code, add, mult, args, cfg) ; break ;
+        case GB200_INT32  : ok = launch_int32  (family, z_code, add, mult, args, cfg) ; break ;
+        case GB200_UINT32 : ok = launch_uint32 (family, z_code, add, mult, args, cfg) ; break ;
+        case GB200_INT64  : ok = launch_int64  (family, z_code, add, mult, args, cfg) ; break ;
+        case GB200_UINT64 : ok = launch_uint64 (family, z_code, add, mult, args, cfg) ; break ;
+        case GB200_FP32   : ok = launch_fp32   (family, z_code, add, mult, args, cfg) ; break ;
+        case GB200_FP64   : ok = launch_fp64   (family, z_code, add, mult, args, cfg) ; break ;
+        default : break ;
+    }
+    if (ok) count_launch () ;
+    return ok ;
+}
+
+} // namespace gb200

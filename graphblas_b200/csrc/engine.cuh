@@ -1,0 +1,147 @@
+// engine.cuh -- host-side context, device buffers and error plumbing shared by engine_*.cu
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <atomic>
+#include <cuda_runtime.h>
+#include "../../include/gb_b200.h"
+#include "common.cuh"
+
+namespace gb200 {
+
+struct Status
+{
+    gb200_status code ;
+    Status (gb200_status c = GB200_SUCCESS) : code (c) { }
+    bool ok () const { return code == GB200_SUCCESS ; }
+} ;
+
+void set_error (const char *fmt, ...) ;
+
+#define GB200_CUDA(call)                                                                    \
+    do {                                                                                    \
+        cudaError_t e__ = (call) ;                                                          \
+        if (e__ != cudaSuccess)                                                             \
+        {                                                                                   \
+            gb200::set_error ("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                 \
+                cudaGetErrorString (e__)) ;                                                 \
+            return (e__ == cudaErrorMemoryAllocation) ? GB200_OUT_OF_MEMORY : GB200_CUDA_ERROR ; \
+        }                                                                                   \
+    } while (0)
+
+#define GB200_TRY(expr)                                                                     \
+    do { gb200_status s__ = (expr) ; if (s__ != GB200_SUCCESS) return s__ ; } while (0)
+
+struct Ctx
+{
+    bool ready = false ;
+    int device = 0 ;
+    int sm_count = 148 ;
+    cudaStream_t stream = nullptr ;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr ;
+    void *pinned = nullptr ;            // small pinned scratch for scalar read-backs
+    size_t pinned_bytes = 0 ;
+    std::recursive_mutex mu ;           // one multiply at a time (the seam may be entered by
+                                        // many user threads, reference Demo/Program/pthread_demo.c)
+    std::atomic<int64_t> launches {0} ;
+    std::atomic<int64_t> multiplies {0} ;
+} ;
+
+Ctx &ctx () ;
+gb200_status ensure_init () ;
+
+inline void count_launch (int n = 1) { ctx ().launches += n ; }
+
+// stream-ordered device buffer
+struct DevBuf
+{
+    void *ptr = nullptr ;
+    size_t bytes = 0 ;
+    DevBuf () { }
+    DevBuf (const DevBuf &) = delete ;
+    DevBuf &operator= (const DevBuf &) = delete ;
+    DevBuf (DevBuf &&o) noexcept : ptr (o.ptr), bytes (o.bytes) { o.ptr = nullptr ; o.bytes = 0 ; }
+    DevBuf &operator= (DevBuf &&o) noexcept
+    {
+        if (this != &o) { release () ; ptr = o.ptr ; bytes = o.bytes ; o.ptr = nullptr ; o.bytes = 0 ; }
+        return *this ;
+    }
+    ~DevBuf () { release () ; }
+    gb200_status alloc (size_t nbytes)
+    {
+        release () ;
+        if (nbytes == 0) nbytes = 16 ;
+        cudaError_t e = cudaMallocAsync (&ptr, nbytes, ctx ().stream) ;
+        if (e != cudaSuccess)
+        {
+            ptr = nullptr ;
+            cudaGetLastError () ;
+            set_error ("device allocation of %zu bytes failed: %s", nbytes, cudaGetErrorString (e)) ;
+            return (e == cudaErrorMemoryAllocation) ? GB200_OUT_OF_MEMORY : GB200_CUDA_ERROR ;
+        }
+        bytes = nbytes ;
+        return GB200_SUCCESS ;
+    }
+    void release ()
+    {
+        if (ptr) { cudaFreeAsync (ptr, ctx ().stream) ; ptr = nullptr ; bytes = 0 ; }
+    }
+    template <class T> T *as () const { return (T *) ptr ; }
+} ;
+
+} // namespace gb200
+
+// ---- opaque handle bodies -----------------------------------------------------------------------
+struct gb200_dmatrix_s
+{
+    gb200::DMat v ;                 // device view
+    gb200::DevBuf p, h, i, x ;
+    int is_hyper_flag ;             // raw A->is_hyper (h != NULL), as used by GB_AxB_alloc.c:49-50
+} ;
+
+struct gb200_result_s
+{
+    gb200_result_info info ;
+    gb200::DevBuf p, h, i, x ;      // p int64 [nvec+1], h int64 [nvec], i int32 [nnz], x Z [nnz]
+} ;
+
+namespace gb200 {
+
+// engine_util.cu
+gb200_status scan_i64 (const int64_t *in, int64_t *out, int64_t n) ;     // out has n+1 entries
+gb200_status scan_u8  (const uint8_t *in, int64_t *out, int64_t n) ;
+gb200_status read_i64 (const int64_t *dptr, int64_t *host) ;             // syncs the stream
+gb200_status fill_bits (void *dst, int elem_size, uint64_t bits, int64_t n) ;
+uint64_t identity_bits (int z_code, int add_opcode, int *acc_size) ;
+gb200_status filter_mask (const gb200_dmatrix_s *M, DMat &Mview, DevBuf &Mp2, DevBuf &Mi2) ;
+
+// the semiring-templated launchers (inst_*.cu)
+struct LaunchCfg ;
+bool launch_typed (int xy_code, int family, int z_code, int add, int mult, const void *args,
+    int grid, int block) ;
+
+// engine_saxpy.cu / engine_dot.cu
+gb200_status run_saxpy (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp,
+    const gb200_dmatrix_s *A, const gb200_dmatrix_s *B, const gb200_semiring &s) ;
+gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp,
+    const gb200_dmatrix_s *A, const gb200_dmatrix_s *B, const gb200_semiring &s) ;
+gb200_status flopcount (const DMat *M, const DMat &A, const DMat &B, DevBuf &flops, DevBuf &cum,
+    int64_t *total) ;
+
+gb200_status launch_mask_pos (const DMat &B, const DMat &M, int64_t *lpos) ;
+
+// Turn per-source-vector results into the final T.  `cum` (nsrc+1) is the cumulative entry count
+// over the source vectors (B's, or M's, stored vectors), names their vector names (nullptr:
+// identity).  Takes ownership of Ci/Cx.
+gb200_status assemble (gb200_result_s *R, int64_t nsrc, const int64_t *names, bool src_hyper,
+    DevBuf &cum, DevBuf &Ci, DevBuf &Cx, int64_t cnz, bool C_is_hyper, int64_t cvlen,
+    int64_t cvdim) ;
+
+// acc (acc_size bytes per slot) -> Z values, optionally gathering flagged slots
+gb200_status convert_acc (const void *acc, int acc_size, void *z, int z_code, int64_t n) ;
+
+} // namespace gb200

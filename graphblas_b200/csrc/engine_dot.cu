@@ -1,0 +1,380 @@
+// engine_dot.cu -- C<M>=A'*B, C<!M>=A'*B and C=A'*B by dot products: the GPU replacement of
+// GB_AxB_dot (reference Source/GB_AxB_dot.c:39-317 and Source/Template/GB_AxB_dot_{mask,compmask,
+// nomask,cij}.c), plus the entry points gb200_AxB_device / gb200_AxB_host.
+//
+// Every candidate C(i,j) is a *pair*; a group of lanes computes the pair (dot_kernel, kernels.cuh),
+// leaving a value and a "some index matched" flag per pair; a scan of the flags then packs the
+// results.  Pairs are enumerated in (j, i) order, so packed indices are ascending in every vector.
+#include "engine.cuh"
+#include "scan.cuh"
+#include "kernels.cuh"
+
+namespace gb200 {
+
+
+static inline int grid_cap (int64_t n, int per_sm)
+{
+    int64_t cap = (int64_t) ctx ().sm_count * per_sm ;
+    if (n > cap) n = cap ;
+    if (n < 1) n = 1 ;
+    return (int) n ;
+}
+
+// stored-vector position of every entry of M (upper bound search in M.p)
+__global__ void expand_vec_kernel (const int64_t *__restrict__ p, int64_t nvec, int64_t nnz,
+    int32_t *__restrict__ mvec)
+{
+    for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; e < nnz ;
+        e += (int64_t) gridDim.x * blockDim.x)
+    {
+        int64_t lo = 0, hi = nvec ;             // find the last v with p[v] <= e
+        while (hi - lo > 1)
+        {
+            const int64_t mid = (lo + hi) >> 1 ;
+            if (__ldg (p + mid) <= e) lo = mid ; else hi = mid ;
+        }
+        mvec [e] = (int32_t) lo ;
+    }
+}
+
+// pack the flagged pairs.  rows: li[e] (mask mode) or the name of A's (e % anvec)-th vector.
+__global__ void dot_gather_kernel (const uint8_t *__restrict__ flags, const int64_t *__restrict__ pos,
+    int64_t npairs, const int32_t *__restrict__ li, DMat A, const void *__restrict__ acc, int acc_size,
+    int zsize, int is_bool, int32_t *__restrict__ Ci, void *__restrict__ Cx)
+{
+    for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; e < npairs ;
+        e += (int64_t) gridDim.x * blockDim.x)
+    {
+        if (!flags [e]) continue ;
+        const int64_t q = pos [e] ;
+        Ci [q] = li ? li [e] : (int32_t) dm_vecname (A, e % A.nvec) ;
+        if (acc_size == 8) ((uint64_t *) Cx) [q] = ((const uint64_t *) acc) [e] ;
+        else
+        {
+            const uint32_t a = ((const uint32_t *) acc) [e] ;
+            if (is_bool) ((uint8_t *) Cx) [q] = (a != 0) ? 1 : 0 ;
+            else if (zsize == 1) ((uint8_t *) Cx) [q] = (uint8_t) a ;
+            else if (zsize == 2) ((uint16_t *) Cx) [q] = (uint16_t) a ;
+            else ((uint32_t *) Cx) [q] = a ;
+        }
+    }
+}
+
+// cum[v] = pos[p[v]] for list-shaped pair spaces; cnt[jb] for rectangular ones
+__global__ void dot_cum_list_kernel (const int64_t *__restrict__ p, const int64_t *__restrict__ pos,
+    int64_t nvec, int64_t *__restrict__ cum)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t <= nvec ;
+        t += (int64_t) gridDim.x * blockDim.x) cum [t] = pos [p [t]] ;
+}
+
+__global__ void dot_cnt_rect_kernel (const int64_t *__restrict__ pos, int64_t anvec, int64_t nb,
+    int64_t *__restrict__ cnt)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nb ;
+        t += (int64_t) gridDim.x * blockDim.x) cnt [t] = pos [(t + 1) * anvec] - pos [t * anvec] ;
+}
+
+static int pick_group (double len)
+{
+    int G = 1 ;
+    while (G < 32 && G * 2 <= len) G <<= 1 ;
+    return G ;
+}
+
+gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp,
+    const gb200_dmatrix_s *Ad, const gb200_dmatrix_s *Bd, const gb200_semiring &s)
+{
+    Ctx &c = ctx () ;
+    const DMat &A = Ad->v ;
+    const DMat &B = Bd->v ;
+    const int64_t cvlen = A.vdim, cvdim = B.vdim ;
+    R->info.method_used = GB200_METHOD_DOT ;
+    R->info.type_code = s.z_code ;
+    R->info.mask_applied = (M != nullptr) ? 1 : 0 ;         // GB_AxB_dot.c:315
+    // GB_AxB_dot.c passes (Mask_comp ? NULL : M) to GB_AxB_alloc
+    const bool C_is_hyper = (cvdim > 1) &&
+        (Ad->is_hyper_flag || Bd->is_hyper_flag || (M != nullptr && !mask_comp && M->is_hyper_flag)) ;
+
+    int acc_size = 0 ;
+    (void) identity_bits (s.z_code, s.add_opcode, &acc_size) ;
+    const int zsize = type_size (s.z_code) ;
+    const int is_bool = (s.z_code == GB200_BOOL) ;
+
+    DMat Mv = DMat () ; DevBuf Mp2, Mi2 ;
+    if (M != nullptr) GB200_TRY (filter_mask (M, Mv, Mp2, Mi2)) ;
+
+    DevBuf nmatch ;
+    GB200_TRY (nmatch.alloc (8)) ;
+    GB200_CUDA (cudaMemsetAsync (nmatch.ptr, 0, 8, c.stream)) ;
+
+    DotArgs da ;
+    memset (&da, 0, sizeof (da)) ;
+    da.A = A ; da.B = B ; da.M = Mv ;
+    da.mult_op = s.mult_opcode ; da.flip = s.flipxy ;
+    da.nmatch = nmatch.as<unsigned long long> () ;
+
+    const double avgA = (A.nvec > 0) ? (double) A.nnz / (double) A.nvec : 0 ;
+    const double avgB = (B.nvec > 0) ? (double) B.nnz / (double) B.nvec : 0 ;
+
+    DevBuf Ci, Cx, ccum ;
+    int64_t cnz = 0 ;
+    gb200_status st ;
+
+    if (M != nullptr && !mask_comp)
+    {
+        // ---- C<M> = A'*B : pairs are the (true) entries of M ----------------------------------
+        const int64_t mnz = Mv.nnz ;
+        DevBuf mvec, vals, flags, pos ;
+        GB200_TRY (mvec.alloc ((mnz > 0 ? mnz : 1) * sizeof (int32_t))) ;
+        GB200_TRY (vals.alloc ((size_t) (mnz > 0 ? mnz : 1) * acc_size)) ;
+        GB200_TRY (flags.alloc (mnz > 0 ? mnz : 1)) ;
+        GB200_TRY (pos.alloc ((mnz + 1) * sizeof (int64_t))) ;
+        if (mnz > 0)
+        {
+            expand_vec_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (Mv.p, Mv.nvec,
+                mnz, mvec.as<int32_t> ()) ;
+            count_launch () ;
+            da.mode = DOT_MASK ; da.mvec = mvec.as<int32_t> () ; da.npairs = mnz ;
+            da.vals = vals.ptr ; da.flags = flags.as<uint8_t> () ;
+            da.G = pick_group ((avgA < avgB) ? avgA : avgB) ;
+            const int64_t gpb = 256 / da.G ;
+            if (!launch_typed (s.xy_code, FAM_DOT, s.z_code, s.add_opcode, s.mult_opcode, &da,
+                grid_cap ((mnz + gpb - 1) / gpb, 16), 256))
+            { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+        }
+        GB200_TRY (scan_u8 (flags.as<uint8_t> (), pos.as<int64_t> (), mnz)) ;
+        GB200_TRY (read_i64 (pos.as<int64_t> () + mnz, &cnz)) ;
+        GB200_TRY (ccum.alloc ((Mv.nvec + 1) * sizeof (int64_t))) ;
+        dot_cum_list_kernel <<<grid_cap ((Mv.nvec + 256) / 256, 8), 256, 0, c.stream>>> (Mv.p,
+            pos.as<int64_t> (), Mv.nvec, ccum.as<int64_t> ()) ;
+        count_launch () ;
+        GB200_TRY (Ci.alloc ((cnz > 0 ? cnz : 1) * sizeof (int32_t))) ;
+        GB200_TRY (Cx.alloc ((size_t) (cnz > 0 ? cnz : 1) * zsize)) ;
+        if (cnz > 0)
+        {
+            dot_gather_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (
+                flags.as<uint8_t> (), pos.as<int64_t> (), mnz, Mv.i, A, vals.ptr, acc_size, zsize,
+                is_bool, Ci.as<int32_t> (), Cx.ptr) ;
+            count_launch () ;
+        }
+        GB200_CUDA (cudaGetLastError ()) ;
+        st = assemble (R, Mv.nvec, Mv.hyper ? Mv.h : nullptr, Mv.hyper != 0, ccum, Ci, Cx, cnz,
+            C_is_hyper, cvlen, cvdim) ;
+    }
+    else
+    {
+        // ---- C<!M> = A'*B or C = A'*B : pairs are (vector of A) x (vector of B), by slabs of B ---
+        const int64_t anvec = A.nvec, bnvec = B.nvec ;
+        DevBuf mposB, cnt ;
+        const bool comp = (M != nullptr) ;
+        if (comp)
+        {
+            GB200_TRY (mposB.alloc ((bnvec > 0 ? bnvec : 1) * sizeof (int64_t))) ;
+            if (bnvec > 0)
+            {
+                GB200_TRY (launch_mask_pos (B, Mv, mposB.as<int64_t> ())) ;
+            }
+        }
+        GB200_TRY (cnt.alloc ((bnvec > 0 ? bnvec : 1) * sizeof (int64_t))) ;
+        GB200_CUDA (cudaMemsetAsync (cnt.ptr, 0, cnt.bytes, c.stream)) ;
+        const int64_t max_pairs = 1LL << 27 ;
+        int64_t nb = (anvec > 0) ? (max_pairs / anvec) : bnvec ;
+        if (nb < 1) nb = 1 ;
+        if (nb > bnvec) nb = bnvec ;
+        std::vector<DevBuf> chunk_i, chunk_x ;
+        std::vector<int64_t> chunk_nz ;
+        da.mode = comp ? DOT_COMP : DOT_NONE ;
+        da.mposB = mposB.as<int64_t> () ;
+        // the list that is walked is A(:,i) when B(:,j) is dense, else the shorter of the two
+        const bool Bdense = (B.nvec > 0 && B.nnz == B.nvec * B.vlen) ;
+        da.G = pick_group (Bdense ? avgA : ((avgA < avgB) ? avgA : avgB)) ;
+        for (int64_t jb0 = 0 ; jb0 < bnvec && anvec > 0 ; jb0 += nb)
+        {
+            const int64_t jb1 = (jb0 + nb < bnvec) ? (jb0 + nb) : bnvec ;
+            const int64_t npairs = anvec * (jb1 - jb0) ;
+            DevBuf vals, flags, pos, ci, cx ;
+            GB200_TRY (vals.alloc ((size_t) npairs * acc_size)) ;
+            GB200_TRY (flags.alloc (npairs)) ;
+            GB200_TRY (pos.alloc ((npairs + 1) * sizeof (int64_t))) ;
+            da.jb0 = jb0 ; da.jb1 = jb1 ; da.npairs = npairs ;
+            da.vals = vals.ptr ; da.flags = flags.as<uint8_t> () ;
+            const int64_t gpb = 256 / da.G ;
+            if (!launch_typed (s.xy_code, FAM_DOT, s.z_code, s.add_opcode, s.mult_opcode, &da,
+                grid_cap ((npairs + gpb - 1) / gpb, 16), 256))
+            { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+            GB200_TRY (scan_u8 (flags.as<uint8_t> (), pos.as<int64_t> (), npairs)) ;
+            int64_t nz = 0 ;
+            GB200_TRY (read_i64 (pos.as<int64_t> () + npairs, &nz)) ;
+            dot_cnt_rect_kernel <<<grid_cap ((jb1 - jb0 + 255) / 256, 8), 256, 0, c.stream>>> (
+                pos.as<int64_t> (), anvec, jb1 - jb0, cnt.as<int64_t> () + jb0) ;
+            count_launch () ;
+            GB200_TRY (ci.alloc ((nz > 0 ? nz : 1) * sizeof (int32_t))) ;
+            GB200_TRY (cx.alloc ((size_t) (nz > 0 ? nz : 1) * zsize)) ;
+            if (nz > 0)
+            {
+                dot_gather_kernel <<<grid_cap ((npairs + 255) / 256, 16), 256, 0, c.stream>>> (
+                    flags.as<uint8_t> (), pos.as<int64_t> (), npairs, nullptr, A, vals.ptr, acc_size,
+                    zsize, is_bool, ci.as<int32_t> (), cx.ptr) ;
+                count_launch () ;
+            }
+            GB200_CUDA (cudaGetLastError ()) ;
+            chunk_i.push_back (std::move (ci)) ;
+            chunk_x.push_back (std::move (cx)) ;
+            chunk_nz.push_back (nz) ;
+            cnz += nz ;
+        }
+        GB200_TRY (ccum.alloc ((bnvec + 1) * sizeof (int64_t))) ;
+        GB200_TRY (scan_i64 (cnt.as<int64_t> (), ccum.as<int64_t> (), bnvec)) ;
+        if (chunk_i.size () == 1)
+        {
+            Ci = std::move (chunk_i [0]) ; Cx = std::move (chunk_x [0]) ;
+        }
+        else
+        {
+            GB200_TRY (Ci.alloc ((cnz > 0 ? cnz : 1) * sizeof (int32_t))) ;
+            GB200_TRY (Cx.alloc ((size_t) (cnz > 0 ? cnz : 1) * zsize)) ;
+            int64_t off = 0 ;
+            for (size_t q = 0 ; q < chunk_i.size () ; q++)
+            {
+                if (chunk_nz [q] > 0)
+                {
+                    GB200_CUDA (cudaMemcpyAsync (Ci.as<int32_t> () + off, chunk_i [q].ptr,
+                        chunk_nz [q] * sizeof (int32_t), cudaMemcpyDeviceToDevice, c.stream)) ;
+                    GB200_CUDA (cudaMemcpyAsync ((char *) Cx.ptr + off * zsize, chunk_x [q].ptr,
+                        (size_t) chunk_nz [q] * zsize, cudaMemcpyDeviceToDevice, c.stream)) ;
+                }
+                off += chunk_nz [q] ;
+            }
+        }
+        st = assemble (R, bnvec, B.hyper ? B.h : nullptr, B.hyper != 0, ccum, Ci, Cx, cnz,
+            C_is_hyper, cvlen, cvdim) ;
+    }
+    if (st != GB200_SUCCESS) return st ;
+    int64_t nm = 0 ;
+    GB200_TRY (read_i64 (nmatch.as<int64_t> (), &nm)) ;
+    R->info.flops = nm ;
+    return GB200_SUCCESS ;
+}
+
+} // namespace gb200
+
+// =============================================================================================
+// C ABI (part 2): the multiply
+// =============================================================================================
+using namespace gb200 ;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+gb200_status gb200_AxB_device (gb200_result *out, gb200_dmatrix M, int mask_comp, gb200_dmatrix A,
+    gb200_dmatrix B, const gb200_semiring *semiring, int do_adotb, int method)
+{
+    (void) method ;     // saxpy-vs-dot was decided by the caller (GB_AxB_meta.c:266-366); HEAP and
+                        // GUSTAVSON requests run the same GPU saxpy
+    if (out == NULL || A == NULL || B == NULL || semiring == NULL) return GB200_INVALID ;
+    *out = NULL ;
+    GB200_TRY (ensure_init ()) ;
+    gb200_semiring s = *semiring ;
+    GB200_TRY (gb200_semiring_canonical (&s)) ;
+    if (A->v.type_code != s.xy_code || B->v.type_code != s.xy_code)
+    {
+        // the typecasting generic path (GB_AxB_Gustavson.c:274-415) is not built
+        set_error ("operand types (%d,%d) differ from the multiply operator's type %d (typecast path "
+            "not built)", A->v.type_code, B->v.type_code, s.xy_code) ;
+        return GB200_NOT_SUPPORTED ;
+    }
+    const int64_t cvlen = do_adotb ? A->v.vdim : A->v.vlen ;
+    const int64_t cvdim = B->v.vdim ;
+    if ((do_adotb && A->v.vlen != B->v.vlen) || (!do_adotb && A->v.vdim != B->v.vlen)
+        || (M != NULL && (M->v.vlen != cvlen || M->v.vdim != cvdim)))
+    {
+        set_error ("gb200_AxB_device: dimension mismatch") ;
+        return GB200_INVALID ;
+    }
+    Ctx &c = ctx () ;
+    std::lock_guard<std::recursive_mutex> lock (c.mu) ;
+    gb200_result_s *R = new (std::nothrow) gb200_result_s () ;
+    if (R == NULL) return GB200_OUT_OF_MEMORY ;
+    memset (&R->info, 0, sizeof (R->info)) ;
+    cudaEventRecord (c.ev0, c.stream) ;
+    gb200_status st = do_adotb ? run_dot (R, M, mask_comp, A, B, s)
+                               : run_saxpy (R, M, mask_comp, A, B, s) ;
+    if (st == GB200_SUCCESS)
+    {
+        cudaEventRecord (c.ev1, c.stream) ;
+        cudaError_t e = cudaStreamSynchronize (c.stream) ;
+        if (e != cudaSuccess)
+        {
+            set_error ("multiply failed on the device: %s", cudaGetErrorString (e)) ;
+            st = GB200_CUDA_ERROR ;
+        }
+        else
+        {
+            float ms = 0 ;
+            cudaEventElapsedTime (&ms, c.ev0, c.ev1) ;
+            R->info.device_ms = ms ;
+        }
+    }
+    if (st != GB200_SUCCESS)
+    {
+        cudaStreamSynchronize (c.stream) ;
+        cudaGetLastError () ;
+        delete R ;
+        return st ;
+    }
+    c.multiplies++ ;
+    *out = R ;
+    return GB200_SUCCESS ;
+}
+
+gb200_status gb200_AxB_host (gb200_result *out, const gb200_matrix *M, int mask_comp,
+    const gb200_matrix *A, const gb200_matrix *B, const gb200_semiring *semiring, int do_adotb,
+    int method)
+{
+    if (out == NULL || A == NULL || B == NULL || semiring == NULL) return GB200_INVALID ;
+    *out = NULL ;
+    // decline before any transfer if the semiring is outside the built-in space
+    gb200_semiring s = *semiring ;
+    GB200_TRY (gb200_semiring_canonical (&s)) ;
+    if (A->type_code != s.xy_code || B->type_code != s.xy_code)
+    {
+        set_error ("operand types differ from the multiply operator's type (typecast path not built)") ;
+        return GB200_NOT_SUPPORTED ;
+    }
+    gb200_dmatrix dM = NULL, dA = NULL, dB = NULL ;
+    gb200_status st = GB200_SUCCESS ;
+    // A and B may be the same host object (C=A*A): upload once
+    if (M != NULL) st = gb200_upload (&dM, M) ;
+    if (st == GB200_SUCCESS) st = gb200_upload (&dA, A) ;
+    const bool same = (A == B) || (A->p == B->p && A->i == B->i && A->x == B->x && A->h == B->h
+        && A->vlen == B->vlen && A->vdim == B->vdim && A->nvec == B->nvec) ;
+    if (st == GB200_SUCCESS) { if (same) dB = dA ; else st = gb200_upload (&dB, B) ; }
+    if (st == GB200_SUCCESS) st = gb200_AxB_device (out, dM, mask_comp, dA, dB, semiring, do_adotb, method) ;
+    if (!same) gb200_dmatrix_free (&dB) ;
+    gb200_dmatrix_free (&dA) ;
+    gb200_dmatrix_free (&dM) ;
+    return st ;
+}
+
+gb200_status gb200_flopcount_device (gb200_dmatrix M, gb200_dmatrix A, gb200_dmatrix B,
+    int64_t *Bflops_out, int64_t *total)
+{
+    if (A == NULL || B == NULL || total == NULL) return GB200_INVALID ;
+    GB200_TRY (ensure_init ()) ;
+    if (A->v.vdim != B->v.vlen) { set_error ("flopcount: dimension mismatch") ; return GB200_INVALID ; }
+    Ctx &c = ctx () ;
+    std::lock_guard<std::recursive_mutex> lock (c.mu) ;
+    DevBuf flops, cum ;
+    GB200_TRY (flopcount (M ? &M->v : nullptr, A->v, B->v, flops, cum, total)) ;
+    if (Bflops_out != NULL)
+    {
+        GB200_CUDA (cudaMemcpyAsync (Bflops_out, cum.ptr, (B->v.nvec + 1) * sizeof (int64_t),
+            cudaMemcpyDeviceToHost, c.stream)) ;
+        GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
+    }
+    return GB200_SUCCESS ;
+}
+
+#pragma GCC visibility pop
+} // extern "C"

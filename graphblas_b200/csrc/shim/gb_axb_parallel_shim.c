@@ -1,0 +1,239 @@
+/* gb_axb_parallel_shim.c -- the reference-side binding of libgb_b200.so.
+ *
+ * This file is what a maintainer of SuiteSparse:GraphBLAS v2.3.3 would add to route the masked
+ * semiring multiply to the B200: it defines GB_AxB_parallel with the exact signature of the
+ * reference (Source/GB.h:1522-1537; the original body is Source/GB_AxB_parallel.c:63-154).  In the
+ * reference's shared library every internal call goes through the PLT, so a library that exports
+ * this symbol and is placed ahead of it in symbol-lookup order (LD_PRELOAD, link order, or
+ * dlopen(RTLD_GLOBAL) before the reference) takes over the path under an UNMODIFIED GrB_mxm /
+ * GrB_mxv / GrB_vxm caller and an UNMODIFIED reference library.
+ *
+ * It is compiled against the reference's internal header "GB.h" (it must see struct
+ * GB_Matrix_opaque to read M, A, B and to build T); no reference source is copied here.  T is
+ * created with the reference's own GB_create so that its arrays come from the allocator the
+ * reference will later free or transplant them with (Source/GB_mxm.c:141-159).
+ *
+ * The compute happens in libgb_b200.so (include/gb_b200.h).  Nothing here computes on the CPU.
+ * Semirings outside the 960 built-in workers (user-defined operators are host function
+ * pointers) are DECLINED: by default the call fails loudly with GrB_PANIC; with
+ * GB200_SHIM_FORWARD=1 it is delegated to the host library's own GB_AxB_parallel (found with
+ * dlsym(RTLD_NEXT)) and counted in gb200_shim_stats so that tests can assert it never happened.
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include "GB.h"
+#include "gb_b200.h"
+
+typedef GrB_Info (*axb_parallel_fn) (GrB_Matrix *, GrB_Matrix, const bool, const GrB_Matrix,
+    const GrB_Matrix, const GrB_Semiring, const bool, const bool, const GrB_Desc_Value,
+    GrB_Desc_Value *, bool *, GB_Context) ;
+
+static int64_t g_gpu_calls = 0, g_forwarded = 0, g_declined = 0 ;
+static int g_enabled = -1 ;         /* -1: read GB200_SHIM_DISABLE on first use */
+static double g_last_device_ms = 0 ;
+static int64_t g_last_flops = 0 ;
+
+__attribute__ ((visibility ("default")))
+void gb200_shim_enable (int on) { g_enabled = on ? 1 : 0 ; }
+
+__attribute__ ((visibility ("default")))
+void gb200_shim_stats (int64_t *gpu_calls, int64_t *forwarded, int64_t *declined)
+{
+    if (gpu_calls) *gpu_calls = g_gpu_calls ;
+    if (forwarded) *forwarded = g_forwarded ;
+    if (declined) *declined = g_declined ;
+}
+
+__attribute__ ((visibility ("default")))
+void gb200_shim_last (double *device_ms, int64_t *flops)
+{
+    if (device_ms) *device_ms = g_last_device_ms ;
+    if (flops) *flops = g_last_flops ;
+}
+
+/* The host library's object-model entry points are looked up at run time (not linked) so that the
+ * shim can be loaded before the host library, which is what gives it precedence. */
+typedef GrB_Info (*gb_create_fn) (GrB_Matrix *, const GrB_Type, const int64_t, const int64_t,
+    const GB_Ap_code, const bool, const int, const double, const int64_t, const int64_t, const bool,
+    GB_Context) ;                                           /* Source/GB.h:1021-1035 */
+typedef GrB_Info (*gb_free_fn) (GrB_Matrix *) ;             /* Source/GB.h:1125 */
+static gb_create_fn host_create = NULL ;
+static gb_free_fn host_free = NULL ;
+
+static int bind_host (void)
+{
+    if (host_create == NULL) host_create = (gb_create_fn) dlsym (RTLD_DEFAULT, "GB_create") ;
+    if (host_free == NULL) host_free = (gb_free_fn) dlsym (RTLD_DEFAULT, "GB_free") ;
+    return (host_create != NULL && host_free != NULL) ;
+}
+
+static axb_parallel_fn host_original (void)
+{
+    static axb_parallel_fn fn = NULL ;
+    if (fn != NULL) return fn ;
+    /* LD_PRELOAD / link-order interposition: the host library is next in the search order */
+    fn = (axb_parallel_fn) dlsym (RTLD_NEXT, "GB_AxB_parallel") ;
+    if (fn == NULL)
+    {
+        /* dlopen(RTLD_GLOBAL) interposition: find the library that owns GB_AxB_meta (the only
+         * caller of this function) and ask it for its own definition */
+        void *meta = dlsym (RTLD_DEFAULT, "GB_AxB_meta") ;
+        Dl_info di ;
+        if (meta != NULL && dladdr (meta, &di) != 0 && di.dli_fname != NULL)
+        {
+            void *h = dlopen (di.dli_fname, RTLD_LAZY | RTLD_NOLOAD) ;
+            if (h != NULL) fn = (axb_parallel_fn) dlsym (h, "GB_AxB_parallel") ;
+        }
+    }
+    if (fn == (axb_parallel_fn) GB_AxB_parallel) fn = NULL ;
+    return fn ;
+}
+
+/* view a reference matrix through the C ABI; `zero` is a 1-entry fallback for a missing p */
+static int as_abi (gb200_matrix *out, const GrB_Matrix A, int64_t **tmp_p)
+{
+    *tmp_p = NULL ;
+    out->vlen = A->vlen ;
+    out->vdim = A->vdim ;
+    out->nvec = A->nvec ;
+    out->h = A->is_hyper ? A->h : NULL ;
+    out->i = A->i ;
+    out->x = A->x ;
+    out->type_code = A->type->code ;
+    out->reserved = 0 ;
+    if (A->p == NULL || A->nzmax == 0)
+    {
+        /* GB_NNZ (A) == 0; A->p might not be allocated (Source/GB.h:274-278) */
+        *tmp_p = calloc ((size_t) A->nvec + 1, sizeof (int64_t)) ;
+        if (*tmp_p == NULL) return (0) ;
+        out->p = *tmp_p ;
+        out->i = NULL ; out->x = NULL ;
+    }
+    else out->p = A->p ;
+    if (A->is_hyper && A->h == NULL) { out->nvec = 0 ; }
+    return (1) ;
+}
+
+__attribute__ ((visibility ("default")))
+GrB_Info GB_AxB_parallel            /* same contract as reference Source/GB.h:1522-1537 */
+(
+    GrB_Matrix *Chandle,
+    GrB_Matrix M,
+    const bool Mask_comp,
+    const GrB_Matrix A,
+    const GrB_Matrix B,
+    const GrB_Semiring semiring,
+    const bool flipxy,
+    const bool do_adotb,
+    const GrB_Desc_Value AxB_method,
+    GrB_Desc_Value *AxB_method_used,
+    bool *mask_applied,
+    GB_Context Context
+)
+{
+    if (g_enabled < 0) g_enabled = (getenv ("GB200_SHIM_DISABLE") != NULL) ? 0 : 1 ;
+    if (!g_enabled)
+    {
+        /* switched off (used by the parity tests to run the reference in the same process) */
+        axb_parallel_fn fn = host_original () ;
+        if (fn == NULL) return (GrB_PANIC) ;
+        return (fn (Chandle, M, Mask_comp, A, B, semiring, flipxy, do_adotb, AxB_method,
+            AxB_method_used, mask_applied, Context)) ;
+    }
+
+    (*Chandle) = NULL ;
+    GrB_BinaryOp add = semiring->add->op ;
+    GrB_BinaryOp mult = semiring->multiply ;
+
+    /* the "is it a built-in worker" test of Source/GB_semiring_builtin.c:59-65 */
+    bool builtin = !((A->type != (flipxy ? mult->ytype : mult->xtype)) ||
+        (B->type != (flipxy ? mult->xtype : mult->ytype)) ||
+        (A->type != B->type) || (A->type->code >= GB_UCT_code) ||
+        (add->opcode >= GB_USER_C_opcode) || (mult->opcode >= GB_USER_C_opcode)) ;
+
+    gb200_semiring s ;
+    s.add_opcode = add->opcode ;
+    s.mult_opcode = mult->opcode ;
+    s.xy_code = mult->xtype->code ;
+    s.z_code = mult->ztype->code ;
+    s.flipxy = flipxy ? 1 : 0 ;
+
+    gb200_result r = NULL ;
+    gb200_status st = GB200_NOT_SUPPORTED ;
+    int64_t *tp_m = NULL, *tp_a = NULL, *tp_b = NULL ;
+    if (builtin)
+    {
+        gb200_matrix am, bm, mm ;
+        int ok = as_abi (&am, A, &tp_a) && as_abi (&bm, B, &tp_b) ;
+        if (ok && M != NULL) ok = as_abi (&mm, M, &tp_m) ;
+        if (!ok) st = GB200_OUT_OF_MEMORY ;
+        else st = gb200_AxB_host (&r, (M != NULL) ? &mm : NULL, Mask_comp ? 1 : 0, &am, &bm, &s,
+            do_adotb ? 1 : 0, (int) AxB_method) ;
+        free (tp_m) ; free (tp_a) ; free (tp_b) ;
+    }
+
+    if (st == GB200_NOT_SUPPORTED)
+    {
+        g_declined++ ;
+        if (getenv ("GB200_SHIM_FORWARD") != NULL)
+        {
+            axb_parallel_fn fn = host_original () ;
+            if (fn != NULL)
+            {
+                g_forwarded++ ;
+                return (fn (Chandle, M, Mask_comp, A, B, semiring, flipxy, do_adotb, AxB_method,
+                    AxB_method_used, mask_applied, Context)) ;
+            }
+        }
+        fprintf (stderr, "[gb_b200 shim] GB_AxB_parallel declined (%s); set GB200_SHIM_FORWARD=1 to "
+            "delegate such calls to the host library\n", builtin ? gb200_last_error () :
+            "semiring or operand types outside the built-in space") ;
+        return (GrB_PANIC) ;
+    }
+    if (st == GB200_OUT_OF_MEMORY) return (GrB_OUT_OF_MEMORY) ;
+    if (st != GB200_SUCCESS)
+    {
+        fprintf (stderr, "[gb_b200 shim] GPU multiply failed: %s\n", gb200_last_error ()) ;
+        return ((st == GB200_INVALID) ? GrB_INVALID_VALUE : GrB_PANIC) ;
+    }
+
+    /* build T with the reference's allocator (postconditions: SURVEY.md 8b) */
+    gb200_result_info f ;
+    gb200_result_get_info (r, &f) ;
+    if (!bind_host ())
+    {
+        fprintf (stderr, "[gb_b200 shim] host GraphBLAS library (GB_create/GB_free) not found\n") ;
+        gb200_result_free (&r) ;
+        return (GrB_PANIC) ;
+    }
+    GrB_Type ctype = add->ztype ;
+    int64_t plen = (f.nvec > 0) ? f.nvec : 1 ;
+    GrB_Info info = host_create (Chandle, ctype, f.vlen, f.vdim, GB_Ap_malloc, true,
+        GB_SAME_HYPER_AS (f.is_hyper), B->hyper_ratio, plen, (f.nnz > 0) ? f.nnz : 1, true, Context) ;
+    if (info != GrB_SUCCESS)
+    {
+        gb200_result_free (&r) ;
+        (*Chandle) = NULL ;
+        return (info) ;
+    }
+    GrB_Matrix C = (*Chandle) ;
+    st = gb200_result_fetch (r, C->p, f.is_hyper ? C->h : NULL, C->i, C->x) ;
+    gb200_result_free (&r) ;
+    if (st != GB200_SUCCESS)
+    {
+        host_free (Chandle) ;
+        (*Chandle) = NULL ;
+        return ((st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC) ;
+    }
+    if (f.is_hyper) C->nvec = f.nvec ;
+    C->nvec_nonempty = f.nvec_nonempty ;
+    C->magic = GB_MAGIC ;
+    (*AxB_method_used) = (GrB_Desc_Value) f.method_used ;
+    (*mask_applied) = (f.mask_applied != 0) ;
+    g_gpu_calls++ ;
+    g_last_device_ms = f.device_ms ;
+    g_last_flops = f.flops ;
+    return (GrB_SUCCESS) ;
+}

@@ -1,0 +1,193 @@
+/* gb_b200.h -- C ABI of libgb_b200.so: the B200 (sm_100a) implementation of the
+ * masked semiring sparse matrix multiply that sits behind GrB_mxm / GrB_mxv / GrB_vxm
+ * in SuiteSparse:GraphBLAS v2.3.3.
+ *
+ * The boundary is the reference's internal funnel
+ *
+ *     GrB_Info GB_AxB_parallel (GrB_Matrix *Chandle, GrB_Matrix M, bool Mask_comp,
+ *         GrB_Matrix A, GrB_Matrix B, GrB_Semiring semiring, bool flipxy, bool do_adotb,
+ *         GrB_Desc_Value AxB_method, GrB_Desc_Value *AxB_method_used, bool *mask_applied,
+ *         GB_Context Context)            -- reference Source/GB.h:1522-1537,
+ *                                           body Source/GB_AxB_parallel.c:63-154
+ *
+ * restated here with plain pointers and sizes (no GraphBLAS, CUDA or torch types), so it can
+ * be bound from C (the shim in graphblas_b200/csrc/shim/), ctypes, cgo...
+ * Matrices are "CSC-agnostic" exactly as at that seam: `vdim` sparse vectors of length
+ * `vlen`, standard (h == NULL, nvec == vdim) or hypersparse (h lists the nvec vectors that
+ * are present), 64-bit indices, indices ascending inside each vector, no duplicates
+ * (reference Source/Template/GB_matrix.h:193-208).
+ *
+ * Every function returns a gb200_status.  No function ever computes on the CPU: if no
+ * sm_100-class device is usable the call fails with GB200_NO_DEVICE.
+ */
+#ifndef GB_B200_H
+#define GB_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (mapped by the shim onto GrB_Info, Include/GraphBLAS.h:208-267) ------- */
+typedef enum
+{
+    GB200_SUCCESS        = 0,   /* -> GrB_SUCCESS                                            */
+    GB200_OUT_OF_MEMORY  = 1,   /* -> GrB_OUT_OF_MEMORY (device or host allocation failed)   */
+    GB200_NOT_SUPPORTED  = 2,   /* the "decline rule": semiring/type/size outside the        */
+                                /* built-in space this library implements; nothing was done  */
+    GB200_INVALID        = 3,   /* -> GrB_INVALID_VALUE: malformed arguments                 */
+    GB200_NO_DEVICE      = 4,   /* -> GrB_PANIC: no usable CUDA device                       */
+    GB200_CUDA_ERROR     = 5    /* -> GrB_PANIC: a CUDA call failed (see gb200_last_error)    */
+} gb200_status ;
+
+/* ---- type codes: identical numbering to GB_Type_code, reference Source/GB.h:450-466 ---- */
+typedef enum
+{
+    GB200_BOOL = 0, GB200_INT8 = 1, GB200_UINT8 = 2, GB200_INT16 = 3, GB200_UINT16 = 4,
+    GB200_INT32 = 5, GB200_UINT32 = 6, GB200_INT64 = 7, GB200_UINT64 = 8,
+    GB200_FP32 = 9, GB200_FP64 = 10
+} gb200_type_code ;
+
+/* ---- binary operator codes: identical numbering to GB_Opcode, Source/GB.h:479-550 ------- */
+typedef enum
+{
+    GB200_FIRST = 7, GB200_SECOND = 8, GB200_MIN = 9, GB200_MAX = 10, GB200_PLUS = 11,
+    GB200_MINUS = 12, GB200_TIMES = 13, GB200_DIV = 14,
+    GB200_ISEQ = 15, GB200_ISNE = 16, GB200_ISGT = 17, GB200_ISLT = 18, GB200_ISGE = 19,
+    GB200_ISLE = 20,
+    GB200_LOR = 21, GB200_LAND = 22, GB200_LXOR = 23,
+    GB200_EQ = 24, GB200_NE = 25, GB200_GT = 26, GB200_LT = 27, GB200_GE = 28, GB200_LE = 29
+} gb200_opcode ;
+
+/* ---- method codes: identical values to GrB_Desc_Value, Include/GraphBLAS.h:2803-2823 ---- */
+typedef enum
+{
+    GB200_METHOD_DEFAULT   = 0,
+    GB200_METHOD_GUSTAVSON = 1001,  /* saxpy; reported when the GPU hash/bitmap saxpy ran    */
+    GB200_METHOD_HEAP      = 1002,  /* accepted as a request, runs the same saxpy kernels    */
+    GB200_METHOD_DOT       = 1003
+} gb200_method ;
+
+/* ---- a borrowed, read-only, host-resident sparse matrix (or n-by-1 vector) -------------- */
+typedef struct
+{
+    int64_t vlen ;          /* length of each sparse vector                                  */
+    int64_t vdim ;          /* number of vectors the matrix may hold                         */
+    int64_t nvec ;          /* vectors present in p/h: == vdim if h == NULL                  */
+    const int64_t *p ;      /* size nvec+1, p[0] == 0, nnz = p[nvec]                         */
+    const int64_t *h ;      /* size nvec, ascending; NULL for the standard form              */
+    const int64_t *i ;      /* size nnz; may be NULL only if nnz == 0                        */
+    const void    *x ;      /* size nnz * sizeof(type); may be NULL only if nnz == 0         */
+    int32_t type_code ;     /* gb200_type_code of x                                          */
+    int32_t reserved ;
+} gb200_matrix ;
+
+/* ---- a semiring, canonicalised the way GB_semiring_builtin does it
+ *      (reference Source/GB_semiring_builtin.c:19-151) ------------------------------------ */
+typedef struct
+{
+    int32_t add_opcode ;    /* monoid: MIN MAX PLUS TIMES (non-bool z); LOR LAND LXOR EQ     */
+    int32_t mult_opcode ;   /* any gb200_opcode; z = mult (x,y)                              */
+    int32_t xy_code ;       /* gb200_type_code of both inputs of mult                        */
+    int32_t z_code ;        /* gb200_type_code of the result (== xy_code, or BOOL for EQ..LE) */
+    int32_t flipxy ;        /* nonzero: z = mult (b,a).  gb200_semiring_canonical folds it   */
+                            /* into the opcode where the reference does; only MINUS and DIV  */
+                            /* observe it at run time (reference Source/axb.m:25,27)          */
+} gb200_semiring ;
+
+/* Canonicalise (boolean renames, flipxy folding).  Returns GB200_NOT_SUPPORTED if the
+ * combination is not one of the 960 built-in workers (Source/GB_AxB_Gustavson_builtin.c:147-200). */
+gb200_status gb200_semiring_canonical (gb200_semiring *s) ;
+
+/* ---- library / device -------------------------------------------------------------------- */
+gb200_status gb200_init (int device) ;       /* device < 0: use env GB200_DEVICE or 0       */
+gb200_status gb200_finalize (void) ;         /* frees all device workspace and handles       */
+const char  *gb200_last_error (void) ;       /* thread-local text of the last failure        */
+const char  *gb200_version (void) ;
+int          gb200_device_count (void) ;
+
+/* ---- device-resident operands (the "resident in HBM" timing mode; also what the host
+ *      entry point below uses internally).  Handles are opaque. ----------------------------- */
+typedef struct gb200_dmatrix_s *gb200_dmatrix ;
+
+gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host) ;
+gb200_status gb200_dmatrix_free (gb200_dmatrix *d) ;
+
+/* the result T of one multiply, resident on the device until fetched or freed */
+typedef struct gb200_result_s *gb200_result ;
+
+typedef struct
+{
+    int64_t vlen, vdim ;    /* vlen = do_adotb ? A->vdim : A->vlen ;  vdim = B->vdim          */
+    int64_t nvec ;          /* entries of p minus one (== vdim if not hypersparse)            */
+    int64_t nvec_nonempty ; /* exact                                                          */
+    int64_t nnz ;
+    int32_t is_hyper ;      /* rule of reference Source/GB_AxB_alloc.c:49-50                   */
+    int32_t type_code ;     /* == semiring z_code                                             */
+    int32_t method_used ;   /* GB200_METHOD_GUSTAVSON or GB200_METHOD_DOT                     */
+    int32_t mask_applied ;  /* 1 iff M (including its complement flag) was honoured           */
+    int64_t flops ;         /* multiply-add pairs performed (reference GB_AxB_flopcount        */
+                            /* definition for saxpy; matched index pairs for dot)             */
+    double  device_ms ;     /* CUDA-event time of the compute, operands resident              */
+} gb200_result_info ;
+
+/* C<M> = A*B (do_adotb == 0: A->vdim == B->vlen) or C<M> = A'*B (do_adotb != 0:
+ * A->vlen == B->vlen, A is NOT materialised transposed), over `semiring`.
+ * M may be NULL.  mask_comp as at the seam.  method: a gb200_method request. */
+gb200_status gb200_AxB_device
+(
+    gb200_result *out,
+    gb200_dmatrix M, int mask_comp,
+    gb200_dmatrix A, gb200_dmatrix B,
+    const gb200_semiring *semiring,
+    int do_adotb, int method
+) ;
+
+gb200_status gb200_result_get_info (gb200_result r, gb200_result_info *info) ;
+
+/* Copy T into caller-owned host arrays (sized from gb200_result_info): p[nvec+1], h[nvec] (only if
+ * is_hyper, else pass NULL), i[nnz], x[nnz*sizeof(type)].  The shim passes arrays obtained from the
+ * reference's own allocator (GB_create), which is how ownership of T stays with the reference. */
+gb200_status gb200_result_fetch (gb200_result r, int64_t *p, int64_t *h, int64_t *i, void *x) ;
+gb200_status gb200_result_free (gb200_result *r) ;
+
+/* ---- the host entry point: what GB_AxB_parallel is replaced by ---------------------------
+ * Uploads M, A, B, runs gb200_AxB_device, and leaves the result on the device for
+ * gb200_result_fetch.  (Two calls so that the caller can allocate T with its own allocator
+ * between them.) */
+gb200_status gb200_AxB_host
+(
+    gb200_result *out,
+    const gb200_matrix *M, int mask_comp,
+    const gb200_matrix *A, const gb200_matrix *B,
+    const gb200_semiring *semiring,
+    int do_adotb, int method
+) ;
+
+/* ---- GB_AxB_flopcount on the device (reference Source/GB_AxB_flopcount.c:85-316) --------
+ * Bflops_out (host, size B->nvec+1, may be NULL) receives the cumulative sum; *total the last
+ * entry. */
+gb200_status gb200_flopcount_device
+(
+    gb200_dmatrix M, gb200_dmatrix A, gb200_dmatrix B,
+    int64_t *Bflops_out, int64_t *total
+) ;
+
+/* ---- multi-GPU: flop-balanced 1-D partition of B's vectors (the slicing GB_AxB_parallel.c:52
+ * and GB_AxB_flopcount.c:32-37 plan for).  Given the cumulative Bflops (size nvec+1) returns
+ * nparts+1 vector boundaries in `bounds`. */
+gb200_status gb200_partition_by_flops
+(
+    const int64_t *Bflops_cumulative, int64_t nvec, int nparts, int64_t *bounds
+) ;
+
+/* counters: how many kernels this library has launched / how many multiplies it has run */
+int64_t gb200_kernel_launches (void) ;
+int64_t gb200_multiplies (void) ;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,272 @@
+"""grbref.py -- TEST INFRASTRUCTURE: ctypes binding of the public GraphBLAS C API (GrB_* / GxB_*,
+reference Include/GraphBLAS.h) of the compiled reference library oracle/_ref/libgraphblas_ref.so.
+
+It plays two roles:
+  * the oracle: with the shim disabled, GrB_mxm / GrB_mxv / GrB_vxm run the reference's own CPU
+    path (GB_AxB_parallel -> Gustavson / heap / dot);
+  * the unmodified caller: with the shim enabled, the *same* calls reach the B200 through the
+    interposed GB_AxB_parallel (graphblas_b200/csrc/shim/gb_axb_parallel_shim.c).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` arm import it.
+Nothing here reads /root/reference at run time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libgraphblas_ref.so")
+DEMO_LIB = os.path.join(ROOT, "oracle", "_ref", "libgbdemo_ref.so")
+SHIM_LIB = os.path.join(ROOT, "graphblas_b200", "libgb_b200_shim.so")
+
+# enums, reference Include/GraphBLAS.h:2784-2823
+GrB_OUTP, GrB_MASK, GrB_INP0, GrB_INP1, GxB_AxB_METHOD = 0, 1, 2, 3, 1000
+GxB_DEFAULT, GrB_REPLACE, GrB_SCMP, GrB_TRAN = 0, 1, 2, 3
+GxB_AxB_GUSTAVSON, GxB_AxB_HEAP, GxB_AxB_DOT = 1001, 1002, 1003
+
+NP_OF = {"BOOL": np.bool_, "INT8": np.int8, "UINT8": np.uint8, "INT16": np.int16,
+         "UINT16": np.uint16, "INT32": np.int32, "UINT32": np.uint32, "INT64": np.int64,
+         "UINT64": np.uint64, "FP32": np.float32, "FP64": np.float64}
+
+_libc = C.CDLL(None)
+_libc.malloc.restype = C.c_void_p
+_libc.malloc.argtypes = [C.c_size_t]
+_libc.free.argtypes = [C.c_void_p]
+
+
+class GrBError(RuntimeError):
+    pass
+
+
+def available() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+class GraphBLAS:
+    """One process-wide instance: loads the shim (optional) ahead of the reference library."""
+    _inst = None
+
+    @classmethod
+    def get(cls, with_shim: bool) -> "GraphBLAS":
+        if cls._inst is None:
+            cls._inst = cls(with_shim)
+        if with_shim and cls._inst.shim is None:
+            raise GrBError("GraphBLAS was already loaded without the shim in this process")
+        return cls._inst
+
+    def __init__(self, with_shim: bool):
+        if not available():
+            raise GrBError(f"{REF_LIB} missing: run `make -C oracle -f Makefile.ref` where "
+                           "/root/reference exists")
+        self.shim = None
+        if with_shim:
+            if not os.path.exists(SHIM_LIB):
+                raise GrBError(f"{SHIM_LIB} missing: run `make -C graphblas_b200 shim`")
+            # order matters: the shim's GB_AxB_parallel must come first in the global scope
+            self.shim = C.CDLL(SHIM_LIB, mode=C.RTLD_GLOBAL)
+            self.shim.gb200_shim_enable(0)
+        self.lib = C.CDLL(REF_LIB, mode=C.RTLD_GLOBAL)
+        self.lib.GrB_error.restype = C.c_char_p
+        self.ok(self.lib.GrB_init(0), "GrB_init")        # GrB_NONBLOCKING
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def ok(self, info: int, where: str) -> None:
+        if info != 0:
+            raise GrBError(f"{where} -> GrB_Info {info}: {self.lib.GrB_error().decode()}")
+
+    def obj(self, name: str) -> C.c_void_p:
+        """A predefined object: GrB_FP64, GxB_PLUS_TIMES_FP64, GrB_PLUS_FP64, GxB_PLUS_INT64_MONOID."""
+        return C.c_void_p.in_dll(self.lib, name)
+
+    def use_gpu(self, on: bool) -> None:
+        if self.shim is None:
+            if on:
+                raise GrBError("shim not loaded")
+            return
+        self.shim.gb200_shim_enable(1 if on else 0)
+
+    def shim_stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.shim.gb200_shim_stats(C.byref(a), C.byref(b), C.byref(c))
+        return {"gpu_calls": a.value, "forwarded": b.value, "declined": c.value}
+
+    def shim_last(self):
+        ms, fl = C.c_double(), C.c_int64()
+        self.shim.gb200_shim_last(C.byref(ms), C.byref(fl))
+        return ms.value, fl.value
+
+    @staticmethod
+    def _malloc_copy(a: np.ndarray) -> C.c_void_p:
+        n = max(a.nbytes, 8)
+        p = _libc.malloc(n)
+        if a.nbytes:
+            C.memmove(p, a.ctypes.data, a.nbytes)
+        return C.c_void_p(p)
+
+    # ---- import / export (reference Include/GraphBLAS.h:5751-6064) -----------------------------
+    def matrix_import(self, fmt: str, type_: str, nrows: int, ncols: int, Ap, Ai, Ax, Ah=None):
+        """fmt in CSR, CSC, HyperCSR, HyperCSC.  Arrays are copied into malloc'd memory whose
+        ownership moves to GraphBLAS."""
+        Ap = np.ascontiguousarray(Ap, dtype=np.uint64)
+        Ai = np.ascontiguousarray(Ai, dtype=np.uint64)
+        Ax = np.ascontiguousarray(Ax, dtype=NP_OF[type_])
+        nvals = int(Ap[-1])
+        A = C.c_void_p()
+        pp, pi, px = self._malloc_copy(Ap), self._malloc_copy(Ai), self._malloc_copy(Ax)
+        t = self.obj("GrB_" + type_)
+        if fmt in ("CSR", "CSC"):
+            fn = getattr(self.lib, "GxB_Matrix_import_" + fmt)
+            info = fn(C.byref(A), t, C.c_uint64(nrows), C.c_uint64(ncols), C.c_uint64(nvals),
+                      C.c_int64(-1), C.byref(pp), C.byref(pi), C.byref(px), None)
+        else:
+            Ah = np.ascontiguousarray(Ah, dtype=np.uint64)
+            ph = self._malloc_copy(Ah)
+            fn = getattr(self.lib, "GxB_Matrix_import_" + fmt)
+            info = fn(C.byref(A), t, C.c_uint64(nrows), C.c_uint64(ncols), C.c_uint64(nvals),
+                      C.c_int64(-1), C.c_uint64(len(Ah)), C.byref(ph), C.byref(pp), C.byref(pi),
+                      C.byref(px), None)
+        self.ok(info, "GxB_Matrix_import_" + fmt)
+        return A
+
+    def matrix_export(self, A: C.c_void_p, fmt: str):
+        """Destructive export; returns dict(type, nrows, ncols, nvals, Ap, Ai, Ax[, Ah])."""
+        t = C.c_void_p()
+        nrows, ncols, nvals = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        nonempty = C.c_int64()
+        pp, pi, px, ph = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nvec = C.c_uint64()
+        fn = getattr(self.lib, "GxB_Matrix_export_" + fmt)
+        if fmt in ("CSR", "CSC"):
+            info = fn(C.byref(A), C.byref(t), C.byref(nrows), C.byref(ncols), C.byref(nvals),
+                      C.byref(nonempty), C.byref(pp), C.byref(pi), C.byref(px), None)
+            np_len = (nrows.value if fmt == "CSR" else ncols.value) + 1
+        else:
+            info = fn(C.byref(A), C.byref(t), C.byref(nrows), C.byref(ncols), C.byref(nvals),
+                      C.byref(nonempty), C.byref(nvec), C.byref(ph), C.byref(pp), C.byref(pi),
+                      C.byref(px), None)
+            np_len = nvec.value + 1
+        self.ok(info, "GxB_Matrix_export_" + fmt)
+        tname = self.type_name(t)
+        out = {"type": tname, "nrows": nrows.value, "ncols": ncols.value, "nvals": nvals.value,
+               "nonempty": nonempty.value}
+        out["Ap"] = self._take(pp, np_len, np.int64)
+        out["Ai"] = self._take(pi, nvals.value, np.int64)
+        out["Ax"] = self._take(px, nvals.value, NP_OF[tname])
+        if fmt not in ("CSR", "CSC"):
+            out["Ah"] = self._take(ph, nvec.value, np.int64)
+        return out
+
+    @staticmethod
+    def _take(ptr: C.c_void_p, n: int, dt) -> np.ndarray:
+        dt = np.dtype(dt)
+        if not ptr.value or n == 0:
+            if ptr.value:
+                _libc.free(ptr)
+            return np.zeros(0, dtype=dt)
+        buf = (C.c_char * (n * dt.itemsize)).from_address(ptr.value)
+        a = np.frombuffer(buf, dtype=dt, count=n).copy()
+        _libc.free(ptr)
+        return a
+
+    def type_name(self, t: C.c_void_p) -> str:
+        for name in NP_OF:
+            if self.obj("GrB_" + name).value == t.value:
+                return name
+        raise GrBError("unknown type handle")
+
+    def vector_import(self, type_: str, n: int, vi, vx):
+        vi = np.ascontiguousarray(vi, dtype=np.uint64)
+        vx = np.ascontiguousarray(vx, dtype=NP_OF[type_])
+        v = C.c_void_p()
+        pi, px = self._malloc_copy(vi), self._malloc_copy(vx)
+        self.ok(self.lib.GxB_Vector_import(C.byref(v), self.obj("GrB_" + type_), C.c_uint64(n),
+                                           C.c_uint64(len(vi)), C.byref(pi), C.byref(px), None),
+                "GxB_Vector_import")
+        return v
+
+    def vector_export(self, v: C.c_void_p):
+        t = C.c_void_p()
+        n, nvals = C.c_uint64(), C.c_uint64()
+        pi, px = C.c_void_p(), C.c_void_p()
+        self.ok(self.lib.GxB_Vector_export(C.byref(v), C.byref(t), C.byref(n), C.byref(nvals),
+                                           C.byref(pi), C.byref(px), None), "GxB_Vector_export")
+        tname = self.type_name(t)
+        return {"type": tname, "n": n.value, "nvals": nvals.value,
+                "vi": self._take(pi, nvals.value, np.int64),
+                "vx": self._take(px, nvals.value, NP_OF[tname])}
+
+    # ---- objects ------------------------------------------------------------------------------
+    def matrix_new(self, type_: str, nrows: int, ncols: int):
+        A = C.c_void_p()
+        self.ok(self.lib.GrB_Matrix_new(C.byref(A), self.obj("GrB_" + type_), C.c_uint64(nrows),
+                                        C.c_uint64(ncols)), "GrB_Matrix_new")
+        return A
+
+    def vector_new(self, type_: str, n: int):
+        v = C.c_void_p()
+        self.ok(self.lib.GrB_Vector_new(C.byref(v), self.obj("GrB_" + type_), C.c_uint64(n)),
+                "GrB_Vector_new")
+        return v
+
+    def matrix_dup(self, A):
+        B = C.c_void_p()
+        self.ok(self.lib.GrB_Matrix_dup(C.byref(B), A), "GrB_Matrix_dup")
+        return B
+
+    def vector_dup(self, v):
+        w = C.c_void_p()
+        self.ok(self.lib.GrB_Vector_dup(C.byref(w), v), "GrB_Vector_dup")
+        return w
+
+    def matrix_free(self, A):
+        self.lib.GrB_Matrix_free(C.byref(A))
+
+    def vector_free(self, v):
+        self.lib.GrB_Vector_free(C.byref(v))
+
+    def matrix_nvals(self, A) -> int:
+        n = C.c_uint64()
+        self.ok(self.lib.GrB_Matrix_nvals(C.byref(n), A), "GrB_Matrix_nvals")
+        return n.value
+
+    def vector_nvals(self, v) -> int:
+        n = C.c_uint64()
+        self.ok(self.lib.GrB_Vector_nvals(C.byref(n), v), "GrB_Vector_nvals")
+        return n.value
+
+    def descriptor(self, outp=GxB_DEFAULT, mask=GxB_DEFAULT, inp0=GxB_DEFAULT, inp1=GxB_DEFAULT,
+                   method=GxB_DEFAULT):
+        if (outp, mask, inp0, inp1, method) == (0, 0, 0, 0, 0):
+            return None
+        d = C.c_void_p()
+        self.ok(self.lib.GrB_Descriptor_new(C.byref(d)), "GrB_Descriptor_new")
+        for f, v in ((GrB_OUTP, outp), (GrB_MASK, mask), (GrB_INP0, inp0), (GrB_INP1, inp1),
+                     (GxB_AxB_METHOD, method)):
+            if v != GxB_DEFAULT:
+                self.ok(self.lib.GrB_Descriptor_set(d, f, v), "GrB_Descriptor_set")
+        return d
+
+    def descriptor_free(self, d):
+        if d is not None:
+            self.lib.GrB_Descriptor_free(C.byref(d))
+
+    # ---- the path under test --------------------------------------------------------------------
+    def mxm(self, Cm, M, accum, semiring: str, A, B, desc):
+        self.ok(self.lib.GrB_mxm(Cm, M, self.obj(accum) if accum else None, self.obj(semiring), A, B,
+                                 desc), "GrB_mxm")
+
+    def mxv(self, w, mask, accum, semiring: str, A, u, desc):
+        self.ok(self.lib.GrB_mxv(w, mask, self.obj(accum) if accum else None, self.obj(semiring), A,
+                                 u, desc), "GrB_mxv")
+
+    def vxm(self, w, mask, accum, semiring: str, u, A, desc):
+        self.ok(self.lib.GrB_vxm(w, mask, self.obj(accum) if accum else None, self.obj(semiring), u,
+                                 A, desc), "GrB_vxm")
+
+    def reduce_int64(self, A, monoid="GxB_PLUS_INT64_MONOID") -> int:
+        s = C.c_int64(0)
+        self.ok(self.lib.GrB_Matrix_reduce_INT64(C.byref(s), None, self.obj(monoid), A, None),
+                "GrB_Matrix_reduce_INT64")
+        return s.value

@@ -1,0 +1,228 @@
+"""GPU parity tests: the B200 path (through the interposed GB_AxB_parallel, i.e. through the C ABI of
+libgb_b200.so) against the compiled reference on the same inputs.  The cases follow the reference's
+own mxm tests (Test/test06.m: semirings x methods x transposes x mask; test74/75: dot; test88:
+hypersparse + heap; test20: mxv/vxm + accum) at sizes the CPU reference finishes in milliseconds."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import gen
+import grbref
+from grbref import (GxB_DEFAULT, GrB_REPLACE, GrB_SCMP, GrB_TRAN, GxB_AxB_GUSTAVSON, GxB_AxB_HEAP,
+                    GxB_AxB_DOT)
+from parity import check_mxm, check_mv
+
+pytestmark = pytest.mark.gpu
+
+NP = grbref.NP_OF
+
+
+# ---------------------------------------------------------------------------------------------
+# config 1 shape: C = A*B, PLUS_TIMES_FP64, ER, no mask (reference picks Gustavson)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fmt", ["CSR", "CSC"])
+def test_cfg1_er_plus_times_fp64(G, fmt):
+    n = 4096
+    A = gen.er(n, n, 8 * n, 1)
+    B = gen.er(n, n, 8 * n, 2)
+    ref, got = check_mxm(G, A=A, B=B, type_="FP64", semiring="GxB_PLUS_TIMES_FP64", fmt=fmt)
+    assert ref["nvals"] > 0
+
+
+@pytest.mark.parametrize("semiring,type_", [
+    ("GxB_PLUS_TIMES_INT64", "INT64"), ("GxB_PLUS_TIMES_UINT32", "UINT32"),
+    ("GxB_MIN_PLUS_FP64", "FP64"), ("GxB_MAX_MIN_INT32", "INT32"),
+    ("GxB_LOR_LAND_BOOL", "BOOL"), ("GxB_PLUS_TIMES_FP32", "FP32"),
+    ("GxB_TIMES_PLUS_INT8", "INT8"), ("GxB_MIN_MAX_UINT16", "UINT16"),
+    ("GxB_LXOR_LOR_BOOL", "BOOL"), ("GxB_EQ_LT_FP32", "FP32"), ("GxB_PLUS_DIV_INT16", "INT16"),
+    ("GxB_PLUS_MINUS_FP64", "FP64"), ("GxB_MAX_FIRST_UINT8", "UINT8"),
+    ("GxB_LAND_GE_INT64", "INT64"), ("GxB_TIMES_SECOND_FP64", "FP64"),
+    ("GxB_PLUS_ISGT_UINT64", "UINT64"), ("GxB_MIN_DIV_INT32", "INT32"),
+])
+@pytest.mark.parametrize("fmt", ["CSR", "CSC"])
+def test_unmasked_semirings(G, semiring, type_, fmt):
+    A = gen.er(300, 200, 2400, 3, NP[type_])
+    B = gen.er(200, 250, 2000, 4, NP[type_])
+    check_mxm(G, A=A, B=B, type_=type_, semiring=semiring, fmt=fmt)
+
+
+@pytest.mark.parametrize("inp0,inp1", [(GxB_DEFAULT, GxB_DEFAULT), (GrB_TRAN, GxB_DEFAULT),
+                                       (GxB_DEFAULT, GrB_TRAN), (GrB_TRAN, GrB_TRAN)])
+@pytest.mark.parametrize("method", [GxB_DEFAULT, GxB_AxB_GUSTAVSON, GxB_AxB_HEAP, GxB_AxB_DOT])
+@pytest.mark.parametrize("fmt", ["CSR", "CSC"])
+def test_transposes_and_methods(G, inp0, inp1, method, fmt):
+    """the 16 CSR/CSC x transpose cases folded by GB_AxB_meta.c:97-180, under every method request"""
+    A = gen.er(120, 120, 900, 5, np.int32)
+    B = gen.er(120, 120, 800, 6, np.int32)
+    check_mxm(G, A=A, B=B, type_="INT32", semiring="GxB_PLUS_MINUS_INT32", fmt=fmt, inp0=inp0,
+              inp1=inp1, method=method)
+
+
+@pytest.mark.parametrize("maskd", [GxB_DEFAULT, GrB_SCMP])
+@pytest.mark.parametrize("outp", [GxB_DEFAULT, GrB_REPLACE])
+@pytest.mark.parametrize("method", [GxB_DEFAULT, GxB_AxB_GUSTAVSON, GxB_AxB_DOT])
+@pytest.mark.parametrize("inp0", [GxB_DEFAULT, GrB_TRAN])
+def test_masked(G, maskd, outp, method, inp0):
+    """valued masks (entries that are present but false do not admit), complement, replace, accum"""
+    n = 150
+    A = gen.er(n, n, 1500, 7, np.float64)
+    B = gen.er(n, n, 1400, 8, np.float64)
+    M = gen.er(n, n, 3000, 9, np.int8, lo=0, hi=2)          # about half the entries are zero
+    Cinit = gen.er(n, n, 700, 10, np.float64)
+    check_mxm(G, A=A, B=B, type_="FP64", semiring="GxB_PLUS_TIMES_FP64", M=M, mtype="INT8",
+              Cinit=Cinit, accum="GrB_PLUS_FP64", mask=maskd, outp=outp, method=method, inp0=inp0)
+
+
+def test_mask_dense_is_dropped(G):
+    """flops <= nnz(M): the saxpy path discards the mask (GB_AxB_sequential.c:88-95); C is the same"""
+    n = 60
+    A = gen.er(n, n, 70, 11, np.int64)
+    B = gen.er(n, n, 70, 12, np.int64)
+    M = sp.csr_matrix(np.ones((n, n), dtype=np.bool_))
+    check_mxm(G, A=A, B=B, type_="INT64", semiring="GxB_PLUS_TIMES_INT64", M=M, mtype="BOOL")
+
+
+@pytest.mark.parametrize("fmt", ["HyperCSR", "HyperCSC"])
+@pytest.mark.parametrize("method", [GxB_DEFAULT, GxB_AxB_DOT])
+@pytest.mark.parametrize("masked", [False, True])
+def test_hypersparse(G, fmt, method, masked):
+    """hypersparse operands (Test/test88.m): vectors found through the hyperlist, hypersparse T"""
+    n = 5000
+    A = gen.er(n, n, 600, 13, np.int32)
+    B = gen.er(n, n, 500, 14, np.int32)
+    # give them some common structure so that products exist
+    A = (A + sp.csr_matrix((np.ones(40, np.int32), (np.arange(40) * 7, np.arange(40) * 11)), shape=(n, n))).tocsr()
+    B = (B + sp.csr_matrix((np.ones(40, np.int32), (np.arange(40) * 11, np.arange(40) * 3)), shape=(n, n))).tocsr()
+    M = gen.er(n, n, 4000, 15, np.bool_) + sp.csr_matrix(
+        (np.ones(40, np.bool_), (np.arange(40) * 7, np.arange(40) * 3)), shape=(n, n)) if masked else None
+    check_mxm(G, A=A, B=B, type_="INT32", semiring="GxB_PLUS_TIMES_INT32", fmt=fmt, method=method,
+              M=M.tocsr() if masked else None, mtype="BOOL")
+
+
+def test_heavy_vectors(G):
+    """a few vectors whose flop count exceeds every shared-memory bin (bitmap path), plus every
+    lighter bin in the same multiply"""
+    n = 3000
+    rng = np.random.default_rng(16)
+    A = gen.er(n, n, 40 * n, 17, np.int64, lo=1, hi=4).tolil()
+    B = gen.er(n, n, 4 * n, 18, np.int64, lo=1, hi=4).tolil()
+    for r in (5, 77, 1500):                                  # dense rows of B -> heavy (CSR: row-wise)
+        cols = rng.choice(n, 1200, replace=False)
+        B[r, cols] = 1
+    for r in (9, 800):                                       # medium rows
+        cols = rng.choice(n, 150, replace=False)
+        B[r, cols] = 2
+    A, B = A.tocsr(), B.tocsr()
+    check_mxm(G, A=B, B=A, type_="INT64", semiring="GxB_PLUS_TIMES_INT64")
+    M = gen.er(n, n, 30 * n, 19, np.bool_)
+    check_mxm(G, A=B, B=A, type_="INT64", semiring="GxB_PLUS_TIMES_INT64", M=M, mtype="BOOL")
+    check_mxm(G, A=B, B=A, type_="INT64", semiring="GxB_MIN_PLUS_INT64", fmt="CSC")
+
+
+def test_empty_and_ragged(G):
+    """empty operands, empty result, 1 x n and n x 1 shapes"""
+    Z = sp.csr_matrix((50, 40), dtype=np.float64)
+    B = gen.er(40, 30, 100, 20, np.float64)
+    check_mxm(G, A=Z, B=B, type_="FP64", semiring="GxB_PLUS_TIMES_FP64")
+    check_mxm(G, A=gen.er(50, 40, 90, 21), B=sp.csr_matrix((40, 30), dtype=np.float64), type_="FP64",
+              semiring="GxB_PLUS_TIMES_FP64")
+    check_mxm(G, A=gen.er(1, 40, 20, 22), B=gen.er(40, 1, 20, 23), type_="FP64",
+              semiring="GxB_PLUS_TIMES_FP64")
+    check_mxm(G, A=gen.er(40, 1, 20, 24), B=gen.er(1, 40, 20, 25), type_="FP64",
+              semiring="GxB_PLUS_TIMES_FP64", fmt="CSC")
+    # disjoint patterns: no product exists
+    A = sp.csr_matrix((np.ones(5), (np.arange(5), np.arange(5))), shape=(10, 10))
+    B = sp.csr_matrix((np.ones(5), (np.arange(5) + 5, np.arange(5))), shape=(10, 10))
+    ref, got = check_mxm(G, A=A, B=B, type_="FP64", semiring="GxB_PLUS_TIMES_FP64")
+    assert got["nvals"] == 0
+
+
+def test_aliased_C_is_A(G):
+    """C<C> = C*C with accum (Test/test28.m): T is always a fresh matrix"""
+    A = gen.er(80, 80, 600, 26, np.int64, lo=1, hi=3)
+    check_mxm(G, A=A, B=A, type_="INT64", semiring="GxB_PLUS_TIMES_INT64", M=A, mtype="INT64",
+              Cinit=A, accum="GrB_PLUS_INT64")
+
+
+# ---------------------------------------------------------------------------------------------
+# triangle counting shape (config 2): C<L> = L*U' (dot) and C<L> = L*L (masked saxpy)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scale", [8, 11])
+@pytest.mark.parametrize("type_", ["INT64", "UINT32"])
+def test_tricount(G, scale, type_):
+    A = gen.rmat_scipy(scale, 16, dtype=NP[type_])
+    L, U = sp.tril(A, -1).tocsr(), sp.triu(A, 1).tocsr()
+    sr = "GxB_PLUS_TIMES_" + type_
+    ref, got = check_mxm(G, A=L, B=U, M=L, mtype=type_, type_=type_, semiring=sr, inp1=GrB_TRAN)
+    ntri_dot = int(got["Ax"].astype(np.int64).sum())
+    ref2, got2 = check_mxm(G, A=L, B=L, M=L, mtype=type_, type_=type_, semiring=sr)
+    ntri_outer = int(got2["Ax"].astype(np.int64).sum())
+    # independent count: trace(A^3)/6
+    A1 = A.astype(np.int64)
+    ntri = int((A1 @ A1).multiply(A1).sum() // 6)
+    assert ntri_dot == ntri_outer == ntri
+
+
+# ---------------------------------------------------------------------------------------------
+# vectors: BFS step (config 3) and Bellman-Ford step (config 4)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fmt", ["CSR", "CSC"])
+@pytest.mark.parametrize("op", ["vxm", "mxv"])
+def test_bfs_levels(G, fmt, op):
+    """the bfs5m loop (Demo/Source/bfs5m.c:71-82) step by step: q<!v> = q*A over LOR_LAND_BOOL with
+    REPLACE; level sets must be identical at every level"""
+    A = gen.rmat_scipy(10, 8, dtype=np.bool_)
+    n = A.shape[0]
+    src = int(np.argmax(np.diff(A.indptr)))
+    visited = np.zeros(n, dtype=bool)
+    q = np.array([src])
+    for level in range(1, 12):
+        visited[q] = True
+        vi = np.nonzero(visited)[0]
+        ref, got = check_mv(G, op=op, A=A, u=(n, q, np.ones(len(q), bool)), type_="BOOL",
+                            semiring="GxB_LOR_LAND_BOOL", n_out=n, mask=(vi, np.ones(len(vi), bool)),
+                            winit=(q, np.ones(len(q), bool)), outp=GrB_REPLACE, maskd=GrB_SCMP, fmt=fmt)
+        q = got["vi"]
+        if len(q) == 0:
+            break
+    assert visited.sum() > n // 4
+
+
+@pytest.mark.parametrize("fmt", ["CSR", "CSC"])
+def test_sssp_bellman_ford(G, fmt):
+    """d = min (d, A min.+ d) iterated (config 4): MIN_PLUS_FP64 with accum MIN; bit-exact"""
+    A = gen.rmat_scipy(9, 8, weighted=True)
+    n = A.shape[0]
+    src = int(np.argmax(np.diff(A.indptr)))
+    d = np.full(n, np.inf)
+    d[src] = 0.0
+    idx = np.arange(n)
+    for it in range(6):
+        ref, got = check_mv(G, op="mxv", A=A, u=(n, idx, d), type_="FP64",
+                            semiring="GxB_MIN_PLUS_FP64", n_out=n, winit=(idx, d),
+                            accum="GrB_MIN_FP64", fmt=fmt)
+        assert np.array_equal(ref["vx"], got["vx"])          # bit-exact, not just within tolerance
+        d = got["vx"]
+    assert np.isfinite(d).sum() > n // 4
+
+
+@pytest.mark.parametrize("op,tran", [("mxv", GxB_DEFAULT), ("mxv", GrB_TRAN), ("vxm", GxB_DEFAULT),
+                                     ("vxm", GrB_TRAN)])
+@pytest.mark.parametrize("semiring,type_", [("GxB_PLUS_TIMES_FP64", "FP64"),
+                                            ("GxB_MAX_PLUS_INT32", "INT32"),
+                                            ("GxB_LOR_LAND_BOOL", "BOOL")])
+@pytest.mark.parametrize("usparse", [True, False])
+def test_mxv_vxm(G, op, tran, semiring, type_, usparse):
+    m, n = 400, 300
+    A = gen.er(m, n, 5000, 27, NP[type_])
+    n_in = (m if tran == GrB_TRAN else n) if op == "mxv" else (n if tran == GrB_TRAN else m)
+    n_out = (n if tran == GrB_TRAN else m) if op == "mxv" else (m if tran == GrB_TRAN else n)
+    rng = np.random.default_rng(28)
+    ui = np.sort(rng.choice(n_in, n_in // 5 if usparse else n_in, replace=False))
+    ux = gen.er(1, len(ui), 4 * len(ui), 29, NP[type_]).toarray().ravel()[:len(ui)].astype(NP[type_])
+    check_mv(G, op=op, A=A, u=(n_in, ui, ux), type_=type_, semiring=semiring, n_out=n_out, tran=tran)
+    mi = np.sort(rng.choice(n_out, n_out // 2, replace=False))
+    check_mv(G, op=op, A=A, u=(n_in, ui, ux), type_=type_, semiring=semiring, n_out=n_out, tran=tran,
+             mask=(mi, rng.integers(0, 2, len(mi)).astype(bool)), maskd=GrB_SCMP)
+    check_mv(G, op=op, A=A, u=(n_in, ui, ux), type_=type_, semiring=semiring, n_out=n_out, tran=tran,
+             mask=(mi, rng.integers(0, 2, len(mi)).astype(bool)))
