@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement: masked GrB_mxm on an RMAT graph, semiring GFLOP/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tri|spgemm|sssp|bfs] [--scale S]
+  python bench.py --impl reference ...      # the reference's own CPU GrB_mxm, bounded sample
+
+A "step" is one pass of the hot path (one GrB_mxm-equivalent multiply through the C ABI of
+libgb_b200.so) over one synthetic input.  Default workload (BASELINE.json: "GrB_mxm ... RMAT
+scale-22"): `tri` = C<L> = L*U' over PLUS_TIMES_INT64 on RMAT scale 22, edge factor 16 -- what
+GrB_mxm(C, L, NULL, GxB_PLUS_TIMES_INT64, L, U, desc{INP1=TRAN}) hands to GB_AxB_parallel
+(reference Demo/Source/tricount.c:166-178): M = L, A = U, B = L, do_adotb, flipxy.
+
+  value : 2 * madds / t, operands resident in HBM (gb200_AxB_device), max over ranks
+  e2e   : same metric through gb200_AxB_host + gb200_result_fetch with HOST numpy buffers
+          (H2D of M, A, B and D2H of T inside the timed region)
+  roofline : dominant kernel (the semiring kernel: dot_kernel / saxpy_*), algorithmic bytes of
+          SURVEY.md 8(d) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : oracle/_ref (the compiled reference), GrB_mxm on a bounded sample of the same
+          workload, on rank 0 at N == 1 only
+
+N > 1 (torchrun, one rank per GPU): the mask's vectors are split into N flop-balanced contiguous
+slices (the reference's own plan, GB_AxB_parallel.c:52); A and B are replicated; no data-path
+collective; the triangle count is all-reduced over NCCL.  The problem is fixed, so scaling is
+"strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+# ---------------------------------------------------------------------------------------------
+# inputs
+# ---------------------------------------------------------------------------------------------
+def build_rmat(scale: int, ef: int, device: str, weighted: bool = False):
+    """-> dict of numpy arrays: n, Ap, Aj (symmetric, loop-free, sorted), optional Ax"""
+    import torch
+    import gen
+    n, r, c = gen.rmat_edges(scale, ef, 42, device)
+    p = gen.csr_from_sorted(n, r, c)
+    out = {"n": n, "rows": r, "cols": c, "p": p}
+    if weighted:
+        out["w"] = gen.rmat_weights(r, c)
+    return out
+
+
+def tri_operands(g, dtype=np.int64):
+    """L = tril(A,-1), U = triu(A,1) as host CSR arrays (vectors are rows)"""
+    import torch
+    import gen
+    n, r, c = g["n"], g["rows"], g["cols"]
+    low = c < r
+    Lr, Lc = r[low], c[low]
+    Ur, Uc = r[~low], c[~low]
+    Lp = gen.csr_from_sorted(n, Lr, Lc).cpu().numpy()
+    Up = gen.csr_from_sorted(n, Ur, Uc).cpu().numpy()
+    Li, Ui = Lc.cpu().numpy(), Uc.cpu().numpy()
+    return (n, Lp, Li, np.ones(len(Li), dtype=dtype)), (n, Up, Ui, np.ones(len(Ui), dtype=dtype))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.stop, self.t = index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, nm in enumerate(names):
+                if len(s) > 2 + k and s[2 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# workloads: each returns the operands at the GB_AxB_parallel seam
+# ---------------------------------------------------------------------------------------------
+def algo_bytes(mats, cnvec, cnz, zsize):
+    """API layout, 8-byte indices, every operand touched once"""
+    b = 8 * (cnvec + 1) + cnz * (8 + zsize)
+    for m in mats:
+        b += 8 * (len(m.p)) + m.nnz * (8 + m.x.dtype.itemsize)
+        if m.h is not None:
+            b += 8 * len(m.h)
+    return b
+
+
+def make_workload(args, device):
+    import graphblas_b200 as gb
+    w = {}
+    if args.workload == "tri":
+        g = build_rmat(args.scale, args.ef, device)
+        (n, Lp, Li, Lx), (_, Up, Ui, Ux) = tri_operands(g)
+        L = gb.Matrix(n, n, Lp, Li, Lx, None, "INT64")
+        U = gb.Matrix(n, n, Up, Ui, Ux, None, "INT64")
+        w.update(name=f"GrB_mxm C<L>=L*U' PLUS_TIMES_INT64 (masked dot), RMAT scale {args.scale} "
+                      f"edgefactor {args.ef}, n={n}, nnz(L)={L.nnz}",
+                 M=L, A=U, B=L, mask_comp=False, do_adotb=True,
+                 semiring=gb.Semiring("PLUS", "TIMES", "INT64", flipxy=True), dtype="int64",
+                 slice="M")
+    elif args.workload == "spgemm":
+        import gen
+        n = 1 << args.scale
+        A = gen.er(n, n, args.ef * n, 1)
+        B = gen.er(n, n, args.ef * n, 2)
+        Am, Bm = gb.Matrix.from_scipy(A, "FP64"), gb.Matrix.from_scipy(B, "FP64")
+        # CSR C=A*B: the seam sees A := B_in, B := A_in, flipxy
+        w.update(name=f"GrB_mxm C=A*B PLUS_TIMES_FP64 (saxpy), Erdos-Renyi n=2^{args.scale}, "
+                      f"{args.ef} nnz/row",
+                 M=None, A=Bm, B=Am, mask_comp=False, do_adotb=False,
+                 semiring=gb.Semiring("PLUS", "TIMES", "FP64", flipxy=True), dtype="f64", slice="B")
+    else:
+        raise SystemExit(f"unknown workload {args.workload}")
+    return w
+
+
+def slice_vectors(m, lo, hi):
+    """keep vectors [lo,hi) of a standard-form matrix, same dimensions (others become empty)"""
+    import graphblas_b200 as gb
+    p = np.zeros(len(m.p), dtype=np.int64)
+    s, e = m.p[lo], m.p[hi]
+    p[lo:hi + 1] = m.p[lo:hi + 1] - s
+    p[hi + 1:] = e - s
+    return gb.Matrix(m.vlen, m.vdim, p, m.i[s:e], m.x[s:e], None, m.type)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: the compiled reference through its public API
+# ---------------------------------------------------------------------------------------------
+def reference_sample(args, w, budget_s=20.0):
+    """GrB_mxm on the reference's CPU path over a bounded sample: every `stride`-th vector of the
+    mask (tri) or of the sliced operand (spgemm).  Returns (gflops, seconds, madds, description)."""
+    import grbref
+    G = grbref.GraphBLAS.get(with_shim=False)
+    sliced = w["M"] if w["slice"] == "M" else w["B"]
+    nvec = sliced.nvec
+    stride = args.cpu_stride
+    cnt = np.diff(sliced.p)
+    keep = np.zeros(nvec, dtype=bool)
+    keep[::stride] = True
+    cnt2 = np.where(keep, cnt, 0)
+    p2 = np.concatenate([[0], np.cumsum(cnt2)])
+    sel = np.repeat(keep, cnt)
+    i2, x2 = sliced.i[sel], sliced.x[sel]
+    t_import = time.time()
+    if args.workload == "tri":
+        # user-level call: C<Ls> = L*U' , CSR, desc INP1 = TRAN (Demo/Source/tricount.c:166-178)
+        L, U = w["B"], w["A"]
+        n = L.vdim
+        l = G.matrix_import("CSR", "INT64", n, n, L.p, L.i, L.x)
+        u = G.matrix_import("CSR", "INT64", n, n, U.p, U.i, U.x)
+        ms = G.matrix_import("CSR", "INT64", n, n, p2, i2, x2)
+        c = G.matrix_new("INT64", n, n)
+        d = G.descriptor(inp1=grbref.GrB_TRAN)
+        t0 = time.perf_counter()
+        G.mxm(c, ms, None, "GxB_PLUS_TIMES_INT64", l, u, d)
+        G.matrix_nvals(c)
+        dt = time.perf_counter() - t0
+        madds = G.reduce_int64(c)
+        for h in (l, u, ms, c):
+            G.matrix_free(h)
+    else:
+        # user-level call: C = As*B, CSR
+        Ain, Bin = w["B"], w["A"]
+        a = G.matrix_import("CSR", "FP64", Ain.vdim, Ain.vlen, p2, i2, x2)
+        b = G.matrix_import("CSR", "FP64", Bin.vdim, Bin.vlen, Bin.p, Bin.i, Bin.x)
+        c = G.matrix_new("FP64", Ain.vdim, Bin.vlen)
+        t0 = time.perf_counter()
+        G.mxm(c, None, None, "GxB_PLUS_TIMES_FP64", a, b, None)
+        G.matrix_nvals(c)
+        dt = time.perf_counter() - t0
+        # madds of the sample = sum over kept entries A(i,k) of nnz(B(k,:))
+        madds = int(np.diff(Bin.p)[i2].sum())
+        for h in (a, b, c):
+            G.matrix_free(h)
+    desc = (f"every {stride}th vector of {'the mask L' if args.workload == 'tri' else 'A'} "
+            f"({int(keep.sum())} of {nvec} vectors, {len(i2)} entries), one GrB_mxm call, 1 thread "
+            f"(the reference multiply is sequential: Source/GB_AxB_parallel.c:102-103)")
+    return 2.0 * madds / dt / 1e9, dt, madds, desc
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="tri", choices=["tri", "spgemm"])
+    ap.add_argument("--scale", type=int, default=22)
+    ap.add_argument("--ef", type=int, default=16)
+    ap.add_argument("--cpu-stride", type=int, default=16)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.workload == "spgemm" and args.scale == 22 and "--scale" not in " ".join(sys.argv):
+        args.scale, args.ef = 20, 8
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    have_cuda = torch.cuda.is_available()
+    device = f"cuda:{local_rank}" if have_cuda else "cpu"
+
+    # ---- reference arm: rank 0 only, CPU ------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import graphblas_b200  # noqa: F401  (Matrix container only; no device call is made)
+        w = make_workload(args, device)
+        vals = []
+        for s in range(args.warmup + args.steps):
+            gf, dt, madds, desc = reference_sample(args, w)
+            if s >= args.warmup:
+                vals.append((gf, dt))
+        gf = float(np.mean([v[0] for v in vals]))
+        dt = float(np.mean([v[1] for v in vals]))
+        line = {"impl": "reference", "metric": "GrB_mxm semiring GFLOP/s", "value": gf,
+                "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+                "config": {"workload": w["name"]},
+                "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": 1, "kind": "reference",
+                                 "sample": desc},
+                "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---- our arm ----------------------------------------------------------------------------
+    if not have_cuda:
+        raise SystemExit("bench.py needs a GPU (there is no CPU path); use --impl reference for "
+                         "the CPU arm")
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    os.environ["GB200_DEVICE"] = str(local_rank)
+    import graphblas_b200 as gb
+    gb.init(local_rank)
+
+    w = make_workload(args, device)
+    torch.cuda.empty_cache()
+    A, B, M = w["A"], w["B"], w["M"]
+    dA = gb.DMatrix(A)
+    dB = dA if B is A else gb.DMatrix(B)
+    dM = None
+    if M is not None:
+        dM = dB if M is B else gb.DMatrix(M)
+
+    # flop-balanced contiguous slices of the sliced operand's vectors, one per rank
+    sliced_name = w["slice"]
+    sliced = M if sliced_name == "M" else B
+    lo, hi = 0, sliced.nvec
+    if world > 1:
+        if sliced_name == "B":
+            cum, _ = gb.flopcount(dM, dA, dB)
+        else:
+            # masked dot: balance by sum over mask entries of (len A(:,i) + len B(:,j))
+            lenA = np.diff(A.p)
+            lenB = np.diff(B.p)
+            cs = np.concatenate([[0], np.cumsum(lenA[M.i])])
+            per_vec = (cs[M.p[1:]] - cs[M.p[:-1]]) + np.diff(M.p) * lenB
+            cum = np.concatenate([[0], np.cumsum(per_vec)]).astype(np.int64)
+        bounds = gb.partition_by_flops(cum, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        mine = slice_vectors(sliced, lo, hi)
+        dmine = gb.DMatrix(mine)
+        if sliced_name == "M":
+            M, dM = mine, dmine
+        else:
+            B, dB = mine, dmine
+
+    def step_device():
+        return gb.axb_device(dM, w["mask_comp"], dA, dB, w["semiring"], w["do_adotb"], fetch=False)
+
+    def step_host():
+        return gb.axb_host(M, w["mask_comp"], A, B, w["semiring"], w["do_adotb"], fetch=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        r = step_device()
+    launches0 = gb.kernel_launches()
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        dev_ms, ker_ms = [], []
+        for _ in range(args.steps):
+            r = step_device()
+            dev_ms.append(r.info["device_ms"])
+            ker_ms.append(r.info["kernel_ms"])
+        torch.cuda.synchronize()
+        t_local = time.perf_counter() - t0
+    launches = gb.kernel_launches() - launches0
+    tt = torch.tensor([t_local, float(np.sum(dev_ms))], dtype=torch.float64, device=device)
+    fl = torch.tensor([r.info["flops"], r.info["nnz"]], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
+    barrier()
+    t_step = tt[0].item() / args.steps
+    madds, cnz = int(fl[0].item()), int(fl[1].item())
+    gflops = 2.0 * madds / t_step / 1e9
+
+    # ---- e2e: host buffers in, host T out, every step -----------------------------------------
+    e2e_steps = max(1, min(args.steps, 3))
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rh = step_host()
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = te[0].item() / e2e_steps
+    mats = [m for m in (M, A, B) if m is not None]
+    uniq = {id(m): m for m in mats}.values()
+    h2d = sum(m.p.nbytes + m.i.nbytes + m.x.nbytes + (m.h.nbytes if m.h is not None else 0)
+              for m in uniq)
+    T = rh.matrix
+    d2h = T.p.nbytes + T.i.nbytes + T.x.nbytes + (T.h.nbytes if T.h is not None else 0)
+
+    # ---- roofline of the dominant (semiring) kernel, rank 0's slice --------------------------
+    peak, peak_src = measured_peak()
+    zsize = T.x.dtype.itemsize
+    ab = algo_bytes(list(uniq), r.info["nvec"], r.info["nnz"], zsize)
+    k_ms = float(np.mean(ker_ms))
+    achieved = ab / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+
+    if rank == 0:
+        line = {"metric": "GrB_mxm semiring GFLOP/s", "value": gflops, "unit": "GFLOP/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+                "config": {"workload": w["name"], "madds_per_step": madds, "nnz_T": cnz,
+                           "l2": "inputs larger than L2 (no flush needed)" if h2d > 2.6e8 else
+                                 "inputs smaller than L2",
+                           "partition": f"{world} flop-balanced contiguous slices of "
+                                        f"{'the mask' if sliced_name == 'M' else 'B'}'s vectors"},
+                "device_ms_per_step": float(np.mean(dev_ms)),
+                "clocks": clk.summary(),
+                "e2e": {"value": 2.0 * madds / t_e2e / 1e9, "unit": "GFLOP/s",
+                        "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None,
+                             "kernel": "dot_kernel" if w["do_adotb"] else "saxpy_*_kernel",
+                             "kernel_ms": k_ms, "algorithmic_bytes": int(ab), "peak_source": peak_src,
+                             "bytes_per_madd": ab / max(r.info["flops"], 1)}}
+        if world == 1 and not args.no_cpu:
+            try:
+                gf, dt, cm, desc = reference_sample(args, w)
+                line["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": 1,
+                                        "kind": "reference", "sample": desc, "seconds": dt,
+                                        "host_cores_present": os.cpu_count()}
+            except Exception as e:  # the reference .so is test infrastructure; say so if absent
+                line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": 1,
+                                        "kind": "reference", "sample": f"unavailable: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

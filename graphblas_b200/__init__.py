@@ -70,7 +70,7 @@ class _CInfo(C.Structure):
     _fields_ = [("vlen", C.c_int64), ("vdim", C.c_int64), ("nvec", C.c_int64),
                 ("nvec_nonempty", C.c_int64), ("nnz", C.c_int64), ("is_hyper", C.c_int32),
                 ("type_code", C.c_int32), ("method_used", C.c_int32), ("mask_applied", C.c_int32),
-                ("flops", C.c_int64), ("device_ms", C.c_double)]
+                ("flops", C.c_int64), ("device_ms", C.c_double), ("kernel_ms", C.c_double)]
 
 
 lib.gb200_last_error.restype = C.c_char_p

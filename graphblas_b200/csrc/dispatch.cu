@@ -17,6 +17,14 @@ bool launch_typed (int xy_code, int family, int z_code, int add, int mult, const
 {
     LaunchCfg cfg ;
     cfg.grid = grid ; cfg.block = block ; cfg.stream = ctx ().stream ;
+    Ctx &c = ctx () ;
+    if (c.kev_used + 2 > (int) c.kev.size ())
+    {
+        cudaEvent_t e0, e1 ;
+        cudaEventCreate (&e0) ; cudaEventCreate (&e1) ;
+        c.kev.push_back (e0) ; c.kev.push_back (e1) ;
+    }
+    cudaEventRecord (c.kev [c.kev_used], c.stream) ;
     bool ok = false ;
     switch (xy_code)
     {
@@ -33,6 +41,8 @@ bool launch_typed (int xy_code, int family, int z_code, int add, int mult, const
         case GB200_FP64   : ok = launch_fp64   (family, z_code, add, mult, args, cfg) ; break ;
         default : break ;
     }
+    cudaEventRecord (c.kev [c.kev_used + 1], c.stream) ;
+    c.kev_used += 2 ;
     if (ok) count_launch () ;
     return ok ;
 }

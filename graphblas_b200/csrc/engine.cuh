@@ -49,6 +49,9 @@ struct Ctx
                                         // many user threads, reference Demo/Program/pthread_demo.c)
     std::atomic<int64_t> launches {0} ;
     std::atomic<int64_t> multiplies {0} ;
+    // CUDA events bracketing every semiring-templated launch of the current multiply
+    std::vector<cudaEvent_t> kev ;
+    int kev_used = 0 ;
 } ;
 
 Ctx &ctx () ;

@@ -297,6 +297,7 @@ gb200_status gb200_AxB_device (gb200_result *out, gb200_dmatrix M, int mask_comp
     gb200_result_s *R = new (std::nothrow) gb200_result_s () ;
     if (R == NULL) return GB200_OUT_OF_MEMORY ;
     memset (&R->info, 0, sizeof (R->info)) ;
+    c.kev_used = 0 ;
     cudaEventRecord (c.ev0, c.stream) ;
     gb200_status st = do_adotb ? run_dot (R, M, mask_comp, A, B, s)
                                : run_saxpy (R, M, mask_comp, A, B, s) ;
@@ -314,6 +315,13 @@ gb200_status gb200_AxB_device (gb200_result *out, gb200_dmatrix M, int mask_comp
             float ms = 0 ;
             cudaEventElapsedTime (&ms, c.ev0, c.ev1) ;
             R->info.device_ms = ms ;
+            double kms = 0 ;
+            for (int q = 0 ; q + 1 < c.kev_used ; q += 2)
+            {
+                float t = 0 ;
+                if (cudaEventElapsedTime (&t, c.kev [q], c.kev [q+1]) == cudaSuccess) kms += t ;
+            }
+            R->info.kernel_ms = kms ;
         }
     }
     if (st != GB200_SUCCESS)

@@ -131,6 +131,7 @@ typedef struct
     int64_t flops ;         /* multiply-add pairs performed (reference GB_AxB_flopcount        */
                             /* definition for saxpy; matched index pairs for dot)             */
     double  device_ms ;     /* CUDA-event time of the compute, operands resident              */
+    double  kernel_ms ;     /* of which: the semiring kernels (saxpy numeric / dot), CUDA events */
 } gb200_result_info ;
 
 /* C<M> = A*B (do_adotb == 0: A->vdim == B->vlen) or C<M> = A'*B (do_adotb != 0:

@@ -40,6 +40,23 @@ class GrBError(RuntimeError):
     pass
 
 
+class _MatrixHeader(C.Structure):
+    """Leading fields of struct GB_Matrix_opaque (reference Source/Template/GB_matrix.h:193-208,
+    307-315), read-only, to look at the raw T returned by GB_AxB_parallel."""
+    _fields_ = [("magic", C.c_int64), ("type", C.c_void_p), ("type_size", C.c_size_t),
+                ("hyper_ratio", C.c_double), ("plen", C.c_int64), ("vlen", C.c_int64),
+                ("vdim", C.c_int64), ("nvec", C.c_int64), ("nvec_nonempty", C.c_int64),
+                ("h", C.c_void_p), ("p", C.c_void_p), ("i", C.c_void_p), ("x", C.c_void_p),
+                ("nzmax", C.c_int64), ("n_pending", C.c_int64), ("max_n_pending", C.c_int64),
+                ("i_pending", C.c_void_p), ("j_pending", C.c_void_p), ("s_pending", C.c_void_p),
+                ("type_pending", C.c_void_p), ("type_pending_size", C.c_size_t),
+                ("operator_pending", C.c_void_p), ("nzombies", C.c_int64),
+                ("AxB_method_used", C.c_int), ("queue_next", C.c_void_p),
+                ("queue_prev", C.c_void_p), ("enqueued", C.c_bool), ("p_shallow", C.c_bool),
+                ("h_shallow", C.c_bool), ("i_shallow", C.c_bool), ("x_shallow", C.c_bool),
+                ("is_hyper", C.c_bool), ("is_csc", C.c_bool), ("sorted_pending", C.c_bool)]
+
+
 def available() -> bool:
     return os.path.exists(REF_LIB)
 
@@ -264,6 +281,44 @@ class GraphBLAS:
     def vxm(self, w, mask, accum, semiring: str, u, A, desc):
         self.ok(self.lib.GrB_vxm(w, mask, self.obj(accum) if accum else None, self.obj(semiring), u,
                                  A, desc), "GrB_vxm")
+
+    # ---- the seam itself: the reference's own GB_AxB_parallel (Source/GB.h:1522-1537) ---------
+    def seam_axb(self, M, mask_comp: bool, A, B, semiring: str, flipxy: bool, do_adotb: bool,
+                 method: int = GxB_DEFAULT):
+        """Calls the reference library's internal GB_AxB_parallel directly on GrB_Matrix handles and
+        returns (T as dict in the CSC-agnostic layout, method_used, mask_applied).  M, A, B must be
+        stored by column (import_CSC / import_HyperCSC) so that the handle's vectors are exactly the
+        seam's vectors."""
+        T = C.c_void_p()
+        used = C.c_int(0)
+        applied = C.c_bool(False)
+        fn = self.lib.GB_AxB_parallel
+        fn.restype = C.c_int
+        info = fn(C.byref(T), M, C.c_bool(mask_comp), A, B, self.obj(semiring), C.c_bool(flipxy),
+                  C.c_bool(do_adotb), C.c_int(method), C.byref(used), C.byref(applied), None)
+        self.ok(info, "GB_AxB_parallel")
+        hdr = _MatrixHeader.from_address(T.value)
+        out = {"vlen": hdr.vlen, "vdim": hdr.vdim, "nvec": hdr.nvec, "is_hyper": bool(hdr.is_hyper),
+               "nvec_nonempty": hdr.nvec_nonempty}
+        nnz = 0
+        if hdr.nzmax > 0:
+            p = np.ctypeslib.as_array((C.c_int64 * (hdr.nvec + 1)).from_address(hdr.p)).copy()
+            nnz = int(p[-1])
+        else:
+            p = np.zeros(hdr.nvec + 1, dtype=np.int64)
+        out["p"] = p
+        out["h"] = (np.ctypeslib.as_array((C.c_int64 * hdr.nvec).from_address(hdr.h)).copy()
+                    if hdr.is_hyper and hdr.nvec > 0 else
+                    (np.zeros(0, dtype=np.int64) if hdr.is_hyper else None))
+        tname = self.type_name(C.c_void_p(hdr.type))
+        dt = np.dtype(NP_OF[tname])
+        out["type"] = tname
+        out["i"] = (np.ctypeslib.as_array((C.c_int64 * nnz).from_address(hdr.i)).copy()
+                    if nnz else np.zeros(0, dtype=np.int64))
+        out["x"] = (np.frombuffer((C.c_char * (nnz * dt.itemsize)).from_address(hdr.x), dtype=dt,
+                                  count=nnz).copy() if nnz else np.zeros(0, dtype=dt))
+        self.matrix_free(T)
+        return out, used.value, bool(applied.value)
 
     def reduce_int64(self, A, monoid="GxB_PLUS_INT64_MONOID") -> int:
         s = C.c_int64(0)

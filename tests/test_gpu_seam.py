@@ -1,0 +1,181 @@
+"""GPU parity at the seam: libgb_b200.so called through its C ABI (gb200_AxB_host / gb200_AxB_device)
+against the pinned oracle restatement on the same arrays, against the golden vectors generated from
+the reference, and through size-independent properties at larger sizes."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import gen
+import semirings
+import graphblas_b200 as gb
+import oracle_c
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NPT = {k: v[1] for k, v in gb.TYPES.items()}
+FLOAT = ("FP32", "FP64")
+
+
+def assert_same(ref: gb.Matrix, got: gb.Matrix, add: str, what=""):
+    assert (ref.vlen, ref.vdim) == (got.vlen, got.vdim), what
+    assert (ref.h is None) == (got.h is None), f"{what}: hypersparsity of T differs"
+    assert np.array_equal(ref.p, got.p), f"{what}: vector pointers differ"
+    if ref.h is not None:
+        assert np.array_equal(ref.h, got.h), f"{what}: hyperlist differs"
+    assert np.array_equal(ref.i, got.i), f"{what}: pattern differs"
+    assert ref.type == got.type, what
+    if ref.type in FLOAT and add in ("PLUS", "TIMES"):
+        assert np.array_equal(np.isnan(ref.x), np.isnan(got.x)), f"{what}: NaN placement"
+        inf = np.isinf(ref.x)
+        assert np.array_equal(inf, np.isinf(got.x)) and np.array_equal(ref.x[inf], got.x[inf]), what
+        fin = np.isfinite(ref.x)
+        r, g = ref.x[fin].astype(np.float64), got.x[fin].astype(np.float64)
+        eps = np.finfo(NPT[ref.type]).eps          # Test/GB_spec_compare.m: 64*eps, relative 1-norm
+        assert np.abs(r - g).sum() <= 64 * eps * np.abs(r).sum(), f"{what}: beyond 64 eps"
+    else:
+        assert np.array_equal(ref.x, got.x, equal_nan=True), f"{what}: values differ (must be exact)"
+
+
+def test_all_960_semirings_saxpy_and_dot():
+    """every built-in worker on the GPU: saxpy (unmasked + masked) and dot (masked + unmasked),
+    both flipxy settings for the operators that observe it"""
+    n = 0
+    for add, mult, t in semirings.all_builtin():
+        dt = NPT[t]
+        A = gb.Matrix.from_scipy(gen.er(40, 30, 260, 61, dt, lo=-3, hi=4).tocsc())
+        B = gb.Matrix.from_scipy(gen.er(30, 35, 240, 62, dt, lo=-3, hi=4).tocsc())
+        At = gb.Matrix.from_scipy(gen.er(30, 40, 260, 63, dt, lo=-3, hi=4).tocsc())
+        M = gb.Matrix.from_scipy(gen.er(40, 35, 500, 64, np.bool_).tocsc())
+        for flip in ((False, True) if mult in ("MINUS", "DIV", "FIRST", "SECOND", "GT", "ISGE") else (False,)):
+            sr = gb.Semiring(add, mult, t, flip)
+            tag = f"{add}_{mult}_{t} flip={flip}"
+            assert_same(oracle_c.axb(None, False, A, B, sr), gb.axb_host(None, False, A, B, sr).matrix, add, tag + " saxpy")
+            assert_same(oracle_c.axb(M, False, A, B, sr), gb.axb_host(M, False, A, B, sr).matrix, add, tag + " masked saxpy")
+            assert_same(oracle_c.axb(M, False, At, B, sr, True), gb.axb_host(M, False, At, B, sr, True).matrix, add, tag + " masked dot")
+            assert_same(oracle_c.axb(None, False, At, B, sr, True), gb.axb_host(None, False, At, B, sr, True).matrix, add, tag + " dot")
+        n += 1
+    assert n == 960
+
+
+def test_golden_vectors_on_gpu():
+    gdir = os.path.join(ROOT, "tests", "golden")
+    files = sorted(f for f in os.listdir(gdir) if f.startswith("seam_") and f.endswith(".npz"))
+    assert len(files) >= 10
+    for f in files:
+        z = np.load(os.path.join(gdir, f), allow_pickle=False)
+
+        def mat(pfx):
+            if pfx + "_p" not in z:
+                return None
+            h = z[pfx + "_h"] if pfx + "_h" in z else None
+            return gb.Matrix(int(z[pfx + "_vlen"]), int(z[pfx + "_vdim"]), z[pfx + "_p"], z[pfx + "_i"],
+                             z[pfx + "_x"], h, str(z[pfx + "_type"]))
+        A, B, M, T = mat("A"), mat("B"), mat("M"), mat("T")
+        sr = gb.Semiring(str(z["add"]), str(z["mult"]), str(z["xytype"]), bool(z["flipxy"]))
+        r = gb.axb_host(M, bool(z["mask_comp"]), A, B, sr, bool(z["do_adotb"]))
+        assert_same(T, r.matrix, sr.add, f)
+        assert r.info["mask_applied"] == int(z["mask_applied"]), f
+        assert (r.info["method_used"] == gb.METHOD_DOT) == bool(z["do_adotb"]), f
+
+
+def test_tri_demo_known_answers_on_gpu():
+    """triangle counts of the reference's Demo/Output/tri_demo.out (:66-1048) through both multiplies"""
+    sr = gb.Semiring("PLUS", "TIMES", "INT64", True)
+    gdir = os.path.join(ROOT, "tests", "golden")
+    for f in sorted(os.listdir(gdir)):
+        if not (f.startswith("tri_") and f.endswith(".npz")):
+            continue
+        z = np.load(os.path.join(gdir, f))
+        n = int(z["n"])
+        A = sp.csr_matrix((np.ones(len(z["i"]), np.int64), z["i"], z["p"]), shape=(n, n))
+        L, U = gb.Matrix.from_scipy(sp.tril(A, -1).tocsr()), gb.Matrix.from_scipy(sp.triu(A, 1).tocsr())
+        dot = gb.axb_host(L, False, U, L, sr, True).matrix
+        outer = gb.axb_host(L, False, L, L, sr, False).matrix
+        assert int(dot.x.sum()) == int(outer.x.sum()) == int(z["ntri"]), f
+
+
+@pytest.mark.parametrize("hyper", [False, True])
+@pytest.mark.parametrize("masked", [False, True])
+def test_flopcount_matches_oracle(hyper, masked):
+    A = gb.Matrix.from_scipy(gen.er(3000, 2000, 30000, 71).tocsc())
+    B = gb.Matrix.from_scipy(gen.er(2000, 2500, 28000, 72).tocsc())
+    B2 = gen.er(2000, 2500, 28000, 72).tolil()
+    B2[:, 7] = 1.0                                  # one vector longer than the multi-block threshold
+    B2[::2, 9] = 1.0
+    B = gb.Matrix.from_scipy(B2.tocsc())
+    M = gb.Matrix.from_scipy(gen.er(3000, 2500, 9000, 73, np.bool_).tocsc())
+    if hyper:
+        A, B, M = A.to_hyper(), B.to_hyper(), M.to_hyper()
+    dA, dB, dM = gb.DMatrix(A), gb.DMatrix(B), gb.DMatrix(M)
+    got, total = gb.flopcount(dM if masked else None, dA, dB)
+    ref, rtotal = oracle_c.flopcount(M if masked else None, A, B)
+    assert total == rtotal and np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("scale", [14, 16])
+def test_rmat_spgemm_and_tricount_properties(scale):
+    """larger RMAT inputs: (1) full parity of C<L>=L*U' against the oracle, (2) dot == masked saxpy
+    == trace(A^3)/6, (3) unmasked C=A*A on a thinned graph against the oracle (heavy bitmap bins)"""
+    A = gen.rmat_scipy(scale, 8, dtype=np.int64)
+    L, U = gb.Matrix.from_scipy(sp.tril(A, -1).tocsr()), gb.Matrix.from_scipy(sp.triu(A, 1).tocsr())
+    sr = gb.Semiring("PLUS", "TIMES", "INT64", True)
+    dot = gb.axb_host(L, False, U, L, sr, True)
+    outer = gb.axb_host(L, False, L, L, sr, False)
+    assert_same(oracle_c.axb(L, False, U, L, sr, True), dot.matrix, "PLUS", "tri dot")
+    assert_same(oracle_c.axb(L, False, L, L, sr, False), outer.matrix, "PLUS", "tri outer")
+    assert int(dot.matrix.x.sum()) == int(outer.matrix.x.sum())
+    assert dot.info["flops"] == int(dot.matrix.x.sum())         # matched pairs == triangles
+    if scale <= 14:
+        Am = gb.Matrix.from_scipy(A.tocsr())
+        got = gb.axb_host(None, False, Am, Am, gb.Semiring("PLUS", "TIMES", "INT64"))
+        assert_same(oracle_c.axb(None, False, Am, Am, gb.Semiring("PLUS", "TIMES", "INT64")), got.matrix,
+                    "PLUS", "A*A")
+        fl, total = oracle_c.flopcount(None, Am, Am)
+        assert got.info["flops"] == total
+
+
+def test_resident_operands_repeatable():
+    """gb200_AxB_device on resident operands: integer results identical run to run and identical to
+    the host entry point; floating PLUS within tolerance"""
+    A = gb.Matrix.from_scipy(gen.er(5000, 5000, 60000, 81, np.int64).tocsc())
+    dA = gb.DMatrix(A)
+    sr = gb.Semiring("PLUS", "TIMES", "INT64")
+    r1 = gb.axb_device(None, False, dA, dA, sr).matrix
+    r2 = gb.axb_device(None, False, dA, dA, sr).matrix
+    r3 = gb.axb_host(None, False, A, A, sr).matrix
+    for r in (r2, r3):
+        assert np.array_equal(r1.p, r.p) and np.array_equal(r1.i, r.i) and np.array_equal(r1.x, r.x)
+
+
+def test_mask_value_types():
+    """a mask may have any built-in type; an entry is true iff its value is nonzero (NaN is true)"""
+    A = gb.Matrix.from_scipy(gen.er(200, 150, 2500, 91).tocsc())
+    B = gb.Matrix.from_scipy(gen.er(150, 180, 2200, 92).tocsc())
+    sr = gb.Semiring("PLUS", "TIMES", "FP64")
+    for t in ("BOOL", "INT8", "UINT16", "INT32", "UINT64", "FP32", "FP64"):
+        Ms = gen.er(200, 180, 9000, 93, NPT[t], lo=0, hi=2)
+        if t in FLOAT:
+            Ms.data[::7] = np.nan
+            Ms.data[1::7] = -0.0
+        M = gb.Matrix.from_scipy(Ms.tocsc(), t)
+        for comp in (False, True):
+            for dot, Ax in ((False, A), (True, gb.Matrix.from_scipy(gen.er(150, 200, 2500, 94).tocsc()))):
+                assert_same(oracle_c.axb(M, comp, Ax, B, sr, dot), gb.axb_host(M, comp, Ax, B, sr, dot).matrix,
+                            "PLUS", f"mask {t} comp={comp} dot={dot}")
+
+
+def test_nan_inf_placement():
+    """NaN / Inf must land in the same places as in the reference (Test/isequal_roundoff.m:18-35)"""
+    A = gen.er(120, 100, 1500, 95)
+    B = gen.er(100, 110, 1400, 96)
+    A.data[::11] = np.inf
+    A.data[3::17] = -np.inf
+    B.data[::13] = np.nan
+    B.data[5::19] = 0.0
+    Am, Bm = gb.Matrix.from_scipy(A.tocsc()), gb.Matrix.from_scipy(B.tocsc())
+    for add, mult in (("PLUS", "TIMES"), ("MIN", "PLUS"), ("MAX", "TIMES"), ("TIMES", "MIN"), ("MIN", "DIV")):
+        sr = gb.Semiring(add, mult, "FP64")
+        assert_same(oracle_c.axb(None, False, Am, Bm, sr), gb.axb_host(None, False, Am, Bm, sr).matrix, add,
+                    f"{add}_{mult}")
