@@ -18,7 +18,31 @@ struct DMat
     int64_t vlen, vdim, nvec, nnz ;
     int hyper ;             // GB_IS_HYPER: is_hyper && nvec < vdim  (Source/GB.h:266-267)
     int type_code ;
+    // optional per-vector hash index (built lazily for the dot kernels): vectors longer than
+    // VECHASH_MIN own an open-addressing table of 2^log slots (keys = indices, vals = offset of the
+    // index inside the vector); hinfo[kk] = (table offset << 6) | log, or -1 for short vectors
+    const int64_t *hinfo ;
+    const int32_t *hkeys ;
+    const int32_t *hofs ;
 } ;
+
+constexpr int64_t VECHASH_MIN = 4096 ;     // == DOTG_CAP: shorter owners use shared memory
+
+// position (in A.i / A.x) of index `key` in the vector [q0,q1) whose hash descriptor is `hi`, or -1
+__device__ __forceinline__ int64_t vechash_probe (const DMat &A, int64_t hi, int64_t q0, int32_t key)
+{
+    const int lg = (int) (hi & 63) ;
+    const int64_t off = hi >> 6 ;
+    const uint32_t mask = (1u << lg) - 1u ;
+    uint32_t h = ((uint32_t) key * 0x9E3779B1u) >> (32 - lg) ;
+    while (true)
+    {
+        const int32_t k = __ldg (A.hkeys + off + h) ;
+        if (k == key) return q0 + __ldg (A.hofs + off + h) ;
+        if (k < 0) return -1 ;
+        h = (h + 1) & mask ;
+    }
+}
 
 // Find vector k of A: returns [pa, pe).  Standard form: direct.  Hypersparse: binary search of
 // the hyperlist (the role of GB_lookup, reference Source/GB.h:3396-3445).

@@ -104,6 +104,8 @@ struct gb200_dmatrix_s
     gb200::DMat v ;                 // device view
     gb200::DevBuf p, h, i, x ;
     int is_hyper_flag ;             // raw A->is_hyper (h != NULL), as used by GB_AxB_alloc.c:49-50
+    gb200::DevBuf hinfo, hkeys, hofs ;  // lazily built per-vector hash index (common.cuh)
+    bool has_vechash = false ;
 } ;
 
 struct gb200_result_s
@@ -135,6 +137,7 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
 gb200_status flopcount (const DMat *M, const DMat &A, const DMat &B, DevBuf &flops, DevBuf &cum,
     int64_t *total) ;
 
+gb200_status ensure_vechash (gb200_dmatrix_s *d) ;
 gb200_status launch_mask_pos (const DMat &B, const DMat &M, int64_t *lpos) ;
 
 // Turn per-source-vector results into the final T.  `cum` (nsrc+1) is the cumulative entry count

@@ -75,6 +75,114 @@ __global__ void dot_cnt_rect_kernel (const int64_t *__restrict__ pos, int64_t an
         t += (int64_t) gridDim.x * blockDim.x) cnt [t] = pos [(t + 1) * anvec] - pos [t * anvec] ;
 }
 
+constexpr int64_t DOTG_CHUNK = 256 ;        // tasks per work item of dotg_kernel
+
+// per mask entry: which vector owns the pair and how long the walk is.  own = 1: B(:,j) owns and
+// A(:,i) is walked (wl > 0); A-owned pairs have wl < 0 and are counted per vector of A; dead: wl = 0
+__global__ void dotg_classify_kernel (DMat A, DMat B, DMat M, const int32_t *__restrict__ mvec,
+    int64_t mnz, uint8_t *__restrict__ own, int32_t *__restrict__ wl,
+    unsigned long long *__restrict__ cntA)
+{
+    for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; e < mnz ;
+        e += (int64_t) gridDim.x * blockDim.x)
+    {
+        uint8_t o = 0 ;
+        int32_t w = 0 ;
+        const int64_t ka = dm_vecpos (A, M.i [e]) ;
+        const int64_t kb = dm_vecpos (B, dm_vecname (M, mvec [e])) ;
+        if (ka >= 0 && kb >= 0)
+        {
+            const int64_t ainz = A.p [ka+1] - A.p [ka], bjnz = B.p [kb+1] - B.p [kb] ;
+            if (ainz > 0 && bjnz > 0)
+            {
+                if (dot_walkA (ainz, bjnz, A.vlen)) { o = 1 ; w = (int32_t) ainz ; }
+                else { w = -(int32_t) bjnz ; atomicAdd (cntA + ka, 1ULL) ; }
+            }
+        }
+        own [e] = o ;
+        wl [e] = w ;
+    }
+}
+
+// plist [0..n0) = B-owned entries in mask order; plist [n0..) = A-owned entries grouped by vector of A
+__global__ void dotg_lists_kernel (DMat A, DMat M, const uint8_t *__restrict__ own,
+    const int32_t *__restrict__ wl, int64_t mnz, const int64_t *__restrict__ pos0,
+    const int64_t *__restrict__ offA, unsigned long long *__restrict__ curA, int64_t n0,
+    int32_t *__restrict__ plist)
+{
+    for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; e < mnz ;
+        e += (int64_t) gridDim.x * blockDim.x)
+    {
+        if (own [e]) plist [pos0 [e]] = (int32_t) e ;
+        else if (wl [e] < 0)
+        {
+            const int64_t ka = dm_vecpos (A, M.i [e]) ;
+            plist [n0 + offA [ka] + (int64_t) atomicAdd (curA + ka, 1ULL)] = (int32_t) e ;
+        }
+    }
+}
+
+__global__ void dotg_ntask_kernel (const int32_t *__restrict__ pl, int64_t np,
+    const int32_t *__restrict__ wl, int64_t *__restrict__ nt)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < np ;
+        t += (int64_t) gridDim.x * blockDim.x)
+    {
+        int32_t w = wl [pl [t]] ;
+        if (w < 0) w = -w ;
+        nt [t] = (w + DOTG_SEG - 1) / DOTG_SEG ;
+    }
+}
+
+__global__ void dotg_tasks_kernel (DMat A, DMat B, DMat M, const int32_t *__restrict__ mvec,
+    int orient, const int32_t *__restrict__ pl, int64_t np, const int32_t *__restrict__ wl,
+    const int64_t *__restrict__ toff, DotTask *__restrict__ tasks)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < np ;
+        t += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int32_t e = pl [t] ;
+        int32_t w = wl [e] ;
+        if (w < 0) w = -w ;
+        int64_t w0 ;
+        if (orient) w0 = B.p [dm_vecpos (B, dm_vecname (M, mvec [e]))] ;       // walk B(:,j)
+        else w0 = A.p [dm_vecpos (A, M.i [e])] ;                               // walk A(:,i)
+        int64_t q = toff [t] ;
+        const bool split = (w > DOTG_SEG) ;
+        for (int32_t s0 = 0 ; s0 < w ; s0 += DOTG_SEG, q++)
+        {
+            DotTask tk ;
+            const int32_t len = (w - s0 < DOTG_SEG) ? (w - s0) : DOTG_SEG ;
+            tk.e = e ; tk.len = split ? -len : len ; tk.w0 = w0 + s0 ;
+            tasks [q] = tk ;
+        }
+    }
+}
+
+__global__ void dotg_nchunks_kernel (const int64_t *__restrict__ start, int64_t n, int64_t ch,
+    int64_t *__restrict__ nch)
+{
+    for (int64_t v = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; v < n ;
+        v += (int64_t) gridDim.x * blockDim.x) nch [v] = (start [v+1] - start [v] + ch - 1) / ch ;
+}
+
+__global__ void dotg_items_kernel (const int64_t *__restrict__ start, const int64_t *__restrict__ ioff,
+    int64_t n, int64_t ch, DotItem *__restrict__ items)
+{
+    for (int64_t v = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; v < n ;
+        v += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t s0 = start [v], s1 = start [v+1] ;
+        int64_t q = ioff [v] ;
+        for (int64_t e0 = s0 ; e0 < s1 ; e0 += ch, q++)
+        {
+            DotItem it ;
+            it.owner = (int32_t) v ; it.pad = 0 ; it.e0 = e0 ; it.e1 = (e0 + ch < s1) ? (e0 + ch) : s1 ;
+            items [q] = it ;
+        }
+    }
+}
+
 static int pick_group (double len)
 {
     int G = 1 ;
@@ -86,6 +194,12 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
     const gb200_dmatrix_s *Ad, const gb200_dmatrix_s *Bd, const gb200_semiring &s)
 {
     Ctx &c = ctx () ;
+    if (M != nullptr && !mask_comp)
+    {
+        // the masked kernel probes long vectors through their hash index (cached on the handle)
+        GB200_TRY (ensure_vechash (const_cast<gb200_dmatrix_s *> (Ad))) ;
+        GB200_TRY (ensure_vechash (const_cast<gb200_dmatrix_s *> (Bd))) ;
+    }
     const DMat &A = Ad->v ;
     const DMat &B = Bd->v ;
     const int64_t cvlen = A.vdim, cvdim = B.vdim ;
@@ -130,18 +244,95 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
         GB200_TRY (vals.alloc ((size_t) (mnz > 0 ? mnz : 1) * acc_size)) ;
         GB200_TRY (flags.alloc (mnz > 0 ? mnz : 1)) ;
         GB200_TRY (pos.alloc ((mnz + 1) * sizeof (int64_t))) ;
+        GB200_CUDA (cudaMemsetAsync (flags.ptr, 0, flags.bytes, c.stream)) ;
+        if (mnz >= (int64_t) INT32_MAX) { set_error ("mask with >= 2^31 entries") ; return GB200_NOT_SUPPORTED ; }
         if (mnz > 0)
         {
+            int asz = 0 ;
+            const uint64_t ident = identity_bits (s.z_code, s.add_opcode, &asz) ;
+            GB200_TRY (fill_bits (vals.ptr, acc_size, ident, mnz)) ;
             expand_vec_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (Mv.p, Mv.nvec,
                 mnz, mvec.as<int32_t> ()) ;
             count_launch () ;
-            da.mode = DOT_MASK ; da.mvec = mvec.as<int32_t> () ; da.npairs = mnz ;
-            da.vals = vals.ptr ; da.flags = flags.as<uint8_t> () ;
-            da.G = pick_group ((avgA < avgB) ? avgA : avgB) ;
-            const int64_t gpb = 256 / da.G ;
-            if (!launch_typed (s.xy_code, FAM_DOT, s.z_code, s.add_opcode, s.mult_opcode, &da,
-                grid_cap ((mnz + gpb - 1) / gpb, 16), 256))
-            { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+            // ---- split the pairs by owner (the longer vector); regroup the A-owned ones by i -------
+            const int64_t anvec = A.nvec ;
+            DevBuf own, wl, cntA, offA, curA, pos0, off0, plist ;
+            GB200_TRY (own.alloc (mnz)) ;
+            GB200_TRY (wl.alloc (mnz * sizeof (int32_t))) ;
+            GB200_TRY (cntA.alloc ((anvec > 0 ? anvec : 1) * sizeof (int64_t))) ;
+            GB200_TRY (curA.alloc ((anvec > 0 ? anvec : 1) * sizeof (int64_t))) ;
+            GB200_TRY (offA.alloc ((anvec + 1) * sizeof (int64_t))) ;
+            GB200_TRY (pos0.alloc ((mnz + 1) * sizeof (int64_t))) ;
+            GB200_TRY (off0.alloc ((Mv.nvec + 1) * sizeof (int64_t))) ;
+            GB200_TRY (plist.alloc (mnz * sizeof (int32_t))) ;
+            GB200_CUDA (cudaMemsetAsync (cntA.ptr, 0, cntA.bytes, c.stream)) ;
+            GB200_CUDA (cudaMemsetAsync (curA.ptr, 0, curA.bytes, c.stream)) ;
+            dotg_classify_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, B, Mv,
+                mvec.as<int32_t> (), mnz, own.as<uint8_t> (), wl.as<int32_t> (),
+                cntA.as<unsigned long long> ()) ;
+            count_launch () ;
+            // B-owned pairs keep the mask's order (a compaction); A-owned pairs: counting sort by i
+            GB200_TRY (scan_u8 (own.as<uint8_t> (), pos0.as<int64_t> (), mnz)) ;
+            GB200_TRY (scan_i64 (cntA.as<int64_t> (), offA.as<int64_t> (), anvec)) ;
+            int64_t n0 = 0, n1 = 0 ;
+            GB200_TRY (read_i64 (pos0.as<int64_t> () + mnz, &n0)) ;
+            GB200_TRY (read_i64 (offA.as<int64_t> () + anvec, &n1)) ;
+            dotg_lists_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, Mv,
+                own.as<uint8_t> (), wl.as<int32_t> (), mnz, pos0.as<int64_t> (), offA.as<int64_t> (),
+                curA.as<unsigned long long> (), n0, plist.as<int32_t> ()) ;
+            dot_cum_list_kernel <<<grid_cap ((Mv.nvec + 256) / 256, 8), 256, 0, c.stream>>> (Mv.p,
+                pos0.as<int64_t> (), Mv.nvec, off0.as<int64_t> ()) ;
+            count_launch (2) ;
+            DotGArgs ga ;
+            memset (&ga, 0, sizeof (ga)) ;
+            ga.A = A ; ga.B = B ; ga.M = Mv ;
+            ga.vals = vals.ptr ; ga.flags = flags.as<uint8_t> () ;
+            ga.nmatch = nmatch.as<unsigned long long> () ;
+            ga.mult_op = s.mult_opcode ; ga.flip = s.flipxy ;
+            for (int orient = 0 ; orient < 2 ; orient++)
+            {
+                const int64_t np = orient ? n1 : n0 ;           // pairs of this orientation
+                if (np == 0) continue ;
+                const int32_t *pl = plist.as<int32_t> () + (orient ? n0 : 0) ;
+                const int64_t *off = orient ? offA.as<int64_t> () : off0.as<int64_t> () ;
+                const int64_t nown = orient ? anvec : Mv.nvec ;
+                // tasks: one per pair, or one per DOTG_SEG-long segment of a long walk
+                DevBuf nt, toff, tasks, otoff, nch, ioff, items ;
+                GB200_TRY (nt.alloc (np * sizeof (int64_t))) ;
+                GB200_TRY (toff.alloc ((np + 1) * sizeof (int64_t))) ;
+                dotg_ntask_kernel <<<grid_cap ((np + 255) / 256, 16), 256, 0, c.stream>>> (pl, np,
+                    wl.as<int32_t> (), nt.as<int64_t> ()) ;
+                count_launch () ;
+                GB200_TRY (scan_i64 (nt.as<int64_t> (), toff.as<int64_t> (), np)) ;
+                int64_t ntasks = 0 ;
+                GB200_TRY (read_i64 (toff.as<int64_t> () + np, &ntasks)) ;
+                GB200_TRY (tasks.alloc (ntasks * sizeof (DotTask))) ;
+                dotg_tasks_kernel <<<grid_cap ((np + 255) / 256, 16), 256, 0, c.stream>>> (A, B, Mv,
+                    mvec.as<int32_t> (), orient, pl, np, wl.as<int32_t> (), toff.as<int64_t> (),
+                    tasks.as<DotTask> ()) ;
+                // task range of every owner, cut into work items
+                GB200_TRY (otoff.alloc ((nown + 1) * sizeof (int64_t))) ;
+                GB200_TRY (nch.alloc ((nown > 0 ? nown : 1) * sizeof (int64_t))) ;
+                GB200_TRY (ioff.alloc ((nown + 1) * sizeof (int64_t))) ;
+                dot_cum_list_kernel <<<grid_cap ((nown + 256) / 256, 8), 256, 0, c.stream>>> (off,
+                    toff.as<int64_t> (), nown, otoff.as<int64_t> ()) ;
+                dotg_nchunks_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
+                    otoff.as<int64_t> (), nown, DOTG_CHUNK, nch.as<int64_t> ()) ;
+                count_launch (3) ;
+                GB200_TRY (scan_i64 (nch.as<int64_t> (), ioff.as<int64_t> (), nown)) ;
+                int64_t nitems = 0 ;
+                GB200_TRY (read_i64 (ioff.as<int64_t> () + nown, &nitems)) ;
+                if (nitems == 0) continue ;
+                GB200_TRY (items.alloc (nitems * sizeof (DotItem))) ;
+                dotg_items_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
+                    otoff.as<int64_t> (), ioff.as<int64_t> (), nown, DOTG_CHUNK, items.as<DotItem> ()) ;
+                count_launch () ;
+                ga.tasks = tasks.as<DotTask> () ;
+                ga.items = items.as<DotItem> () ; ga.nitems = nitems ; ga.orient = orient ;
+                if (!launch_typed (s.xy_code, FAM_DOTG, s.z_code, s.add_opcode, s.mult_opcode, &ga,
+                    grid_cap (nitems, 3), DOTG_THREADS))
+                { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+            }
         }
         GB200_TRY (scan_u8 (flags.as<uint8_t> (), pos.as<int64_t> (), mnz)) ;
         GB200_TRY (read_i64 (pos.as<int64_t> () + mnz, &cnz)) ;

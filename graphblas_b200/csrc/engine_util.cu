@@ -245,6 +245,93 @@ __global__ void remap_ptr_kernel (const int64_t *__restrict__ p, const int64_t *
         t += (int64_t) gridDim.x * blockDim.x) p2 [t] = pos [p [t]] ;
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-vector hash index for the dot kernels (see DMat in common.cuh)
+// ---------------------------------------------------------------------------------------------
+__global__ void vh_size_kernel (const int64_t *__restrict__ p, int64_t nvec, int64_t *__restrict__ sz)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nvec ;
+        t += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t len = p [t+1] - p [t] ;
+        int64_t s = 0 ;
+        if (len > VECHASH_MIN) { s = 1 ; while (s < 2 * len) s <<= 1 ; }
+        sz [t] = s ;
+    }
+}
+
+__global__ void vh_info_kernel (const int64_t *__restrict__ sz, const int64_t *__restrict__ off,
+    int64_t nvec, int64_t *__restrict__ hinfo)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nvec ;
+        t += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t s = sz [t] ;
+        int lg = 0 ; while ((1LL << lg) < s) lg++ ;
+        hinfo [t] = (s == 0) ? -1 : ((off [t] << 6) | lg) ;
+    }
+}
+
+// one block per long vector
+__global__ void vh_fill_kernel (const int64_t *__restrict__ p, const int32_t *__restrict__ idx,
+    const int64_t *__restrict__ hinfo, int64_t nvec, int32_t *__restrict__ hkeys,
+    int32_t *__restrict__ hofs)
+{
+    for (int64_t v = blockIdx.x ; v < nvec ; v += gridDim.x)
+    {
+        const int64_t hi = hinfo [v] ;
+        if (hi < 0) continue ;
+        const int lg = (int) (hi & 63) ;
+        const int64_t off = hi >> 6 ;
+        const uint32_t mask = (1u << lg) - 1u ;
+        const int64_t p0 = p [v], p1 = p [v+1] ;
+        for (int64_t q = p0 + threadIdx.x ; q < p1 ; q += blockDim.x)
+        {
+            const int32_t key = idx [q] ;
+            uint32_t h = ((uint32_t) key * 0x9E3779B1u) >> (32 - lg) ;
+            while (atomicCAS (hkeys + off + h, -1, key) != -1) h = (h + 1) & mask ;
+            hofs [off + h] = (int32_t) (q - p0) ;
+        }
+    }
+}
+
+gb200_status ensure_vechash (gb200_dmatrix_s *d)
+{
+    if (d->has_vechash) return GB200_SUCCESS ;
+    Ctx &c = ctx () ;
+    const int64_t nvec = d->v.nvec ;
+    DevBuf sz, off ;
+    GB200_TRY (sz.alloc ((nvec > 0 ? nvec : 1) * sizeof (int64_t))) ;
+    GB200_TRY (off.alloc ((nvec + 1) * sizeof (int64_t))) ;
+    GB200_TRY (d->hinfo.alloc ((nvec > 0 ? nvec : 1) * sizeof (int64_t))) ;
+    if (nvec > 0)
+    {
+        vh_size_kernel <<<grid_for (nvec), 256, 0, c.stream>>> (d->v.p, nvec, sz.as<int64_t> ()) ;
+        count_launch () ;
+    }
+    GB200_TRY (scan_i64 (sz.as<int64_t> (), off.as<int64_t> (), nvec)) ;
+    int64_t total = 0 ;
+    GB200_TRY (read_i64 (off.as<int64_t> () + nvec, &total)) ;
+    GB200_TRY (d->hkeys.alloc ((size_t) (total > 0 ? total : 1) * sizeof (int32_t))) ;
+    GB200_TRY (d->hofs.alloc ((size_t) (total > 0 ? total : 1) * sizeof (int32_t))) ;
+    if (nvec > 0)
+    {
+        GB200_CUDA (cudaMemsetAsync (d->hkeys.ptr, 0xFF, (size_t) (total > 0 ? total : 1) * sizeof (int32_t), c.stream)) ;
+        vh_info_kernel <<<grid_for (nvec), 256, 0, c.stream>>> (sz.as<int64_t> (), off.as<int64_t> (),
+            nvec, d->hinfo.as<int64_t> ()) ;
+        if (total > 0)
+            vh_fill_kernel <<<grid_for (nvec * 256, 256, 16), 256, 0, c.stream>>> (d->v.p, d->v.i,
+                d->hinfo.as<int64_t> (), nvec, d->hkeys.as<int32_t> (), d->hofs.as<int32_t> ()) ;
+        count_launch (2) ;
+    }
+    GB200_CUDA (cudaGetLastError ()) ;
+    d->v.hinfo = d->hinfo.as<int64_t> () ;
+    d->v.hkeys = d->hkeys.as<int32_t> () ;
+    d->v.hofs = d->hofs.as<int32_t> () ;
+    d->has_vechash = true ;
+    return GB200_SUCCESS ;
+}
+
 gb200_status filter_mask (const gb200_dmatrix_s *M, DMat &Mview, DevBuf &Mp2, DevBuf &Mi2)
 {
     Ctx &c = ctx () ;
@@ -275,6 +362,7 @@ gb200_status filter_mask (const gb200_dmatrix_s *M, DMat &Mview, DevBuf &Mp2, De
     Mview.i = Mi2.as<int32_t> () ;
     Mview.nnz = n - nfalse ;
     Mview.x = nullptr ;
+    Mview.hinfo = nullptr ; Mview.hkeys = nullptr ; Mview.hofs = nullptr ;
     return GB200_SUCCESS ;
 }
 

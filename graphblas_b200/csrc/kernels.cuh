@@ -283,9 +283,165 @@ __global__ void dot_kernel (DotArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// masked dot products, C<M> = A'*B, grouped by the LONGER vector of each pair ("owner").
+//
+// For a mask entry (i,j) the shorter of A(:,i), B(:,j) is walked and the longer one is probed.  On a
+// power-law graph the walked lengths sum to ~10x the number of matches, so the probes must not go
+// to DRAM: pairs are grouped by their owner vector, a thread block loads the owner into a
+// shared-memory hash table once and then serves every task of its work item from it (owners longer
+// than DOTG_CAP are probed through their global hash index, which stays L2-resident because all
+// work items of one owner run back to back).  orient 0: owner = B(:,j); orient 1: owner = A(:,i)
+// (the mask entries regrouped by i).  A TASK is one pair, or one DOTG_SEG-long segment of a pair
+// whose walked list is longer than that (segments are combined with the monoid's atomic); the warps
+// of a block pull tasks from a shared counter, so one long pair cannot stall a block.
+// ---------------------------------------------------------------------------------------------
+constexpr int DOTG_SLOTS = 8192 ;           // shared-memory hash slots per block (64 KB)
+constexpr int DOTG_CAP = 4096 ;             // owners up to this long use the shared-memory table
+constexpr int DOTG_SEG = 1024 ;             // longest walk of one task
+constexpr int DOTG_THREADS = 512 ;
+
+struct DotItem { int32_t owner ; int32_t pad ; int64_t e0, e1 ; } ;        // owner, task range
+struct DotTask { int32_t e ; int32_t len ; int64_t w0 ; } ;                // len < 0: segment of a split pair
+
+struct DotGArgs
+{
+    DMat A, B, M ;
+    const DotTask *tasks ;
+    const DotItem *items ;
+    int64_t nitems ;
+    int orient ;
+    void *vals ;                // pre-set to the monoid identity
+    uint8_t *flags ;            // pre-zeroed
+    unsigned long long *nmatch ;
+    int mult_op ; int flip ;
+} ;
+
+// stored-vector position of vector `name`, or -1
+__device__ __forceinline__ int64_t dm_vecpos (const DMat &A, int64_t name)
+{
+    if (!A.hyper) return name ;
+    int64_t lo = 0, hi = A.nvec - 1 ;
+    while (lo <= hi)
+    {
+        const int64_t mid = (lo + hi) >> 1, hv = __ldg (A.h + mid) ;
+        if (hv == name) return mid ;
+        if (hv < name) lo = mid + 1 ; else hi = mid - 1 ;
+    }
+    return -1 ;
+}
+
+// true: walk A(:,i) and probe B(:,j) (owner B); false: walk B(:,j) and probe A(:,i) (owner A)
+__device__ __forceinline__ bool dot_walkA (int64_t ainz, int64_t bjnz, int64_t vlen)
+{
+    return (bjnz == vlen) || (ainz != vlen && ainz <= bjnz) ;
+}
+
+template <class S>
+__global__ void __launch_bounds__ (DOTG_THREADS, 3)
+dotg_kernel (DotGArgs a)
+{
+    using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
+    extern __shared__ int32_t dotg_sm [] ;
+    int32_t *tkeys = dotg_sm ;
+    int32_t *tpos = dotg_sm + DOTG_SLOTS ;
+    __shared__ int s_next ;
+    const S sr (a.mult_op, a.flip != 0) ;
+    const T *__restrict__ Ax = (const T *) a.A.x ;
+    const T *__restrict__ Bx = (const T *) a.B.x ;
+    acc_t *__restrict__ vals = (acc_t *) a.vals ;
+    const int lane = threadIdx.x & 31 ;
+    const DMat &O = a.orient ? a.A : a.B ;      // owner matrix (probed)
+    const DMat &W = a.orient ? a.B : a.A ;      // walked matrix
+    const int32_t *__restrict__ Wi = W.i ;
+    const int64_t vlen = a.A.vlen ;
+    unsigned long long nm = 0 ;
+    for (int64_t it = blockIdx.x ; it < a.nitems ; it += gridDim.x)
+    {
+        const DotItem item = a.items [it] ;
+        // ---- the owner vector ---------------------------------------------------------------
+        int64_t ko = item.owner ;
+        if (!a.orient) ko = dm_vecpos (a.B, dm_vecname (a.M, item.owner)) ;
+        const int64_t o0 = __ldg (O.p + ko), o1 = __ldg (O.p + ko + 1) ;
+        const int64_t olen = o1 - o0 ;
+        const int mode = (olen == vlen) ? 0 : ((olen <= DOTG_CAP) ? 1 : 2) ;
+        const int64_t ohinfo = (mode == 2) ? __ldg (O.hinfo + ko) : -1 ;
+        __syncthreads () ;                          // previous item's probes and counter are done
+        if (threadIdx.x == 0) s_next = 0 ;
+        if (mode == 1)
+        {
+            for (int t = threadIdx.x ; t < DOTG_SLOTS ; t += blockDim.x) tkeys [t] = -1 ;
+            __syncthreads () ;
+            for (int64_t q = o0 + threadIdx.x ; q < o1 ; q += blockDim.x)
+            {
+                const int32_t key = __ldg (O.i + q) ;
+                uint32_t h = hash32 ((uint32_t) key) >> 19 ;          // 13 bits
+                while (atomicCAS (tkeys + h, -1, key) != -1) h = (h + 1) & (DOTG_SLOTS - 1) ;
+                tpos [h] = (int32_t) (q - o0) ;
+            }
+        }
+        __syncthreads () ;
+        // ---- tasks of this item: warps pull them from a shared counter -----------------------
+        const int ntask = (int) (item.e1 - item.e0) ;
+        while (true)
+        {
+            int tk = 0 ;
+            if (lane == 0) tk = atomicAdd (&s_next, 1) ;
+            tk = __shfl_sync (0xffffffffu, tk, 0) ;
+            if (tk >= ntask) break ;
+            const DotTask task = a.tasks [item.e0 + tk] ;
+            const bool split = (task.len < 0) ;
+            const int64_t w0 = task.w0, w1 = task.w0 + (split ? -task.len : task.len) ;
+            acc_t cij = Mon::identity () ;
+            bool found = false ;
+            for (int64_t p = w0 + lane ; p < w1 ; p += 32)
+            {
+                const int32_t k = __ldg (Wi + p) ;
+                int64_t pos = -1 ;
+                if (mode == 0) pos = o0 + k ;
+                else if (mode == 1)
+                {
+                    uint32_t h = hash32 ((uint32_t) k) >> 19 ;
+                    while (true)
+                    {
+                        const int32_t kk = tkeys [h] ;
+                        if (kk == k) { pos = o0 + tpos [h] ; break ; }
+                        if (kk < 0) break ;
+                        h = (h + 1) & (DOTG_SLOTS - 1) ;
+                    }
+                }
+                else pos = vechash_probe (O, ohinfo, o0, k) ;
+                if (pos >= 0)
+                {
+                    const acc_t prod = a.orient ? sr.product (Ax [pos], Bx [p]) : sr.product (Ax [p], Bx [pos]) ;
+                    cij = found ? Mon::combine (cij, prod) : prod ;
+                    found = true ; nm++ ;
+                    if (Mon::has_terminal () && Mon::is_terminal (cij)) break ;
+                }
+            }
+            const unsigned fm = __ballot_sync (0xffffffffu, found) ;
+            if (fm == 0) continue ;                 // flags [e] stays 0
+            if (!found) cij = Mon::identity () ;
+            for (int off = 16 ; off > 0 ; off >>= 1)
+            {
+                const acc_t other = __shfl_down_sync (0xffffffffu, cij, off) ;
+                cij = Mon::combine (cij, other) ;
+            }
+            if (lane == 0)
+            {
+                if (split) Mon::atomic_combine (vals + task.e, cij) ;
+                else vals [task.e] = cij ;
+                a.flags [task.e] = 1 ;
+            }
+        }
+    }
+    for (int off = 16 ; off > 0 ; off >>= 1) nm += __shfl_down_sync (0xffffffffu, nm, off) ;
+    if (lane == 0 && nm) atomicAdd (a.nmatch, nm) ;
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers, one set per (xy type); defined in inst_*.cu through GB200_INSTANTIATE_TYPE
 // ---------------------------------------------------------------------------------------------
-enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2 } ;
+enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -300,6 +456,17 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
         saxpy_light_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyArgs *) args) ;
     else if (family == FAM_SAXPY_HEAVY)
         saxpy_heavy_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyArgs *) args) ;
+    else if (family == FAM_DOTG)
+    {
+        const int smem = 2 * DOTG_SLOTS * (int) sizeof (int32_t) ;
+        static bool attr_set = false ;          // one flag per instantiation
+        if (!attr_set)
+        {
+            cudaFuncSetAttribute (dotg_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ;
+            attr_set = true ;
+        }
+        dotg_kernel<S> <<<cfg.grid, cfg.block, smem, cfg.stream>>> (*(const DotGArgs *) args) ;
+    }
     else
         dot_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotArgs *) args) ;
 }
