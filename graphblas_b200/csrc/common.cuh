@@ -86,6 +86,7 @@ __device__ __forceinline__ int64_t bsearch_i32 (const int32_t *__restrict__ idx,
 }
 
 __device__ __forceinline__ uint32_t hash32 (uint32_t k) { return k * 0x9E3779B1u ; }
+__device__ __forceinline__ uint32_t hash32b (uint32_t k) { return (k ^ (k >> 15)) * 0x85EBCA6Bu ; }
 
 // one work item of a heavy column: B entries [pb0,pb1) of stored vector kk, workspace slot w
 struct HeavyItem { int32_t kk ; int32_t w ; int64_t pb0 ; int64_t pb1 ; } ;

@@ -159,20 +159,39 @@ __global__ void dotg_tasks_kernel (DMat A, DMat B, DMat M, const int32_t *__rest
     }
 }
 
-__global__ void dotg_nchunks_kernel (const int64_t *__restrict__ start, int64_t n, int64_t ch,
-    int64_t *__restrict__ nch)
+__device__ int64_t g_giant_mult = 4 ;
+
+// tasks per work item: giant owners (Bloom filter of 64 KB to build per item) get bigger items
+__device__ __forceinline__ int64_t dotg_chunk_of (const DMat &O, const DMat &M, int orient, int64_t v)
 {
-    for (int64_t v = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; v < n ;
-        v += (int64_t) gridDim.x * blockDim.x) nch [v] = (start [v+1] - start [v] + ch - 1) / ch ;
+    int64_t ko = v ;
+    if (!orient) ko = dm_vecpos (O, dm_vecname (M, v)) ;
+    if (ko < 0) return DOTG_CHUNK ;
+    const int64_t olen = O.p [ko+1] - O.p [ko] ;
+    return (olen > DOTG_CAP) ? g_giant_mult * DOTG_CHUNK : DOTG_CHUNK ;
 }
 
-__global__ void dotg_items_kernel (const int64_t *__restrict__ start, const int64_t *__restrict__ ioff,
-    int64_t n, int64_t ch, DotItem *__restrict__ items)
+__global__ void dotg_nchunks_kernel (DMat O, DMat M, int orient, const int64_t *__restrict__ start,
+    int64_t n, int64_t *__restrict__ nch)
+{
+    for (int64_t v = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; v < n ;
+        v += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t cnt = start [v+1] - start [v] ;
+        const int64_t ch = (cnt > 0) ? dotg_chunk_of (O, M, orient, v) : 1 ;
+        nch [v] = (cnt + ch - 1) / ch ;
+    }
+}
+
+__global__ void dotg_items_kernel (DMat O, DMat M, int orient, const int64_t *__restrict__ start,
+    const int64_t *__restrict__ ioff, int64_t n, DotItem *__restrict__ items)
 {
     for (int64_t v = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; v < n ;
         v += (int64_t) gridDim.x * blockDim.x)
     {
         const int64_t s0 = start [v], s1 = start [v+1] ;
+        if (s1 <= s0) continue ;
+        const int64_t ch = dotg_chunk_of (O, M, orient, v) ;
         int64_t q = ioff [v] ;
         for (int64_t e0 = s0 ; e0 < s1 ; e0 += ch, q++)
         {
@@ -285,6 +304,15 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             count_launch (2) ;
             DotGArgs ga ;
             memset (&ga, 0, sizeof (ga)) ;
+            DevBuf next_item ;
+            GB200_TRY (next_item.alloc (16)) ;
+            ga.next_item = next_item.as<unsigned long long> () ;
+            ga.use_bloom = getenv ("GB200_DOTG_BLOOM") ? atoi (getenv ("GB200_DOTG_BLOOM")) : 1 ;
+            {
+                const int64_t gm = getenv ("GB200_DOTG_GIANT") ? atoll (getenv ("GB200_DOTG_GIANT")) : 4 ;
+                GB200_CUDA (cudaMemcpyToSymbolAsync (g_giant_mult, &gm, sizeof (gm), 0,
+                    cudaMemcpyHostToDevice, c.stream)) ;
+            }
             ga.A = A ; ga.B = B ; ga.M = Mv ;
             ga.vals = vals.ptr ; ga.flags = flags.as<uint8_t> () ;
             ga.nmatch = nmatch.as<unsigned long long> () ;
@@ -317,7 +345,7 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 dot_cum_list_kernel <<<grid_cap ((nown + 256) / 256, 8), 256, 0, c.stream>>> (off,
                     toff.as<int64_t> (), nown, otoff.as<int64_t> ()) ;
                 dotg_nchunks_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                    otoff.as<int64_t> (), nown, DOTG_CHUNK, nch.as<int64_t> ()) ;
+                    orient ? A : B, Mv, orient, otoff.as<int64_t> (), nown, nch.as<int64_t> ()) ;
                 count_launch (3) ;
                 GB200_TRY (scan_i64 (nch.as<int64_t> (), ioff.as<int64_t> (), nown)) ;
                 int64_t nitems = 0 ;
@@ -325,8 +353,10 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 if (nitems == 0) continue ;
                 GB200_TRY (items.alloc (nitems * sizeof (DotItem))) ;
                 dotg_items_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                    otoff.as<int64_t> (), ioff.as<int64_t> (), nown, DOTG_CHUNK, items.as<DotItem> ()) ;
+                    orient ? A : B, Mv, orient, otoff.as<int64_t> (), ioff.as<int64_t> (), nown,
+                    items.as<DotItem> ()) ;
                 count_launch () ;
+                GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 16, c.stream)) ;
                 ga.tasks = tasks.as<DotTask> () ;
                 ga.items = items.as<DotItem> () ; ga.nitems = nitems ; ga.orient = orient ;
                 if (!launch_typed (s.xy_code, FAM_DOTG, s.z_code, s.add_opcode, s.mult_opcode, &ga,

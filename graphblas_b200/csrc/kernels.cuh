@@ -313,6 +313,8 @@ struct DotGArgs
     void *vals ;                // pre-set to the monoid identity
     uint8_t *flags ;            // pre-zeroed
     unsigned long long *nmatch ;
+    unsigned long long *next_item ;     // dynamic work-item counter (zeroed before launch)
+    int use_bloom ;
     int mult_op ; int flip ;
 } ;
 
@@ -355,8 +357,15 @@ dotg_kernel (DotGArgs a)
     const int32_t *__restrict__ Wi = W.i ;
     const int64_t vlen = a.A.vlen ;
     unsigned long long nm = 0 ;
-    for (int64_t it = blockIdx.x ; it < a.nitems ; it += gridDim.x)
+    __shared__ unsigned long long s_item ;
+    while (true)
     {
+        // work items vary in cost by orders of magnitude: blocks pull them from a global counter
+        __syncthreads () ;
+        if (threadIdx.x == 0) s_item = atomicAdd (a.next_item, 1ULL) ;
+        __syncthreads () ;
+        const int64_t it = (int64_t) s_item ;
+        if (it >= a.nitems) break ;
         const DotItem item = a.items [it] ;
         // ---- the owner vector ---------------------------------------------------------------
         int64_t ko = item.owner ;
@@ -365,18 +374,35 @@ dotg_kernel (DotGArgs a)
         const int64_t olen = o1 - o0 ;
         const int mode = (olen == vlen) ? 0 : ((olen <= DOTG_CAP) ? 1 : 2) ;
         const int64_t ohinfo = (mode == 2) ? __ldg (O.hinfo + ko) : -1 ;
+        // mode 1: table of 4x the owner's length (load <= 0.25 keeps probe sequences short and the
+        // clearing cost proportional to the owner); mode 2: all 64 KB are a Bloom filter in front of
+        // the owner's global hash index, so that most misses never leave the SM
+        int lg = 6 ;
+        while ((1 << lg) < 4 * olen && lg < 13) lg++ ;
+        const uint32_t tmask = (1u << lg) - 1u ;
+        uint32_t *bloom = (uint32_t *) dotg_sm ;
         __syncthreads () ;                          // previous item's probes and counter are done
         if (threadIdx.x == 0) s_next = 0 ;
         if (mode == 1)
         {
-            for (int t = threadIdx.x ; t < DOTG_SLOTS ; t += blockDim.x) tkeys [t] = -1 ;
+            for (int t = threadIdx.x ; t <= (int) tmask ; t += blockDim.x) tkeys [t] = -1 ;
             __syncthreads () ;
             for (int64_t q = o0 + threadIdx.x ; q < o1 ; q += blockDim.x)
             {
                 const int32_t key = __ldg (O.i + q) ;
-                uint32_t h = hash32 ((uint32_t) key) >> 19 ;          // 13 bits
-                while (atomicCAS (tkeys + h, -1, key) != -1) h = (h + 1) & (DOTG_SLOTS - 1) ;
+                uint32_t h = hash32 ((uint32_t) key) >> (32 - lg) ;
+                while (atomicCAS (tkeys + h, -1, key) != -1) h = (h + 1) & tmask ;
                 tpos [h] = (int32_t) (q - o0) ;
+            }
+        }
+        else if (mode == 2 && a.use_bloom)
+        {
+            for (int t = threadIdx.x ; t < 2 * DOTG_SLOTS ; t += blockDim.x) bloom [t] = 0u ;
+            __syncthreads () ;
+            for (int64_t q = o0 + threadIdx.x ; q < o1 ; q += blockDim.x)
+            {
+                const uint32_t b = hash32b ((uint32_t) __ldg (O.i + q)) >> 13 ;    // 19 bits
+                atomicOr (bloom + (b >> 5), 1u << (b & 31)) ;
             }
         }
         __syncthreads () ;
@@ -400,16 +426,20 @@ dotg_kernel (DotGArgs a)
                 if (mode == 0) pos = o0 + k ;
                 else if (mode == 1)
                 {
-                    uint32_t h = hash32 ((uint32_t) k) >> 19 ;
+                    uint32_t h = hash32 ((uint32_t) k) >> (32 - lg) ;
                     while (true)
                     {
                         const int32_t kk = tkeys [h] ;
                         if (kk == k) { pos = o0 + tpos [h] ; break ; }
                         if (kk < 0) break ;
-                        h = (h + 1) & (DOTG_SLOTS - 1) ;
+                        h = (h + 1) & tmask ;
                     }
                 }
-                else pos = vechash_probe (O, ohinfo, o0, k) ;
+                else
+                {
+                    const uint32_t b = hash32b ((uint32_t) k) >> 13 ;
+                    if (!a.use_bloom || ((bloom [b >> 5] >> (b & 31)) & 1u)) pos = vechash_probe (O, ohinfo, o0, k) ;
+                }
                 if (pos >= 0)
                 {
                     const acc_t prod = a.orient ? sr.product (Ax [pos], Bx [p]) : sr.product (Ax [p], Bx [pos]) ;
