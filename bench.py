@@ -161,9 +161,67 @@ def make_workload(args, device):
                       f"{args.ef} nnz/row",
                  M=None, A=Bm, B=Am, mask_comp=False, do_adotb=False,
                  semiring=gb.Semiring("PLUS", "TIMES", "FP64", flipxy=True), dtype="f64", slice="B")
+    elif args.workload == "spgemm_rmat":
+        import gen
+        g = build_rmat(args.scale, args.ef, device, weighted=True)
+        n = g["n"]
+        Am = gb.Matrix(n, n, g["p"].cpu().numpy(), g["cols"].cpu().numpy(), g["w"].cpu().numpy(), None,
+                       "FP64")
+        w.update(name=f"GrB_mxm C=A*A PLUS_TIMES_FP64 (saxpy), RMAT scale {args.scale} edgefactor "
+                      f"{args.ef}, n={n}, nnz(A)={Am.nnz}",
+                 M=None, A=Am, B=Am, mask_comp=False, do_adotb=False,
+                 semiring=gb.Semiring("PLUS", "TIMES", "FP64", flipxy=True), dtype="f64", slice="B")
+    elif args.workload == "sssp":
+        # GrB_mxv (d, NULL, GrB_MIN_FP64, GxB_MIN_PLUS_FP64, A, d, NULL), A CSR: the seam sees
+        # A'*B by dot products with B = d (n x 1, all entries present), SURVEY.md 3.5
+        g = build_rmat(args.scale, args.ef, device, weighted=True)
+        n = g["n"]
+        Am = gb.Matrix(n, n, g["p"].cpu().numpy(), g["cols"].cpu().numpy(), g["w"].cpu().numpy(), None,
+                       "FP64")
+        src = int(np.argmax(np.diff(Am.p)))
+        d = np.full(n, np.inf)
+        d[src] = 0.0
+        # a few relaxation rounds on the host side of the harness so that d is a realistic iterate
+        dv = gb.Matrix(n, 1, np.array([0, n]), np.arange(n), d, None, "FP64")
+        w.update(name=f"GrB_mxv d=A min.+ d MIN_PLUS_FP64 (dot, dense vector), RMAT scale {args.scale} "
+                      f"edgefactor {args.ef}, n={n}, nnz(A)={Am.nnz}, one Bellman-Ford relaxation",
+                 M=None, A=Am, B=dv, mask_comp=False, do_adotb=True,
+                 semiring=gb.Semiring("MIN", "PLUS", "FP64"), dtype="f64", slice="A")
+    elif args.workload == "bfs":
+        # bfs5m level loop (Demo/Source/bfs5m.c:71-82): q<!v> = q*A over LOR_LAND_BOOL, A CSR: the
+        # seam sees A*B by saxpy with B = q (n x 1), M = v complemented, flipxy
+        g = build_rmat(args.scale, args.ef, device)
+        n = g["n"]
+        Am = gb.Matrix(n, n, g["p"].cpu().numpy(), g["cols"].cpu().numpy(),
+                       np.ones(len(g["cols"]), dtype=np.bool_), None, "BOOL")
+        w.update(name=f"BFS level loop GrB_vxm q<!v>=q*A LOR_LAND_BOOL (saxpy, vector), RMAT scale "
+                      f"{args.scale} edgefactor {args.ef}, n={n}, nnz(A)={Am.nnz}",
+                 M=None, A=Am, B=None, mask_comp=True, do_adotb=(args.bfs_dir == "pull"),
+                 semiring=gb.Semiring("LOR", "LAND", "BOOL", flipxy=True), dtype="bool", slice="none",
+                 bfs_source=int(np.argmax(np.diff(Am.p))))
     else:
         raise SystemExit(f"unknown workload {args.workload}")
     return w
+
+
+def bfs_levels(gb, w, dA):
+    """run the level loop once (through the device entry point) and record, per level, the frontier
+    q and the visited vector v that the reference would hand to GB_AxB_parallel"""
+    A = w["A"]
+    n = A.vlen
+    visited = np.zeros(n, dtype=bool)
+    q = np.array([w["bfs_source"]], dtype=np.int64)
+    levels = []
+    while len(q):
+        visited[q] = True
+        vi = np.nonzero(visited)[0]
+        qm = gb.Matrix(n, 1, np.array([0, len(q)]), q, np.ones(len(q), np.bool_), None, "BOOL")
+        vm = gb.Matrix(n, 1, np.array([0, len(vi)]), vi, np.ones(len(vi), np.bool_), None, "BOOL")
+        levels.append((qm, vm))
+        r = gb.axb_device(gb.DMatrix(vm), True, dA, gb.DMatrix(qm), w["semiring"], w["do_adotb"])
+        t = r.matrix.i
+        q = t[~visited[t]] if not r.info["mask_applied"] else t
+    return levels
 
 
 def slice_vectors(m, lo, hi):
@@ -238,7 +296,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="tri", choices=["tri", "spgemm"])
+    ap.add_argument("--workload", default="tri",
+                    choices=["tri", "spgemm", "spgemm_rmat", "sssp", "bfs"])
+    ap.add_argument("--bfs-dir", default="push", choices=["push", "pull"])
     ap.add_argument("--scale", type=int, default=22)
     ap.add_argument("--ef", type=int, default=16)
     ap.add_argument("--cpu-stride", type=int, default=16)
@@ -296,39 +356,61 @@ def main():
     torch.cuda.empty_cache()
     A, B, M = w["A"], w["B"], w["M"]
     dA = gb.DMatrix(A)
-    dB = dA if B is A else gb.DMatrix(B)
-    dM = None
-    if M is not None:
-        dM = dB if M is B else gb.DMatrix(M)
-
-    # flop-balanced contiguous slices of the sliced operand's vectors, one per rank
     sliced_name = w["slice"]
-    sliced = M if sliced_name == "M" else B
-    lo, hi = 0, sliced.nvec
-    if world > 1:
-        if sliced_name == "B":
-            cum, _ = gb.flopcount(dM, dA, dB)
-        else:
-            # masked dot: balance by sum over mask entries of (len A(:,i) + len B(:,j))
-            lenA = np.diff(A.p)
-            lenB = np.diff(B.p)
-            cs = np.concatenate([[0], np.cumsum(lenA[M.i])])
-            per_vec = (cs[M.p[1:]] - cs[M.p[:-1]]) + np.diff(M.p) * lenB
-            cum = np.concatenate([[0], np.cumsum(per_vec)]).astype(np.int64)
-        bounds = gb.partition_by_flops(cum, world)
-        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-        mine = slice_vectors(sliced, lo, hi)
-        dmine = gb.DMatrix(mine)
-        if sliced_name == "M":
-            M, dM = mine, dmine
-        else:
-            B, dB = mine, dmine
+
+    # ---- the multiplies of one step: list of (M, A, B) host triples + their resident handles ----
+    if args.workload == "bfs":
+        if world > 1:
+            raise SystemExit("the vector push step needs an exchange of the frontier (SURVEY.md 8e); "
+                             "bench.py runs it on one GPU")
+        levels = bfs_levels(gb, w, dA)
+        calls = [(vm, A, qm, gb.DMatrix(vm), dA, gb.DMatrix(qm)) for qm, vm in levels]
+        w["name"] += f", {len(levels)} levels from vertex {w['bfs_source']}"
+    else:
+        dB = dA if B is A else gb.DMatrix(B)
+        dM = None
+        if M is not None:
+            dM = dB if M is B else gb.DMatrix(M)
+        # flop-balanced contiguous slices of the sliced operand's vectors, one per rank
+        if world > 1:
+            sliced = {"M": M, "B": B, "A": A}[sliced_name]
+            if sliced_name == "B":
+                cum, _ = gb.flopcount(dM, dA, dB)
+            elif sliced_name == "A":
+                cum = A.p                       # dot with a vector: work of a vector of A = its length
+            else:
+                # masked dot: balance by sum over mask entries of (len A(:,i) + len B(:,j))
+                lenA = np.diff(A.p)
+                lenB = np.diff(B.p)
+                cs = np.concatenate([[0], np.cumsum(lenA[M.i])])
+                per_vec = (cs[M.p[1:]] - cs[M.p[:-1]]) + np.diff(M.p) * lenB
+                cum = np.concatenate([[0], np.cumsum(per_vec)]).astype(np.int64)
+            bounds = gb.partition_by_flops(cum, world)
+            lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+            mine = slice_vectors(sliced, lo, hi)
+            dmine = gb.DMatrix(mine)
+            if sliced_name == "M":
+                M, dM = mine, dmine
+            elif sliced_name == "A":
+                A, dA = mine, dmine
+            else:
+                B, dB = mine, dmine
+        calls = [(M, A, B, dM, dA, dB)]
 
     def step_device():
-        return gb.axb_device(dM, w["mask_comp"], dA, dB, w["semiring"], w["do_adotb"], fetch=False)
+        out = {"flops": 0, "nnz": 0, "device_ms": 0.0, "kernel_ms": 0.0, "nvec": 0}
+        for (_, _, _, dm, da, db) in calls:
+            r = gb.axb_device(dm, w["mask_comp"], da, db, w["semiring"], w["do_adotb"], fetch=False)
+            for k in ("flops", "nnz", "device_ms", "kernel_ms"):
+                out[k] += r.info[k]
+            out["nvec"] += r.info["nvec"] + 1
+        return out
 
     def step_host():
-        return gb.axb_host(M, w["mask_comp"], A, B, w["semiring"], w["do_adotb"], fetch=True)
+        outs = []
+        for (m, a, b, _, _, _) in calls:
+            outs.append(gb.axb_host(m, w["mask_comp"], a, b, w["semiring"], w["do_adotb"], fetch=True))
+        return outs
 
     def barrier():
         torch.cuda.synchronize()
@@ -345,13 +427,13 @@ def main():
         dev_ms, ker_ms = [], []
         for _ in range(args.steps):
             r = step_device()
-            dev_ms.append(r.info["device_ms"])
-            ker_ms.append(r.info["kernel_ms"])
+            dev_ms.append(r["device_ms"])
+            ker_ms.append(r["kernel_ms"])
         torch.cuda.synchronize()
         t_local = time.perf_counter() - t0
     launches = gb.kernel_launches() - launches0
     tt = torch.tensor([t_local, float(np.sum(dev_ms))], dtype=torch.float64, device=device)
-    fl = torch.tensor([r.info["flops"], r.info["nnz"]], dtype=torch.int64, device=device)
+    fl = torch.tensor([r["flops"], r["nnz"]], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(fl, op=dist.ReduceOp.SUM)
@@ -372,19 +454,35 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e = te[0].item() / e2e_steps
-    mats = [m for m in (M, A, B) if m is not None]
-    uniq = {id(m): m for m in mats}.values()
-    h2d = sum(m.p.nbytes + m.i.nbytes + m.x.nbytes + (m.h.nbytes if m.h is not None else 0)
-              for m in uniq)
-    T = rh.matrix
-    d2h = T.p.nbytes + T.i.nbytes + T.x.nbytes + (T.h.nbytes if T.h is not None else 0)
+    h2d = d2h = 0
+    ab = 0
+    for (m, a, b, _, _, _), res in zip(calls, rh):
+        uniq = list({id(x): x for x in (m, a, b) if x is not None}.values())
+        # a complemented mask is not read by the saxpy method (GB_AxB_sequential.c:76-81)
+        read = [x for x in uniq if not (x is m and w["mask_comp"] and not res.info["mask_applied"])]
+        h2d += sum(x.p.nbytes + x.i.nbytes + x.x.nbytes + (x.h.nbytes if x.h is not None else 0)
+                   for x in uniq)
+        T = res.matrix
+        d2h += T.p.nbytes + T.i.nbytes + T.x.nbytes + (T.h.nbytes if T.h is not None else 0)
+        if args.workload == "bfs" and not w["do_adotb"]:
+            # vector push: only the vectors of A named by the frontier are traversed
+            lens = np.diff(a.p)[b.i]
+            ab += 8 * len(a.p) + int(lens.sum()) * (8 + a.x.dtype.itemsize) \
+                + b.nnz * (8 + b.x.dtype.itemsize) + T.nnz * (8 + T.x.dtype.itemsize)
+            ab += sum(x.nnz * (8 + x.x.dtype.itemsize) for x in read if x is m)
+        else:
+            ab += algo_bytes(read, res.info["nvec"], res.info["nnz"], T.x.dtype.itemsize)
 
-    # ---- roofline of the dominant (semiring) kernel, rank 0's slice --------------------------
+    # ---- roofline of the dominant (semiring) kernels, rank 0's slice --------------------------
     peak, peak_src = measured_peak()
-    zsize = T.x.dtype.itemsize
-    ab = algo_bytes(list(uniq), r.info["nvec"], r.info["nnz"], zsize)
     k_ms = float(np.mean(ker_ms))
     achieved = ab / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{args.workload}_s{args.scale}")
+    except Exception:
+        pass
 
     if rank == 0:
         line = {"metric": "GrB_mxm semiring GFLOP/s", "value": gflops, "unit": "GFLOP/s",
@@ -392,10 +490,11 @@ def main():
                 "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
                 "config": {"workload": w["name"], "madds_per_step": madds, "nnz_T": cnz,
+                           "multiplies_per_step": len(calls),
                            "l2": "inputs larger than L2 (no flush needed)" if h2d > 2.6e8 else
                                  "inputs smaller than L2",
                            "partition": f"{world} flop-balanced contiguous slices of "
-                                        f"{'the mask' if sliced_name == 'M' else 'B'}'s vectors"},
+                                        f"{ {'M': 'the mask', 'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors"},
                 "device_ms_per_step": float(np.mean(dev_ms)),
                 "clocks": clk.summary(),
                 "e2e": {"value": 2.0 * madds / t_e2e / 1e9, "unit": "GFLOP/s",
@@ -403,10 +502,11 @@ def main():
                         "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None,
-                             "kernel": "dot_kernel" if w["do_adotb"] else "saxpy_*_kernel",
+                             "frac": achieved / peak, "traffic": traffic,
+                             "kernel": "dotg_kernel/dot_kernel" if w["do_adotb"] else "saxpy_*_kernel",
                              "kernel_ms": k_ms, "algorithmic_bytes": int(ab), "peak_source": peak_src,
-                             "bytes_per_madd": ab / max(r.info["flops"], 1)}}
+                             "bytes_per_madd": ab / max(r["flops"], 1),
+                             "step_algo_gbs": ab / (float(np.mean(dev_ms)) * 1e-3) / 1e9}}
         if world == 1 and not args.no_cpu:
             try:
                 gf, dt, cm, desc = reference_sample(args, w)
