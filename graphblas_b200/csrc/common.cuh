@@ -24,7 +24,16 @@ struct DMat
     const int64_t *hinfo ;
     const int32_t *hkeys ;
     const int32_t *hofs ;
+    // optional 64 KB Bloom filter per long vector (same vectors as the hash index), precomputed so
+    // that a thread block can copy it into shared memory instead of rebuilding it: hbloom +
+    // hbinfo[kk] * BLOOM_WORDS, hbinfo[kk] < 0 (or hbinfo == nullptr): none
+    const int32_t *hbinfo ;
+    const uint32_t *hbloom ;
+    int iso ;               // 1: every stored value equals x[0] (a pattern-only matrix)
 } ;
+
+constexpr int BLOOM_WORDS = 16384 ;         // 2^19 bits
+__device__ __forceinline__ uint32_t bloom_bit (uint32_t k) { return ((k ^ (k >> 15)) * 0x85EBCA6Bu) >> 13 ; }
 
 constexpr int64_t VECHASH_MIN = 4096 ;     // == DOTG_CAP: shorter owners use shared memory
 

@@ -520,8 +520,11 @@ gb200_status gb200_AxB_device (gb200_result *out, gb200_dmatrix M, int mask_comp
     memset (&R->info, 0, sizeof (R->info)) ;
     c.kev_used = 0 ;
     cudaEventRecord (c.ev0, c.stream) ;
-    gb200_status st = do_adotb ? run_dot (R, M, mask_comp, A, B, s)
-                               : run_saxpy (R, M, mask_comp, A, B, s) ;
+    gb200_status st ;
+    if (vec_shape (A, B) && (M == NULL || (M->v.vdim == 1 && M->v.nvec == 1 && !M->v.hyper)))
+        st = do_adotb ? run_dotv (R, M, mask_comp, A, B, s) : run_saxpyv (R, M, mask_comp, A, B, s) ;
+    else
+        st = do_adotb ? run_dot (R, M, mask_comp, A, B, s) : run_saxpy (R, M, mask_comp, A, B, s) ;
     if (st == GB200_SUCCESS)
     {
         cudaEventRecord (c.ev1, c.stream) ;

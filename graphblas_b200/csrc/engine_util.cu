@@ -295,6 +295,76 @@ __global__ void vh_fill_kernel (const int64_t *__restrict__ p, const int32_t *__
     }
 }
 
+// Bloom filters of the long vectors: bidx[v] = rank of v among them (from the scan of `is long`)
+__global__ void vh_binfo_kernel (const int64_t *__restrict__ sz, const int64_t *__restrict__ rank,
+    int64_t nvec, int32_t *__restrict__ binfo)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nvec ;
+        t += (int64_t) gridDim.x * blockDim.x) binfo [t] = (sz [t] > 0) ? (int32_t) rank [t] : -1 ;
+}
+
+__global__ void vh_islong_kernel (const int64_t *__restrict__ sz, int64_t nvec, uint8_t *__restrict__ f)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nvec ;
+        t += (int64_t) gridDim.x * blockDim.x) f [t] = (sz [t] > 0) ? 1 : 0 ;
+}
+
+__global__ void vh_bloom_kernel (const int64_t *__restrict__ p, const int32_t *__restrict__ idx,
+    const int32_t *__restrict__ binfo, int64_t nvec, uint32_t *__restrict__ bloom)
+{
+    for (int64_t v = blockIdx.x ; v < nvec ; v += gridDim.x)
+    {
+        const int32_t b = binfo [v] ;
+        if (b < 0) continue ;
+        uint32_t *bl = bloom + (int64_t) b * BLOOM_WORDS ;
+        for (int64_t q = p [v] + threadIdx.x ; q < p [v+1] ; q += blockDim.x)
+        {
+            const uint32_t h = bloom_bit ((uint32_t) idx [q]) ;
+            atomicOr (bl + (h >> 5), 1u << (h & 31)) ;
+        }
+    }
+}
+
+// are all stored values equal (bytewise) to the first one
+template <class W>
+__global__ void iso_kernel (const W *__restrict__ x, int64_t n, unsigned int *__restrict__ differs)
+{
+    const W x0 = x [0] ;
+    bool d = false ;
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < n ;
+        t += (int64_t) gridDim.x * blockDim.x) d |= (x [t] != x0) ;
+    if (d) *differs = 1u ;
+}
+
+gb200_status ensure_iso (gb200_dmatrix_s *d)
+{
+    if (d->iso_known) return GB200_SUCCESS ;
+    Ctx &c = ctx () ;
+    const int64_t n = d->v.nnz ;
+    d->v.iso = 0 ;
+    if (n > 0)
+    {
+        DevBuf flag ;
+        GB200_TRY (flag.alloc (8)) ;
+        GB200_CUDA (cudaMemsetAsync (flag.ptr, 0, 8, c.stream)) ;
+        const int g = grid_for (n) ;
+        switch (type_size (d->v.type_code))
+        {
+            case 1 : iso_kernel<uint8_t>  <<<g, 256, 0, c.stream>>> ((const uint8_t *)  d->v.x, n, flag.as<unsigned int> ()) ; break ;
+            case 2 : iso_kernel<uint16_t> <<<g, 256, 0, c.stream>>> ((const uint16_t *) d->v.x, n, flag.as<unsigned int> ()) ; break ;
+            case 4 : iso_kernel<uint32_t> <<<g, 256, 0, c.stream>>> ((const uint32_t *) d->v.x, n, flag.as<unsigned int> ()) ; break ;
+            default: iso_kernel<uint64_t> <<<g, 256, 0, c.stream>>> ((const uint64_t *) d->v.x, n, flag.as<unsigned int> ()) ; break ;
+        }
+        count_launch () ;
+        GB200_CUDA (cudaGetLastError ()) ;
+        int64_t differs = 0 ;
+        GB200_TRY (read_i64 (flag.as<int64_t> (), &differs)) ;
+        d->v.iso = (differs == 0) ? 1 : 0 ;
+    }
+    d->iso_known = 1 ;
+    return GB200_SUCCESS ;
+}
+
 gb200_status ensure_vechash (gb200_dmatrix_s *d)
 {
     if (d->has_vechash) return GB200_SUCCESS ;
@@ -328,6 +398,35 @@ gb200_status ensure_vechash (gb200_dmatrix_s *d)
     d->v.hinfo = d->hinfo.as<int64_t> () ;
     d->v.hkeys = d->hkeys.as<int32_t> () ;
     d->v.hofs = d->hofs.as<int32_t> () ;
+    d->v.hbinfo = nullptr ; d->v.hbloom = nullptr ;
+    if (total > 0)
+    {
+        // one precomputed 64 KB Bloom filter per long vector, within a 2 GiB budget
+        DevBuf islong, rank ;
+        GB200_TRY (islong.alloc (nvec)) ;
+        GB200_TRY (rank.alloc ((nvec + 1) * sizeof (int64_t))) ;
+        vh_islong_kernel <<<grid_for (nvec), 256, 0, c.stream>>> (sz.as<int64_t> (), nvec, islong.as<uint8_t> ()) ;
+        count_launch () ;
+        GB200_TRY (scan_u8 (islong.as<uint8_t> (), rank.as<int64_t> (), nvec)) ;
+        int64_t nlong = 0 ;
+        GB200_TRY (read_i64 (rank.as<int64_t> () + nvec, &nlong)) ;
+        const size_t bytes = (size_t) nlong * BLOOM_WORDS * sizeof (uint32_t) ;
+        if (nlong > 0 && bytes <= ((size_t) 2 << 30) && !getenv ("GB200_NO_PREBLOOM"))
+        {
+            GB200_TRY (d->hbinfo.alloc (nvec * sizeof (int32_t))) ;
+            GB200_TRY (d->hbloom.alloc (bytes)) ;
+            GB200_CUDA (cudaMemsetAsync (d->hbloom.ptr, 0, bytes, c.stream)) ;
+            vh_binfo_kernel <<<grid_for (nvec), 256, 0, c.stream>>> (sz.as<int64_t> (), rank.as<int64_t> (),
+                nvec, d->hbinfo.as<int32_t> ()) ;
+            vh_bloom_kernel <<<grid_for (nvec * 256, 256, 16), 256, 0, c.stream>>> (d->v.p, d->v.i,
+                d->hbinfo.as<int32_t> (), nvec, d->hbloom.as<uint32_t> ()) ;
+            count_launch (2) ;
+            GB200_CUDA (cudaGetLastError ()) ;
+            d->v.hbinfo = d->hbinfo.as<int32_t> () ;
+            d->v.hbloom = d->hbloom.as<uint32_t> () ;
+        }
+        GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
+    }
     d->has_vechash = true ;
     return GB200_SUCCESS ;
 }
@@ -363,6 +462,7 @@ gb200_status filter_mask (const gb200_dmatrix_s *M, DMat &Mview, DevBuf &Mp2, De
     Mview.nnz = n - nfalse ;
     Mview.x = nullptr ;
     Mview.hinfo = nullptr ; Mview.hkeys = nullptr ; Mview.hofs = nullptr ;
+    Mview.hbinfo = nullptr ; Mview.hbloom = nullptr ; Mview.iso = 0 ;
     return GB200_SUCCESS ;
 }
 
@@ -681,6 +781,8 @@ gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host)
     d->v.vlen = host->vlen ; d->v.vdim = host->vdim ; d->v.nvec = nvec ; d->v.nnz = nnz ;
     d->v.hyper = (host->h != NULL && nvec < host->vdim) ? 1 : 0 ;
     d->v.type_code = host->type_code ;
+    d->v.hinfo = nullptr ; d->v.hkeys = nullptr ; d->v.hofs = nullptr ;
+    d->v.hbinfo = nullptr ; d->v.hbloom = nullptr ; d->v.iso = 0 ;
     *out = d ;
     return GB200_SUCCESS ;
 }

@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "semiring.cuh"
+#include "kernels_vec.cuh"
 
 namespace gb200 {
 
@@ -471,7 +472,8 @@ dotg_kernel (DotGArgs a)
 // ---------------------------------------------------------------------------------------------
 // launchers, one set per (xy type); defined in inst_*.cu through GB200_INSTANTIATE_TYPE
 // ---------------------------------------------------------------------------------------------
-enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3 } ;
+enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_DOTV = 4,
+    FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -497,6 +499,14 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
         }
         dotg_kernel<S> <<<cfg.grid, cfg.block, smem, cfg.stream>>> (*(const DotGArgs *) args) ;
     }
+    else if (family == FAM_DOTV)
+        dotv_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotVArgs *) args) ;
+    else if (family == FAM_DOTV_LONG)
+        dotv_long_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotVArgs *) args) ;
+    else if (family == FAM_SAXPYV)
+        saxpyv_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyVArgs *) args) ;
+    else if (family == FAM_SAXPYV_LONG)
+        saxpyv_long_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyVArgs *) args) ;
     else
         dot_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotArgs *) args) ;
 }

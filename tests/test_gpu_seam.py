@@ -179,3 +179,79 @@ def test_nan_inf_placement():
         sr = gb.Semiring(add, mult, "FP64")
         assert_same(oracle_c.axb(None, False, Am, Bm, sr), gb.axb_host(None, False, Am, Bm, sr).matrix, add,
                     f"{add}_{mult}")
+
+
+# ---------------------------------------------------------------------------------------------
+# vector multiplies (B is n-by-1): the GrB_mxv / GrB_vxm shapes, pull (dot) and push (saxpy)
+# ---------------------------------------------------------------------------------------------
+def _vector(n, idx, x, t):
+    return gb.Matrix(n, 1, np.array([0, len(idx)]), np.asarray(idx, np.int64), np.asarray(x, NPT[t]), None, t)
+
+
+def _filter_by_mask(T: gb.Matrix, M: gb.Matrix, comp: bool) -> gb.Matrix:
+    """what GB_mask leaves of an n-by-1 T under <M> or <!M> (valued mask)"""
+    true_idx = M.i[M.x.astype(bool) | (np.isnan(M.x) if M.x.dtype.kind == "f" else False)]
+    keep = np.isin(T.i, true_idx)
+    if comp:
+        keep = ~keep
+    return gb.Matrix(T.vlen, 1, np.array([0, int(keep.sum())]), T.i[keep], T.x[keep], None, T.type)
+
+
+@pytest.mark.parametrize("add,mult,t", [("PLUS", "TIMES", "FP64"), ("MIN", "PLUS", "FP64"),
+                                        ("LOR", "LAND", "BOOL"), ("MAX", "MIN", "INT32"),
+                                        ("PLUS", "TIMES", "UINT8"), ("LXOR", "GT", "INT16"),
+                                        ("TIMES", "FIRST", "INT64"), ("MIN", "SECOND", "FP32")])
+@pytest.mark.parametrize("dense_u", [False, True])
+def test_vector_pull_and_push(add, mult, t, dense_u):
+    """w = A'*u (dot) and w = A*u (saxpy) with no mask, M and !M, including vectors of A longer than
+    the per-group limit (hub rows) so that the segment kernels run"""
+    n = 6000
+    rng = np.random.default_rng(97)
+    As = gen.er(n, n, 10 * n, 98, NPT[t], lo=-3, hi=4).tolil()
+    for r in (3, 777):                                       # two hub vectors (> 2048 entries)
+        cols = rng.choice(n, 3000, replace=False)
+        As[r, cols] = 1
+        As[cols, r] = 1
+    A = gb.Matrix.from_scipy(As.tocsc(), t)
+    nu = n if dense_u else n // 7
+    ui = np.sort(rng.choice(n, nu, replace=False))
+    ux = rng.integers(-3, 4, nu) if t not in FLOAT else rng.random(nu) * 2 - 0.5
+    if t == "BOOL":
+        ux = rng.integers(0, 2, nu)
+    if t.startswith("U"):
+        ux = np.abs(ux)
+    u = _vector(n, ui, ux, t)
+    mi = np.sort(rng.choice(n, n // 3, replace=False))
+    M = _vector(n, mi, rng.integers(0, 2, len(mi)), "INT8")
+    sr = gb.Semiring(add, mult, t)
+    for dot in (True, False):
+        for mask, comp in ((None, False), (M, False), (M, True)):
+            ref_info = {}
+            ref = oracle_c.axb(mask, comp, A, u, sr, dot, ref_info)
+            got = gb.axb_host(mask, comp, A, u, sr, dot)
+            what = f"{add}_{mult}_{t} dot={dot} mask={'none' if mask is None else ('!M' if comp else 'M')}"
+            if mask is not None and got.info["mask_applied"] and not ref_info["mask_applied"]:
+                # the push kernel applies !M itself; the reference filters T afterwards (same final C)
+                assert comp and not dot, what
+                ref = _filter_by_mask(ref, mask, comp)
+            else:
+                assert bool(got.info["mask_applied"]) == bool(ref_info["mask_applied"]), what
+            assert_same(ref, got.matrix, add, what)
+
+
+def test_vector_push_unfused_compmask(monkeypatch):
+    """GB200_FUSE_COMPMASK=0: the complemented mask is dropped exactly as the reference's saxpy does"""
+    monkeypatch.setenv("GB200_FUSE_COMPMASK", "0")
+    n = 3000
+    A = gb.Matrix.from_scipy(gen.er(n, n, 8 * n, 99, np.bool_).tocsc(), "BOOL")
+    rng = np.random.default_rng(100)
+    ui = np.sort(rng.choice(n, 200, replace=False))
+    u = _vector(n, ui, np.ones(200), "BOOL")
+    mi = np.sort(rng.choice(n, 1000, replace=False))
+    M = _vector(n, mi, np.ones(1000), "BOOL")
+    sr = gb.Semiring("LOR", "LAND", "BOOL", True)
+    info = {}
+    ref = oracle_c.axb(M, True, A, u, sr, False, info)
+    got = gb.axb_host(M, True, A, u, sr, False)
+    assert got.info["mask_applied"] == 0 == info["mask_applied"]
+    assert_same(ref, got.matrix, "LOR", "unfused !M")
