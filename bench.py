@@ -10,13 +10,18 @@ scale-22"): `tri` = C<L> = L*U' over PLUS_TIMES_INT64 on RMAT scale 22, edge fac
 GrB_mxm(C, L, NULL, GxB_PLUS_TIMES_INT64, L, U, desc{INP1=TRAN}) hands to GB_AxB_parallel
 (reference Demo/Source/tricount.c:166-178): M = L, A = U, B = L, do_adotb, flipxy.
 
-  value : 2 * madds / t, operands resident in HBM (gb200_AxB_device), max over ranks
-  e2e   : same metric through gb200_AxB_host + gb200_result_fetch with HOST numpy buffers
-          (H2D of M, A, B and D2H of T inside the timed region)
+  value : 2 * madds / t, operands resident in HBM (gb200_AxB_device); t = CUDA-event time of the K
+          steps on the library's launching stream (gb200_timer_mark), max over ranks
+  e2e   : same metric through gb200_AxB_host + gb200_result_fetch with HOST buffers in page-locked
+          memory from gb200_host_malloc (what every GraphBLAS array is after GxB_init with the
+          gb200_host_* allocator): H2D of M, A, B and D2H of T inside the timed region
   roofline : dominant kernel (the semiring kernel: dot_kernel / saxpy_*), algorithmic bytes of
           SURVEY.md 8(d) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : oracle/_ref (the compiled reference), GrB_mxm on a bounded sample of the same
-          workload, on rank 0 at N == 1 only
+  cpu_baseline : oracle/_ref (the compiled reference), GrB_mxm / GrB_mxv on a bounded sample of
+          the same workload, on rank 0 at N == 1 only.  One call of the reference is sequential
+          (Source/GB_AxB_parallel.c:102-103), so the sample is cut into one independent slice of
+          output vectors per host core and the slices run concurrently from user threads (the
+          reference is thread-safe for that, Demo/Program/pthread_demo.c)
 
 N > 1 (torchrun, one rank per GPU): the mask's vectors are split into N flop-balanced contiguous
 slices (the reference's own plan, GB_AxB_parallel.c:52); A and B are replicated; no data-path
@@ -237,56 +242,148 @@ def slice_vectors(m, lo, hi):
 # ---------------------------------------------------------------------------------------------
 # the reference arm / CPU baseline: the compiled reference through its public API
 # ---------------------------------------------------------------------------------------------
-def reference_sample(args, w, budget_s=20.0):
-    """GrB_mxm on the reference's CPU path over a bounded sample: every `stride`-th vector of the
-    mask (tri) or of the sliced operand (spgemm).  Returns (gflops, seconds, madds, description)."""
+def _interleaved_parts(m, stride, nparts):
+    """Every `stride`-th vector of m, dealt round-robin to `nparts` slices.  Each slice keeps the
+    dimensions of m (the other vectors are empty).  -> list of (p, i, x), kept-vector count"""
+    nvec = m.nvec
+    cnt = np.diff(m.p)
+    v = np.arange(nvec)
+    sampled = (v % stride) == 0
+    owner = (v // stride) % nparts
+    parts = []
+    for t in range(nparts):
+        keep = sampled & (owner == t)
+        cnt2 = np.where(keep, cnt, 0)
+        p2 = np.concatenate([[0], np.cumsum(cnt2)])
+        sel = np.repeat(keep, cnt)
+        parts.append((p2, m.i[sel], m.x[sel]))
+    return parts, int(sampled.sum())
+
+
+def host_bfs_levels(A, src):
+    """(q, visited) index arrays per level of the bfs5m loop, computed with numpy on the host (used
+    by the reference arm, which must not touch the GPU library)"""
+    n = A.vlen
+    visited = np.zeros(n, dtype=bool)
+    q = np.array([src], dtype=np.int64)
+    out = []
+    while len(q):
+        visited[q] = True
+        out.append((q, np.nonzero(visited)[0]))
+        starts, ends = A.p[q], A.p[q + 1]
+        tot = int((ends - starts).sum())
+        if tot == 0:
+            break
+        idx = np.repeat(starts - np.concatenate([[0], np.cumsum(ends - starts)[:-1]]), ends - starts) \
+            + np.arange(tot)
+        nb = np.unique(A.i[idx])
+        q = nb[~visited[nb]]
+    return out
+
+
+def reference_sample(args, w):
+    """The reference's CPU path through its public API on a bounded sample of the workload, the
+    sample cut into one slice of output vectors per host thread.
+    -> (gflops, seconds, madds, description, threads)"""
     import grbref
+    from concurrent.futures import ThreadPoolExecutor
     G = grbref.GraphBLAS.get(with_shim=False)
-    sliced = w["M"] if w["slice"] == "M" else w["B"]
-    nvec = sliced.nvec
+    T = max(1, args.cpu_threads or (os.cpu_count() or 1))
     stride = args.cpu_stride
-    cnt = np.diff(sliced.p)
-    keep = np.zeros(nvec, dtype=bool)
-    keep[::stride] = True
-    cnt2 = np.where(keep, cnt, 0)
-    p2 = np.concatenate([[0], np.cumsum(cnt2)])
-    sel = np.repeat(keep, cnt)
-    i2, x2 = sliced.i[sel], sliced.x[sel]
-    t_import = time.time()
-    if args.workload == "tri":
-        # user-level call: C<Ls> = L*U' , CSR, desc INP1 = TRAN (Demo/Source/tricount.c:166-178)
+    wl = args.workload
+    sr_name = "GxB_" + "_".join((w["semiring"].add, w["semiring"].mult, w["semiring"].xytype))
+    tname = w["semiring"].xytype
+    handles, vhandles = [], []
+
+    if wl == "tri":
+        # user-level call: C<Ls> = L*U', CSR, desc INP1 = TRAN (Demo/Source/tricount.c:166-178)
         L, U = w["B"], w["A"]
         n = L.vdim
-        l = G.matrix_import("CSR", "INT64", n, n, L.p, L.i, L.x)
-        u = G.matrix_import("CSR", "INT64", n, n, U.p, U.i, U.x)
-        ms = G.matrix_import("CSR", "INT64", n, n, p2, i2, x2)
-        c = G.matrix_new("INT64", n, n)
+        parts, nkept = _interleaved_parts(L, stride, T)
+        l = G.matrix_import("CSR", tname, n, n, L.p, L.i, L.x)
+        u = G.matrix_import("CSR", tname, n, n, U.p, U.i, U.x)
+        ms = [G.matrix_import("CSR", tname, n, n, *pt) for pt in parts]
+        cs = [G.matrix_new(tname, n, n) for _ in parts]
         d = G.descriptor(inp1=grbref.GrB_TRAN)
-        t0 = time.perf_counter()
-        G.mxm(c, ms, None, "GxB_PLUS_TIMES_INT64", l, u, d)
-        G.matrix_nvals(c)
-        dt = time.perf_counter() - t0
-        madds = G.reduce_int64(c)
-        for h in (l, u, ms, c):
-            G.matrix_free(h)
-    else:
+        handles = [l, u] + ms + cs
+
+        def run(t):
+            G.mxm(cs[t], ms[t], None, sr_name, l, u, d)
+            G.matrix_nvals(cs[t])
+        madds_of = lambda: sum(G.reduce_int64(c) for c in cs)      # values are 0/1: sum = matches
+        what = f"every {stride}th vector of the mask L ({nkept} of {L.nvec})"
+        call = "GrB_mxm"
+    elif wl in ("spgemm", "spgemm_rmat"):
         # user-level call: C = As*B, CSR
         Ain, Bin = w["B"], w["A"]
-        a = G.matrix_import("CSR", "FP64", Ain.vdim, Ain.vlen, p2, i2, x2)
-        b = G.matrix_import("CSR", "FP64", Bin.vdim, Bin.vlen, Bin.p, Bin.i, Bin.x)
-        c = G.matrix_new("FP64", Ain.vdim, Bin.vlen)
-        t0 = time.perf_counter()
-        G.mxm(c, None, None, "GxB_PLUS_TIMES_FP64", a, b, None)
-        G.matrix_nvals(c)
-        dt = time.perf_counter() - t0
-        # madds of the sample = sum over kept entries A(i,k) of nnz(B(k,:))
-        madds = int(np.diff(Bin.p)[i2].sum())
-        for h in (a, b, c):
-            G.matrix_free(h)
-    desc = (f"every {stride}th vector of {'the mask L' if args.workload == 'tri' else 'A'} "
-            f"({int(keep.sum())} of {nvec} vectors, {len(i2)} entries), one GrB_mxm call, 1 thread "
-            f"(the reference multiply is sequential: Source/GB_AxB_parallel.c:102-103)")
-    return 2.0 * madds / dt / 1e9, dt, madds, desc
+        parts, nkept = _interleaved_parts(Ain, stride, T)
+        b = G.matrix_import("CSR", tname, Bin.vdim, Bin.vlen, Bin.p, Bin.i, Bin.x)
+        As = [G.matrix_import("CSR", tname, Ain.vdim, Ain.vlen, *pt) for pt in parts]
+        cs = [G.matrix_new(tname, Ain.vdim, Bin.vlen) for _ in parts]
+        handles = [b] + As + cs
+        lenB = np.diff(Bin.p)
+
+        def run(t):
+            G.mxm(cs[t], None, None, sr_name, As[t], b, None)
+            G.matrix_nvals(cs[t])
+        madds_of = lambda: int(sum(int(lenB[pt[1]].sum()) for pt in parts))
+        what = f"every {stride}th row of A ({nkept} of {Ain.nvec})"
+        call = "GrB_mxm"
+    elif wl == "sssp":
+        # user-level call: w = As min.+ d (GrB_mxv, A CSR): rows of A are independent outputs
+        Am, dv = w["A"], w["B"]
+        n = Am.vdim
+        parts, nkept = _interleaved_parts(Am, stride, T)
+        As = [G.matrix_import("CSR", tname, n, n, *pt) for pt in parts]
+        dd = G.vector_import(tname, n, dv.i, dv.x)
+        ws = [G.vector_new(tname, n) for _ in parts]
+        handles, vhandles = As, [dd] + ws
+
+        def run(t):
+            G.mxv(ws[t], None, None, sr_name, As[t], dd, None)
+            G.vector_nvals(ws[t])
+        madds_of = lambda: int(sum(len(pt[1]) for pt in parts))     # d is dense: every entry matches
+        what = f"every {stride}th row of A ({nkept} of {Am.nvec})"
+        call = "GrB_mxv"
+    else:
+        # bfs: the level loop q<!v> = q*A (GrB_vxm, REPLACE, SCMP); one frontier vector cannot be
+        # sliced by the caller, so this leg is one thread
+        T = 1
+        Am = w["A"]
+        n = Am.vdim
+        levels = host_bfs_levels(Am, w["bfs_source"])
+        a = G.matrix_import("CSR", tname, n, n, Am.p, Am.i, Am.x)
+        qs = [G.vector_import(tname, n, q, np.ones(len(q), np.bool_)) for q, _ in levels]
+        vs = [G.vector_import(tname, n, v, np.ones(len(v), np.bool_)) for _, v in levels]
+        ws = [G.vector_new(tname, n) for _ in levels]
+        d = G.descriptor(outp=grbref.GrB_REPLACE, mask=grbref.GrB_SCMP)
+        handles, vhandles = [a], qs + vs + ws
+        lenA = np.diff(Am.p)
+
+        def run(t):
+            for q, v, wv in zip(qs, vs, ws):
+                G.vxm(wv, v, None, sr_name, q, a, d)
+                G.vector_nvals(wv)
+        madds_of = lambda: int(sum(int(lenA[q].sum()) for q, _ in levels))
+        what = f"all {len(levels)} levels"
+        call = "GrB_vxm"
+
+    t0 = time.perf_counter()
+    if T == 1:
+        run(0)
+    else:
+        with ThreadPoolExecutor(T) as ex:
+            list(ex.map(run, range(T)))
+    dt = time.perf_counter() - t0
+    madds = madds_of()
+    for h in handles:
+        G.matrix_free(h)
+    for h in vhandles:
+        G.vector_free(h)
+    desc = (f"{what}, cut into {T} slices of output vectors, one {call} per slice on {T} concurrent "
+            f"user threads of {os.cpu_count()} host cores (a single reference call is sequential: "
+            f"Source/GB_AxB_parallel.c:102-103)")
+    return 2.0 * madds / dt / 1e9, dt, madds, desc, T
 
 
 # ---------------------------------------------------------------------------------------------
@@ -301,11 +398,15 @@ def main():
     ap.add_argument("--bfs-dir", default="push", choices=["push", "pull"])
     ap.add_argument("--scale", type=int, default=22)
     ap.add_argument("--ef", type=int, default=16)
-    ap.add_argument("--cpu-stride", type=int, default=16)
+    ap.add_argument("--cpu-stride", type=int, default=0, help="sample every n-th output vector "
+                    "(0: workload default)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="0: all host cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.workload == "spgemm" and args.scale == 22 and "--scale" not in " ".join(sys.argv):
         args.scale, args.ef = 20, 8
+    if args.cpu_stride <= 0:
+        args.cpu_stride = {"tri": 4, "spgemm": 1, "spgemm_rmat": 8, "sssp": 1, "bfs": 1}[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -323,7 +424,7 @@ def main():
         w = make_workload(args, device)
         vals = []
         for s in range(args.warmup + args.steps):
-            gf, dt, madds, desc = reference_sample(args, w)
+            gf, dt, madds, desc, threads = reference_sample(args, w)
             if s >= args.warmup:
                 vals.append((gf, dt))
         gf = float(np.mean([v[0] for v in vals]))
@@ -333,8 +434,8 @@ def main():
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
                 "config": {"workload": w["name"]},
-                "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": 1, "kind": "reference",
-                                 "sample": desc},
+                "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": threads,
+                                 "kind": "reference", "sample": desc},
                 "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -355,10 +456,10 @@ def main():
     w = make_workload(args, device)
     torch.cuda.empty_cache()
     A, B, M = w["A"], w["B"], w["M"]
-    dA = gb.DMatrix(A)
     sliced_name = w["slice"]
+    dA = gb.DMatrix(A)
 
-    # ---- the multiplies of one step: list of (M, A, B) host triples + their resident handles ----
+    # ---- the multiplies of one step: (M, A, B) host triples + their resident handles ------------
     if args.workload == "bfs":
         if world > 1:
             raise SystemExit("the vector push step needs an exchange of the frontier (SURVEY.md 8e); "
@@ -379,12 +480,13 @@ def main():
             elif sliced_name == "A":
                 cum = A.p                       # dot with a vector: work of a vector of A = its length
             else:
-                # masked dot: balance by sum over mask entries of (len A(:,i) + len B(:,j))
+                # masked dot: balance by sum over mask entries of min (len A(:,i), len B(:,j)), the
+                # length of the list the kernel walks
                 lenA = np.diff(A.p)
                 lenB = np.diff(B.p)
-                cs = np.concatenate([[0], np.cumsum(lenA[M.i])])
-                per_vec = (cs[M.p[1:]] - cs[M.p[:-1]]) + np.diff(M.p) * lenB
-                cum = np.concatenate([[0], np.cumsum(per_vec)]).astype(np.int64)
+                walk = np.minimum(lenA[M.i], np.repeat(lenB, np.diff(M.p))) + 1
+                cs = np.concatenate([[0], np.cumsum(walk)])
+                cum = cs[M.p].astype(np.int64)
             bounds = gb.partition_by_flops(cum, world)
             lo, hi = int(bounds[rank]), int(bounds[rank + 1])
             mine = slice_vectors(sliced, lo, hi)
@@ -397,6 +499,17 @@ def main():
                 B, dB = mine, dmine
         calls = [(M, A, B, dM, dA, dB)]
 
+    # host operands of the end-to-end leg live in page-locked memory (gb200_host_malloc)
+    pinned = {}
+
+    def pin(m):
+        if m is None:
+            return None
+        if id(m) not in pinned:
+            pinned[id(m)] = m.pinned()
+        return pinned[id(m)]
+    hcalls = [(pin(m), pin(a), pin(b)) for (m, a, b, _, _, _) in calls]
+
     def step_device():
         out = {"flops": 0, "nnz": 0, "device_ms": 0.0, "kernel_ms": 0.0, "nvec": 0}
         for (_, _, _, dm, da, db) in calls:
@@ -407,9 +520,19 @@ def main():
         return out
 
     def step_host():
+        """one step through the host entry points: host operands in, host T out.  The matrix A of a
+        BFS step is uploaded once per step and shared by its level multiplies."""
         outs = []
-        for (m, a, b, _, _, _) in calls:
-            outs.append(gb.axb_host(m, w["mask_comp"], a, b, w["semiring"], w["do_adotb"], fetch=True))
+        if args.workload == "bfs":
+            da = gb.DMatrix(hcalls[0][1])
+            for (m, a, b) in hcalls:
+                outs.append(gb.axb_device(gb.DMatrix(m), w["mask_comp"], da, gb.DMatrix(b),
+                                          w["semiring"], w["do_adotb"], fetch=True, pinned=True))
+            da.free()
+        else:
+            for (m, a, b) in hcalls:
+                outs.append(gb.axb_host(m, w["mask_comp"], a, b, w["semiring"], w["do_adotb"],
+                                        fetch=True, pinned=True))
         return outs
 
     def barrier():
@@ -424,15 +547,18 @@ def main():
     barrier()
     with ClockSampler(local_rank) as clk:
         t0 = time.perf_counter()
+        gb.timer_mark(0)
         dev_ms, ker_ms = [], []
         for _ in range(args.steps):
             r = step_device()
             dev_ms.append(r["device_ms"])
             ker_ms.append(r["kernel_ms"])
+        gb.timer_mark(1)
+        t_events = gb.timer_elapsed_ms(0, 1) * 1e-3     # synchronises on the second mark
         torch.cuda.synchronize()
-        t_local = time.perf_counter() - t0
+        t_wall = time.perf_counter() - t0
     launches = gb.kernel_launches() - launches0
-    tt = torch.tensor([t_local, float(np.sum(dev_ms))], dtype=torch.float64, device=device)
+    tt = torch.tensor([t_events, t_wall], dtype=torch.float64, device=device)
     fl = torch.tensor([r["flops"], r["nnz"]], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -445,6 +571,7 @@ def main():
     # ---- e2e: host buffers in, host T out, every step -----------------------------------------
     e2e_steps = max(1, min(args.steps, 3))
     step_host()
+    step_host()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -456,14 +583,20 @@ def main():
     t_e2e = te[0].item() / e2e_steps
     h2d = d2h = 0
     ab = 0
-    for (m, a, b, _, _, _), res in zip(calls, rh):
+    nbytes = lambda x: x.p.nbytes + x.i.nbytes + x.x.nbytes + (x.h.nbytes if x.h is not None else 0)
+    seen_once = set()
+    for (m, a, b), res in zip(hcalls, rh):
         uniq = list({id(x): x for x in (m, a, b) if x is not None}.values())
         # a complemented mask is not read by the saxpy method (GB_AxB_sequential.c:76-81)
         read = [x for x in uniq if not (x is m and w["mask_comp"] and not res.info["mask_applied"])]
-        h2d += sum(x.p.nbytes + x.i.nbytes + x.x.nbytes + (x.h.nbytes if x.h is not None else 0)
-                   for x in uniq)
+        for x in uniq:
+            if args.workload == "bfs" and x is a:
+                if id(x) in seen_once:
+                    continue                    # A of a BFS step crosses PCIe once per step
+                seen_once.add(id(x))
+            h2d += nbytes(x)
         T = res.matrix
-        d2h += T.p.nbytes + T.i.nbytes + T.x.nbytes + (T.h.nbytes if T.h is not None else 0)
+        d2h += nbytes(T)
         if args.workload == "bfs" and not w["do_adotb"]:
             # vector push: only the vectors of A named by the frontier are traversed
             lens = np.diff(a.p)[b.i]
@@ -472,6 +605,7 @@ def main():
             ab += sum(x.nnz * (8 + x.x.dtype.itemsize) for x in read if x is m)
         else:
             ab += algo_bytes(read, res.info["nvec"], res.info["nnz"], T.x.dtype.itemsize)
+    del rh
 
     # ---- roofline of the dominant (semiring) kernels, rank 0's slice --------------------------
     peak, peak_src = measured_peak()
@@ -480,7 +614,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{args.workload}_s{args.scale}")
+            key = args.workload + ("_pull" if args.workload == "bfs" and w["do_adotb"] else "")
+            traffic = json.load(f).get(f"{key}_s{args.scale}")
     except Exception:
         pass
 
@@ -491,30 +626,35 @@ def main():
                 "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
                 "config": {"workload": w["name"], "madds_per_step": madds, "nnz_T": cnz,
                            "multiplies_per_step": len(calls),
+                           "timing": "CUDA events on the library's launching stream around the K "
+                                     "steps, max over ranks; wall clock alongside",
                            "l2": "inputs larger than L2 (no flush needed)" if h2d > 2.6e8 else
                                  "inputs smaller than L2",
                            "partition": f"{world} flop-balanced contiguous slices of "
                                         f"{ {'M': 'the mask', 'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors"},
+                "wall_ms_per_step": tt[1].item() / args.steps * 1e3,
                 "device_ms_per_step": float(np.mean(dev_ms)),
                 "clocks": clk.summary(),
                 "e2e": {"value": 2.0 * madds / t_e2e / 1e9, "unit": "GFLOP/s",
                         "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h)},
+                        "d2h_bytes_per_step": int(d2h),
+                        "host_memory": "page-locked (gb200_host_malloc)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
-                             "kernel": "dotg_kernel/dot_kernel" if w["do_adotb"] else "saxpy_*_kernel",
+                             "kernel": w.get("kernel", "dotg_kernel/dot_kernel" if w["do_adotb"]
+                                             else "saxpy_*_kernel"),
                              "kernel_ms": k_ms, "algorithmic_bytes": int(ab), "peak_source": peak_src,
                              "bytes_per_madd": ab / max(r["flops"], 1),
                              "step_algo_gbs": ab / (float(np.mean(dev_ms)) * 1e-3) / 1e9}}
         if world == 1 and not args.no_cpu:
             try:
-                gf, dt, cm, desc = reference_sample(args, w)
-                line["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": 1,
+                gf, dt, cm, desc, threads = reference_sample(args, w)
+                line["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": threads,
                                         "kind": "reference", "sample": desc, "seconds": dt,
                                         "host_cores_present": os.cpu_count()}
             except Exception as e:  # the reference .so is test infrastructure; say so if absent
-                line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": 1,
+                line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": 0,
                                         "kind": "reference", "sample": f"unavailable: {e}"}
         print(json.dumps(line))
     if world > 1:

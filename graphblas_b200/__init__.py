@@ -80,13 +80,54 @@ lib.gb200_multiplies.restype = C.c_int64
 for _name in ("gb200_init", "gb200_finalize", "gb200_upload", "gb200_dmatrix_free",
               "gb200_AxB_device", "gb200_AxB_host", "gb200_result_get_info", "gb200_result_fetch",
               "gb200_result_free", "gb200_flopcount_device", "gb200_partition_by_flops",
-              "gb200_semiring_canonical", "gb200_device_count"):
+              "gb200_semiring_canonical", "gb200_device_count", "gb200_timer_mark",
+              "gb200_timer_elapsed_ms"):
     getattr(lib, _name).restype = C.c_int
+lib.gb200_host_malloc.restype = C.c_void_p
+lib.gb200_host_malloc.argtypes = [C.c_size_t]
+lib.gb200_host_free.restype = None
+lib.gb200_host_free.argtypes = [C.c_void_p]
+lib.gb200_host_trim.restype = None
 
 
 def _check(code: int, where: str) -> None:
     if code != 0:
         raise GB200Error(code, where)
+
+
+class _HostBlock:
+    """A block from gb200_host_malloc (page-locked when large), exposed through the array interface
+    so that numpy can view it; returned to the library's cache when the last view dies."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = max(int(nbytes), 1)
+        self.ptr = lib.gb200_host_malloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError(f"gb200_host_malloc({self.nbytes})")
+        self.__array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1",
+                                    "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib.gb200_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def host_empty(n: int, dtype) -> np.ndarray:
+    """np.empty(n, dtype) on memory from gb200_host_malloc -- what a host application gets for every
+    GraphBLAS array after GxB_init(mode, gb200_host_malloc, ...)."""
+    dt = np.dtype(dtype)
+    blk = _HostBlock(n * dt.itemsize)
+    return np.asarray(blk)[: n * dt.itemsize].view(dt)
+
+
+def host_array(a: np.ndarray) -> np.ndarray:
+    out = host_empty(a.size, a.dtype)
+    out[...] = a.reshape(-1)
+    return out
 
 
 @dataclass
@@ -160,6 +201,12 @@ class Matrix:
         return cls(vlen, vdim, s.indptr.astype(np.int64), s.indices.astype(np.int64), s.data, None,
                    type)
 
+    def pinned(self) -> "Matrix":
+        """The same matrix with its arrays in memory from gb200_host_malloc."""
+        return Matrix(self.vlen, self.vdim, host_array(self.p), host_array(self.i),
+                      host_array(self.x), host_array(self.h) if self.h is not None else None,
+                      self.type)
+
     def to_hyper(self) -> "Matrix":
         """Same matrix in hypersparse form (only non-empty vectors are listed)."""
         cnt = np.diff(self.p)
@@ -207,17 +254,18 @@ class Result:
     info: dict
 
 
-def _fetch(rh: C.c_void_p, fetch: bool) -> Result:
+def _fetch(rh: C.c_void_p, fetch: bool, pinned: bool = False) -> Result:
     ci = _CInfo()
     _check(lib.gb200_result_get_info(rh, C.byref(ci)), "gb200_result_get_info")
     info = {k: getattr(ci, k) for k, _ in _CInfo._fields_}
     m = None
     if fetch:
         tname, dt = TYPE_BY_CODE[ci.type_code]
-        p = np.empty(ci.nvec + 1, dtype=np.int64)
-        h = np.empty(ci.nvec, dtype=np.int64) if ci.is_hyper else None
-        i = np.empty(ci.nnz, dtype=np.int64)
-        x = np.empty(ci.nnz, dtype=dt)
+        empty = host_empty if pinned else np.empty
+        p = empty(ci.nvec + 1, np.int64)
+        h = empty(ci.nvec, np.int64) if ci.is_hyper else None
+        i = empty(ci.nnz, np.int64)
+        x = empty(ci.nnz, dt)
         _check(lib.gb200_result_fetch(rh, p.ctypes.data_as(C.c_void_p),
                                       h.ctypes.data_as(C.c_void_p) if h is not None else None,
                                       i.ctypes.data_as(C.c_void_p) if ci.nnz else None,
@@ -233,18 +281,22 @@ def init(device: int = -1) -> None:
 
 
 def axb_device(M: Optional[DMatrix], mask_comp: bool, A: DMatrix, B: DMatrix, semiring: Semiring,
-               do_adotb: bool = False, method: int = METHOD_DEFAULT, fetch: bool = True) -> Result:
+               do_adotb: bool = False, method: int = METHOD_DEFAULT, fetch: bool = True,
+               pinned: bool = False) -> Result:
     """C<M>=A*B (or A'*B) with operands already resident (gb200_AxB_device)."""
     rh = C.c_void_p()
     s = semiring.c()
     _check(lib.gb200_AxB_device(C.byref(rh), M._h if M is not None else None, int(mask_comp), A._h,
                                 B._h, C.byref(s), int(do_adotb), method), "gb200_AxB_device")
-    return _fetch(rh, fetch)
+    return _fetch(rh, fetch, pinned)
 
 
 def axb_host(M: Optional[Matrix], mask_comp: bool, A: Matrix, B: Matrix, semiring: Semiring,
-             do_adotb: bool = False, method: int = METHOD_DEFAULT, fetch: bool = True) -> Result:
-    """The GB_AxB_parallel replacement: host operands in, host T out (gb200_AxB_host + fetch)."""
+             do_adotb: bool = False, method: int = METHOD_DEFAULT, fetch: bool = True,
+             pinned: bool = False) -> Result:
+    """The GB_AxB_parallel replacement: host operands in, host T out (gb200_AxB_host + fetch).
+    pinned: T's arrays come from gb200_host_malloc (as GB_create would hand out under GxB_init
+    with the gb200_host_* allocator)."""
     rh = C.c_void_p()
     s = semiring.c()
     cm = M.c() if M is not None else None
@@ -252,7 +304,7 @@ def axb_host(M: Optional[Matrix], mask_comp: bool, A: Matrix, B: Matrix, semirin
     _check(lib.gb200_AxB_host(C.byref(rh), C.byref(cm) if cm is not None else None, int(mask_comp),
                               C.byref(ca), C.byref(cb), C.byref(s), int(do_adotb), method),
            "gb200_AxB_host")
-    return _fetch(rh, fetch)
+    return _fetch(rh, fetch, pinned)
 
 
 def flopcount(M: Optional[DMatrix], A: DMatrix, B: DMatrix):
@@ -276,3 +328,13 @@ def partition_by_flops(cum: np.ndarray, nparts: int) -> np.ndarray:
 
 def kernel_launches() -> int:
     return lib.gb200_kernel_launches()
+
+
+def timer_mark(slot: int) -> None:
+    _check(lib.gb200_timer_mark(slot), "gb200_timer_mark")
+
+
+def timer_elapsed_ms(a: int, b: int) -> float:
+    ms = C.c_double()
+    _check(lib.gb200_timer_elapsed_ms(a, b, C.byref(ms)), "gb200_timer_elapsed_ms")
+    return ms.value

@@ -111,6 +111,9 @@ struct gb200_dmatrix_s
     gb200::DevBuf longitems ;       // lazily built segments of the vectors longer than VEC_LONG
     int64_t n_longitems = 0 ;
     bool has_longitems = false ;
+    gb200::DevBuf tilerow ;         // lazily built: stored vector holding entry t * SPMV_TILE
+    int64_t n_tiles = 0 ;
+    bool has_tilerow = false ;
 } ;
 
 struct gb200_result_s

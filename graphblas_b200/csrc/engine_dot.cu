@@ -576,16 +576,24 @@ gb200_status gb200_AxB_host (gb200_result *out, const gb200_matrix *M, int mask_
     }
     gb200_dmatrix dM = NULL, dA = NULL, dB = NULL ;
     gb200_status st = GB200_SUCCESS ;
-    // A and B may be the same host object (C=A*A): upload once
-    if (M != NULL) st = gb200_upload (&dM, M) ;
-    if (st == GB200_SUCCESS) st = gb200_upload (&dA, A) ;
-    const bool same = (A == B) || (A->p == B->p && A->i == B->i && A->x == B->x && A->h == B->h
-        && A->vlen == B->vlen && A->vdim == B->vdim && A->nvec == B->nvec) ;
-    if (st == GB200_SUCCESS) { if (same) dB = dA ; else st = gb200_upload (&dB, B) ; }
+    // operands may be the same host object (C=A*A; the tricount mask C<L>=L*U' is its own operand):
+    // each distinct object crosses PCIe once
+    auto same = [] (const gb200_matrix *X, const gb200_matrix *Y)
+    {
+        return X != NULL && Y != NULL && ((X == Y) || (X->p == Y->p && X->i == Y->i && X->x == Y->x
+            && X->h == Y->h && X->vlen == Y->vlen && X->vdim == Y->vdim && X->nvec == Y->nvec
+            && X->type_code == Y->type_code)) ;
+    } ;
+    st = gb200_upload (&dA, A) ;
+    if (st == GB200_SUCCESS) { if (same (A, B)) dB = dA ; else st = gb200_upload (&dB, B) ; }
+    if (st == GB200_SUCCESS && M != NULL)
+    {
+        if (same (M, A)) dM = dA ; else if (same (M, B)) dM = dB ; else st = gb200_upload (&dM, M) ;
+    }
     if (st == GB200_SUCCESS) st = gb200_AxB_device (out, dM, mask_comp, dA, dB, semiring, do_adotb, method) ;
-    if (!same) gb200_dmatrix_free (&dB) ;
+    if (dM != dA && dM != dB) gb200_dmatrix_free (&dM) ;
+    if (dB != dA) gb200_dmatrix_free (&dB) ;
     gb200_dmatrix_free (&dA) ;
-    gb200_dmatrix_free (&dM) ;
     return st ;
 }
 

@@ -1,0 +1,201 @@
+// engine_host.cu -- host-side services of the C ABI that are not part of a multiply:
+//   * the page-locked malloc/calloc/realloc/free quartet a host application hands to GxB_init
+//     (reference Include/GraphBLAS.h:330-340; every GraphBLAS array then lives in pinned memory,
+//     including the T that the shim allocates through GB_create, Source/GB.h:1021-1035)
+//   * CUDA-event timers on the library's stream
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+#include "engine.cuh"
+
+namespace gb200 {
+
+// ---------------------------------------------------------------------------------------------
+// pinned block cache.  Page-locking is expensive, so freed blocks are kept by capacity (rounded up
+// to a size class: powers of two split in four) and handed out again; a block is reused only for a
+// request that fills at least half of it.
+// ---------------------------------------------------------------------------------------------
+struct HostPool
+{
+    std::mutex mu ;
+    std::unordered_map<void *, size_t> live ;           // pinned blocks in use: ptr -> capacity
+    std::multimap<size_t, void *> cache ;               // free pinned blocks by capacity
+    size_t cached_bytes = 0 ;
+    bool no_device = false ;                            // cudaMallocHost failed once: stop trying
+} ;
+
+static HostPool &pool () { static HostPool *p = new HostPool () ; return *p ; }    // never destroyed
+
+static size_t size_class (size_t n)
+{
+    size_t c = GB200_HOST_PIN_MIN ;
+    while (c < n) c <<= 1 ;
+    if (c == n || c == GB200_HOST_PIN_MIN) return c ;
+    // four classes per octave: 1.25, 1.5, 1.75, 2.0 x the lower power of two
+    const size_t lo = c >> 1, step = lo >> 2 ;
+    for (size_t q = lo + step ; q < c ; q += step) if (q >= n) return q ;
+    return c ;
+}
+
+static void *pinned_get (size_t size)
+{
+    HostPool &hp = pool () ;
+    if (hp.no_device) return nullptr ;
+    const size_t cap = size_class (size) ;
+    {
+        std::lock_guard<std::mutex> lock (hp.mu) ;
+        auto it = hp.cache.lower_bound (cap) ;
+        if (it != hp.cache.end () && it->first <= 2 * cap)
+        {
+            void *p = it->second ;
+            const size_t c = it->first ;
+            hp.cache.erase (it) ;
+            hp.cached_bytes -= c ;
+            hp.live [p] = c ;
+            return p ;
+        }
+    }
+    void *p = nullptr ;
+    cudaError_t e = cudaMallocHost (&p, cap) ;
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError () ;
+        // out of pinnable memory: drop the cache and retry once; no device at all: plain malloc
+        if (e == cudaErrorMemoryAllocation)
+        {
+            gb200_host_trim () ;
+            e = cudaMallocHost (&p, cap) ;
+            if (e != cudaSuccess) { cudaGetLastError () ; return nullptr ; }
+        }
+        else { hp.no_device = true ; return nullptr ; }
+    }
+    std::lock_guard<std::mutex> lock (hp.mu) ;
+    hp.live [p] = cap ;
+    return p ;
+}
+
+} // namespace gb200
+
+using namespace gb200 ;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+void *gb200_host_malloc (size_t size)
+{
+    if (size >= GB200_HOST_PIN_MIN)
+    {
+        void *p = pinned_get (size) ;
+        if (p != nullptr) return p ;
+    }
+    return malloc (size > 0 ? size : 1) ;
+}
+
+void *gb200_host_calloc (size_t n, size_t size)
+{
+    if (size != 0 && n > SIZE_MAX / size) return nullptr ;
+    const size_t bytes = n * size ;
+    if (bytes >= GB200_HOST_PIN_MIN)
+    {
+        void *p = pinned_get (bytes) ;
+        if (p != nullptr) { memset (p, 0, bytes) ; return p ; }
+    }
+    return calloc (n > 0 ? n : 1, size > 0 ? size : 1) ;
+}
+
+void gb200_host_free (void *p)
+{
+    if (p == nullptr) return ;
+    HostPool &hp = pool () ;
+    {
+        std::lock_guard<std::mutex> lock (hp.mu) ;
+        auto it = hp.live.find (p) ;
+        if (it != hp.live.end ())
+        {
+            const size_t cap = it->second ;
+            hp.live.erase (it) ;
+            hp.cache.emplace (cap, p) ;
+            hp.cached_bytes += cap ;
+            return ;
+        }
+    }
+    free (p) ;
+}
+
+void *gb200_host_realloc (void *p, size_t size)
+{
+    if (p == nullptr) return gb200_host_malloc (size) ;
+    HostPool &hp = pool () ;
+    size_t cap = 0 ;
+    {
+        std::lock_guard<std::mutex> lock (hp.mu) ;
+        auto it = hp.live.find (p) ;
+        if (it != hp.live.end ()) cap = it->second ;
+    }
+    if (cap == 0)
+    {
+        // a malloc block: stays one unless it grows past the pinning threshold
+        if (size < GB200_HOST_PIN_MIN) return realloc (p, size > 0 ? size : 1) ;
+        // its old size is unknown to us, so let realloc move it first, then copy into a pinned block
+        void *q = realloc (p, size) ;
+        if (q == nullptr) return nullptr ;
+        void *r = pinned_get (size) ;
+        if (r == nullptr) return q ;
+        memcpy (r, q, size) ;
+        free (q) ;
+        return r ;
+    }
+    if (size <= cap && size >= cap / 4) return p ;         // fits: keep the block
+    void *q = gb200_host_malloc (size) ;
+    if (q == nullptr) return nullptr ;
+    memcpy (q, p, size < cap ? size : cap) ;
+    gb200_host_free (p) ;
+    return q ;
+}
+
+void gb200_host_trim (void)
+{
+    HostPool &hp = pool () ;
+    std::multimap<size_t, void *> drop ;
+    {
+        std::lock_guard<std::mutex> lock (hp.mu) ;
+        drop.swap (hp.cache) ;
+        hp.cached_bytes = 0 ;
+    }
+    for (auto &kv : drop) cudaFreeHost (kv.second) ;
+    cudaGetLastError () ;
+}
+
+// ---- timers ------------------------------------------------------------------------------------
+static cudaEvent_t g_timer [8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr } ;
+
+gb200_status gb200_timer_mark (int slot)
+{
+    if (slot < 0 || slot >= 8) return GB200_INVALID ;
+    GB200_TRY (ensure_init ()) ;
+    Ctx &c = ctx () ;
+    std::lock_guard<std::recursive_mutex> lock (c.mu) ;
+    if (g_timer [slot] == nullptr) GB200_CUDA (cudaEventCreate (&g_timer [slot])) ;
+    GB200_CUDA (cudaEventRecord (g_timer [slot], c.stream)) ;
+    return GB200_SUCCESS ;
+}
+
+gb200_status gb200_timer_elapsed_ms (int slot_a, int slot_b, double *ms)
+{
+    if (slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8 || ms == nullptr) return GB200_INVALID ;
+    if (g_timer [slot_a] == nullptr || g_timer [slot_b] == nullptr)
+    {
+        set_error ("gb200_timer_elapsed_ms: slot not marked") ;
+        return GB200_INVALID ;
+    }
+    GB200_TRY (ensure_init ()) ;
+    GB200_CUDA (cudaEventSynchronize (g_timer [slot_b])) ;
+    float t = 0 ;
+    GB200_CUDA (cudaEventElapsedTime (&t, g_timer [slot_a], g_timer [slot_b])) ;
+    *ms = t ;
+    return GB200_SUCCESS ;
+}
+
+#pragma GCC visibility pop
+} // extern "C"

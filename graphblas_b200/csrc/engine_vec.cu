@@ -89,6 +89,42 @@ static gb200_status ensure_longitems (gb200_dmatrix_s *d)
     return GB200_SUCCESS ;
 }
 
+// tile_row [t] = the stored vector kk with p [kk] <= t * SPMV_TILE < p [kk+1]
+__global__ void tile_row_kernel (const int64_t *__restrict__ p, int64_t nvec, int64_t ntiles,
+    int32_t *__restrict__ tile_row)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < ntiles ;
+        t += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t pos = t * SPMV_TILE ;
+        int64_t lo = 0, hi = nvec ;             // last kk in [0,nvec) with p [kk] <= pos
+        while (hi - lo > 1)
+        {
+            const int64_t mid = (lo + hi) >> 1 ;
+            if (__ldg (p + mid) <= pos) lo = mid ; else hi = mid ;
+        }
+        tile_row [t] = (int32_t) lo ;
+    }
+}
+
+static gb200_status ensure_tilerow (gb200_dmatrix_s *d)
+{
+    if (d->has_tilerow) return GB200_SUCCESS ;
+    Ctx &c = ctx () ;
+    const int64_t ntiles = (d->v.nnz + SPMV_TILE - 1) / SPMV_TILE ;
+    d->n_tiles = ntiles ;
+    if (ntiles > 0)
+    {
+        GB200_TRY (d->tilerow.alloc (ntiles * sizeof (int32_t))) ;
+        tile_row_kernel <<<grid_cap ((ntiles + 255) / 256, 8), 256, 0, c.stream>>> (d->v.p, d->v.nvec,
+            ntiles, d->tilerow.as<int32_t> ()) ;
+        count_launch () ;
+        GB200_CUDA (cudaGetLastError ()) ;
+    }
+    d->has_tilerow = true ;
+    return GB200_SUCCESS ;
+}
+
 // ---------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------
@@ -212,7 +248,12 @@ gb200_status run_dotv (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_com
     const gb200_dmatrix_s *Ad, const gb200_dmatrix_s *Bd, const gb200_semiring &s)
 {
     Ctx &c = ctx () ;
-    GB200_TRY (ensure_longitems (const_cast<gb200_dmatrix_s *> (Ad))) ;
+    // no mask: every vector of A is computed, so the entries of A are streamed in equal tiles;
+    // with a mask whole vectors are skipped, which the vector-per-lane-group kernel does for free
+    const char *senv = getenv ("GB200_SPMV_STREAM") ;
+    const bool stream = (M == nullptr) && !(senv != nullptr && atoi (senv) == 0) ;
+    if (stream) GB200_TRY (ensure_tilerow (const_cast<gb200_dmatrix_s *> (Ad))) ;
+    else GB200_TRY (ensure_longitems (const_cast<gb200_dmatrix_s *> (Ad))) ;
     const DMat &A = Ad->v ;
     const DMat &B = Bd->v ;
     const int64_t cvlen = A.vdim, vlen = A.vlen, anvec = A.nvec ;
@@ -254,6 +295,23 @@ gb200_status run_dotv (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_com
     GB200_TRY (nmatch.alloc (8)) ;
     GB200_CUDA (cudaMemsetAsync (nmatch.ptr, 0, 8, c.stream)) ;
 
+    if (stream)
+    {
+        int asz = 0 ;
+        const uint64_t ident = identity_bits (s.z_code, s.add_opcode, &asz) ;
+        GB200_TRY (fill_bits (vals.ptr, acc_size, ident, anvec)) ;
+        GB200_CUDA (cudaMemsetAsync (flags.ptr, 0, anvec, c.stream)) ;
+        SpmvArgs sp ;
+        memset (&sp, 0, sizeof (sp)) ;
+        sp.A = A ; sp.bval = bv ; sp.bpres = bp ;
+        sp.tile_row = Ad->tilerow.as<int32_t> () ; sp.ntiles = Ad->n_tiles ;
+        sp.vals = vals.ptr ; sp.flags = flags.as<uint8_t> () ;
+        sp.nmatch = nmatch.as<unsigned long long> () ;
+        sp.mult_op = s.mult_opcode ; sp.flip = s.flipxy ;
+        if (!launch_typed (s.xy_code, bp ? FAM_SPMV_PRES : FAM_SPMV, s.z_code, s.add_opcode,
+            s.mult_opcode, &sp, grid_cap (sp.ntiles, 8), SPMV_THREADS))
+        { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+    }
     DotVArgs da ;
     memset (&da, 0, sizeof (da)) ;
     da.A = A ; da.bval = bv ; da.bpres = bp ;
@@ -268,10 +326,10 @@ gb200_status run_dotv (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_com
     if (getenv ("GB200_DOTV_G")) G = atoi (getenv ("GB200_DOTV_G")) ;
     da.G = G ;
     const int64_t gpb = 256 / G ;
-    if (!launch_typed (s.xy_code, FAM_DOTV, s.z_code, s.add_opcode, s.mult_opcode, &da,
+    if (!stream && !launch_typed (s.xy_code, FAM_DOTV, s.z_code, s.add_opcode, s.mult_opcode, &da,
         grid_cap ((anvec + gpb - 1) / gpb, 8), 256))
     { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
-    if (da.nitems > 0)
+    if (!stream && da.nitems > 0)
     {
         if (!launch_typed (s.xy_code, FAM_DOTV_LONG, s.z_code, s.add_opcode, s.mult_opcode, &da,
             grid_cap ((da.nitems + 7) / 8, 8), 256))

@@ -473,7 +473,7 @@ dotg_kernel (DotGArgs a)
 // launchers, one set per (xy type); defined in inst_*.cu through GB200_INSTANTIATE_TYPE
 // ---------------------------------------------------------------------------------------------
 enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_DOTV = 4,
-    FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7 } ;
+    FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -507,6 +507,10 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
         saxpyv_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyVArgs *) args) ;
     else if (family == FAM_SAXPYV_LONG)
         saxpyv_long_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyVArgs *) args) ;
+    else if (family == FAM_SPMV)
+        spmv_stream_kernel<S, false> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
+    else if (family == FAM_SPMV_PRES)
+        spmv_stream_kernel<S, true> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
     else
         dot_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotArgs *) args) ;
 }

@@ -164,6 +164,147 @@ dotv_long_kernel (DotVArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// pull without a mask, streamed: w = A'*u as an entry-balanced SpMV over the semiring.
+//
+// dotv_kernel gives every vector of A one lane group, so on a power-law matrix most lanes of a
+// group idle (short vectors) or one group drags on (hubs).  Here the ENTRIES of A are cut into tiles
+// of SPMV_TILE consecutive entries, whatever vectors they belong to: a block streams its tile
+// (indices and values fully coalesced, u gathered through L2), leaves the products in shared memory,
+// and then reduces the vector segments that lie in the tile -- a thread per short segment, a warp per
+// segment longer than 32.  A vector that lies inside one tile is stored directly; one that straddles
+// tiles is combined with the monoid's atomic.  tile_row [t] (depends on A only, cached on the
+// handle) is the stored vector that holds entry t * SPMV_TILE.
+// ---------------------------------------------------------------------------------------------
+constexpr int SPMV_TILE = 2048 ;
+constexpr int SPMV_THREADS = 256 ;
+constexpr int SPMV_PER_THREAD = SPMV_TILE / SPMV_THREADS ;
+
+struct SpmvArgs
+{
+    DMat A ;
+    const void *bval ;              // u as a dense array of vlen values
+    const uint32_t *bpres ;         // presence bitmap of u (HAS_PRES instantiation), else nullptr
+    const int32_t *tile_row ;       // ntiles entries
+    int64_t ntiles ;
+    void *vals ;                    // acc_t per stored vector of A, pre-set to the identity
+    uint8_t *flags ;                // pre-zeroed
+    unsigned long long *nmatch ;
+    int mult_op ; int flip ;
+} ;
+
+template <class S, bool HAS_PRES>
+__global__ void __launch_bounds__ (SPMV_THREADS)
+spmv_stream_kernel (SpmvArgs a)
+{
+    using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
+    __shared__ acc_t sprod [SPMV_TILE] ;
+    __shared__ uint32_t spres [SPMV_TILE / 32] ;
+    __shared__ int32_t s_long [SPMV_TILE / 32] ;
+    __shared__ int s_nlong ;
+    const S sr (a.mult_op, a.flip != 0) ;
+    const T *__restrict__ Ax = (const T *) a.A.x ;
+    const T *__restrict__ Bv = (const T *) a.bval ;
+    const int32_t *__restrict__ Ai = a.A.i ;
+    const int64_t *__restrict__ Ap = a.A.p ;
+    acc_t *__restrict__ vals = (acc_t *) a.vals ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5 ;
+    const int64_t nnz = a.A.nnz, nvec = a.A.nvec ;
+    unsigned long long nm = 0 ;
+    for (int64_t tile = blockIdx.x ; tile < a.ntiles ; tile += gridDim.x)
+    {
+        const int64_t e0 = tile * SPMV_TILE ;
+        const int64_t e1 = (e0 + SPMV_TILE < nnz) ? (e0 + SPMV_TILE) : nnz ;
+        // ---- phase 1: products of the tile into shared memory --------------------------------
+        #pragma unroll
+        for (int k = 0 ; k < SPMV_PER_THREAD ; k++)
+        {
+            const int idx = k * SPMV_THREADS + tid ;
+            const int64_t p = e0 + idx ;
+            bool f = false ;
+            acc_t v = Mon::identity () ;
+            if (p < e1)
+            {
+                const int64_t j = __ldg (Ai + p) ;
+                if (!HAS_PRES || bit_test (a.bpres, j))
+                {
+                    v = sr.product (Ax [p], Bv [j]) ;
+                    f = true ;
+                }
+            }
+            sprod [idx] = v ;
+            if (HAS_PRES)
+            {
+                const unsigned m = __ballot_sync (0xffffffffu, f) ;
+                if (lane == 0) spres [idx >> 5] = m ;
+            }
+            nm += f ? 1 : 0 ;
+        }
+        if (tid == 0) s_nlong = 0 ;
+        __syncthreads () ;
+        // ---- phase 2: the vector segments inside the tile ------------------------------------
+        const int64_t r0 = a.tile_row [tile] ;
+        const int64_t r_end = (tile + 1 < a.ntiles) ? (int64_t) a.tile_row [tile + 1] : (nvec - 1) ;
+        for (int64_t r = r0 + tid ; r <= r_end ; r += SPMV_THREADS)
+        {
+            const int64_t ps = __ldg (Ap + r), pe = __ldg (Ap + r + 1) ;
+            const int s = (int) (((ps > e0) ? ps : e0) - e0) ;
+            const int e = (int) (((pe < e1) ? pe : e1) - e0) ;
+            if (e <= s) continue ;
+            if (e - s > 32) { s_long [atomicAdd (&s_nlong, 1)] = (int32_t) (r - r0) ; continue ; }
+            acc_t acc = Mon::identity () ;
+            bool found = false ;
+            for (int q = s ; q < e ; q++)
+            {
+                if (!HAS_PRES || ((spres [q >> 5] >> (q & 31)) & 1u))
+                {
+                    const acc_t v = sprod [q] ;
+                    acc = found ? Mon::combine (acc, v) : v ;
+                    found = true ;
+                }
+            }
+            if (found)
+            {
+                if (ps >= e0 && pe <= e1) vals [r] = acc ; else Mon::atomic_combine (vals + r, acc) ;
+                a.flags [r] = 1 ;
+            }
+        }
+        __syncthreads () ;
+        const int nlong = s_nlong ;
+        for (int k = warp ; k < nlong ; k += SPMV_THREADS / 32)
+        {
+            const int64_t r = r0 + s_long [k] ;
+            const int64_t ps = __ldg (Ap + r), pe = __ldg (Ap + r + 1) ;
+            const int s = (int) (((ps > e0) ? ps : e0) - e0) ;
+            const int e = (int) (((pe < e1) ? pe : e1) - e0) ;
+            acc_t acc = Mon::identity () ;
+            bool found = false ;
+            for (int q = s + lane ; q < e ; q += 32)
+            {
+                if (!HAS_PRES || ((spres [q >> 5] >> (q & 31)) & 1u))
+                {
+                    const acc_t v = sprod [q] ;
+                    acc = found ? Mon::combine (acc, v) : v ;
+                    found = true ;
+                }
+            }
+            const unsigned fm = __ballot_sync (0xffffffffu, found) ;
+            if (fm == 0) continue ;
+            if (!found) acc = Mon::identity () ;
+            for (int off = 16 ; off > 0 ; off >>= 1)
+                acc = Mon::combine (acc, __shfl_down_sync (0xffffffffu, acc, off)) ;
+            if (lane == 0)
+            {
+                if (ps >= e0 && pe <= e1) vals [r] = acc ; else Mon::atomic_combine (vals + r, acc) ;
+                a.flags [r] = 1 ;
+            }
+        }
+        __syncthreads () ;
+    }
+    for (int off = 16 ; off > 0 ; off >>= 1) nm += __shfl_down_sync (0xffffffffu, nm, off) ;
+    if (lane == 0 && nm) atomicAdd (a.nmatch, nm) ;
+}
+
+// ---------------------------------------------------------------------------------------------
 // push: w = A*u.  acc (vlen accumulators, pre-set to the identity) and pres (vlen bits, zeroed).
 // ---------------------------------------------------------------------------------------------
 struct SaxpyVArgs

@@ -184,6 +184,29 @@ gb200_status gb200_partition_by_flops
     const int64_t *Bflops_cumulative, int64_t nvec, int nparts, int64_t *bounds
 ) ;
 
+/* ---- pinned host memory ---------------------------------------------------------------------
+ * A malloc / calloc / realloc / free quartet with the signatures GxB_init takes (reference
+ * Include/GraphBLAS.h:330-340).  A host application that starts the reference with
+ *     GxB_init (mode, gb200_host_malloc, gb200_host_calloc, gb200_host_realloc, gb200_host_free)
+ * keeps every GraphBLAS array (operands, and the T that the shim builds with GB_create) in
+ * page-locked memory, so the copies of gb200_AxB_host / gb200_result_fetch run at PCIe speed.
+ * Blocks of at least GB200_HOST_PIN_MIN bytes are page-locked and recycled through a size-class
+ * cache (page-locking costs ~0.3 ms per MiB); smaller ones come from malloc.  Usable before
+ * gb200_init; without a CUDA device they fall back to plain malloc (memory, not compute). */
+#define GB200_HOST_PIN_MIN (1 << 16)
+void *gb200_host_malloc  (size_t size) ;
+void *gb200_host_calloc  (size_t n, size_t size) ;
+void *gb200_host_realloc (void *p, size_t size) ;
+void  gb200_host_free    (void *p) ;
+void  gb200_host_trim    (void) ;            /* release the cached page-locked blocks       */
+
+/* ---- timing on the library's own stream (CUDA events) ----------------------------------------
+ * gb200_timer_mark records event `slot` (0..7) on the stream every kernel of this library is
+ * launched on; gb200_timer_elapsed_ms synchronises on slot_b and returns the device time between
+ * the two marks.  This is how bench.py times K steps on the launching stream. */
+gb200_status gb200_timer_mark (int slot) ;
+gb200_status gb200_timer_elapsed_ms (int slot_a, int slot_b, double *ms) ;
+
 /* counters: how many kernels this library has launched / how many multiplies it has run */
 int64_t gb200_kernel_launches (void) ;
 int64_t gb200_multiplies (void) ;
