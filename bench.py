@@ -402,6 +402,7 @@ def main():
                     "(0: workload default)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="0: all host cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.workload == "spgemm" and args.scale == 22 and "--scale" not in " ".join(sys.argv):
         args.scale, args.ef = 20, 8
@@ -570,11 +571,13 @@ def main():
 
     # ---- e2e: host buffers in, host T out, every step -----------------------------------------
     e2e_steps = max(1, min(args.steps, 3))
+    rh = None
     step_host()
     step_host()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
+        rh = None               # T of the previous step goes back to the host allocator first
         rh = step_host()
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)

@@ -52,6 +52,7 @@ struct Ctx
     // CUDA events bracketing every semiring-templated launch of the current multiply
     std::vector<cudaEvent_t> kev ;
     int kev_used = 0 ;
+    int mask_policy = 0 ;               // of the current multiply: 0 reference rule, 1 keep, 2 drop
 } ;
 
 Ctx &ctx () ;

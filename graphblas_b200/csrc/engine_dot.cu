@@ -491,8 +491,9 @@ extern "C" {
 gb200_status gb200_AxB_device (gb200_result *out, gb200_dmatrix M, int mask_comp, gb200_dmatrix A,
     gb200_dmatrix B, const gb200_semiring *semiring, int do_adotb, int method)
 {
-    (void) method ;     // saxpy-vs-dot was decided by the caller (GB_AxB_meta.c:266-366); HEAP and
-                        // GUSTAVSON requests run the same GPU saxpy
+    // saxpy-vs-dot was decided by the caller (GB_AxB_meta.c:266-366); HEAP and GUSTAVSON requests
+    // run the same GPU saxpy.  Only the mask-policy flags of the request are looked at.
+    const int mask_policy = (method & GB200_MASK_KEEP) ? 1 : ((method & GB200_MASK_DROP) ? 2 : 0) ;
     if (out == NULL || A == NULL || B == NULL || semiring == NULL) return GB200_INVALID ;
     *out = NULL ;
     GB200_TRY (ensure_init ()) ;
@@ -519,6 +520,7 @@ gb200_status gb200_AxB_device (gb200_result *out, gb200_dmatrix M, int mask_comp
     if (R == NULL) return GB200_OUT_OF_MEMORY ;
     memset (&R->info, 0, sizeof (R->info)) ;
     c.kev_used = 0 ;
+    c.mask_policy = mask_policy ;
     cudaEventRecord (c.ev0, c.stream) ;
     gb200_status st ;
     if (vec_shape (A, B) && (M == NULL || (M->v.vdim == 1 && M->v.nvec == 1 && !M->v.hyper)))

@@ -559,10 +559,11 @@ gb200_status run_saxpy (gb200_result_s *R, const gb200_dmatrix_s *Min, int mask_
     if (M != nullptr && mask_comp) M = nullptr ;            // saxpy cannot use a complemented mask
     DevBuf flops, cum ;
     int64_t total = 0 ;
+    if (M != nullptr && c.mask_policy == 2) M = nullptr ;   // the caller decided for all slices
     if (M != nullptr)
     {
         GB200_TRY (flopcount (&M->v, A, B, flops, cum, &total)) ;
-        if (total <= M->v.nnz) M = nullptr ;                // mask too dense to be worth using
+        if (total <= M->v.nnz && c.mask_policy != 1) M = nullptr ;  // mask too dense to be worth using
     }
     if (M == nullptr) GB200_TRY (flopcount (nullptr, A, B, flops, cum, &total)) ;
     R->info.mask_applied = (M != nullptr) ? 1 : 0 ;

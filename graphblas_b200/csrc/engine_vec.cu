@@ -380,11 +380,12 @@ gb200_status run_saxpyv (gb200_result_s *R, const gb200_dmatrix_s *Min, int mask
         const char *env = getenv ("GB200_FUSE_COMPMASK") ;
         if (env != nullptr && atoi (env) == 0) M = nullptr ;
     }
+    else if (M != nullptr && c.mask_policy == 2) M = nullptr ;
     else if (M != nullptr)
     {
         DevBuf flops, cum ;
         GB200_TRY (flopcount (&M->v, A, B, flops, cum, &masked_flops)) ;
-        if (masked_flops <= M->v.nnz) M = nullptr ;             // GB_AxB_sequential.c:88-95
+        if (masked_flops <= M->v.nnz && c.mask_policy != 1) M = nullptr ;   // GB_AxB_sequential.c:88-95
     }
     R->info.mask_applied = (M != nullptr) ? 1 : 0 ;
 

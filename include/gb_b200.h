@@ -67,7 +67,14 @@ typedef enum
     GB200_METHOD_DEFAULT   = 0,
     GB200_METHOD_GUSTAVSON = 1001,  /* saxpy; reported when the GPU hash/bitmap saxpy ran    */
     GB200_METHOD_HEAP      = 1002,  /* accepted as a request, runs the same saxpy kernels    */
-    GB200_METHOD_DOT       = 1003
+    GB200_METHOD_DOT       = 1003,
+    /* Optional flags OR-ed into a method request (not GrB_Desc_Value codes).  The saxpy path
+     * uses a non-complemented mask only when it pays: it is dropped when total_flops <= nnz(M)
+     * (reference Source/GB_AxB_sequential.c:88-95).  A caller that runs one multiply as several
+     * slices (graphblas_b200/sharded.py, one slice per GPU) makes that decision once on the
+     * global counts and passes it down so that every slice returns the same kind of T: */
+    GB200_MASK_KEEP        = 0x10000,   /* use M whatever the local flop count says           */
+    GB200_MASK_DROP        = 0x20000    /* ignore M (mask_applied = 0)                        */
 } gb200_method ;
 
 /* ---- a borrowed, read-only, host-resident sparse matrix (or n-by-1 vector) -------------- */
