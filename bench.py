@@ -509,15 +509,16 @@ def main():
         if id(m) not in pinned:
             pinned[id(m)] = m.pinned()
         return pinned[id(m)]
-    hcalls = [(pin(m), pin(a), pin(b)) for (m, a, b, _, _, _) in calls]
+    hcalls = [] if args.no_e2e else [(pin(m), pin(a), pin(b)) for (m, a, b, _, _, _) in calls]
 
     def step_device():
-        out = {"flops": 0, "nnz": 0, "device_ms": 0.0, "kernel_ms": 0.0, "nvec": 0}
+        out = {"flops": 0, "nnz": 0, "device_ms": 0.0, "kernel_ms": 0.0, "nvec": 0, "infos": []}
         for (_, _, _, dm, da, db) in calls:
             r = gb.axb_device(dm, w["mask_comp"], da, db, w["semiring"], w["do_adotb"], fetch=False)
             for k in ("flops", "nnz", "device_ms", "kernel_ms"):
                 out[k] += r.info[k]
             out["nvec"] += r.info["nvec"] + 1
+            out["infos"].append(r.info)
         return out
 
     def step_host():
@@ -569,46 +570,74 @@ def main():
     madds, cnz = int(fl[0].item()), int(fl[1].item())
     gflops = 2.0 * madds / t_step / 1e9
 
-    # ---- e2e: host buffers in, host T out, every step -----------------------------------------
-    e2e_steps = max(1, min(args.steps, 3))
-    rh = None
-    step_host()
-    step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        rh = None               # T of the previous step goes back to the host allocator first
-        rh = step_host()
-    torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    t_e2e = te[0].item() / e2e_steps
-    h2d = d2h = 0
-    ab = 0
+    # ---- algorithmic bytes of one step, from the operands and T's counts -------
     nbytes = lambda x: x.p.nbytes + x.i.nbytes + x.x.nbytes + (x.h.nbytes if x.h is not None else 0)
-    seen_once = set()
-    for (m, a, b), res in zip(hcalls, rh):
+    zsize = np.dtype(gb.TYPES[w["semiring"].ztype][1]).itemsize
+    ab = 0
+    for (m, a, b, _, _, _), info in zip(calls, r["infos"]):
         uniq = list({id(x): x for x in (m, a, b) if x is not None}.values())
         # a complemented mask is not read by the saxpy method (GB_AxB_sequential.c:76-81)
-        read = [x for x in uniq if not (x is m and w["mask_comp"] and not res.info["mask_applied"])]
-        for x in uniq:
-            if args.workload == "bfs" and x is a:
-                if id(x) in seen_once:
-                    continue                    # A of a BFS step crosses PCIe once per step
-                seen_once.add(id(x))
-            h2d += nbytes(x)
-        T = res.matrix
-        d2h += nbytes(T)
+        read = [x for x in uniq if not (x is m and w["mask_comp"] and not info["mask_applied"])]
         if args.workload == "bfs" and not w["do_adotb"]:
             # vector push: only the vectors of A named by the frontier are traversed
             lens = np.diff(a.p)[b.i]
             ab += 8 * len(a.p) + int(lens.sum()) * (8 + a.x.dtype.itemsize) \
-                + b.nnz * (8 + b.x.dtype.itemsize) + T.nnz * (8 + T.x.dtype.itemsize)
+                + b.nnz * (8 + b.x.dtype.itemsize) + info["nnz"] * (8 + zsize)
             ab += sum(x.nnz * (8 + x.x.dtype.itemsize) for x in read if x is m)
         else:
-            ab += algo_bytes(read, res.info["nvec"], res.info["nnz"], T.x.dtype.itemsize)
-    del rh
+            ab += algo_bytes(read, info["nvec"], info["nnz"], zsize)
+
+    # ---- e2e: host buffers in, host T out, every step -----------------------------------------
+    t_e2e, h2d, d2h, brk = None, 0, 0, None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 3))
+        rh = None
+        step_host()
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            rh = None               # T of the previous step goes back to the host allocator first
+            rh = step_host()
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        t_e2e = te[0].item() / e2e_steps
+        seen_once = set()
+        for (m, a, b), res in zip(hcalls, rh):
+            for x in {id(x): x for x in (m, a, b) if x is not None}.values():
+                if args.workload == "bfs" and x is a:
+                    if id(x) in seen_once:
+                        continue                    # A of a BFS step crosses PCIe once per step
+                    seen_once.add(id(x))
+                h2d += nbytes(x)
+            d2h += nbytes(res.matrix)
+        del rh, res
+        # where one end-to-end step spends its time: the same step through the three entry points
+        # gb200_AxB_host is made of (upload, multiply on resident operands, fetch), each synchronous
+        brk = {"upload_ms": 0.0, "multiply_ms": 0.0, "fetch_ms": 0.0}
+        if args.workload != "bfs":
+            for (m, a, b) in hcalls:
+                t1 = time.perf_counter()
+                ha = gb.DMatrix(a)
+                hb = ha if b is a else gb.DMatrix(b)
+                hm = None if m is None else (ha if m is a else (hb if m is b else gb.DMatrix(m)))
+                t2 = time.perf_counter()
+                import ctypes as _C
+                rhd = _C.c_void_p()
+                sc = w["semiring"].c()
+                gb._check(gb.lib.gb200_AxB_device(_C.byref(rhd), hm._h if hm is not None else None,
+                                                  int(w["mask_comp"]), ha._h, hb._h, _C.byref(sc),
+                                                  int(w["do_adotb"]), 0), "gb200_AxB_device")
+                t3 = time.perf_counter()
+                gb._fetch(rhd, True, True)
+                t4 = time.perf_counter()
+                for hx in {id(x): x for x in (ha, hb, hm) if x is not None}.values():
+                    hx.free()
+                brk["upload_ms"] += (t2 - t1) * 1e3
+                brk["multiply_ms"] += (t3 - t2) * 1e3
+                brk["fetch_ms"] += (t4 - t3) * 1e3
 
     # ---- roofline of the dominant (semiring) kernels, rank 0's slice --------------------------
     peak, peak_src = measured_peak()
@@ -631,17 +660,18 @@ def main():
                            "multiplies_per_step": len(calls),
                            "timing": "CUDA events on the library's launching stream around the K "
                                      "steps, max over ranks; wall clock alongside",
-                           "l2": "inputs larger than L2 (no flush needed)" if h2d > 2.6e8 else
+                           "l2": "inputs larger than L2 (no flush needed)" if ab > 2.6e8 else
                                  "inputs smaller than L2",
                            "partition": f"{world} flop-balanced contiguous slices of "
                                         f"{ {'M': 'the mask', 'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors"},
                 "wall_ms_per_step": tt[1].item() / args.steps * 1e3,
                 "device_ms_per_step": float(np.mean(dev_ms)),
                 "clocks": clk.summary(),
-                "e2e": {"value": 2.0 * madds / t_e2e / 1e9, "unit": "GFLOP/s",
+                "e2e": None if t_e2e is None else
+                       {"value": 2.0 * madds / t_e2e / 1e9, "unit": "GFLOP/s",
                         "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),
-                        "host_memory": "page-locked (gb200_host_malloc)"},
+                        "host_memory": "page-locked (gb200_host_malloc)", "breakdown": brk},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,

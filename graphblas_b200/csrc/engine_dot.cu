@@ -5,6 +5,7 @@
 // Every candidate C(i,j) is a *pair*; a group of lanes computes the pair (dot_kernel, kernels.cuh),
 // leaving a value and a "some index matched" flag per pair; a scan of the flags then packs the
 // results.  Pairs are enumerated in (j, i) order, so packed indices are ascending in every vector.
+#include <chrono>
 #include "engine.cuh"
 #include "scan.cuh"
 #include "kernels.cuh"
@@ -78,15 +79,16 @@ __global__ void dot_cnt_rect_kernel (const int64_t *__restrict__ pos, int64_t an
 constexpr int64_t DOTG_CHUNK = 256 ;        // tasks per work item of dotg_kernel
 
 // per mask entry: which vector owns the pair and how long the walk is.  own = 1: B(:,j) owns and
-// A(:,i) is walked (wl > 0); A-owned pairs have wl < 0 and are counted per vector of A; dead: wl = 0
+// A(:,i) is walked (wl > 0); A-owned pairs have wl < 0 and are counted per vector of A; dead: wl = 0.
+// Pairs whose owner is shorter than DOTG_SMALL are not worth a shared-memory table: small = 1.
 __global__ void dotg_classify_kernel (DMat A, DMat B, DMat M, const int32_t *__restrict__ mvec,
-    int64_t mnz, uint8_t *__restrict__ own, int32_t *__restrict__ wl,
+    int64_t mnz, uint8_t *__restrict__ own, uint8_t *__restrict__ small, int32_t *__restrict__ wl,
     unsigned long long *__restrict__ cntA)
 {
     for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; e < mnz ;
         e += (int64_t) gridDim.x * blockDim.x)
     {
-        uint8_t o = 0 ;
+        uint8_t o = 0, sm = 0 ;
         int32_t w = 0 ;
         const int64_t ka = dm_vecpos (A, M.i [e]) ;
         const int64_t kb = dm_vecpos (B, dm_vecname (M, mvec [e])) ;
@@ -95,25 +97,32 @@ __global__ void dotg_classify_kernel (DMat A, DMat B, DMat M, const int32_t *__r
             const int64_t ainz = A.p [ka+1] - A.p [ka], bjnz = B.p [kb+1] - B.p [kb] ;
             if (ainz > 0 && bjnz > 0)
             {
-                if (dot_walkA (ainz, bjnz, A.vlen)) { o = 1 ; w = (int32_t) ainz ; }
+                const bool walkA = dot_walkA (ainz, bjnz, A.vlen) ;
+                const int64_t olen = walkA ? bjnz : ainz ;
+                if (olen < DOTG_SMALL) { sm = 1 ; w = 1 ; }
+                else if (walkA) { o = 1 ; w = (int32_t) ainz ; }
                 else { w = -(int32_t) bjnz ; atomicAdd (cntA + ka, 1ULL) ; }
             }
         }
         own [e] = o ;
+        small [e] = sm ;
         wl [e] = w ;
     }
 }
 
-// plist [0..n0) = B-owned entries in mask order; plist [n0..) = A-owned entries grouped by vector of A
+// plist [0..n0) = B-owned entries in mask order; plist [n0..n0+n1) = A-owned entries grouped by vector
+// of A; slist = the small pairs in mask order
 __global__ void dotg_lists_kernel (DMat A, DMat M, const uint8_t *__restrict__ own,
-    const int32_t *__restrict__ wl, int64_t mnz, const int64_t *__restrict__ pos0,
+    const uint8_t *__restrict__ small, const int32_t *__restrict__ wl, int64_t mnz,
+    const int64_t *__restrict__ pos0, const int64_t *__restrict__ poss,
     const int64_t *__restrict__ offA, unsigned long long *__restrict__ curA, int64_t n0,
-    int32_t *__restrict__ plist)
+    int32_t *__restrict__ plist, int32_t *__restrict__ slist)
 {
     for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; e < mnz ;
         e += (int64_t) gridDim.x * blockDim.x)
     {
         if (own [e]) plist [pos0 [e]] = (int32_t) e ;
+        else if (small [e]) slist [poss [e]] = (int32_t) e ;
         else if (wl [e] < 0)
         {
             const int64_t ka = dm_vecpos (A, M.i [e]) ;
@@ -159,39 +168,44 @@ __global__ void dotg_tasks_kernel (DMat A, DMat B, DMat M, const int32_t *__rest
     }
 }
 
-__device__ int64_t g_giant_mult = 4 ;
-
-// tasks per work item: giant owners (Bloom filter of 64 KB to build per item) get bigger items
-__device__ __forceinline__ int64_t dotg_chunk_of (const DMat &O, const DMat &M, int orient, int64_t v)
+// Owners that need several table loads are HUB owners: their items are big (DOTG_HUB_TASKS tasks,
+// walked a lane per task) and go to their own launch; the others get DOTG_CHUNK tasks per item.
+// Returns the tasks per work item of owner v if it belongs to the class `hub`, else 0.
+__device__ __forceinline__ int64_t dotg_chunk_of (const DMat &O, const DMat &M, int orient, int64_t v,
+    int64_t cap, int hub)
 {
     int64_t ko = v ;
     if (!orient) ko = dm_vecpos (O, dm_vecname (M, v)) ;
-    if (ko < 0) return DOTG_CHUNK ;
+    if (ko < 0) return hub ? 0 : DOTG_CHUNK ;
     const int64_t olen = O.p [ko+1] - O.p [ko] ;
-    return (olen > DOTG_CAP) ? g_giant_mult * DOTG_CHUNK : DOTG_CHUNK ;
+    const bool is_hub = (olen > cap && olen != O.vlen) ;
+    if (is_hub != (hub != 0)) return 0 ;
+    return is_hub ? (int64_t) DOTG_HUB_TASKS : DOTG_CHUNK ;
 }
 
-__global__ void dotg_nchunks_kernel (DMat O, DMat M, int orient, const int64_t *__restrict__ start,
-    int64_t n, int64_t *__restrict__ nch)
+__global__ void dotg_nchunks_kernel (DMat O, DMat M, int orient, int64_t cap, int hub,
+    const int64_t *__restrict__ start, int64_t n, int64_t *__restrict__ nch)
 {
     for (int64_t v = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; v < n ;
         v += (int64_t) gridDim.x * blockDim.x)
     {
         const int64_t cnt = start [v+1] - start [v] ;
-        const int64_t ch = (cnt > 0) ? dotg_chunk_of (O, M, orient, v) : 1 ;
-        nch [v] = (cnt + ch - 1) / ch ;
+        const int64_t ch = (cnt > 0) ? dotg_chunk_of (O, M, orient, v, cap, hub) : 0 ;
+        nch [v] = (ch > 0) ? (cnt + ch - 1) / ch : 0 ;
     }
 }
 
-__global__ void dotg_items_kernel (DMat O, DMat M, int orient, const int64_t *__restrict__ start,
-    const int64_t *__restrict__ ioff, int64_t n, DotItem *__restrict__ items)
+__global__ void dotg_items_kernel (DMat O, DMat M, int orient, int64_t cap, int hub,
+    const int64_t *__restrict__ start, const int64_t *__restrict__ ioff, int64_t n,
+    DotItem *__restrict__ items)
 {
     for (int64_t v = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; v < n ;
         v += (int64_t) gridDim.x * blockDim.x)
     {
         const int64_t s0 = start [v], s1 = start [v+1] ;
         if (s1 <= s0) continue ;
-        const int64_t ch = dotg_chunk_of (O, M, orient, v) ;
+        const int64_t ch = dotg_chunk_of (O, M, orient, v, cap, hub) ;
+        if (ch <= 0) continue ;
         int64_t q = ioff [v] ;
         for (int64_t e0 = s0 ; e0 < s1 ; e0 += ch, q++)
         {
@@ -215,9 +229,9 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
     Ctx &c = ctx () ;
     if (M != nullptr && !mask_comp)
     {
-        // the masked kernel probes long vectors through their hash index (cached on the handle)
-        GB200_TRY (ensure_vechash (const_cast<gb200_dmatrix_s *> (Ad))) ;
-        GB200_TRY (ensure_vechash (const_cast<gb200_dmatrix_s *> (Bd))) ;
+        // pattern-only operands (one repeated value) need no value loads (cached on the handle)
+        GB200_TRY (ensure_iso (const_cast<gb200_dmatrix_s *> (Ad))) ;
+        GB200_TRY (ensure_iso (const_cast<gb200_dmatrix_s *> (Bd))) ;
     }
     const DMat &A = Ad->v ;
     const DMat &B = Bd->v ;
@@ -275,44 +289,56 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             count_launch () ;
             // ---- split the pairs by owner (the longer vector); regroup the A-owned ones by i -------
             const int64_t anvec = A.nvec ;
-            DevBuf own, wl, cntA, offA, curA, pos0, off0, plist ;
+            const char *iso_env = getenv ("GB200_DOTG_ISO") ;        // 0: take the general path anyway
+            const bool iso = (A.iso && B.iso) && !(iso_env != nullptr && atoi (iso_env) == 0) ;
+            const int64_t cap = dotg_cap (iso) ;
+            DevBuf own, small, wl, cntA, offA, curA, pos0, poss, off0, plist, slist ;
             GB200_TRY (own.alloc (mnz)) ;
+            GB200_TRY (small.alloc (mnz)) ;
             GB200_TRY (wl.alloc (mnz * sizeof (int32_t))) ;
             GB200_TRY (cntA.alloc ((anvec > 0 ? anvec : 1) * sizeof (int64_t))) ;
             GB200_TRY (curA.alloc ((anvec > 0 ? anvec : 1) * sizeof (int64_t))) ;
             GB200_TRY (offA.alloc ((anvec + 1) * sizeof (int64_t))) ;
             GB200_TRY (pos0.alloc ((mnz + 1) * sizeof (int64_t))) ;
+            GB200_TRY (poss.alloc ((mnz + 1) * sizeof (int64_t))) ;
             GB200_TRY (off0.alloc ((Mv.nvec + 1) * sizeof (int64_t))) ;
             GB200_TRY (plist.alloc (mnz * sizeof (int32_t))) ;
+            GB200_TRY (slist.alloc (mnz * sizeof (int32_t))) ;
             GB200_CUDA (cudaMemsetAsync (cntA.ptr, 0, cntA.bytes, c.stream)) ;
             GB200_CUDA (cudaMemsetAsync (curA.ptr, 0, curA.bytes, c.stream)) ;
             dotg_classify_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, B, Mv,
-                mvec.as<int32_t> (), mnz, own.as<uint8_t> (), wl.as<int32_t> (),
+                mvec.as<int32_t> (), mnz, own.as<uint8_t> (), small.as<uint8_t> (), wl.as<int32_t> (),
                 cntA.as<unsigned long long> ()) ;
             count_launch () ;
             // B-owned pairs keep the mask's order (a compaction); A-owned pairs: counting sort by i
             GB200_TRY (scan_u8 (own.as<uint8_t> (), pos0.as<int64_t> (), mnz)) ;
+            GB200_TRY (scan_u8 (small.as<uint8_t> (), poss.as<int64_t> (), mnz)) ;
             GB200_TRY (scan_i64 (cntA.as<int64_t> (), offA.as<int64_t> (), anvec)) ;
-            int64_t n0 = 0, n1 = 0 ;
+            int64_t n0 = 0, n1 = 0, ns = 0 ;
             GB200_TRY (read_i64 (pos0.as<int64_t> () + mnz, &n0)) ;
+            GB200_TRY (read_i64 (poss.as<int64_t> () + mnz, &ns)) ;
             GB200_TRY (read_i64 (offA.as<int64_t> () + anvec, &n1)) ;
             dotg_lists_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, Mv,
-                own.as<uint8_t> (), wl.as<int32_t> (), mnz, pos0.as<int64_t> (), offA.as<int64_t> (),
-                curA.as<unsigned long long> (), n0, plist.as<int32_t> ()) ;
+                own.as<uint8_t> (), small.as<uint8_t> (), wl.as<int32_t> (), mnz, pos0.as<int64_t> (),
+                poss.as<int64_t> (), offA.as<int64_t> (), curA.as<unsigned long long> (), n0,
+                plist.as<int32_t> (), slist.as<int32_t> ()) ;
             dot_cum_list_kernel <<<grid_cap ((Mv.nvec + 256) / 256, 8), 256, 0, c.stream>>> (Mv.p,
                 pos0.as<int64_t> (), Mv.nvec, off0.as<int64_t> ()) ;
             count_launch (2) ;
+            if (ns > 0)
+            {
+                // short owner, shorter walk: a group of 4 lanes per pair, no table
+                da.mode = DOT_MASK ; da.mvec = mvec.as<int32_t> () ; da.plist = slist.as<int32_t> () ;
+                da.npairs = ns ; da.vals = vals.ptr ; da.flags = flags.as<uint8_t> () ; da.G = 4 ;
+                if (!launch_typed (s.xy_code, FAM_DOT, s.z_code, s.add_opcode, s.mult_opcode, &da,
+                    grid_cap ((ns + 63) / 64, 16), 256))
+                { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+            }
             DotGArgs ga ;
             memset (&ga, 0, sizeof (ga)) ;
             DevBuf next_item ;
             GB200_TRY (next_item.alloc (16)) ;
             ga.next_item = next_item.as<unsigned long long> () ;
-            ga.use_bloom = getenv ("GB200_DOTG_BLOOM") ? atoi (getenv ("GB200_DOTG_BLOOM")) : 1 ;
-            {
-                const int64_t gm = getenv ("GB200_DOTG_GIANT") ? atoll (getenv ("GB200_DOTG_GIANT")) : 4 ;
-                GB200_CUDA (cudaMemcpyToSymbolAsync (g_giant_mult, &gm, sizeof (gm), 0,
-                    cudaMemcpyHostToDevice, c.stream)) ;
-            }
             ga.A = A ; ga.B = B ; ga.M = Mv ;
             ga.vals = vals.ptr ; ga.flags = flags.as<uint8_t> () ;
             ga.nmatch = nmatch.as<unsigned long long> () ;
@@ -325,7 +351,7 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 const int64_t *off = orient ? offA.as<int64_t> () : off0.as<int64_t> () ;
                 const int64_t nown = orient ? anvec : Mv.nvec ;
                 // tasks: one per pair, or one per DOTG_SEG-long segment of a long walk
-                DevBuf nt, toff, tasks, otoff, nch, ioff, items ;
+                DevBuf nt, toff, tasks, otoff, nch, ioff ;
                 GB200_TRY (nt.alloc (np * sizeof (int64_t))) ;
                 GB200_TRY (toff.alloc ((np + 1) * sizeof (int64_t))) ;
                 dotg_ntask_kernel <<<grid_cap ((np + 255) / 256, 16), 256, 0, c.stream>>> (pl, np,
@@ -338,30 +364,39 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 dotg_tasks_kernel <<<grid_cap ((np + 255) / 256, 16), 256, 0, c.stream>>> (A, B, Mv,
                     mvec.as<int32_t> (), orient, pl, np, wl.as<int32_t> (), toff.as<int64_t> (),
                     tasks.as<DotTask> ()) ;
-                // task range of every owner, cut into work items
+                // task range of every owner, cut into work items: hub owners first (the big items)
                 GB200_TRY (otoff.alloc ((nown + 1) * sizeof (int64_t))) ;
                 GB200_TRY (nch.alloc ((nown > 0 ? nown : 1) * sizeof (int64_t))) ;
                 GB200_TRY (ioff.alloc ((nown + 1) * sizeof (int64_t))) ;
                 dot_cum_list_kernel <<<grid_cap ((nown + 256) / 256, 8), 256, 0, c.stream>>> (off,
                     toff.as<int64_t> (), nown, otoff.as<int64_t> ()) ;
-                dotg_nchunks_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                    orient ? A : B, Mv, orient, otoff.as<int64_t> (), nown, nch.as<int64_t> ()) ;
-                count_launch (3) ;
-                GB200_TRY (scan_i64 (nch.as<int64_t> (), ioff.as<int64_t> (), nown)) ;
-                int64_t nitems = 0 ;
-                GB200_TRY (read_i64 (ioff.as<int64_t> () + nown, &nitems)) ;
-                if (nitems == 0) continue ;
-                GB200_TRY (items.alloc (nitems * sizeof (DotItem))) ;
-                dotg_items_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                    orient ? A : B, Mv, orient, otoff.as<int64_t> (), ioff.as<int64_t> (), nown,
-                    items.as<DotItem> ()) ;
                 count_launch () ;
-                GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 16, c.stream)) ;
-                ga.tasks = tasks.as<DotTask> () ;
-                ga.items = items.as<DotItem> () ; ga.nitems = nitems ; ga.orient = orient ;
-                if (!launch_typed (s.xy_code, FAM_DOTG, s.z_code, s.add_opcode, s.mult_opcode, &ga,
-                    grid_cap (nitems, 3), DOTG_THREADS))
-                { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+                ga.tasks = tasks.as<DotTask> () ; ga.orient = orient ;
+                for (int hub = 1 ; hub >= 0 ; hub--)
+                {
+                    dotg_nchunks_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
+                        orient ? A : B, Mv, orient, cap, hub, otoff.as<int64_t> (), nown,
+                        nch.as<int64_t> ()) ;
+                    count_launch () ;
+                    GB200_TRY (scan_i64 (nch.as<int64_t> (), ioff.as<int64_t> (), nown)) ;
+                    int64_t nitems = 0 ;
+                    GB200_TRY (read_i64 (ioff.as<int64_t> () + nown, &nitems)) ;
+                    if (nitems == 0) continue ;
+                    DevBuf items ;
+                    GB200_TRY (items.alloc (nitems * sizeof (DotItem))) ;
+                    dotg_items_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
+                        orient ? A : B, Mv, orient, cap, hub, otoff.as<int64_t> (), ioff.as<int64_t> (),
+                        nown, items.as<DotItem> ()) ;
+                    count_launch () ;
+                    GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 16, c.stream)) ;
+                    ga.items = items.as<DotItem> () ; ga.nitems = nitems ;
+                    const int fam = hub ? (iso ? FAM_DOTG_HUB_ISO : FAM_DOTG_HUB)
+                                        : (iso ? FAM_DOTG_ISO : FAM_DOTG) ;
+                    if (!launch_typed (s.xy_code, fam, s.z_code, s.add_opcode, s.mult_opcode, &ga,
+                        grid_cap (nitems, (iso && !hub) ? 3 : 2), DOTG_THREADS))
+                    { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+                    // `items` is released in stream order, after the kernel that reads it
+                }
             }
         }
         GB200_TRY (scan_u8 (flags.as<uint8_t> (), pos.as<int64_t> (), mnz)) ;
@@ -578,6 +613,10 @@ gb200_status gb200_AxB_host (gb200_result *out, const gb200_matrix *M, int mask_
     }
     gb200_dmatrix dM = NULL, dA = NULL, dB = NULL ;
     gb200_status st = GB200_SUCCESS ;
+    const bool trace = (getenv ("GB200_TRACE") != NULL) ;       // wall time of the phases, to stderr
+    auto now = [] () { return std::chrono::duration<double, std::milli> (
+        std::chrono::steady_clock::now ().time_since_epoch ()).count () ; } ;
+    const double t0 = trace ? now () : 0 ;
     // operands may be the same host object (C=A*A; the tricount mask C<L>=L*U' is its own operand):
     // each distinct object crosses PCIe once
     auto same = [] (const gb200_matrix *X, const gb200_matrix *Y)
@@ -592,10 +631,15 @@ gb200_status gb200_AxB_host (gb200_result *out, const gb200_matrix *M, int mask_
     {
         if (same (M, A)) dM = dA ; else if (same (M, B)) dM = dB ; else st = gb200_upload (&dM, M) ;
     }
+    const double t1 = trace ? now () : 0 ;
     if (st == GB200_SUCCESS) st = gb200_AxB_device (out, dM, mask_comp, dA, dB, semiring, do_adotb, method) ;
+    const double t2 = trace ? now () : 0 ;
     if (dM != dA && dM != dB) gb200_dmatrix_free (&dM) ;
     if (dB != dA) gb200_dmatrix_free (&dB) ;
     gb200_dmatrix_free (&dA) ;
+    if (trace)
+        fprintf (stderr, "gb200_AxB_host: upload %.3f ms, multiply %.3f ms, release %.3f ms\n",
+            t1 - t0, t2 - t1, now () - t2) ;
     return st ;
 }
 

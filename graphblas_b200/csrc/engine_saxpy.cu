@@ -265,6 +265,68 @@ __global__ void sym_hash_kernel (DMat A, DMat B, const int32_t *__restrict__ col
 }
 
 // =============================================================================================
+// symbolic phase when the index range is small (vlen <= SYMB_MAX_VLEN): a vlen-bit bitmap in shared
+// memory instead of a hash set.  Marking is one shared atomicOr per product; the pattern comes out of
+// the bitmap already ascending, so the FILL pass needs no sort.
+// =============================================================================================
+constexpr int64_t SYMB_MAX_VLEN = 512 * 1024 ;          // 64 KB of shared memory
+
+template <bool FILL>
+__global__ void sym_bitmap_kernel (DMat A, DMat B, const int32_t *__restrict__ cols, int64_t ncols,
+    int nwords, int64_t *__restrict__ cnt, const int64_t *__restrict__ Cp, int32_t *__restrict__ Ci)
+{
+    extern __shared__ uint32_t sbm [] ;
+    __shared__ int64_t ws [33] ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5 ;
+    for (int64_t c = blockIdx.x ; c < ncols ; c += gridDim.x)
+    {
+        const int64_t kk = cols [c] ;
+        for (int t = threadIdx.x ; t < nwords ; t += blockDim.x) sbm [t] = 0u ;
+        __syncthreads () ;
+        const int64_t pb0 = B.p [kk], pb1 = B.p [kk+1] ;
+        for (int64_t pb = pb0 + warp ; pb < pb1 ; pb += nwarps)
+        {
+            int64_t pa, pe ;
+            if (!dm_lookup (A, B.i [pb], pa, pe)) continue ;
+            for (int64_t p = pa + lane ; p < pe ; p += 32)
+            {
+                const uint32_t i = (uint32_t) __ldg (A.i + p) ;
+                const uint32_t bit = 1u << (i & 31) ;
+                if (!(sbm [i >> 5] & bit)) atomicOr (sbm + (i >> 5), bit) ;
+            }
+        }
+        __syncthreads () ;
+        if (!FILL)
+        {
+            int64_t mine = 0 ;
+            for (int t = threadIdx.x ; t < nwords ; t += blockDim.x) mine += __popc (sbm [t]) ;
+            int64_t total ;
+            block_excl_scan_i64 (mine, ws, total) ;
+            if (threadIdx.x == 0) cnt [kk] = total ;
+        }
+        else
+        {
+            int64_t run = Cp [kk] ;
+            for (int t0 = 0 ; t0 < nwords ; t0 += blockDim.x)
+            {
+                const int t = t0 + threadIdx.x ;
+                uint32_t word = (t < nwords) ? sbm [t] : 0u ;
+                int64_t total ;
+                int64_t q = run + block_excl_scan_i64 (__popc (word), ws, total) ;
+                while (word)
+                {
+                    const int b = __ffs (word) - 1 ;
+                    Ci [q++] = (int32_t) (t * 32 + b) ;
+                    word &= word - 1 ;
+                }
+                run += total ;
+            }
+        }
+        __syncthreads () ;
+    }
+}
+
+// =============================================================================================
 // heavy vectors: one bitmap of vlen bits per vector in flight
 // =============================================================================================
 // split the heavy vectors of one batch into work items of about `target` flops each
@@ -334,6 +396,14 @@ __global__ void heavy_mark_list_kernel (const int32_t *__restrict__ heavy, int64
             atomicOr (bm + (i >> 5), 1u << (i & 31)) ;
         }
     }
+}
+
+// dst [t] = src [idx [t]]
+__global__ void gather_i64_kernel (const int64_t *__restrict__ src, const int32_t *__restrict__ idx,
+    int64_t n, int64_t *__restrict__ dst)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < n ;
+        t += (int64_t) gridDim.x * blockDim.x) dst [t] = src [idx [t]] ;
 }
 
 // nnz of each heavy vector = popcount of its bitmap
@@ -599,9 +669,30 @@ gb200_status run_saxpy (gb200_result_s *R, const gb200_dmatrix_s *Min, int mask_
         DevBuf cnt ;
         GB200_TRY (cnt.alloc ((nvec > 0 ? nvec : 1) * sizeof (int64_t))) ;
         GB200_CUDA (cudaMemsetAsync (cnt.ptr, 0, cnt.bytes, c.stream)) ;
+        // small index range: a shared-memory bitmap replaces the hash set (and the sort of the fill
+        // pass) wherever scanning vlen/32 words costs less than sorting the vector
+        const int symb_words = (int) ((cvlen + 31) / 32) ;
+        const char *benv = getenv ("GB200_SYM_BITMAP") ;
+        const bool symb_ok = (cvlen <= SYMB_MAX_VLEN) && !(benv != nullptr && atoi (benv) == 0) ;
+        auto use_bitmap = [&] (int cl) { return symb_ok && symb_words <= 8 * class_limit [cl] ; } ;
+        if (symb_ok && (size_t) symb_words * 4 > 48 * 1024)
+        {
+            GB200_CUDA (cudaFuncSetAttribute (sym_bitmap_kernel<false>,
+                cudaFuncAttributeMaxDynamicSharedMemorySize, symb_words * 4)) ;
+            GB200_CUDA (cudaFuncSetAttribute (sym_bitmap_kernel<true>,
+                cudaFuncAttributeMaxDynamicSharedMemorySize, symb_words * 4)) ;
+        }
         for (int cl = 0 ; cl < 4 ; cl++)
         {
             if (bins.n [cl] == 0) continue ;
+            if (use_bitmap (cl))
+            {
+                sym_bitmap_kernel<false> <<<grid_cap (bins.n [cl], 32), class_threads [cl],
+                    (size_t) symb_words * 4, c.stream>>> (A, B, bins.list (cl, nvec), bins.n [cl],
+                    symb_words, cnt.as<int64_t> (), nullptr, nullptr) ;
+                count_launch () ;
+                continue ;
+            }
             const size_t smem = (size_t) 4 << class_log [cl] ;
             if (smem > 48 * 1024)
                 GB200_CUDA (cudaFuncSetAttribute (sym_hash_kernel<false>,
@@ -639,22 +730,54 @@ gb200_status run_saxpy (gb200_result_s *R, const gb200_dmatrix_s *Min, int mask_
         for (int cl = 0 ; cl < 4 ; cl++)
         {
             if (bins.n [cl] == 0) continue ;
-            const size_t smem = ((size_t) 4 << class_log [cl]) + ((size_t) 2 << class_log [cl]) ;
-            if (smem > 48 * 1024)
-                GB200_CUDA (cudaFuncSetAttribute (sym_hash_kernel<true>,
-                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
-            sym_hash_kernel<true> <<<grid_cap (bins.n [cl], 32), class_threads [cl], smem, c.stream>>> (
-                A, B, bins.list (cl, nvec), bins.n [cl], class_log [cl], nullptr, ccum.as<int64_t> (),
-                Ci.as<int32_t> ()) ;
+            if (use_bitmap (cl))
+            {
+                sym_bitmap_kernel<true> <<<grid_cap (bins.n [cl], 32), class_threads [cl],
+                    (size_t) symb_words * 4, c.stream>>> (A, B, bins.list (cl, nvec), bins.n [cl],
+                    symb_words, nullptr, ccum.as<int64_t> (), Ci.as<int32_t> ()) ;
+            }
+            else
+            {
+                const size_t smem = ((size_t) 4 << class_log [cl]) + ((size_t) 2 << class_log [cl]) ;
+                if (smem > 48 * 1024)
+                    GB200_CUDA (cudaFuncSetAttribute (sym_hash_kernel<true>,
+                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
+                sym_hash_kernel<true> <<<grid_cap (bins.n [cl], 32), class_threads [cl], smem, c.stream>>> (
+                    A, B, bins.list (cl, nvec), bins.n [cl], class_log [cl], nullptr, ccum.as<int64_t> (),
+                    Ci.as<int32_t> ()) ;
+            }
             count_launch () ;
             sa.cols = bins.list (cl, nvec) ; sa.ncols = bins.n [cl] ;
             if (!launch_typed (s.xy_code, FAM_SAXPY_LIGHT, s.z_code, s.add_opcode, s.mult_opcode, &sa,
                 grid_cap (bins.n [cl], 32), class_threads [cl]))
             { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
         }
-        for (int64_t h0 = 0 ; h0 < nheavy ; h0 += hws.W)
+        // The accumulators of the heavy vectors in flight are hit by one atomic per product: a batch
+        // is cut so that they (and the bitmaps and ranks) stay resident in L2, otherwise every atomic
+        // is a DRAM read-modify-write
+        std::vector<int64_t> hcnt ((size_t) nheavy) ;
+        if (nheavy > 0)
         {
-            const int64_t nh = (nheavy - h0 < hws.W) ? (nheavy - h0) : hws.W ;
+            DevBuf hc ;
+            GB200_TRY (hc.alloc (nheavy * sizeof (int64_t))) ;
+            gather_i64_kernel <<<grid_cap ((nheavy + 255) / 256, 8), 256, 0, c.stream>>> (cnt.as<int64_t> (),
+                bins.list (CL_HEAVY, nvec), nheavy, hc.as<int64_t> ()) ;
+            count_launch () ;
+            GB200_CUDA (cudaMemcpyAsync (hcnt.data (), hc.ptr, nheavy * sizeof (int64_t),
+                cudaMemcpyDeviceToHost, c.stream)) ;
+            GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
+        }
+        const char *l2env = getenv ("GB200_HEAVY_L2_MB") ;
+        const int64_t l2_budget = ((l2env != nullptr && atoll (l2env) > 0) ? atoll (l2env) : 64) << 20 ;
+        for (int64_t h0 = 0, nh = 0 ; h0 < nheavy ; h0 += nh)
+        {
+            int64_t bytes = 0 ;
+            for (nh = 0 ; h0 + nh < nheavy && nh < hws.W ; nh++)
+            {
+                const int64_t add = hcnt [h0 + nh] * acc_size + hws.nwords * 8 ;
+                if (nh > 0 && bytes + add > l2_budget) break ;
+                bytes += add ;
+            }
             const int32_t *heavy = bins.list (CL_HEAVY, nvec) + h0 ;
             int64_t nitems = 0 ;
             GB200_TRY (heavy_make_items (hws, B, heavy, nh, flops.as<int64_t> (), &nitems)) ;

@@ -746,7 +746,9 @@ gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host)
                 GB200_CUDA (cudaMemcpyAsync (d->h.ptr, host->h, nvec * sizeof (int64_t),
                     cudaMemcpyHostToDevice, c.stream)) ;
         }
-        GB200_TRY (d->i.alloc ((nnz > 0 ? nnz : 1) * sizeof (int32_t))) ;
+        // 16 bytes of slack: the masked dot kernel reads indices in aligned 16-byte chunks
+        GB200_TRY (d->i.alloc (((nnz > 0 ? nnz : 1) + 4) * sizeof (int32_t))) ;
+        GB200_CUDA (cudaMemsetAsync (d->i.as<int32_t> () + (nnz > 0 ? nnz : 1), 0, 4 * sizeof (int32_t), c.stream)) ;
         GB200_TRY (d->x.alloc ((nnz > 0 ? nnz : 1) * (size_t) tsz)) ;
         if (nnz > 0)
         {

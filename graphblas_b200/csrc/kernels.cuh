@@ -129,6 +129,7 @@ struct DotArgs
     int mode ;                  // DOT_MASK: pairs are the entries of M
                                 // DOT_COMP / DOT_NONE: pairs are (ia, jb), ia < A.nvec, jb in [jb0,jb1)
     const int32_t *mvec ;       // DOT_MASK: stored-vector position in M of every entry of M
+    const int32_t *plist ;      // DOT_MASK: the entries of M to compute (nullptr: all npairs of them)
     const int64_t *mposB ;      // DOT_COMP: jb -> position of vector j in M.p, or -1
     int64_t jb0, jb1 ;
     int64_t npairs ;
@@ -157,8 +158,9 @@ __global__ void dot_kernel (DotArgs a)
     unsigned long long nm = 0 ;
     for (int64_t itn = 0 ; itn < niter ; itn++)
     {
-        const int64_t e = gid0 + itn * gstride ;
-        bool live = (e < a.npairs) ;
+        const int64_t t = gid0 + itn * gstride ;
+        bool live = (t < a.npairs) ;
+        const int64_t e = (live && a.plist) ? (int64_t) a.plist [t] : t ;
         int64_t pa = 0, pe = 0, pb = 0, pbe = 0 ;
         if (live)
         {
@@ -270,7 +272,7 @@ __global__ void dot_kernel (DotArgs a)
             // (bit-for-bit except +0.0 + -0.0), so it can be combined unconditionally
             if (gl + off < G) cij = Mon::combine (cij, other) ;
         }
-        if (e < a.npairs && gl == 0)
+        if (t < a.npairs && gl == 0)
         {
             const int wl = threadIdx.x & 31 ;
             const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(G - 1))) ;
@@ -287,19 +289,31 @@ __global__ void dot_kernel (DotArgs a)
 // masked dot products, C<M> = A'*B, grouped by the LONGER vector of each pair ("owner").
 //
 // For a mask entry (i,j) the shorter of A(:,i), B(:,j) is walked and the longer one is probed.  On a
-// power-law graph the walked lengths sum to ~10x the number of matches, so the probes must not go
-// to DRAM: pairs are grouped by their owner vector, a thread block loads the owner into a
-// shared-memory hash table once and then serves every task of its work item from it (owners longer
-// than DOTG_CAP are probed through their global hash index, which stays L2-resident because all
-// work items of one owner run back to back).  orient 0: owner = B(:,j); orient 1: owner = A(:,i)
-// (the mask entries regrouped by i).  A TASK is one pair, or one DOTG_SEG-long segment of a pair
-// whose walked list is longer than that (segments are combined with the monoid's atomic); the warps
-// of a block pull tasks from a shared counter, so one long pair cannot stall a block.
+// power-law graph the walked lengths sum to ~7x the number of matches, so a probe must cost a
+// handful of instructions and never leave the SM: pairs are grouped by their owner vector, a thread
+// block loads the owner into a shared-memory CUCKOO table (two tables, two hash functions, total
+// load <= 0.25) once and then serves every task of its work item from it.  A cuckoo lookup is
+// exactly two shared-memory loads and two compares -- no probe loop, so no divergence -- which lets
+// the walk be unrolled DOTG_U-fold with all its loads in flight.  Owners longer than the table's
+// capacity are loaded segment by segment (both lists are sorted, so every task keeps a cursor and
+// each walked index is probed against exactly one segment).  orient 0: owner = B(:,j); orient 1:
+// owner = A(:,i) (the mask entries regrouped by i).  A TASK is one pair, or one DOTG_SEG-long
+// segment of a pair whose walked list is longer than that (pieces are combined with the monoid's
+// atomic); the warps of a block pull tasks from a shared counter, so one long pair cannot stall a
+// block.  ISO = both operands hold one repeated value (a pattern-only matrix, e.g. an adjacency
+// matrix of ones): the product is a constant, no value is loaded, and a task reduces to counting
+// its matches.  Pairs whose owner is shorter than DOTG_SMALL never get here (dot_kernel does them).
 // ---------------------------------------------------------------------------------------------
-constexpr int DOTG_SLOTS = 8192 ;           // shared-memory hash slots per block (64 KB)
-constexpr int DOTG_CAP = 4096 ;             // owners up to this long use the shared-memory table
+constexpr int DOTG_SMEM = 64 * 1024 ;       // table bytes per block
 constexpr int DOTG_SEG = 1024 ;             // longest walk of one task
 constexpr int DOTG_THREADS = 512 ;
+constexpr int DOTG_U = 4 ;                  // walk unrolling: 32 * DOTG_U indices per warp iteration
+constexpr int DOTG_HUB_TASKS = 16384 ;      // tasks of one HUB work item (one 16-bit cursor each)
+constexpr int DOTG_SMALL = 32 ;             // owners shorter than this: dot_kernel, one lane group per pair
+constexpr int DOTG_MAXIT = 48 ;             // longest eviction chain before a table is rebuilt
+
+// owner entries per table load: the two tables together are filled to 3/8 at most
+__host__ __device__ constexpr int dotg_cap (bool iso) { return (DOTG_SMEM / (iso ? 4 : 8)) * 3 / 8 ; }
 
 struct DotItem { int32_t owner ; int32_t pad ; int64_t e0, e1 ; } ;        // owner, task range
 struct DotTask { int32_t e ; int32_t len ; int64_t w0 ; } ;                // len < 0: segment of a split pair
@@ -315,7 +329,6 @@ struct DotGArgs
     uint8_t *flags ;            // pre-zeroed
     unsigned long long *nmatch ;
     unsigned long long *next_item ;     // dynamic work-item counter (zeroed before launch)
-    int use_bloom ;
     int mult_op ; int flip ;
 } ;
 
@@ -339,26 +352,301 @@ __device__ __forceinline__ bool dot_walkA (int64_t ainz, int64_t bjnz, int64_t v
     return (bjnz == vlen) || (ainz != vlen && ainz <= bjnz) ;
 }
 
-template <class S>
-__global__ void __launch_bounds__ (DOTG_THREADS, 3)
+// c (+) c (+) ... (+) c, n >= 1 times, by doubling (any associative monoid; exact for the integer,
+// boolean and MIN/MAX monoids)
+template <class Mon> __device__ __forceinline__ typename Mon::acc_t iso_fold (typename Mon::acc_t c, uint32_t n)
+{
+    using acc_t = typename Mon::acc_t ;
+    if constexpr (Mon::add == GB200_MIN || Mon::add == GB200_MAX || Mon::add == GB200_LOR
+        || Mon::add == GB200_LAND) return c ;                          // idempotent
+    else if constexpr (Mon::add == GB200_PLUS && !std::is_floating_point<acc_t>::value)
+        return wrap_mul<acc_t> (c, (acc_t) n) ;
+    else
+    {
+        acc_t r = c, base = c ;
+        bool have = false ;
+        while (n)
+        {
+            if (n & 1u) { r = have ? Mon::combine (r, base) : base ; have = true ; }
+            n >>= 1 ;
+            if (n) base = Mon::combine (base, base) ;
+        }
+        return r ;
+    }
+}
+
+// what the task loop of one (item, segment) needs
+template <class S> struct DotGSeg
+{
+    const DotTask *tasks ;      // of this item
+    int ntask ;
+    const int32_t *Wi ;         // walked matrix: indices, values
+    const typename S::T *Wx ;
+    const typename S::T *Ox ;   // owner values of this segment
+    typename S::acc_t *vals ;
+    uint8_t *flags ;
+    int32_t vhi ;               // indices above vhi belong to a later segment
+    int NS, sh ;                // table geometry and the two multipliers
+    uint32_t c1, c2 ;
+    bool orient ;
+    typename S::acc_t ciso ;
+} ;
+
+// one cuckoo lookup: exactly two shared-memory loads, no loop
+template <bool ISO, bool DENSE, class slot_t>
+__device__ __forceinline__ bool dotg_probe (const slot_t *tab, uint32_t kq, int NS, int sh, uint32_t c1,
+    uint32_t c2, uint32_t &pos)
+{
+    constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
+    if constexpr (DENSE) { pos = kq ; return (kq != NOKEY) ; }
+    else if constexpr (ISO)
+    {
+        const uint32_t e1 = tab [(kq * c1) >> sh] ;
+        const uint32_t e2 = tab [NS + ((kq * c2) >> sh)] ;
+        return (e1 == kq) | (e2 == kq) ;
+    }
+    else
+    {
+        const uint64_t e1 = tab [(kq * c1) >> sh] ;
+        const uint64_t e2 = tab [NS + ((kq * c2) >> sh)] ;
+        const bool h1 = ((uint32_t) e1 == kq), h2 = ((uint32_t) e2 == kq) ;
+        pos = (uint32_t) ((h1 ? e1 : e2) >> 32) ;
+        return h1 | h2 ;
+    }
+}
+
+// HUB items (owner longer than one table load): every LANE pulls tasks from the shared counter and
+// walks, by itself, the part of its task that falls into the current segment -- eight indices (two
+// 16-byte loads) per step, the cursor of every task kept in shared memory between segments.  There
+// is no cross-lane reduction and the per-visit overhead is paid by one lane, not by a warp; hub items
+// hold thousands of tasks, so the lanes stay busy.  The loop is a state machine so that the 32 lanes
+// of a warp reconverge every step whatever the lengths of their tasks.
+template <class S, bool ISO, class slot_t>
+__device__ __forceinline__ void dotg_lanes (const S &sr, const DotGSeg<S> &g, const slot_t *tab,
+    int *s_next, uint16_t *s_cur, unsigned long long &nm)
+{
+    using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
+    constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
+    const int NS = g.NS, sh = g.sh ;
+    const uint32_t c1 = g.c1, c2 = g.c2 ;
+    int t = -1 ;                        // the task this lane is walking
+    bool more = true ;                  // the counter may still hold tasks
+    int32_t e = 0 ;
+    const int32_t *wp = nullptr ;       // the walked list
+    const T *wx = nullptr ;
+    int pbeg = 0, len = 0, q = 0 ;      // first index to look at, end, next aligned chunk
+    uint32_t cnt = 0 ;
+    acc_t cij = Mon::identity () ;
+    bool found = false ;
+    while (true)
+    {
+        if (t < 0 && more)
+        {
+            const int c = atomicAdd (s_next, 1) ;
+            if (c >= g.ntask) more = false ;
+            else
+            {
+                const int cur = (int) s_cur [c] ;
+                const DotTask d = g.tasks [c] ;
+                const int ln = (d.len < 0) ? -d.len : d.len ;
+                if (cur < ln)
+                {
+                    t = c ; e = d.e ; len = ln ; pbeg = cur ;
+                    wp = g.Wi + d.w0 ; wx = g.Wx + d.w0 ;
+                    // chunks are 16-byte aligned in the index array (its base is 256-byte aligned)
+                    q = cur - (int) ((d.w0 + cur) & 3) ;
+                    cnt = 0 ; found = false ; cij = Mon::identity () ;
+                }
+            }
+        }
+        if (!__any_sync (0xffffffffu, t >= 0 || more)) break ;
+        if (t >= 0)
+        {
+            const int4 ka = __ldg ((const int4 *) (wp + q)) ;
+            int4 kb = make_int4 (0, 0, 0, 0) ;
+            if (q + 4 < len) kb = __ldg ((const int4 *) (wp + q + 4)) ;
+            const int32_t kk [8] = { ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w } ;
+            // Indices of the chunk outside [pbeg,len) belong to other lists and are not probed.  An
+            // index above vhi, or one left behind by an earlier segment, needs no test: the table
+            // holds the owner's indices of this segment only, so it simply misses.
+            const unsigned span = (unsigned) (len - pbeg) ;
+            #pragma unroll
+            for (int c = 0 ; c < 8 ; c++)
+            {
+                const int p = q + c ;
+                const uint32_t kq = ((unsigned) (p - pbeg) < span) ? (uint32_t) kk [c] : NOKEY ;
+                uint32_t pos = 0 ;
+                const bool hit = dotg_probe<ISO, false, slot_t> (tab, kq, NS, sh, c1, c2, pos) ;
+                if constexpr (ISO) cnt += hit ? 1u : 0u ;
+                else if (hit)
+                {
+                    const T ov = g.Ox [pos], wv = wx [p] ;
+                    const acc_t prod = g.orient ? sr.product (ov, wv) : sr.product (wv, ov) ;
+                    cij = found ? Mon::combine (cij, prod) : prod ;
+                    found = true ; cnt++ ;
+                }
+            }
+            // the lists are sorted: the segment ends inside this chunk iff its last index is above vhi
+            const int jl = (len - 1 - q < 7) ? (len - 1 - q) : 7 ;
+            int32_t klast = kk [0] ;
+            #pragma unroll
+            for (int c = 1 ; c < 8 ; c++) klast = (jl >= c) ? kk [c] : klast ;
+            bool stop = false ;
+            int newcur = len ;
+            if (klast > g.vhi)
+            {
+                stop = true ;
+                newcur = (q > pbeg) ? q : pbeg ;
+                #pragma unroll
+                for (int c = 0 ; c < 8 ; c++)
+                    if ((unsigned) (q + c - pbeg) < span && kk [c] <= g.vhi) newcur = q + c + 1 ;
+            }
+            q += 8 ;
+            bool done = stop || (q >= len) ;
+            if (Mon::has_terminal () && !ISO)
+                if (found && Mon::is_terminal (cij)) { done = true ; newcur = len ; }
+            if (done)
+            {
+                s_cur [t] = (uint16_t) newcur ;
+                if (cnt)
+                {
+                    if constexpr (ISO) cij = iso_fold<Mon> (g.ciso, cnt) ;
+                    Mon::atomic_combine (g.vals + e, cij) ;     // one piece per segment
+                    g.flags [e] = 1 ;
+                    nm += cnt ;
+                }
+                t = -1 ;
+            }
+        }
+    }
+}
+
+// Regular items (the owner fits one table load): the warps of the block pull the tasks of the item
+// and walk them against the table in `tab`, DOTG_U x 32 indices per iteration with all loads in
+// flight.  DENSE: the owner holds every index, so there is no table.
+template <class S, bool ISO, bool DENSE, class slot_t>
+__device__ __forceinline__ void dotg_walk (const S &sr, const DotGSeg<S> &g, const slot_t *tab,
+    int *s_next, unsigned long long &nm)
+{
+    using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
+    constexpr uint32_t NOKEY = 0xFFFFFFFEu ;            // a walked index that must not be probed
+    const int lane = threadIdx.x & 31 ;
+    const int NS = g.NS, sh = g.sh ;
+    const uint32_t c1 = g.c1, c2 = g.c2 ;
+    int tk = 0 ;
+    if (lane == 0) tk = atomicAdd (s_next, 1) ;
+    tk = __shfl_sync (0xffffffffu, tk, 0) ;
+    DotTask task ;
+    if (tk < g.ntask) task = g.tasks [tk] ;
+    while (tk < g.ntask)
+    {
+        // claim the next task and fetch its descriptor before working on this one
+        int tkn = 0 ;
+        if (lane == 0) tkn = atomicAdd (s_next, 1) ;
+        tkn = __shfl_sync (0xffffffffu, tkn, 0) ;
+        DotTask tnext ;
+        if (tkn < g.ntask) tnext = g.tasks [tkn] ;
+
+        const bool split = (task.len < 0) ;
+        const int len = split ? -task.len : task.len ;
+        const int32_t *__restrict__ wp = g.Wi + task.w0 ;
+        acc_t cij = Mon::identity () ;
+        bool found = false ;
+        uint32_t cnt = 0 ;
+        for (int p0 = 0 ; p0 < len ; p0 += 32 * DOTG_U)
+        {
+            uint32_t k [DOTG_U] ;
+            #pragma unroll
+            for (int u = 0 ; u < DOTG_U ; u++)
+            {
+                const int p = p0 + 32 * u + lane ;
+                k [u] = (p < len) ? (uint32_t) __ldg (wp + p) : NOKEY ;
+            }
+            #pragma unroll
+            for (int u = 0 ; u < DOTG_U ; u++)
+            {
+                if (u > 0 && p0 + 32 * u >= len) break ;        // warp-uniform
+                const int p = p0 + 32 * u + lane ;
+                uint32_t pos = 0 ;
+                const bool hit = dotg_probe<ISO, DENSE, slot_t> (tab, k [u], NS, sh, c1, c2, pos) ;
+                if constexpr (ISO) cnt += hit ? 1u : 0u ;
+                else if (hit)
+                {
+                    const T ov = g.Ox [pos], wv = g.Wx [task.w0 + p] ;
+                    const acc_t prod = g.orient ? sr.product (ov, wv) : sr.product (wv, ov) ;
+                    cij = found ? Mon::combine (cij, prod) : prod ;
+                    found = true ; cnt++ ;
+                }
+            }
+            if (Mon::has_terminal () && !ISO)
+            {
+                // the terminal value is absorbing: once any lane holds it the pair is decided
+                if (__any_sync (0xffffffffu, found && Mon::is_terminal (cij))) break ;
+            }
+        }
+        // ---- combine the lanes' partial results -------------------------------------------------
+        bool any ;
+        if constexpr (ISO)
+        {
+            cnt = __reduce_add_sync (0xffffffffu, cnt) ;
+            any = (cnt != 0) ;
+            if (any) cij = iso_fold<Mon> (g.ciso, cnt) ;
+            if (lane == 0) nm += cnt ;
+        }
+        else
+        {
+            any = (__ballot_sync (0xffffffffu, found) != 0) ;
+            nm += cnt ;
+            if (any)
+            {
+                for (int off = 16 ; off > 0 ; off >>= 1)
+                {
+                    // a lane without any match holds the identity; identity (+) t == t for every
+                    // monoid (bit-for-bit except +0.0 + -0.0)
+                    const acc_t other = __shfl_down_sync (0xffffffffu, cij, off) ;
+                    cij = Mon::combine (cij, other) ;
+                }
+            }
+        }
+        if (any && lane == 0)
+        {
+            if (split) Mon::atomic_combine (g.vals + task.e, cij) ;
+            else g.vals [task.e] = cij ;
+            g.flags [task.e] = 1 ;
+        }
+        tk = tkn ; task = tnext ;
+    }
+}
+
+// HUB = false: items whose owner fits one table load (or is dense); HUB = true: items of longer owners
+template <class S, bool ISO, bool HUB>
+__global__ void __launch_bounds__ (DOTG_THREADS, (ISO && !HUB) ? 3 : 2)
 dotg_kernel (DotGArgs a)
 {
     using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
-    extern __shared__ int32_t dotg_sm [] ;
-    int32_t *tkeys = dotg_sm ;
-    int32_t *tpos = dotg_sm + DOTG_SLOTS ;
-    __shared__ int s_next ;
+    using slot_t = typename std::conditional<ISO, uint32_t, uint64_t>::type ;
+    extern __shared__ __align__ (16) unsigned char dotg_raw [] ;
+    slot_t *tab = (slot_t *) dotg_raw ;
+    __shared__ int s_next, s_fail ;
+    __shared__ unsigned long long s_item ;
+    __shared__ uint16_t s_cur [HUB ? DOTG_HUB_TASKS : 1] ;
+    constexpr int CAP = dotg_cap (ISO) ;
+    constexpr slot_t EMPTY = (slot_t) ~(slot_t) 0 ;
     const S sr (a.mult_op, a.flip != 0) ;
     const T *__restrict__ Ax = (const T *) a.A.x ;
     const T *__restrict__ Bx = (const T *) a.B.x ;
-    acc_t *__restrict__ vals = (acc_t *) a.vals ;
     const int lane = threadIdx.x & 31 ;
-    const DMat &O = a.orient ? a.A : a.B ;      // owner matrix (probed)
-    const DMat &W = a.orient ? a.B : a.A ;      // walked matrix
-    const int32_t *__restrict__ Wi = W.i ;
+    const bool orient = (a.orient != 0) ;
+    const DMat &O = orient ? a.A : a.B ;        // owner matrix (probed)
+    const DMat &W = orient ? a.B : a.A ;        // walked matrix
+    const T *__restrict__ Oxb = orient ? Ax : Bx ;
     const int64_t vlen = a.A.vlen ;
+    DotGSeg<S> g ;
+    g.Wi = W.i ; g.Wx = orient ? Bx : Ax ;
+    g.vals = (acc_t *) a.vals ; g.flags = a.flags ; g.orient = orient ;
+    g.ciso = Mon::identity () ;
+    if (ISO) g.ciso = sr.product (Ax [0], Bx [0]) ;
     unsigned long long nm = 0 ;
-    __shared__ unsigned long long s_item ;
     while (true)
     {
         // work items vary in cost by orders of magnitude: blocks pull them from a global counter
@@ -370,98 +658,71 @@ dotg_kernel (DotGArgs a)
         const DotItem item = a.items [it] ;
         // ---- the owner vector ---------------------------------------------------------------
         int64_t ko = item.owner ;
-        if (!a.orient) ko = dm_vecpos (a.B, dm_vecname (a.M, item.owner)) ;
+        if (!orient) ko = dm_vecpos (a.B, dm_vecname (a.M, item.owner)) ;
         const int64_t o0 = __ldg (O.p + ko), o1 = __ldg (O.p + ko + 1) ;
         const int64_t olen = o1 - o0 ;
-        const int mode = (olen == vlen) ? 0 : ((olen <= DOTG_CAP) ? 1 : 2) ;
-        const int64_t ohinfo = (mode == 2) ? __ldg (O.hinfo + ko) : -1 ;
-        // mode 1: table of 4x the owner's length (load <= 0.25 keeps probe sequences short and the
-        // clearing cost proportional to the owner); mode 2: all 64 KB are a Bloom filter in front of
-        // the owner's global hash index, so that most misses never leave the SM
-        int lg = 6 ;
-        while ((1 << lg) < 4 * olen && lg < 13) lg++ ;
-        const uint32_t tmask = (1u << lg) - 1u ;
-        uint32_t *bloom = (uint32_t *) dotg_sm ;
-        __syncthreads () ;                          // previous item's probes and counter are done
-        if (threadIdx.x == 0) s_next = 0 ;
-        if (mode == 1)
+        const bool dense = (olen == vlen) ;
+        const int nseg = (!HUB || dense) ? 1 : (int) ((olen + CAP - 1) / CAP) ;
+        g.tasks = a.tasks + item.e0 ;
+        g.ntask = (int) (item.e1 - item.e0) ;
+        if (HUB) for (int t = threadIdx.x ; t < g.ntask ; t += blockDim.x) s_cur [t] = 0 ;
+        for (int seg = 0 ; seg < nseg ; seg++)
         {
-            for (int t = threadIdx.x ; t <= (int) tmask ; t += blockDim.x) tkeys [t] = -1 ;
-            __syncthreads () ;
-            for (int64_t q = o0 + threadIdx.x ; q < o1 ; q += blockDim.x)
+            const int64_t s0 = o0 + (int64_t) seg * CAP ;
+            const int64_t s1 = (s0 + CAP < o1) ? (s0 + CAP) : o1 ;
+            const int slen = (int) (s1 - s0) ;
+            g.vhi = (seg == nseg - 1) ? INT32_MAX : __ldg (O.i + s1 - 1) ;
+            g.Ox = Oxb + s0 ;
+            int lg = 5 ;                        // 2^lg slots per table: total load between 3/16 and 3/8
+            while (3 * (1 << lg) < 4 * slen) lg++ ;
+            const int NS = 1 << lg, sh = 32 - lg ;
+            uint32_t c1 = 0x9E3779B1u, c2 = 0x85EBCA6Bu ;
+            if (!dense)
             {
-                const int32_t key = __ldg (O.i + q) ;
-                uint32_t h = hash32 ((uint32_t) key) >> (32 - lg) ;
-                while (atomicCAS (tkeys + h, -1, key) != -1) h = (h + 1) & tmask ;
-                tpos [h] = (int32_t) (q - o0) ;
-            }
-        }
-        else if (mode == 2 && a.use_bloom)
-        {
-            for (int t = threadIdx.x ; t < 2 * DOTG_SLOTS ; t += blockDim.x) bloom [t] = 0u ;
-            __syncthreads () ;
-            for (int64_t q = o0 + threadIdx.x ; q < o1 ; q += blockDim.x)
-            {
-                const uint32_t b = hash32b ((uint32_t) __ldg (O.i + q)) >> 13 ;    // 19 bits
-                atomicOr (bloom + (b >> 5), 1u << (b & 31)) ;
-            }
-        }
-        __syncthreads () ;
-        // ---- tasks of this item: warps pull them from a shared counter -----------------------
-        const int ntask = (int) (item.e1 - item.e0) ;
-        while (true)
-        {
-            int tk = 0 ;
-            if (lane == 0) tk = atomicAdd (&s_next, 1) ;
-            tk = __shfl_sync (0xffffffffu, tk, 0) ;
-            if (tk >= ntask) break ;
-            const DotTask task = a.tasks [item.e0 + tk] ;
-            const bool split = (task.len < 0) ;
-            const int64_t w0 = task.w0, w1 = task.w0 + (split ? -task.len : task.len) ;
-            acc_t cij = Mon::identity () ;
-            bool found = false ;
-            for (int64_t p = w0 + lane ; p < w1 ; p += 32)
-            {
-                const int32_t k = __ldg (Wi + p) ;
-                int64_t pos = -1 ;
-                if (mode == 0) pos = o0 + k ;
-                else if (mode == 1)
+                for (int attempt = 0 ; ; attempt++)
                 {
-                    uint32_t h = hash32 ((uint32_t) k) >> (32 - lg) ;
-                    while (true)
+                    __syncthreads () ;                  // the table's previous users are done
+                    for (int t = threadIdx.x ; t < 2 * NS ; t += blockDim.x) tab [t] = EMPTY ;
+                    if (threadIdx.x == 0) s_fail = 0 ;
+                    __syncthreads () ;
+                    for (int q = threadIdx.x ; q < slen ; q += blockDim.x)
                     {
-                        const int32_t kk = tkeys [h] ;
-                        if (kk == k) { pos = o0 + tpos [h] ; break ; }
-                        if (kk < 0) break ;
-                        h = (h + 1) & tmask ;
+                        slot_t cur ;
+                        if constexpr (ISO) cur = (uint32_t) __ldg (O.i + s0 + q) ;
+                        else cur = ((uint64_t) (uint32_t) q << 32) | (uint32_t) __ldg (O.i + s0 + q) ;
+                        int which = 0, n = 0 ;
+                        #pragma unroll 1
+                        for ( ; n < DOTG_MAXIT ; n++)
+                        {
+                            const uint32_t k = (uint32_t) cur ;
+                            const uint32_t loc = which ? (NS + ((k * c2) >> sh)) : ((k * c1) >> sh) ;
+                            if constexpr (ISO) cur = atomicExch (tab + loc, cur) ;
+                            else cur = atomicExch ((unsigned long long *) tab + loc, (unsigned long long) cur) ;
+                            if (cur == EMPTY) break ;
+                            which ^= 1 ;                // the evicted entry moves to its other table
+                        }
+                        if (n == DOTG_MAXIT) s_fail = 1 ;
                     }
-                }
-                else
-                {
-                    const uint32_t b = hash32b ((uint32_t) k) >> 13 ;
-                    if (!a.use_bloom || ((bloom [b >> 5] >> (b & 31)) & 1u)) pos = vechash_probe (O, ohinfo, o0, k) ;
-                }
-                if (pos >= 0)
-                {
-                    const acc_t prod = a.orient ? sr.product (Ax [pos], Bx [p]) : sr.product (Ax [p], Bx [pos]) ;
-                    cij = found ? Mon::combine (cij, prod) : prod ;
-                    found = true ; nm++ ;
-                    if (Mon::has_terminal () && Mon::is_terminal (cij)) break ;
+                    __syncthreads () ;
+                    if (!s_fail) break ;
+                    if (attempt >= 30) __trap () ;      // never seen; fail loudly rather than wrongly
+                    c1 = (c1 * 0x01000193u + 0xFE94F82Au) | 1u ;
+                    c2 = (c2 * 0x01000193u + 0x4A8BE922u) | 1u ;
                 }
             }
-            const unsigned fm = __ballot_sync (0xffffffffu, found) ;
-            if (fm == 0) continue ;                 // flags [e] stays 0
-            if (!found) cij = Mon::identity () ;
-            for (int off = 16 ; off > 0 ; off >>= 1)
+            else __syncthreads () ;
+            if (threadIdx.x == 0) s_next = 0 ;
+            __syncthreads () ;
+            g.NS = NS ; g.sh = sh ; g.c1 = c1 ; g.c2 = c2 ;
+            if constexpr (HUB)
             {
-                const acc_t other = __shfl_down_sync (0xffffffffu, cij, off) ;
-                cij = Mon::combine (cij, other) ;
+                if (dense) dotg_walk<S, ISO, true, slot_t> (sr, g, tab, &s_next, nm) ;
+                else dotg_lanes<S, ISO, slot_t> (sr, g, tab, &s_next, s_cur, nm) ;
             }
-            if (lane == 0)
+            else
             {
-                if (split) Mon::atomic_combine (vals + task.e, cij) ;
-                else vals [task.e] = cij ;
-                a.flags [task.e] = 1 ;
+                if (dense) dotg_walk<S, ISO, true, slot_t> (sr, g, tab, &s_next, nm) ;
+                else dotg_walk<S, ISO, false, slot_t> (sr, g, tab, &s_next, nm) ;
             }
         }
     }
@@ -473,7 +734,8 @@ dotg_kernel (DotGArgs a)
 // launchers, one set per (xy type); defined in inst_*.cu through GB200_INSTANTIATE_TYPE
 // ---------------------------------------------------------------------------------------------
 enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_DOTV = 4,
-    FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9 } ;
+    FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9,
+    FAM_DOTG_ISO = 10, FAM_SPMV_NOPIPE = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -488,16 +750,27 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
         saxpy_light_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyArgs *) args) ;
     else if (family == FAM_SAXPY_HEAVY)
         saxpy_heavy_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyArgs *) args) ;
-    else if (family == FAM_DOTG)
+    else if (family == FAM_DOTG || family == FAM_DOTG_ISO || family == FAM_DOTG_HUB
+        || family == FAM_DOTG_HUB_ISO)
     {
-        const int smem = 2 * DOTG_SLOTS * (int) sizeof (int32_t) ;
         static bool attr_set = false ;          // one flag per instantiation
         if (!attr_set)
         {
-            cudaFuncSetAttribute (dotg_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) ;
+            cudaFuncSetAttribute (dotg_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            cudaFuncSetAttribute (dotg_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            cudaFuncSetAttribute (dotg_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            cudaFuncSetAttribute (dotg_kernel<S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
             attr_set = true ;
         }
-        dotg_kernel<S> <<<cfg.grid, cfg.block, smem, cfg.stream>>> (*(const DotGArgs *) args) ;
+        const DotGArgs &ga = *(const DotGArgs *) args ;
+        if (family == FAM_DOTG_ISO)
+            dotg_kernel<S, true, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+        else if (family == FAM_DOTG)
+            dotg_kernel<S, false, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+        else if (family == FAM_DOTG_HUB_ISO)
+            dotg_kernel<S, true, true> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+        else
+            dotg_kernel<S, false, true> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
     }
     else if (family == FAM_DOTV)
         dotv_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotVArgs *) args) ;
@@ -508,9 +781,11 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
     else if (family == FAM_SAXPYV_LONG)
         saxpyv_long_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyVArgs *) args) ;
     else if (family == FAM_SPMV)
-        spmv_stream_kernel<S, false> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
+        spmv_stream_kernel<S, false, true> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
     else if (family == FAM_SPMV_PRES)
-        spmv_stream_kernel<S, true> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
+        spmv_stream_kernel<S, true, true> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
+    else if (family == FAM_SPMV_NOPIPE)
+        spmv_stream_kernel<S, false, false> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
     else
         dot_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotArgs *) args) ;
 }

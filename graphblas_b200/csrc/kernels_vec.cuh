@@ -192,8 +192,10 @@ struct SpmvArgs
     int mult_op ; int flip ;
 } ;
 
-template <class S, bool HAS_PRES>
-__global__ void __launch_bounds__ (SPMV_THREADS)
+// PIPE: the indices and values of the block's NEXT tile are loaded into registers before the
+// segments of the current tile are reduced, so the entry stream stays in flight across the barriers.
+template <class S, bool HAS_PRES, bool PIPE>
+__global__ void __launch_bounds__ (SPMV_THREADS, PIPE ? 4 : 6)
 spmv_stream_kernel (SpmvArgs a)
 {
     using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
@@ -210,24 +212,38 @@ spmv_stream_kernel (SpmvArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5 ;
     const int64_t nnz = a.A.nnz, nvec = a.A.nvec ;
     unsigned long long nm = 0 ;
+    int32_t ji [SPMV_PER_THREAD] ;
+    T av [SPMV_PER_THREAD] ;
+    auto load_tile = [&] (int64_t tile)
+    {
+        const int64_t e0 = tile * SPMV_TILE ;
+        #pragma unroll
+        for (int k = 0 ; k < SPMV_PER_THREAD ; k++)
+        {
+            const int64_t p = e0 + k * SPMV_THREADS + tid ;
+            ji [k] = (p < nnz) ? __ldg (Ai + p) : -1 ;
+            if (p < nnz) av [k] = Ax [p] ;
+        }
+    } ;
+    if (PIPE && blockIdx.x < a.ntiles) load_tile (blockIdx.x) ;
     for (int64_t tile = blockIdx.x ; tile < a.ntiles ; tile += gridDim.x)
     {
         const int64_t e0 = tile * SPMV_TILE ;
         const int64_t e1 = (e0 + SPMV_TILE < nnz) ? (e0 + SPMV_TILE) : nnz ;
+        if (!PIPE) load_tile (tile) ;
         // ---- phase 1: products of the tile into shared memory --------------------------------
         #pragma unroll
         for (int k = 0 ; k < SPMV_PER_THREAD ; k++)
         {
             const int idx = k * SPMV_THREADS + tid ;
-            const int64_t p = e0 + idx ;
             bool f = false ;
             acc_t v = Mon::identity () ;
-            if (p < e1)
+            const int64_t j = ji [k] ;
+            if (j >= 0)
             {
-                const int64_t j = __ldg (Ai + p) ;
                 if (!HAS_PRES || bit_test (a.bpres, j))
                 {
-                    v = sr.product (Ax [p], Bv [j]) ;
+                    v = sr.product (av [k], Bv [j]) ;
                     f = true ;
                 }
             }
@@ -241,6 +257,7 @@ spmv_stream_kernel (SpmvArgs a)
         }
         if (tid == 0) s_nlong = 0 ;
         __syncthreads () ;
+        if (PIPE && tile + gridDim.x < a.ntiles) load_tile (tile + gridDim.x) ;
         // ---- phase 2: the vector segments inside the tile ------------------------------------
         const int64_t r0 = a.tile_row [tile] ;
         const int64_t r_end = (tile + 1 < a.ntiles) ? (int64_t) a.tile_row [tile + 1] : (nvec - 1) ;

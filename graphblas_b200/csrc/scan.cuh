@@ -2,6 +2,7 @@
 // Replaces GB_cumsum (reference Source/GB_cumsum.c:36-89) for Bflops, vector pointers of C and
 // the stream compaction of masked results.
 #pragma once
+#include <type_traits>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -47,7 +48,7 @@ __device__ __forceinline__ int64_t block_excl_scan_i64 (int64_t v, int64_t *ws, 
 }
 
 constexpr int SCAN_THREADS = 256 ;
-constexpr int SCAN_ITEMS = 8 ;
+constexpr int SCAN_ITEMS = 16 ;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS ;
 
 struct ScanState
@@ -58,65 +59,111 @@ struct ScanState
     int64_t *inclusive ;            // per tile
 } ;
 
-// out[t] = sum of in[0..t) for t = 0..n  (n+1 outputs; out[n] is the total)
+// out[t] = sum of in[0..t) for t = 0..n  (n+1 outputs; out[n] is the total).  Single pass with
+// decoupled look-back.  A warp owns 32 * SCAN_ITEMS consecutive items, item q of lane l being
+// q * 32 + l of them, so every load and store is coalesced; rows of 32 are scanned with shuffles.  The
+// look-back over the predecessor tiles is done by a whole warp, 32 tiles per step.
 template <class InT>
 __global__ void __launch_bounds__ (SCAN_THREADS)
 scan_kernel (const InT *__restrict__ in, int64_t *__restrict__ out, int64_t n, ScanState st)
 {
-    __shared__ int64_t ws [33] ;
+    // the sum of one row of 32 small items fits 32 bits
+    using row_t = typename std::conditional<(sizeof (InT) < 8), int32_t, int64_t>::type ;
+    __shared__ int64_t ws [SCAN_THREADS / 32 + 1] ;
     __shared__ unsigned int s_tile ;
     __shared__ int64_t s_prefix ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5 ;
     if (threadIdx.x == 0) s_tile = atomicAdd (st.ticket, 1u) ;
     __syncthreads () ;
     const int64_t tile = s_tile ;
-    const int64_t base = tile * SCAN_TILE + (int64_t) threadIdx.x * SCAN_ITEMS ;
-    int64_t v [SCAN_ITEMS] ;
-    int64_t tsum = 0 ;
+    const int64_t base = tile * SCAN_TILE + (int64_t) warp * (32 * SCAN_ITEMS) + lane ;
+    int64_t ex [SCAN_ITEMS] ;       // exclusive prefix of every item inside the warp's chunk
+    int64_t carry = 0 ;
     #pragma unroll
     for (int q = 0 ; q < SCAN_ITEMS ; q++)
     {
-        const int64_t idx = base + q ;
-        v [q] = (idx < n) ? (int64_t) in [idx] : 0 ;
-        tsum += v [q] ;
+        const int64_t idx = base + q * 32 ;
+        const row_t x = (idx < n) ? (row_t) in [idx] : (row_t) 0 ;
+        row_t incl = x ;
+        #pragma unroll
+        for (int off = 1 ; off < 32 ; off <<= 1)
+        {
+            const row_t y = __shfl_up_sync (0xffffffffu, incl, off) ;
+            if (lane >= off) incl += y ;
+        }
+        ex [q] = carry + (int64_t) (incl - x) ;
+        carry += (int64_t) __shfl_sync (0xffffffffu, incl, 31) ;
     }
-    int64_t total ;
-    int64_t texcl = block_excl_scan_i64 (tsum, ws, total) ;
-    if (threadIdx.x == 0)
+    if (lane == 0) ws [warp] = carry ;
+    __syncthreads () ;
+    if (warp == 0)
     {
+        // exclusive prefix of the warps' totals, and the tile's total
+        const int64_t w = (lane < SCAN_THREADS / 32) ? ws [lane] : 0 ;
+        int64_t wi = w ;
+        #pragma unroll
+        for (int off = 1 ; off < 32 ; off <<= 1)
+        {
+            const int64_t y = __shfl_up_sync (0xffffffffu, wi, off) ;
+            if (lane >= off) wi += y ;
+        }
+        const int64_t total = __shfl_sync (0xffffffffu, wi, 31) ;
+        if (lane < SCAN_THREADS / 32) ws [lane] = wi - w ;
         int64_t prefix = 0 ;
         if (tile == 0)
         {
-            ((volatile int64_t *) st.inclusive) [0] = total ;
-            __threadfence () ;
-            ((volatile int *) st.flag) [0] = 2 ;
+            if (lane == 0)
+            {
+                ((volatile int64_t *) st.inclusive) [0] = total ;
+                __threadfence () ;
+                ((volatile int *) st.flag) [0] = 2 ;
+            }
         }
         else
         {
-            ((volatile int64_t *) st.aggregate) [tile] = total ;
-            __threadfence () ;
-            ((volatile int *) st.flag) [tile] = 1 ;
-            for (int64_t t = tile - 1 ; t >= 0 ; t--)
+            if (lane == 0)
             {
-                int f ;
-                while ((f = ((volatile int *) st.flag) [t]) == 0) { }
+                ((volatile int64_t *) st.aggregate) [tile] = total ;
                 __threadfence () ;
-                if (f == 2) { prefix += ((volatile int64_t *) st.inclusive) [t] ; break ; }
-                prefix += ((volatile int64_t *) st.aggregate) [t] ;
+                ((volatile int *) st.flag) [tile] = 1 ;
             }
-            ((volatile int64_t *) st.inclusive) [tile] = prefix + total ;
-            __threadfence () ;
-            ((volatile int *) st.flag) [tile] = 2 ;
+            for (int64_t t = tile - 1 ; ; t -= 32)
+            {
+                const int64_t idx = t - lane ;
+                int f = 2 ;                         // before tile 0: an inclusive prefix of zero
+                int64_t val = 0 ;
+                if (idx >= 0)
+                {
+                    while ((f = ((volatile int *) st.flag) [idx]) == 0) { }
+                    __threadfence () ;
+                    val = (f == 2) ? ((volatile int64_t *) st.inclusive) [idx]
+                                   : ((volatile int64_t *) st.aggregate) [idx] ;
+                }
+                // the nearest predecessor with an inclusive prefix ends the walk
+                const unsigned done = __ballot_sync (0xffffffffu, f == 2) ;
+                const int last = done ? (__ffs (done) - 1) : 31 ;
+                int64_t part = (lane <= last) ? val : 0 ;
+                #pragma unroll
+                for (int off = 16 ; off > 0 ; off >>= 1) part += __shfl_down_sync (0xffffffffu, part, off) ;
+                prefix += __shfl_sync (0xffffffffu, part, 0) ;
+                if (done) break ;
+            }
+            if (lane == 0)
+            {
+                ((volatile int64_t *) st.inclusive) [tile] = prefix + total ;
+                __threadfence () ;
+                ((volatile int *) st.flag) [tile] = 2 ;
+            }
         }
-        s_prefix = prefix ;
+        if (lane == 0) s_prefix = prefix ;
     }
     __syncthreads () ;
-    int64_t run = s_prefix + texcl ;
+    const int64_t add = s_prefix + ws [warp] ;
     #pragma unroll
     for (int q = 0 ; q < SCAN_ITEMS ; q++)
     {
-        const int64_t idx = base + q ;
-        if (idx <= n) out [idx] = run ;
-        run += v [q] ;
+        const int64_t idx = base + q * 32 ;
+        if (idx <= n) out [idx] = add + ex [q] ;
     }
 }
 

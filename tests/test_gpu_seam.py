@@ -255,3 +255,59 @@ def test_vector_push_unfused_compmask(monkeypatch):
     got = gb.axb_host(M, True, A, u, sr, False)
     assert got.info["mask_applied"] == 0 == info["mask_applied"]
     assert_same(ref, got.matrix, "LOR", "unfused !M")
+
+
+# ---------------------------------------------------------------------------------------------
+# masked dot with hub vectors: owners longer than one shared-memory table load (segments with
+# cursors), a dense owner, walks longer than one task (split pairs), pattern-only (iso) operands
+# and valued ones, pairs with short owners (the lane-group kernel)
+# ---------------------------------------------------------------------------------------------
+def _hub_matrix(n, seed, dtype, iso):
+    rng = np.random.default_rng(seed)
+    S = gen.er(n, n, 6 * n, seed, dtype, lo=1, hi=5).tolil()
+    for c, ln in ((5, 9000), (17, 5000), (40, n), (41, 2500), (90, 1500)):
+        rows = np.sort(rng.choice(n, ln, replace=False))
+        S[rows, c] = rng.integers(1, 5, ln)
+    S = S.tocsc()
+    if iso:
+        S.data[:] = 1
+    return S
+
+
+@pytest.mark.parametrize("iso", [True, False])
+@pytest.mark.parametrize("add,mult,t", [("PLUS", "TIMES", "INT64"), ("MIN", "PLUS", "FP64"),
+                                        ("LOR", "LAND", "BOOL"), ("TIMES", "PLUS", "INT32"),
+                                        ("LXOR", "LOR", "BOOL"), ("PLUS", "SECOND", "FP32"),
+                                        ("MAX", "MINUS", "INT8"), ("EQ", "GE", "UINT16")])
+def test_masked_dot_hubs(iso, add, mult, t):
+    n = 12000
+    dt = NPT[t]
+    A = gb.Matrix.from_scipy(_hub_matrix(n, 201, dt, iso), t)
+    B = gb.Matrix.from_scipy(_hub_matrix(n, 202, dt, iso), t)
+    rng = np.random.default_rng(203)
+    Ms = gen.er(n, n, 4 * n, 204, np.bool_).tolil()
+    hubs = [5, 17, 40, 41, 90]
+    for i in hubs:                      # hub-by-hub pairs and hub-by-anything rows/columns
+        for j in hubs:
+            Ms[i, j] = True
+        Ms[i, rng.choice(n, 300, replace=False)] = True
+        Ms[rng.choice(n, 300, replace=False), i] = True
+    M = gb.Matrix.from_scipy(Ms.tocsc(), "BOOL")
+    sr = gb.Semiring(add, mult, t)
+    for m in (M, M.to_hyper()):
+        ref = oracle_c.axb(m, False, A, B, sr, True)
+        got = gb.axb_host(m, False, A, B, sr, True)
+        assert_same(ref, got.matrix, add, f"{add}_{mult}_{t} iso={iso}")
+        assert got.info["mask_applied"] == 1 and got.info["method_used"] == gb.METHOD_DOT
+
+
+def test_masked_dot_general_path_on_iso_input(monkeypatch):
+    """GB200_DOTG_ISO=0 sends pattern-only operands through the valued kernel: same T"""
+    A = gen.rmat_scipy(13, 8, dtype=np.int64)
+    L, U = gb.Matrix.from_scipy(sp.tril(A, -1).tocsr()), gb.Matrix.from_scipy(sp.triu(A, 1).tocsr())
+    sr = gb.Semiring("PLUS", "TIMES", "INT64", True)
+    fast = gb.axb_host(L, False, U, L, sr, True)
+    monkeypatch.setenv("GB200_DOTG_ISO", "0")
+    slow = gb.axb_host(L, False, U, L, sr, True)
+    assert_same(fast.matrix, slow.matrix, "PLUS", "iso vs general")
+    assert fast.info["flops"] == slow.info["flops"] == int(fast.matrix.x.sum())

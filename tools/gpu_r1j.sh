@@ -1,0 +1,11 @@
+set -x
+O=gpurun_out/r1j; mkdir -p $O
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > $O/pytest.log
+python bench.py --workload tri --scale 20 --steps 3 --no-cpu > $O/bench_tri20.json 2> $O/bench_tri20.err
+GB200_DOTG_ISO=0 python bench.py --workload tri --scale 20 --steps 3 --no-cpu --no-e2e > $O/bench_tri20_noiso.json 2> $O/bench_tri20_noiso.err
+python bench.py --steps 3 --no-cpu > $O/bench_tri22.json 2> $O/bench_tri22.err
+GB200_DOTG_ISO=0 python bench.py --steps 3 --no-cpu --no-e2e > $O/bench_tri22_noiso.json 2> $O/bench_tri22_noiso.err
+for v in "1 6" "0 6" "1 4" "1 8" "0 8"; do set -- $v; GB200_SPMV_PIPE=$1 GB200_SPMV_GRID=$2 python bench.py --workload sssp --steps 5 --no-cpu --no-e2e > $O/bench_sssp_p$1_g$2.json 2> $O/bench_sssp_p$1_g$2.err; done
+tools/prof.sh $O tri22 dotg_kernel 4 --workload tri --scale 22
+tools/launches.sh $O/launches_tri22.csv --workload tri --scale 22
+du -sh $O; tail -n 3 $O/*.err; cat $O/pytest.log
