@@ -511,14 +511,43 @@ def main():
         return pinned[id(m)]
     hcalls = [] if args.no_e2e else [(pin(m), pin(a), pin(b)) for (m, a, b, _, _, _) in calls]
 
+    # vector pull on N > 1 GPUs: every rank owns a block of A's vectors = of w's entries, and the
+    # slices of w are all-gathered over NCCL every step; T never leaves HBM
+    exchange = None
+    if world > 1 and sliced_name == "A" and A.vdim >= 1 and B.vdim == 1:
+        cap = int(np.diff(bounds).max())
+        zdt = {"FP64": torch.float64, "FP32": torch.float32, "INT64": torch.int64, "INT32": torch.int32,
+               "BOOL": torch.bool}.get(w["semiring"].ztype, torch.uint8)
+        exchange = {"p": torch.zeros(2, dtype=torch.int64, device=device),
+                    "i": torch.zeros(cap, dtype=torch.int64, device=device),
+                    "x": torch.zeros(cap, dtype=zdt, device=device),
+                    "n": torch.zeros(1, dtype=torch.int64, device=device),
+                    "ai": torch.zeros(cap * world, dtype=torch.int64, device=device),
+                    "ax": torch.zeros(cap * world, dtype=zdt, device=device),
+                    "an": torch.zeros(world, dtype=torch.int64, device=device), "bytes": 0}
+
     def step_device():
         out = {"flops": 0, "nnz": 0, "device_ms": 0.0, "kernel_ms": 0.0, "nvec": 0, "infos": []}
         for (_, _, _, dm, da, db) in calls:
-            r = gb.axb_device(dm, w["mask_comp"], da, db, w["semiring"], w["do_adotb"], fetch=False)
+            if exchange is not None:
+                rh, info = gb.axb_device_keep(dm, w["mask_comp"], da, db, w["semiring"], w["do_adotb"])
+                ex = exchange
+                gb.fetch_into(rh, ex["p"].data_ptr(), 0, ex["i"].data_ptr() if info["nnz"] else 0,
+                              ex["x"].data_ptr() if info["nnz"] else 0)
+                gb.free_result(rh)
+                ex["n"][0] = info["nnz"]
+                dist.all_gather_into_tensor(ex["an"], ex["n"])
+                dist.all_gather_into_tensor(ex["ai"], ex["i"])
+                dist.all_gather_into_tensor(ex["ax"], ex["x"])
+                torch.cuda.synchronize()
+                ex["bytes"] = (ex["i"].numel() * 8 + ex["x"].numel() * ex["x"].element_size()) * world
+            else:
+                info = gb.axb_device(dm, w["mask_comp"], da, db, w["semiring"], w["do_adotb"],
+                                     fetch=False).info
             for k in ("flops", "nnz", "device_ms", "kernel_ms"):
-                out[k] += r.info[k]
-            out["nvec"] += r.info["nvec"] + 1
-            out["infos"].append(r.info)
+                out[k] += info[k]
+            out["nvec"] += info["nvec"] + 1
+            out["infos"].append(info)
         return out
 
     def step_host():
@@ -663,7 +692,10 @@ def main():
                            "l2": "inputs larger than L2 (no flush needed)" if ab > 2.6e8 else
                                  "inputs smaller than L2",
                            "partition": f"{world} flop-balanced contiguous slices of "
-                                        f"{ {'M': 'the mask', 'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors"},
+                                        f"{ {'M': 'the mask', 'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors",
+                           "exchange": ("NCCL all-gather of the slices of w every step, "
+                                        f"{exchange['bytes']} B gathered per rank") if exchange else
+                                       "none (independent output vectors; scalars all-reduced)"},
                 "wall_ms_per_step": tt[1].item() / args.steps * 1e3,
                 "device_ms_per_step": float(np.mean(dev_ms)),
                 "clocks": clk.summary(),

@@ -276,6 +276,30 @@ def _fetch(rh: C.c_void_p, fetch: bool, pinned: bool = False) -> Result:
     return Result(m, info)
 
 
+def axb_device_keep(M: Optional["DMatrix"], mask_comp: bool, A: "DMatrix", B: "DMatrix",
+                    semiring: Semiring, do_adotb: bool = False, method: int = METHOD_DEFAULT):
+    """gb200_AxB_device, leaving T on the device: returns (handle, info).  Use fetch_into / free_result."""
+    rh = C.c_void_p()
+    s = semiring.c()
+    _check(lib.gb200_AxB_device(C.byref(rh), M._h if M is not None else None, int(mask_comp), A._h,
+                                B._h, C.byref(s), int(do_adotb), method), "gb200_AxB_device")
+    ci = _CInfo()
+    _check(lib.gb200_result_get_info(rh, C.byref(ci)), "gb200_result_get_info")
+    return rh, {k: getattr(ci, k) for k, _ in _CInfo._fields_}
+
+
+def fetch_into(rh, p_ptr: int, h_ptr: int, i_ptr: int, x_ptr: int) -> None:
+    """gb200_result_fetch into caller-owned buffers given by address (host, or device memory of the
+    same GPU, e.g. torch.Tensor.data_ptr())."""
+    _check(lib.gb200_result_fetch(rh, C.c_void_p(p_ptr), C.c_void_p(h_ptr) if h_ptr else None,
+                                  C.c_void_p(i_ptr) if i_ptr else None,
+                                  C.c_void_p(x_ptr) if x_ptr else None), "gb200_result_fetch")
+
+
+def free_result(rh) -> None:
+    lib.gb200_result_free(C.byref(rh))
+
+
 def init(device: int = -1) -> None:
     _check(lib.gb200_init(device), "gb200_init")
 

@@ -105,9 +105,6 @@ struct gb200_dmatrix_s
     gb200::DMat v ;                 // device view
     gb200::DevBuf p, h, i, x ;
     int is_hyper_flag ;             // raw A->is_hyper (h != NULL), as used by GB_AxB_alloc.c:49-50
-    gb200::DevBuf hinfo, hkeys, hofs ;  // lazily built per-vector hash index (common.cuh)
-    gb200::DevBuf hbinfo, hbloom ;      // ... and Bloom filters of the same vectors
-    bool has_vechash = false ;
     int iso_known = 0 ;                 // lazily computed: are all stored values equal
     gb200::DevBuf longitems ;       // lazily built segments of the vectors longer than VEC_LONG
     int64_t n_longitems = 0 ;
@@ -152,7 +149,6 @@ gb200_status run_saxpyv (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_c
 gb200_status flopcount (const DMat *M, const DMat &A, const DMat &B, DevBuf &flops, DevBuf &cum,
     int64_t *total) ;
 
-gb200_status ensure_vechash (gb200_dmatrix_s *d) ;
 gb200_status ensure_iso (gb200_dmatrix_s *d) ;
 gb200_status launch_mask_pos (const DMat &B, const DMat &M, int64_t *lpos) ;
 

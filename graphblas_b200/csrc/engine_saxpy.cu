@@ -331,7 +331,7 @@ __global__ void sym_bitmap_kernel (DMat A, DMat B, const int32_t *__restrict__ c
 // =============================================================================================
 // split the heavy vectors of one batch into work items of about `target` flops each
 __global__ void heavy_items_kernel (DMat B, const int32_t *__restrict__ heavy, int64_t nh,
-    const int64_t *__restrict__ flops, int64_t target, HeavyItem *__restrict__ items,
+    const int64_t *__restrict__ flops, int64_t target, int64_t wbase, HeavyItem *__restrict__ items,
     unsigned int *__restrict__ nitems)
 {
     for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nh ;
@@ -348,10 +348,46 @@ __global__ void heavy_items_kernel (DMat B, const int32_t *__restrict__ heavy, i
         for (int64_t q = 0 ; q < nchunks ; q++)
         {
             HeavyItem it ;
-            it.kk = kk ; it.w = (int32_t) t ;
+            it.kk = kk ; it.w = (int32_t) (wbase + t) ;
             it.pb0 = pb0 + q * ch ;
             it.pb1 = (pb0 + (q + 1) * ch < pb1) ? (pb0 + (q + 1) * ch) : pb1 ;
             items [base + q] = it ;
+        }
+    }
+}
+
+// the same split with the items laid out in the order of the heavy list (item range of vector t =
+// [ioff [t], ioff [t+1])), so that a run of vectors is a run of items: nch == nullptr fills the items
+__device__ __forceinline__ int64_t heavy_chunking (const DMat &B, int32_t kk, int64_t f, int64_t target,
+    int64_t &ch)
+{
+    const int64_t bjnz = B.p [kk+1] - B.p [kk] ;
+    int64_t nchunks = (f + target - 1) / target ;
+    if (nchunks > bjnz) nchunks = bjnz ;
+    if (nchunks < 1) nchunks = 1 ;
+    ch = (bjnz + nchunks - 1) / nchunks ;
+    return (bjnz + ch - 1) / ch ;
+}
+
+__global__ void heavy_items_ordered_kernel (DMat B, const int32_t *__restrict__ heavy, int64_t nh,
+    const int64_t *__restrict__ flops, int64_t target, int64_t *__restrict__ nch,
+    const int64_t *__restrict__ ioff, HeavyItem *__restrict__ items)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nh ;
+        t += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int32_t kk = heavy [t] ;
+        int64_t ch ;
+        const int64_t nchunks = heavy_chunking (B, kk, flops [kk], target, ch) ;
+        if (nch != nullptr) { nch [t] = nchunks ; continue ; }
+        const int64_t pb0 = B.p [kk], pb1 = B.p [kk+1] ;
+        for (int64_t q = 0 ; q < nchunks ; q++)
+        {
+            HeavyItem it ;
+            it.kk = kk ; it.w = (int32_t) t ;
+            it.pb0 = pb0 + q * ch ;
+            it.pb1 = (pb0 + (q + 1) * ch < pb1) ? (pb0 + (q + 1) * ch) : pb1 ;
+            items [ioff [t] + q] = it ;
         }
     }
 }
@@ -577,23 +613,30 @@ struct HeavyWs
 {
     DevBuf bitmap, rank, items, nitems ;
     int64_t nwords = 0, W = 0 ;
+    bool persist = false ;          // the bitmaps of ALL heavy vectors fit: marked once, kept
 } ;
 
-static const int64_t HEAVY_TARGET = 1 << 16 ;               // flops per heavy work item
+static const int64_t HEAVY_TARGET = 1 << 16 ;               // flops per heavy work item, at most
+static const int64_t HEAVY_TARGET_MIN = 1 << 12 ;           // ... and at least (small batches)
 
 static gb200_status heavy_ws_alloc (HeavyWs &ws, int64_t vlen, int64_t nheavy, int64_t bnz,
     int64_t total_flops)
 {
     ws.nwords = (vlen + 31) / 32 ;
-    const int64_t budget = 1LL << 30 ;                      // bytes for bitmaps + ranks in flight
+    // bytes for bitmaps + ranks in flight: an eighth of the free HBM (180 GB per B200), at least 1 GiB
+    size_t free_b = 0, total_b = 0 ;
+    if (cudaMemGetInfo (&free_b, &total_b) != cudaSuccess) { cudaGetLastError () ; free_b = 0 ; }
+    int64_t budget = (int64_t) (free_b / 8) ;
+    if (budget < (1LL << 30)) budget = 1LL << 30 ;
+    if (budget > (16LL << 30)) budget = 16LL << 30 ;
     int64_t W = budget / (8 * (ws.nwords > 0 ? ws.nwords : 1)) ;
     if (W < 1) W = 1 ;
-    if (W > nheavy) W = nheavy ;
+    if (W >= nheavy) { W = nheavy ; ws.persist = true ; }
     ws.W = W ;
     GB200_TRY (ws.bitmap.alloc ((size_t) W * ws.nwords * 4)) ;
     GB200_TRY (ws.rank.alloc ((size_t) W * ws.nwords * 4)) ;
     // items per batch: sum of min (bjnz, ceil (flops/target)) <= min (bnz, total/target) + W
-    int64_t cap = total_flops / HEAVY_TARGET + 1 ;
+    int64_t cap = total_flops / HEAVY_TARGET_MIN + 1 ;
     if (cap > bnz) cap = bnz ;
     GB200_TRY (ws.items.alloc ((size_t) (cap + W + 1) * sizeof (HeavyItem))) ;
     GB200_TRY (ws.nitems.alloc (8)) ;
@@ -601,12 +644,12 @@ static gb200_status heavy_ws_alloc (HeavyWs &ws, int64_t vlen, int64_t nheavy, i
 }
 
 static gb200_status heavy_make_items (HeavyWs &ws, const DMat &B, const int32_t *heavy, int64_t nh,
-    const int64_t *flops, int64_t *nitems)
+    const int64_t *flops, int64_t *nitems, int64_t wbase = 0, int64_t target = HEAVY_TARGET)
 {
     Ctx &c = ctx () ;
     GB200_CUDA (cudaMemsetAsync (ws.nitems.ptr, 0, 8, c.stream)) ;
     heavy_items_kernel <<<grid_cap ((nh + 127) / 128, 8), 128, 0, c.stream>>> (B, heavy, nh, flops,
-        HEAVY_TARGET, ws.items.as<HeavyItem> (), ws.nitems.as<unsigned int> ()) ;
+        target, wbase, ws.items.as<HeavyItem> (), ws.nitems.as<unsigned int> ()) ;
     count_launch () ;
     GB200_TRY (read_i64 (ws.nitems.as<int64_t> (), nitems)) ;
     *nitems &= 0xffffffffLL ;
@@ -755,39 +798,103 @@ gb200_status run_saxpy (gb200_result_s *R, const gb200_dmatrix_s *Min, int mask_
         // The accumulators of the heavy vectors in flight are hit by one atomic per product: a batch
         // is cut so that they (and the bitmaps and ranks) stay resident in L2, otherwise every atomic
         // is a DRAM read-modify-write
-        std::vector<int64_t> hcnt ((size_t) nheavy) ;
+        std::vector<int64_t> hcnt ((size_t) nheavy), hflops ((size_t) nheavy) ;
         if (nheavy > 0)
         {
             DevBuf hc ;
-            GB200_TRY (hc.alloc (nheavy * sizeof (int64_t))) ;
+            GB200_TRY (hc.alloc (2 * nheavy * sizeof (int64_t))) ;
             gather_i64_kernel <<<grid_cap ((nheavy + 255) / 256, 8), 256, 0, c.stream>>> (cnt.as<int64_t> (),
                 bins.list (CL_HEAVY, nvec), nheavy, hc.as<int64_t> ()) ;
-            count_launch () ;
+            gather_i64_kernel <<<grid_cap ((nheavy + 255) / 256, 8), 256, 0, c.stream>>> (flops.as<int64_t> (),
+                bins.list (CL_HEAVY, nvec), nheavy, hc.as<int64_t> () + nheavy) ;
+            count_launch (2) ;
             GB200_CUDA (cudaMemcpyAsync (hcnt.data (), hc.ptr, nheavy * sizeof (int64_t),
                 cudaMemcpyDeviceToHost, c.stream)) ;
+            GB200_CUDA (cudaMemcpyAsync (hflops.data (), hc.as<int64_t> () + nheavy,
+                nheavy * sizeof (int64_t), cudaMemcpyDeviceToHost, c.stream)) ;
             GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
         }
         const char *l2env = getenv ("GB200_HEAVY_L2_MB") ;
-        const int64_t l2_budget = ((l2env != nullptr && atoll (l2env) > 0) ? atoll (l2env) : 64) << 20 ;
-        for (int64_t h0 = 0, nh = 0 ; h0 < nheavy ; h0 += nh)
+        const int64_t l2_budget = ((l2env != nullptr && atoll (l2env) > 0) ? atoll (l2env) : 128) << 20 ;
+        if (hws.persist && nheavy > 0)
         {
-            int64_t bytes = 0 ;
+            // Every heavy bitmap is still there from the symbolic phase: rank them all in one launch,
+            // lay the work items of all vectors out in list order, and then only the numeric kernel
+            // runs per L2-sized batch -- no host round trip between batches.
+            const int32_t *heavy = bins.list (CL_HEAVY, nvec) ;
+            heavy_rank_kernel <<<grid_cap (nheavy, 8), 256, 0, c.stream>>> (heavy, nheavy,
+                hws.bitmap.as<uint32_t> (), hws.rank.as<int32_t> (), hws.nwords, ccum.as<int64_t> (),
+                Ci.as<int32_t> ()) ;
+            count_launch () ;
+            std::vector<int64_t> bstart ;
+            int64_t bytes = 0, hflops_total = 0 ;
+            for (int64_t t = 0 ; t < nheavy ; t++)
+            {
+                const int64_t add = hcnt [t] * acc_size + hws.nwords * 8 ;
+                if (t == 0 || bytes + add > l2_budget) { bstart.push_back (t) ; bytes = 0 ; }
+                bytes += add ;
+                hflops_total += hflops [t] ;
+            }
+            bstart.push_back (nheavy) ;
+            const int64_t nbatch = (int64_t) bstart.size () - 1 ;
+            // enough work items per batch to fill the machine
+            int64_t target = hflops_total / (nbatch * (int64_t) c.sm_count * 16) ;
+            if (target > HEAVY_TARGET) target = HEAVY_TARGET ;
+            if (target < HEAVY_TARGET_MIN) target = HEAVY_TARGET_MIN ;
+            DevBuf nch, ioff ;
+            GB200_TRY (nch.alloc (nheavy * sizeof (int64_t))) ;
+            GB200_TRY (ioff.alloc ((nheavy + 1) * sizeof (int64_t))) ;
+            heavy_items_ordered_kernel <<<grid_cap ((nheavy + 127) / 128, 8), 128, 0, c.stream>>> (B, heavy,
+                nheavy, flops.as<int64_t> (), target, nch.as<int64_t> (), nullptr, nullptr) ;
+            count_launch () ;
+            GB200_TRY (scan_i64 (nch.as<int64_t> (), ioff.as<int64_t> (), nheavy)) ;
+            heavy_items_ordered_kernel <<<grid_cap ((nheavy + 127) / 128, 8), 128, 0, c.stream>>> (B, heavy,
+                nheavy, flops.as<int64_t> (), target, nullptr, ioff.as<int64_t> (),
+                hws.items.as<HeavyItem> ()) ;
+            count_launch () ;
+            std::vector<int64_t> hoff ((size_t) nheavy + 1) ;
+            GB200_CUDA (cudaMemcpyAsync (hoff.data (), ioff.ptr, (nheavy + 1) * sizeof (int64_t),
+                cudaMemcpyDeviceToHost, c.stream)) ;
+            GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
+            for (int64_t b = 0 ; b < nbatch ; b++)
+            {
+                const int64_t i0 = hoff [bstart [b]], i1 = hoff [bstart [b+1]] ;
+                if (i1 <= i0) continue ;
+                sa.items = hws.items.as<HeavyItem> () + i0 ; sa.nitems = i1 - i0 ;
+                if (!launch_typed (s.xy_code, FAM_SAXPY_HEAVY, s.z_code, s.add_opcode, s.mult_opcode, &sa,
+                    grid_cap (i1 - i0, 16), 256))
+                { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+            }
+        }
+        else for (int64_t h0 = 0, nh = 0 ; h0 < nheavy ; h0 += nh)
+        {
+            int64_t bytes = 0, bflops = 0 ;
             for (nh = 0 ; h0 + nh < nheavy && nh < hws.W ; nh++)
             {
                 const int64_t add = hcnt [h0 + nh] * acc_size + hws.nwords * 8 ;
                 if (nh > 0 && bytes + add > l2_budget) break ;
                 bytes += add ;
+                bflops += hflops [h0 + nh] ;
             }
+            // enough work items to fill the machine even when the batch is small
+            int64_t target = bflops / ((int64_t) c.sm_count * 16) ;
+            if (target > HEAVY_TARGET) target = HEAVY_TARGET ;
+            if (target < HEAVY_TARGET_MIN) target = HEAVY_TARGET_MIN ;
             const int32_t *heavy = bins.list (CL_HEAVY, nvec) + h0 ;
+            const int64_t wbase = hws.persist ? h0 : 0 ;        // bitmap of the batch's first vector
             int64_t nitems = 0 ;
-            GB200_TRY (heavy_make_items (hws, B, heavy, nh, flops.as<int64_t> (), &nitems)) ;
-            GB200_CUDA (cudaMemsetAsync (hws.bitmap.ptr, 0, (size_t) nh * hws.nwords * 4, c.stream)) ;
-            heavy_mark_kernel <<<grid_cap (nitems, 16), 256, 0, c.stream>>> (A, B,
-                hws.items.as<HeavyItem> (), nitems, hws.bitmap.as<uint32_t> (), hws.nwords) ;
+            GB200_TRY (heavy_make_items (hws, B, heavy, nh, flops.as<int64_t> (), &nitems, wbase, target)) ;
+            if (!hws.persist)
+            {
+                GB200_CUDA (cudaMemsetAsync (hws.bitmap.ptr, 0, (size_t) nh * hws.nwords * 4, c.stream)) ;
+                heavy_mark_kernel <<<grid_cap (nitems, 16), 256, 0, c.stream>>> (A, B,
+                    hws.items.as<HeavyItem> (), nitems, hws.bitmap.as<uint32_t> (), hws.nwords) ;
+                count_launch () ;
+            }
             heavy_rank_kernel <<<grid_cap (nh, 8), 256, 0, c.stream>>> (heavy, nh,
-                hws.bitmap.as<uint32_t> (), hws.rank.as<int32_t> (), hws.nwords, ccum.as<int64_t> (),
-                Ci.as<int32_t> ()) ;
-            count_launch (2) ;
+                hws.bitmap.as<uint32_t> () + wbase * hws.nwords, hws.rank.as<int32_t> () + wbase * hws.nwords,
+                hws.nwords, ccum.as<int64_t> (), Ci.as<int32_t> ()) ;
+            count_launch () ;
             sa.items = hws.items.as<HeavyItem> () ; sa.nitems = nitems ;
             if (!launch_typed (s.xy_code, FAM_SAXPY_HEAVY, s.z_code, s.add_opcode, s.mult_opcode, &sa,
                 grid_cap (nitems, 16), 256))

@@ -245,86 +245,6 @@ __global__ void remap_ptr_kernel (const int64_t *__restrict__ p, const int64_t *
         t += (int64_t) gridDim.x * blockDim.x) p2 [t] = pos [p [t]] ;
 }
 
-// ---------------------------------------------------------------------------------------------
-// per-vector hash index for the dot kernels (see DMat in common.cuh)
-// ---------------------------------------------------------------------------------------------
-__global__ void vh_size_kernel (const int64_t *__restrict__ p, int64_t nvec, int64_t *__restrict__ sz)
-{
-    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nvec ;
-        t += (int64_t) gridDim.x * blockDim.x)
-    {
-        const int64_t len = p [t+1] - p [t] ;
-        int64_t s = 0 ;
-        if (len > VECHASH_MIN) { s = 1 ; while (s < 2 * len) s <<= 1 ; }
-        sz [t] = s ;
-    }
-}
-
-__global__ void vh_info_kernel (const int64_t *__restrict__ sz, const int64_t *__restrict__ off,
-    int64_t nvec, int64_t *__restrict__ hinfo)
-{
-    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nvec ;
-        t += (int64_t) gridDim.x * blockDim.x)
-    {
-        const int64_t s = sz [t] ;
-        int lg = 0 ; while ((1LL << lg) < s) lg++ ;
-        hinfo [t] = (s == 0) ? -1 : ((off [t] << 6) | lg) ;
-    }
-}
-
-// one block per long vector
-__global__ void vh_fill_kernel (const int64_t *__restrict__ p, const int32_t *__restrict__ idx,
-    const int64_t *__restrict__ hinfo, int64_t nvec, int32_t *__restrict__ hkeys,
-    int32_t *__restrict__ hofs)
-{
-    for (int64_t v = blockIdx.x ; v < nvec ; v += gridDim.x)
-    {
-        const int64_t hi = hinfo [v] ;
-        if (hi < 0) continue ;
-        const int lg = (int) (hi & 63) ;
-        const int64_t off = hi >> 6 ;
-        const uint32_t mask = (1u << lg) - 1u ;
-        const int64_t p0 = p [v], p1 = p [v+1] ;
-        for (int64_t q = p0 + threadIdx.x ; q < p1 ; q += blockDim.x)
-        {
-            const int32_t key = idx [q] ;
-            uint32_t h = ((uint32_t) key * 0x9E3779B1u) >> (32 - lg) ;
-            while (atomicCAS (hkeys + off + h, -1, key) != -1) h = (h + 1) & mask ;
-            hofs [off + h] = (int32_t) (q - p0) ;
-        }
-    }
-}
-
-// Bloom filters of the long vectors: bidx[v] = rank of v among them (from the scan of `is long`)
-__global__ void vh_binfo_kernel (const int64_t *__restrict__ sz, const int64_t *__restrict__ rank,
-    int64_t nvec, int32_t *__restrict__ binfo)
-{
-    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nvec ;
-        t += (int64_t) gridDim.x * blockDim.x) binfo [t] = (sz [t] > 0) ? (int32_t) rank [t] : -1 ;
-}
-
-__global__ void vh_islong_kernel (const int64_t *__restrict__ sz, int64_t nvec, uint8_t *__restrict__ f)
-{
-    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < nvec ;
-        t += (int64_t) gridDim.x * blockDim.x) f [t] = (sz [t] > 0) ? 1 : 0 ;
-}
-
-__global__ void vh_bloom_kernel (const int64_t *__restrict__ p, const int32_t *__restrict__ idx,
-    const int32_t *__restrict__ binfo, int64_t nvec, uint32_t *__restrict__ bloom)
-{
-    for (int64_t v = blockIdx.x ; v < nvec ; v += gridDim.x)
-    {
-        const int32_t b = binfo [v] ;
-        if (b < 0) continue ;
-        uint32_t *bl = bloom + (int64_t) b * BLOOM_WORDS ;
-        for (int64_t q = p [v] + threadIdx.x ; q < p [v+1] ; q += blockDim.x)
-        {
-            const uint32_t h = bloom_bit ((uint32_t) idx [q]) ;
-            atomicOr (bl + (h >> 5), 1u << (h & 31)) ;
-        }
-    }
-}
-
 // are all stored values equal (bytewise) to the first one
 template <class W>
 __global__ void iso_kernel (const W *__restrict__ x, int64_t n, unsigned int *__restrict__ differs)
@@ -365,72 +285,6 @@ gb200_status ensure_iso (gb200_dmatrix_s *d)
     return GB200_SUCCESS ;
 }
 
-gb200_status ensure_vechash (gb200_dmatrix_s *d)
-{
-    if (d->has_vechash) return GB200_SUCCESS ;
-    Ctx &c = ctx () ;
-    const int64_t nvec = d->v.nvec ;
-    DevBuf sz, off ;
-    GB200_TRY (sz.alloc ((nvec > 0 ? nvec : 1) * sizeof (int64_t))) ;
-    GB200_TRY (off.alloc ((nvec + 1) * sizeof (int64_t))) ;
-    GB200_TRY (d->hinfo.alloc ((nvec > 0 ? nvec : 1) * sizeof (int64_t))) ;
-    if (nvec > 0)
-    {
-        vh_size_kernel <<<grid_for (nvec), 256, 0, c.stream>>> (d->v.p, nvec, sz.as<int64_t> ()) ;
-        count_launch () ;
-    }
-    GB200_TRY (scan_i64 (sz.as<int64_t> (), off.as<int64_t> (), nvec)) ;
-    int64_t total = 0 ;
-    GB200_TRY (read_i64 (off.as<int64_t> () + nvec, &total)) ;
-    GB200_TRY (d->hkeys.alloc ((size_t) (total > 0 ? total : 1) * sizeof (int32_t))) ;
-    GB200_TRY (d->hofs.alloc ((size_t) (total > 0 ? total : 1) * sizeof (int32_t))) ;
-    if (nvec > 0)
-    {
-        GB200_CUDA (cudaMemsetAsync (d->hkeys.ptr, 0xFF, (size_t) (total > 0 ? total : 1) * sizeof (int32_t), c.stream)) ;
-        vh_info_kernel <<<grid_for (nvec), 256, 0, c.stream>>> (sz.as<int64_t> (), off.as<int64_t> (),
-            nvec, d->hinfo.as<int64_t> ()) ;
-        if (total > 0)
-            vh_fill_kernel <<<grid_for (nvec * 256, 256, 16), 256, 0, c.stream>>> (d->v.p, d->v.i,
-                d->hinfo.as<int64_t> (), nvec, d->hkeys.as<int32_t> (), d->hofs.as<int32_t> ()) ;
-        count_launch (2) ;
-    }
-    GB200_CUDA (cudaGetLastError ()) ;
-    d->v.hinfo = d->hinfo.as<int64_t> () ;
-    d->v.hkeys = d->hkeys.as<int32_t> () ;
-    d->v.hofs = d->hofs.as<int32_t> () ;
-    d->v.hbinfo = nullptr ; d->v.hbloom = nullptr ;
-    if (total > 0)
-    {
-        // one precomputed 64 KB Bloom filter per long vector, within a 2 GiB budget
-        DevBuf islong, rank ;
-        GB200_TRY (islong.alloc (nvec)) ;
-        GB200_TRY (rank.alloc ((nvec + 1) * sizeof (int64_t))) ;
-        vh_islong_kernel <<<grid_for (nvec), 256, 0, c.stream>>> (sz.as<int64_t> (), nvec, islong.as<uint8_t> ()) ;
-        count_launch () ;
-        GB200_TRY (scan_u8 (islong.as<uint8_t> (), rank.as<int64_t> (), nvec)) ;
-        int64_t nlong = 0 ;
-        GB200_TRY (read_i64 (rank.as<int64_t> () + nvec, &nlong)) ;
-        const size_t bytes = (size_t) nlong * BLOOM_WORDS * sizeof (uint32_t) ;
-        if (nlong > 0 && bytes <= ((size_t) 2 << 30) && !getenv ("GB200_NO_PREBLOOM"))
-        {
-            GB200_TRY (d->hbinfo.alloc (nvec * sizeof (int32_t))) ;
-            GB200_TRY (d->hbloom.alloc (bytes)) ;
-            GB200_CUDA (cudaMemsetAsync (d->hbloom.ptr, 0, bytes, c.stream)) ;
-            vh_binfo_kernel <<<grid_for (nvec), 256, 0, c.stream>>> (sz.as<int64_t> (), rank.as<int64_t> (),
-                nvec, d->hbinfo.as<int32_t> ()) ;
-            vh_bloom_kernel <<<grid_for (nvec * 256, 256, 16), 256, 0, c.stream>>> (d->v.p, d->v.i,
-                d->hbinfo.as<int32_t> (), nvec, d->hbloom.as<uint32_t> ()) ;
-            count_launch (2) ;
-            GB200_CUDA (cudaGetLastError ()) ;
-            d->v.hbinfo = d->hbinfo.as<int32_t> () ;
-            d->v.hbloom = d->hbloom.as<uint32_t> () ;
-        }
-        GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
-    }
-    d->has_vechash = true ;
-    return GB200_SUCCESS ;
-}
-
 gb200_status filter_mask (const gb200_dmatrix_s *M, DMat &Mview, DevBuf &Mp2, DevBuf &Mi2)
 {
     Ctx &c = ctx () ;
@@ -461,8 +315,7 @@ gb200_status filter_mask (const gb200_dmatrix_s *M, DMat &Mview, DevBuf &Mp2, De
     Mview.i = Mi2.as<int32_t> () ;
     Mview.nnz = n - nfalse ;
     Mview.x = nullptr ;
-    Mview.hinfo = nullptr ; Mview.hkeys = nullptr ; Mview.hofs = nullptr ;
-    Mview.hbinfo = nullptr ; Mview.hbloom = nullptr ; Mview.iso = 0 ;
+    Mview.iso = 0 ;
     return GB200_SUCCESS ;
 }
 
@@ -783,8 +636,7 @@ gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host)
     d->v.vlen = host->vlen ; d->v.vdim = host->vdim ; d->v.nvec = nvec ; d->v.nnz = nnz ;
     d->v.hyper = (host->h != NULL && nvec < host->vdim) ? 1 : 0 ;
     d->v.type_code = host->type_code ;
-    d->v.hinfo = nullptr ; d->v.hkeys = nullptr ; d->v.hofs = nullptr ;
-    d->v.hbinfo = nullptr ; d->v.hbloom = nullptr ; d->v.iso = 0 ;
+    d->v.iso = 0 ;
     *out = d ;
     return GB200_SUCCESS ;
 }
@@ -814,10 +666,10 @@ gb200_status gb200_result_fetch (gb200_result r, int64_t *p, int64_t *h, int64_t
     std::lock_guard<std::recursive_mutex> lock (c.mu) ;
     const gb200_result_info &f = r->info ;
     GB200_CUDA (cudaMemcpyAsync (p, r->p.ptr, (f.nvec + 1) * sizeof (int64_t),
-        cudaMemcpyDeviceToHost, c.stream)) ;
+        cudaMemcpyDefault, c.stream)) ;
     if (f.is_hyper && h != NULL && f.nvec > 0)
         GB200_CUDA (cudaMemcpyAsync (h, r->h.ptr, f.nvec * sizeof (int64_t),
-            cudaMemcpyDeviceToHost, c.stream)) ;
+            cudaMemcpyDefault, c.stream)) ;
     if (f.nnz > 0)
     {
         if (i == NULL || x == NULL) { set_error ("gb200_result_fetch: NULL i or x") ; return GB200_INVALID ; }
@@ -831,10 +683,10 @@ gb200_status gb200_result_fetch (gb200_result r, int64_t *p, int64_t *h, int64_t
                 stage.as<int64_t> (), len) ;
             count_launch () ;
             GB200_CUDA (cudaMemcpyAsync (i + off, stage.ptr, len * sizeof (int64_t),
-                cudaMemcpyDeviceToHost, c.stream)) ;
+                cudaMemcpyDefault, c.stream)) ;
         }
         GB200_CUDA (cudaMemcpyAsync (x, r->x.ptr, (size_t) f.nnz * type_size (f.type_code),
-            cudaMemcpyDeviceToHost, c.stream)) ;
+            cudaMemcpyDefault, c.stream)) ;
         GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
     }
     GB200_CUDA (cudaStreamSynchronize (c.stream)) ;

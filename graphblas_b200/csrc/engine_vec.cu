@@ -93,10 +93,11 @@ static gb200_status ensure_longitems (gb200_dmatrix_s *d)
 __global__ void tile_row_kernel (const int64_t *__restrict__ p, int64_t nvec, int64_t ntiles,
     int32_t *__restrict__ tile_row)
 {
-    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < ntiles ;
+    // entry ntiles: the vector that holds the last entry (trailing empty vectors are never visited)
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t <= ntiles ;
         t += (int64_t) gridDim.x * blockDim.x)
     {
-        const int64_t pos = t * SPMV_TILE ;
+        const int64_t pos = (t < ntiles) ? t * SPMV_TILE : (p [nvec] - 1) ;
         int64_t lo = 0, hi = nvec ;             // last kk in [0,nvec) with p [kk] <= pos
         while (hi - lo > 1)
         {
@@ -115,8 +116,8 @@ static gb200_status ensure_tilerow (gb200_dmatrix_s *d)
     d->n_tiles = ntiles ;
     if (ntiles > 0)
     {
-        GB200_TRY (d->tilerow.alloc (ntiles * sizeof (int32_t))) ;
-        tile_row_kernel <<<grid_cap ((ntiles + 255) / 256, 8), 256, 0, c.stream>>> (d->v.p, d->v.nvec,
+        GB200_TRY (d->tilerow.alloc ((ntiles + 1) * sizeof (int32_t))) ;
+        tile_row_kernel <<<grid_cap ((ntiles + 256) / 256, 8), 256, 0, c.stream>>> (d->v.p, d->v.nvec,
             ntiles, d->tilerow.as<int32_t> ()) ;
         count_launch () ;
         GB200_CUDA (cudaGetLastError ()) ;

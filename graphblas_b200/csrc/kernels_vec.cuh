@@ -210,7 +210,7 @@ spmv_stream_kernel (SpmvArgs a)
     const int64_t *__restrict__ Ap = a.A.p ;
     acc_t *__restrict__ vals = (acc_t *) a.vals ;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5 ;
-    const int64_t nnz = a.A.nnz, nvec = a.A.nvec ;
+    const int64_t nnz = a.A.nnz ;
     unsigned long long nm = 0 ;
     int32_t ji [SPMV_PER_THREAD] ;
     T av [SPMV_PER_THREAD] ;
@@ -260,7 +260,7 @@ spmv_stream_kernel (SpmvArgs a)
         if (PIPE && tile + gridDim.x < a.ntiles) load_tile (tile + gridDim.x) ;
         // ---- phase 2: the vector segments inside the tile ------------------------------------
         const int64_t r0 = a.tile_row [tile] ;
-        const int64_t r_end = (tile + 1 < a.ntiles) ? (int64_t) a.tile_row [tile + 1] : (nvec - 1) ;
+        const int64_t r_end = a.tile_row [tile + 1] ;       // ntiles + 1 entries
         for (int64_t r = r0 + tid ; r <= r_end ; r += SPMV_THREADS)
         {
             const int64_t ps = __ldg (Ap + r), pe = __ldg (Ap + r + 1) ;

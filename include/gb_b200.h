@@ -155,9 +155,11 @@ gb200_status gb200_AxB_device
 
 gb200_status gb200_result_get_info (gb200_result r, gb200_result_info *info) ;
 
-/* Copy T into caller-owned host arrays (sized from gb200_result_info): p[nvec+1], h[nvec] (only if
+/* Copy T into caller-owned arrays (sized from gb200_result_info): p[nvec+1], h[nvec] (only if
  * is_hyper, else pass NULL), i[nnz], x[nnz*sizeof(type)].  The shim passes arrays obtained from the
- * reference's own allocator (GB_create), which is how ownership of T stays with the reference. */
+ * reference's own allocator (GB_create), which is how ownership of T stays with the reference.
+ * The destinations may also be device pointers of the same GPU (unified addressing): that is how a
+ * multi-GPU caller keeps its slice of T in HBM for the NCCL exchange of SURVEY.md 8(e). */
 gb200_status gb200_result_fetch (gb200_result r, int64_t *p, int64_t *h, int64_t *i, void *x) ;
 gb200_status gb200_result_free (gb200_result *r) ;
 
