@@ -21,21 +21,31 @@ static inline int grid_cap (int64_t n, int per_sm)
     return (int) n ;
 }
 
-// stored-vector position of every entry of M (upper bound search in M.p)
+// stored-vector position of every entry of M: a warp takes 32 consecutive vectors; a lane fills the
+// run of a short vector itself, the warp fills the long ones together
 __global__ void expand_vec_kernel (const int64_t *__restrict__ p, int64_t nvec, int64_t nnz,
     int32_t *__restrict__ mvec)
 {
-    for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; e < nnz ;
-        e += (int64_t) gridDim.x * blockDim.x)
+    const int lane = threadIdx.x & 31 ;
+    const int64_t wid = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5 ;
+    const int64_t nw = ((int64_t) gridDim.x * blockDim.x) >> 5 ;
+    for (int64_t v0 = wid * 32 ; v0 < nvec ; v0 += nw * 32)
     {
-        int64_t lo = 0, hi = nvec ;             // find the last v with p[v] <= e
-        while (hi - lo > 1)
+        const int64_t v = v0 + lane ;
+        int64_t e0 = 0, e1 = 0 ;
+        if (v < nvec) { e0 = __ldg (p + v) ; e1 = __ldg (p + v + 1) ; }
+        const bool is_long = (e1 - e0 > 64) ;
+        if (!is_long) for (int64_t e = e0 ; e < e1 ; e++) mvec [e] = (int32_t) v ;
+        unsigned todo = __ballot_sync (0xffffffffu, is_long) ;
+        while (todo)
         {
-            const int64_t mid = (lo + hi) >> 1 ;
-            if (__ldg (p + mid) <= e) lo = mid ; else hi = mid ;
+            const int src = __ffs (todo) - 1 ;
+            todo &= todo - 1 ;
+            const int64_t s0 = __shfl_sync (0xffffffffu, e0, src), s1 = __shfl_sync (0xffffffffu, e1, src) ;
+            for (int64_t e = s0 + lane ; e < s1 ; e += 32) mvec [e] = (int32_t) (v0 + src) ;
         }
-        mvec [e] = (int32_t) lo ;
     }
+    (void) nnz ;
 }
 
 // pack the flagged pairs.  rows: li[e] (mask mode) or the name of A's (e % anvec)-th vector.
@@ -116,30 +126,27 @@ __global__ void dotg_lists_kernel (DMat A, DMat M, const uint8_t *__restrict__ o
     const uint8_t *__restrict__ small, const int32_t *__restrict__ wl, int64_t mnz,
     const int64_t *__restrict__ pos0, const int64_t *__restrict__ poss,
     const int64_t *__restrict__ offA, unsigned long long *__restrict__ curA, int64_t n0,
-    int32_t *__restrict__ plist, int32_t *__restrict__ slist)
+    int32_t *__restrict__ plist, int32_t *__restrict__ slist, int64_t *__restrict__ nt)
 {
+    // nt [t] = tasks of the pair at plist [t]: one per DOTG_SEG-long piece of its walk
     for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; e < mnz ;
         e += (int64_t) gridDim.x * blockDim.x)
     {
-        if (own [e]) plist [pos0 [e]] = (int32_t) e ;
+        const int32_t w = wl [e] ;
+        if (own [e])
+        {
+            const int64_t t = pos0 [e] ;
+            plist [t] = (int32_t) e ;
+            nt [t] = (w + DOTG_SEG - 1) / DOTG_SEG ;
+        }
         else if (small [e]) slist [poss [e]] = (int32_t) e ;
-        else if (wl [e] < 0)
+        else if (w < 0)
         {
             const int64_t ka = dm_vecpos (A, M.i [e]) ;
-            plist [n0 + offA [ka] + (int64_t) atomicAdd (curA + ka, 1ULL)] = (int32_t) e ;
+            const int64_t t = n0 + offA [ka] + (int64_t) atomicAdd (curA + ka, 1ULL) ;
+            plist [t] = (int32_t) e ;
+            nt [t] = (-w + DOTG_SEG - 1) / DOTG_SEG ;
         }
-    }
-}
-
-__global__ void dotg_ntask_kernel (const int32_t *__restrict__ pl, int64_t np,
-    const int32_t *__restrict__ wl, int64_t *__restrict__ nt)
-{
-    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < np ;
-        t += (int64_t) gridDim.x * blockDim.x)
-    {
-        int32_t w = wl [pl [t]] ;
-        if (w < 0) w = -w ;
-        nt [t] = (w + DOTG_SEG - 1) / DOTG_SEG ;
     }
 }
 
@@ -284,7 +291,7 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             int asz = 0 ;
             const uint64_t ident = identity_bits (s.z_code, s.add_opcode, &asz) ;
             GB200_TRY (fill_bits (vals.ptr, acc_size, ident, mnz)) ;
-            expand_vec_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (Mv.p, Mv.nvec,
+            expand_vec_kernel <<<grid_cap ((Mv.nvec + 255) / 256, 16), 256, 0, c.stream>>> (Mv.p, Mv.nvec,
                 mnz, mvec.as<int32_t> ()) ;
             count_launch () ;
             // ---- split the pairs by owner (the longer vector); regroup the A-owned ones by i -------
@@ -318,10 +325,12 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             GB200_TRY (read_i64 (pos0.as<int64_t> () + mnz, &n0)) ;
             GB200_TRY (read_i64 (poss.as<int64_t> () + mnz, &ns)) ;
             GB200_TRY (read_i64 (offA.as<int64_t> () + anvec, &n1)) ;
+            DevBuf ntall ;
+            GB200_TRY (ntall.alloc ((n0 + n1 + 1) * sizeof (int64_t))) ;
             dotg_lists_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, Mv,
                 own.as<uint8_t> (), small.as<uint8_t> (), wl.as<int32_t> (), mnz, pos0.as<int64_t> (),
                 poss.as<int64_t> (), offA.as<int64_t> (), curA.as<unsigned long long> (), n0,
-                plist.as<int32_t> (), slist.as<int32_t> ()) ;
+                plist.as<int32_t> (), slist.as<int32_t> (), ntall.as<int64_t> ()) ;
             dot_cum_list_kernel <<<grid_cap ((Mv.nvec + 256) / 256, 8), 256, 0, c.stream>>> (Mv.p,
                 pos0.as<int64_t> (), Mv.nvec, off0.as<int64_t> ()) ;
             count_launch (2) ;
@@ -351,13 +360,9 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 const int64_t *off = orient ? offA.as<int64_t> () : off0.as<int64_t> () ;
                 const int64_t nown = orient ? anvec : Mv.nvec ;
                 // tasks: one per pair, or one per DOTG_SEG-long segment of a long walk
-                DevBuf nt, toff, tasks, otoff, nch, ioff ;
-                GB200_TRY (nt.alloc (np * sizeof (int64_t))) ;
+                DevBuf toff, tasks, otoff, nch, ioff ;
                 GB200_TRY (toff.alloc ((np + 1) * sizeof (int64_t))) ;
-                dotg_ntask_kernel <<<grid_cap ((np + 255) / 256, 16), 256, 0, c.stream>>> (pl, np,
-                    wl.as<int32_t> (), nt.as<int64_t> ()) ;
-                count_launch () ;
-                GB200_TRY (scan_i64 (nt.as<int64_t> (), toff.as<int64_t> (), np)) ;
+                GB200_TRY (scan_i64 (ntall.as<int64_t> () + (orient ? n0 : 0), toff.as<int64_t> (), np)) ;
                 int64_t ntasks = 0 ;
                 GB200_TRY (read_i64 (toff.as<int64_t> () + np, &ntasks)) ;
                 GB200_TRY (tasks.alloc (ntasks * sizeof (DotTask))) ;

@@ -309,11 +309,11 @@ gb200_status run_dotv (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_com
         sp.vals = vals.ptr ; sp.flags = flags.as<uint8_t> () ;
         sp.nmatch = nmatch.as<unsigned long long> () ;
         sp.mult_op = s.mult_opcode ; sp.flip = s.flipxy ;
-        const char *penv = getenv ("GB200_SPMV_PIPE") ;            // 1: register prefetch of the next tile
+        const char *oenv = getenv ("GB200_SPMV_OCC8") ;            // 1: the 32-register build, 8 blocks per SM
         const char *genv = getenv ("GB200_SPMV_GRID") ;            // blocks per SM
-        const bool nopipe = !(penv != nullptr && atoi (penv) != 0) && bp == nullptr ;  // measured: no gain from it
-        const int per_sm = (genv != nullptr && atoi (genv) > 0) ? atoi (genv) : 6 ;
-        if (!launch_typed (s.xy_code, bp ? FAM_SPMV_PRES : (nopipe ? FAM_SPMV_NOPIPE : FAM_SPMV), s.z_code,
+        const bool occ8 = (oenv != nullptr && atoi (oenv) != 0 && bp == nullptr) ;
+        const int per_sm = (genv != nullptr && atoi (genv) > 0) ? atoi (genv) : (occ8 ? 8 : 6) ;
+        if (!launch_typed (s.xy_code, bp ? FAM_SPMV_PRES : (occ8 ? FAM_SPMV_OCC8 : FAM_SPMV), s.z_code,
             s.add_opcode, s.mult_opcode, &sp, grid_cap (sp.ntiles, per_sm), SPMV_THREADS))
         { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
     }

@@ -392,23 +392,23 @@ template <class S> struct DotGSeg
     typename S::acc_t ciso ;
 } ;
 
-// one cuckoo lookup: exactly two shared-memory loads, no loop
+// one cuckoo lookup: exactly two shared-memory loads, no loop (tab2 = the second table)
 template <bool ISO, bool DENSE, class slot_t>
-__device__ __forceinline__ bool dotg_probe (const slot_t *tab, uint32_t kq, int NS, int sh, uint32_t c1,
-    uint32_t c2, uint32_t &pos)
+__device__ __forceinline__ bool dotg_probe (const slot_t *__restrict__ tab, const slot_t *__restrict__ tab2,
+    uint32_t kq, int sh, uint32_t c1, uint32_t c2, uint32_t &pos)
 {
     constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
     if constexpr (DENSE) { pos = kq ; return (kq != NOKEY) ; }
     else if constexpr (ISO)
     {
         const uint32_t e1 = tab [(kq * c1) >> sh] ;
-        const uint32_t e2 = tab [NS + ((kq * c2) >> sh)] ;
+        const uint32_t e2 = tab2 [(kq * c2) >> sh] ;
         return (e1 == kq) | (e2 == kq) ;
     }
     else
     {
         const uint64_t e1 = tab [(kq * c1) >> sh] ;
-        const uint64_t e2 = tab [NS + ((kq * c2) >> sh)] ;
+        const uint64_t e2 = tab2 [(kq * c2) >> sh] ;
         const bool h1 = ((uint32_t) e1 == kq), h2 = ((uint32_t) e2 == kq) ;
         pos = (uint32_t) ((h1 ? e1 : e2) >> 32) ;
         return h1 | h2 ;
@@ -427,8 +427,9 @@ __device__ __forceinline__ void dotg_lanes (const S &sr, const DotGSeg<S> &g, co
 {
     using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
     constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
-    const int NS = g.NS, sh = g.sh ;
+    const int sh = g.sh ;
     const uint32_t c1 = g.c1, c2 = g.c2 ;
+    const slot_t *__restrict__ tab2 = tab + g.NS ;
     int t = -1 ;                        // the task this lane is walking
     bool more = true ;                  // the counter may still hold tasks
     int32_t e = 0 ;
@@ -476,7 +477,7 @@ __device__ __forceinline__ void dotg_lanes (const S &sr, const DotGSeg<S> &g, co
                 const int p = q + c ;
                 const uint32_t kq = ((unsigned) (p - pbeg) < span) ? (uint32_t) kk [c] : NOKEY ;
                 uint32_t pos = 0 ;
-                const bool hit = dotg_probe<ISO, false, slot_t> (tab, kq, NS, sh, c1, c2, pos) ;
+                const bool hit = dotg_probe<ISO, false, slot_t> (tab, tab2, kq, sh, c1, c2, pos) ;
                 if constexpr (ISO) cnt += hit ? 1u : 0u ;
                 else if (hit)
                 {
@@ -531,8 +532,9 @@ __device__ __forceinline__ void dotg_walk (const S &sr, const DotGSeg<S> &g, con
     using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
     constexpr uint32_t NOKEY = 0xFFFFFFFEu ;            // a walked index that must not be probed
     const int lane = threadIdx.x & 31 ;
-    const int NS = g.NS, sh = g.sh ;
+    const int sh = g.sh ;
     const uint32_t c1 = g.c1, c2 = g.c2 ;
+    const slot_t *__restrict__ tab2 = tab + g.NS ;
     int tk = 0 ;
     if (lane == 0) tk = atomicAdd (s_next, 1) ;
     tk = __shfl_sync (0xffffffffu, tk, 0) ;
@@ -565,11 +567,11 @@ __device__ __forceinline__ void dotg_walk (const S &sr, const DotGSeg<S> &g, con
             #pragma unroll
             for (int u = 0 ; u < DOTG_U ; u++)
             {
-                if (u > 0 && p0 + 32 * u >= len) break ;        // warp-uniform
+                if (u > 0 && p0 + 32 * u >= len) continue ;     // warp-uniform
                 const int p = p0 + 32 * u + lane ;
                 uint32_t pos = 0 ;
-                const bool hit = dotg_probe<ISO, DENSE, slot_t> (tab, k [u], NS, sh, c1, c2, pos) ;
-                if constexpr (ISO) cnt += hit ? 1u : 0u ;
+                const bool hit = dotg_probe<ISO, DENSE, slot_t> (tab, tab2, k [u], sh, c1, c2, pos) ;
+                if constexpr (ISO) { if (hit) cnt++ ; }
                 else if (hit)
                 {
                     const T ov = g.Ox [pos], wv = g.Wx [task.w0 + p] ;
@@ -735,7 +737,7 @@ dotg_kernel (DotGArgs a)
 // ---------------------------------------------------------------------------------------------
 enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_DOTV = 4,
     FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9,
-    FAM_DOTG_ISO = 10, FAM_SPMV_NOPIPE = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13 } ;
+    FAM_DOTG_ISO = 10, FAM_SPMV_OCC8 = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -781,11 +783,11 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
     else if (family == FAM_SAXPYV_LONG)
         saxpyv_long_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyVArgs *) args) ;
     else if (family == FAM_SPMV)
-        spmv_stream_kernel<S, false, true> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
-    else if (family == FAM_SPMV_PRES)
-        spmv_stream_kernel<S, true, true> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
-    else if (family == FAM_SPMV_NOPIPE)
         spmv_stream_kernel<S, false, false> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
+    else if (family == FAM_SPMV_PRES)
+        spmv_stream_kernel<S, true, false> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
+    else if (family == FAM_SPMV_OCC8)
+        spmv_stream_kernel<S, false, true> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SpmvArgs *) args) ;
     else
         dot_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotArgs *) args) ;
 }

@@ -175,6 +175,19 @@ dotv_long_kernel (DotVArgs a)
 // tiles is combined with the monoid's atomic.  tile_row [t] (depends on A only, cached on the
 // handle) is the stored vector that holds entry t * SPMV_TILE.
 // ---------------------------------------------------------------------------------------------
+// streaming load (evict-first): the entry stream of A must not push the gathered vector out of L2
+template <class W> __device__ __forceinline__ W ld_stream (const W *ptr)
+{
+    if constexpr (sizeof (W) == 1)
+    { const unsigned char r = __ldcs ((const unsigned char *) ptr) ; return *(const W *) &r ; }
+    else if constexpr (sizeof (W) == 2)
+    { const unsigned short r = __ldcs ((const unsigned short *) ptr) ; return *(const W *) &r ; }
+    else if constexpr (sizeof (W) == 4)
+    { const unsigned int r = __ldcs ((const unsigned int *) ptr) ; return *(const W *) &r ; }
+    else
+    { const unsigned long long r = __ldcs ((const unsigned long long *) ptr) ; return *(const W *) &r ; }
+}
+
 constexpr int SPMV_TILE = 2048 ;
 constexpr int SPMV_THREADS = 256 ;
 constexpr int SPMV_PER_THREAD = SPMV_TILE / SPMV_THREADS ;
@@ -192,10 +205,9 @@ struct SpmvArgs
     int mult_op ; int flip ;
 } ;
 
-// PIPE: the indices and values of the block's NEXT tile are loaded into registers before the
-// segments of the current tile are reduced, so the entry stream stays in flight across the barriers.
-template <class S, bool HAS_PRES, bool PIPE>
-__global__ void __launch_bounds__ (SPMV_THREADS, PIPE ? 4 : 6)
+// OCC8: compiled for 8 resident blocks per SM (32 registers) instead of 6
+template <class S, bool HAS_PRES, bool OCC8>
+__global__ void __launch_bounds__ (SPMV_THREADS, OCC8 ? 8 : 6)
 spmv_stream_kernel (SpmvArgs a)
 {
     using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
@@ -212,38 +224,24 @@ spmv_stream_kernel (SpmvArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5 ;
     const int64_t nnz = a.A.nnz ;
     unsigned long long nm = 0 ;
-    int32_t ji [SPMV_PER_THREAD] ;
-    T av [SPMV_PER_THREAD] ;
-    auto load_tile = [&] (int64_t tile)
-    {
-        const int64_t e0 = tile * SPMV_TILE ;
-        #pragma unroll
-        for (int k = 0 ; k < SPMV_PER_THREAD ; k++)
-        {
-            const int64_t p = e0 + k * SPMV_THREADS + tid ;
-            ji [k] = (p < nnz) ? __ldg (Ai + p) : -1 ;
-            if (p < nnz) av [k] = Ax [p] ;
-        }
-    } ;
-    if (PIPE && blockIdx.x < a.ntiles) load_tile (blockIdx.x) ;
     for (int64_t tile = blockIdx.x ; tile < a.ntiles ; tile += gridDim.x)
     {
         const int64_t e0 = tile * SPMV_TILE ;
         const int64_t e1 = (e0 + SPMV_TILE < nnz) ? (e0 + SPMV_TILE) : nnz ;
-        if (!PIPE) load_tile (tile) ;
         // ---- phase 1: products of the tile into shared memory --------------------------------
         #pragma unroll
         for (int k = 0 ; k < SPMV_PER_THREAD ; k++)
         {
             const int idx = k * SPMV_THREADS + tid ;
+            const int64_t p = e0 + idx ;
             bool f = false ;
             acc_t v = Mon::identity () ;
-            const int64_t j = ji [k] ;
-            if (j >= 0)
+            if (p < e1)
             {
+                const int64_t j = ld_stream (Ai + p) ;
                 if (!HAS_PRES || bit_test (a.bpres, j))
                 {
-                    v = sr.product (av [k], Bv [j]) ;
+                    v = sr.product (ld_stream (Ax + p), Bv [j]) ;
                     f = true ;
                 }
             }
@@ -257,7 +255,6 @@ spmv_stream_kernel (SpmvArgs a)
         }
         if (tid == 0) s_nlong = 0 ;
         __syncthreads () ;
-        if (PIPE && tile + gridDim.x < a.ntiles) load_tile (tile + gridDim.x) ;
         // ---- phase 2: the vector segments inside the tile ------------------------------------
         const int64_t r0 = a.tile_row [tile] ;
         const int64_t r_end = a.tile_row [tile + 1] ;       // ntiles + 1 entries
