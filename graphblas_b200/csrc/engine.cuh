@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <map>
 #include <mutex>
 #include <atomic>
 #include <cuda_runtime.h>
@@ -60,18 +61,33 @@ gb200_status ensure_init () ;
 
 inline void count_launch (int n = 1) { ctx ().launches += n ; }
 
-// stream-ordered device buffer
+// Device workspace comes from a caching allocator of the library's own (engine_util.cu): freed
+// blocks are kept by size class and handed out again.  Everything this library does runs on ONE
+// stream, so a block that is released while kernels that use it are still queued can safely be given
+// to later work on the same stream.  (cudaMallocAsync's pool was measured to re-map memory every few
+// multiplies when whole operands are allocated and freed per call -- +80 ms on a 56 ms multiply.)
+void *dev_pool_alloc (size_t nbytes, size_t *capacity) ;     // nullptr: out of device memory
+void dev_pool_free (void *ptr, size_t capacity) ;
+void dev_pool_trim () ;                                      // give every cached block back to the driver
+
 struct DevBuf
 {
     void *ptr = nullptr ;
     size_t bytes = 0 ;
+    size_t cap = 0 ;
     DevBuf () { }
     DevBuf (const DevBuf &) = delete ;
     DevBuf &operator= (const DevBuf &) = delete ;
-    DevBuf (DevBuf &&o) noexcept : ptr (o.ptr), bytes (o.bytes) { o.ptr = nullptr ; o.bytes = 0 ; }
+    DevBuf (DevBuf &&o) noexcept : ptr (o.ptr), bytes (o.bytes), cap (o.cap)
+    { o.ptr = nullptr ; o.bytes = 0 ; o.cap = 0 ; }
     DevBuf &operator= (DevBuf &&o) noexcept
     {
-        if (this != &o) { release () ; ptr = o.ptr ; bytes = o.bytes ; o.ptr = nullptr ; o.bytes = 0 ; }
+        if (this != &o)
+        {
+            release () ;
+            ptr = o.ptr ; bytes = o.bytes ; cap = o.cap ;
+            o.ptr = nullptr ; o.bytes = 0 ; o.cap = 0 ;
+        }
         return *this ;
     }
     ~DevBuf () { release () ; }
@@ -79,20 +95,18 @@ struct DevBuf
     {
         release () ;
         if (nbytes == 0) nbytes = 16 ;
-        cudaError_t e = cudaMallocAsync (&ptr, nbytes, ctx ().stream) ;
-        if (e != cudaSuccess)
+        ptr = dev_pool_alloc (nbytes, &cap) ;
+        if (ptr == nullptr)
         {
-            ptr = nullptr ;
-            cudaGetLastError () ;
-            set_error ("device allocation of %zu bytes failed: %s", nbytes, cudaGetErrorString (e)) ;
-            return (e == cudaErrorMemoryAllocation) ? GB200_OUT_OF_MEMORY : GB200_CUDA_ERROR ;
+            set_error ("device allocation of %zu bytes failed", nbytes) ;
+            return GB200_OUT_OF_MEMORY ;
         }
         bytes = nbytes ;
         return GB200_SUCCESS ;
     }
     void release ()
     {
-        if (ptr) { cudaFreeAsync (ptr, ctx ().stream) ; ptr = nullptr ; bytes = 0 ; }
+        if (ptr) { dev_pool_free (ptr, cap) ; ptr = nullptr ; bytes = 0 ; cap = 0 ; }
     }
     template <class T> T *as () const { return (T *) ptr ; }
 } ;

@@ -58,13 +58,85 @@ static gb200_status do_init (int device)
     GB200_CUDA (cudaEventCreate (&c.ev1)) ;
     c.pinned_bytes = 1 << 16 ;
     GB200_CUDA (cudaMallocHost (&c.pinned, c.pinned_bytes)) ;
-    // keep freed blocks in the stream-ordered pool: workspace is reused call after call
-    cudaMemPool_t pool ;
-    GB200_CUDA (cudaDeviceGetDefaultMemPool (&pool, device)) ;
-    uint64_t thresh = UINT64_MAX ;
-    GB200_CUDA (cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &thresh)) ;
     c.ready = true ;
     return GB200_SUCCESS ;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device block cache (see DevBuf in engine.cuh)
+// ---------------------------------------------------------------------------------------------
+struct DevPool
+{
+    std::mutex mu ;
+    std::multimap<size_t, void *> cache ;       // free blocks by capacity
+    size_t cached = 0 ;
+} ;
+static DevPool &dev_pool () { static DevPool *p = new DevPool () ; return *p ; }   // never destroyed
+
+static size_t dev_size_class (size_t n)
+{
+    size_t c = 512 ;
+    while (c < n) c <<= 1 ;
+    if (c <= (1u << 20) || c == n) return c ;
+    // eight classes per octave above 1 MiB: at most 12.5 % of slack
+    const size_t lo = c >> 1, step = lo >> 3 ;
+    for (size_t q = lo + step ; q < c ; q += step) if (q >= n) return q ;
+    return c ;
+}
+
+void *dev_pool_alloc (size_t nbytes, size_t *capacity)
+{
+    DevPool &dp = dev_pool () ;
+    const size_t cap = dev_size_class (nbytes) ;
+    {
+        std::lock_guard<std::mutex> lock (dp.mu) ;
+        auto it = dp.cache.find (cap) ;
+        if (it != dp.cache.end ())
+        {
+            void *p = it->second ;
+            dp.cache.erase (it) ;
+            dp.cached -= cap ;
+            *capacity = cap ;
+            return p ;
+        }
+    }
+    void *p = nullptr ;
+    cudaError_t e = cudaMalloc (&p, cap) ;
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError () ;
+        dev_pool_trim () ;                      // drop the cache and try once more
+        e = cudaMalloc (&p, cap) ;
+        if (e != cudaSuccess) { cudaGetLastError () ; return nullptr ; }
+    }
+    *capacity = cap ;
+    return p ;
+}
+
+void dev_pool_free (void *ptr, size_t capacity)
+{
+    if (ptr == nullptr) return ;
+    DevPool &dp = dev_pool () ;
+    std::lock_guard<std::mutex> lock (dp.mu) ;
+    dp.cache.emplace (capacity, ptr) ;
+    dp.cached += capacity ;
+}
+
+void dev_pool_trim ()
+{
+    DevPool &dp = dev_pool () ;
+    std::multimap<size_t, void *> drop ;
+    {
+        std::lock_guard<std::mutex> lock (dp.mu) ;
+        drop.swap (dp.cache) ;
+        dp.cached = 0 ;
+    }
+    if (drop.empty ()) return ;
+    // blocks may still be in use by queued work of the library's stream
+    Ctx &c = ctx () ;
+    if (c.stream != nullptr) cudaStreamSynchronize (c.stream) ;
+    for (auto &kv : drop) cudaFree (kv.second) ;
+    cudaGetLastError () ;
 }
 
 gb200_status ensure_init ()
@@ -470,6 +542,7 @@ gb200_status gb200_finalize (void)
     std::lock_guard<std::recursive_mutex> lock (c.mu) ;
     if (!c.ready) return GB200_SUCCESS ;
     cudaStreamSynchronize (c.stream) ;
+    dev_pool_trim () ;
     cudaFreeHost (c.pinned) ; c.pinned = nullptr ;
     cudaEventDestroy (c.ev0) ; cudaEventDestroy (c.ev1) ;
     cudaStreamDestroy (c.stream) ; c.stream = nullptr ;
