@@ -519,7 +519,8 @@ def main():
                 # length of the list the kernel walks
                 lenA = np.diff(A.p)
                 lenB = np.diff(B.p)
-                walk = np.minimum(lenA[M.i], np.repeat(lenB, np.diff(M.p))) + 1
+                # + a fixed cost per pair (task set-up is worth about 32 probes)
+                walk = np.minimum(lenA[M.i], np.repeat(lenB, np.diff(M.p))) + 32
                 cs = np.concatenate([[0], np.cumsum(walk)])
                 cum = cs[M.p].astype(np.int64)
             bounds = gb.partition_by_flops(cum, world)
@@ -544,6 +545,7 @@ def main():
             pinned[id(m)] = m.pinned()
         return pinned[id(m)]
     hcalls = [] if args.no_e2e else [(pin(m), pin(a), pin(b)) for (m, a, b, _, _, _) in calls]
+    hfull = hcalls
 
     # vector pull on N > 1 GPUs: every rank owns a block of A's vectors = of w's entries, and the
     # slices of w are all-gathered over NCCL every step; T never leaves HBM
@@ -584,10 +586,54 @@ def main():
             out["infos"].append(info)
         return out
 
+    def upload_gathered(m):
+        """N > 1: a replicated operand crosses PCIe once in total -- every rank uploads 1/N of each
+        array over its own link and the pieces are all-gathered over NVLink -- and the
+        library takes the arrays from HBM (gb200_upload_from_device)."""
+        ptrs, keep = [], []
+        for arr in (m.p, m.h, m.i, m.x):
+            if arr is None or arr.size == 0:
+                ptrs.append(0)
+                continue
+            raw = arr.view(np.uint8).reshape(-1)
+            chunk = -(-raw.size // world)
+            chunk += (-chunk) % 16
+            lo, hi = min(rank * chunk, raw.size), min((rank + 1) * chunk, raw.size)
+            local = torch.empty(chunk, dtype=torch.uint8, device=device)
+            if hi > lo:
+                local[: hi - lo].copy_(torch.from_numpy(raw[lo:hi]), non_blocking=True)
+            full = torch.empty(chunk * world, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(full, local)
+            keep.append(full)
+            ptrs.append(full.data_ptr())
+        torch.cuda.synchronize()
+        d = gb.DMatrix.from_device(m, ptrs[0], ptrs[1], ptrs[2], ptrs[3])
+        del keep                                    # the library holds its own (narrowed) copy
+        return d
+
     def step_host():
         """one step through the host entry points: host operands in, host T out.  The matrix A of a
         BFS step is uploaded once per step and shared by its level multiplies."""
         outs = []
+        if world > 1 and args.workload != "bfs":
+            for (m, a, b), (mfull, afull, bfull) in zip(hcalls, hfull):
+                # replicated operands are gathered; the rank's own slice goes straight over PCIe
+                cache = {}
+
+                def up(x, replicated):
+                    if x is None:
+                        return None
+                    if id(x) not in cache:
+                        cache[id(x)] = upload_gathered(x) if replicated else gb.DMatrix(x)
+                    return cache[id(x)]
+                da_ = up(a, sliced_name != "A")
+                db_ = up(b, sliced_name != "B")
+                dm_ = up(m, sliced_name != "M")
+                outs.append(gb.axb_device(dm_, w["mask_comp"], da_, db_, w["semiring"], w["do_adotb"],
+                                          fetch=True, pinned=True))
+                for dx in cache.values():
+                    dx.free()
+            return outs
         if args.workload == "bfs":
             da = gb.DMatrix(hcalls[0][1])
             for (m, a, b) in hcalls:
@@ -624,6 +670,11 @@ def main():
         t_wall = time.perf_counter() - t0
     launches = gb.kernel_launches() - launches0
     tt = torch.tensor([t_events, t_wall], dtype=torch.float64, device=device)
+    rank_ms = [t_events / args.steps * 1e3]
+    if world > 1:
+        allt = torch.zeros(world, dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(allt, tt[:1].clone())
+        rank_ms = [float(v) / args.steps * 1e3 for v in allt.tolist()]
     fl = torch.tensor([r["flops"], r["nnz"]], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -669,18 +720,20 @@ def main():
         t_e2e = te[0].item() / e2e_steps
         seen_once = set()
         for (m, a, b), res in zip(hcalls, rh):
+            mine_x = {"M": m, "A": a, "B": b}.get(sliced_name)
             for x in {id(x): x for x in (m, a, b) if x is not None}.values():
                 if args.workload == "bfs" and x is a:
                     if id(x) in seen_once:
                         continue                    # A of a BFS step crosses PCIe once per step
                     seen_once.add(id(x))
-                h2d += nbytes(x)
+                # N > 1: a rank uploads its own slice whole and 1/N of every replicated operand
+                h2d += nbytes(x) if (world == 1 or x is mine_x) else -(-nbytes(x) // world)
             d2h += nbytes(res.matrix)
         del rh, res
         # where one end-to-end step spends its time: the same step through the three entry points
         # gb200_AxB_host is made of (upload, multiply on resident operands, fetch), each synchronous
         brk = {"upload_ms": 0.0, "multiply_ms": 0.0, "fetch_ms": 0.0}
-        if args.workload != "bfs":
+        if args.workload != "bfs" and world == 1:
             for (m, a, b) in hcalls:
                 t1 = time.perf_counter()
                 ha = gb.DMatrix(a)
@@ -731,13 +784,16 @@ def main():
                                         f"{exchange['bytes']} B gathered per rank") if exchange else
                                        "none (independent output vectors; scalars all-reduced)"},
                 "wall_ms_per_step": tt[1].item() / args.steps * 1e3,
+                "rank_ms_per_step": [round(v, 3) for v in rank_ms],
                 "device_ms_per_step": float(np.mean(dev_ms)),
                 "clocks": clk.summary(),
                 "e2e": None if t_e2e is None else
                        {"value": 2.0 * madds / t_e2e / 1e9, "unit": "GFLOP/s",
                         "ms_per_step": t_e2e * 1e3, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),
-                        "host_memory": "page-locked (gb200_host_malloc)", "breakdown": brk},
+                        "host_memory": "page-locked (gb200_host_malloc)", "breakdown": brk,
+                        "upload": "1/N of every replicated operand per rank over PCIe + NCCL "
+                                  "all-gather over NVLink" if world > 1 else "host to device over PCIe"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,

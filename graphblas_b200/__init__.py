@@ -77,7 +77,7 @@ lib.gb200_last_error.restype = C.c_char_p
 lib.gb200_version.restype = C.c_char_p
 lib.gb200_kernel_launches.restype = C.c_int64
 lib.gb200_multiplies.restype = C.c_int64
-for _name in ("gb200_init", "gb200_finalize", "gb200_upload", "gb200_dmatrix_free",
+for _name in ("gb200_init", "gb200_finalize", "gb200_upload", "gb200_upload_from_device", "gb200_dmatrix_free",
               "gb200_AxB_device", "gb200_AxB_host", "gb200_result_get_info", "gb200_result_fetch",
               "gb200_result_free", "gb200_flopcount_device", "gb200_partition_by_flops",
               "gb200_semiring_canonical", "gb200_device_count", "gb200_timer_mark",
@@ -235,6 +235,19 @@ class DMatrix:
         cm = m.c()
         _check(lib.gb200_upload(C.byref(self._h), C.byref(cm)), "gb200_upload")
         self.host = m
+
+    @classmethod
+    def from_device(cls, like: Matrix, p_ptr: int, h_ptr: int, i_ptr: int, x_ptr: int) -> "DMatrix":
+        """gb200_upload_from_device: the arrays of `like` (same layout, 64-bit indices) already sit
+        in HBM at the given addresses, e.g. after an NCCL all-gather; `like` supplies shape and nnz."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.host = like
+        cm = _CMatrix(like.vlen, like.vdim, like.nvec, p_ptr, h_ptr if like.h is not None else None,
+                      i_ptr if like.nnz else None, x_ptr if like.nnz else None, TYPES[like.type][0], 0)
+        _check(lib.gb200_upload_from_device(C.byref(self._h), C.byref(cm), C.c_int64(like.nnz)),
+               "gb200_upload_from_device")
+        return self
 
     def free(self):
         if self._h:

@@ -164,6 +164,7 @@ gb200_status flopcount (const DMat *M, const DMat &A, const DMat &B, DevBuf &flo
     int64_t *total) ;
 
 gb200_status ensure_iso (gb200_dmatrix_s *d) ;
+gb200_status cast_values (const void *in, int from, int to, int64_t n, DevBuf &out) ;
 gb200_status launch_mask_pos (const DMat &B, const DMat &M, int64_t *lpos) ;
 
 // Turn per-source-vector results into the final T.  `cum` (nsrc+1) is the cumulative entry count

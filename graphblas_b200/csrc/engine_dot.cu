@@ -539,13 +539,26 @@ gb200_status gb200_AxB_device (gb200_result *out, gb200_dmatrix M, int mask_comp
     GB200_TRY (ensure_init ()) ;
     gb200_semiring s = *semiring ;
     GB200_TRY (gb200_semiring_canonical (&s)) ;
-    if (A->v.type_code != s.xy_code || B->v.type_code != s.xy_code)
+    // operands of another built-in type are cast to the multiply operator's input type first (the
+    // reference's typecasting generic path, GB_AxB_Gustavson.c:274-415): a temporary view of the
+    // operand with a cast copy of its values; pointers, indices and hyperlist are shared
+    gb200_dmatrix_s castA, castB ;
+    if (A->v.type_code != s.xy_code)
     {
-        // the typecasting generic path (GB_AxB_Gustavson.c:274-415) is not built
-        set_error ("operand types (%d,%d) differ from the multiply operator's type %d (typecast path "
-            "not built)", A->v.type_code, B->v.type_code, s.xy_code) ;
-        return GB200_NOT_SUPPORTED ;
+        std::lock_guard<std::recursive_mutex> lock (ctx ().mu) ;
+        castA.v = A->v ; castA.is_hyper_flag = A->is_hyper_flag ;
+        GB200_TRY (cast_values (A->v.x, A->v.type_code, s.xy_code, A->v.nnz, castA.x)) ;
+        castA.v.x = castA.x.ptr ; castA.v.type_code = s.xy_code ; castA.v.iso = 0 ;
     }
+    if (B->v.type_code != s.xy_code)
+    {
+        std::lock_guard<std::recursive_mutex> lock (ctx ().mu) ;
+        castB.v = B->v ; castB.is_hyper_flag = B->is_hyper_flag ;
+        GB200_TRY (cast_values (B->v.x, B->v.type_code, s.xy_code, B->v.nnz, castB.x)) ;
+        castB.v.x = castB.x.ptr ; castB.v.type_code = s.xy_code ; castB.v.iso = 0 ;
+    }
+    if (A->v.type_code != s.xy_code) A = &castA ;
+    if (B->v.type_code != s.xy_code) B = &castB ;
     const int64_t cvlen = do_adotb ? A->v.vdim : A->v.vlen ;
     const int64_t cvdim = B->v.vdim ;
     if ((do_adotb && A->v.vlen != B->v.vlen) || (!do_adotb && A->v.vdim != B->v.vlen)
@@ -611,9 +624,10 @@ gb200_status gb200_AxB_host (gb200_result *out, const gb200_matrix *M, int mask_
     // decline before any transfer if the semiring is outside the built-in space
     gb200_semiring s = *semiring ;
     GB200_TRY (gb200_semiring_canonical (&s)) ;
-    if (A->type_code != s.xy_code || B->type_code != s.xy_code)
+    if (A->type_code < GB200_BOOL || A->type_code > GB200_FP64 || B->type_code < GB200_BOOL
+        || B->type_code > GB200_FP64)
     {
-        set_error ("operand types differ from the multiply operator's type (typecast path not built)") ;
+        set_error ("operand of a user-defined type") ;
         return GB200_NOT_SUPPORTED ;
     }
     gb200_dmatrix dM = NULL, dA = NULL, dB = NULL ;
@@ -643,8 +657,9 @@ gb200_status gb200_AxB_host (gb200_result *out, const gb200_matrix *M, int mask_
     if (dB != dA) gb200_dmatrix_free (&dB) ;
     gb200_dmatrix_free (&dA) ;
     if (trace)
-        fprintf (stderr, "gb200_AxB_host: upload %.3f ms, multiply %.3f ms, release %.3f ms\n",
-            t1 - t0, t2 - t1, now () - t2) ;
+        fprintf (stderr, "gb200_AxB_host: upload %.3f ms, multiply %.3f ms (device %.3f ms), release %.3f ms\n",
+            t1 - t0, t2 - t1, (st == GB200_SUCCESS && *out != NULL) ? (*out)->info.device_ms : 0.0,
+            now () - t2) ;
     return st ;
 }
 

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <limits>
+#include <type_traits>
 #include "engine.cuh"
 #include "scan.cuh"
 #include "semiring.cuh"
@@ -271,6 +272,83 @@ gb200_status read_i64 (const int64_t *dptr, int64_t *host)
     GB200_CUDA (cudaMemcpyAsync (c.pinned, dptr, sizeof (int64_t), cudaMemcpyDeviceToHost, c.stream)) ;
     GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
     *host = *(int64_t *) c.pinned ;
+    return GB200_SUCCESS ;
+}
+
+// ---------------------------------------------------------------------------------------------
+// typecasting of built-in operand types.  The reference's generic path casts every entry of A and B
+// to the multiply operator's input type as it is used (Source/GB_AxB_Gustavson.c:360-404,
+// GB_AxB_dot.c:189-305, GB_cast_factory); casting is a pure function of the entry, so the value
+// array is cast once up front and the built-in worker runs on the copy.  Rule: GB_CAST,
+// Source/GB.h:2925-2947 -- float/double NaN -> integer 0, +Inf / -Inf -> the largest / smallest
+// integer, to bool: x != 0, anything else the C cast.  (A finite value outside the integer's range is
+// undefined behaviour in C, Source/GB.h:2902-2913; the device saturates.)
+// ---------------------------------------------------------------------------------------------
+template <class To, class From> __device__ __forceinline__ To cast_one (From x)
+{
+    if constexpr (std::is_same<To, bool>::value) return (x != (From) 0) ;
+    else if constexpr (std::is_integral<To>::value && std::is_floating_point<From>::value)
+    {
+        if (isnan (x)) return (To) 0 ;
+        if (isinf (x)) return (x > 0) ? std::numeric_limits<To>::max () : std::numeric_limits<To>::min () ;
+        // what gcc on x86-64 does with the values C leaves undefined: narrow targets go through int
+        // and a negative value to an unsigned target through the signed conversion (both modular)
+        if constexpr (sizeof (To) < 4) return (To) (int) x ;
+        else if constexpr (std::is_unsigned<To>::value) return (x < 0) ? (To) (long long) x : (To) x ;
+        else return (To) x ;
+    }
+    else return (To) x ;
+}
+
+template <class To, class From>
+__global__ void cast_kernel (const From *__restrict__ in, To *__restrict__ out, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < n ;
+        t += (int64_t) gridDim.x * blockDim.x) out [t] = cast_one<To, From> (in [t]) ;
+}
+
+template <class To>
+static void cast_to (const void *in, int from, void *out, int64_t n, cudaStream_t st)
+{
+    const int g = grid_for (n) ;
+    switch (from)
+    {
+        case GB200_BOOL   : cast_kernel<To, bool>     <<<g, 256, 0, st>>> ((const bool *) in, (To *) out, n) ; break ;
+        case GB200_INT8   : cast_kernel<To, int8_t>   <<<g, 256, 0, st>>> ((const int8_t *) in, (To *) out, n) ; break ;
+        case GB200_UINT8  : cast_kernel<To, uint8_t>  <<<g, 256, 0, st>>> ((const uint8_t *) in, (To *) out, n) ; break ;
+        case GB200_INT16  : cast_kernel<To, int16_t>  <<<g, 256, 0, st>>> ((const int16_t *) in, (To *) out, n) ; break ;
+        case GB200_UINT16 : cast_kernel<To, uint16_t> <<<g, 256, 0, st>>> ((const uint16_t *) in, (To *) out, n) ; break ;
+        case GB200_INT32  : cast_kernel<To, int32_t>  <<<g, 256, 0, st>>> ((const int32_t *) in, (To *) out, n) ; break ;
+        case GB200_UINT32 : cast_kernel<To, uint32_t> <<<g, 256, 0, st>>> ((const uint32_t *) in, (To *) out, n) ; break ;
+        case GB200_INT64  : cast_kernel<To, int64_t>  <<<g, 256, 0, st>>> ((const int64_t *) in, (To *) out, n) ; break ;
+        case GB200_UINT64 : cast_kernel<To, uint64_t> <<<g, 256, 0, st>>> ((const uint64_t *) in, (To *) out, n) ; break ;
+        case GB200_FP32   : cast_kernel<To, float>    <<<g, 256, 0, st>>> ((const float *) in, (To *) out, n) ; break ;
+        default           : cast_kernel<To, double>   <<<g, 256, 0, st>>> ((const double *) in, (To *) out, n) ; break ;
+    }
+}
+
+// out = the n values `in` of type `from`, cast to type `to` (a new buffer)
+gb200_status cast_values (const void *in, int from, int to, int64_t n, DevBuf &out)
+{
+    Ctx &c = ctx () ;
+    GB200_TRY (out.alloc ((size_t) (n > 0 ? n : 1) * type_size (to))) ;
+    if (n <= 0) return GB200_SUCCESS ;
+    switch (to)
+    {
+        case GB200_BOOL   : cast_to<bool>     (in, from, out.ptr, n, c.stream) ; break ;
+        case GB200_INT8   : cast_to<int8_t>   (in, from, out.ptr, n, c.stream) ; break ;
+        case GB200_UINT8  : cast_to<uint8_t>  (in, from, out.ptr, n, c.stream) ; break ;
+        case GB200_INT16  : cast_to<int16_t>  (in, from, out.ptr, n, c.stream) ; break ;
+        case GB200_UINT16 : cast_to<uint16_t> (in, from, out.ptr, n, c.stream) ; break ;
+        case GB200_INT32  : cast_to<int32_t>  (in, from, out.ptr, n, c.stream) ; break ;
+        case GB200_UINT32 : cast_to<uint32_t> (in, from, out.ptr, n, c.stream) ; break ;
+        case GB200_INT64  : cast_to<int64_t>  (in, from, out.ptr, n, c.stream) ; break ;
+        case GB200_UINT64 : cast_to<uint64_t> (in, from, out.ptr, n, c.stream) ; break ;
+        case GB200_FP32   : cast_to<float>    (in, from, out.ptr, n, c.stream) ; break ;
+        default           : cast_to<double>   (in, from, out.ptr, n, c.stream) ; break ;
+    }
+    count_launch () ;
+    GB200_CUDA (cudaGetLastError ()) ;
     return GB200_SUCCESS ;
 }
 
@@ -629,7 +707,7 @@ gb200_status gb200_semiring_canonical (gb200_semiring *s)
 }
 
 // ---- upload ------------------------------------------------------------------------------------
-gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host)
+static gb200_status upload_any (gb200_dmatrix *out, const gb200_matrix *host, int64_t nnz_known)
 {
     if (out == NULL || host == NULL) return GB200_INVALID ;
     *out = NULL ;
@@ -650,8 +728,9 @@ gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host)
         return GB200_NOT_SUPPORTED ;
     }
     const int64_t nvec = host->nvec ;
-    const int64_t nnz = host->p [nvec] - host->p [0] ;
-    if (host->p [0] != 0 || nnz < 0 || (nnz > 0 && (host->i == NULL || host->x == NULL)))
+    // nnz_known >= 0: the arrays are device memory (p cannot be read here); the caller vouches for p[0] == 0
+    const int64_t nnz = (nnz_known >= 0) ? nnz_known : (host->p [nvec] - host->p [0]) ;
+    if ((nnz_known < 0 && host->p [0] != 0) || nnz < 0 || (nnz > 0 && (host->i == NULL || host->x == NULL)))
     {
         set_error ("gb200_upload: malformed matrix (p[0] != 0 or missing arrays)") ;
         return GB200_INVALID ;
@@ -664,13 +743,13 @@ gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host)
     {
         GB200_TRY (d->p.alloc ((nvec + 1) * sizeof (int64_t))) ;
         GB200_CUDA (cudaMemcpyAsync (d->p.ptr, host->p, (nvec + 1) * sizeof (int64_t),
-            cudaMemcpyHostToDevice, c.stream)) ;
+            cudaMemcpyDefault, c.stream)) ;
         if (host->h != NULL)
         {
             GB200_TRY (d->h.alloc ((nvec > 0 ? nvec : 1) * sizeof (int64_t))) ;
             if (nvec > 0)
                 GB200_CUDA (cudaMemcpyAsync (d->h.ptr, host->h, nvec * sizeof (int64_t),
-                    cudaMemcpyHostToDevice, c.stream)) ;
+                    cudaMemcpyDefault, c.stream)) ;
         }
         // 16 bytes of slack: the masked dot kernel reads indices in aligned 16-byte chunks
         GB200_TRY (d->i.alloc (((nnz > 0 ? nnz : 1) + 4) * sizeof (int32_t))) ;
@@ -686,13 +765,13 @@ gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host)
             {
                 const int64_t len = (nnz - off < chunk) ? (nnz - off) : chunk ;
                 GB200_CUDA (cudaMemcpyAsync (stage.ptr, host->i + off, len * sizeof (int64_t),
-                    cudaMemcpyHostToDevice, c.stream)) ;
+                    cudaMemcpyDefault, c.stream)) ;
                 narrow_idx_kernel <<<grid_for (len), 256, 0, c.stream>>> (stage.as<int64_t> (),
                     d->i.as<int32_t> () + off, len) ;
                 count_launch () ;
             }
             GB200_CUDA (cudaMemcpyAsync (d->x.ptr, host->x, (size_t) nnz * tsz,
-                cudaMemcpyHostToDevice, c.stream)) ;
+                cudaMemcpyDefault, c.stream)) ;
             GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
         }
         GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
@@ -712,6 +791,17 @@ gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host)
     d->v.iso = 0 ;
     *out = d ;
     return GB200_SUCCESS ;
+}
+
+gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host)
+{
+    return upload_any (out, host, -1) ;
+}
+
+gb200_status gb200_upload_from_device (gb200_dmatrix *out, const gb200_matrix *dev, int64_t nnz)
+{
+    if (nnz < 0) return GB200_INVALID ;
+    return upload_any (out, dev, nnz) ;
 }
 
 gb200_status gb200_dmatrix_free (gb200_dmatrix *d)

@@ -147,10 +147,12 @@ GrB_Info GB_AxB_parallel            /* same contract as reference Source/GB.h:15
     GrB_BinaryOp add = semiring->add->op ;
     GrB_BinaryOp mult = semiring->multiply ;
 
-    /* the "is it a built-in worker" test of Source/GB_semiring_builtin.c:59-65 */
-    bool builtin = !((A->type != (flipxy ? mult->ytype : mult->xtype)) ||
-        (B->type != (flipxy ? mult->xtype : mult->ytype)) ||
-        (A->type != B->type) || (A->type->code >= GB_UCT_code) ||
+    /* Built-in operators over built-in types (the opcode / type-code part of the test of
+     * Source/GB_semiring_builtin.c:59-65).  Operands whose built-in type differs from the multiply
+     * operator's input type are accepted: the library casts them on the device exactly as the
+     * reference's typecasting path does (GB_AxB_Gustavson.c:360-404, GB_CAST Source/GB.h:2925-2947). */
+    bool builtin = !((A->type->code >= GB_UCT_code) || (B->type->code >= GB_UCT_code) ||
+        (mult->xtype->code >= GB_UCT_code) || (mult->xtype != mult->ytype) ||
         (add->opcode >= GB_USER_C_opcode) || (mult->opcode >= GB_USER_C_opcode)) ;
 
     gb200_semiring s ;

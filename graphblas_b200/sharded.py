@@ -162,12 +162,12 @@ def _vec_lengths(m: Matrix, names: np.ndarray) -> np.ndarray:
 
 
 def masked_dot_walk_cum(M: Matrix, A: Matrix, B: Matrix) -> np.ndarray:
-    """Per stored vector of M: sum over its entries (i,j) of min(len A(:,i), len B(:,j)) + 1 -- the
+    """Per stored vector of M: sum over its entries (i,j) of min(len A(:,i), len B(:,j)) + 32 -- the
     length of the list the masked dot kernel walks for that entry -- cumulative."""
     names = M.h if M.h is not None else np.arange(M.vdim)
     lenB = np.repeat(_vec_lengths(B, names), np.diff(M.p))
     lenA = _vec_lengths(A, M.i)
-    cs = np.concatenate([[0], np.cumsum(np.minimum(lenA, lenB) + 1)]).astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(np.minimum(lenA, lenB) + 32)]).astype(np.int64)
     return cs[M.p]
 
 

@@ -120,6 +120,10 @@ int          gb200_device_count (void) ;
 typedef struct gb200_dmatrix_s *gb200_dmatrix ;
 
 gb200_status gb200_upload (gb200_dmatrix *out, const gb200_matrix *host) ;
+/* The same for operand arrays that are already in HBM of this GPU -- the NCCL all-gather of a
+ * replicated operand over NVLink ("A replicated or all-gathered") instead of N copies over
+ * PCIe.  p, h, i, x of `dev` are device pointers in the same 64-bit layout; nnz = p[nvec] (p[0] == 0). */
+gb200_status gb200_upload_from_device (gb200_dmatrix *out, const gb200_matrix *dev, int64_t nnz) ;
 gb200_status gb200_dmatrix_free (gb200_dmatrix *d) ;
 
 /* the result T of one multiply, resident on the device until fetched or freed */

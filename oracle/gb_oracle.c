@@ -523,6 +523,70 @@ static int dot (oresult *R, const omat *M, int mask_comp, const omat *A, const o
     return ok ;
 }
 
+/* ---- typecasting of built-in types: the generic path of the reference casts every entry of A and B
+ * to the multiply operator's input type before use (Source/GB_AxB_Gustavson.c:360-404,
+ * GB_AxB_dot.c:189-305, via GB_cast_factory); the rule is GB_CAST, Source/GB.h:2925-2947: a float or
+ * double NaN becomes integer 0, +Inf / -Inf the largest / smallest integer, anything else is the C
+ * cast; to bool: x != 0.  Casting is a pure function of the entry, so casting the arrays up front
+ * gives the same T. */
+static void *cast_array (const void *src, int from, int to, int64_t n)
+{
+    void *dst = malloc ((size_t) (n > 0 ? n : 1) * tsize [to]) ;
+    if (dst == NULL) return NULL ;
+    for (int64_t k = 0 ; k < n ; k++)
+    {
+        int64_t sv = 0 ; uint64_t uv = 0 ; double dv = 0 ; float fv = 0 ;
+        int kind ;                          /* 0 signed, 1 unsigned, 2 float, 3 double */
+        switch (from)
+        {
+            case T_BOOL   : uv = ((const uint8_t  *) src) [k] ? 1 : 0 ; kind = 1 ; break ;
+            case T_INT8   : sv = ((const int8_t   *) src) [k] ; kind = 0 ; break ;
+            case T_UINT8  : uv = ((const uint8_t  *) src) [k] ; kind = 1 ; break ;
+            case T_INT16  : sv = ((const int16_t  *) src) [k] ; kind = 0 ; break ;
+            case T_UINT16 : uv = ((const uint16_t *) src) [k] ; kind = 1 ; break ;
+            case T_INT32  : sv = ((const int32_t  *) src) [k] ; kind = 0 ; break ;
+            case T_UINT32 : uv = ((const uint32_t *) src) [k] ; kind = 1 ; break ;
+            case T_INT64  : sv = ((const int64_t  *) src) [k] ; kind = 0 ; break ;
+            case T_UINT64 : uv = ((const uint64_t *) src) [k] ; kind = 1 ; break ;
+            case T_FP32   : fv = ((const float    *) src) [k] ; dv = fv ; kind = 2 ; break ;
+            default       : dv = ((const double   *) src) [k] ; kind = 3 ; break ;
+        }
+#define TO_INT(T, LO, HI)                                                                       \
+        {                                                                                       \
+            T r ;                                                                               \
+            if (kind == 0) r = (T) sv ;                                                         \
+            else if (kind == 1) r = (T) uv ;                                                    \
+            else if (isnan (dv)) r = 0 ;                                                        \
+            else if (isinf (dv)) r = (dv > 0) ? HI : LO ;                                       \
+            else r = (kind == 2) ? (T) fv : (T) dv ;                                            \
+            ((T *) dst) [k] = r ;                                                               \
+        }
+        switch (to)
+        {
+            case T_BOOL   :
+                ((uint8_t *) dst) [k] = (kind == 0) ? (sv != 0) : ((kind == 1) ? (uv != 0) : (dv != 0)) ;
+                break ;
+            case T_INT8   : TO_INT (int8_t,   INT8_MIN,  INT8_MAX)   break ;
+            case T_UINT8  : TO_INT (uint8_t,  0,         UINT8_MAX)  break ;
+            case T_INT16  : TO_INT (int16_t,  INT16_MIN, INT16_MAX)  break ;
+            case T_UINT16 : TO_INT (uint16_t, 0,         UINT16_MAX) break ;
+            case T_INT32  : TO_INT (int32_t,  INT32_MIN, INT32_MAX)  break ;
+            case T_UINT32 : TO_INT (uint32_t, 0,         UINT32_MAX) break ;
+            case T_INT64  : TO_INT (int64_t,  INT64_MIN, INT64_MAX)  break ;
+            case T_UINT64 : TO_INT (uint64_t, 0,         UINT64_MAX) break ;
+            case T_FP32   :
+                ((float *) dst) [k] = (kind == 0) ? (float) sv : ((kind == 1) ? (float) uv :
+                    ((kind == 2) ? fv : (float) dv)) ;
+                break ;
+            default       :
+                ((double *) dst) [k] = (kind == 0) ? (double) sv : ((kind == 1) ? (double) uv : dv) ;
+                break ;
+        }
+#undef TO_INT
+    }
+    return dst ;
+}
+
 /* ---- entry point: the contract of GB_AxB_parallel (Source/GB.h:1522-1537) on plain arrays.
  * Returns 0 on success, 1 out of memory, 2 semiring not built in. */
 int oracle_AxB (oresult *R, const omat *M, int mask_comp, const omat *A, const omat *B,
@@ -530,9 +594,25 @@ int oracle_AxB (oresult *R, const omat *M, int mask_comp, const omat *A, const o
 {
     osemiring s = { add, mult, xy, z, flip } ;
     canonical (&s) ;
-    if (A->type_code != s.xy || B->type_code != s.xy) return 2 ;
+    if (A->type_code < T_BOOL || A->type_code > T_FP64 || B->type_code < T_BOOL
+        || B->type_code > T_FP64) return 2 ;
+    omat Ac = *A, Bc = *B ;
+    void *ax = NULL, *bx = NULL ;
+    if (A->type_code != s.xy)
+    {
+        ax = cast_array (A->x, A->type_code, s.xy, A->p [A->nvec]) ;
+        if (ax == NULL) return 1 ;
+        Ac.x = ax ; Ac.type_code = s.xy ;
+    }
+    if (B->type_code != s.xy)
+    {
+        bx = cast_array (B->x, B->type_code, s.xy, B->p [B->nvec]) ;
+        if (bx == NULL) { free (ax) ; return 1 ; }
+        Bc.x = bx ; Bc.type_code = s.xy ;
+    }
     memset (R, 0, sizeof (*R)) ;
-    int ok = do_adotb ? dot (R, M, mask_comp, A, B, s) : saxpy (R, M, mask_comp, A, B, s) ;
+    int ok = do_adotb ? dot (R, M, mask_comp, &Ac, &Bc, s) : saxpy (R, M, mask_comp, &Ac, &Bc, s) ;
+    free (ax) ; free (bx) ;
     return ok ? 0 : 1 ;
 }
 

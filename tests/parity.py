@@ -74,13 +74,14 @@ def compare(ref: dict, got: dict, add: str) -> tuple[bool, str]:
 
 def run_mxm(G, gpu: bool, *, A, B, type_, semiring, M=None, mtype="BOOL", Cinit=None, accum=None,
             fmt="CSR", outp=GxB_DEFAULT, mask=GxB_DEFAULT, inp0=GxB_DEFAULT, inp1=GxB_DEFAULT,
-            method=GxB_DEFAULT, ctype=None, cfmt=None):
-    """C<M> = accum (C, A*B) through GrB_mxm; returns the CSR export of C and the shim stats delta"""
+            method=GxB_DEFAULT, ctype=None, cfmt=None, btype=None):
+    """C<M> = accum (C, A*B) through GrB_mxm; returns the CSR export of C and the shim stats delta.
+    btype: type of B if it differs from A's (the multiply then typecasts its operands)"""
     sr = semiring.replace("GxB_", "").split("_")
     ztype = "BOOL" if sr[1] in ("EQ", "NE", "GT", "LT", "GE", "LE") else sr[2]
     ctype = ctype or ztype
     a = import_sp(G, A, type_, fmt)
-    b = a if B is A else import_sp(G, B, type_, fmt)
+    b = a if B is A else import_sp(G, B, btype or type_, fmt)
     nrows = A.shape[1] if inp0 == GrB_TRAN else A.shape[0]
     ncols = B.shape[0] if inp1 == GrB_TRAN else B.shape[1]
     if Cinit is not None:

@@ -226,3 +226,27 @@ def test_mxv_vxm(G, op, tran, semiring, type_, usparse):
              mask=(mi, rng.integers(0, 2, len(mi)).astype(bool)), maskd=GrB_SCMP)
     check_mv(G, op=op, A=A, u=(n_in, ui, ux), type_=type_, semiring=semiring, n_out=n_out, tran=tran,
              mask=(mi, rng.integers(0, 2, len(mi)).astype(bool)))
+
+
+# ---------------------------------------------------------------------------------------------
+# typecasting: operands of built-in types other than the multiply operator's
+# are cast on the device as GB_CAST does (Source/GB.h:2925-2947), through the unmodified GrB_mxm
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ta,tb,semiring", [("INT32", "FP32", "GxB_PLUS_TIMES_FP64"),
+                                            ("FP64", "FP32", "GxB_MIN_PLUS_INT16"),
+                                            ("BOOL", "UINT8", "GxB_MAX_TIMES_FP32"),
+                                            ("FP64", "INT64", "GxB_LOR_LAND_BOOL"),
+                                            ("INT8", "FP64", "GxB_PLUS_MIN_UINT16")])
+@pytest.mark.parametrize("method", [GxB_AxB_GUSTAVSON, GxB_AxB_DOT])
+def test_typecast_operands(G, ta, tb, semiring, method):
+    A = gen.er(150, 120, 1400, 31, NP[ta], lo=-6, hi=7)
+    B = gen.er(120, 130, 1300, 32, NP[tb], lo=-6, hi=7)
+    for S, t in ((A, ta), (B, tb)):
+        if t in ("FP32", "FP64"):
+            S.data = (S.data * 1.37).astype(NP[t])
+            S.data[::9] = np.nan
+            S.data[1::11] = np.inf
+            S.data[2::13] = -np.inf
+    M = gen.er(150, 130, 4000, 33, np.int8, lo=0, hi=2)
+    check_mxm(G, A=A, B=B, type_=ta, btype=tb, semiring=semiring, method=method)
+    check_mxm(G, A=A, B=B, type_=ta, btype=tb, semiring=semiring, method=method, M=M, mtype="INT8")

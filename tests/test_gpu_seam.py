@@ -311,3 +311,30 @@ def test_masked_dot_general_path_on_iso_input(monkeypatch):
     slow = gb.axb_host(L, False, U, L, sr, True)
     assert_same(fast.matrix, slow.matrix, "PLUS", "iso vs general")
     assert fast.info["flops"] == slow.info["flops"] == int(fast.matrix.x.sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# typecasting at the seam: the library casts operands of other built-in types on the device
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ta,tb,add,mult,txy", [("INT32", "FP32", "PLUS", "TIMES", "FP64"),
+                                                ("FP64", "FP64", "PLUS", "TIMES", "INT16"),
+                                                ("FP32", "INT8", "MIN", "PLUS", "INT64"),
+                                                ("BOOL", "UINT8", "MAX", "TIMES", "FP32"),
+                                                ("FP64", "INT64", "LOR", "LAND", "BOOL"),
+                                                ("UINT64", "INT8", "PLUS", "MIN", "UINT16"),
+                                                ("FP32", "FP64", "LXOR", "GT", "INT32")])
+def test_typecast_at_the_seam(ta, tb, add, mult, txy):
+    def operand(r, c, nnz, seed, t):
+        S = gen.er(r, c, nnz, seed, NPT[t], lo=-6, hi=7).tocsc()
+        if t in FLOAT:
+            S.data = (S.data * 1.37).astype(NPT[t])
+            S.data[::9] = np.nan
+            S.data[1::11] = np.inf
+            S.data[2::13] = -np.inf
+        return gb.Matrix.from_scipy(S, t)
+    A, At, B = operand(400, 300, 5000, 401, ta), operand(300, 400, 5000, 402, ta), operand(300, 350, 4500, 403, tb)
+    M = gb.Matrix.from_scipy(gen.er(400, 350, 9000, 404, np.int8, lo=0, hi=2).tocsc())
+    sr = gb.Semiring(add, mult, txy)
+    for mask in (None, M):
+        assert_same(oracle_c.axb(mask, False, A, B, sr), gb.axb_host(mask, False, A, B, sr).matrix, add, "saxpy")
+        assert_same(oracle_c.axb(mask, False, At, B, sr, True), gb.axb_host(mask, False, At, B, sr, True).matrix, add, "dot")

@@ -244,3 +244,39 @@ def test_partition_by_flops():
         assert b[0] == 0 and b[-1] == 5000 and np.all(np.diff(b) >= 0)
         work = np.diff(cum[b])
         assert work.max() <= cum[-1] / parts + 1000
+
+
+# ---------------------------------------------------------------------------------------------
+# typecasting of built-in operand types: the reference's generic path casts the
+# entries of A and B to the multiply operator's input type (GB_CAST, Source/GB.h:2925-2947)
+# ---------------------------------------------------------------------------------------------
+TYPECASTS = [("INT32", "FP32", "PLUS", "TIMES", "FP64"), ("FP64", "FP64", "PLUS", "TIMES", "INT16"),
+             ("FP32", "INT8", "MIN", "PLUS", "INT64"), ("BOOL", "UINT8", "MAX", "TIMES", "FP32"),
+             ("FP64", "INT64", "LOR", "LAND", "BOOL"), ("UINT64", "INT8", "PLUS", "MIN", "UINT16"),
+             ("FP32", "FP64", "LXOR", "GT", "INT32")]
+
+
+def typecast_operands(ta, tb, seed):
+    A = gen.er(40, 30, 300, seed, NP[ta], lo=-6, hi=7).tocsc()
+    B = gen.er(30, 35, 280, seed + 1, NP[tb], lo=-6, hi=7).tocsc()
+    for S, t in ((A, ta), (B, tb)):
+        if t in ("FP32", "FP64"):
+            S.data = (S.data * 1.37).astype(NP[t])       # fractional parts: the cast truncates
+            S.data[::9] = np.nan
+            S.data[1::11] = np.inf
+            S.data[2::13] = -np.inf
+    return gb.Matrix.from_scipy(A, ta), gb.Matrix.from_scipy(B, tb)
+
+
+@pytest.mark.parametrize("ta,tb,add,mult,txy", TYPECASTS)
+@pytest.mark.parametrize("dot", [False, True])
+def test_oracle_typecast_vs_reference(G, ta, tb, add, mult, txy, dot):
+    A, B = typecast_operands(ta, tb, 301)
+    if dot:
+        A = gb.Matrix.from_scipy(gen.er(30, 40, 300, 303, NP[ta], lo=-6, hi=7).tocsc(), ta)
+    M = gb.Matrix.from_scipy(gen.er(40, 35, 500, 304, np.int8, lo=0, hi=2).tocsc())
+    sr = gb.Semiring(add, mult, txy)
+    for mask in (None, M):
+        ref, used, applied = seam_reference(G, mask, False, A, B, sr, dot, GxB_AxB_GUSTAVSON)
+        got = oracle_c.axb(mask, False, A, B, sr, dot)
+        same(ref, got, exact=not (txy in ("FP32", "FP64") and add in ("PLUS", "TIMES")))
