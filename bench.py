@@ -437,6 +437,9 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0, help="0: all host cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--slice-of", type=int, default=0, help="one GPU: run the slice --slice-rank of a "
+                    "K-way partition (what one rank of --gpus K computes), for profiling")
+    ap.add_argument("--slice-rank", type=int, default=0)
     args = ap.parse_args()
     if args.workload == "spgemm" and args.scale == 22 and "--scale" not in " ".join(sys.argv):
         args.scale, args.ef = 20, 8
@@ -508,24 +511,25 @@ def main():
         if M is not None:
             dM = dB if M is B else gb.DMatrix(M)
         # flop-balanced contiguous slices of the sliced operand's vectors, one per rank
-        if world > 1:
+        nslices, srank = (args.slice_of, args.slice_rank) if (world == 1 and args.slice_of > 1) else (world, rank)
+        if nslices > 1:
             sliced = {"M": M, "B": B, "A": A}[sliced_name]
             if sliced_name == "B":
                 cum, _ = gb.flopcount(dM, dA, dB)
             elif sliced_name == "A":
                 cum = A.p                       # dot with a vector: work of a vector of A = its length
             else:
-                # masked dot: balance by sum over mask entries of min (len A(:,i), len B(:,j)), the
-                # length of the list the kernel walks
-                lenA = np.diff(A.p)
-                lenB = np.diff(B.p)
-                # + a fixed cost per pair (task set-up is worth about 32 probes)
-                walk = np.minimum(lenA[M.i], np.repeat(lenB, np.diff(M.p))) + 32
-                cs = np.concatenate([[0], np.cumsum(walk)])
-                cum = cs[M.p].astype(np.int64)
-            bounds = gb.partition_by_flops(cum, world)
-            lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-            mine = slice_vectors(sliced, lo, hi)
+                cum = None                      # masked dot: cut by owner vector, below
+            if sliced_name == "M":
+                # a rank takes the mask entries whose owner vector (the longer of A(:,i), B(:,j)) is
+                # in its range: no hub is loaded by more than one rank (graphblas_b200/sharded.py)
+                from graphblas_b200 import sharded
+                mine, (lo, hi), _ = sharded.owner_aligned_mask(M, A, B, nslices, srank)
+                bounds = None
+            else:
+                bounds = gb.partition_by_flops(cum, nslices)
+                lo, hi = int(bounds[srank]), int(bounds[srank + 1])
+                mine = slice_vectors(sliced, lo, hi)
             dmine = gb.DMatrix(mine)
             if sliced_name == "M":
                 M, dM = mine, dmine
@@ -778,8 +782,11 @@ def main():
                                      "steps, max over ranks; wall clock alongside",
                            "l2": "inputs larger than L2 (no flush needed)" if ab > 2.6e8 else
                                  "inputs smaller than L2",
-                           "partition": f"{world} flop-balanced contiguous slices of "
-                                        f"{ {'M': 'the mask', 'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors",
+                           "partition": (f"{world} parts of the mask's entries by owner vector (B(:,j) with j in "
+                                         "the rank's range, or A(:,i) with i in it), balanced by walk length"
+                                         if sliced_name == "M" else
+                                         f"{world} flop-balanced contiguous slices of "
+                                         f"{ {'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors"),
                            "exchange": ("NCCL all-gather of the slices of w every step, "
                                         f"{exchange['bytes']} B gathered per rank") if exchange else
                                        "none (independent output vectors; scalars all-reduced)"},

@@ -179,7 +179,7 @@ __global__ void dotg_tasks_kernel (DMat A, DMat B, DMat M, const int32_t *__rest
 // walked a lane per task) and go to their own launch; the others get DOTG_CHUNK tasks per item.
 // Returns the tasks per work item of owner v if it belongs to the class `hub`, else 0.
 __device__ __forceinline__ int64_t dotg_chunk_of (const DMat &O, const DMat &M, int orient, int64_t v,
-    int64_t cap, int hub)
+    int64_t cap, int hub, int64_t hub_chunk)
 {
     int64_t ko = v ;
     if (!orient) ko = dm_vecpos (O, dm_vecname (M, v)) ;
@@ -187,22 +187,22 @@ __device__ __forceinline__ int64_t dotg_chunk_of (const DMat &O, const DMat &M, 
     const int64_t olen = O.p [ko+1] - O.p [ko] ;
     const bool is_hub = (olen > cap && olen != O.vlen) ;
     if (is_hub != (hub != 0)) return 0 ;
-    return is_hub ? (int64_t) DOTG_HUB_TASKS : DOTG_CHUNK ;
+    return is_hub ? hub_chunk : DOTG_CHUNK ;
 }
 
-__global__ void dotg_nchunks_kernel (DMat O, DMat M, int orient, int64_t cap, int hub,
+__global__ void dotg_nchunks_kernel (DMat O, DMat M, int orient, int64_t cap, int hub, int64_t hub_chunk,
     const int64_t *__restrict__ start, int64_t n, int64_t *__restrict__ nch)
 {
     for (int64_t v = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; v < n ;
         v += (int64_t) gridDim.x * blockDim.x)
     {
         const int64_t cnt = start [v+1] - start [v] ;
-        const int64_t ch = (cnt > 0) ? dotg_chunk_of (O, M, orient, v, cap, hub) : 0 ;
+        const int64_t ch = (cnt > 0) ? dotg_chunk_of (O, M, orient, v, cap, hub, hub_chunk) : 0 ;
         nch [v] = (ch > 0) ? (cnt + ch - 1) / ch : 0 ;
     }
 }
 
-__global__ void dotg_items_kernel (DMat O, DMat M, int orient, int64_t cap, int hub,
+__global__ void dotg_items_kernel (DMat O, DMat M, int orient, int64_t cap, int hub, int64_t hub_chunk,
     const int64_t *__restrict__ start, const int64_t *__restrict__ ioff, int64_t n,
     DotItem *__restrict__ items)
 {
@@ -211,7 +211,7 @@ __global__ void dotg_items_kernel (DMat O, DMat M, int orient, int64_t cap, int 
     {
         const int64_t s0 = start [v], s1 = start [v+1] ;
         if (s1 <= s0) continue ;
-        const int64_t ch = dotg_chunk_of (O, M, orient, v, cap, hub) ;
+        const int64_t ch = dotg_chunk_of (O, M, orient, v, cap, hub, hub_chunk) ;
         if (ch <= 0) continue ;
         int64_t q = ioff [v] ;
         for (int64_t e0 = s0 ; e0 < s1 ; e0 += ch, q++)
@@ -377,10 +377,18 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                     toff.as<int64_t> (), nown, otoff.as<int64_t> ()) ;
                 count_launch () ;
                 ga.tasks = tasks.as<DotTask> () ; ga.orient = orient ;
+                // Tasks per hub item: a lane-per-task item wants many tasks per lane, but there must
+                // also be several items per resident block or a few big hubs serialise the launch
+                // (one rank of an 8-GPU run holds an eighth of the hubs)
+                int64_t hub_chunk = ntasks / (2 * 6 * (int64_t) c.sm_count * 2) ;
+                hub_chunk = ((hub_chunk + 511) / 512) * 512 ;
+                if (hub_chunk < 2048) hub_chunk = 2048 ;
+                if (hub_chunk > DOTG_HUB_TASKS) hub_chunk = DOTG_HUB_TASKS ;
+                if (getenv ("GB200_DOTG_HUB_CHUNK")) hub_chunk = atoll (getenv ("GB200_DOTG_HUB_CHUNK")) ;
                 for (int hub = 1 ; hub >= 0 ; hub--)
                 {
                     dotg_nchunks_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                        orient ? A : B, Mv, orient, cap, hub, otoff.as<int64_t> (), nown,
+                        orient ? A : B, Mv, orient, cap, hub, hub_chunk, otoff.as<int64_t> (), nown,
                         nch.as<int64_t> ()) ;
                     count_launch () ;
                     GB200_TRY (scan_i64 (nch.as<int64_t> (), ioff.as<int64_t> (), nown)) ;
@@ -390,8 +398,8 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                     DevBuf items ;
                     GB200_TRY (items.alloc (nitems * sizeof (DotItem))) ;
                     dotg_items_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                        orient ? A : B, Mv, orient, cap, hub, otoff.as<int64_t> (), ioff.as<int64_t> (),
-                        nown, items.as<DotItem> ()) ;
+                        orient ? A : B, Mv, orient, cap, hub, hub_chunk, otoff.as<int64_t> (),
+                        ioff.as<int64_t> (), nown, items.as<DotItem> ()) ;
                     count_launch () ;
                     GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 16, c.stream)) ;
                     ga.items = items.as<DotItem> () ; ga.nitems = nitems ;

@@ -7,8 +7,10 @@ of GB_AxB_flopcount (Source/GB_AxB_flopcount.c:32-37).  SURVEY.md 8(e) maps ever
 
   matrix x matrix, saxpy   B's vectors are cut into N contiguous slices of equal flops, A (and M) are
                            replicated, every rank computes its slice of C; no data-path collective
-  masked dot               M's (= C's) vectors are cut, balanced by the length of the lists the kernel
-                           walks; A and B replicated; no data-path collective
+  masked dot               M's ENTRIES are cut by owner vector (owner_aligned_mask): a rank takes the
+                           pairs whose longer vector is B(:,j) with j in its range, or A(:,i) with i in
+                           its range; A and B replicated; no data-path collective; the ranks' T are
+                           disjoint parts of the whole T
   vector pull (A'*u)       A's vectors (= output entries) are cut by entry count; the slices of w are
                            all-gathered
   vector push (A*u)        u's entries are cut by flops; every rank gets a partial w over the whole
@@ -171,6 +173,55 @@ def masked_dot_walk_cum(M: Matrix, A: Matrix, B: Matrix) -> np.ndarray:
     return cs[M.p]
 
 
+def owner_aligned_mask(M: Matrix, A: Matrix, B: Matrix, nparts: int, part: int, hub_len: int = 6144):
+    """The part of the mask that rank `part` of `nparts` computes in C<M> = A'*B, as a matrix M_r with
+    M's dimensions: the entries (i,j) whose LONGER vector ("owner", the one the masked dot kernel loads
+    into shared memory) belongs to the rank -- B(:,j) with j in the rank's range of M's vectors, or
+    A(:,i) with i in the rank's range of row indices.  Cutting M by vectors alone would hand every
+    rank 1/N of the pairs of each A-owned hub, so every rank would load every hub (measured on RMAT
+    scale 22, N = 8: 4.0x instead of the 7x the kernels allow).  The parts are disjoint and cover M;
+    both ranges are balanced by the length of the walked lists.  Returns (M_r, (jlo, jhi), (ilo, ihi))."""
+    names = M.h if M.h is not None else np.arange(M.vdim, dtype=np.int64)
+    cnt = np.diff(M.p)
+    vpos = np.repeat(np.arange(M.nvec, dtype=np.int64), cnt)
+    lenB = np.repeat(_vec_lengths(B, names), cnt)
+    lenA = _vec_lengths(A, M.i)
+    vlen = A.vlen
+    b_owns = (lenB == vlen) | ((lenA != vlen) & (lenA <= lenB))        # the kernel's own rule
+    # cost of a pair: the walked length + task set-up (worth ~32 probes); a probe of a hub owner
+    # (loaded segment by segment, cursor per task) was measured at ~1.6x a probe of a regular owner
+    olen = np.where(b_owns, lenB, lenA)
+    hub = np.where((olen > hub_len) & (olen != vlen), 8, 5)
+    wB = np.where(b_owns, (lenA + 32) * hub, 0).astype(np.int64)        # walk A(:,i)
+    wA = np.where(~b_owns, (lenB + 32) * hub, 0).astype(np.int64)
+    cumB = np.concatenate([[0], np.cumsum(wB)]).astype(np.int64)[M.p]
+    cumA = np.concatenate([[0], np.cumsum(np.bincount(M.i, weights=wA, minlength=M.vlen))]).astype(np.int64)
+    jb = partition_by_flops(cumB, nparts)
+    ib = partition_by_flops(cumA, nparts)
+    jlo, jhi, ilo, ihi = int(jb[part]), int(jb[part + 1]), int(ib[part]), int(ib[part + 1])
+    sel = (b_owns & (vpos >= jlo) & (vpos < jhi)) | (~b_owns & (M.i >= ilo) & (M.i < ihi))
+    p = np.concatenate([[0], np.cumsum(np.bincount(vpos[sel], minlength=M.nvec))]).astype(np.int64)
+    return Matrix(M.vlen, M.vdim, p, M.i[sel], M.x[sel], M.h, M.type), (jlo, jhi), (ilo, ihi)
+
+
+def merge_disjoint(parts: list[Matrix]) -> Matrix:
+    """Union of matrices with the same dimensions whose patterns are disjoint (the per-rank results of
+    an owner-aligned masked dot): entries re-sorted inside every vector.  Hypersparse parts list only
+    their own non-empty vectors, so vectors are matched by name."""
+    first = parts[0]
+    hyper = first.h is not None
+    vname = [np.repeat(t.h if hyper else np.arange(t.nvec, dtype=np.int64), np.diff(t.p)) for t in parts]
+    names = np.unique(np.concatenate([t.h for t in parts])) if hyper else None
+    v = np.concatenate(vname)
+    i = np.concatenate([t.i for t in parts])
+    x = np.concatenate([t.x for t in parts])
+    vpos = np.searchsorted(names, v) if hyper else v
+    nvec = len(names) if hyper else first.nvec
+    order = np.lexsort((i, vpos))
+    p = np.concatenate([[0], np.cumsum(np.bincount(vpos, minlength=nvec))]).astype(np.int64)
+    return Matrix(first.vlen, first.vdim, p, i[order], x[order], names, first.type)
+
+
 # ---------------------------------------------------------------------------------------------
 # the multiply
 # ---------------------------------------------------------------------------------------------
@@ -192,22 +243,27 @@ def mxm(M: Optional[Matrix], mask_comp: bool, A: Matrix, B: Matrix, semiring: Se
         return _vector_push(comm, mul, M, mask_comp, A, B, semiring, method)
 
     W, r = comm.world, comm.rank
-    use_mask_slices = do_adotb and M is not None and not mask_comp
-    if use_mask_slices:
-        cum, sliced, what = masked_dot_walk_cum(M, A, B), M, "M"
-    else:
-        cum, sliced, what = saxpy_flops_cum(M, A, B), B, "B"
-        if do_adotb:
-            # unmasked / complemented dot: every (i,j) pair is computed; cost of B(:,j) ~ its length
-            cum = (B.p + np.arange(len(B.p))).astype(np.int64)
+    if do_adotb and M is not None and not mask_comp:
+        # masked dot: every mask entry is an independent dot product; a rank takes the entries whose
+        # owner vector is its own (owner_aligned_mask).  Its T is a disjoint part of the whole T
+        # (not a contiguous run of vectors): gather=True merges the parts.
+        Mr, (lo, hi), _ = owner_aligned_mask(M, A, B, W, r)
+        res = mul(Mr, False, A, B, semiring, True, method)
+        nnz_all, flops_all = comm.sum_i64([res.info["nnz"], res.info["flops"]])
+        T = res.matrix
+        full = None
+        if gather:
+            full = T if W == 1 else merge_disjoint(_gather_parts(comm, T))
+        return ShardedResult(T, lo, hi, "M(owner)", nnz_all, flops_all, True,
+                             int(res.info["method_used"]), full, res.info)
+    cum, sliced, what = saxpy_flops_cum(M, A, B), B, "B"
+    if do_adotb:
+        # unmasked / complemented dot: every (i,j) pair is computed; cost of B(:,j) ~ its length
+        cum = (B.p + np.arange(len(B.p))).astype(np.int64)
     bounds = partition_by_flops(cum, W)
     lo, hi = int(bounds[r]), int(bounds[r + 1])
     mine = slice_vectors(sliced, lo, hi)
-    Mr, Br = M, B
-    if what == "M":
-        Mr = mine
-    else:
-        Br = mine
+    Mr, Br = M, mine
     # the saxpy mask rule (GB_AxB_sequential.c:88-95) compares GLOBAL counts: decide once.  The flop
     # count that the rule uses honours the mask's range pruning, so it comes from the multiplies
     # themselves: first pass with KEEP, and if the global rule says "drop", redo without the mask.
@@ -225,6 +281,19 @@ def mxm(M: Optional[Matrix], mask_comp: bool, A: Matrix, B: Matrix, semiring: Se
         full = _gather_matrix(comm, T)
     return ShardedResult(T, lo, hi, what, nnz_all, flops_all, bool(res.info["mask_applied"]),
                          int(res.info["method_used"]), full, res.info)
+
+
+def _gather_parts(comm: _Comm, T: Matrix) -> list:
+    """every rank's T (same dimensions and vector list), on every rank"""
+    nz = comm.gather_i64(T.nnz)
+    Is = comm.allgather_bytes(T.i, nz)
+    Xs = comm.allgather_bytes(T.x, nz)
+    nv = comm.gather_i64(len(T.p))
+    Ps = comm.allgather_bytes(T.p, nv)
+    Hs = [None] * comm.world
+    if T.h is not None:
+        Hs = comm.allgather_bytes(T.h, [n - 1 for n in nv])
+    return [Matrix(T.vlen, T.vdim, Ps[q], Is[q], Xs[q], Hs[q], T.type) for q in range(comm.world)]
 
 
 def _gather_matrix(comm: _Comm, T: Matrix) -> Matrix:

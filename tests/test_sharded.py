@@ -130,7 +130,7 @@ def _worker(rank: int, world: int, port: int, errq):
             assert r.nnz == ref.nnz, what + ": global nnz"
             assert r.mask_applied == bool(ref_info["mask_applied"]), what + ": mask_applied"
             assert 0 <= r.lo <= r.hi, what
-            if r.sliced in ("B", "M") and world > 1:
+            if r.sliced == "B" and world > 1:
                 # slices are disjoint and cover: the local nnz add up (checked through r.nnz) and the
                 # local T has entries only inside its own range of vectors
                 cnt = np.diff(r.local.p)
@@ -194,3 +194,24 @@ def test_partition_is_flop_balanced():
         per = np.diff(cum[b])
         assert per.sum() == total
         assert per.max() <= total / parts + np.diff(cum).max()
+
+
+def test_owner_aligned_mask_parts_are_disjoint_and_cover():
+    """every mask entry goes to exactly one rank, and an owner vector never serves two ranks"""
+    S = gen.rmat_scipy(11, 8).tocsc().astype(np.int64)
+    L = gb.Matrix.from_scipy(__import__("scipy.sparse", fromlist=["tril"]).tril(S, -1).tocsc())
+    U = gb.Matrix.from_scipy(__import__("scipy.sparse", fromlist=["triu"]).triu(S, 1).tocsc())
+    for M in (L, L.to_hyper()):
+        for W in (2, 5):
+            parts = [sharded.owner_aligned_mask(M, U, L, W, r) for r in range(W)]
+            assert sum(p[0].nnz for p in parts) == M.nnz
+            merged = sharded.merge_disjoint([p[0] for p in parts])
+            assert np.array_equal(merged.p, M.p) and np.array_equal(merged.i, M.i)
+            lenA, lenB = np.diff(U.p), np.diff(L.p)
+            names = M.h if M.h is not None else np.arange(M.vdim)
+            for Mr, (jlo, jhi), (ilo, ihi) in parts:
+                j = names[np.repeat(np.arange(Mr.nvec), np.diff(Mr.p))]
+                b_owns = lenA[Mr.i] <= lenB[j]
+                pos = np.searchsorted(names, j)
+                assert np.all((pos[b_owns] >= jlo) & (pos[b_owns] < jhi))
+                assert np.all((Mr.i[~b_owns] >= ilo) & (Mr.i[~b_owns] < ihi))
