@@ -338,3 +338,30 @@ def test_typecast_at_the_seam(ta, tb, add, mult, txy):
     for mask in (None, M):
         assert_same(oracle_c.axb(mask, False, A, B, sr), gb.axb_host(mask, False, A, B, sr).matrix, add, "saxpy")
         assert_same(oracle_c.axb(mask, False, At, B, sr, True), gb.axb_host(mask, False, At, B, sr, True).matrix, add, "dot")
+
+
+def test_masked_dot_edge_cases():
+    """empty mask, a mask whose entries are all false, empty operands, a single pair, 1-by-n shapes"""
+    n = 500
+    A = gb.Matrix.from_scipy(gen.er(n, n, 9 * n, 501, np.int32, lo=1, hi=5).tocsc())
+    B = gb.Matrix.from_scipy(gen.er(n, n, 9 * n, 502, np.int32, lo=1, hi=5).tocsc())
+    sr = gb.Semiring("PLUS", "TIMES", "INT32")
+    empty = gb.Matrix.from_scipy(sp.csc_matrix((n, n), dtype=np.bool_))
+    Mf = gen.er(n, n, 6 * n, 503, np.int8, lo=0, hi=1).tocsc()     # present, all false
+    Mf.data[:] = 0
+    one = gb.Matrix.from_scipy(sp.csc_matrix((np.array([True]), (np.array([7]), np.array([9]))), shape=(n, n)))
+    Ae = gb.Matrix.from_scipy(sp.csc_matrix((n, n), dtype=np.int32))
+    M = gb.Matrix.from_scipy(gen.er(n, n, 6 * n, 504, np.bool_).tocsc())
+    for m, a, b, what in ((empty, A, B, "empty mask"), (gb.Matrix.from_scipy(Mf, "INT8"), A, B, "all-false mask"),
+                          (one, A, B, "one pair"), (M, Ae, B, "empty A"), (M, A, Ae, "empty B"),
+                          (M.to_hyper(), A.to_hyper(), B.to_hyper(), "all hypersparse")):
+        for comp in (False, True):
+            if comp and what in ("empty mask", "all-false mask"):
+                continue                                    # C<!empty> = A'*B is the full n*n dot product
+            assert_same(oracle_c.axb(m, comp, a, b, sr, True), gb.axb_host(m, comp, a, b, sr, True).matrix,
+                        "PLUS", f"{what} comp={comp}")
+    row = gb.Matrix.from_scipy(gen.er(n, 1, 40, 505, np.int32, lo=1, hi=5).tocsc())
+    col = gb.Matrix.from_scipy(gen.er(n, 3, 90, 506, np.int32, lo=1, hi=5).tocsc())
+    m13 = gb.Matrix.from_scipy(sp.csc_matrix(np.ones((1, 3), dtype=np.bool_)))
+    assert_same(oracle_c.axb(m13, False, row, col, sr, True), gb.axb_host(m13, False, row, col, sr, True).matrix,
+                "PLUS", "1-by-3 result")
