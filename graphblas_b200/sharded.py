@@ -191,9 +191,12 @@ def owner_aligned_mask(M: Matrix, A: Matrix, B: Matrix, nparts: int, part: int, 
     # cost of a pair: the walked length + task set-up (worth ~32 probes); a probe of a hub owner
     # (loaded segment by segment, cursor per task) was measured at ~1.6x a probe of a regular owner
     olen = np.where(b_owns, lenB, lenA)
-    hub = np.where((olen > hub_len) & (olen != vlen), 8, 5)
-    wB = np.where(b_owns, (lenA + 32) * hub, 0).astype(np.int64)        # walk A(:,i)
-    wA = np.where(~b_owns, (lenB + 32) * hub, 0).astype(np.int64)
+    is_hub = (olen > hub_len) & (olen != vlen)
+    hub = np.where(is_hub, 8, 5)
+    # ... and every segment of a hub is one more visit of the task (~24 probes' worth)
+    visits = np.where(is_hub, 24 * ((olen + hub_len - 1) // hub_len), 0)
+    wB = np.where(b_owns, (lenA + visits + 32) * hub, 0).astype(np.int64)       # walk A(:,i)
+    wA = np.where(~b_owns, (lenB + visits + 32) * hub, 0).astype(np.int64)
     cumB = np.concatenate([[0], np.cumsum(wB)]).astype(np.int64)[M.p]
     cumA = np.concatenate([[0], np.cumsum(np.bincount(M.i, weights=wA, minlength=M.vlen))]).astype(np.int64)
     jb = partition_by_flops(cumB, nparts)
