@@ -782,7 +782,8 @@ def main():
                                      "steps, max over ranks; wall clock alongside",
                            "l2": "inputs larger than L2 (no flush needed)" if ab > 2.6e8 else
                                  "inputs smaller than L2",
-                           "partition": (f"{world} parts of the mask's entries by owner vector (B(:,j) with j in "
+                           "partition": "none (one GPU)" if world == 1 else
+                                        (f"{world} parts of the mask's entries by owner vector (B(:,j) with j in "
                                          "the rank's range, or A(:,i) with i in it), balanced by walk length"
                                          if sliced_name == "M" else
                                          f"{world} flop-balanced contiguous slices of "

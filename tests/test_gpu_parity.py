@@ -250,3 +250,24 @@ def test_typecast_operands(G, ta, tb, semiring, method):
     M = gen.er(150, 130, 4000, 33, np.int8, lo=0, hi=2)
     check_mxm(G, A=A, B=B, type_=ta, btype=tb, semiring=semiring, method=method)
     check_mxm(G, A=A, B=B, type_=ta, btype=tb, semiring=semiring, method=method, M=M, mtype="INT8")
+
+
+# ---------------------------------------------------------------------------------------------
+# k-truss iteration (Extras/ktruss/ktruss_graphblas.c:103): C<C> = C*C over PLUS_LAND_INT64 with C as
+# mask and both operands, then the entries below the support are dropped; the next caller of the path
+# ---------------------------------------------------------------------------------------------
+def test_ktruss_iterations(G):
+    A = gen.rmat_scipy(9, 12, dtype=np.int64)
+    Cm = A.copy().tocsr()
+    Cm.data[:] = 1
+    k = 4
+    for _ in range(4):
+        ref, got = check_mxm(G, A=Cm, B=Cm, M=Cm, mtype="INT64", type_="INT64",
+                             semiring="GxB_PLUS_LAND_INT64")
+        T = sp.csr_matrix((got["Ax"], got["Ai"], got["Ap"]), shape=Cm.shape)
+        keep = T.data >= k - 2
+        rows = np.repeat(np.arange(T.shape[0]), np.diff(T.indptr))[keep]
+        nxt = sp.csr_matrix((np.ones(int(keep.sum()), np.int64), (rows, T.indices[keep])), shape=Cm.shape)
+        if nxt.nnz == Cm.nnz or nxt.nnz == 0:
+            break
+        Cm = nxt
