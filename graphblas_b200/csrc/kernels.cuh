@@ -289,14 +289,15 @@ __global__ void dot_kernel (DotArgs a)
 // masked dot products, C<M> = A'*B, grouped by the LONGER vector of each pair ("owner").
 //
 // For a mask entry (i,j) the shorter of A(:,i), B(:,j) is walked and the longer one is probed.  On a
-// power-law graph the walked lengths sum to ~7x the number of matches, so a probe must cost a
+// power-law graph the walked lengths sum to ~8.6x the number of matches, so a probe must cost a
 // handful of instructions and never leave the SM: pairs are grouped by their owner vector, a thread
 // block loads the owner into a shared-memory CUCKOO table (two tables, two hash functions, total
-// load <= 0.25) once and then serves every task of its work item from it.  A cuckoo lookup is
+// load <= 3/8) once and then serves every task of its work item from it.  A cuckoo lookup is
 // exactly two shared-memory loads and two compares -- no probe loop, so no divergence -- which lets
 // the walk be unrolled DOTG_U-fold with all its loads in flight.  Owners longer than the table's
-// capacity are loaded segment by segment (both lists are sorted, so every task keeps a cursor and
-// each walked index is probed against exactly one segment).  orient 0: owner = B(:,j); orient 1:
+// capacity ("hubs") are loaded segment by segment (both lists are sorted, so every task keeps a
+// cursor and each walked index is probed against exactly one segment) by the HUB instantiation, in
+// which a LANE, not a warp, walks a task (dotg_lanes).  orient 0: owner = B(:,j); orient 1:
 // owner = A(:,i) (the mask entries regrouped by i).  A TASK is one pair, or one DOTG_SEG-long
 // segment of a pair whose walked list is longer than that (pieces are combined with the monoid's
 // atomic); the warps of a block pull tasks from a shared counter, so one long pair cannot stall a
@@ -308,7 +309,7 @@ constexpr int DOTG_SMEM = 64 * 1024 ;       // table bytes per block
 constexpr int DOTG_SEG = 1024 ;             // longest walk of one task
 constexpr int DOTG_THREADS = 512 ;
 constexpr int DOTG_U = 4 ;                  // walk unrolling: 32 * DOTG_U indices per warp iteration
-constexpr int DOTG_HUB_TASKS = 16384 ;      // tasks of one HUB work item (one 16-bit cursor each)
+constexpr int DOTG_HUB_TASKS = 16384 ;      // most tasks of one HUB work item (one 16-bit cursor each)
 constexpr int DOTG_SMALL = 32 ;             // owners shorter than this: dot_kernel, one lane group per pair
 constexpr int DOTG_MAXIT = 48 ;             // longest eviction chain before a table is rebuilt
 
