@@ -799,6 +799,7 @@ def main():
                 "wall_ms_per_step": tt[1].item() / args.steps * 1e3,
                 "rank_ms_per_step": [round(v, 3) for v in rank_ms],
                 "device_ms_per_step": float(np.mean(dev_ms)),
+                "device_ms_steps": [round(float(v), 3) for v in dev_ms],
                 "clocks": clk.summary(),
                 "e2e": None if t_e2e is None else
                        {"value": 2.0 * madds / t_e2e / 1e9, "unit": "GFLOP/s",
