@@ -440,6 +440,8 @@ def main():
     ap.add_argument("--slice-of", type=int, default=0, help="one GPU: run the slice --slice-rank of a "
                     "K-way partition (what one rank of --gpus K computes), for profiling")
     ap.add_argument("--slice-rank", type=int, default=0)
+    ap.add_argument("--calibrate", type=int, default=2, help="N > 1, masked dot: rounds of measured "
+                    "re-balancing of the ranks' parts before the timed region")
     args = ap.parse_args()
     if args.workload == "spgemm" and args.scale == 22 and "--scale" not in " ".join(sys.argv):
         args.scale, args.ef = 20, 8
@@ -527,9 +529,34 @@ def main():
                 cum = None                      # masked dot: cut by owner vector, below
             if sliced_name == "M":
                 # a rank takes the mask entries whose owner vector (the longer of A(:,i), B(:,j)) is
-                # in its range: no hub is loaded by more than one rank (graphblas_b200/sharded.py)
+                # in its range: no hub is loaded by more than one rank (graphblas_b200/sharded.py).
+                # The cut follows a cost model of the kernels; two calibration rounds (one multiply per
+                # rank, outside the timed region) correct it with the ranks' measured times.
                 from graphblas_b200 import sharded
-                mine, (lo, hi), _ = sharded.owner_aligned_mask(M, A, B, nslices, srank)
+                op = sharded.OwnerPartition(M, A, B, nslices)
+                calib = []
+
+                def part_ms(r):
+                    dm_r = gb.DMatrix(op.mask(r))
+                    t = 0.0
+                    for _ in range(2):              # the first one warms the allocator
+                        t = gb.axb_device(dm_r, w["mask_comp"], dA, dB, w["semiring"], w["do_adotb"],
+                                          fetch=False).info["device_ms"]
+                    dm_r.free()
+                    return t
+                for _ in range(args.calibrate):
+                    if world > 1:
+                        tl = torch.zeros(world, dtype=torch.float64, device=device)
+                        tl[rank] = part_ms(rank)
+                        dist.all_reduce(tl)
+                        times = tl.tolist()
+                    else:
+                        times = [part_ms(r) for r in range(nslices)]   # --slice-of: every rank in turn
+                    calib.append([round(v, 3) for v in times])
+                    op.rebalance(times)
+                w["calibration_ms"] = calib
+                mine = op.mask(srank)
+                (lo, hi), _ = op.ranges(srank)
                 bounds = None
             else:
                 bounds = gb.partition_by_flops(cum, nslices)
@@ -793,6 +820,7 @@ def main():
                                          if sliced_name == "M" else
                                          f"{world} flop-balanced contiguous slices of "
                                          f"{ {'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors"),
+                           "calibration_ms": w.get("calibration_ms"),
                            "exchange": ("NCCL all-gather of the slices of w every step, "
                                         f"{exchange['bytes']} B gathered per rank") if exchange else
                                        "none (independent output vectors; scalars all-reduced)"},

@@ -173,38 +173,79 @@ def masked_dot_walk_cum(M: Matrix, A: Matrix, B: Matrix) -> np.ndarray:
     return cs[M.p]
 
 
-def owner_aligned_mask(M: Matrix, A: Matrix, B: Matrix, nparts: int, part: int, hub_len: int = 6144):
-    """The part of the mask that rank `part` of `nparts` computes in C<M> = A'*B, as a matrix M_r with
-    M's dimensions: the entries (i,j) whose LONGER vector ("owner", the one the masked dot kernel loads
-    into shared memory) belongs to the rank -- B(:,j) with j in the rank's range of M's vectors, or
+class OwnerPartition:
+    """The owner-aligned cut of a mask for C<M> = A'*B on N ranks.
+
+    A rank computes the mask entries (i,j) whose LONGER vector ("owner", the one the masked dot kernel
+    loads into shared memory) belongs to it: B(:,j) with j in the rank's range of M's vectors, or
     A(:,i) with i in the rank's range of row indices.  Cutting M by vectors alone would hand every
     rank 1/N of the pairs of each A-owned hub, so every rank would load every hub (measured on RMAT
-    scale 22, N = 8: 4.0x instead of the 7x the kernels allow).  The parts are disjoint and cover M;
-    both ranges are balanced by the length of the walked lists.  Returns (M_r, (jlo, jhi), (ilo, ihi))."""
-    names = M.h if M.h is not None else np.arange(M.vdim, dtype=np.int64)
-    cnt = np.diff(M.p)
-    vpos = np.repeat(np.arange(M.nvec, dtype=np.int64), cnt)
-    lenB = np.repeat(_vec_lengths(B, names), cnt)
-    lenA = _vec_lengths(A, M.i)
-    vlen = A.vlen
-    b_owns = (lenB == vlen) | ((lenA != vlen) & (lenA <= lenB))        # the kernel's own rule
-    # cost of a pair: the walked length + task set-up (worth ~32 probes); a probe of a hub owner
-    # (loaded segment by segment, cursor per task) was measured at ~1.6x a probe of a regular owner
-    olen = np.where(b_owns, lenB, lenA)
-    is_hub = (olen > hub_len) & (olen != vlen)
-    hub = np.where(is_hub, 8, 5)
-    # ... and every segment of a hub is one more visit of the task (~24 probes' worth)
-    visits = np.where(is_hub, 24 * ((olen + hub_len - 1) // hub_len), 0)
-    wB = np.where(b_owns, (lenA + visits + 32) * hub, 0).astype(np.int64)       # walk A(:,i)
-    wA = np.where(~b_owns, (lenB + visits + 32) * hub, 0).astype(np.int64)
-    cumB = np.concatenate([[0], np.cumsum(wB)]).astype(np.int64)[M.p]
-    cumA = np.concatenate([[0], np.cumsum(np.bincount(M.i, weights=wA, minlength=M.vlen))]).astype(np.int64)
-    jb = partition_by_flops(cumB, nparts)
-    ib = partition_by_flops(cumA, nparts)
-    jlo, jhi, ilo, ihi = int(jb[part]), int(jb[part + 1]), int(ib[part]), int(ib[part + 1])
-    sel = (b_owns & (vpos >= jlo) & (vpos < jhi)) | (~b_owns & (M.i >= ilo) & (M.i < ihi))
-    p = np.concatenate([[0], np.cumsum(np.bincount(vpos[sel], minlength=M.nvec))]).astype(np.int64)
-    return Matrix(M.vlen, M.vdim, p, M.i[sel], M.x[sel], M.h, M.type), (jlo, jhi), (ilo, ihi)
+    scale 22, N = 8: 4.0x instead of the 7x the kernels allow).  The parts are disjoint and cover M.
+    Both ranges are balanced by a cost model of the kernels; rebalance() corrects the model with the
+    ranks' measured times (set-up work: a calibration multiply per rank, outside any timed region)."""
+
+    def __init__(self, M: Matrix, A: Matrix, B: Matrix, nparts: int, hub_len: int = 6144):
+        self.M, self.nparts = M, nparts
+        names = M.h if M.h is not None else np.arange(M.vdim, dtype=np.int64)
+        cnt = np.diff(M.p)
+        self.vpos = np.repeat(np.arange(M.nvec, dtype=np.int64), cnt)
+        lenB = np.repeat(_vec_lengths(B, names), cnt)
+        lenA = _vec_lengths(A, M.i)
+        vlen = A.vlen
+        self.b_owns = (lenB == vlen) | ((lenA != vlen) & (lenA <= lenB))   # the kernel's own rule
+        # cost of a pair: the walked length + task set-up (worth ~32 probes); a probe of a hub owner
+        # (loaded segment by segment, cursor per task) was measured at ~1.6x a probe of a regular
+        # owner, and every segment of a hub is one more visit of the task (~24 probes' worth)
+        olen = np.where(self.b_owns, lenB, lenA)
+        is_hub = (olen > hub_len) & (olen != vlen)
+        hub = np.where(is_hub, 8, 5)
+        visits = np.where(is_hub, 24 * ((olen + hub_len - 1) // hub_len), 0)
+        wB = np.where(self.b_owns, (lenA + visits + 32) * hub, 0).astype(np.float64)    # walk A(:,i)
+        wA = np.where(~self.b_owns, (lenB + visits + 32) * hub, 0).astype(np.float64)
+        # per vector of M (B-owned pairs) and per row index (A-owned pairs)
+        self.wvec = np.add.reduceat(np.concatenate([wB, [0.0]]), np.minimum(M.p[:-1], len(wB))) * (cnt > 0) \
+            if M.nvec else np.zeros(0)
+        self.wrow = np.bincount(M.i, weights=wA, minlength=M.vlen)
+        self.cut()
+
+    def cut(self):
+        """equal-cost contiguous ranges of vectors (jb) and of rows (ib)"""
+        cumB = np.concatenate([[0], np.cumsum(np.rint(self.wvec))]).astype(np.int64)
+        cumA = np.concatenate([[0], np.cumsum(np.rint(self.wrow))]).astype(np.int64)
+        self.jb = partition_by_flops(cumB, self.nparts)
+        self.ib = partition_by_flops(cumA, self.nparts)
+
+    def ranges(self, part: int):
+        return (int(self.jb[part]), int(self.jb[part + 1])), (int(self.ib[part]), int(self.ib[part + 1]))
+
+    def mask(self, part: int) -> Matrix:
+        """M_r: the entries of M that rank `part` computes (M's dimensions and vector list)"""
+        M = self.M
+        (jlo, jhi), (ilo, ihi) = self.ranges(part)
+        sel = (self.b_owns & (self.vpos >= jlo) & (self.vpos < jhi)) \
+            | (~self.b_owns & (M.i >= ilo) & (M.i < ihi))
+        p = np.concatenate([[0], np.cumsum(np.bincount(self.vpos[sel], minlength=M.nvec))]).astype(np.int64)
+        return Matrix(M.vlen, M.vdim, p, M.i[sel], M.x[sel], M.h, M.type)
+
+    def rebalance(self, times) -> None:
+        """times[r] = measured time of rank r's part under the current cut: the modelled cost of
+        everything rank r owns is scaled by (its time / the mean), and the ranges are cut again."""
+        t = np.asarray(times, dtype=np.float64)
+        if len(t) != self.nparts or not np.all(t > 0):
+            return
+        f = t / t.mean()
+        for r in range(self.nparts):
+            (jlo, jhi), (ilo, ihi) = self.ranges(r)
+            self.wvec[jlo:jhi] *= f[r]
+            self.wrow[ilo:ihi] *= f[r]
+        self.cut()
+
+
+def owner_aligned_mask(M: Matrix, A: Matrix, B: Matrix, nparts: int, part: int, hub_len: int = 6144):
+    """(M_r, (jlo, jhi), (ilo, ihi)) of OwnerPartition for one rank"""
+    op = OwnerPartition(M, A, B, nparts, hub_len)
+    rj, ri = op.ranges(part)
+    return op.mask(part), rj, ri
 
 
 def merge_disjoint(parts: list[Matrix]) -> Matrix:

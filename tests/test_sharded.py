@@ -215,3 +215,31 @@ def test_owner_aligned_mask_parts_are_disjoint_and_cover():
                 pos = np.searchsorted(names, j)
                 assert np.all((pos[b_owns] >= jlo) & (pos[b_owns] < jhi))
                 assert np.all((Mr.i[~b_owns] >= ilo) & (Mr.i[~b_owns] < ihi))
+
+
+def test_owner_partition_rebalance_converges():
+    """rebalance() with measured times: a cost the model does not know (one half of the index range
+    50 % dearer) is learnt from the ranks' times and the parts even out"""
+    S = gen.rmat_scipy(12, 8).tocsc().astype(np.int64)
+    import scipy.sparse as sps
+    L = gb.Matrix.from_scipy(sps.tril(S, -1).tocsc())
+    U = gb.Matrix.from_scipy(sps.triu(S, 1).tocsc())
+    W = 4
+    op = sharded.OwnerPartition(L, U, L, W)
+    true_vec = op.wvec * np.where(np.arange(L.nvec) < L.nvec // 2, 1.0, 1.5)
+    true_row = op.wrow * np.where(np.arange(L.vlen) < L.vlen // 2, 1.0, 1.5)
+
+    def times():
+        out = []
+        for r in range(W):
+            (jlo, jhi), (ilo, ihi) = op.ranges(r)
+            out.append(true_vec[jlo:jhi].sum() + true_row[ilo:ihi].sum())
+        return np.array(out)
+    t0 = times()
+    for _ in range(3):
+        op.rebalance(times())
+    t1 = times()
+    assert t1.max() / t1.mean() < t0.max() / t0.mean()
+    assert t1.max() / t1.mean() < 1.05
+    # the parts still cover the mask exactly once
+    assert sum(op.mask(r).nnz for r in range(W)) == L.nnz
