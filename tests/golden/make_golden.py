@@ -51,6 +51,25 @@ def seam_case(G, name, A, B, M, comp, sr, dot, method, exact):
     print(f"seam_{name}: nnz(T)={T.nnz} method {used} mask_applied {applied}")
 
 
+def typecast_cases(G):
+    """operands of built-in types other than the multiply operator's: the reference typecasts them
+    (GB_CAST, Source/GB.h:2925-2947), including NaN -> 0 and +-Inf -> the integer range"""
+    def operand(seed, r, c, nz, t):
+        S = gen.er(r, c, nz, seed, grbref.NP_OF[t], lo=-6, hi=7).tocsc()
+        if t in ("FP32", "FP64"):
+            S.data = (S.data * 1.37).astype(grbref.NP_OF[t])
+            S.data[::9] = np.nan
+            S.data[1::11] = np.inf
+            S.data[2::13] = -np.inf
+        return gb.Matrix.from_scipy(S, t)
+    M = gb.Matrix.from_scipy(gen.er(60, 55, 700, 113, np.int8, lo=0, hi=2).tocsc())
+    seam_case(G, "typecast_int32_fp32_to_fp64", operand(111, 60, 50, 400, "INT32"),
+              operand(112, 50, 55, 380, "FP32"), None, False, gb.Semiring("PLUS", "TIMES", "FP64"), False,
+              grbref.GxB_AxB_GUSTAVSON, True)
+    seam_case(G, "typecast_fp64_to_int16_masked_dot", operand(114, 50, 60, 400, "FP64"),
+              operand(115, 50, 55, 380, "FP64"), M, False, gb.Semiring("MIN", "PLUS", "INT16"), True, 0, True)
+
+
 def main():
     G = grbref.GraphBLAS.get(with_shim=False)
     m = lambda s, r, c, nz, dt: gb.Matrix.from_scipy(gen.er(r, c, nz, s, dt).tocsc())
@@ -76,6 +95,8 @@ def main():
     d0 = gb.Matrix(70, 1, np.array([0, 70]), np.arange(70), np.random.default_rng(1).random(70))
     seam_case(G, "min_plus_fp64_dense_vector", Aw, d0, None, False,
               gb.Semiring("MIN", "PLUS", "FP64"), True, 0, True)
+
+    typecast_cases(G)
 
     # tri_demo known answers
     for name, (ntri, line) in TRI_KNOWN.items():
