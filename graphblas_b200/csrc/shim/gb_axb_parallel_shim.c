@@ -46,6 +46,16 @@ void gb200_shim_stats (int64_t *gpu_calls, int64_t *forwarded, int64_t *declined
     if (declined) *declined = g_declined ;
 }
 
+/* GB200_SHIM_STATS=1: one line on stderr when the process ends, so that a test can see that an
+ * unmodified program (e.g. the reference's own tri_demo under LD_PRELOAD) really ran on the GPU */
+__attribute__ ((destructor))
+static void shim_report (void)
+{
+    if (getenv ("GB200_SHIM_STATS") != NULL)
+        fprintf (stderr, "[gb_b200 shim] gpu_calls=%lld forwarded=%lld declined=%lld\n",
+            (long long) g_gpu_calls, (long long) g_forwarded, (long long) g_declined) ;
+}
+
 __attribute__ ((visibility ("default")))
 void gb200_shim_last (double *device_ms, int64_t *flops)
 {
