@@ -25,6 +25,13 @@ BFS = {("1", "4", "4"): (65, 5), ("0", "5", "5", "30", "1"): (5, 3), ("1", "200"
        ("0", "10000", "10000", "100000", "0"): (10000, 5)}
 
 
+# args -> size of the maximal independent set (Demo/Output/mis_demo.out:59,94,765,827,952); the
+# program verifies the set itself ("maximal independent set status verified")
+MIS = {("1", "4", "4"): 13, ("0", "5", "5", "30", "1"): 1, ("1", "200", "200", "0"): 18430,
+       ("0", "10000", "10000", "100000", "0"): 1684}
+MIS_BIG = {("0", "100000", "100000", "10000000", "0"): 2798}
+
+
 def run(prog, args, gpu):
     exe = os.path.join(REFDIR, prog)
     if not os.path.exists(exe):
@@ -51,6 +58,13 @@ def bfs_result(out):
     lev = set(re.findall(r"max BFS level: (\d+)", out))
     assert len(reach) == 1 and len(lev) == 1, (reach, lev)     # the four BFS variants agree
     return int(reach.pop()), int(lev.pop())
+
+
+def mis_size(out):
+    assert "error" not in out and "maximal independent set status verified" in out
+    found = re.findall(r"independent set found: (\d+) of", out)
+    assert found
+    return int(found[0])
 
 
 def gpu_calls(err):
@@ -87,3 +101,19 @@ def test_bfs_demo_unmodified_binary_on_gpu(args):
     assert bfs_result(out) == BFS[args]
     calls, forwarded, declined = gpu_calls(err)
     assert calls >= 4 and forwarded == 0 and declined == 0     # one GrB_vxm per level and variant
+
+
+@pytest.mark.parametrize("args", list(MIS))
+def test_mis_demo_reference(args):
+    """Luby's algorithm: GrB_vxm over MAX_FIRST_FP64 with a candidates mask, then LOR_LAND_BOOL"""
+    out, _ = run("mis_demo", args, gpu=False)
+    assert mis_size(out) == MIS[args]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", list(MIS) + list(MIS_BIG))
+def test_mis_demo_unmodified_binary_on_gpu(args):
+    out, err = run("mis_demo", args, gpu=True)
+    assert mis_size(out) == {**MIS, **MIS_BIG}[args]
+    calls, forwarded, declined = gpu_calls(err)
+    assert calls >= 2 and forwarded == 0 and declined == 0
