@@ -1,0 +1,110 @@
+"""tools/ab_tri.py -- A/B of environment-selected variants of the masked dot (triangle counting,
+C<L>=L*U' PLUS_TIMES_INT64 on RMAT) in ONE process on one GPU: every variant must return the same T
+bit for bit as the first one (the baseline, itself parity-tested against the reference by
+tests/), and its device / semiring-kernel times are printed.  Not a bench: no JSON contract.
+
+    python tools/ab_tri.py --scale 22 --out gpurun_out/ab/ab.json
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+T1 = {"GB200_DOTG_TRIM": "1"}
+C1K = dict(T1, GB200_DOTG_CHUNK="1024")
+VARIANTS = [
+    ("trim", T1),
+    ("base", {"GB200_DOTG_TRIM": "0"}),
+    ("chunk1024", C1K),
+    ("chunk2048", dict(T1, GB200_DOTG_CHUNK="2048")),
+    ("chunk4096", dict(T1, GB200_DOTG_CHUNK="4096")),
+    ("hub256", dict(C1K, GB200_DOTG_VAR_HUB="1")),
+    ("batch8", dict(C1K, GB200_DOTG_VAR_REG="1")),
+    ("batch4", dict(C1K, GB200_DOTG_VAR_REG="2")),
+    ("batch16", dict(C1K, GB200_DOTG_VAR_REG="3")),
+    ("batch8_c256", dict(T1, GB200_DOTG_VAR_REG="1")),
+    ("batch8_c512", dict(T1, GB200_DOTG_CHUNK="512", GB200_DOTG_VAR_REG="1")),
+    ("batch8_c2048", dict(T1, GB200_DOTG_CHUNK="2048", GB200_DOTG_VAR_REG="1")),
+    ("batch4_c2048", dict(T1, GB200_DOTG_CHUNK="2048", GB200_DOTG_VAR_REG="2")),
+    ("hub256_batch8", dict(C1K, GB200_DOTG_VAR_HUB="1", GB200_DOTG_VAR_REG="1")),
+    ("hub256_batch4", dict(C1K, GB200_DOTG_VAR_HUB="1", GB200_DOTG_VAR_REG="2")),
+    ("hub256_batch8_h4096", dict(C1K, GB200_DOTG_VAR_HUB="1", GB200_DOTG_VAR_REG="1", GB200_DOTG_HUB_CHUNK="4096")),
+    ("hub256_batch4_h4096", dict(C1K, GB200_DOTG_VAR_HUB="1", GB200_DOTG_VAR_REG="2", GB200_DOTG_HUB_CHUNK="4096")),
+]
+KEYS = ("GB200_DOTG_TRIM", "GB200_DOTG_HUB_CHUNK", "GB200_DOTG_CHUNK", "GB200_DOTG_ISO",
+        "GB200_DOTG_VAR_HUB", "GB200_DOTG_VAR_REG")
+# the answer of the first measured run (profiles/r1_trim): a base that is itself wrong is noticed
+KNOWN = {22: (44374678, 2111700731)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=int, default=22)
+    ap.add_argument("--ef", type=int, default=16)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--only", default="", help="comma-separated variant names")
+    args = ap.parse_args()
+    t0 = time.time()
+    import torch
+    import bench
+    import graphblas_b200 as gb
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    g = bench.build_rmat(args.scale, args.ef, dev)
+    (n, Lp, Li, Lx), (_, Up, Ui, Ux) = bench.tri_operands(g)
+    del g
+    if dev == "cuda":
+        torch.cuda.empty_cache()
+    L = gb.Matrix(n, n, Lp, Li, Lx, None, "INT64")
+    U = gb.Matrix(n, n, Up, Ui, Ux, None, "INT64")
+    sr = gb.Semiring("PLUS", "TIMES", "INT64", flipxy=True)
+    dL, dU = gb.DMatrix(L), gb.DMatrix(U)
+    print(f"inputs ready after {time.time() - t0:.1f} s: n={n} nnz(L)={L.nnz}", flush=True)
+    report = {"scale": args.scale, "n": n, "nnz_L": L.nnz, "variants": []}
+    ref = None
+    only = [v for v in args.only.split(",") if v]
+    for name, env in VARIANTS:
+        if only and name not in only:
+            continue
+        for k in KEYS:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        row = {"name": name, "env": env}
+        try:
+            ms, kms = [], []
+            for _ in range(args.reps):
+                info = gb.axb_device(dL, False, dU, dL, sr, True, fetch=False).info
+                ms.append(info["device_ms"])
+                kms.append(info["kernel_ms"])
+            res = gb.axb_device(dL, False, dU, dL, sr, True, fetch=True)
+            T = res.matrix
+            row.update(device_ms=ms, kernel_ms=kms, best_ms=min(ms), nnz_T=T.nnz,
+                       madds=res.info["flops"], ntri=int(T.x.sum()))
+            if args.scale in KNOWN and args.ef == 16:
+                row["known_answer"] = bool((T.nnz, int(T.x.sum())) == KNOWN[args.scale])
+            if ref is None:
+                ref = T
+                row["same_as_base"] = True
+            else:
+                row["same_as_base"] = bool(np.array_equal(ref.p, T.p) and np.array_equal(ref.i, T.i)
+                                           and np.array_equal(ref.x, T.x))
+        except Exception as e:      # a variant that fails must not hide the others
+            row["error"] = repr(e)
+        report["variants"].append(row)
+        print(json.dumps(row), flush=True)
+        if args.out:
+            os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+            with open(args.out, "w") as f:
+                json.dump(report, f, indent=1)
+    print(f"total {time.time() - t0:.1f} s")
+
+
+if __name__ == "__main__":
+    main()
