@@ -86,7 +86,9 @@ __global__ void dot_cnt_rect_kernel (const int64_t *__restrict__ pos, int64_t an
         t += (int64_t) gridDim.x * blockDim.x) cnt [t] = pos [(t + 1) * anvec] - pos [t * anvec] ;
 }
 
-constexpr int64_t DOTG_CHUNK = 256 ;        // tasks per work item of dotg_kernel (regular owners)
+// tasks per work item of dotg_kernel (regular owners): every item of an owner builds the owner's table
+// again, so items are large (measured, tri scale 22: 128: 46.5, 256: 43.8, 512: 42.8, 1024: 42.4 ms)
+constexpr int64_t DOTG_CHUNK = 1024 ;
 
 // Both lists are sorted, so a match can only lie between the owner's first and last index: the walked
 // list is trimmed to that range before it becomes a task (two binary searches per pair).  For
@@ -352,8 +354,6 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             // 0: walk the whole list of every pair (for A/B measurements)
             const char *trim_env = getenv ("GB200_DOTG_TRIM") ;
             const int trim = (trim_env != nullptr && atoi (trim_env) == 0) ? 0 : 1 ;
-            const int var_hub = (getenv ("GB200_DOTG_VAR_HUB") != nullptr) ? atoi (getenv ("GB200_DOTG_VAR_HUB")) : 0 ;
-            const int var_reg = (getenv ("GB200_DOTG_VAR_REG") != nullptr) ? atoi (getenv ("GB200_DOTG_VAR_REG")) : 0 ;
             DevBuf own, small, wl, ws, cntA, offA, curA, pos0, poss, off0, plist, slist ;
             GB200_TRY (own.alloc (mnz)) ;
             GB200_TRY (small.alloc (mnz)) ;
@@ -463,11 +463,8 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                     count_launch () ;
                     GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 16, c.stream)) ;
                     ga.items = items.as<DotItem> () ; ga.nitems = nitems ;
-                    int fam = hub ? (iso ? FAM_DOTG_HUB_ISO : FAM_DOTG_HUB)
-                                  : (iso ? FAM_DOTG_ISO : FAM_DOTG) ;
-                    if (fam == FAM_DOTG_HUB_ISO && var_hub) fam = FAM_DOTG_HUB_ISO_V1 ;
-                    if (fam == FAM_DOTG_ISO && var_reg)
-                        fam = (var_reg == 1) ? FAM_DOTG_ISO_V1 : ((var_reg == 2) ? FAM_DOTG_ISO_V2 : FAM_DOTG_ISO_V3) ;
+                    const int fam = hub ? (iso ? FAM_DOTG_HUB_ISO : FAM_DOTG_HUB)
+                                        : (iso ? FAM_DOTG_ISO : FAM_DOTG) ;
                     if (!launch_typed (s.xy_code, fam, s.z_code, s.add_opcode, s.mult_opcode, &ga,
                         grid_cap (nitems, (iso && !hub) ? 3 : 2), DOTG_THREADS))
                     { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }

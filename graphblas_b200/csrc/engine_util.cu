@@ -751,9 +751,9 @@ static gb200_status upload_any (gb200_dmatrix *out, const gb200_matrix *host, in
                 GB200_CUDA (cudaMemcpyAsync (d->h.ptr, host->h, nvec * sizeof (int64_t),
                     cudaMemcpyDefault, c.stream)) ;
         }
-        // 16 bytes of slack: the masked dot kernel reads indices in aligned 16-byte chunks
-        GB200_TRY (d->i.alloc (((nnz > 0 ? nnz : 1) + 4) * sizeof (int32_t))) ;
-        GB200_CUDA (cudaMemsetAsync (d->i.as<int32_t> () + (nnz > 0 ? nnz : 1), 0, 4 * sizeof (int32_t), c.stream)) ;
+        // 32 bytes of slack: the masked dot kernel reads indices in aligned 16- or 32-byte chunks
+        GB200_TRY (d->i.alloc (((nnz > 0 ? nnz : 1) + 8) * sizeof (int32_t))) ;
+        GB200_CUDA (cudaMemsetAsync (d->i.as<int32_t> () + (nnz > 0 ? nnz : 1), 0, 8 * sizeof (int32_t), c.stream)) ;
         GB200_TRY (d->x.alloc ((nnz > 0 ? nnz : 1) * (size_t) tsz)) ;
         if (nnz > 0)
         {

@@ -426,8 +426,9 @@ template <class S, bool ISO, class slot_t, bool LD256>
 __device__ __forceinline__ void dotg_lanes (const S &sr, const DotGSeg<S> &g, const slot_t *tab,
     int *s_next, uint16_t *s_cur, unsigned long long &nm)
 {
-    // LD256: a chunk is one 32-byte load (LDG.256, sm_100) instead of two 16-byte ones -- every lane
-    // reads its own list, so a load costs one L1 wavefront per lane whatever its width
+    // LD256: a chunk is one 32-byte load (LDG.E.ENL2.256, sm_100) instead of two 16-byte ones -- every
+    // lane reads its own list, so a load costs one L1 wavefront per lane whatever its width (measured
+    // on the pattern-only kernel, tri scale 22: 41.7 -> 40.5 ms; the valued kernel keeps 16-byte loads)
     constexpr int AL = LD256 ? 7 : 3 ;
     using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
     constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
@@ -636,82 +637,8 @@ __device__ __forceinline__ void dotg_walk (const S &sr, const DotGSeg<S> &g, con
     }
 }
 
-// Regular items, pattern-only operands, tasks claimed DOTG_BATCH at a time: one shared atomic and one
-// coalesced load of the descriptors per batch, the fields of a task broadcast by shuffles, the count
-// of task t kept by lane t and the results written by the first lanes after the batch.  (After the
-// walks are trimmed a task is ~140 indices long, and claiming, fetching and finishing tasks one at a
-// time was ~40 % of the instructions of the kernel.)
-template <class S, class slot_t, int DOTG_BATCH>
-__device__ __forceinline__ void dotg_walk_batch (const S &sr, const DotGSeg<S> &g, const slot_t *tab,
-    int *s_next, unsigned long long &nm)
-{
-    using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
-    constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
-    const int lane = threadIdx.x & 31 ;
-    const int sh = g.sh ;
-    const uint32_t c1 = g.c1, c2 = g.c2 ;
-    const slot_t *__restrict__ tab2 = tab + g.NS ;
-    int base = 0 ;
-    if (lane == 0) base = atomicAdd (s_next, DOTG_BATCH) ;
-    base = __shfl_sync (0xffffffffu, base, 0) ;
-    DotTask mine ;
-    mine.e = 0 ; mine.len = 0 ; mine.w0 = 0 ;
-    if (lane < DOTG_BATCH && base + lane < g.ntask) mine = g.tasks [base + lane] ;
-    while (base < g.ntask)
-    {
-        // claim the next batch and fetch its descriptors before working on this one
-        int nbase = 0 ;
-        if (lane == 0) nbase = atomicAdd (s_next, DOTG_BATCH) ;
-        nbase = __shfl_sync (0xffffffffu, nbase, 0) ;
-        DotTask next ;
-        next.e = 0 ; next.len = 0 ; next.w0 = 0 ;
-        if (lane < DOTG_BATCH && nbase + lane < g.ntask) next = g.tasks [nbase + lane] ;
-
-        const int nb = (g.ntask - base < DOTG_BATCH) ? (g.ntask - base) : DOTG_BATCH ;
-        uint32_t mycnt = 0 ;
-        for (int t = 0 ; t < nb ; t++)
-        {
-            const int rawlen = __shfl_sync (0xffffffffu, mine.len, t) ;
-            const int64_t w0 = __shfl_sync (0xffffffffu, mine.w0, t) ;
-            const int len = (rawlen < 0) ? -rawlen : rawlen ;
-            const int32_t *__restrict__ wp = g.Wi + w0 ;
-            uint32_t cnt = 0 ;
-            for (int p0 = 0 ; p0 < len ; p0 += 32 * DOTG_U)
-            {
-                uint32_t k [DOTG_U] ;
-                #pragma unroll
-                for (int u = 0 ; u < DOTG_U ; u++)
-                {
-                    const int p = p0 + 32 * u + lane ;
-                    k [u] = (p < len) ? (uint32_t) __ldg (wp + p) : NOKEY ;
-                }
-                #pragma unroll
-                for (int u = 0 ; u < DOTG_U ; u++)
-                {
-                    if (u > 0 && p0 + 32 * u >= len) continue ;     // warp-uniform
-                    uint32_t pos = 0 ;
-                    if (dotg_probe<true, false, slot_t> (tab, tab2, k [u], sh, c1, c2, pos)) cnt++ ;
-                }
-            }
-            cnt = __reduce_add_sync (0xffffffffu, cnt) ;
-            if (lane == t) mycnt = cnt ;
-        }
-        if (mycnt != 0)                 // only lanes < nb can hold a count
-        {
-            const acc_t cij = iso_fold<Mon> (g.ciso, mycnt) ;
-            if (mine.len < 0) Mon::atomic_combine (g.vals + mine.e, cij) ;
-            else g.vals [mine.e] = cij ;
-            g.flags [mine.e] = 1 ;
-            nm += mycnt ;
-        }
-        base = nbase ; mine = next ;
-    }
-}
-
 // HUB = false: items whose owner fits one table load (or is dense); HUB = true: items of longer owners
-// VAR > 0 (pattern-only operands only): the hub kernel reads its chunks with 32-byte loads (VAR = 1),
-// the regular kernel claims its tasks in batches of 8, 4, 16 (VAR = 1, 2, 3)
-template <class S, bool ISO, bool HUB, int VAR = 0>
+template <class S, bool ISO, bool HUB>
 __global__ void __launch_bounds__ (DOTG_THREADS, (ISO && !HUB) ? 3 : 2)
 dotg_kernel (DotGArgs a)
 {
@@ -809,13 +736,11 @@ dotg_kernel (DotGArgs a)
             if constexpr (HUB)
             {
                 if (dense) dotg_walk<S, ISO, true, slot_t> (sr, g, tab, &s_next, nm) ;
-                else dotg_lanes<S, ISO, slot_t, VAR == 1> (sr, g, tab, &s_next, s_cur, nm) ;
+                else dotg_lanes<S, ISO, slot_t, ISO> (sr, g, tab, &s_next, s_cur, nm) ;
             }
             else
             {
                 if (dense) dotg_walk<S, ISO, true, slot_t> (sr, g, tab, &s_next, nm) ;
-                else if constexpr (ISO && VAR > 0)
-                    dotg_walk_batch<S, slot_t, (VAR == 1) ? 8 : ((VAR == 2) ? 4 : 16)> (sr, g, tab, &s_next, nm) ;
                 else dotg_walk<S, ISO, false, slot_t> (sr, g, tab, &s_next, nm) ;
             }
         }
@@ -829,8 +754,7 @@ dotg_kernel (DotGArgs a)
 // ---------------------------------------------------------------------------------------------
 enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_DOTV = 4,
     FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9,
-    FAM_DOTG_ISO = 10, FAM_SPMV_OCC8 = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13,
-    FAM_DOTG_ISO_V1 = 14, FAM_DOTG_HUB_ISO_V1 = 15, FAM_DOTG_ISO_V2 = 16, FAM_DOTG_ISO_V3 = 17 } ;
+    FAM_DOTG_ISO = 10, FAM_SPMV_OCC8 = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -846,8 +770,7 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
     else if (family == FAM_SAXPY_HEAVY)
         saxpy_heavy_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyArgs *) args) ;
     else if (family == FAM_DOTG || family == FAM_DOTG_ISO || family == FAM_DOTG_HUB
-        || family == FAM_DOTG_HUB_ISO || family == FAM_DOTG_ISO_V1 || family == FAM_DOTG_HUB_ISO_V1
-        || family == FAM_DOTG_ISO_V2 || family == FAM_DOTG_ISO_V3)
+        || family == FAM_DOTG_HUB_ISO)
     {
         static bool attr_set = false ;          // one flag per instantiation
         if (!attr_set)
@@ -856,10 +779,6 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
             cudaFuncSetAttribute (dotg_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
             cudaFuncSetAttribute (dotg_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
             cudaFuncSetAttribute (dotg_kernel<S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
-            cudaFuncSetAttribute (dotg_kernel<S, true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
-            cudaFuncSetAttribute (dotg_kernel<S, true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
-            cudaFuncSetAttribute (dotg_kernel<S, true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
-            cudaFuncSetAttribute (dotg_kernel<S, true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
             attr_set = true ;
         }
         const DotGArgs &ga = *(const DotGArgs *) args ;
@@ -869,14 +788,6 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
             dotg_kernel<S, false, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
         else if (family == FAM_DOTG_HUB_ISO)
             dotg_kernel<S, true, true> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
-        else if (family == FAM_DOTG_ISO_V1)
-            dotg_kernel<S, true, false, 1> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
-        else if (family == FAM_DOTG_HUB_ISO_V1)
-            dotg_kernel<S, true, true, 1> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
-        else if (family == FAM_DOTG_ISO_V2)
-            dotg_kernel<S, true, false, 2> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
-        else if (family == FAM_DOTG_ISO_V3)
-            dotg_kernel<S, true, false, 3> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
         else
             dotg_kernel<S, false, true> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
     }

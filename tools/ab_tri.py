@@ -17,29 +17,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-T1 = {"GB200_DOTG_TRIM": "1"}
-C1K = dict(T1, GB200_DOTG_CHUNK="1024")
 VARIANTS = [
-    ("trim", T1),
-    ("base", {"GB200_DOTG_TRIM": "0"}),
-    ("chunk1024", C1K),
-    ("chunk2048", dict(T1, GB200_DOTG_CHUNK="2048")),
-    ("chunk4096", dict(T1, GB200_DOTG_CHUNK="4096")),
-    ("hub256", dict(C1K, GB200_DOTG_VAR_HUB="1")),
-    ("batch8", dict(C1K, GB200_DOTG_VAR_REG="1")),
-    ("batch4", dict(C1K, GB200_DOTG_VAR_REG="2")),
-    ("batch16", dict(C1K, GB200_DOTG_VAR_REG="3")),
-    ("batch8_c256", dict(T1, GB200_DOTG_VAR_REG="1")),
-    ("batch8_c512", dict(T1, GB200_DOTG_CHUNK="512", GB200_DOTG_VAR_REG="1")),
-    ("batch8_c2048", dict(T1, GB200_DOTG_CHUNK="2048", GB200_DOTG_VAR_REG="1")),
-    ("batch4_c2048", dict(T1, GB200_DOTG_CHUNK="2048", GB200_DOTG_VAR_REG="2")),
-    ("hub256_batch8", dict(C1K, GB200_DOTG_VAR_HUB="1", GB200_DOTG_VAR_REG="1")),
-    ("hub256_batch4", dict(C1K, GB200_DOTG_VAR_HUB="1", GB200_DOTG_VAR_REG="2")),
-    ("hub256_batch8_h4096", dict(C1K, GB200_DOTG_VAR_HUB="1", GB200_DOTG_VAR_REG="1", GB200_DOTG_HUB_CHUNK="4096")),
-    ("hub256_batch4_h4096", dict(C1K, GB200_DOTG_VAR_HUB="1", GB200_DOTG_VAR_REG="2", GB200_DOTG_HUB_CHUNK="4096")),
+    ("default", {}),
+    ("notrim", {"GB200_DOTG_TRIM": "0"}),
+    ("chunk256", {"GB200_DOTG_CHUNK": "256"}),
+    ("chunk512", {"GB200_DOTG_CHUNK": "512"}),
+    ("chunk2048", {"GB200_DOTG_CHUNK": "2048"}),
+    ("hub2048", {"GB200_DOTG_HUB_CHUNK": "2048"}),
+    ("hub4096", {"GB200_DOTG_HUB_CHUNK": "4096"}),
+    ("hub8192", {"GB200_DOTG_HUB_CHUNK": "8192"}),
+    ("hub16384", {"GB200_DOTG_HUB_CHUNK": "16384"}),
+    ("valued", {"GB200_DOTG_ISO": "0"}),
+    ("valued_notrim", {"GB200_DOTG_ISO": "0", "GB200_DOTG_TRIM": "0"}),
 ]
-KEYS = ("GB200_DOTG_TRIM", "GB200_DOTG_HUB_CHUNK", "GB200_DOTG_CHUNK", "GB200_DOTG_ISO",
-        "GB200_DOTG_VAR_HUB", "GB200_DOTG_VAR_REG")
+KEYS = ("GB200_DOTG_TRIM", "GB200_DOTG_HUB_CHUNK", "GB200_DOTG_CHUNK", "GB200_DOTG_ISO")
 # the answer of the first measured run (profiles/r1_trim): a base that is itself wrong is noticed
 KNOWN = {22: (44374678, 2111700731)}
 
