@@ -795,11 +795,13 @@ def main():
     peak, peak_src = measured_peak()
     k_ms = float(np.mean(ker_ms))
     achieved = ab / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    traffic = None
+    traffic = traffic_note = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             key = args.workload + ("_pull" if args.workload == "bfs" and w["do_adotb"] else "")
-            traffic = json.load(f).get(f"{key}_s{args.scale}")
+            tj = json.load(f)
+            traffic = tj.get(f"{key}_s{args.scale}")
+            traffic_note = tj.get(f"{key}_s{args.scale}_note")
     except Exception:
         pass
 
@@ -839,6 +841,7 @@ def main():
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
+                             **({"traffic_note": traffic_note} if traffic_note else {}),
                              "kernel": w.get("kernel", "dotg_kernel/dot_kernel" if w["do_adotb"]
                                              else "saxpy_*_kernel"),
                              "kernel_ms": k_ms, "algorithmic_bytes": int(ab), "peak_source": peak_src,

@@ -289,7 +289,8 @@ __global__ void dot_kernel (DotArgs a)
 // masked dot products, C<M> = A'*B, grouped by the LONGER vector of each pair ("owner").
 //
 // For a mask entry (i,j) the shorter of A(:,i), B(:,j) is walked and the longer one is probed.  On a
-// power-law graph the walked lengths sum to ~8.6x the number of matches, so a probe must cost a
+// power-law graph the walked lengths sum to ~8.6x the number of matches (~5x once the walks are trimmed
+// to the owner's index range, engine_dot.cu), so a probe must cost a
 // handful of instructions and never leave the SM: pairs are grouped by their owner vector, a thread
 // block loads the owner into a shared-memory CUCKOO table (two tables, two hash functions, total
 // load <= 3/8) once and then serves every task of its work item from it.  A cuckoo lookup is
