@@ -84,5 +84,7 @@ open(os.path.join(dst, "README.md"), "w").write("\n".join(md) + "\n")
 tj = os.path.join(ROOT, "profiles", "traffic.json")
 old = json.load(open(tj)) if os.path.exists(tj) else {}
 old.update(traffic)
+for k in traffic:                                  # a fresh capture supersedes a "not captured" note
+    old.pop(k + "_note", None)
 json.dump(old, open(tj, "w"), indent=1)
 print("\n".join(md)[:3000])
