@@ -417,6 +417,18 @@ __device__ __forceinline__ bool dotg_probe (const slot_t *__restrict__ tab, cons
     }
 }
 
+// eight consecutive 32-bit indices with ONE 32-byte load (LDG.E.ENL2.256 on sm_100); p is 32-byte aligned
+__device__ __forceinline__ void ldg256 (const int32_t *p, int32_t (&k) [8])
+{
+#ifdef GB200_HOST_EMULATION             // tools/emu_kernels.py runs this source on the host
+    for (int c = 0 ; c < 8 ; c++) k [c] = p [c] ;
+#else
+    asm volatile ("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r" (k [0]), "=r" (k [1]), "=r" (k [2]), "=r" (k [3]), "=r" (k [4]),
+          "=r" (k [5]), "=r" (k [6]), "=r" (k [7]) : "l" (p)) ;
+#endif
+}
+
 // HUB items (owner longer than one table load): every LANE pulls tasks from the shared counter and
 // walks, by itself, the part of its task that falls into the current segment -- eight indices (two
 // 16-byte loads) per step, the cursor of every task kept in shared memory between segments.  There
@@ -471,12 +483,7 @@ __device__ __forceinline__ void dotg_lanes (const S &sr, const DotGSeg<S> &g, co
         if (t >= 0)
         {
             int32_t kk [8] ;
-            if constexpr (LD256)
-            {
-                asm volatile ("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                    : "=r" (kk [0]), "=r" (kk [1]), "=r" (kk [2]), "=r" (kk [3]), "=r" (kk [4]),
-                      "=r" (kk [5]), "=r" (kk [6]), "=r" (kk [7]) : "l" (wp + q)) ;
-            }
+            if constexpr (LD256) ldg256 (wp + q, kk) ;
             else
             {
                 const int4 ka = __ldg ((const int4 *) (wp + q)) ;

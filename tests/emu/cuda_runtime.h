@@ -1,0 +1,176 @@
+// tests/emu/cuda_runtime.h -- a HOST stand-in for the CUDA device environment, for tests only.
+//
+// tests/test_kernel_emulation.py compiles the kernel SOURCES of graphblas_b200/csrc (kernels.cuh and the
+// headers it includes) with g++ and this directory first on the include path, so that
+// `#include <cuda_runtime.h>` lands here.  One CUDA thread is one OS thread:
+//   * a block is launched as blockDim.x std::threads; blocks of a grid run one after another;
+//   * threadIdx is thread_local, blockIdx / blockDim / gridDim are set per block;
+//   * __syncthreads is a barrier over the block; warp intrinsics (__shfl*_sync, __ballot_sync,
+//     __any_sync, __reduce_add_sync) are a barrier over the 32 threads of a warp plus an exchange buffer
+//     -- every use in the kernels has all 32 lanes converged on the call with the full mask;
+//   * __shared__ variables are function-local statics (one block at a time, so one copy is right);
+//     the one `extern __shared__` array is rewritten by the test driver to point at emu::dyn_smem;
+//   * atomics are the GCC __atomic builtins; __ldg / __ldcs are plain loads.
+// Nothing here is shipped or linked into the product.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <thread>
+#include <vector>
+#include <barrier>
+#include <memory>
+#include <functional>
+
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline __attribute__ ((always_inline))
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __align__(n) alignas (n)
+#define GB200_HOST_EMULATION 1
+
+struct uint3 { unsigned x, y, z ; } ;
+struct dim3 { unsigned x = 1, y = 1, z = 1 ; } ;
+struct int4 { int x, y, z, w ; } ;
+static inline int4 make_int4 (int x, int y, int z, int w) { int4 r = { x, y, z, w } ; return r ; }
+typedef void *cudaStream_t ;
+
+namespace emu {
+struct Warp
+{
+    std::barrier<> bar { 32 } ;
+    uint64_t slot [32] ;
+} ;
+struct Block
+{
+    std::unique_ptr<std::barrier<>> bar ;
+    std::vector<std::unique_ptr<Warp>> warps ;
+} ;
+inline Block *g_block = nullptr ;
+inline thread_local Warp *t_warp = nullptr ;
+inline thread_local int t_lane = 0 ;
+alignas (128) inline unsigned char dyn_smem [232448] ;          // 227 KB
+
+template <class T> static inline uint64_t bits (T v) { uint64_t b = 0 ; memcpy (&b, &v, sizeof (T)) ; return b ; }
+template <class T> static inline T unbits (uint64_t b) { T v ; memcpy (&v, &b, sizeof (T)) ; return v ; }
+// every lane publishes a word, then reads the word of lane `src`
+static inline uint64_t exchange (uint64_t mine, int src)
+{
+    t_warp->slot [t_lane] = mine ;
+    t_warp->bar.arrive_and_wait () ;
+    const uint64_t r = t_warp->slot [src & 31] ;
+    t_warp->bar.arrive_and_wait () ;
+    return r ;
+}
+} // namespace emu
+
+inline thread_local uint3 threadIdx = { 0, 0, 0 } ;
+inline uint3 blockIdx = { 0, 0, 0 } ;
+inline dim3 blockDim, gridDim ;
+
+static inline void __syncthreads () { emu::g_block->bar->arrive_and_wait () ; }
+static inline void __syncwarp (unsigned = 0xffffffffu) { emu::t_warp->bar.arrive_and_wait () ; }
+static inline void __threadfence () { __atomic_thread_fence (__ATOMIC_SEQ_CST) ; }
+static inline void __trap () { fprintf (stderr, "emu: __trap()\n") ; abort () ; }
+static inline int __popc (unsigned v) { return __builtin_popcount (v) ; }
+static inline int __ffs (unsigned v) { return __builtin_ffs ((int) v) ; }
+template <class T> static inline T __ldg (const T *p) { return *p ; }
+template <class T> static inline T __ldcs (const T *p) { return *p ; }
+
+template <class T> static inline T __shfl_sync (unsigned, T v, int src, int width = 32)
+{
+    const int base = emu::t_lane & ~(width - 1) ;
+    return emu::unbits<T> (emu::exchange (emu::bits (v), base + (src & (width - 1)))) ;
+}
+template <class T> static inline T __shfl_down_sync (unsigned, T v, unsigned off, int width = 32)
+{
+    const int pos = emu::t_lane & (width - 1) ;
+    const int src = (pos + (int) off < width) ? (emu::t_lane + (int) off) : emu::t_lane ;
+    return emu::unbits<T> (emu::exchange (emu::bits (v), src)) ;
+}
+template <class T> static inline T __shfl_up_sync (unsigned, T v, unsigned off, int width = 32)
+{
+    const int pos = emu::t_lane & (width - 1) ;
+    const int src = (pos - (int) off >= 0) ? (emu::t_lane - (int) off) : emu::t_lane ;
+    return emu::unbits<T> (emu::exchange (emu::bits (v), src)) ;
+}
+static inline unsigned __ballot_sync (unsigned, int pred)
+{
+    emu::t_warp->slot [emu::t_lane] = pred ? 1 : 0 ;
+    emu::t_warp->bar.arrive_and_wait () ;
+    unsigned m = 0 ;
+    for (int l = 0 ; l < 32 ; l++) if (emu::t_warp->slot [l]) m |= (1u << l) ;
+    emu::t_warp->bar.arrive_and_wait () ;
+    return m ;
+}
+static inline int __any_sync (unsigned mask, int pred) { return __ballot_sync (mask, pred) != 0 ; }
+static inline int __all_sync (unsigned mask, int pred) { return __ballot_sync (mask, pred) == 0xffffffffu ; }
+static inline unsigned __reduce_add_sync (unsigned, unsigned v)
+{
+    emu::t_warp->slot [emu::t_lane] = v ;
+    emu::t_warp->bar.arrive_and_wait () ;
+    unsigned s = 0 ;
+    for (int l = 0 ; l < 32 ; l++) s += (unsigned) emu::t_warp->slot [l] ;
+    emu::t_warp->bar.arrive_and_wait () ;
+    return s ;
+}
+
+// ---- atomics ----------------------------------------------------------------------------------
+#define EMU_ATOMIC_INT(T) \
+static inline T atomicAdd (T *p, T v) { return __atomic_fetch_add (p, v, __ATOMIC_RELAXED) ; } \
+static inline T atomicExch (T *p, T v) { return __atomic_exchange_n (p, v, __ATOMIC_RELAXED) ; } \
+static inline T atomicOr (T *p, T v) { return __atomic_fetch_or (p, v, __ATOMIC_RELAXED) ; } \
+static inline T atomicAnd (T *p, T v) { return __atomic_fetch_and (p, v, __ATOMIC_RELAXED) ; } \
+static inline T atomicXor (T *p, T v) { return __atomic_fetch_xor (p, v, __ATOMIC_RELAXED) ; } \
+static inline T atomicCAS (T *p, T expect, T v) \
+{ __atomic_compare_exchange_n (p, &expect, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED) ; return expect ; } \
+static inline T atomicMin (T *p, T v) \
+{ T old = __atomic_load_n (p, __ATOMIC_RELAXED) ; \
+  while (v < old && !__atomic_compare_exchange_n (p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return old ; } \
+static inline T atomicMax (T *p, T v) \
+{ T old = __atomic_load_n (p, __ATOMIC_RELAXED) ; \
+  while (v > old && !__atomic_compare_exchange_n (p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { } return old ; }
+EMU_ATOMIC_INT (int)
+EMU_ATOMIC_INT (unsigned int)
+EMU_ATOMIC_INT (unsigned long long)
+EMU_ATOMIC_INT (long long)
+#undef EMU_ATOMIC_INT
+#define EMU_ATOMIC_FP(T, U) \
+static inline T atomicAdd (T *p, T v) \
+{ U old = __atomic_load_n ((U *) p, __ATOMIC_RELAXED) ; \
+  while (true) { T o ; memcpy (&o, &old, sizeof (T)) ; T n = o + v ; U nb ; memcpy (&nb, &n, sizeof (T)) ; \
+    if (__atomic_compare_exchange_n ((U *) p, &old, nb, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return o ; } }
+EMU_ATOMIC_FP (float, unsigned int)
+EMU_ATOMIC_FP (double, unsigned long long)
+#undef EMU_ATOMIC_FP
+
+// ---- launching ----------------------------------------------------------------------------------
+namespace emu {
+// run `body` (a call of one __global__ function) as a grid of `grid` blocks of `block` threads
+static inline void launch (unsigned grid, unsigned block, const std::function<void ()> &body)
+{
+    if (block % 32 != 0) { fprintf (stderr, "emu: block size must be a multiple of 32\n") ; abort () ; }
+    gridDim.x = grid ; blockDim.x = block ;
+    for (unsigned b = 0 ; b < grid ; b++)
+    {
+        Block blk ;
+        blk.bar.reset (new std::barrier<> (block)) ;
+        for (unsigned w = 0 ; w < block / 32 ; w++) blk.warps.emplace_back (new Warp ()) ;
+        g_block = &blk ;
+        blockIdx.x = b ;
+        std::vector<std::thread> th ;
+        for (unsigned t = 0 ; t < block ; t++)
+            th.emplace_back ([t, &blk, &body] ()
+            {
+                threadIdx.x = t ; t_lane = (int) (t & 31) ; t_warp = blk.warps [t >> 5].get () ;
+                body () ;
+            }) ;
+        for (auto &x : th) x.join () ;
+        g_block = nullptr ;
+    }
+}
+} // namespace emu
