@@ -6,8 +6,8 @@
 //   * a block is launched as blockDim.x std::threads; blocks of a grid run one after another;
 //   * threadIdx is thread_local, blockIdx / blockDim / gridDim are set per block;
 //   * __syncthreads is a barrier over the block; warp intrinsics (__shfl*_sync, __ballot_sync,
-//     __any_sync, __reduce_add_sync) are a barrier over the 32 threads of a warp plus an exchange buffer
-//     -- every use in the kernels has all 32 lanes converged on the call with the full mask;
+//     __any_sync, __reduce_add_sync) are a rendezvous of the lanes named by the mask (the full warp, or
+//     an aligned lane group) plus an exchange buffer;
 //   * __shared__ variables are function-local statics (one block at a time, so one copy is right);
 //     the one `extern __shared__` array is rewritten by the test driver to point at emu::dyn_smem;
 //   * atomics are the GCC __atomic builtins; __ldg / __ldcs are plain loads.
@@ -21,6 +21,7 @@
 #include <thread>
 #include <vector>
 #include <barrier>
+#include <atomic>
 #include <memory>
 #include <functional>
 
@@ -40,9 +41,13 @@ static inline int4 make_int4 (int x, int y, int z, int w) { int4 r = { x, y, z, 
 typedef void *cudaStream_t ;
 
 namespace emu {
+// A rendezvous of the lanes named by `mask` (the full warp, or an aligned group of lanes as dotv_kernel and
+// dot_kernel use): a counting barrier per (lowest lane, size) of the mask -- lanes that left a loop early may
+// wait on the full mask while a lane group of the same warp still meets on its own mask; waiting lanes yield.
+struct Group { std::atomic<int> count { 0 } ; std::atomic<int> gen { 0 } ; } ;
 struct Warp
 {
-    std::barrier<> bar { 32 } ;
+    Group grp [32][33] ;
     uint64_t slot [32] ;
 } ;
 struct Block
@@ -55,15 +60,29 @@ inline thread_local Warp *t_warp = nullptr ;
 inline thread_local int t_lane = 0 ;
 alignas (128) inline unsigned char dyn_smem [232448] ;          // 227 KB
 
+static inline void group_sync (unsigned mask)
+{
+    const int leader = __builtin_ffs ((int) mask) - 1, n = __builtin_popcount (mask) ;
+    if (!((mask >> t_lane) & 1u)) { fprintf (stderr, "emu: lane %d is not in the mask %08x it syncs on\n", t_lane, mask) ; abort () ; }
+    Group &g = t_warp->grp [leader][n] ;
+    const int gen = g.gen.load (std::memory_order_acquire) ;
+    if (g.count.fetch_add (1, std::memory_order_acq_rel) + 1 == n)
+    {
+        g.count.store (0, std::memory_order_relaxed) ;
+        g.gen.fetch_add (1, std::memory_order_release) ;
+    }
+    else while (g.gen.load (std::memory_order_acquire) == gen) std::this_thread::yield () ;
+}
+
 template <class T> static inline uint64_t bits (T v) { uint64_t b = 0 ; memcpy (&b, &v, sizeof (T)) ; return b ; }
 template <class T> static inline T unbits (uint64_t b) { T v ; memcpy (&v, &b, sizeof (T)) ; return v ; }
-// every lane publishes a word, then reads the word of lane `src`
-static inline uint64_t exchange (uint64_t mine, int src)
+// every lane of the mask publishes a word, then reads the word of lane `src`
+static inline uint64_t exchange (unsigned mask, uint64_t mine, int src)
 {
     t_warp->slot [t_lane] = mine ;
-    t_warp->bar.arrive_and_wait () ;
+    group_sync (mask) ;
     const uint64_t r = t_warp->slot [src & 31] ;
-    t_warp->bar.arrive_and_wait () ;
+    group_sync (mask) ;
     return r ;
 }
 } // namespace emu
@@ -73,7 +92,7 @@ inline uint3 blockIdx = { 0, 0, 0 } ;
 inline dim3 blockDim, gridDim ;
 
 static inline void __syncthreads () { emu::g_block->bar->arrive_and_wait () ; }
-static inline void __syncwarp (unsigned = 0xffffffffu) { emu::t_warp->bar.arrive_and_wait () ; }
+static inline void __syncwarp (unsigned mask = 0xffffffffu) { emu::group_sync (mask) ; }
 static inline void __threadfence () { __atomic_thread_fence (__ATOMIC_SEQ_CST) ; }
 static inline void __trap () { fprintf (stderr, "emu: __trap()\n") ; abort () ; }
 static inline int __popc (unsigned v) { return __builtin_popcount (v) ; }
@@ -81,41 +100,45 @@ static inline int __ffs (unsigned v) { return __builtin_ffs ((int) v) ; }
 template <class T> static inline T __ldg (const T *p) { return *p ; }
 template <class T> static inline T __ldcs (const T *p) { return *p ; }
 
-template <class T> static inline T __shfl_sync (unsigned, T v, int src, int width = 32)
+template <class T> static inline T __shfl_sync (unsigned mask, T v, int src, int width = 32)
 {
     const int base = emu::t_lane & ~(width - 1) ;
-    return emu::unbits<T> (emu::exchange (emu::bits (v), base + (src & (width - 1)))) ;
+    return emu::unbits<T> (emu::exchange (mask, emu::bits (v), base + (src & (width - 1)))) ;
 }
-template <class T> static inline T __shfl_down_sync (unsigned, T v, unsigned off, int width = 32)
+// a source lane outside the mask (possible only at the edge of a group) gives the caller's own value,
+// which is what the kernels rely on: they guard the use with `gl + off < G`
+template <class T> static inline T __shfl_down_sync (unsigned mask, T v, unsigned off, int width = 32)
 {
     const int pos = emu::t_lane & (width - 1) ;
-    const int src = (pos + (int) off < width) ? (emu::t_lane + (int) off) : emu::t_lane ;
-    return emu::unbits<T> (emu::exchange (emu::bits (v), src)) ;
+    int src = (pos + (int) off < width) ? (emu::t_lane + (int) off) : emu::t_lane ;
+    if (!((mask >> src) & 1u)) src = emu::t_lane ;
+    return emu::unbits<T> (emu::exchange (mask, emu::bits (v), src)) ;
 }
-template <class T> static inline T __shfl_up_sync (unsigned, T v, unsigned off, int width = 32)
+template <class T> static inline T __shfl_up_sync (unsigned mask, T v, unsigned off, int width = 32)
 {
     const int pos = emu::t_lane & (width - 1) ;
-    const int src = (pos - (int) off >= 0) ? (emu::t_lane - (int) off) : emu::t_lane ;
-    return emu::unbits<T> (emu::exchange (emu::bits (v), src)) ;
+    int src = (pos - (int) off >= 0) ? (emu::t_lane - (int) off) : emu::t_lane ;
+    if (!((mask >> src) & 1u)) src = emu::t_lane ;
+    return emu::unbits<T> (emu::exchange (mask, emu::bits (v), src)) ;
 }
-static inline unsigned __ballot_sync (unsigned, int pred)
+static inline unsigned __ballot_sync (unsigned mask, int pred)
 {
     emu::t_warp->slot [emu::t_lane] = pred ? 1 : 0 ;
-    emu::t_warp->bar.arrive_and_wait () ;
+    emu::group_sync (mask) ;
     unsigned m = 0 ;
-    for (int l = 0 ; l < 32 ; l++) if (emu::t_warp->slot [l]) m |= (1u << l) ;
-    emu::t_warp->bar.arrive_and_wait () ;
+    for (int l = 0 ; l < 32 ; l++) if (((mask >> l) & 1u) && emu::t_warp->slot [l]) m |= (1u << l) ;
+    emu::group_sync (mask) ;
     return m ;
 }
 static inline int __any_sync (unsigned mask, int pred) { return __ballot_sync (mask, pred) != 0 ; }
-static inline int __all_sync (unsigned mask, int pred) { return __ballot_sync (mask, pred) == 0xffffffffu ; }
-static inline unsigned __reduce_add_sync (unsigned, unsigned v)
+static inline int __all_sync (unsigned mask, int pred) { return __ballot_sync (mask, pred) == mask ; }
+static inline unsigned __reduce_add_sync (unsigned mask, unsigned v)
 {
     emu::t_warp->slot [emu::t_lane] = v ;
-    emu::t_warp->bar.arrive_and_wait () ;
+    emu::group_sync (mask) ;
     unsigned s = 0 ;
-    for (int l = 0 ; l < 32 ; l++) s += (unsigned) emu::t_warp->slot [l] ;
-    emu::t_warp->bar.arrive_and_wait () ;
+    for (int l = 0 ; l < 32 ; l++) if ((mask >> l) & 1u) s += (unsigned) emu::t_warp->slot [l] ;
+    emu::group_sync (mask) ;
     return s ;
 }
 

@@ -239,6 +239,7 @@ template <class S, bool ISO> static void run_case (const char *name, int64_t n, 
 
 int main (int argc, char **argv)
 {
+    setvbuf (stdout, nullptr, _IOLBF, 0) ;
     const int ncases = (argc > 1) ? atoi (argv [1]) : 1 ;
     // vector lengths: hubs beyond one table load (6144 pattern-only, 3072 valued), a dense vector,
     // regular owners, owners shorter than DOTG_SMALL, empty vectors; walks longer than DOTG_SEG

@@ -11,7 +11,10 @@ intersection loop.  The only edits made to the source text: the launchers at the
 cut off (`<<< >>>` is not C++), and the `extern __shared__` array becomes a pointer to the emulated
 dynamic shared memory.  The 32-byte PTX load has a plain-C twin under GB200_HOST_EMULATION (kernels.cuh).
 
-    python tools/emu_kernels.py [--cases 2] [--keep]
+The vector multiplies (streamed SpMV, masked pull, push: kernels_vec.cuh as run_dotv / run_saxpyv
+sequence them) are covered the same way by tests/emu/emu_vec.cpp.
+
+    python tools/emu_kernels.py [--cases 2] [--only emu_dotg|emu_vec] [--keep]
 """
 import argparse
 import os
@@ -35,9 +38,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=2)
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--only", default="", choices=["", "emu_dotg", "emu_vec"])
     args = ap.parse_args()
     kern = open(os.path.join(CS, "kernels.cuh")).read()
     eng = open(os.path.join(CS, "engine_dot.cu")).read()
+    engv = open(os.path.join(CS, "engine_vec.cu")).read()
     stop = kern.index("// launchers, one set per (xy type)")
     stop = kern.rindex("// ----", 0, stop)
     kern = kern[:stop] + "\n} // namespace gb200\n"
@@ -55,15 +60,23 @@ def main():
         cut(eng, "__global__ void dotg_nchunks_kernel"),
         cut(eng, "__global__ void dotg_items_kernel"),
     ])
+    setup_vec = "".join([
+        cut(engv, "__global__ void vec_nseg_kernel"),
+        cut(engv, "__global__ void vec_items_kernel"),
+        cut(engv, "__global__ void tile_row_kernel"),
+    ])
     d = tempfile.mkdtemp(prefix="emu_kernels_")
     open(os.path.join(d, "kernels_emu.cuh"), "w").write(kern)
     open(os.path.join(d, "setup_emu.cuh"), "w").write("namespace gb200 {\n" + setup + "}\n")
-    cpp = os.path.join(d, "emu.cpp")
-    open(cpp, "w").write(open(os.path.join(EMU, "emu_dotg.cpp")).read())
-    exe = os.path.join(d, "emu")
-    subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-w", "-I", EMU, "-I", CS, "-I", d,
-                           "-o", exe, cpp])
-    rc = subprocess.call([exe, str(args.cases)])
+    open(os.path.join(d, "setup_vec_emu.cuh"), "w").write("namespace gb200 {\n" + setup_vec + "}\n")
+    rc = 0
+    for name, argv in (("emu_dotg", [str(args.cases)]), ("emu_vec", [])):
+        if args.only and args.only != name:
+            continue
+        exe = os.path.join(d, name)
+        subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-w", "-I", EMU, "-I", CS, "-I", d,
+                               "-o", exe, os.path.join(EMU, name + ".cpp")])
+        rc |= subprocess.call([exe] + argv)
     if args.keep:
         print("sources kept in", d)
     sys.exit(rc)
