@@ -188,13 +188,13 @@ GrB_Info GB_AxB_parallel            /* same contract as reference Source/GB.h:15
 
     if (st == GB200_NOT_SUPPORTED)
     {
-        g_declined++ ;
+        __atomic_fetch_add (&g_declined, 1, __ATOMIC_RELAXED) ;    /* user threads may be concurrent */
         if (getenv ("GB200_SHIM_FORWARD") != NULL)
         {
             axb_parallel_fn fn = host_original () ;
             if (fn != NULL)
             {
-                g_forwarded++ ;
+                __atomic_fetch_add (&g_forwarded, 1, __ATOMIC_RELAXED) ;
                 return (fn (Chandle, M, Mask_comp, A, B, semiring, flipxy, do_adotb, AxB_method,
                     AxB_method_used, mask_applied, Context)) ;
             }
@@ -244,7 +244,7 @@ GrB_Info GB_AxB_parallel            /* same contract as reference Source/GB.h:15
     C->magic = GB_MAGIC ;
     (*AxB_method_used) = (GrB_Desc_Value) f.method_used ;
     (*mask_applied) = (f.mask_applied != 0) ;
-    g_gpu_calls++ ;
+    __atomic_fetch_add (&g_gpu_calls, 1, __ATOMIC_RELAXED) ;
     g_last_device_ms = f.device_ms ;
     g_last_flops = f.flops ;
     return (GrB_SUCCESS) ;
