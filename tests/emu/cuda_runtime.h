@@ -24,6 +24,11 @@
 #include <atomic>
 #include <memory>
 #include <functional>
+#include <mutex>
+#include <condition_variable>
+#include <ctime>
+using std::isnan ;
+using std::isinf ;
 
 #define __host__
 #define __device__
@@ -35,7 +40,7 @@
 #define GB200_HOST_EMULATION 1
 
 struct uint3 { unsigned x, y, z ; } ;
-struct dim3 { unsigned x = 1, y = 1, z = 1 ; } ;
+struct dim3 { unsigned x, y, z ; dim3 (unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x (x_), y (y_), z (z_) { } } ;
 struct int4 { int x, y, z, w ; } ;
 static inline int4 make_int4 (int x, int y, int z, int w) { int4 r = { x, y, z, w } ; return r ; }
 typedef void *cudaStream_t ;
@@ -62,6 +67,7 @@ alignas (128) inline unsigned char dyn_smem [232448] ;          // 227 KB
 
 static inline void group_sync (unsigned mask)
 {
+    if (t_warp == nullptr) { fprintf (stderr, "emu: warp intrinsic in a kernel launched thread-by-thread\n") ; abort () ; }
     const int leader = __builtin_ffs ((int) mask) - 1, n = __builtin_popcount (mask) ;
     if (!((mask >> t_lane) & 1u)) { fprintf (stderr, "emu: lane %d is not in the mask %08x it syncs on\n", t_lane, mask) ; abort () ; }
     Group &g = t_warp->grp [leader][n] ;
@@ -91,7 +97,11 @@ inline thread_local uint3 threadIdx = { 0, 0, 0 } ;
 inline uint3 blockIdx = { 0, 0, 0 } ;
 inline dim3 blockDim, gridDim ;
 
-static inline void __syncthreads () { emu::g_block->bar->arrive_and_wait () ; }
+static inline void __syncthreads ()
+{
+    if (emu::g_block == nullptr) { fprintf (stderr, "emu: __syncthreads in a kernel launched thread-by-thread\n") ; abort () ; }
+    emu::g_block->bar->arrive_and_wait () ;
+}
 static inline void __syncwarp (unsigned mask = 0xffffffffu) { emu::group_sync (mask) ; }
 static inline void __threadfence () { __atomic_thread_fence (__ATOMIC_SEQ_CST) ; }
 static inline void __trap () { fprintf (stderr, "emu: __trap()\n") ; abort () ; }
@@ -173,27 +183,142 @@ EMU_ATOMIC_FP (double, unsigned long long)
 
 // ---- launching ----------------------------------------------------------------------------------
 namespace emu {
-// run `body` (a call of one __global__ function) as a grid of `grid` blocks of `block` threads
-static inline void launch (unsigned grid, unsigned block, const std::function<void ()> &body)
+// A pool of OS threads that play the CUDA threads of one block at a time (blocks of a grid run one after
+// another: the single-pass scan's look-back and the kernels that pull work from a global counter only ever
+// wait for EARLIER blocks).  The pool is never destroyed: the process may exit with its threads parked.
+struct Pool
 {
-    if (block % 32 != 0) { fprintf (stderr, "emu: block size must be a multiple of 32\n") ; abort () ; }
-    gridDim.x = grid ; blockDim.x = block ;
-    for (unsigned b = 0 ; b < grid ; b++)
+    std::mutex mu ;
+    std::condition_variable go, done ;
+    std::vector<std::thread> th ;
+    uint64_t gen = 0 ;
+    unsigned want = 0, running = 0 ;
+    const std::function<void ()> *body = nullptr ;
+    Block *blk = nullptr ;
+} ;
+static inline Pool &pool () { static Pool *p = new Pool () ; return *p ; }
+
+static inline void worker (unsigned t)
+{
+    Pool &P = pool () ;
+    uint64_t seen = 0 ;
+    while (true)
     {
-        Block blk ;
-        blk.bar.reset (new std::barrier<> (block)) ;
-        for (unsigned w = 0 ; w < block / 32 ; w++) blk.warps.emplace_back (new Warp ()) ;
-        g_block = &blk ;
-        blockIdx.x = b ;
-        std::vector<std::thread> th ;
-        for (unsigned t = 0 ; t < block ; t++)
-            th.emplace_back ([t, &blk, &body] ()
-            {
-                threadIdx.x = t ; t_lane = (int) (t & 31) ; t_warp = blk.warps [t >> 5].get () ;
-                body () ;
-            }) ;
-        for (auto &x : th) x.join () ;
-        g_block = nullptr ;
+        const std::function<void ()> *body ;
+        Block *blk ;
+        {
+            std::unique_lock<std::mutex> lk (P.mu) ;
+            P.go.wait (lk, [&] { return P.gen != seen ; }) ;
+            seen = P.gen ;
+            if (t >= P.want) continue ;
+            body = P.body ; blk = P.blk ;
+        }
+        threadIdx.x = t ; t_lane = (int) (t & 31) ; t_warp = blk->warps [t >> 5].get () ;
+        (*body) () ;
+        {
+            std::lock_guard<std::mutex> lk (P.mu) ;
+            if (--P.running == 0) P.done.notify_one () ;
+        }
     }
 }
+
+// run `body` (a call of one __global__ function) as a grid of `grid` blocks of `block` threads
+static inline void launch (dim3 grid, unsigned block, const std::function<void ()> &body)
+{
+    if (block == 0 || grid.x == 0 || grid.y == 0) return ;
+    if (block % 32 != 0) { fprintf (stderr, "emu: block size %u is not a multiple of 32\n", block) ; abort () ; }
+    static std::mutex one_launch ;                  // kernels of one stream run one after another
+    std::lock_guard<std::mutex> serial (one_launch) ;
+    Pool &P = pool () ;
+    while (P.th.size () < block) { const unsigned t = (unsigned) P.th.size () ; P.th.emplace_back (worker, t) ; P.th.back ().detach () ; }
+    gridDim = grid ; blockDim.x = block ;
+    Block blk ;
+    blk.bar.reset (new std::barrier<> (block)) ;
+    for (unsigned w = 0 ; w < block / 32 ; w++) blk.warps.emplace_back (new Warp ()) ;
+    g_block = &blk ;
+    for (unsigned by = 0 ; by < grid.y ; by++)
+    for (unsigned b = 0 ; b < grid.x ; b++)
+    {
+        blockIdx.x = b ; blockIdx.y = by ;
+        std::unique_lock<std::mutex> lk (P.mu) ;
+        P.body = &body ; P.blk = &blk ; P.want = block ; P.running = block ; P.gen++ ;
+        P.go.notify_all () ;
+        P.done.wait (lk, [&] { return P.running == 0 ; }) ;
+    }
+    g_block = nullptr ;
+}
+// A kernel without any block- or warp-level synchronisation (tools/emu_library.py decides that from the
+// source text) needs no concurrency: its CUDA threads run one after another in the calling thread.
+static inline void launch_seq (dim3 grid, unsigned block, const std::function<void ()> &body)
+{
+    static std::mutex one_launch ;
+    std::lock_guard<std::mutex> serial (one_launch) ;
+    gridDim = grid ; blockDim.x = block ;
+    g_block = nullptr ; t_warp = nullptr ;
+    for (unsigned by = 0 ; by < grid.y ; by++)
+    for (unsigned b = 0 ; b < grid.x ; b++)
+    {
+        blockIdx.x = b ; blockIdx.y = by ;
+        for (unsigned t = 0 ; t < block ; t++) { threadIdx.x = t ; t_lane = (int) (t & 31) ; body () ; }
+    }
+    threadIdx.x = 0 ;
+}
+// the forms a rewritten `kernel <<<grid, block [, smem [, stream]]>>> (args)` takes
+static inline dim3 grid_of (dim3 g) { return g ; }
+template <class G> static inline dim3 grid_of (G g) { return dim3 ((unsigned) g) ; }
+template <class G, class B> static inline void launch_cfg (G g, B b, const std::function<void ()> &body)
+{ launch (grid_of (g), (unsigned) b, body) ; }
+template <class G, class B, class S> static inline void launch_cfg (G g, B b, S, const std::function<void ()> &body)
+{ launch (grid_of (g), (unsigned) b, body) ; }
+template <class G, class B, class S, class T> static inline void launch_cfg (G g, B b, S, T, const std::function<void ()> &body)
+{ launch (grid_of (g), (unsigned) b, body) ; }
+template <class G, class B> static inline void launch_cfg_seq (G g, B b, const std::function<void ()> &body)
+{ launch_seq (grid_of (g), (unsigned) b, body) ; }
+template <class G, class B, class S> static inline void launch_cfg_seq (G g, B b, S, const std::function<void ()> &body)
+{ launch_seq (grid_of (g), (unsigned) b, body) ; }
+template <class G, class B, class S, class T> static inline void launch_cfg_seq (G g, B b, S, T, const std::function<void ()> &body)
+{ launch_seq (grid_of (g), (unsigned) b, body) ; }
 } // namespace emu
+
+// ---- the slice of the runtime API the library uses: "device" memory is host memory --------------
+typedef int cudaError_t ;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 } ;
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault } ;
+enum { cudaStreamNonBlocking = 1 } ;
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 } ;
+struct cudaDeviceProp { char name [256] ; int major, minor, multiProcessorCount ; size_t totalGlobalMem ; } ;
+struct emuEvent { double ms ; } ;
+typedef emuEvent *cudaEvent_t ;
+static inline double emu_now_ms ()
+{ struct timespec ts ; clock_gettime (CLOCK_MONOTONIC, &ts) ; return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6 ; }
+static inline cudaError_t cudaGetDeviceCount (int *n) { *n = 1 ; return cudaSuccess ; }
+static inline cudaError_t cudaSetDevice (int) { return cudaSuccess ; }
+static inline cudaError_t cudaGetDeviceProperties (cudaDeviceProp *p, int)
+{
+    memset (p, 0, sizeof (*p)) ; strcpy (p->name, "host emulation (tests/emu)") ;
+    p->major = 10 ; p->minor = 0 ; p->multiProcessorCount = 1 ; p->totalGlobalMem = (size_t) 8 << 30 ;
+    return cudaSuccess ;
+}
+static inline cudaError_t cudaMemGetInfo (size_t *f, size_t *t) { *f = (size_t) 4 << 30 ; *t = (size_t) 8 << 30 ; return cudaSuccess ; }
+static inline cudaError_t cudaGetLastError () { return cudaSuccess ; }
+static inline const char *cudaGetErrorString (cudaError_t) { return "host emulation" ; }
+template <class P> static inline cudaError_t cudaMalloc (P **p, size_t n)
+{ *p = (P *) aligned_alloc (256, (n + 255) / 256 * 256 + 256) ; return *p ? cudaSuccess : cudaErrorMemoryAllocation ; }
+template <class P> static inline cudaError_t cudaMallocAsync (P **p, size_t n, cudaStream_t) { return cudaMalloc (p, n) ; }
+template <class P> static inline cudaError_t cudaMallocHost (P **p, size_t n) { return cudaMalloc (p, n) ; }
+static inline cudaError_t cudaFree (void *p) { free (p) ; return cudaSuccess ; }
+static inline cudaError_t cudaFreeHost (void *p) { free (p) ; return cudaSuccess ; }
+static inline cudaError_t cudaMemcpyAsync (void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr)
+{ if (n) memmove (d, s, n) ; return cudaSuccess ; }
+static inline cudaError_t cudaMemcpy (void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove (d, s, n) ; return cudaSuccess ; }
+static inline cudaError_t cudaMemsetAsync (void *d, int v, size_t n, cudaStream_t = nullptr) { if (n) memset (d, v, n) ; return cudaSuccess ; }
+static inline cudaError_t cudaMemset (void *d, int v, size_t n) { if (n) memset (d, v, n) ; return cudaSuccess ; }
+static inline cudaError_t cudaStreamCreateWithFlags (cudaStream_t *s, unsigned) { *s = (cudaStream_t) 1 ; return cudaSuccess ; }
+static inline cudaError_t cudaStreamSynchronize (cudaStream_t) { return cudaSuccess ; }
+static inline cudaError_t cudaStreamDestroy (cudaStream_t) { return cudaSuccess ; }
+static inline cudaError_t cudaEventCreate (cudaEvent_t *e) { *e = new emuEvent () ; (*e)->ms = 0 ; return cudaSuccess ; }
+static inline cudaError_t cudaEventDestroy (cudaEvent_t e) { delete e ; return cudaSuccess ; }
+static inline cudaError_t cudaEventRecord (cudaEvent_t e, cudaStream_t = nullptr) { e->ms = emu_now_ms () ; return cudaSuccess ; }
+static inline cudaError_t cudaEventSynchronize (cudaEvent_t) { return cudaSuccess ; }
+static inline cudaError_t cudaEventElapsedTime (float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float) (b->ms - a->ms) ; return cudaSuccess ; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute (F, cudaFuncAttribute, int) { return cudaSuccess ; }

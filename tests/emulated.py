@@ -1,0 +1,46 @@
+"""emulated.py -- test helper: builds libgb_b200_emu.so (tools/emu_library.py: the product sources compiled
+for the host against tests/emu/cuda_runtime.h) and points the ctypes binding of graphblas_b200 at it for
+the duration of a test.  The product package knows nothing about this; without the swap it only ever loads
+libgb_b200.so and fails without a GPU."""
+import contextlib
+import ctypes as C
+import importlib.util
+import os
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_FUNCS = ("gb200_last_error", "gb200_version", "gb200_kernel_launches", "gb200_multiplies", "gb200_init",
+          "gb200_finalize", "gb200_upload", "gb200_upload_from_device", "gb200_dmatrix_free", "gb200_AxB_device",
+          "gb200_AxB_host", "gb200_result_get_info", "gb200_result_fetch", "gb200_result_free",
+          "gb200_flopcount_device", "gb200_partition_by_flops", "gb200_semiring_canonical",
+          "gb200_device_count", "gb200_timer_mark", "gb200_timer_elapsed_ms", "gb200_host_malloc",
+          "gb200_host_free", "gb200_host_trim")
+_lib = None
+
+
+def library(types="bool,int8,uint8,int16,uint16,int32,uint32,int64,uint64,fp32,fp64"):
+    global _lib
+    if _lib is None:
+        spec = importlib.util.spec_from_file_location("emu_library", os.path.join(ROOT, "tools", "emu_library.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        out = os.path.join(tempfile.gettempdir(), f"gb200_emu_{os.getuid()}")
+        _lib = C.CDLL(mod.build(out, [t for t in types.split(",") if t]))
+    return _lib
+
+
+@contextlib.contextmanager
+def swapped():
+    """graphblas_b200.lib -> the emulated library, inside the with block"""
+    import graphblas_b200 as gb
+    emu, real = library(), gb.lib
+    for name in _FUNCS:
+        f, g = getattr(real, name), getattr(emu, name)
+        g.restype = f.restype
+        if f.argtypes is not None:
+            g.argtypes = f.argtypes
+    gb.lib = emu
+    try:
+        yield gb
+    finally:
+        gb.lib = real

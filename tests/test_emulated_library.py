@@ -1,0 +1,73 @@
+"""The WHOLE library on the host: tools/emu_library.py compiles the product sources (host orchestration of
+engine_*.cu and every kernel; `<<< >>>` launches rewritten textually) against tests/emu/cuda_runtime.h
+into libgb_b200_emu.so, and the GPU parity tests of tests/test_gpu_seam.py are then run through the real
+ctypes binding with `graphblas_b200.lib` pointed at it (tests/emulated.py) -- against the same pinned
+oracle, golden vectors and known answers as on the GPU.  A sample of them, sized for the CPU suite; any
+other `-m gpu` seam test can be run the same way when developing without a GPU.
+
+This is test infrastructure: the product package never loads the emulated library, and a green run here
+is NOT a parity claim for the GPU (the memory model, the warp scheduling and the one PTX load are
+emulated); it checks the engine's sequencing and the kernels' logic on every CPU run."""
+import numpy as np
+import pytest
+
+import emulated
+import gen
+import oracle_c
+import semirings
+import test_gpu_seam as T
+
+
+@pytest.fixture(scope="module")
+def emu():
+    emulated.library()          # built once (cached by a hash of the sources)
+    return emulated
+
+
+def test_library_identity(emu):
+    with emu.swapped() as gb:
+        assert gb.lib.gb200_device_count() == 1
+        assert b"gb_b200" in gb.lib.gb200_version()
+    import graphblas_b200 as gb
+    assert gb.lib._name.endswith("libgb_b200.so")       # the swap is undone
+
+
+def test_semiring_sample(emu):
+    """every 60th of the 960 built-in workers: saxpy, masked saxpy, masked dot, dot against the oracle"""
+    with emu.swapped() as gb:
+        n = 0
+        for add, mult, t in list(semirings.all_builtin())[::60]:
+            dt = T.NPT[t]
+            A = gb.Matrix.from_scipy(gen.er(40, 30, 260, 61, dt, lo=-3, hi=4).tocsc())
+            B = gb.Matrix.from_scipy(gen.er(30, 35, 240, 62, dt, lo=-3, hi=4).tocsc())
+            At = gb.Matrix.from_scipy(gen.er(30, 40, 260, 63, dt, lo=-3, hi=4).tocsc())
+            M = gb.Matrix.from_scipy(gen.er(40, 35, 500, 64, np.bool_).tocsc())
+            sr = gb.Semiring(add, mult, t)
+            tag = f"{add}_{mult}_{t}"
+            T.assert_same(oracle_c.axb(None, False, A, B, sr), gb.axb_host(None, False, A, B, sr).matrix, add, tag + " saxpy")
+            T.assert_same(oracle_c.axb(M, False, A, B, sr), gb.axb_host(M, False, A, B, sr).matrix, add, tag + " masked saxpy")
+            T.assert_same(oracle_c.axb(M, False, At, B, sr, True), gb.axb_host(M, False, At, B, sr, True).matrix, add, tag + " masked dot")
+            T.assert_same(oracle_c.axb(None, False, At, B, sr, True), gb.axb_host(None, False, At, B, sr, True).matrix, add, tag + " dot")
+            n += 1
+        assert n == 16
+
+
+SEAM = [
+    ("flopcount", lambda: [T.test_flopcount_matches_oracle(h, m) for h in (False, True) for m in (False, True)]),
+    ("golden vectors", T.test_golden_vectors_on_gpu),
+    ("tri_demo known answers", T.test_tri_demo_known_answers_on_gpu),
+    ("masked dot, hubs, pattern-only PLUS_TIMES_INT64", lambda: T.test_masked_dot_hubs(True, "PLUS", "TIMES", "INT64")),
+    ("masked dot, hubs, valued MIN_PLUS_FP64", lambda: T.test_masked_dot_hubs(False, "MIN", "PLUS", "FP64")),
+    ("masked dot, edge cases", T.test_masked_dot_edge_cases),
+    ("NaN / Inf placement", T.test_nan_inf_placement),
+    ("typecast INT32 x FP32 -> FP64", lambda: T.test_typecast_at_the_seam("INT32", "FP32", "PLUS", "TIMES", "FP64")),
+    ("vector pull and push, PLUS_TIMES_FP64", lambda: T.test_vector_pull_and_push("PLUS", "TIMES", "FP64", False)),
+    ("vector pull and push, MIN_PLUS_FP64, dense u", lambda: T.test_vector_pull_and_push("MIN", "PLUS", "FP64", True)),
+    ("vector pull and push, LOR_LAND_BOOL", lambda: T.test_vector_pull_and_push("LOR", "LAND", "BOOL", False)),
+]
+
+
+@pytest.mark.parametrize("what,body", SEAM, ids=[s[0] for s in SEAM])
+def test_seam_test_on_the_host(emu, what, body):
+    with emu.swapped():
+        body()
