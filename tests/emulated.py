@@ -18,15 +18,37 @@ _FUNCS = ("gb200_last_error", "gb200_version", "gb200_kernel_launches", "gb200_m
 _lib = None
 
 
-def library(types="bool,int8,uint8,int16,uint16,int32,uint32,int64,uint64,fp32,fp64"):
+def library(types="bool,int8,uint8,int16,uint16,int32,uint32,int64,uint64,fp32,fp64", global_scope=False):
+    """global_scope: load with RTLD_GLOBAL -- needed (and must happen BEFORE graphblas_b200 is imported) when the
+    emulated shim is used in this process, so that the shim's gb200_* references find this library first"""
     global _lib
     if _lib is None:
         spec = importlib.util.spec_from_file_location("emu_library", os.path.join(ROOT, "tools", "emu_library.py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         out = os.path.join(tempfile.gettempdir(), f"gb200_emu_{os.getuid()}")
-        _lib = C.CDLL(mod.build(out, [t for t in types.split(",") if t]))
+        _lib = C.CDLL(mod.build(out, [t for t in types.split(",") if t]),
+                      mode=C.RTLD_GLOBAL if global_scope else C.DEFAULT_MODE)
     return _lib
+
+
+def shim(ref="/root/reference"):
+    """the reference-side binding (csrc/shim/gb_axb_parallel_shim.c) linked against the emulated library;
+    None where the reference's headers are absent"""
+    if not os.path.isdir(os.path.join(ref, "Source")):
+        return None
+    library()
+    out = os.path.join(tempfile.gettempdir(), f"gb200_emu_{os.getuid()}")
+    so = os.path.join(out, "libgb_b200_shim_emu.so")
+    src = os.path.join(ROOT, "graphblas_b200", "csrc", "shim", "gb_axb_parallel_shim.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(out, "libgb_b200_emu.so"))):
+        import subprocess
+        subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-DNDEBUG", "-Wno-pragmas",
+                               "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ref, "Source", "Template"),
+                               "-I", os.path.join(ref, "Source"), "-I", os.path.join(ref, "Include"),
+                               "-fvisibility=hidden", "-o", so, src, "-L", out, "-l:libgb_b200_emu.so",
+                               "-Wl,-rpath," + out, "-ldl"])
+    return so
 
 
 @contextlib.contextmanager
