@@ -1,7 +1,8 @@
 """The N>1 path on CPU: graphblas_b200.sharded over torch.distributed (gloo, world_size 2 and 3) with
 the oracle injected as the local multiply, so that the partitioning / exchange / concatenation logic
-is checked without a GPU.  The GPU legs of the same cases are in test_gpu_seam.py (N=1, the CUDA
-library as the local multiply) and bench.py --gpus N (NCCL)."""
+is checked without a GPU; one world_size-2 run uses the EMULATED library (tests/emulated.py: the product's
+own gb200_AxB_host compiled for the host) as the local multiply instead.  The GPU legs of the same cases are
+in test_gpu_seam.py (N=1, the CUDA library as the local multiply) and bench.py --gpus N (NCCL)."""
 import os
 import socket
 import sys
@@ -112,15 +113,31 @@ def cases():
     return out
 
 
-def _worker(rank: int, world: int, port: int, errq):
+# the cases run with the EMULATED library as the local multiply (tests/emulated.py): the product's own
+# gb200_AxB_host, mask-policy flags included, instead of the oracle stand-in above
+# (not the push with a complemented mask: the library applies <!M> inside the kernel and reports
+# mask_applied, where the reference's saxpy ignores it -- same C, different T; test_gpu_seam.py covers it)
+EMULATED_CASES = ("saxpy masked", "saxpy mask dropped by the global rule", "saxpy hyper A and M", "dot masked",
+                  "vector push, no mask, MIN_PLUS", "vector pull, dense vector (SSSP)",
+                  "vector pull, complemented mask")
+
+
+def _worker(rank: int, world: int, port: int, errq, emulated_lib: bool = False):
     try:
+        import contextlib
         import torch.distributed as dist
         dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
                                 world_size=world)
+        if emulated_lib:
+            import emulated
         for name, M, comp, A, B, sr, dot in cases():
+            if emulated_lib and name not in EMULATED_CASES:
+                continue
             ref_info = {}
             ref = oracle_c.axb(M, comp, A, B, sr, dot, info=ref_info)
-            r = sharded.mxm(M, comp, A, B, sr, dot, gather=True, multiply=oracle_multiply)
+            with (emulated.swapped() if emulated_lib else contextlib.nullcontext()):
+                r = sharded.mxm(M, comp, A, B, sr, dot, gather=True,
+                                multiply=None if emulated_lib else oracle_multiply)
             what = f"[{world} ranks, rank {rank}] {name}"
             assert r.full is not None, what
             got = r.full
@@ -149,13 +166,16 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_multiply_gloo(world):
+@pytest.mark.parametrize("world,emulated_lib", [(2, False), (3, False), (2, True)])
+def test_sharded_multiply_gloo(world, emulated_lib):
     import torch.multiprocessing as mp
+    if emulated_lib:
+        import emulated
+        emulated.library()              # built here once; the ranks load it from the cache
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, errq)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, errq, emulated_lib)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
