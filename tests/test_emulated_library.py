@@ -71,3 +71,23 @@ SEAM = [
 def test_seam_test_on_the_host(emu, what, body):
     with emu.swapped():
         body()
+
+
+def test_owner_aligned_parts_merge_to_the_whole(emu):
+    """the N-GPU cut of the masked dot (graphblas_b200/sharded.py, what bench.py --gpus N runs): every
+    rank's part through the library, merged, equals the whole T and the oracle's"""
+    import scipy.sparse as sps
+    from graphblas_b200 import sharded
+    with emu.swapped() as gb:
+        S = gen.rmat_scipy(10, 8).tocsc().astype(np.int64)
+        L = gb.Matrix.from_scipy(sps.tril(S, -1).tocsc())
+        U = gb.Matrix.from_scipy(sps.triu(S, 1).tocsc())
+        sr = gb.Semiring("PLUS", "TIMES", "INT64", True)
+        ref = oracle_c.axb(L, False, U, L, sr, True)
+        whole = gb.axb_host(L, False, U, L, sr, True).matrix
+        T.assert_same(ref, whole, "PLUS", "whole")
+        op = sharded.OwnerPartition(L, U, L, 4, hub_len=64)
+        parts = [gb.axb_host(op.mask(r), False, U, L, sr, True).matrix for r in range(4)]
+        merged = sharded.merge_disjoint(parts)
+        T.assert_same(ref, merged, "PLUS", "merged parts")
+        assert int(merged.x.sum()) == int(ref.x.sum())          # the triangle count
