@@ -91,3 +91,38 @@ def test_owner_aligned_parts_merge_to_the_whole(emu):
         merged = sharded.merge_disjoint(parts)
         T.assert_same(ref, merged, "PLUS", "merged parts")
         assert int(merged.x.sum()) == int(ref.x.sum())          # the triangle count
+
+
+def test_concurrent_callers(emu):
+    """SURVEY 8b, threading: the reference may be entered from many user threads (openmp_demo, pthread_demo);
+    the library serialises device use behind a mutex.  Four threads multiply different operands at once
+    (ctypes releases the GIL around the calls) and each gets its own right answer."""
+    import threading
+    with emu.swapped() as gb:
+        jobs = []
+        for k in range(4):
+            A = gb.Matrix.from_scipy(gen.er(120, 90, 1500, 700 + k, np.int64, lo=1, hi=6).tocsc())
+            B = gb.Matrix.from_scipy(gen.er(90, 100, 1400, 710 + k, np.int64, lo=1, hi=6).tocsc())
+            At = gb.Matrix.from_scipy(gen.er(90, 120, 1500, 720 + k, np.int64, lo=1, hi=6).tocsc())
+            M = gb.Matrix.from_scipy(gen.er(120, 100, 2500, 730 + k, np.bool_).tocsc())
+            jobs.append((A, B, At, M))
+        sr = gb.Semiring("PLUS", "TIMES", "INT64")
+        want = [(oracle_c.axb(M, False, A, B, sr), oracle_c.axb(M, False, At, B, sr, True)) for A, B, At, M in jobs]
+        got, errs = [None] * 4, []
+
+        def work(k):
+            try:
+                A, B, At, M = jobs[k]
+                for _ in range(2):
+                    got[k] = (gb.axb_host(M, False, A, B, sr).matrix, gb.axb_host(M, False, At, B, sr, True).matrix)
+            except Exception as e:      # surfaced below, in the main thread
+                errs.append(repr(e))
+        th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(600)
+        assert not errs, errs
+        for k in range(4):
+            T.assert_same(want[k][0], got[k][0], "PLUS", f"thread {k} masked saxpy")
+            T.assert_same(want[k][1], got[k][1], "PLUS", f"thread {k} masked dot")
