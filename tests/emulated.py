@@ -18,6 +18,16 @@ _FUNCS = ("gb200_last_error", "gb200_version", "gb200_kernel_launches", "gb200_m
 _lib = None
 
 
+def _sanitize():
+    """GB200_EMU_SANITIZE=1: the AddressSanitizer + UBSan build (tools/emu_library.py); run python with
+    LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0"""
+    return os.environ.get("GB200_EMU_SANITIZE", "") not in ("", "0")
+
+
+def _outdir():
+    return os.path.join(tempfile.gettempdir(), f"gb200_emu_{os.getuid()}" + ("_asan" if _sanitize() else ""))
+
+
 def library(types="bool,int8,uint8,int16,uint16,int32,uint32,int64,uint64,fp32,fp64", global_scope=False):
     """global_scope: load with RTLD_GLOBAL -- needed (and must happen BEFORE graphblas_b200 is imported) when the
     emulated shim is used in this process, so that the shim's gb200_* references find this library first"""
@@ -26,8 +36,7 @@ def library(types="bool,int8,uint8,int16,uint16,int32,uint32,int64,uint64,fp32,f
         spec = importlib.util.spec_from_file_location("emu_library", os.path.join(ROOT, "tools", "emu_library.py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
-        out = os.path.join(tempfile.gettempdir(), f"gb200_emu_{os.getuid()}")
-        _lib = C.CDLL(mod.build(out, [t for t in types.split(",") if t]),
+        _lib = C.CDLL(mod.build(_outdir(), [t for t in types.split(",") if t], _sanitize()),
                       mode=C.RTLD_GLOBAL if global_scope else C.DEFAULT_MODE)
     return _lib
 
@@ -38,7 +47,7 @@ def shim(ref="/root/reference"):
     if not os.path.isdir(os.path.join(ref, "Source")):
         return None
     library()
-    out = os.path.join(tempfile.gettempdir(), f"gb200_emu_{os.getuid()}")
+    out = _outdir()
     so = os.path.join(out, "libgb_b200_shim_emu.so")
     src = os.path.join(ROOT, "graphblas_b200", "csrc", "shim", "gb_axb_parallel_shim.c")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(out, "libgb_b200_emu.so"))):

@@ -139,8 +139,12 @@ def source_hash() -> str:
     return h.hexdigest()[:16]
 
 
-def build(out: str, types) -> str:
-    tag = source_hash() + "_" + "_".join(types)
+def build(out: str, types, sanitize: bool = False) -> str:
+    """sanitize: AddressSanitizer + UBSan build (load it with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+    and ASAN_OPTIONS=detect_leaks=0): "device" memory is heap memory, so an out-of-bounds access of a kernel
+    or of the engine is reported with a stack"""
+    tag = source_hash() + "_" + "_".join(types) + ("_asan" if sanitize else "")
+    san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"] if sanitize else []
     lib = os.path.join(out, "libgb_b200_emu.so")
     stamp = os.path.join(out, "stamp")
     if os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == tag:
@@ -177,11 +181,11 @@ def build(out: str, types) -> str:
 
     def cc(u):
         o = u[:-4] + ".o"
-        subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-pthread", "-w", "-I", EMU, "-c", u, "-o", o])
+        subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-pthread", "-w", *san, "-I", EMU, "-c", u, "-o", o])
         return o
     with concurrent.futures.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs = list(ex.map(cc, units))
-    subprocess.check_call(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", lib] + objs)   # binds its own gb200_* calls locally: the real library may be loaded RTLD_GLOBAL in the same process
+    subprocess.check_call(["g++", "-shared", "-pthread", *san, "-Wl,-Bsymbolic", "-o", lib] + objs)   # binds its own gb200_* calls locally: the real library may be loaded RTLD_GLOBAL in the same process
     open(stamp, "w").write(tag)
     return lib
 
@@ -190,8 +194,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="/tmp/gb200_emu")
     ap.add_argument("--types", default="bool,int32,int64,fp64")
+    ap.add_argument("--sanitize", action="store_true")
     args = ap.parse_args()
-    print(build(args.out, [t for t in args.types.split(",") if t]))
+    print(build(args.out, [t for t in args.types.split(",") if t], args.sanitize))
 
 
 if __name__ == "__main__":
