@@ -227,34 +227,41 @@ __global__ void dotg_tasks_kernel (DMat A, DMat B, DMat M, const int32_t *__rest
     }
 }
 
-// Owners that need several table loads are HUB owners: their items are big (DOTG_HUB_TASKS tasks,
-// walked a lane per task) and go to their own launch; the others get DOTG_CHUNK tasks per item.
-// Returns the tasks per work item of owner v if it belongs to the class `hub`, else 0.
-__device__ __forceinline__ int64_t dotg_chunk_of (const DMat &O, const DMat &M, int orient, int64_t v,
-    int64_t cap, int hub, int64_t chunk)
+// Owner classes.  0: the owner fits one load of the cuckoo tables (or is dense): flat kernel, DOTG_CHUNK
+// tasks per item.  1: a longer owner ("hub") whose index range fits DOTF_MAXPARTS bitmap parts: flat
+// kernel with a shared-memory bitmap, big items.  2: any other hub: the segmented cuckoo kernel
+// dotg_kernel<HUB>, big items.  flat == 0 (GB200_DOTF=0, for A/B runs) sends class 0 to
+// dotg_kernel<!HUB> and every hub to class 2.
+struct DotgClasses { int64_t cap ; int64_t bm_bits ; int flat ; int64_t chunk [3] ; } ;
+
+__device__ __forceinline__ int dotg_class_of (const DMat &O, const DMat &M, int orient, int64_t v,
+    const DotgClasses &K)
 {
     int64_t ko = v ;
     if (!orient) ko = dm_vecpos (O, dm_vecname (M, v)) ;
-    if (ko < 0) return hub ? 0 : chunk ;
-    const int64_t olen = O.p [ko+1] - O.p [ko] ;
-    const bool is_hub = (olen > cap && olen != O.vlen) ;
-    if (is_hub != (hub != 0)) return 0 ;
-    return chunk ;
+    if (ko < 0) return 0 ;
+    const int64_t o0 = O.p [ko], o1 = O.p [ko+1] ;
+    const int64_t olen = o1 - o0 ;
+    if (olen <= K.cap || olen == O.vlen) return 0 ;
+    if (!K.flat) return 2 ;
+    const int64_t lo0 = ((int64_t) __ldg (O.i + o0)) & ~(int64_t) 31 ;
+    const int64_t nparts = (((int64_t) __ldg (O.i + o1 - 1)) - lo0) / K.bm_bits + 1 ;
+    return (nparts <= DOTF_MAXPARTS) ? 1 : 2 ;
 }
 
-__global__ void dotg_nchunks_kernel (DMat O, DMat M, int orient, int64_t cap, int hub, int64_t chunk,
+__global__ void dotg_nchunks_kernel (DMat O, DMat M, int orient, DotgClasses K, int cls,
     const int64_t *__restrict__ start, int64_t n, int64_t *__restrict__ nch)
 {
     for (int64_t v = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; v < n ;
         v += (int64_t) gridDim.x * blockDim.x)
     {
         const int64_t cnt = start [v+1] - start [v] ;
-        const int64_t ch = (cnt > 0) ? dotg_chunk_of (O, M, orient, v, cap, hub, chunk) : 0 ;
-        nch [v] = (ch > 0) ? (cnt + ch - 1) / ch : 0 ;
+        const int64_t ch = K.chunk [cls] ;
+        nch [v] = (cnt > 0 && dotg_class_of (O, M, orient, v, K) == cls) ? (cnt + ch - 1) / ch : 0 ;
     }
 }
 
-__global__ void dotg_items_kernel (DMat O, DMat M, int orient, int64_t cap, int hub, int64_t chunk,
+__global__ void dotg_items_kernel (DMat O, DMat M, int orient, DotgClasses K, int cls,
     const int64_t *__restrict__ start, const int64_t *__restrict__ ioff, int64_t n,
     DotItem *__restrict__ items)
 {
@@ -263,8 +270,8 @@ __global__ void dotg_items_kernel (DMat O, DMat M, int orient, int64_t cap, int 
     {
         const int64_t s0 = start [v], s1 = start [v+1] ;
         if (s1 <= s0) continue ;
-        const int64_t ch = dotg_chunk_of (O, M, orient, v, cap, hub, chunk) ;
-        if (ch <= 0) continue ;
+        if (dotg_class_of (O, M, orient, v, K) != cls) continue ;
+        const int64_t ch = K.chunk [cls] ;
         int64_t q = ioff [v] ;
         for (int64_t e0 = s0 ; e0 < s1 ; e0 += ch, q++)
         {
@@ -354,6 +361,9 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             // 0: walk the whole list of every pair (for A/B measurements)
             const char *trim_env = getenv ("GB200_DOTG_TRIM") ;
             const int trim = (trim_env != nullptr && atoi (trim_env) == 0) ? 0 : 1 ;
+            // 0: the round-1 kernels (warp per task / lane per task) instead of the flat ones
+            const char *flat_env = getenv ("GB200_DOTF") ;
+            const bool flat = !(flat_env != nullptr && atoi (flat_env) == 0) ;
             DevBuf own, small, wl, ws, cntA, offA, curA, pos0, poss, off0, plist, slist ;
             GB200_TRY (own.alloc (mnz)) ;
             GB200_TRY (small.alloc (mnz)) ;
@@ -403,7 +413,9 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             memset (&ga, 0, sizeof (ga)) ;
             DevBuf next_item ;
             GB200_TRY (next_item.alloc (16)) ;
+            GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 16, c.stream)) ;
             ga.next_item = next_item.as<unsigned long long> () ;
+            ga.failed = (unsigned int *) (next_item.as<unsigned long long> () + 1) ;
             ga.A = A ; ga.B = B ; ga.M = Mv ;
             ga.vals = vals.ptr ; ga.flags = flags.as<uint8_t> () ;
             ga.nmatch = nmatch.as<unsigned long long> () ;
@@ -433,9 +445,9 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                     toff.as<int64_t> (), nown, otoff.as<int64_t> ()) ;
                 count_launch () ;
                 ga.tasks = tasks.as<DotTask> () ; ga.orient = orient ;
-                // Tasks per hub item: a lane-per-task item wants many tasks per lane, but there must
-                // also be several items per resident block or a few big hubs serialise the launch
-                // (one rank of an 8-GPU run holds an eighth of the hubs)
+                // Tasks per hub item: big items amortise the owner's table, but there must also be
+                // several items per resident block or a few big hubs serialise the launch (one rank of
+                // an 8-GPU run holds an eighth of the hubs)
                 int64_t hub_chunk = ntasks / (2 * 6 * (int64_t) c.sm_count * 2) ;
                 hub_chunk = ((hub_chunk + 511) / 512) * 512 ;
                 if (hub_chunk < 2048) hub_chunk = 2048 ;
@@ -445,11 +457,21 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 int64_t reg_chunk = DOTG_CHUNK ;
                 if (getenv ("GB200_DOTG_CHUNK")) reg_chunk = atoll (getenv ("GB200_DOTG_CHUNK")) ;
                 if (reg_chunk < 1) reg_chunk = DOTG_CHUNK ;
-                for (int hub = 1 ; hub >= 0 ; hub--)
+                DotgClasses K ;
+                K.cap = cap ; K.bm_bits = dotf_bm_bits (iso) ; K.flat = flat ? 1 : 0 ;
+                // smaller bitmap parts (a multiple of 32 indices): lets a test reach several parts
+                if (getenv ("GB200_DOTF_BM_BITS"))
                 {
+                    const int64_t bb = (atoll (getenv ("GB200_DOTF_BM_BITS")) / 32) * 32 ;
+                    if (bb >= 32 && bb <= K.bm_bits) K.bm_bits = bb ;
+                }
+                ga.bm_bits = K.bm_bits ;
+                K.chunk [0] = reg_chunk ; K.chunk [1] = hub_chunk ; K.chunk [2] = hub_chunk ;
+                for (int cls = 2 ; cls >= 0 ; cls--)
+                {
+                    if (cls == 1 && !flat) continue ;
                     dotg_nchunks_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                        orient ? A : B, Mv, orient, cap, hub, hub ? hub_chunk : reg_chunk,
-                        otoff.as<int64_t> (), nown, nch.as<int64_t> ()) ;
+                        orient ? A : B, Mv, orient, K, cls, otoff.as<int64_t> (), nown, nch.as<int64_t> ()) ;
                     count_launch () ;
                     GB200_TRY (scan_i64 (nch.as<int64_t> (), ioff.as<int64_t> (), nown)) ;
                     int64_t nitems = 0 ;
@@ -458,18 +480,35 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                     DevBuf items ;
                     GB200_TRY (items.alloc (nitems * sizeof (DotItem))) ;
                     dotg_items_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                        orient ? A : B, Mv, orient, cap, hub, hub ? hub_chunk : reg_chunk,
-                        otoff.as<int64_t> (), ioff.as<int64_t> (), nown, items.as<DotItem> ()) ;
+                        orient ? A : B, Mv, orient, K, cls, otoff.as<int64_t> (), ioff.as<int64_t> (), nown,
+                        items.as<DotItem> ()) ;
                     count_launch () ;
-                    GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 16, c.stream)) ;
+                    GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 8, c.stream)) ;
                     ga.items = items.as<DotItem> () ; ga.nitems = nitems ;
-                    const int fam = hub ? (iso ? FAM_DOTG_HUB_ISO : FAM_DOTG_HUB)
-                                        : (iso ? FAM_DOTG_ISO : FAM_DOTG) ;
+                    int fam, per_sm, threads ;
+                    if (cls == 2) { fam = iso ? FAM_DOTG_HUB_ISO : FAM_DOTG_HUB ; per_sm = 2 ; threads = DOTG_THREADS ; }
+                    else if (cls == 1) { fam = iso ? FAM_DOTF_BM_ISO : FAM_DOTF_BM ; per_sm = 1 ; threads = DOTF_BM_THREADS ; }
+                    else if (flat) { fam = iso ? FAM_DOTF_ISO : FAM_DOTF ; per_sm = iso ? 3 : 2 ; threads = DOTF_THREADS ; }
+                    else { fam = iso ? FAM_DOTG_ISO : FAM_DOTG ; per_sm = iso ? 3 : 2 ; threads = DOTG_THREADS ; }
                     if (!launch_typed (s.xy_code, fam, s.z_code, s.add_opcode, s.mult_opcode, &ga,
-                        grid_cap (nitems, (iso && !hub) ? 3 : 2), DOTG_THREADS))
+                        grid_cap (nitems, per_sm), threads))
                     { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
                     // `items` is released in stream order, after the kernel that reads it
                 }
+            }
+            // an owner whose cuckoo tables could not be built (never seen): every pair again, table-free
+            int64_t failed = 0 ;
+            GB200_TRY (read_i64 (next_item.as<int64_t> () + 1, &failed)) ;
+            if (failed != 0)
+            {
+                GB200_CUDA (cudaMemsetAsync (flags.ptr, 0, flags.bytes, c.stream)) ;
+                GB200_TRY (fill_bits (vals.ptr, acc_size, ident, mnz)) ;
+                GB200_CUDA (cudaMemsetAsync (nmatch.ptr, 0, 8, c.stream)) ;
+                da.mode = DOT_MASK ; da.mvec = mvec.as<int32_t> () ; da.plist = nullptr ;
+                da.npairs = mnz ; da.vals = vals.ptr ; da.flags = flags.as<uint8_t> () ; da.G = 8 ;
+                if (!launch_typed (s.xy_code, FAM_DOT, s.z_code, s.add_opcode, s.mult_opcode, &da,
+                    grid_cap ((mnz + 31) / 32, 16), 256))
+                { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
             }
         }
         GB200_TRY (scan_u8 (flags.as<uint8_t> (), pos.as<int64_t> (), mnz)) ;

@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "semiring.cuh"
+#include "scan.cuh"
 #include "kernels_vec.cuh"
 
 namespace gb200 {
@@ -331,6 +332,9 @@ struct DotGArgs
     uint8_t *flags ;            // pre-zeroed
     unsigned long long *nmatch ;
     unsigned long long *next_item ;     // dynamic work-item counter (zeroed before launch)
+    unsigned int *failed ;              // set to 1 if an owner's cuckoo tables could not be built: the
+                                        // host then recomputes the pairs with the table-free dot_kernel
+    int64_t bm_bits ;                   // dotf_kernel<BITMAP>: indices per bitmap part (a multiple of 32)
     int mult_op ; int flip ;
 } ;
 
@@ -654,7 +658,7 @@ dotg_kernel (DotGArgs a)
     using slot_t = typename std::conditional<ISO, uint32_t, uint64_t>::type ;
     extern __shared__ __align__ (16) unsigned char dotg_raw [] ;
     slot_t *tab = (slot_t *) dotg_raw ;
-    __shared__ int s_next, s_fail ;
+    __shared__ int s_next, s_fail, s_skip ;
     __shared__ unsigned long long s_item ;
     __shared__ uint16_t s_cur [HUB ? DOTG_HUB_TASKS : 1] ;
     constexpr int CAP = dotg_cap (ISO) ;
@@ -693,6 +697,7 @@ dotg_kernel (DotGArgs a)
         g.tasks = a.tasks + item.e0 ;
         g.ntask = (int) (item.e1 - item.e0) ;
         if (HUB) for (int t = threadIdx.x ; t < g.ntask ; t += blockDim.x) s_cur [t] = 0 ;
+        if (threadIdx.x == 0) s_skip = 0 ;
         for (int seg = 0 ; seg < nseg ; seg++)
         {
             const int64_t s0 = o0 + (int64_t) seg * CAP ;
@@ -732,7 +737,13 @@ dotg_kernel (DotGArgs a)
                     }
                     __syncthreads () ;
                     if (!s_fail) break ;
-                    if (attempt >= 30) __trap () ;      // never seen; fail loudly rather than wrongly
+                    if (attempt >= 30)
+                    {
+                        // never seen.  No trap (a trap poisons the context of the host process): the
+                        // item is abandoned, the flag tells the host to recompute with dot_kernel
+                        if (threadIdx.x == 0) { *a.failed = 1u ; s_skip = 1 ; }
+                        break ;
+                    }
                     c1 = (c1 * 0x01000193u + 0xFE94F82Au) | 1u ;
                     c2 = (c2 * 0x01000193u + 0x4A8BE922u) | 1u ;
                 }
@@ -740,6 +751,7 @@ dotg_kernel (DotGArgs a)
             else __syncthreads () ;
             if (threadIdx.x == 0) s_next = 0 ;
             __syncthreads () ;
+            if (s_skip) break ;
             g.NS = NS ; g.sh = sh ; g.c1 = c1 ; g.c2 = c2 ;
             if constexpr (HUB)
             {
@@ -757,12 +769,19 @@ dotg_kernel (DotGArgs a)
     if (lane == 0 && nm) atomicAdd (a.nmatch, nm) ;
 }
 
+} // namespace gb200
+
+#include "kernels_dotf.cuh"
+
+namespace gb200 {
+
 // ---------------------------------------------------------------------------------------------
 // launchers, one set per (xy type); defined in inst_*.cu through GB200_INSTANTIATE_TYPE
 // ---------------------------------------------------------------------------------------------
 enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_DOTV = 4,
     FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9,
-    FAM_DOTG_ISO = 10, FAM_SPMV_OCC8 = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13 } ;
+    FAM_DOTG_ISO = 10, FAM_SPMV_OCC8 = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13,
+    FAM_DOTF = 14, FAM_DOTF_ISO = 15, FAM_DOTF_BM = 16, FAM_DOTF_BM_ISO = 17 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -798,6 +817,28 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
             dotg_kernel<S, true, true> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
         else
             dotg_kernel<S, false, true> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+    }
+    else if (family == FAM_DOTF || family == FAM_DOTF_ISO || family == FAM_DOTF_BM
+        || family == FAM_DOTF_BM_ISO)
+    {
+        static bool attr_set = false ;          // one flag per instantiation
+        if (!attr_set)
+        {
+            cudaFuncSetAttribute (dotf_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            cudaFuncSetAttribute (dotf_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            cudaFuncSetAttribute (dotf_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTF_BM_SMEM) ;
+            cudaFuncSetAttribute (dotf_kernel<S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTF_BM_SMEM) ;
+            attr_set = true ;
+        }
+        const DotGArgs &ga = *(const DotGArgs *) args ;
+        if (family == FAM_DOTF_ISO)
+            dotf_kernel<S, true, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+        else if (family == FAM_DOTF)
+            dotf_kernel<S, false, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+        else if (family == FAM_DOTF_BM_ISO)
+            dotf_kernel<S, true, true> <<<cfg.grid, cfg.block, DOTF_BM_SMEM, cfg.stream>>> (ga) ;
+        else
+            dotf_kernel<S, false, true> <<<cfg.grid, cfg.block, DOTF_BM_SMEM, cfg.stream>>> (ga) ;
     }
     else if (family == FAM_DOTV)
         dotv_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotVArgs *) args) ;

@@ -152,6 +152,17 @@ static inline unsigned __reduce_add_sync (unsigned mask, unsigned v)
     return s ;
 }
 
+static inline unsigned __reduce_or_sync (unsigned mask, unsigned v)
+{
+    emu::t_warp->slot [emu::t_lane] = v ;
+    emu::group_sync (mask) ;
+    unsigned s = 0 ;
+    for (int l = 0 ; l < 32 ; l++) if ((mask >> l) & 1u) s |= (unsigned) emu::t_warp->slot [l] ;
+    emu::group_sync (mask) ;
+    return s ;
+}
+static inline int __clz (unsigned v) { return v ? __builtin_clz (v) : 32 ; }
+
 // ---- atomics ----------------------------------------------------------------------------------
 #define EMU_ATOMIC_INT(T) \
 static inline T atomicAdd (T *p, T v) { return __atomic_fetch_add (p, v, __ATOMIC_RELAXED) ; } \

@@ -301,6 +301,20 @@ def test_masked_dot_hubs(iso, add, mult, t):
         assert got.info["mask_applied"] == 1 and got.info["method_used"] == gb.METHOD_DOT
 
 
+@pytest.mark.parametrize("iso", [True, False])
+@pytest.mark.parametrize("bits", ["4096", "1024", "old"])
+def test_masked_dot_hub_variants(monkeypatch, iso, bits):
+    """the hub owners through (a) several bitmap parts of the flat kernel (GB200_DOTF_BM_BITS=4096: the
+    12000-wide index range takes 3 parts), (b) more parts than the flat kernel accepts (1024: the segmented
+    cuckoo kernel serves them), (c) the round-1 kernels alone (GB200_DOTF=0): same T as the oracle"""
+    if bits == "old":
+        monkeypatch.setenv("GB200_DOTF", "0")
+    else:
+        monkeypatch.setenv("GB200_DOTF_BM_BITS", bits)
+    for add, mult, t in (("PLUS", "TIMES", "INT64"), ("MIN", "PLUS", "FP64"), ("LXOR", "LOR", "BOOL")):
+        test_masked_dot_hubs(iso, add, mult, t)
+
+
 def test_masked_dot_general_path_on_iso_input(monkeypatch):
     """GB200_DOTG_ISO=0 sends pattern-only operands through the valued kernel: same T"""
     A = gen.rmat_scipy(13, 8, dtype=np.int64)

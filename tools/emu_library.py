@@ -28,7 +28,7 @@ ALL_TYPES = ["bool", "int8", "uint8", "int16", "uint16", "int32", "uint32", "int
 
 
 SYNC_TOKENS = ("__syncthreads", "__syncwarp", "__shfl", "__ballot_sync", "__any_sync", "__all_sync",
-               "__reduce_add_sync", "__match_")
+               "__reduce_add_sync", "__reduce_or_sync", "__match_")
 
 
 def function_bodies(text: str) -> dict:
