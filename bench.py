@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the headline measurement: masked GrB_mxm on an RMAT graph, semiring GFLOP/s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tri|spgemm|sssp|bfs] [--scale S]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tri|spgemm|spgemm_rmat|sssp|bfs]
   python bench.py --impl reference ...      # the reference's own CPU GrB_mxm, bounded sample
 
 A "step" is one pass of the hot path (one GrB_mxm-equivalent multiply through the C ABI of
@@ -10,27 +10,41 @@ scale-22"): `tri` = C<L> = L*U' over PLUS_TIMES_INT64 on RMAT scale 22, edge fac
 GrB_mxm(C, L, NULL, GxB_PLUS_TIMES_INT64, L, U, desc{INP1=TRAN}) hands to GB_AxB_parallel
 (reference Demo/Source/tricount.c:166-178): M = L, A = U, B = L, do_adotb, flipxy.
 
+  parity : BEFORE any number is printed the GPU's T is compared with the compiled reference
+          (oracle/_ref) on the vectors the cpu_baseline sample computes: identical pointers, pattern
+          and values (integer / bool / MIN / MAX: bit-exact; fp64 PLUS_TIMES: 64 eps in the 1-norm,
+          the reference's own test criterion).  A mismatch exits non-zero with no JSON line.
   value : 2 * madds / t, operands resident in HBM (gb200_AxB_device); t = CUDA-event time of the K
           steps on the library's launching stream (gb200_timer_mark), max over ranks
   e2e   : same metric through gb200_AxB_host + gb200_result_fetch with HOST buffers in page-locked
           memory from gb200_host_malloc (what every GraphBLAS array is after GxB_init with the
           gb200_host_* allocator): H2D of M, A, B and D2H of T inside the timed region
-  roofline : dominant kernel (the semiring kernel: dot_kernel / saxpy_*), algorithmic bytes of
-          SURVEY.md 8(d) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
+  t_api : wall time of the UNMODIFIED reference's GrB_mxm / GrB_mxv / GrB_vxm with
+          libgb_b200_shim.so interposed (GB_AxB_parallel -> GPU), GraphBLAS started with
+          GxB_init (gb200_host_*): the call an application makes (SURVEY.md 8d "Timing window")
+  roofline : dominant kernel (the semiring kernel: dot / saxpy), algorithmic bytes of SURVEY.md
+          8(d) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs; `traffic` = DRAM bytes of
+          the same kernels from the committed ncu capture (profiles/traffic.json)
   cpu_baseline : oracle/_ref (the compiled reference), GrB_mxm / GrB_mxv on a bounded sample of
           the same workload, on rank 0 at N == 1 only.  One call of the reference is sequential
           (Source/GB_AxB_parallel.c:102-103), so the sample is cut into one independent slice of
           output vectors per host core and the slices run concurrently from user threads (the
           reference is thread-safe for that, Demo/Program/pthread_demo.c)
+  secondary : the same {value, roofline, e2e, t_api, parity, cpu_baseline} for the other configs of
+          BASELINE.json on one GPU: unmasked C=A*A (saxpy) on RMAT, SSSP (mxv) and BFS (vxm) at scale 22
 
-N > 1 (torchrun, one rank per GPU): the mask's vectors are split into N flop-balanced contiguous
-slices (the reference's own plan, GB_AxB_parallel.c:52); A and B are replicated; no data-path
-collective; the triangle count is all-reduced over NCCL.  The problem is fixed, so scaling is
-"strong".
+N > 1 (torchrun, one rank per GPU): the mask's entries are split into N owner-aligned parts (the
+reference's own plan, GB_AxB_parallel.c:52); A and B are replicated; no data-path collective; the
+triangle count is all-reduced over NCCL.  The problem is fixed, so scaling is "strong".
+
+`--impl reference` never imports graphblas_b200 (so no product library is mapped into that process)
+and builds its inputs on the CPU with the same counter-based generator.
 """
 from __future__ import annotations
 
 import argparse
+import copy
+import importlib.util
 import json
 import os
 import subprocess
@@ -44,13 +58,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+METRIC = "GrB_mxm semiring GFLOP/s"
+
+
+def pure_containers():
+    """graphblas_b200/containers.py loaded BY PATH: Matrix / Semiring without the package's
+    __init__ (which maps libgb_b200.so).  Used by the reference arm."""
+    name = "gb200_pure_containers"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(
+        name, os.path.join(ROOT, "graphblas_b200", "containers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
 
 # ---------------------------------------------------------------------------------------------
 # inputs
 # ---------------------------------------------------------------------------------------------
 def build_rmat(scale: int, ef: int, device: str, weighted: bool = False):
-    """-> dict of numpy arrays: n, Ap, Aj (symmetric, loop-free, sorted), optional Ax"""
-    import torch
+    """-> dict of torch tensors: n, rows, cols (symmetric, loop-free, sorted), p, optional w"""
     import gen
     n, r, c = gen.rmat_edges(scale, ef, 42, device)
     p = gen.csr_from_sorted(n, r, c)
@@ -62,7 +91,6 @@ def build_rmat(scale: int, ef: int, device: str, weighted: bool = False):
 
 def tri_operands(g, dtype=np.int64):
     """L = tril(A,-1), U = triu(A,1) as host CSR arrays (vectors are rows)"""
-    import torch
     import gen
     n, r, c = g["n"], g["rows"], g["cols"]
     low = c < r
@@ -176,70 +204,74 @@ def algo_bytes(mats, cnvec, cnz, zsize):
     return b
 
 
-def make_workload(args, device):
-    import graphblas_b200 as gb
+def make_workload(C, args, device):
+    """C: the containers module (graphblas_b200 itself, or the pure containers for the reference arm)"""
     w = {}
     if args.workload == "tri":
         g = build_rmat(args.scale, args.ef, device)
         (n, Lp, Li, Lx), (_, Up, Ui, Ux) = tri_operands(g)
-        L = gb.Matrix(n, n, Lp, Li, Lx, None, "INT64")
-        U = gb.Matrix(n, n, Up, Ui, Ux, None, "INT64")
+        L = C.Matrix(n, n, Lp, Li, Lx, None, "INT64")
+        U = C.Matrix(n, n, Up, Ui, Ux, None, "INT64")
         w.update(name=f"GrB_mxm C<L>=L*U' PLUS_TIMES_INT64 (masked dot), RMAT scale {args.scale} "
                       f"edgefactor {args.ef}, n={n}, nnz(L)={L.nnz}",
                  M=L, A=U, B=L, mask_comp=False, do_adotb=True,
-                 semiring=gb.Semiring("PLUS", "TIMES", "INT64", flipxy=True), dtype="int64",
+                 semiring=C.Semiring("PLUS", "TIMES", "INT64", flipxy=True), dtype="int64",
                  slice="M")
     elif args.workload == "spgemm":
         import gen
         n = 1 << args.scale
         A = gen.er(n, n, args.ef * n, 1)
         B = gen.er(n, n, args.ef * n, 2)
-        Am, Bm = gb.Matrix.from_scipy(A, "FP64"), gb.Matrix.from_scipy(B, "FP64")
+        Am, Bm = C.Matrix.from_scipy(A, "FP64"), C.Matrix.from_scipy(B, "FP64")
         # CSR C=A*B: the seam sees A := B_in, B := A_in, flipxy (SURVEY.md 3.2)
         w.update(name=f"GrB_mxm C=A*B PLUS_TIMES_FP64 (saxpy), Erdos-Renyi n=2^{args.scale}, "
                       f"{args.ef} nnz/row",
                  M=None, A=Bm, B=Am, mask_comp=False, do_adotb=False,
-                 semiring=gb.Semiring("PLUS", "TIMES", "FP64", flipxy=True), dtype="f64", slice="B")
+                 semiring=C.Semiring("PLUS", "TIMES", "FP64", flipxy=True), dtype="f64", slice="B")
     elif args.workload == "spgemm_rmat":
-        import gen
         g = build_rmat(args.scale, args.ef, device, weighted=True)
         n = g["n"]
-        Am = gb.Matrix(n, n, g["p"].cpu().numpy(), g["cols"].cpu().numpy(), g["w"].cpu().numpy(), None,
-                       "FP64")
+        Am = C.Matrix(n, n, g["p"].cpu().numpy(), g["cols"].cpu().numpy(), g["w"].cpu().numpy(), None,
+                      "FP64")
         w.update(name=f"GrB_mxm C=A*A PLUS_TIMES_FP64 (saxpy), RMAT scale {args.scale} edgefactor "
                       f"{args.ef}, n={n}, nnz(A)={Am.nnz}",
                  M=None, A=Am, B=Am, mask_comp=False, do_adotb=False,
-                 semiring=gb.Semiring("PLUS", "TIMES", "FP64", flipxy=True), dtype="f64", slice="B")
+                 semiring=C.Semiring("PLUS", "TIMES", "FP64", flipxy=True), dtype="f64", slice="B")
     elif args.workload == "sssp":
         # GrB_mxv (d, NULL, GrB_MIN_FP64, GxB_MIN_PLUS_FP64, A, d, NULL), A CSR: the seam sees
         # A'*B by dot products with B = d (n x 1, all entries present), SURVEY.md 3.5
         g = build_rmat(args.scale, args.ef, device, weighted=True)
         n = g["n"]
-        Am = gb.Matrix(n, n, g["p"].cpu().numpy(), g["cols"].cpu().numpy(), g["w"].cpu().numpy(), None,
-                       "FP64")
+        Am = C.Matrix(n, n, g["p"].cpu().numpy(), g["cols"].cpu().numpy(), g["w"].cpu().numpy(), None,
+                      "FP64")
         src = int(np.argmax(np.diff(Am.p)))
         d = np.full(n, np.inf)
         d[src] = 0.0
-        # a few relaxation rounds on the host side of the harness so that d is a realistic iterate
-        dv = gb.Matrix(n, 1, np.array([0, n]), np.arange(n), d, None, "FP64")
+        dv = C.Matrix(n, 1, np.array([0, n]), np.arange(n), d, None, "FP64")
         w.update(name=f"GrB_mxv d=A min.+ d MIN_PLUS_FP64 (dot, dense vector), RMAT scale {args.scale} "
                       f"edgefactor {args.ef}, n={n}, nnz(A)={Am.nnz}, one Bellman-Ford relaxation",
                  M=None, A=Am, B=dv, mask_comp=False, do_adotb=True,
-                 semiring=gb.Semiring("MIN", "PLUS", "FP64"), dtype="f64", slice="A")
+                 semiring=C.Semiring("MIN", "PLUS", "FP64"), dtype="f64", slice="A")
     elif args.workload == "bfs":
         # bfs5m level loop (Demo/Source/bfs5m.c:71-82): q<!v> = q*A over LOR_LAND_BOOL, A CSR: the
         # seam sees A*B by saxpy with B = q (n x 1), M = v complemented, flipxy (SURVEY.md 3.4)
         g = build_rmat(args.scale, args.ef, device)
         n = g["n"]
-        Am = gb.Matrix(n, n, g["p"].cpu().numpy(), g["cols"].cpu().numpy(),
-                       np.ones(len(g["cols"]), dtype=np.bool_), None, "BOOL")
+        Am = C.Matrix(n, n, g["p"].cpu().numpy(), g["cols"].cpu().numpy(),
+                      np.ones(len(g["cols"]), dtype=np.bool_), None, "BOOL")
         w.update(name=f"BFS level loop GrB_vxm q<!v>=q*A LOR_LAND_BOOL (saxpy, vector), RMAT scale "
                       f"{args.scale} edgefactor {args.ef}, n={n}, nnz(A)={Am.nnz}",
                  M=None, A=Am, B=None, mask_comp=True, do_adotb=(args.bfs_dir == "pull"),
-                 semiring=gb.Semiring("LOR", "LAND", "BOOL", flipxy=True), dtype="bool", slice="none",
+                 semiring=C.Semiring("LOR", "LAND", "BOOL", flipxy=True), dtype="bool", slice="none",
                  bfs_source=int(np.argmax(np.diff(Am.p))))
     else:
         raise SystemExit(f"unknown workload {args.workload}")
+    sr = w["semiring"]
+    w["config"] = {"workload": w["name"], "scale": args.scale, "edgefactor": args.ef,
+                   "semiring": f"{sr.add}_{sr.mult}_{sr.xytype}",
+                   "l2": "inputs larger than L2 (no flush needed)"
+                         if sum(x.nnz for x in (w["A"],) if x is not None) * 12 > 2.6e8
+                         else "inputs smaller than L2"}
     return w
 
 
@@ -263,35 +295,38 @@ def bfs_levels(gb, w, dA):
     return levels
 
 
-def slice_vectors(m, lo, hi):
+def slice_vectors(C, m, lo, hi):
     """keep vectors [lo,hi) of a standard-form matrix, same dimensions (others become empty)"""
-    import graphblas_b200 as gb
     p = np.zeros(len(m.p), dtype=np.int64)
     s, e = m.p[lo], m.p[hi]
     p[lo:hi + 1] = m.p[lo:hi + 1] - s
     p[hi + 1:] = e - s
-    return gb.Matrix(m.vlen, m.vdim, p, m.i[s:e], m.x[s:e], None, m.type)
+    return C.Matrix(m.vlen, m.vdim, p, m.i[s:e], m.x[s:e], None, m.type)
 
 
 # ---------------------------------------------------------------------------------------------
-# the reference arm / CPU baseline: the compiled reference through its public API
+# the reference's public API on the workload: cpu_baseline / reference arm (shim off) and
+# t_api (shim on)
 # ---------------------------------------------------------------------------------------------
 def _interleaved_parts(m, stride, nparts):
     """Every `stride`-th vector of m, dealt round-robin to `nparts` slices.  Each slice keeps the
-    dimensions of m (the other vectors are empty).  -> list of (p, i, x), kept-vector count"""
+    dimensions of m (the other vectors are empty).  -> list of (p, i, x), list of kept-vector masks"""
     nvec = m.nvec
+    if stride == 1 and nparts == 1:
+        return [(m.p, m.i, m.x)], [np.ones(nvec, dtype=bool)]
     cnt = np.diff(m.p)
     v = np.arange(nvec)
     sampled = (v % stride) == 0
     owner = (v // stride) % nparts
-    parts = []
+    parts, keeps = [], []
     for t in range(nparts):
         keep = sampled & (owner == t)
         cnt2 = np.where(keep, cnt, 0)
         p2 = np.concatenate([[0], np.cumsum(cnt2)])
         sel = np.repeat(keep, cnt)
         parts.append((p2, m.i[sel], m.x[sel]))
-    return parts, int(sampled.sum())
+        keeps.append(keep)
+    return parts, keeps
 
 
 def host_bfs_levels(A, src):
@@ -315,84 +350,104 @@ def host_bfs_levels(A, src):
     return out
 
 
-def reference_sample(args, w):
-    """The reference's CPU path through its public API on a bounded sample of the workload, the
-    sample cut into one slice of output vectors per host thread.
-    -> (gflops, seconds, madds, description, threads)"""
-    import grbref
+def api_run(G, wl, w, stride, T, keep=False, reps=1):
+    """The workload through the reference library's PUBLIC API (GrB_mxm / GrB_mxv / GrB_vxm) on every
+    `stride`-th output vector, cut into T slices that run concurrently on T user threads.  With the
+    shim off this is the reference's CPU path (cpu_baseline, reference arm); with the shim on and
+    stride = T = 1 it is the call an application makes, landing on the GPU (t_api).
+    -> dict(seconds (best of reps), madds, desc, threads, outputs (keep=True: what the calls
+    returned, exported, with the kept-vector masks))"""
     from concurrent.futures import ThreadPoolExecutor
-    G = grbref.GraphBLAS.get(with_shim=False)
-    T = max(1, args.cpu_threads or (os.cpu_count() or 1))
-    stride = args.cpu_stride
-    wl = args.workload
-    sr_name = "GxB_" + "_".join((w["semiring"].add, w["semiring"].mult, w["semiring"].xytype))
-    tname = w["semiring"].xytype
+    import grbref
+    sr = w["semiring"]
+    sr_name = "GxB_" + "_".join((sr.add, sr.mult, sr.xytype))
+    tname = sr.xytype
     handles, vhandles = [], []
-
+    outputs = None
     if wl == "tri":
         # user-level call: C<Ls> = L*U', CSR, desc INP1 = TRAN (Demo/Source/tricount.c:166-178)
         L, U = w["B"], w["A"]
         n = L.vdim
-        parts, nkept = _interleaved_parts(L, stride, T)
+        parts, keeps = _interleaved_parts(L, stride, T)
         l = G.matrix_import("CSR", tname, n, n, L.p, L.i, L.x)
         u = G.matrix_import("CSR", tname, n, n, U.p, U.i, U.x)
-        ms = [G.matrix_import("CSR", tname, n, n, *pt) for pt in parts]
-        cs = [G.matrix_new(tname, n, n) for _ in parts]
+        ms = [l] if (stride == 1 and T == 1) else [G.matrix_import("CSR", tname, n, n, *pt) for pt in parts]
         d = G.descriptor(inp1=grbref.GrB_TRAN)
-        handles = [l, u] + ms + cs
+        handles = [l, u] + (ms if ms[0] is not l else [])
+        cs = []
+
+        def prepare():
+            cs[:] = [G.matrix_new(tname, n, n) for _ in parts]
 
         def run(t):
             G.mxm(cs[t], ms[t], None, sr_name, l, u, d)
             G.matrix_nvals(cs[t])
         madds_of = lambda: sum(G.reduce_int64(c) for c in cs)      # values are 0/1: sum = matches
-        what = f"every {stride}th vector of the mask L ({nkept} of {L.nvec})"
+        what = f"every {stride}th vector of the mask L ({int(sum(k.sum() for k in keeps))} of {L.nvec})"
         call = "GrB_mxm"
+        export = lambda: [G.matrix_export(c, "CSR") for c in cs]
+        release = lambda: [G.matrix_free(c) for c in cs]
     elif wl in ("spgemm", "spgemm_rmat"):
         # user-level call: C = As*B, CSR
         Ain, Bin = w["B"], w["A"]
-        parts, nkept = _interleaved_parts(Ain, stride, T)
+        parts, keeps = _interleaved_parts(Ain, stride, T)
         b = G.matrix_import("CSR", tname, Bin.vdim, Bin.vlen, Bin.p, Bin.i, Bin.x)
         As = [G.matrix_import("CSR", tname, Ain.vdim, Ain.vlen, *pt) for pt in parts]
-        cs = [G.matrix_new(tname, Ain.vdim, Bin.vlen) for _ in parts]
-        handles = [b] + As + cs
+        handles = [b] + As
         lenB = np.diff(Bin.p)
+        cs = []
+
+        def prepare():
+            cs[:] = [G.matrix_new(tname, Ain.vdim, Bin.vlen) for _ in parts]
 
         def run(t):
             G.mxm(cs[t], None, None, sr_name, As[t], b, None)
             G.matrix_nvals(cs[t])
         madds_of = lambda: int(sum(int(lenB[pt[1]].sum()) for pt in parts))
-        what = f"every {stride}th row of A ({nkept} of {Ain.nvec})"
+        what = f"every {stride}th row of A ({int(sum(k.sum() for k in keeps))} of {Ain.nvec})"
         call = "GrB_mxm"
+        export = lambda: [G.matrix_export(c, "CSR") for c in cs]
+        release = lambda: [G.matrix_free(c) for c in cs]
     elif wl == "sssp":
         # user-level call: w = As min.+ d (GrB_mxv, A CSR): rows of A are independent outputs
         Am, dv = w["A"], w["B"]
         n = Am.vdim
-        parts, nkept = _interleaved_parts(Am, stride, T)
+        parts, keeps = _interleaved_parts(Am, stride, T)
         As = [G.matrix_import("CSR", tname, n, n, *pt) for pt in parts]
         dd = G.vector_import(tname, n, dv.i, dv.x)
-        ws = [G.vector_new(tname, n) for _ in parts]
-        handles, vhandles = As, [dd] + ws
+        handles, vhandles = As, [dd]
+        ws = []
+
+        def prepare():
+            ws[:] = [G.vector_new(tname, n) for _ in parts]
 
         def run(t):
             G.mxv(ws[t], None, None, sr_name, As[t], dd, None)
             G.vector_nvals(ws[t])
         madds_of = lambda: int(sum(len(pt[1]) for pt in parts))     # d is dense: every entry matches
-        what = f"every {stride}th row of A ({nkept} of {Am.nvec})"
+        what = f"every {stride}th row of A ({int(sum(k.sum() for k in keeps))} of {Am.nvec})"
         call = "GrB_mxv"
+        export = lambda: [G.vector_export(x) for x in ws]
+        release = lambda: [G.vector_free(x) for x in ws]
     else:
         # bfs: the level loop q<!v> = q*A (GrB_vxm, REPLACE, SCMP); one frontier vector cannot be
         # sliced by the caller, so this leg is one thread
         T = 1
         Am = w["A"]
         n = Am.vdim
-        levels = host_bfs_levels(Am, w["bfs_source"])
+        levels = w.get("host_levels") or host_bfs_levels(Am, w["bfs_source"])
+        w["host_levels"] = levels
+        keeps = None
         a = G.matrix_import("CSR", tname, n, n, Am.p, Am.i, Am.x)
         qs = [G.vector_import(tname, n, q, np.ones(len(q), np.bool_)) for q, _ in levels]
         vs = [G.vector_import(tname, n, v, np.ones(len(v), np.bool_)) for _, v in levels]
-        ws = [G.vector_new(tname, n) for _ in levels]
         d = G.descriptor(outp=grbref.GrB_REPLACE, mask=grbref.GrB_SCMP)
-        handles, vhandles = [a], qs + vs + ws
+        handles, vhandles = [a], qs + vs
         lenA = np.diff(Am.p)
+        ws = []
+
+        def prepare():
+            ws[:] = [G.vector_new(tname, n) for _ in levels]
 
         def run(t):
             for q, v, wv in zip(qs, vs, ws):
@@ -401,15 +456,27 @@ def reference_sample(args, w):
         madds_of = lambda: int(sum(int(lenA[q].sum()) for q, _ in levels))
         what = f"all {len(levels)} levels"
         call = "GrB_vxm"
+        export = lambda: [G.vector_export(x) for x in ws]
+        release = lambda: [G.vector_free(x) for x in ws]
 
-    t0 = time.perf_counter()
-    if T == 1:
-        run(0)
-    else:
-        with ThreadPoolExecutor(T) as ex:
-            list(ex.map(run, range(T)))
-    dt = time.perf_counter() - t0
+    best = None
+    for rep in range(reps):
+        prepare()
+        t0 = time.perf_counter()
+        if T == 1:
+            run(0)
+        else:
+            with ThreadPoolExecutor(T) as ex:
+                list(ex.map(run, range(T)))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        if rep + 1 < reps:
+            release()
     madds = madds_of()
+    if keep:
+        outputs = {"parts": export(), "keeps": keeps}      # export is destructive: frees the outputs
+    else:
+        release()
     for h in handles:
         G.matrix_free(h)
     for h in vhandles:
@@ -417,92 +484,110 @@ def reference_sample(args, w):
     desc = (f"{what}, cut into {T} slices of output vectors, one {call} per slice on {T} concurrent "
             f"user threads of {os.cpu_count()} host cores (a single reference call is sequential: "
             f"Source/GB_AxB_parallel.c:102-103)")
-    return 2.0 * madds / dt / 1e9, dt, madds, desc, T
+    return {"seconds": best, "madds": madds, "gflops": 2.0 * madds / best / 1e9, "desc": desc,
+            "threads": T, "outputs": outputs}
+
+
+def pick_stride(wl, madds_total, T, seconds=12.0):
+    """sample every n-th output vector so that the reference's CPU leg takes about `seconds`:
+    measured rates of the reference on one host thread, madds/s (profiles/r1)"""
+    rate = {"tri": 6.0e6, "spgemm": 2.0e7, "spgemm_rmat": 3.0e7, "sssp": 8.0e7, "bfs": 1e12}[wl]
+    return int(max(1, np.ceil(madds_total / (rate * T * seconds))))
+
+
+def _rows_of(p, i, x, keep):
+    """entries of the kept vectors of a CSR-like triple, in order -> (counts, i, x)"""
+    cnt = np.diff(p)
+    sel = np.repeat(keep, cnt)
+    return cnt[keep], i[sel], x[sel]
+
+
+def parity_check(wl, w, sample, gpu_T):
+    """The vectors the reference computed (sample['outputs']) against the same vectors of the GPU's T.
+    gpu_T: a Matrix (tri / spgemm / sssp) or the list of per-level index arrays (bfs).
+    Integer / bool / MIN-PLUS: identical.  fp64 PLUS_TIMES: identical pattern, values within 64 eps in
+    the 1-norm (Test/GB_spec_compare.m:18-24).  -> the `parity` object of the JSON line"""
+    out = {"against": "oracle/_ref (the compiled reference) through GrB_mxm/mxv/vxm on the "
+                      "cpu_baseline sample", "checked_vectors": 0, "checked_entries": 0,
+           "identical": True, "criterion": "bit-exact pointers, pattern, values"}
+    fp_plus = (w["semiring"].add in ("PLUS", "TIMES") and w["semiring"].xytype in ("FP32", "FP64"))
+    if fp_plus:
+        out["criterion"] = "identical pointers and pattern; values: |ref-got|_1 <= 64 eps |ref|_1"
+    parts, keeps = sample["outputs"]["parts"], sample["outputs"]["keeps"]
+    num = den = 0.0
+
+    def fail(msg):
+        out["identical"] = False
+        out["first_difference"] = msg
+
+    if wl in ("tri", "spgemm", "spgemm_rmat"):
+        for ex, keep in zip(parts, keeps):
+            rc, ri, rx = _rows_of(ex["Ap"], ex["Ai"], ex["Ax"], keep)
+            gc, gi, gx = _rows_of(gpu_T.p, gpu_T.i, gpu_T.x, keep)
+            out["checked_vectors"] += int(keep.sum())
+            out["checked_entries"] += int(rc.sum())
+            if int(np.diff(ex["Ap"])[~keep].sum()) != 0:
+                return fail("the reference wrote outside the sampled vectors") or out
+            if not np.array_equal(rc, gc):
+                return fail("vector lengths differ") or out
+            if not np.array_equal(ri, gi):
+                return fail("patterns differ") or out
+            if fp_plus:
+                if not np.array_equal(np.isnan(rx), np.isnan(gx)) or \
+                        not np.array_equal(rx[np.isinf(rx)], gx[np.isinf(rx)]):
+                    return fail("NaN / Inf placement differs") or out
+                fin = np.isfinite(rx)
+                num += float(np.abs(rx[fin] - gx[fin]).sum())
+                den += float(np.abs(rx[fin]).sum())
+            elif not np.array_equal(rx, gx):
+                return fail("values differ") or out
+    elif wl == "sssp":
+        gmap = np.full(gpu_T.vlen, -1, dtype=np.int64)
+        gmap[gpu_T.i] = np.arange(gpu_T.nnz)
+        for ex, keep in zip(parts, keeps):
+            vi, vx = ex["vi"], ex["vx"]
+            order = np.argsort(vi, kind="stable")
+            vi, vx = vi[order], vx[order]
+            want = np.nonzero(keep & (gmap >= 0))[0]
+            out["checked_vectors"] += int(keep.sum())
+            out["checked_entries"] += len(vi)
+            if not np.array_equal(vi, want):
+                return fail("pattern of w differs") or out
+            if not np.array_equal(vx.view(np.uint64), gpu_T.x[gmap[vi]].view(np.uint64)):
+                return fail("values of w differ") or out
+    else:
+        for lvl, (ex, got) in enumerate(zip(parts, gpu_T)):
+            vi = np.sort(ex["vi"])
+            out["checked_vectors"] += 1
+            out["checked_entries"] += len(vi)
+            if not np.array_equal(vi, np.sort(got)):
+                return fail(f"frontier of level {lvl} differs") or out
+            if not ex["vx"].all():
+                return fail(f"level {lvl}: a false value in the reference's w") or out
+        if len(parts) != len(gpu_T):
+            return fail("number of levels differs") or out
+    if fp_plus:
+        out["rel_err_1norm"] = num / den if den > 0 else 0.0
+        out["tolerance"] = 64 * float(np.finfo(np.float64).eps)
+        if den > 0 and num > out["tolerance"] * den:
+            fail("values outside 64 eps in the 1-norm")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="tri",
-                    choices=["tri", "spgemm", "spgemm_rmat", "sssp", "bfs"])
-    ap.add_argument("--bfs-dir", default="push", choices=["push", "pull"])
-    ap.add_argument("--scale", type=int, default=22)
-    ap.add_argument("--ef", type=int, default=16)
-    ap.add_argument("--cpu-stride", type=int, default=0, help="sample every n-th output vector "
-                    "(0: workload default)")
-    ap.add_argument("--cpu-threads", type=int, default=0, help="0: all host cores")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
-    ap.add_argument("--slice-of", type=int, default=0, help="one GPU: run the slice --slice-rank of a "
-                    "K-way partition (what one rank of --gpus K computes), for profiling")
-    ap.add_argument("--slice-rank", type=int, default=0)
-    ap.add_argument("--calibrate", type=int, default=2, help="N > 1, masked dot: rounds of measured "
-                    "re-balancing of the ranks' parts before the timed region")
-    args = ap.parse_args()
-    if args.workload == "spgemm" and args.scale == 22 and "--scale" not in " ".join(sys.argv):
-        args.scale, args.ef = 20, 8
-    if args.cpu_stride <= 0:
-        args.cpu_stride = {"tri": 4, "spgemm": 1, "spgemm_rmat": 8, "sssp": 1, "bfs": 1}[args.workload]
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-
+# our arm: one workload on this process' GPU (rank of world)
+# ---------------------------------------------------------------------------------------------
+def measure(args, env, primary=True):
     import torch
-    have_cuda = torch.cuda.is_available()
-    device = f"cuda:{local_rank}" if have_cuda else "cpu"
-
-    # ---- reference arm: rank 0 only, CPU ------------------------------------------------------
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        import graphblas_b200  # noqa: F401  (Matrix container only; no device call is made)
-        w = make_workload(args, device)
-        vals = []
-        for s in range(args.warmup + args.steps):
-            gf, dt, madds, desc, threads = reference_sample(args, w)
-            if s >= args.warmup:
-                vals.append((gf, dt))
-            if s == 0 and args.workload not in ("bfs",):
-                # keep the whole run within a few minutes whatever K and W are: thin the sample
-                total = dt * (args.warmup + args.steps)
-                if total > 150.0:
-                    args.cpu_stride *= int(np.ceil(total / 150.0))
-        gf = float(np.mean([v[0] for v in vals]))
-        dt = float(np.mean([v[1] for v in vals]))
-        line = {"impl": "reference", "metric": "GrB_mxm semiring GFLOP/s", "value": gf,
-                "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-                "config": {"workload": w["name"]},
-                "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": threads,
-                                 "kind": "reference", "sample": desc},
-                "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return
-
-    # ---- our arm ----------------------------------------------------------------------------
-    if not have_cuda:
-        raise SystemExit("bench.py needs a GPU (there is no CPU path); use --impl reference for "
-                         "the CPU arm")
     import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(device))
-    os.environ["GB200_DEVICE"] = str(local_rank)
     import graphblas_b200 as gb
-    gb.init(local_rank)
-
-    w = make_workload(args, device)
+    rank, world, local_rank, device = env["rank"], env["world"], env["local_rank"], env["device"]
+    w = make_workload(gb, args, device)
     torch.cuda.empty_cache()
     A, B, M = w["A"], w["B"], w["M"]
     sliced_name = w["slice"]
     dA = gb.DMatrix(A)
+    do_cpu = (world == 1 and not args.no_cpu and rank == 0)
 
     # ---- the multiplies of one step: (M, A, B) host triples + their resident handles ------------
     if args.workload == "bfs":
@@ -512,6 +597,7 @@ def main():
         levels = bfs_levels(gb, w, dA)
         calls = [(vm, A, qm, gb.DMatrix(vm), dA, gb.DMatrix(qm)) for qm, vm in levels]
         w["name"] += f", {len(levels)} levels from vertex {w['bfs_source']}"
+        w["config"]["workload"] = w["name"]
     else:
         dB = dA if B is A else gb.DMatrix(B)
         dM = None
@@ -556,12 +642,11 @@ def main():
                     op.rebalance(times)
                 w["calibration_ms"] = calib
                 mine = op.mask(srank)
-                (lo, hi), _ = op.ranges(srank)
                 bounds = None
             else:
                 bounds = gb.partition_by_flops(cum, nslices)
                 lo, hi = int(bounds[srank]), int(bounds[srank + 1])
-                mine = slice_vectors(sliced, lo, hi)
+                mine = slice_vectors(gb, sliced, lo, hi)
             dmine = gb.DMatrix(mine)
             if sliced_name == "M":
                 M, dM = mine, dmine
@@ -570,6 +655,48 @@ def main():
             else:
                 B, dB = mine, dmine
         calls = [(M, A, B, dM, dA, dB)]
+
+    # ---- parity gate (one GPU): the reference on a bounded sample, the GPU's T on the same vectors
+    parity = cpu = None
+    G = None
+    if do_cpu or (world == 1 and not args.no_api and rank == 0):
+        import grbref
+        try:
+            G = grbref.GraphBLAS.get(with_shim=True, pinned=True)
+            G.use_gpu(False)
+        except Exception as e:          # the reference .so is test infrastructure; say so if absent
+            G = None
+            cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference",
+                   "sample": f"unavailable: {e}"}
+    if do_cpu and G is not None:
+        T = max(1, args.cpu_threads or (os.cpu_count() or 1))
+        first = gb.axb_device(calls[0][3], w["mask_comp"], calls[0][4], calls[0][5], w["semiring"],
+                              w["do_adotb"], fetch=(args.workload != "bfs"))
+        if args.workload == "bfs":
+            madds_total = int(sum(int(np.diff(A.p)[qm.i].sum()) for qm, _ in levels))
+            gpu_T = []
+            for (vm, _, qm, dvm, da, dqm) in calls:
+                r = gb.axb_device(dvm, True, da, dqm, w["semiring"], w["do_adotb"])
+                t = r.matrix.i
+                if not r.info["mask_applied"]:
+                    vis = np.zeros(A.vlen, dtype=bool)
+                    vis[vm.i] = True
+                    t = t[~vis[t]]
+                gpu_T.append(t)
+            w["host_levels"] = [(qm.i, vm.i) for qm, vm in levels]
+        else:
+            madds_total = first.info["flops"]
+            gpu_T = first.matrix
+        stride = args.cpu_stride if args.cpu_stride > 0 else pick_stride(args.workload, madds_total, T)
+        sample = api_run(G, args.workload, w, stride, T, keep=True)
+        parity = parity_check(args.workload, w, sample, gpu_T)
+        cpu = {"value": sample["gflops"], "unit": "GFLOP/s", "cores": sample["threads"],
+               "kind": "reference", "sample": sample["desc"], "seconds": sample["seconds"],
+               "host_cores_present": os.cpu_count()}
+        del sample, gpu_T, first
+        if not parity["identical"]:
+            sys.stderr.write(f"PARITY GATE FAILED ({args.workload}): {json.dumps(parity)}\n")
+            sys.exit(3)
 
     # host operands of the end-to-end leg live in page-locked memory (gb200_host_malloc)
     pinned = {}
@@ -770,13 +897,13 @@ def main():
         # gb200_AxB_host is made of (upload, multiply on resident operands, fetch), each synchronous
         brk = {"upload_ms": 0.0, "multiply_ms": 0.0, "fetch_ms": 0.0}
         if args.workload != "bfs" and world == 1:
+            import ctypes as _C
             for (m, a, b) in hcalls:
                 t1 = time.perf_counter()
                 ha = gb.DMatrix(a)
                 hb = ha if b is a else gb.DMatrix(b)
                 hm = None if m is None else (ha if m is a else (hb if m is b else gb.DMatrix(m)))
                 t2 = time.perf_counter()
-                import ctypes as _C
                 rhd = _C.c_void_p()
                 sc = w["semiring"].c()
                 gb._check(gb.lib.gb200_AxB_device(_C.byref(rhd), hm._h if hm is not None else None,
@@ -790,6 +917,31 @@ def main():
                 brk["upload_ms"] += (t2 - t1) * 1e3
                 brk["multiply_ms"] += (t3 - t2) * 1e3
                 brk["fetch_ms"] += (t4 - t3) * 1e3
+    pinned.clear()
+    hcalls = hfull = []
+
+    # ---- t_api: the unmodified reference's GrB_mxm / mxv / vxm with the shim interposed --------
+    api = None
+    if G is not None and world == 1 and rank == 0 and not args.no_api:
+        try:
+            before = G.shim_stats()
+            G.use_gpu(True)
+            api_run(G, args.workload, w, 1, 1, keep=False, reps=1)          # warm-up call
+            res = api_run(G, args.workload, w, 1, 1, keep=False, reps=2)
+            after = G.shim_stats()
+            api = {"ms": res["seconds"] * 1e3, "value": 2.0 * madds / res["seconds"] / 1e9,
+                   "unit": "GFLOP/s",
+                   "call": {"tri": "GrB_mxm", "spgemm": "GrB_mxm", "spgemm_rmat": "GrB_mxm",
+                            "sssp": "GrB_mxv", "bfs": "GrB_vxm x levels"}[args.workload],
+                   "through": "unmodified reference library (oracle/_ref) + libgb_b200_shim.so "
+                              "(GB_AxB_parallel interposed), GxB_init with gb200_host_* (page-locked "
+                              "GraphBLAS arrays); wall clock of the call, best of 2",
+                   "gpu_calls": after["gpu_calls"] - before["gpu_calls"],
+                   "declined": after["declined"] - before["declined"]}
+        except Exception as e:
+            api = {"ms": None, "error": repr(e)}
+        finally:
+            G.use_gpu(False)
 
     # ---- roofline of the dominant (semiring) kernels, rank 0's slice --------------------------
     peak, peak_src = measured_peak()
@@ -805,17 +957,16 @@ def main():
     except Exception:
         pass
 
+    line = None
     if rank == 0:
-        line = {"metric": "GrB_mxm semiring GFLOP/s", "value": gflops, "unit": "GFLOP/s",
+        line = {"metric": METRIC, "value": gflops, "unit": "GFLOP/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-                "config": {"workload": w["name"], "madds_per_step": madds, "nnz_T": cnz,
-                           "multiplies_per_step": len(calls),
+                "config": w["config"],
+                "detail": {"madds_per_step": madds, "nnz_T": cnz, "multiplies_per_step": len(calls),
                            "timing": "CUDA events on the library's launching stream around the K "
                                      "steps, max over ranks; wall clock alongside",
-                           "l2": "inputs larger than L2 (no flush needed)" if ab > 2.6e8 else
-                                 "inputs smaller than L2",
                            "partition": "none (one GPU)" if world == 1 else
                                         (f"{world} parts of the mask's entries by owner vector (B(:,j) with j in "
                                          "the rank's range, or A(:,i) with i in it), balanced by walk length"
@@ -826,6 +977,7 @@ def main():
                            "exchange": ("NCCL all-gather of the slices of w every step, "
                                         f"{exchange['bytes']} B gathered per rank") if exchange else
                                        "none (independent output vectors; scalars all-reduced)"},
+                "parity": parity,
                 "wall_ms_per_step": tt[1].item() / args.steps * 1e3,
                 "rank_ms_per_step": [round(v, 3) for v in rank_ms],
                 "device_ms_per_step": float(np.mean(dev_ms)),
@@ -838,24 +990,155 @@ def main():
                         "host_memory": "page-locked (gb200_host_malloc)", "breakdown": brk,
                         "upload": "1/N of every replicated operand per rank over PCIe + NCCL "
                                   "all-gather over NVLink" if world > 1 else "host to device over PCIe"},
+                "t_api": api,
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
                              **({"traffic_note": traffic_note} if traffic_note else {}),
+                             **({"traffic_over_algorithmic": traffic / ab} if traffic else {}),
                              "kernel": w.get("kernel", "dotg_kernel/dot_kernel" if w["do_adotb"]
                                              else "saxpy_*_kernel"),
                              "kernel_ms": k_ms, "algorithmic_bytes": int(ab), "peak_source": peak_src,
                              "bytes_per_madd": ab / max(r["flops"], 1),
                              "step_algo_gbs": ab / (float(np.mean(dev_ms)) * 1e-3) / 1e9}}
-        if world == 1 and not args.no_cpu:
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+    # release the resident operands before the next workload
+    for c in calls:
+        for dx in c[3:]:
+            if dx is not None:
+                dx.free()
+    del calls
+    torch.cuda.empty_cache()
+    return line
+
+
+# the other configs of BASELINE.json, one GPU, after the headline line
+SECONDARY = [
+    {"workload": "spgemm_rmat", "scale": 18, "ef": 16},      # unmasked C=A*A (cfg 5, one GPU's worth)
+    {"workload": "sssp", "scale": 22, "ef": 16},             # cfg 4
+    {"workload": "bfs", "scale": 22, "ef": 16},              # cfg 3
+]
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference arm: the compiled reference on the box's host cores, nothing of ours mapped
+# ---------------------------------------------------------------------------------------------
+def reference_arm(args):
+    import grbref
+    C = pure_containers()
+    w = make_workload(C, args, "cpu")
+    G = grbref.GraphBLAS.get(with_shim=False)
+    T = max(1, args.cpu_threads or (os.cpu_count() or 1))
+    # the madds of the whole workload are not known without running it: use the measured figure of
+    # the default graph to bound the sample, and thin it further after the first step if needed
+    if args.cpu_stride <= 0:
+        args.cpu_stride = {"tri": 4, "spgemm": 1, "spgemm_rmat": 8, "sssp": 1, "bfs": 1}[args.workload]
+    vals = []
+    for s in range(args.warmup + args.steps):
+        res = api_run(G, args.workload, w, args.cpu_stride, T)
+        if s >= args.warmup:
+            vals.append((res["gflops"], res["seconds"]))
+        if s == 0 and args.workload not in ("bfs",):
+            # keep the whole run within a few minutes whatever K and W are: thin the sample
+            total = res["seconds"] * (args.warmup + args.steps)
+            if total > 150.0:
+                args.cpu_stride *= int(np.ceil(total / 150.0))
+    gf = float(np.mean([v[0] for v in vals]))
+    dt = float(np.mean([v[1] for v in vals]))
+    line = {"impl": "reference", "metric": METRIC, "value": gf,
+            "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+            "config": w["config"],
+            "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": res["threads"],
+                             "kind": "reference", "sample": res["desc"]},
+            "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "loaded_product_library": any("libgb_b200" in ln for ln in open("/proc/self/maps"))}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="tri",
+                    choices=["tri", "spgemm", "spgemm_rmat", "sssp", "bfs"])
+    ap.add_argument("--bfs-dir", default="push", choices=["push", "pull"])
+    ap.add_argument("--scale", type=int, default=22)
+    ap.add_argument("--ef", type=int, default=16)
+    ap.add_argument("--cpu-stride", type=int, default=0, help="sample every n-th output vector "
+                    "(0: sized for about 12 s of CPU work)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="0: all host cores")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the parity gate")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-api", action="store_true", help="skip the t_api leg")
+    ap.add_argument("--no-secondary", action="store_true", help="only the headline workload")
+    ap.add_argument("--secondary-scale", type=int, default=0, help="run the secondary workloads at "
+                    "this scale instead of their own (quick checks)")
+    ap.add_argument("--slice-of", type=int, default=0, help="one GPU: run the slice --slice-rank of a "
+                    "K-way partition (what one rank of --gpus K computes), for profiling")
+    ap.add_argument("--slice-rank", type=int, default=0)
+    ap.add_argument("--calibrate", type=int, default=2, help="N > 1, masked dot: rounds of measured "
+                    "re-balancing of the ranks' parts before the timed region")
+    args = ap.parse_args()
+    explicit = " ".join(sys.argv[1:])
+    if args.workload == "spgemm" and "--scale" not in explicit:
+        args.scale, args.ef = 20, 8
+    if args.workload == "spgemm_rmat" and "--scale" not in explicit:
+        args.scale = 18
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # ---- reference arm: rank 0 only, CPU, no product library ------------------------------------
+    if args.impl == "reference":
+        if rank == 0:
+            reference_arm(args)
+        return
+
+    # ---- our arm ----------------------------------------------------------------------------
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU path); use --impl reference for "
+                         "the CPU arm")
+    import torch.distributed as dist
+    device = f"cuda:{local_rank}"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    os.environ["GB200_DEVICE"] = str(local_rank)
+    import graphblas_b200 as gb
+    gb.init(local_rank)
+    env = {"rank": rank, "world": world, "local_rank": local_rank, "device": device}
+
+    line = measure(args, env)
+    default_line = (args.workload == "tri" and args.slice_of <= 1)
+    if world == 1 and default_line and not args.no_secondary:
+        sec = []
+        for cfg in SECONDARY:
+            a2 = copy.copy(args)
+            a2.workload, a2.scale, a2.ef = cfg["workload"], cfg["scale"], cfg["ef"]
+            if args.secondary_scale > 0:
+                a2.scale = min(a2.scale, args.secondary_scale)
+            a2.cpu_stride = 0
+            a2.steps, a2.warmup = max(3, min(args.steps, 5)), 3
             try:
-                gf, dt, cm, desc, threads = reference_sample(args, w)
-                line["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": threads,
-                                        "kind": "reference", "sample": desc, "seconds": dt,
-                                        "host_cores_present": os.cpu_count()}
-            except Exception as e:  # the reference .so is test infrastructure; say so if absent
-                line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": 0,
-                                        "kind": "reference", "sample": f"unavailable: {e}"}
+                l2 = measure(a2, env, primary=False)
+                keep = ("value", "unit", "ms_per_step", "dtype", "config", "detail", "parity", "e2e",
+                        "t_api", "roofline", "cpu_baseline", "gpu_launches", "device_ms_per_step")
+                sec.append({k: l2[k] for k in keep if k in l2})
+            except SystemExit:
+                raise
+            except Exception as e:      # a secondary line must not take the headline down
+                sec.append({"config": cfg, "error": repr(e)})
+        line["secondary"] = sec
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -28,24 +28,9 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
 
-# ---- codes (identical to the reference's GB_Type_code / GB_Opcode, Source/GB.h:450-550) ----------
-TYPES = {
-    "BOOL": (0, np.bool_), "INT8": (1, np.int8), "UINT8": (2, np.uint8), "INT16": (3, np.int16),
-    "UINT16": (4, np.uint16), "INT32": (5, np.int32), "UINT32": (6, np.uint32),
-    "INT64": (7, np.int64), "UINT64": (8, np.uint64), "FP32": (9, np.float32),
-    "FP64": (10, np.float64),
-}
-TYPE_BY_CODE = {v[0]: (k, v[1]) for k, v in TYPES.items()}
-OPCODES = {
-    "FIRST": 7, "SECOND": 8, "MIN": 9, "MAX": 10, "PLUS": 11, "MINUS": 12, "TIMES": 13, "DIV": 14,
-    "ISEQ": 15, "ISNE": 16, "ISGT": 17, "ISLT": 18, "ISGE": 19, "ISLE": 20,
-    "LOR": 21, "LAND": 22, "LXOR": 23, "EQ": 24, "NE": 25, "GT": 26, "LT": 27, "GE": 28, "LE": 29,
-}
-COMPARE_OPS = ("EQ", "NE", "GT", "LT", "GE", "LE")
-METHOD_DEFAULT, METHOD_GUSTAVSON, METHOD_HEAP, METHOD_DOT = 0, 1001, 1002, 1003
-
-STATUS = {0: "SUCCESS", 1: "OUT_OF_MEMORY", 2: "NOT_SUPPORTED", 3: "INVALID", 4: "NO_DEVICE",
-          5: "CUDA_ERROR"}
+from .containers import (TYPES, TYPE_BY_CODE, OPCODES, COMPARE_OPS, METHOD_DEFAULT,  # noqa: F401
+                         METHOD_GUSTAVSON, METHOD_HEAP, METHOD_DOT, STATUS, _CMatrix, _CSemiring,
+                         Semiring, Matrix)
 
 
 class GB200Error(RuntimeError):
@@ -55,17 +40,6 @@ class GB200Error(RuntimeError):
         super().__init__(f"{where}: GB200_{STATUS.get(code, code)}: {msg}")
 
 
-class _CMatrix(C.Structure):
-    _fields_ = [("vlen", C.c_int64), ("vdim", C.c_int64), ("nvec", C.c_int64),
-                ("p", C.c_void_p), ("h", C.c_void_p), ("i", C.c_void_p), ("x", C.c_void_p),
-                ("type_code", C.c_int32), ("reserved", C.c_int32)]
-
-
-class _CSemiring(C.Structure):
-    _fields_ = [("add_opcode", C.c_int32), ("mult_opcode", C.c_int32), ("xy_code", C.c_int32),
-                ("z_code", C.c_int32), ("flipxy", C.c_int32)]
-
-
 class _CInfo(C.Structure):
     _fields_ = [("vlen", C.c_int64), ("vdim", C.c_int64), ("nvec", C.c_int64),
                 ("nvec_nonempty", C.c_int64), ("nnz", C.c_int64), ("is_hyper", C.c_int32),
@@ -73,21 +47,40 @@ class _CInfo(C.Structure):
                 ("flops", C.c_int64), ("device_ms", C.c_double), ("kernel_ms", C.c_double)]
 
 
-lib.gb200_last_error.restype = C.c_char_p
-lib.gb200_version.restype = C.c_char_p
-lib.gb200_kernel_launches.restype = C.c_int64
-lib.gb200_multiplies.restype = C.c_int64
-for _name in ("gb200_init", "gb200_finalize", "gb200_upload", "gb200_upload_from_device", "gb200_dmatrix_free",
-              "gb200_AxB_device", "gb200_AxB_host", "gb200_result_get_info", "gb200_result_fetch",
-              "gb200_result_free", "gb200_flopcount_device", "gb200_partition_by_flops",
-              "gb200_semiring_canonical", "gb200_device_count", "gb200_timer_mark",
-              "gb200_timer_elapsed_ms"):
-    getattr(lib, _name).restype = C.c_int
-lib.gb200_host_malloc.restype = C.c_void_p
-lib.gb200_host_malloc.argtypes = [C.c_size_t]
-lib.gb200_host_free.restype = None
-lib.gb200_host_free.argtypes = [C.c_void_p]
-lib.gb200_host_trim.restype = None
+# every entry point of include/gb_b200.h with its full signature (without argtypes ctypes would pass
+# Python ints as 32-bit C ints where the ABI takes int64_t)
+_VP, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
+_SIGS = {
+    "gb200_last_error": (C.c_char_p, []),
+    "gb200_version": (C.c_char_p, []),
+    "gb200_kernel_launches": (_I64, []),
+    "gb200_multiplies": (_I64, []),
+    "gb200_device_count": (_I, []),
+    "gb200_init": (_I, [_I]),
+    "gb200_finalize": (_I, []),
+    "gb200_semiring_canonical": (_I, [_VP]),
+    "gb200_upload": (_I, [_VP, _VP]),
+    "gb200_upload_from_device": (_I, [_VP, _VP, _I64]),
+    "gb200_dmatrix_free": (_I, [_VP]),
+    "gb200_AxB_device": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _I, _I]),
+    "gb200_AxB_host": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _I, _I]),
+    "gb200_result_get_info": (_I, [_VP, _VP]),
+    "gb200_result_fetch": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "gb200_result_free": (_I, [_VP]),
+    "gb200_flopcount_device": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "gb200_partition_by_flops": (_I, [_VP, _I64, _I, _VP]),
+    "gb200_timer_mark": (_I, [_I]),
+    "gb200_timer_elapsed_ms": (_I, [_I, _I, _VP]),
+    "gb200_host_malloc": (_VP, [C.c_size_t]),
+    "gb200_host_calloc": (_VP, [C.c_size_t, C.c_size_t]),
+    "gb200_host_realloc": (_VP, [_VP, C.c_size_t]),
+    "gb200_host_free": (None, [_VP]),
+    "gb200_host_trim": (None, []),
+    "gb200_device_trim": (None, []),
+}
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.restype, _fn.argtypes = _res, _args
 
 
 def _check(code: int, where: str) -> None:
@@ -128,103 +121,6 @@ def host_array(a: np.ndarray) -> np.ndarray:
     out = host_empty(a.size, a.dtype)
     out[...] = a.reshape(-1)
     return out
-
-
-@dataclass
-class Semiring:
-    """add monoid, multiply operator, operand type: e.g. Semiring('PLUS', 'TIMES', 'FP64')."""
-    add: str
-    mult: str
-    xytype: str
-    flipxy: bool = False
-
-    @classmethod
-    def parse(cls, name: str) -> "Semiring":
-        """'PLUS_TIMES_FP64' / 'GxB_LOR_LAND_BOOL' -> Semiring."""
-        parts = name.replace("GxB_", "").replace("GrB_", "").split("_")
-        return cls(parts[0], parts[1], parts[2])
-
-    @property
-    def ztype(self) -> str:
-        return "BOOL" if self.mult in COMPARE_OPS else self.xytype
-
-    def c(self) -> _CSemiring:
-        return _CSemiring(OPCODES[self.add], OPCODES[self.mult], TYPES[self.xytype][0],
-                          TYPES[self.ztype][0], 1 if self.flipxy else 0)
-
-
-@dataclass
-class Matrix:
-    """A host sparse matrix in the reference's CSC-agnostic layout."""
-    vlen: int
-    vdim: int
-    p: np.ndarray
-    i: np.ndarray
-    x: np.ndarray
-    h: Optional[np.ndarray] = None
-    type: str = field(default="")
-
-    def __post_init__(self):
-        self.p = np.ascontiguousarray(self.p, dtype=np.int64)
-        self.i = np.ascontiguousarray(self.i, dtype=np.int64)
-        if self.h is not None:
-            self.h = np.ascontiguousarray(self.h, dtype=np.int64)
-        if not self.type:
-            for k, (_, dt) in TYPES.items():
-                if np.dtype(dt) == self.x.dtype:
-                    self.type = k
-        self.x = np.ascontiguousarray(self.x, dtype=TYPES[self.type][1])
-
-    @property
-    def nvec(self) -> int:
-        return len(self.p) - 1
-
-    @property
-    def nnz(self) -> int:
-        return int(self.p[-1])
-
-    def c(self) -> _CMatrix:
-        return _CMatrix(self.vlen, self.vdim, self.nvec, self.p.ctypes.data,
-                        self.h.ctypes.data if self.h is not None else None,
-                        self.i.ctypes.data if self.i.size else None,
-                        self.x.ctypes.data if self.x.size else None,
-                        TYPES[self.type][0], 0)
-
-    @classmethod
-    def from_scipy(cls, s, type: str = "") -> "Matrix":
-        """scipy CSC -> vectors are columns; scipy CSR -> vectors are rows."""
-        s.sort_indices()
-        if s.format == "csc":
-            vlen, vdim = s.shape
-        else:
-            vdim, vlen = s.shape
-        return cls(vlen, vdim, s.indptr.astype(np.int64), s.indices.astype(np.int64), s.data, None,
-                   type)
-
-    def pinned(self) -> "Matrix":
-        """The same matrix with its arrays in memory from gb200_host_malloc."""
-        return Matrix(self.vlen, self.vdim, host_array(self.p), host_array(self.i),
-                      host_array(self.x), host_array(self.h) if self.h is not None else None,
-                      self.type)
-
-    def to_hyper(self) -> "Matrix":
-        """Same matrix in hypersparse form (only non-empty vectors are listed)."""
-        cnt = np.diff(self.p)
-        if self.h is not None:
-            keep = cnt > 0
-            return Matrix(self.vlen, self.vdim, np.concatenate([[0], np.cumsum(cnt[keep])]),
-                          self.i, self.x, self.h[keep], self.type)
-        keep = np.nonzero(cnt > 0)[0]
-        return Matrix(self.vlen, self.vdim, np.concatenate([[0], np.cumsum(cnt[keep])]), self.i,
-                      self.x, keep.astype(np.int64), self.type)
-
-    def to_standard(self) -> "Matrix":
-        if self.h is None:
-            return self
-        cnt = np.zeros(self.vdim, dtype=np.int64)
-        cnt[self.h] = np.diff(self.p)
-        return Matrix(self.vlen, self.vdim, np.concatenate([[0], np.cumsum(cnt)]), self.i, self.x,
-                      None, self.type)
 
 
 class DMatrix:
@@ -268,25 +164,27 @@ class Result:
 
 
 def _fetch(rh: C.c_void_p, fetch: bool, pinned: bool = False) -> Result:
-    ci = _CInfo()
-    _check(lib.gb200_result_get_info(rh, C.byref(ci)), "gb200_result_get_info")
-    info = {k: getattr(ci, k) for k, _ in _CInfo._fields_}
-    m = None
-    if fetch:
-        tname, dt = TYPE_BY_CODE[ci.type_code]
-        empty = host_empty if pinned else np.empty
-        p = empty(ci.nvec + 1, np.int64)
-        h = empty(ci.nvec, np.int64) if ci.is_hyper else None
-        i = empty(ci.nnz, np.int64)
-        x = empty(ci.nnz, dt)
-        _check(lib.gb200_result_fetch(rh, p.ctypes.data_as(C.c_void_p),
-                                      h.ctypes.data_as(C.c_void_p) if h is not None else None,
-                                      i.ctypes.data_as(C.c_void_p) if ci.nnz else None,
-                                      x.ctypes.data_as(C.c_void_p) if ci.nnz else None),
-               "gb200_result_fetch")
-        m = Matrix(ci.vlen, ci.vdim, p, i, x, h, tname)
-    lib.gb200_result_free(C.byref(rh))
-    return Result(m, info)
+    try:
+        ci = _CInfo()
+        _check(lib.gb200_result_get_info(rh, C.byref(ci)), "gb200_result_get_info")
+        info = {k: getattr(ci, k) for k, _ in _CInfo._fields_}
+        m = None
+        if fetch:
+            tname, dt = TYPE_BY_CODE[ci.type_code]
+            empty = host_empty if pinned else np.empty
+            p = empty(ci.nvec + 1, np.int64)
+            h = empty(ci.nvec, np.int64) if ci.is_hyper else None
+            i = empty(ci.nnz, np.int64)
+            x = empty(ci.nnz, dt)
+            _check(lib.gb200_result_fetch(rh, p.ctypes.data_as(C.c_void_p),
+                                          h.ctypes.data_as(C.c_void_p) if h is not None else None,
+                                          i.ctypes.data_as(C.c_void_p) if ci.nnz else None,
+                                          x.ctypes.data_as(C.c_void_p) if ci.nnz else None),
+                   "gb200_result_fetch")
+            m = Matrix(ci.vlen, ci.vdim, p, i, x, h, tname)
+        return Result(m, info)
+    finally:
+        lib.gb200_result_free(C.byref(rh))      # also when the fetch failed
 
 
 def axb_device_keep(M: Optional["DMatrix"], mask_comp: bool, A: "DMatrix", B: "DMatrix",

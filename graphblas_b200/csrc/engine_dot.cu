@@ -227,10 +227,10 @@ __global__ void dotg_tasks_kernel (DMat A, DMat B, DMat M, const int32_t *__rest
     }
 }
 
-// Owner classes.  0: the owner fits one load of the cuckoo tables (or is dense): flat kernel, DOTG_CHUNK
-// tasks per item.  1: a longer owner ("hub") whose index range fits DOTF_MAXPARTS bitmap parts: flat
-// kernel with a shared-memory bitmap, big items.  2: any other hub: the segmented cuckoo kernel
-// dotg_kernel<HUB>, big items.  flat == 0 (GB200_DOTF=0, for A/B runs) sends class 0 to
+// Owner classes.  0: the owner fits one load of the cuckoo tables (or is dense): row-walk kernel,
+// DOTG_CHUNK tasks per item.  1: a longer owner ("hub") whose index range fits DOTR_MAXPARTS bitmap
+// parts: row-walk kernel with a shared-memory bitmap, big items.  2: any other hub: the segmented
+// cuckoo kernel dotg_kernel<HUB>, big items.  flat == 0 (GB200_DOTR=0, for A/B runs) sends class 0 to
 // dotg_kernel<!HUB> and every hub to class 2.
 struct DotgClasses { int64_t cap ; int64_t bm_bits ; int flat ; int64_t chunk [3] ; } ;
 
@@ -246,7 +246,7 @@ __device__ __forceinline__ int dotg_class_of (const DMat &O, const DMat &M, int 
     if (!K.flat) return 2 ;
     const int64_t lo0 = ((int64_t) __ldg (O.i + o0)) & ~(int64_t) 31 ;
     const int64_t nparts = (((int64_t) __ldg (O.i + o1 - 1)) - lo0) / K.bm_bits + 1 ;
-    return (nparts <= DOTF_MAXPARTS) ? 1 : 2 ;
+    return (nparts <= DOTR_MAXPARTS) ? 1 : 2 ;
 }
 
 __global__ void dotg_nchunks_kernel (DMat O, DMat M, int orient, DotgClasses K, int cls,
@@ -361,8 +361,8 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             // 0: walk the whole list of every pair (for A/B measurements)
             const char *trim_env = getenv ("GB200_DOTG_TRIM") ;
             const int trim = (trim_env != nullptr && atoi (trim_env) == 0) ? 0 : 1 ;
-            // 0: the round-1 kernels (warp per task / lane per task) instead of the flat ones
-            const char *flat_env = getenv ("GB200_DOTF") ;
+            // 0: warp per task / lane per task (dotg_kernel) instead of the row walk (kernels_dotr.cuh)
+            const char *flat_env = getenv ("GB200_DOTR") ;
             const bool flat = !(flat_env != nullptr && atoi (flat_env) == 0) ;
             DevBuf own, small, wl, ws, cntA, offA, curA, pos0, poss, off0, plist, slist ;
             GB200_TRY (own.alloc (mnz)) ;
@@ -458,11 +458,11 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 if (getenv ("GB200_DOTG_CHUNK")) reg_chunk = atoll (getenv ("GB200_DOTG_CHUNK")) ;
                 if (reg_chunk < 1) reg_chunk = DOTG_CHUNK ;
                 DotgClasses K ;
-                K.cap = cap ; K.bm_bits = dotf_bm_bits (iso) ; K.flat = flat ? 1 : 0 ;
+                K.cap = cap ; K.bm_bits = dotr_bm_bits (iso) ; K.flat = flat ? 1 : 0 ;
                 // smaller bitmap parts (a multiple of 32 indices): lets a test reach several parts
-                if (getenv ("GB200_DOTF_BM_BITS"))
+                if (getenv ("GB200_DOTR_BM_BITS"))
                 {
-                    const int64_t bb = (atoll (getenv ("GB200_DOTF_BM_BITS")) / 32) * 32 ;
+                    const int64_t bb = (atoll (getenv ("GB200_DOTR_BM_BITS")) / 32) * 32 ;
                     if (bb >= 32 && bb <= K.bm_bits) K.bm_bits = bb ;
                 }
                 ga.bm_bits = K.bm_bits ;
@@ -487,8 +487,8 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                     ga.items = items.as<DotItem> () ; ga.nitems = nitems ;
                     int fam, per_sm, threads ;
                     if (cls == 2) { fam = iso ? FAM_DOTG_HUB_ISO : FAM_DOTG_HUB ; per_sm = 2 ; threads = DOTG_THREADS ; }
-                    else if (cls == 1) { fam = iso ? FAM_DOTF_BM_ISO : FAM_DOTF_BM ; per_sm = 1 ; threads = DOTF_BM_THREADS ; }
-                    else if (flat) { fam = iso ? FAM_DOTF_ISO : FAM_DOTF ; per_sm = iso ? 3 : 2 ; threads = DOTF_THREADS ; }
+                    else if (cls == 1) { fam = iso ? FAM_DOTR_BM_ISO : FAM_DOTR_BM ; per_sm = 1 ; threads = DOTR_BM_THREADS ; }
+                    else if (flat) { fam = iso ? FAM_DOTR_ISO : FAM_DOTR ; per_sm = iso ? 3 : 2 ; threads = DOTR_THREADS ; }
                     else { fam = iso ? FAM_DOTG_ISO : FAM_DOTG ; per_sm = iso ? 3 : 2 ; threads = DOTG_THREADS ; }
                     if (!launch_typed (s.xy_code, fam, s.z_code, s.add_opcode, s.mult_opcode, &ga,
                         grid_cap (nitems, per_sm), threads))

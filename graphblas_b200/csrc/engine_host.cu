@@ -7,6 +7,8 @@
 #include <cstring>
 #include <map>
 #include <unordered_map>
+#include <vector>
+#include <unistd.h>
 #include "engine.cuh"
 
 namespace gb200 {
@@ -22,10 +24,43 @@ struct HostPool
     std::unordered_map<void *, size_t> live ;           // pinned blocks in use: ptr -> capacity
     std::multimap<size_t, void *> cache ;               // free pinned blocks by capacity
     size_t cached_bytes = 0 ;
-    bool no_device = false ;                            // cudaMallocHost failed once: stop trying
+    size_t cache_limit = 0 ;                            // most bytes kept in `cache` (0: not read yet)
+    bool no_device = false ;                            // there is no CUDA device at all: plain malloc
 } ;
 
 static HostPool &pool () { static HostPool *p = new HostPool () ; return *p ; }    // never destroyed
+
+// Upper bound of the free-block cache: GB200_HOST_CACHE_MB, else a quarter of the machine's RAM (a
+// long-running host with varying sizes must not accumulate page-locked memory without limit).
+static size_t cache_limit_locked (HostPool &hp)
+{
+    if (hp.cache_limit == 0)
+    {
+        const char *env = getenv ("GB200_HOST_CACHE_MB") ;
+        if (env != nullptr && atoll (env) >= 0) hp.cache_limit = ((size_t) atoll (env) << 20) + 1 ;
+        else
+        {
+            const long pages = sysconf (_SC_PHYS_PAGES), psz = sysconf (_SC_PAGE_SIZE) ;
+            size_t ram = (pages > 0 && psz > 0) ? (size_t) pages * (size_t) psz : ((size_t) 16 << 30) ;
+            hp.cache_limit = ram / 4 + 1 ;
+        }
+    }
+    return hp.cache_limit ;
+}
+
+// evict largest-first until the cache fits its limit; the evicted blocks are unpinned by the caller
+// outside the lock (cudaFreeHost synchronises)
+static void evict_locked (HostPool &hp, std::vector<void *> &drop)
+{
+    const size_t limit = cache_limit_locked (hp) ;
+    while (hp.cached_bytes > limit && !hp.cache.empty ())
+    {
+        auto it = std::prev (hp.cache.end ()) ;
+        hp.cached_bytes -= it->first ;
+        drop.push_back (it->second) ;
+        hp.cache.erase (it) ;
+    }
+}
 
 static size_t size_class (size_t n)
 {
@@ -41,10 +76,10 @@ static size_t size_class (size_t n)
 static void *pinned_get (size_t size)
 {
     HostPool &hp = pool () ;
-    if (hp.no_device) return nullptr ;
     const size_t cap = size_class (size) ;
     {
         std::lock_guard<std::mutex> lock (hp.mu) ;
+        if (hp.no_device) return nullptr ;
         auto it = hp.cache.lower_bound (cap) ;
         if (it != hp.cache.end () && it->first <= 2 * cap)
         {
@@ -61,14 +96,23 @@ static void *pinned_get (size_t size)
     if (e != cudaSuccess)
     {
         cudaGetLastError () ;
-        // out of pinnable memory: drop the cache and retry once; no device at all: plain malloc
+        // out of pinnable memory: drop the cache and retry once.  No device / no driver: plain malloc
+        // from now on.  Any other (possibly transient) error: plain malloc for this block only.
         if (e == cudaErrorMemoryAllocation)
         {
             gb200_host_trim () ;
             e = cudaMallocHost (&p, cap) ;
             if (e != cudaSuccess) { cudaGetLastError () ; return nullptr ; }
         }
-        else { hp.no_device = true ; return nullptr ; }
+        else
+        {
+            if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+            {
+                std::lock_guard<std::mutex> lock (hp.mu) ;
+                hp.no_device = true ;
+            }
+            return nullptr ;
+        }
     }
     std::lock_guard<std::mutex> lock (hp.mu) ;
     hp.live [p] = cap ;
@@ -108,6 +152,8 @@ void gb200_host_free (void *p)
 {
     if (p == nullptr) return ;
     HostPool &hp = pool () ;
+    std::vector<void *> drop ;
+    bool mine = false ;
     {
         std::lock_guard<std::mutex> lock (hp.mu) ;
         auto it = hp.live.find (p) ;
@@ -117,10 +163,13 @@ void gb200_host_free (void *p)
             hp.live.erase (it) ;
             hp.cache.emplace (cap, p) ;
             hp.cached_bytes += cap ;
-            return ;
+            evict_locked (hp, drop) ;
+            mine = true ;
         }
     }
-    free (p) ;
+    for (void *q : drop) cudaFreeHost (q) ;
+    if (!drop.empty ()) cudaGetLastError () ;
+    if (!mine) free (p) ;
 }
 
 void *gb200_host_realloc (void *p, size_t size)

@@ -114,13 +114,46 @@ void *dev_pool_alloc (size_t nbytes, size_t *capacity)
     return p ;
 }
 
+// Upper bound of the free-block cache: GB200_DEVICE_CACHE_MB, else half of the device's memory, so
+// that other users of the same GPU (torch, NCCL) are not starved by blocks this library holds free.
+static size_t dev_cache_limit ()
+{
+    static size_t limit = 0 ;
+    if (limit == 0)
+    {
+        const char *env = getenv ("GB200_DEVICE_CACHE_MB") ;
+        size_t free_b = 0, total_b = 0 ;
+        if (env != nullptr && atoll (env) >= 0) limit = ((size_t) atoll (env) << 20) + 1 ;
+        else if (cudaMemGetInfo (&free_b, &total_b) == cudaSuccess && total_b > 0) limit = total_b / 2 + 1 ;
+        else { cudaGetLastError () ; limit = ((size_t) 64 << 30) + 1 ; }
+    }
+    return limit ;
+}
+
 void dev_pool_free (void *ptr, size_t capacity)
 {
     if (ptr == nullptr) return ;
     DevPool &dp = dev_pool () ;
-    std::lock_guard<std::mutex> lock (dp.mu) ;
-    dp.cache.emplace (capacity, ptr) ;
-    dp.cached += capacity ;
+    std::vector<void *> drop ;
+    {
+        std::lock_guard<std::mutex> lock (dp.mu) ;
+        dp.cache.emplace (capacity, ptr) ;
+        dp.cached += capacity ;
+        const size_t limit = dev_cache_limit () ;
+        while (dp.cached > limit && !dp.cache.empty ())     // largest first
+        {
+            auto it = std::prev (dp.cache.end ()) ;
+            dp.cached -= it->first ;
+            drop.push_back (it->second) ;
+            dp.cache.erase (it) ;
+        }
+    }
+    if (drop.empty ()) return ;
+    // the blocks may still be in use by queued work of the library's stream
+    Ctx &c = ctx () ;
+    if (c.stream != nullptr) cudaStreamSynchronize (c.stream) ;
+    for (void *q : drop) cudaFree (q) ;
+    cudaGetLastError () ;
 }
 
 void dev_pool_trim ()
@@ -143,7 +176,9 @@ void dev_pool_trim ()
 gb200_status ensure_init ()
 {
     Ctx &c = ctx () ;
-    if (!c.ready) { GB200_TRY (do_init (-1)) ; }
+    bool ready ;
+    { std::lock_guard<std::recursive_mutex> lock (c.mu) ; ready = c.ready ; }
+    if (!ready) { GB200_TRY (do_init (-1)) ; }
     GB200_CUDA (cudaSetDevice (c.device)) ;
     return GB200_SUCCESS ;
 }
@@ -628,6 +663,13 @@ gb200_status gb200_finalize (void)
     return GB200_SUCCESS ;
 }
 
+void gb200_device_trim (void)
+{
+    Ctx &c = ctx () ;
+    std::lock_guard<std::recursive_mutex> lock (c.mu) ;
+    if (c.ready) dev_pool_trim () ;
+}
+
 int64_t gb200_kernel_launches (void) { return ctx ().launches.load () ; }
 int64_t gb200_multiplies (void) { return ctx ().multiplies.load () ; }
 
@@ -828,6 +870,8 @@ gb200_status gb200_result_fetch (gb200_result r, int64_t *p, int64_t *h, int64_t
     Ctx &c = ctx () ;
     std::lock_guard<std::recursive_mutex> lock (c.mu) ;
     const gb200_result_info &f = r->info ;
+    // every argument is checked before any copy is queued
+    if (f.nnz > 0 && (i == NULL || x == NULL)) { set_error ("gb200_result_fetch: NULL i or x") ; return GB200_INVALID ; }
     GB200_CUDA (cudaMemcpyAsync (p, r->p.ptr, (f.nvec + 1) * sizeof (int64_t),
         cudaMemcpyDefault, c.stream)) ;
     if (f.is_hyper && h != NULL && f.nvec > 0)
@@ -835,7 +879,6 @@ gb200_status gb200_result_fetch (gb200_result r, int64_t *p, int64_t *h, int64_t
             cudaMemcpyDefault, c.stream)) ;
     if (f.nnz > 0)
     {
-        if (i == NULL || x == NULL) { set_error ("gb200_result_fetch: NULL i or x") ; return GB200_INVALID ; }
         const int64_t chunk = (f.nnz < (1LL << 26)) ? f.nnz : (1LL << 26) ;
         DevBuf stage ;
         GB200_TRY (stage.alloc (chunk * sizeof (int64_t))) ;

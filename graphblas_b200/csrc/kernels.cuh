@@ -334,7 +334,7 @@ struct DotGArgs
     unsigned long long *next_item ;     // dynamic work-item counter (zeroed before launch)
     unsigned int *failed ;              // set to 1 if an owner's cuckoo tables could not be built: the
                                         // host then recomputes the pairs with the table-free dot_kernel
-    int64_t bm_bits ;                   // dotf_kernel<BITMAP>: indices per bitmap part (a multiple of 32)
+    int64_t bm_bits ;                   // dotr_kernel<BITMAP>: indices per bitmap part (a multiple of 32)
     int mult_op ; int flip ;
 } ;
 
@@ -771,7 +771,7 @@ dotg_kernel (DotGArgs a)
 
 } // namespace gb200
 
-#include "kernels_dotf.cuh"
+#include "kernels_dotr.cuh"
 
 namespace gb200 {
 
@@ -781,7 +781,7 @@ namespace gb200 {
 enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_DOTV = 4,
     FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9,
     FAM_DOTG_ISO = 10, FAM_SPMV_OCC8 = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13,
-    FAM_DOTF = 14, FAM_DOTF_ISO = 15, FAM_DOTF_BM = 16, FAM_DOTF_BM_ISO = 17 } ;
+    FAM_DOTR = 14, FAM_DOTR_ISO = 15, FAM_DOTR_BM = 16, FAM_DOTR_BM_ISO = 17 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -818,27 +818,27 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
         else
             dotg_kernel<S, false, true> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
     }
-    else if (family == FAM_DOTF || family == FAM_DOTF_ISO || family == FAM_DOTF_BM
-        || family == FAM_DOTF_BM_ISO)
+    else if (family == FAM_DOTR || family == FAM_DOTR_ISO || family == FAM_DOTR_BM
+        || family == FAM_DOTR_BM_ISO)
     {
         static bool attr_set = false ;          // one flag per instantiation
         if (!attr_set)
         {
-            cudaFuncSetAttribute (dotf_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
-            cudaFuncSetAttribute (dotf_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
-            cudaFuncSetAttribute (dotf_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTF_BM_SMEM) ;
-            cudaFuncSetAttribute (dotf_kernel<S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTF_BM_SMEM) ;
+            cudaFuncSetAttribute (dotr_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            cudaFuncSetAttribute (dotr_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            cudaFuncSetAttribute (dotr_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTR_BM_SMEM) ;
+            cudaFuncSetAttribute (dotr_kernel<S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTR_BM_SMEM) ;
             attr_set = true ;
         }
         const DotGArgs &ga = *(const DotGArgs *) args ;
-        if (family == FAM_DOTF_ISO)
-            dotf_kernel<S, true, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
-        else if (family == FAM_DOTF)
-            dotf_kernel<S, false, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
-        else if (family == FAM_DOTF_BM_ISO)
-            dotf_kernel<S, true, true> <<<cfg.grid, cfg.block, DOTF_BM_SMEM, cfg.stream>>> (ga) ;
+        if (family == FAM_DOTR_ISO)
+            dotr_kernel<S, true, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+        else if (family == FAM_DOTR)
+            dotr_kernel<S, false, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+        else if (family == FAM_DOTR_BM_ISO)
+            dotr_kernel<S, true, true> <<<cfg.grid, cfg.block, DOTR_BM_SMEM, cfg.stream>>> (ga) ;
         else
-            dotf_kernel<S, false, true> <<<cfg.grid, cfg.block, DOTF_BM_SMEM, cfg.stream>>> (ga) ;
+            dotr_kernel<S, false, true> <<<cfg.grid, cfg.block, DOTR_BM_SMEM, cfg.stream>>> (ga) ;
     }
     else if (family == FAM_DOTV)
         dotv_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotVArgs *) args) ;

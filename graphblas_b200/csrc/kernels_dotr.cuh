@@ -1,0 +1,432 @@
+// kernels_dotr.cuh -- the ROW-WALK masked dot kernel, C<M> = A'*B (included by kernels.cuh).
+//
+// Reference behaviour restated: Source/Template/GB_AxB_dot_mask.c:33-159 (one dot product per entry
+// of M) with the inner loop of GB_AxB_dot_cij.c:47-256 (first product copied, later ones combined,
+// entry emitted only if some index matched).
+//
+// Like dotg_kernel (kernels.cuh) the pairs arrive grouped by their OWNER (the longer vector), the
+// owner goes into shared memory once per work item and the shorter list of every pair is walked
+// against it.  What differs is who walks and what the owner is kept in:
+//
+//   * a WARP claims a batch of up to 32 tasks with one shared-memory atomic, lane l keeps the
+//     descriptor of task l, and the warp walks the tasks one after another in ROWS of 32 consecutive
+//     indices: one coalesced load, one probe per lane, one vote.  The first two rows of the next task
+//     are requested before the current task is walked, so a warp always has loads in flight although
+//     most tasks are only a few rows long.  Per row: ~16 warp instructions and, for the bitmap, ~5
+//     wavefronts of the L1/shared-memory pipe (measured before: 65 instructions per row in
+//     dotg_kernel's regular walk; 11 wavefronts per 32 probes in its lane-per-task hub walk, whose 32
+//     lanes each load their own 32 bytes).
+//   * regular owners (<= dotg_cap entries): the cuckoo tables of dotg_kernel.  A table that cannot be
+//     built falls back to a binary search of the owner's list in global memory for that item.
+//   * hub owners: a BITMAP over a part of the owner's index range in shared memory -- one shared
+//     read and one bit test per probe, no build failures.  An owner whose range needs several parts is
+//     served part by part: both lists are sorted, so every task keeps a 16-bit cursor (the row at
+//     which it left the previous part) in shared memory, and an index is looked up in exactly one
+//     part (an index outside [lo, lo+nbits) misses by the range test alone).
+#pragma once
+
+namespace gb200 {
+
+constexpr int DOTR_THREADS = 512 ;              // cuckoo instantiation (64 KB table, 2-3 blocks per SM)
+constexpr int DOTR_BM_THREADS = 1024 ;          // bitmap instantiation (one block per SM)
+constexpr int DOTR_BM_BYTES = 184 * 1024 ;      // bitmap (pattern-only) or bitmap + rank (valued)
+constexpr int DOTR_CUR_TASKS = DOTG_HUB_TASKS ; // cursors of one hub item: 2 bytes each
+constexpr int DOTR_BM_SMEM = DOTR_BM_BYTES + 2 * DOTR_CUR_TASKS ;
+constexpr int DOTR_MAXPARTS = 16 ;              // hub owners whose range needs more parts: dotg_kernel<HUB>
+constexpr int DOTR_REBUILDS = 30 ;
+
+// indices covered by one bitmap part
+__host__ __device__ constexpr int64_t dotr_bm_bits (bool iso)
+{
+    return iso ? (int64_t) DOTR_BM_BYTES * 8 : (int64_t) DOTR_BM_BYTES * 4 ;
+}
+
+enum { DOTR_CUCKOO = 0, DOTR_DENSE = 1, DOTR_BSEARCH = 2, DOTR_BITMAP = 3 } ;
+
+template <class S> struct DotRCtx
+{
+    const DotTask *tasks ;      // of this item
+    int ntask ;
+    const int32_t *Wi ;         // walked matrix: indices, values
+    const typename S::T *Wx ;
+    const typename S::T *Ox ;   // owner values (of the whole owner vector)
+    const int32_t *Oi ;         // owner indices (BSEARCH)
+    int olen ;
+    typename S::acc_t *vals ;
+    uint8_t *flags ;
+    typename S::acc_t ciso ;
+    bool orient ;
+    bool multi ;                // several parts: partial results meet in the accumulator
+    bool last ;                 // bitmap: this is the owner's last part
+    int mode ;                  // cuckoo instantiation: DOTR_CUCKOO / DENSE / BSEARCH
+    int NS, sh ;
+    uint32_t c1, c2 ;
+    uint32_t lo, nbits ;        // bitmap part: indices [lo, lo + nbits)
+    int32_t hi ;                // lo + nbits
+} ;
+
+// one probe of index kq (NOKEY: a lane past the end of the list, never a hit)
+template <class S, bool ISO, int MODE, class slot_t>
+__device__ __forceinline__ bool dotr_probe (const DotRCtx<S> &g, const void *table, uint32_t kq, uint32_t &pos)
+{
+    constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
+    if constexpr (MODE == DOTR_BITMAP)
+    {
+        const uint32_t *__restrict__ bm = (const uint32_t *) table ;
+        const uint32_t kk = kq - g.lo ;
+        bool hit = false ;
+        if (kk < g.nbits)
+        {
+            const uint32_t word = bm [kk >> 5] ;
+            hit = (word >> (kk & 31)) & 1u ;
+            if constexpr (!ISO)
+            {
+                const uint32_t *__restrict__ rk = bm + (DOTR_BM_BYTES / 8) ;
+                if (hit) pos = rk [kk >> 5] + __popc (word & ((1u << (kk & 31)) - 1u)) ;
+            }
+        }
+        return hit ;
+    }
+    else if constexpr (MODE == DOTR_CUCKOO)
+    {
+        const slot_t *__restrict__ tab = (const slot_t *) table ;
+        return dotg_probe<ISO, false, slot_t> (tab, tab + g.NS, kq, g.sh, g.c1, g.c2, pos) ;
+    }
+    else if constexpr (MODE == DOTR_DENSE) { pos = kq ; return (kq != NOKEY) ; }
+    else
+    {
+        int l = 0, h = (kq != NOKEY) ? g.olen : 0 ;
+        while (l < h)
+        {
+            const int mid = (l + h) >> 1 ;
+            const uint32_t v = (uint32_t) __ldg (g.Oi + mid) ;
+            if (v == kq) { pos = (uint32_t) mid ; return true ; }
+            if (v < kq) l = mid + 1 ; else h = mid ;
+        }
+        return false ;
+    }
+}
+
+// The warps of the block pull batches of tasks of the item until its counter runs out.
+// s_cur (BITMAP): per task of the item, the row at which the previous part left it.
+template <class S, bool ISO, int MODE, class slot_t>
+__device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, const void *table,
+    int *s_next, uint16_t *s_cur, int nwarps, unsigned long long &nm)
+{
+    using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
+    constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
+    constexpr unsigned FULL = 0xffffffffu ;
+    constexpr bool BITMAP = (MODE == DOTR_BITMAP) ;
+    const int lane = threadIdx.x & 31 ;
+    while (true)
+    {
+        // ---- claim a batch: 32 tasks while the item is long, fewer towards its end (the warps of a
+        // block finish an item together) -------------------------------------------------------------
+        int t0 = 0, nb = 0 ;
+        if (lane == 0)
+        {
+            int cur = *((volatile int *) s_next) ;
+            while (cur < g.ntask)
+            {
+                const int rem = g.ntask - cur ;
+                int c = rem / (2 * nwarps) ;
+                c = (c < 2) ? 2 : ((c > 32) ? 32 : c) ;
+                if (c > rem) c = rem ;
+                const int seen = atomicCAS (s_next, cur, cur + c) ;
+                if (seen == cur) { t0 = cur ; nb = c ; break ; }
+                cur = seen ;
+            }
+        }
+        t0 = __shfl_sync (FULL, t0, 0) ;
+        nb = __shfl_sync (FULL, nb, 0) ;
+        if (nb == 0) break ;
+        // ---- lane l keeps task t0 + l ------------------------------------------------------------
+        int len = 0, cur = 0 ;
+        int32_t e = 0 ;
+        long long w0 = 0 ;
+        bool split = false ;
+        if (lane < nb)
+        {
+            const DotTask d = g.tasks [t0 + lane] ;
+            split = (d.len < 0) ;
+            len = split ? -d.len : d.len ;
+            e = d.e ; w0 = d.w0 ;
+            if constexpr (BITMAP) if (g.multi) cur = (int) s_cur [t0 + lane] ;
+        }
+        uint32_t mycnt = 0 ;            // results of the task this lane keeps
+        acc_t myacc = Mon::identity () ;
+        int mycur = cur ;
+        // rows 0 and 1 of the first task
+        int tl = __shfl_sync (FULL, len, 0), p0 = __shfl_sync (FULL, cur, 0) ;
+        const int32_t *wp = g.Wi + __shfl_sync (FULL, w0, 0) ;
+        uint32_t kA = NOKEY, kB = NOKEY ;
+        if (p0 + lane < tl) kA = (uint32_t) __ldg (wp + p0 + lane) ;
+        if (p0 + 32 + lane < tl) kB = (uint32_t) __ldg (wp + p0 + 32 + lane) ;
+        for (int t = 0 ; t < nb ; t++)
+        {
+            // ---- request rows 0 and 1 of the next task before walking this one ------------------
+            int ntl = 0, np0 = 0 ;
+            const int32_t *nwp = wp ;
+            uint32_t nkA = NOKEY, nkB = NOKEY ;
+            if (t + 1 < nb)
+            {
+                ntl = __shfl_sync (FULL, len, t + 1) ; np0 = __shfl_sync (FULL, cur, t + 1) ;
+                nwp = g.Wi + __shfl_sync (FULL, w0, t + 1) ;
+                if (np0 + lane < ntl) nkA = (uint32_t) __ldg (nwp + np0 + lane) ;
+                if (np0 + 32 + lane < ntl) nkB = (uint32_t) __ldg (nwp + np0 + 32 + lane) ;
+            }
+            // ---- walk task t: rows of 32 indices, two per iteration ------------------------------
+            uint32_t cnt = 0 ;
+            acc_t acc = Mon::identity () ;
+            bool found = false ;
+            int stop = tl ;             // BITMAP: where the next part resumes
+            const T *__restrict__ wx = g.Wx + (wp - g.Wi) ;
+            if (p0 < tl)
+            {
+                const int32_t *__restrict__ rp = wp + p0 + lane ;   // this lane's index of the row
+                int rem = tl - p0 - lane ;                          // > 32 u: the lane has one in row u
+                for (int p = p0 ; ; )
+                {
+                    bool over = false ;
+                    #pragma unroll
+                    for (int u = 0 ; u < 2 ; u++)
+                    {
+                        const int pr = p + 32 * u ;
+                        if (u > 0 && (pr >= tl || over)) continue ;         // warp-uniform
+                        const uint32_t kq = u ? kB : kA ;
+                        uint32_t pos = 0 ;
+                        const bool hit = dotr_probe<S, ISO, MODE, slot_t> (g, table, kq, pos) ;
+                        if constexpr (ISO) cnt += hit ? 1u : 0u ;
+                        else if (hit)
+                        {
+                            const T ov = g.Ox [pos], wv = wx [pr + lane] ;
+                            const acc_t prod = g.orient ? sr.product (ov, wv) : sr.product (wv, ov) ;
+                            acc = found ? Mon::combine (acc, prod) : prod ;
+                            found = true ; cnt++ ;
+                        }
+                        if constexpr (BITMAP)
+                        {
+                            // the lists are sorted: an index at or above hi ends this part's stretch
+                            if (!g.last && __any_sync (FULL, (int32_t) kq >= g.hi)) { over = true ; stop = pr ; }
+                        }
+                    }
+                    if (over) break ;
+                    if constexpr (!ISO)
+                        if (Mon::has_terminal ())
+                            if (__any_sync (FULL, found && Mon::is_terminal (acc))) break ;   // stop = tl: decided
+                    p += 64 ;
+                    if (p >= tl) break ;
+                    rp += 64 ; rem -= 64 ;
+                    kA = (rem > 0) ? (uint32_t) __ldg (rp) : NOKEY ;
+                    kB = (rem > 32) ? (uint32_t) __ldg (rp + 32) : NOKEY ;
+                }
+            }
+            // ---- the task's result goes to the lane that keeps it --------------------------------
+            if constexpr (ISO)
+            {
+                const uint32_t tot = __reduce_add_sync (FULL, cnt) ;
+                if (lane == t) { mycnt = tot ; mycur = stop ; }
+            }
+            else
+            {
+                const uint32_t tot = __reduce_add_sync (FULL, cnt) ;
+                if (tot)
+                {
+                    // a lane without any match holds the identity; identity (+) t == t for every
+                    // monoid (bit-for-bit except +0.0 + -0.0)
+                    #pragma unroll
+                    for (int off = 16 ; off > 0 ; off >>= 1)
+                        acc = Mon::combine (acc, __shfl_down_sync (FULL, acc, off)) ;
+                    acc = __shfl_sync (FULL, acc, 0) ;
+                }
+                if (lane == t) { mycnt = tot ; myacc = acc ; mycur = stop ; }
+            }
+            kA = nkA ; kB = nkB ; tl = ntl ; p0 = np0 ; wp = nwp ;
+        }
+        // ---- every lane writes the result of its task ----------------------------------------------
+        if (lane < nb)
+        {
+            if constexpr (BITMAP) if (g.multi) s_cur [t0 + lane] = (uint16_t) mycur ;
+            if (mycnt)
+            {
+                if constexpr (ISO) myacc = iso_fold<Mon> (g.ciso, mycnt) ;
+                if (split || g.multi) Mon::atomic_combine (g.vals + e, myacc) ;
+                else g.vals [e] = myacc ;
+                g.flags [e] = 1 ;
+                nm += mycnt ;
+            }
+        }
+    }
+}
+
+// one pass of the cuckoo build (the same as dotg_kernel's); returns through *s_fail
+template <bool ISO, class slot_t>
+__device__ __forceinline__ void dotr_cuckoo_pass (slot_t *tab, const int32_t *__restrict__ Oi, int slen,
+    int NS, int sh, uint32_t c1, uint32_t c2, int *s_fail)
+{
+    constexpr slot_t EMPTY = (slot_t) ~(slot_t) 0 ;
+    for (int t = threadIdx.x ; t < 2 * NS ; t += blockDim.x) tab [t] = EMPTY ;
+    if (threadIdx.x == 0) *s_fail = 0 ;
+    __syncthreads () ;
+    for (int q = threadIdx.x ; q < slen ; q += blockDim.x)
+    {
+        slot_t cur ;
+        if constexpr (ISO) cur = (uint32_t) __ldg (Oi + q) ;
+        else cur = ((uint64_t) (uint32_t) q << 32) | (uint32_t) __ldg (Oi + q) ;
+        int which = 0, n = 0 ;
+        #pragma unroll 1
+        for ( ; n < DOTG_MAXIT ; n++)
+        {
+            const uint32_t k = (uint32_t) cur ;
+            const uint32_t loc = which ? (NS + ((k * c2) >> sh)) : ((k * c1) >> sh) ;
+            if constexpr (ISO) cur = atomicExch (tab + loc, cur) ;
+            else cur = atomicExch ((unsigned long long *) tab + loc, (unsigned long long) cur) ;
+            if (cur == EMPTY) break ;
+            which ^= 1 ;                        // the evicted entry moves to its other table
+        }
+        if (n == DOTG_MAXIT) *s_fail = 1 ;
+    }
+    __syncthreads () ;
+}
+
+template <class S, bool ISO, bool BITMAP>
+__global__ void __launch_bounds__ (BITMAP ? DOTR_BM_THREADS : DOTR_THREADS, BITMAP ? 1 : (ISO ? 3 : 2))
+dotr_kernel (DotGArgs a)
+{
+    using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
+    using slot_t = typename std::conditional<ISO, uint32_t, uint64_t>::type ;
+    constexpr int NW = (BITMAP ? DOTR_BM_THREADS : DOTR_THREADS) / 32 ;
+    extern __shared__ __align__ (16) unsigned char dotr_raw [] ;
+    __shared__ int64_t s_ws [33] ;
+    __shared__ int s_next, s_fail ;
+    __shared__ unsigned long long s_item ;
+    __shared__ int s_q0 ;
+    constexpr int CAP = dotg_cap (ISO) ;
+    const S sr (a.mult_op, a.flip != 0) ;
+    const T *__restrict__ Ax = (const T *) a.A.x ;
+    const T *__restrict__ Bx = (const T *) a.B.x ;
+    const int lane = threadIdx.x & 31 ;
+    const bool orient = (a.orient != 0) ;
+    const DMat &O = orient ? a.A : a.B ;        // owner matrix (probed)
+    const DMat &W = orient ? a.B : a.A ;        // walked matrix
+    const T *__restrict__ Oxb = orient ? Ax : Bx ;
+    const int64_t vlen = a.A.vlen ;
+    uint16_t *s_cur = (uint16_t *) (dotr_raw + DOTR_BM_BYTES) ;         // BITMAP only
+    DotRCtx<S> g ;
+    g.Wi = W.i ; g.Wx = orient ? Bx : Ax ;
+    g.vals = (acc_t *) a.vals ; g.flags = a.flags ; g.orient = orient ;
+    g.ciso = Mon::identity () ;
+    if (ISO) g.ciso = sr.product (Ax [0], Bx [0]) ;
+    g.multi = false ; g.last = true ; g.lo = 0 ; g.nbits = 0 ; g.hi = INT32_MAX ;
+    g.mode = DOTR_CUCKOO ; g.NS = 0 ; g.sh = 0 ; g.c1 = 0 ; g.c2 = 0 ;
+    unsigned long long nm = 0 ;
+    while (true)
+    {
+        __syncthreads () ;
+        if (threadIdx.x == 0) s_item = atomicAdd (a.next_item, 1ULL) ;
+        __syncthreads () ;
+        const int64_t it = (int64_t) s_item ;
+        if (it >= a.nitems) break ;
+        const DotItem item = a.items [it] ;
+        int64_t ko = item.owner ;
+        if (!orient) ko = dm_vecpos (a.B, dm_vecname (a.M, item.owner)) ;
+        const int64_t o0 = __ldg (O.p + ko), o1 = __ldg (O.p + ko + 1) ;
+        const int olen = (int) (o1 - o0) ;
+        g.tasks = a.tasks + item.e0 ;
+        g.ntask = (int) (item.e1 - item.e0) ;
+        g.Ox = Oxb + o0 ; g.Oi = O.i + o0 ; g.olen = olen ;
+        if constexpr (!BITMAP)
+        {
+            // ---- regular owner: cuckoo tables (or nothing at all for a dense owner) -----------------
+            const bool dense = ((int64_t) olen == vlen) ;
+            g.mode = dense ? DOTR_DENSE : DOTR_CUCKOO ;
+            if (!dense && olen > CAP) g.mode = DOTR_BSEARCH ;       // never scheduled here; stay correct
+            if (g.mode == DOTR_CUCKOO)
+            {
+                int lg = 5 ;                    // 2^lg slots per table: total load between 3/16 and 3/8
+                while (3 * (1 << lg) < 4 * olen) lg++ ;
+                const int NS = 1 << lg, sh = 32 - lg ;
+                uint32_t c1 = 0x9E3779B1u, c2 = 0x85EBCA6Bu ;
+                for (int attempt = 0 ; ; attempt++)
+                {
+                    dotr_cuckoo_pass<ISO, slot_t> ((slot_t *) dotr_raw, g.Oi, olen, NS, sh, c1, c2, &s_fail) ;
+                    const bool failed = (s_fail != 0) ;
+                    __syncthreads () ;          // everyone has read s_fail before it is reset
+                    if (!failed) break ;
+                    if (attempt >= DOTR_REBUILDS) { g.mode = DOTR_BSEARCH ; break ; }
+                    c1 = (c1 * 0x01000193u + 0xFE94F82Au) | 1u ;
+                    c2 = (c2 * 0x01000193u + 0x4A8BE922u) | 1u ;
+                }
+                g.NS = NS ; g.sh = sh ; g.c1 = c1 ; g.c2 = c2 ;
+            }
+            if (threadIdx.x == 0) s_next = 0 ;
+            __syncthreads () ;
+            if (g.mode == DOTR_CUCKOO) dotr_walk<S, ISO, DOTR_CUCKOO, slot_t> (sr, g, dotr_raw, &s_next, nullptr, NW, nm) ;
+            else if (g.mode == DOTR_DENSE) dotr_walk<S, ISO, DOTR_DENSE, slot_t> (sr, g, dotr_raw, &s_next, nullptr, NW, nm) ;
+            else dotr_walk<S, ISO, DOTR_BSEARCH, slot_t> (sr, g, dotr_raw, &s_next, nullptr, NW, nm) ;
+        }
+        else
+        {
+            // ---- hub owner: bitmap parts over [omin, omax] ------------------------------------------
+            uint32_t *bm = (uint32_t *) dotr_raw ;
+            uint32_t *rk = bm + (DOTR_BM_BYTES / 8) ;
+            const int64_t BITS = a.bm_bits ;    // dotr_bm_bits (ISO) unless a test asks for small parts
+            const int64_t omin = __ldg (O.i + o0), omax = __ldg (O.i + o1 - 1) ;
+            const int64_t lo0 = omin & ~(int64_t) 31 ;
+            const int nparts = (int) ((omax - lo0) / BITS) + 1 ;
+            g.multi = (nparts > 1) ;
+            if (g.multi) for (int t = threadIdx.x ; t < g.ntask ; t += blockDim.x) s_cur [t] = 0 ;
+            for (int part = 0 ; part < nparts ; part++)
+            {
+                const int64_t lo = lo0 + (int64_t) part * BITS ;
+                const int64_t hi = (lo + BITS < omax + 1) ? (lo + BITS) : (omax + 1) ;
+                const int nwords = (int) ((hi - lo + 31) >> 5) ;
+                __syncthreads () ;              // the previous part's walkers are done
+                for (int t = threadIdx.x ; t < nwords ; t += blockDim.x) bm [t] = 0u ;
+                if (!ISO && threadIdx.x == 0)
+                {
+                    // owner entries before this part: the position of a hit counts from the owner's start
+                    int l = 0, h = olen ;
+                    while (l < h)
+                    {
+                        const int mid = (l + h) >> 1 ;
+                        if ((int64_t) __ldg (g.Oi + mid) < lo) l = mid + 1 ; else h = mid ;
+                    }
+                    s_q0 = l ;
+                }
+                __syncthreads () ;
+                for (int q = threadIdx.x ; q < olen ; q += blockDim.x)
+                {
+                    const int64_t k = __ldg (g.Oi + q) ;
+                    if (k >= lo && k < hi)
+                    {
+                        const uint32_t kk = (uint32_t) (k - lo) ;
+                        atomicOr (bm + (kk >> 5), 1u << (kk & 31)) ;
+                    }
+                }
+                __syncthreads () ;
+                if constexpr (!ISO)
+                {
+                    // rk [w] = owner entries before word w
+                    const int per = (nwords + (int) blockDim.x - 1) / (int) blockDim.x ;
+                    const int wa = threadIdx.x * per ;
+                    const int wb = (wa + per < nwords) ? (wa + per) : nwords ;
+                    int64_t mine = 0 ;
+                    for (int t = wa ; t < wb ; t++) mine += __popc (bm [t]) ;
+                    int64_t tot ;
+                    int64_t run = s_q0 + block_excl_scan_i64 (mine, s_ws, tot) ;
+                    for (int t = wa ; t < wb ; t++) { rk [t] = (uint32_t) run ; run += __popc (bm [t]) ; }
+                }
+                if (threadIdx.x == 0) s_next = 0 ;
+                __syncthreads () ;
+                g.lo = (uint32_t) lo ; g.nbits = (uint32_t) (hi - lo) ; g.hi = (int32_t) hi ;
+                g.last = (part == nparts - 1) ;
+                dotr_walk<S, ISO, DOTR_BITMAP, slot_t> (sr, g, dotr_raw, &s_next, s_cur, NW, nm) ;
+            }
+        }
+    }
+    for (int off = 16 ; off > 0 ; off >>= 1) nm += __shfl_down_sync (0xffffffffu, nm, off) ;
+    if (lane == 0 && nm) atomicAdd (a.nmatch, nm) ;
+}
+
+} // namespace gb200

@@ -110,7 +110,8 @@ gb200_status gb200_semiring_canonical (gb200_semiring *s) ;
 
 /* ---- library / device -------------------------------------------------------------------- */
 gb200_status gb200_init (int device) ;       /* device < 0: use env GB200_DEVICE or 0       */
-gb200_status gb200_finalize (void) ;         /* frees all device workspace and handles       */
+gb200_status gb200_finalize (void) ;         /* frees the device workspace cache, the stream and its   */
+                                             /* events; operand / result handles stay the caller's     */
 const char  *gb200_last_error (void) ;       /* thread-local text of the last failure        */
 const char  *gb200_version (void) ;
 int          gb200_device_count (void) ;
@@ -212,6 +213,10 @@ void *gb200_host_calloc  (size_t n, size_t size) ;
 void *gb200_host_realloc (void *p, size_t size) ;
 void  gb200_host_free    (void *p) ;
 void  gb200_host_trim    (void) ;            /* release the cached page-locked blocks       */
+/* Both caches are bounded: freed page-locked blocks are kept up to GB200_HOST_CACHE_MB (default: a
+ * quarter of the machine's RAM), freed device blocks up to GB200_DEVICE_CACHE_MB (default: half of
+ * the device's memory); beyond that the largest free blocks go back to the driver. */
+void  gb200_device_trim  (void) ;            /* release the cached free device blocks       */
 
 /* ---- timing on the library's own stream (CUDA events) ----------------------------------------
  * gb200_timer_mark records event `slot` (0..7) on the stream every kernel of this library is

@@ -293,7 +293,7 @@ template <class G, class B, class S, class T> static inline void launch_cfg_seq 
 
 // ---- the slice of the runtime API the library uses: "device" memory is host memory --------------
 typedef int cudaError_t ;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 } ;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInsufficientDriver = 35, cudaErrorNoDevice = 100 } ;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault } ;
 enum { cudaStreamNonBlocking = 1 } ;
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 } ;

@@ -20,6 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libgraphblas_ref.so")
 DEMO_LIB = os.path.join(ROOT, "oracle", "_ref", "libgbdemo_ref.so")
 SHIM_LIB = os.path.join(ROOT, "graphblas_b200", "libgb_b200_shim.so")
+GPU_LIB = os.path.join(ROOT, "graphblas_b200", "libgb_b200.so")
 
 # enums, reference Include/GraphBLAS.h:2784-2823
 GrB_OUTP, GrB_MASK, GrB_INP0, GrB_INP1, GxB_AxB_METHOD = 0, 1, 2, 3, 1000
@@ -66,14 +67,18 @@ class GraphBLAS:
     _inst = None
 
     @classmethod
-    def get(cls, with_shim: bool) -> "GraphBLAS":
+    def get(cls, with_shim: bool, pinned: bool = False) -> "GraphBLAS":
         if cls._inst is None:
-            cls._inst = cls(with_shim)
+            cls._inst = cls(with_shim, pinned)
         if with_shim and cls._inst.shim is None:
             raise GrBError("GraphBLAS was already loaded without the shim in this process")
         return cls._inst
 
-    def __init__(self, with_shim: bool):
+    def __init__(self, with_shim: bool, pinned: bool = False):
+        """pinned: start the reference with GxB_init (mode, gb200_host_malloc, gb200_host_calloc,
+        gb200_host_realloc, gb200_host_free) -- reference Include/GraphBLAS.h:330-340 -- which is what
+        INTEGRATION.md tells a host application to do: every GraphBLAS array (operands, and the T the
+        shim builds with GB_create) then lives in page-locked memory."""
         if not available():
             raise GrBError(f"{REF_LIB} missing: run `make -C oracle -f Makefile.ref` where "
                            "/root/reference exists")
@@ -86,7 +91,21 @@ class GraphBLAS:
             self.shim.gb200_shim_enable(0)
         self.lib = C.CDLL(REF_LIB, mode=C.RTLD_GLOBAL)
         self.lib.GrB_error.restype = C.c_char_p
-        self.ok(self.lib.GrB_init(0), "GrB_init")        # GrB_NONBLOCKING
+        self.host_malloc = None
+        self._free = _libc.free
+        if pinned:
+            gpu = C.CDLL(GPU_LIB, mode=C.RTLD_GLOBAL)
+            gpu.gb200_host_malloc.restype = C.c_void_p
+            gpu.gb200_host_malloc.argtypes = [C.c_size_t]
+            self.host_malloc = gpu.gb200_host_malloc
+            gpu.gb200_host_free.restype = None
+            gpu.gb200_host_free.argtypes = [C.c_void_p]
+            self._free = gpu.gb200_host_free
+            fns = [C.cast(getattr(gpu, "gb200_host_" + f), C.c_void_p)
+                   for f in ("malloc", "calloc", "realloc", "free")]
+            self.ok(self.lib.GxB_init(0, *fns), "GxB_init")
+        else:
+            self.ok(self.lib.GrB_init(0), "GrB_init")        # GrB_NONBLOCKING
 
     # ---- plumbing ---------------------------------------------------------------------------
     def ok(self, info: int, where: str) -> None:
@@ -114,10 +133,11 @@ class GraphBLAS:
         self.shim.gb200_shim_last(C.byref(ms), C.byref(fl))
         return ms.value, fl.value
 
-    @staticmethod
-    def _malloc_copy(a: np.ndarray) -> C.c_void_p:
+    def _malloc_copy(self, a: np.ndarray) -> C.c_void_p:
+        """a copy of `a` in memory from the allocator GraphBLAS was started with (import hands
+        ownership of the arrays to the library, which later frees them with that allocator)"""
         n = max(a.nbytes, 8)
-        p = _libc.malloc(n)
+        p = self.host_malloc(n) if self.host_malloc is not None else _libc.malloc(n)
         if a.nbytes:
             C.memmove(p, a.ctypes.data, a.nbytes)
         return C.c_void_p(p)
@@ -175,16 +195,15 @@ class GraphBLAS:
             out["Ah"] = self._take(ph, nvec.value, np.int64)
         return out
 
-    @staticmethod
-    def _take(ptr: C.c_void_p, n: int, dt) -> np.ndarray:
+    def _take(self, ptr: C.c_void_p, n: int, dt) -> np.ndarray:
         dt = np.dtype(dt)
         if not ptr.value or n == 0:
             if ptr.value:
-                _libc.free(ptr)
+                self._free(ptr)
             return np.zeros(0, dtype=dt)
         buf = (C.c_char * (n * dt.itemsize)).from_address(ptr.value)
         a = np.frombuffer(buf, dtype=dt, count=n).copy()
-        _libc.free(ptr)
+        self._free(ptr)
         return a
 
     def type_name(self, t: C.c_void_p) -> str:

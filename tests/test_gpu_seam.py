@@ -302,15 +302,15 @@ def test_masked_dot_hubs(iso, add, mult, t):
 
 
 @pytest.mark.parametrize("iso", [True, False])
-@pytest.mark.parametrize("bits", ["4096", "1024", "old"])
+@pytest.mark.parametrize("bits", ["4096", "1024", "512", "old"])
 def test_masked_dot_hub_variants(monkeypatch, iso, bits):
-    """the hub owners through (a) several bitmap parts of the flat kernel (GB200_DOTF_BM_BITS=4096: the
-    12000-wide index range takes 3 parts), (b) more parts than the flat kernel accepts (1024: the segmented
-    cuckoo kernel serves them), (c) the round-1 kernels alone (GB200_DOTF=0): same T as the oracle"""
+    """the hub owners through (a) several bitmap parts of the row-walk kernel (GB200_DOTR_BM_BITS=4096:
+    the 12000-wide index range takes 3 parts; 1024: 12 parts), (b) more parts than it accepts (512: the
+    segmented cuckoo kernel serves them), (c) the round-1 kernels alone (GB200_DOTR=0): same T as the oracle"""
     if bits == "old":
-        monkeypatch.setenv("GB200_DOTF", "0")
+        monkeypatch.setenv("GB200_DOTR", "0")
     else:
-        monkeypatch.setenv("GB200_DOTF_BM_BITS", bits)
+        monkeypatch.setenv("GB200_DOTR_BM_BITS", bits)
     for add, mult, t in (("PLUS", "TIMES", "INT64"), ("MIN", "PLUS", "FP64"), ("LXOR", "LOR", "BOOL")):
         test_masked_dot_hubs(iso, add, mult, t)
 

@@ -19,9 +19,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 VARIANTS = [
     ("default", {}),
-    ("old", {"GB200_DOTF": "0"}),
-    ("valued_old", {"GB200_DOTF": "0", "GB200_DOTG_ISO": "0"}),
-    ("bm_half", {"GB200_DOTF_BM_BITS": "884736"}),
+    ("old", {"GB200_DOTR": "0"}),
+    ("valued_old", {"GB200_DOTR": "0", "GB200_DOTG_ISO": "0"}),
+    ("bm_half", {"GB200_DOTR_BM_BITS": "753664"}),
     ("notrim", {"GB200_DOTG_TRIM": "0"}),
     ("chunk256", {"GB200_DOTG_CHUNK": "256"}),
     ("chunk512", {"GB200_DOTG_CHUNK": "512"}),
@@ -33,8 +33,8 @@ VARIANTS = [
     ("valued", {"GB200_DOTG_ISO": "0"}),
     ("valued_notrim", {"GB200_DOTG_ISO": "0", "GB200_DOTG_TRIM": "0"}),
 ]
-KEYS = ("GB200_DOTG_TRIM", "GB200_DOTG_HUB_CHUNK", "GB200_DOTG_CHUNK", "GB200_DOTG_ISO", "GB200_DOTF",
-        "GB200_DOTF_BM_BITS")
+KEYS = ("GB200_DOTG_TRIM", "GB200_DOTG_HUB_CHUNK", "GB200_DOTG_CHUNK", "GB200_DOTG_ISO", "GB200_DOTR",
+        "GB200_DOTR_BM_BITS")
 # the answer of the first measured run (profiles/r1_trim): a base that is itself wrong is noticed
 KNOWN = {22: (44374678, 2111700731)}
 

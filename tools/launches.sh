@@ -3,4 +3,4 @@
 # bench.py step (ncu --metrics gpu__time_duration.sum; cold-cache, serialised: shares, not absolutes)
 out=$1; shift
 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:gb200:: -c 3000 --csv \
-    --log-file $out python bench.py "$@" --steps 1 --warmup 0 --no-cpu --no-e2e > ${out%.csv}.log 2>&1
+    --log-file $out python bench.py "$@" --steps 1 --warmup 0 --no-cpu --no-e2e --no-api --no-secondary > ${out%.csv}.log 2>&1
