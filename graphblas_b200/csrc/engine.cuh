@@ -139,6 +139,7 @@ namespace gb200 {
 // engine_util.cu
 gb200_status scan_i64 (const int64_t *in, int64_t *out, int64_t n) ;     // out has n+1 entries
 gb200_status scan_u8  (const uint8_t *in, int64_t *out, int64_t n) ;
+gb200_status scan_i32 (const int32_t *in, int64_t *out, int64_t n) ;     // items < 2^26 each
 gb200_status read_i64 (const int64_t *dptr, int64_t *host) ;             // syncs the stream
 gb200_status fill_bits (void *dst, int elem_size, uint64_t bits, int64_t n) ;
 uint64_t identity_bits (int z_code, int add_opcode, int *acc_size) ;

@@ -120,108 +120,108 @@ __device__ __forceinline__ void dotg_trim (const int32_t *__restrict__ Wi, int64
     else t1 = w1 ;
 }
 
-// per mask entry: which vector owns the pair and how long the walk is.  own = 1: B(:,j) owns and
-// A(:,i) is walked (wl > 0); A-owned pairs have wl < 0 and are counted per vector of A; dead: wl = 0.
-// ws = where the (trimmed) walk starts inside the walked list.
-// Pairs whose owner is shorter than DOTG_SMALL are not worth a shared-memory table: small = 1.
+// ---- set-up of the masked dot: two passes over the mask entries -------------------------------------
+// A pair is DEAD (an empty side, or nothing left after the trim), SMALL (owner shorter than DOTG_SMALL:
+// dot_kernel, no table), B-OWNED (B(:,j) is the longer list: A(:,i) is walked) or A-OWNED.  B-owned
+// pairs keep the mask's order, so the tasks of an owner B(:,j) are a contiguous run found by a scan;
+// A-owned pairs are regrouped by i with a counting sort (counts by atomics in the first pass, cursors in
+// the second).  A TASK is one pair, or one DOTG_SEG-long piece of a pair with a longer walk.
+enum { PK_DEAD = 0, PK_SMALL = 1, PK_BOWN = 2, PK_AOWN = 3 } ;
+
+// pass 1: classification with the trim.  w0 [e] = where the (trimmed) walk starts in the walked matrix,
+// lk [e] = its length | kind << 30, nt0 [e] = tasks of a B-owned pair (else 0), cntA [ka] += tasks of an
+// A-owned pair, slist = the small pairs (any order: they are independent).
 __global__ void dotg_classify_kernel (DMat A, DMat B, DMat M, const int32_t *__restrict__ mvec,
-    int64_t mnz, int trim, uint8_t *__restrict__ own, uint8_t *__restrict__ small,
-    int32_t *__restrict__ wl, int32_t *__restrict__ ws, unsigned long long *__restrict__ cntA)
+    int64_t mnz, int trim, int64_t *__restrict__ w0out, int32_t *__restrict__ lk, int32_t *__restrict__ nt0,
+    unsigned long long *__restrict__ cntA, int32_t *__restrict__ slist, unsigned int *__restrict__ nsmall)
 {
-    for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; e < mnz ;
-        e += (int64_t) gridDim.x * blockDim.x)
+    const int lane = threadIdx.x & 31 ;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x ;
+    const int64_t niter = (mnz + stride - 1) / stride ;
+    int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ;
+    for (int64_t itn = 0 ; itn < niter ; itn++, e += stride)
     {
-        uint8_t o = 0, sm = 0 ;
-        int32_t w = 0, s = 0 ;
-        const int64_t ka = dm_vecpos (A, M.i [e]) ;
-        const int64_t kb = dm_vecpos (B, dm_vecname (M, mvec [e])) ;
-        if (ka >= 0 && kb >= 0)
+        int kind = PK_DEAD ;
+        int32_t len = 0, ntk = 0 ;
+        int64_t wstart = 0 ;
+        if (e < mnz)
         {
-            const int64_t pa = A.p [ka], pae = A.p [ka+1], pb = B.p [kb], pbe = B.p [kb+1] ;
-            const int64_t ainz = pae - pa, bjnz = pbe - pb ;
-            if (ainz > 0 && bjnz > 0)
+            const int64_t ka = dm_vecpos (A, M.i [e]) ;
+            const int64_t kb = dm_vecpos (B, dm_vecname (M, mvec [e])) ;
+            if (ka >= 0 && kb >= 0)
             {
-                const bool walkA = dot_walkA (ainz, bjnz, A.vlen) ;
-                const int64_t olen = walkA ? bjnz : ainz ;
-                if (olen < DOTG_SMALL) { sm = 1 ; w = 1 ; }
-                else
+                const int64_t pa = A.p [ka], pae = A.p [ka+1], pb = B.p [kb], pbe = B.p [kb+1] ;
+                const int64_t ainz = pae - pa, bjnz = pbe - pb ;
+                if (ainz > 0 && bjnz > 0)
                 {
-                    const int64_t w0 = walkA ? pa : pb, w1 = walkA ? pae : pbe ;
-                    int64_t t0 = w0, t1 = w1 ;
-                    if (trim)
+                    const bool walkA = dot_walkA (ainz, bjnz, A.vlen) ;
+                    const int64_t olen = walkA ? bjnz : ainz ;
+                    if (olen < DOTG_SMALL) kind = PK_SMALL ;
+                    else
                     {
-                        const int32_t *__restrict__ Oi = walkA ? B.i : A.i ;
-                        const int64_t o0 = walkA ? pb : pa, o1 = walkA ? pbe : pae ;
-                        dotg_trim (walkA ? A.i : B.i, w0, w1, __ldg (Oi + o0), __ldg (Oi + o1 - 1), t0, t1) ;
-                    }
-                    const int32_t len = (int32_t) (t1 - t0) ;
-                    s = (int32_t) (t0 - w0) ;
-                    if (len > 0)
-                    {
-                        if (walkA) { o = 1 ; w = len ; }
-                        else { w = -len ; atomicAdd (cntA + ka, 1ULL) ; }
+                        const int64_t wa = walkA ? pa : pb, wb = walkA ? pae : pbe ;
+                        int64_t t0 = wa, t1 = wb ;
+                        if (trim)
+                        {
+                            const int32_t *__restrict__ Oi = walkA ? B.i : A.i ;
+                            const int64_t o0 = walkA ? pb : pa, o1 = walkA ? pbe : pae ;
+                            dotg_trim (walkA ? A.i : B.i, wa, wb, __ldg (Oi + o0), __ldg (Oi + o1 - 1), t0, t1) ;
+                        }
+                        len = (int32_t) (t1 - t0) ;
+                        wstart = t0 ;
+                        if (len > 0)
+                        {
+                            ntk = (len + DOTG_SEG - 1) / DOTG_SEG ;
+                            if (walkA) kind = PK_BOWN ;
+                            else { kind = PK_AOWN ; atomicAdd (cntA + ka, (unsigned long long) ntk) ; }
+                        }
                     }
                 }
             }
+            w0out [e] = wstart ;
+            lk [e] = len | (kind << 30) ;
+            nt0 [e] = (kind == PK_BOWN) ? ntk : 0 ;
         }
-        own [e] = o ;
-        small [e] = sm ;
-        wl [e] = w ;
-        ws [e] = s ;
+        // the small pairs of the warp are appended with one atomic
+        const unsigned sm = __ballot_sync (0xffffffffu, kind == PK_SMALL) ;
+        if (sm)
+        {
+            unsigned int base = 0 ;
+            if (lane == 0) base = atomicAdd (nsmall, (unsigned int) __popc (sm)) ;
+            base = __shfl_sync (0xffffffffu, base, 0) ;
+            if (kind == PK_SMALL) slist [base + __popc (sm & ((1u << lane) - 1u))] = (int32_t) e ;
+        }
     }
 }
 
-// plist [0..n0) = B-owned entries in mask order; plist [n0..n0+n1) = A-owned entries grouped by vector
-// of A; slist = the small pairs in mask order
-__global__ void dotg_lists_kernel (DMat A, DMat M, const uint8_t *__restrict__ own,
-    const uint8_t *__restrict__ small, const int32_t *__restrict__ wl, int64_t mnz,
-    const int64_t *__restrict__ pos0, const int64_t *__restrict__ poss,
-    const int64_t *__restrict__ offA, unsigned long long *__restrict__ curA, int64_t n0,
-    int32_t *__restrict__ plist, int32_t *__restrict__ slist, int64_t *__restrict__ nt)
+// pass 2: the task records.  B-owned pairs: at toff0 [e]; A-owned pairs: behind them, grouped by the
+// vector of A (offA = scan of cntA, curA = running cursor of every vector).
+__global__ void dotg_scatter_kernel (DMat A, DMat M, int64_t mnz, const int64_t *__restrict__ w0in,
+    const int32_t *__restrict__ lk, const int64_t *__restrict__ toff0, const int64_t *__restrict__ offA,
+    unsigned long long *__restrict__ curA, int64_t ntask0, DotTask *__restrict__ tasks)
 {
-    // nt [t] = tasks of the pair at plist [t]: one per DOTG_SEG-long piece of its walk
     for (int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; e < mnz ;
         e += (int64_t) gridDim.x * blockDim.x)
     {
-        const int32_t w = wl [e] ;
-        if (own [e])
-        {
-            const int64_t t = pos0 [e] ;
-            plist [t] = (int32_t) e ;
-            nt [t] = (w + DOTG_SEG - 1) / DOTG_SEG ;
-        }
-        else if (small [e]) slist [poss [e]] = (int32_t) e ;
-        else if (w < 0)
+        const int32_t v = lk [e] ;
+        const int kind = (int) (((uint32_t) v) >> 30) ;
+        if (kind < PK_BOWN) continue ;
+        const int32_t w = v & 0x3fffffff ;
+        const int32_t ntk = (w + DOTG_SEG - 1) / DOTG_SEG ;
+        int64_t q ;
+        if (kind == PK_BOWN) q = toff0 [e] ;
+        else
         {
             const int64_t ka = dm_vecpos (A, M.i [e]) ;
-            const int64_t t = n0 + offA [ka] + (int64_t) atomicAdd (curA + ka, 1ULL) ;
-            plist [t] = (int32_t) e ;
-            nt [t] = (-w + DOTG_SEG - 1) / DOTG_SEG ;
+            q = ntask0 + offA [ka] + (int64_t) atomicAdd (curA + ka, (unsigned long long) ntk) ;
         }
-    }
-}
-
-__global__ void dotg_tasks_kernel (DMat A, DMat B, DMat M, const int32_t *__restrict__ mvec,
-    int orient, const int32_t *__restrict__ pl, int64_t np, const int32_t *__restrict__ wl,
-    const int32_t *__restrict__ ws, const int64_t *__restrict__ toff, DotTask *__restrict__ tasks)
-{
-    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < np ;
-        t += (int64_t) gridDim.x * blockDim.x)
-    {
-        const int32_t e = pl [t] ;
-        int32_t w = wl [e] ;
-        if (w < 0) w = -w ;
-        int64_t w0 ;
-        if (orient) w0 = B.p [dm_vecpos (B, dm_vecname (M, mvec [e]))] ;       // walk B(:,j)
-        else w0 = A.p [dm_vecpos (A, M.i [e])] ;                               // walk A(:,i)
-        w0 += ws [e] ;                                                          // the trimmed part of it
-        int64_t q = toff [t] ;
+        const int64_t ws = w0in [e] ;
         const bool split = (w > DOTG_SEG) ;
         for (int32_t s0 = 0 ; s0 < w ; s0 += DOTG_SEG, q++)
         {
             DotTask tk ;
             const int32_t len = (w - s0 < DOTG_SEG) ? (w - s0) : DOTG_SEG ;
-            tk.e = e ; tk.len = split ? -len : len ; tk.w0 = w0 + s0 ;
+            tk.e = (int32_t) e ; tk.len = split ? -len : len ; tk.w0 = ws + s0 ;
             tasks [q] = tk ;
         }
     }
@@ -230,9 +230,10 @@ __global__ void dotg_tasks_kernel (DMat A, DMat B, DMat M, const int32_t *__rest
 // Owner classes.  0: the owner fits one load of the cuckoo tables (or is dense): row-walk kernel,
 // DOTG_CHUNK tasks per item.  1: a longer owner ("hub") whose index range fits DOTR_MAXPARTS bitmap
 // parts: row-walk kernel with a shared-memory bitmap, big items.  2: any other hub: the segmented
-// cuckoo kernel dotg_kernel<HUB>, big items.  flat == 0 (GB200_DOTR=0, for A/B runs) sends class 0 to
+// cuckoo kernel dotg_kernel<HUB>, big items.  3: a tiny owner (<= dotr_tiny_cap entries): the work item
+// goes to a warp (dotr_warp_kernel).  flat == 0 (GB200_DOTR=0, for A/B runs) sends classes 0 and 3 to
 // dotg_kernel<!HUB> and every hub to class 2.
-struct DotgClasses { int64_t cap ; int64_t bm_bits ; int flat ; int64_t chunk [3] ; } ;
+struct DotgClasses { int64_t cap ; int64_t tiny ; int64_t bm_bits ; int flat ; int64_t chunk [4] ; } ;
 
 __device__ __forceinline__ int dotg_class_of (const DMat &O, const DMat &M, int orient, int64_t v,
     const DotgClasses &K)
@@ -242,6 +243,7 @@ __device__ __forceinline__ int dotg_class_of (const DMat &O, const DMat &M, int 
     if (ko < 0) return 0 ;
     const int64_t o0 = O.p [ko], o1 = O.p [ko+1] ;
     const int64_t olen = o1 - o0 ;
+    if (olen <= K.tiny && olen != O.vlen) return 3 ;     // tiny owner: a warp takes the item
     if (olen <= K.cap || olen == O.vlen) return 0 ;
     if (!K.flat) return 2 ;
     const int64_t lo0 = ((int64_t) __ldg (O.i + o0)) & ~(int64_t) 31 ;
@@ -364,41 +366,39 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             // 0: warp per task / lane per task (dotg_kernel) instead of the row walk (kernels_dotr.cuh)
             const char *flat_env = getenv ("GB200_DOTR") ;
             const bool flat = !(flat_env != nullptr && atoi (flat_env) == 0) ;
-            DevBuf own, small, wl, ws, cntA, offA, curA, pos0, poss, off0, plist, slist ;
-            GB200_TRY (own.alloc (mnz)) ;
-            GB200_TRY (small.alloc (mnz)) ;
-            GB200_TRY (wl.alloc (mnz * sizeof (int32_t))) ;
-            GB200_TRY (ws.alloc (mnz * sizeof (int32_t))) ;
+            DevBuf w0buf, lk, nt0, cntA, offA, curA, toff0, off0, slist, nsmall, tasks ;
+            GB200_TRY (w0buf.alloc (mnz * sizeof (int64_t))) ;
+            GB200_TRY (lk.alloc (mnz * sizeof (int32_t))) ;
+            GB200_TRY (nt0.alloc (mnz * sizeof (int32_t))) ;
             GB200_TRY (cntA.alloc ((anvec > 0 ? anvec : 1) * sizeof (int64_t))) ;
             GB200_TRY (curA.alloc ((anvec > 0 ? anvec : 1) * sizeof (int64_t))) ;
             GB200_TRY (offA.alloc ((anvec + 1) * sizeof (int64_t))) ;
-            GB200_TRY (pos0.alloc ((mnz + 1) * sizeof (int64_t))) ;
-            GB200_TRY (poss.alloc ((mnz + 1) * sizeof (int64_t))) ;
+            GB200_TRY (toff0.alloc ((mnz + 1) * sizeof (int64_t))) ;
             GB200_TRY (off0.alloc ((Mv.nvec + 1) * sizeof (int64_t))) ;
-            GB200_TRY (plist.alloc (mnz * sizeof (int32_t))) ;
             GB200_TRY (slist.alloc (mnz * sizeof (int32_t))) ;
+            GB200_TRY (nsmall.alloc (8)) ;
             GB200_CUDA (cudaMemsetAsync (cntA.ptr, 0, cntA.bytes, c.stream)) ;
             GB200_CUDA (cudaMemsetAsync (curA.ptr, 0, curA.bytes, c.stream)) ;
+            GB200_CUDA (cudaMemsetAsync (nsmall.ptr, 0, 8, c.stream)) ;
             dotg_classify_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, B, Mv,
-                mvec.as<int32_t> (), mnz, trim, own.as<uint8_t> (), small.as<uint8_t> (), wl.as<int32_t> (),
-                ws.as<int32_t> (), cntA.as<unsigned long long> ()) ;
+                mvec.as<int32_t> (), mnz, trim, w0buf.as<int64_t> (), lk.as<int32_t> (), nt0.as<int32_t> (),
+                cntA.as<unsigned long long> (), slist.as<int32_t> (), nsmall.as<unsigned int> ()) ;
             count_launch () ;
-            // B-owned pairs keep the mask's order (a compaction); A-owned pairs: counting sort by i
-            GB200_TRY (scan_u8 (own.as<uint8_t> (), pos0.as<int64_t> (), mnz)) ;
-            GB200_TRY (scan_u8 (small.as<uint8_t> (), poss.as<int64_t> (), mnz)) ;
+            // B-owned pairs keep the mask's order (a scan of their task counts); A-owned: counting sort by i
+            GB200_TRY (scan_i32 (nt0.as<int32_t> (), toff0.as<int64_t> (), mnz)) ;
             GB200_TRY (scan_i64 (cntA.as<int64_t> (), offA.as<int64_t> (), anvec)) ;
-            int64_t n0 = 0, n1 = 0, ns = 0 ;
-            GB200_TRY (read_i64 (pos0.as<int64_t> () + mnz, &n0)) ;
-            GB200_TRY (read_i64 (poss.as<int64_t> () + mnz, &ns)) ;
-            GB200_TRY (read_i64 (offA.as<int64_t> () + anvec, &n1)) ;
-            DevBuf ntall ;
-            GB200_TRY (ntall.alloc ((n0 + n1 + 1) * sizeof (int64_t))) ;
-            dotg_lists_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, Mv,
-                own.as<uint8_t> (), small.as<uint8_t> (), wl.as<int32_t> (), mnz, pos0.as<int64_t> (),
-                poss.as<int64_t> (), offA.as<int64_t> (), curA.as<unsigned long long> (), n0,
-                plist.as<int32_t> (), slist.as<int32_t> (), ntall.as<int64_t> ()) ;
+            int64_t nt_b = 0, nt_a = 0, ns = 0 ;
+            GB200_TRY (read_i64 (toff0.as<int64_t> () + mnz, &nt_b)) ;
+            GB200_TRY (read_i64 (offA.as<int64_t> () + anvec, &nt_a)) ;
+            GB200_TRY (read_i64 (nsmall.as<int64_t> (), &ns)) ;
+            ns &= 0xffffffffLL ;
+            GB200_TRY (tasks.alloc ((nt_b + nt_a + 1) * sizeof (DotTask))) ;
+            dotg_scatter_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, Mv, mnz,
+                w0buf.as<int64_t> (), lk.as<int32_t> (), toff0.as<int64_t> (), offA.as<int64_t> (),
+                curA.as<unsigned long long> (), nt_b, tasks.as<DotTask> ()) ;
+            // first task of every owner B(:,j): the scan at the start of the mask's vector j
             dot_cum_list_kernel <<<grid_cap ((Mv.nvec + 256) / 256, 8), 256, 0, c.stream>>> (Mv.p,
-                pos0.as<int64_t> (), Mv.nvec, off0.as<int64_t> ()) ;
+                toff0.as<int64_t> (), Mv.nvec, off0.as<int64_t> ()) ;
             count_launch (2) ;
             if (ns > 0)
             {
@@ -422,29 +422,16 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             ga.mult_op = s.mult_opcode ; ga.flip = s.flipxy ;
             for (int orient = 0 ; orient < 2 ; orient++)
             {
-                const int64_t np = orient ? n1 : n0 ;           // pairs of this orientation
-                if (np == 0) continue ;
-                const int32_t *pl = plist.as<int32_t> () + (orient ? n0 : 0) ;
-                const int64_t *off = orient ? offA.as<int64_t> () : off0.as<int64_t> () ;
+                const int64_t ntasks = orient ? nt_a : nt_b ;   // tasks of this orientation
+                if (ntasks == 0) continue ;
+                // task range of owner v: [otoff [v], otoff [v+1]) of this orientation's tasks
+                const int64_t *otoff = orient ? offA.as<int64_t> () : off0.as<int64_t> () ;
                 const int64_t nown = orient ? anvec : Mv.nvec ;
-                // tasks: one per pair, or one per DOTG_SEG-long segment of a long walk
-                DevBuf toff, tasks, otoff, nch, ioff ;
-                GB200_TRY (toff.alloc ((np + 1) * sizeof (int64_t))) ;
-                GB200_TRY (scan_i64 (ntall.as<int64_t> () + (orient ? n0 : 0), toff.as<int64_t> (), np)) ;
-                int64_t ntasks = 0 ;
-                GB200_TRY (read_i64 (toff.as<int64_t> () + np, &ntasks)) ;
-                GB200_TRY (tasks.alloc (ntasks * sizeof (DotTask))) ;
-                dotg_tasks_kernel <<<grid_cap ((np + 255) / 256, 16), 256, 0, c.stream>>> (A, B, Mv,
-                    mvec.as<int32_t> (), orient, pl, np, wl.as<int32_t> (), ws.as<int32_t> (),
-                    toff.as<int64_t> (), tasks.as<DotTask> ()) ;
-                // task range of every owner, cut into work items: hub owners first (the big items)
-                GB200_TRY (otoff.alloc ((nown + 1) * sizeof (int64_t))) ;
+                DevBuf nch, ioff ;
                 GB200_TRY (nch.alloc ((nown > 0 ? nown : 1) * sizeof (int64_t))) ;
                 GB200_TRY (ioff.alloc ((nown + 1) * sizeof (int64_t))) ;
-                dot_cum_list_kernel <<<grid_cap ((nown + 256) / 256, 8), 256, 0, c.stream>>> (off,
-                    toff.as<int64_t> (), nown, otoff.as<int64_t> ()) ;
-                count_launch () ;
-                ga.tasks = tasks.as<DotTask> () ; ga.orient = orient ;
+                ga.tasks = tasks.as<DotTask> () + (orient ? nt_b : 0) ; ga.orient = orient ;
+                // the owners' task ranges are cut into work items: hub owners first (the big items)
                 // Tasks per hub item: big items amortise the owner's table, but there must also be
                 // several items per resident block or a few big hubs serialise the launch (one rank of
                 // an 8-GPU run holds an eighth of the hubs)
@@ -459,6 +446,9 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 if (reg_chunk < 1) reg_chunk = DOTG_CHUNK ;
                 DotgClasses K ;
                 K.cap = cap ; K.bm_bits = dotr_bm_bits (iso) ; K.flat = flat ? 1 : 0 ;
+                // 0: no warp items (tiny owners go to the block kernel), for A/B runs
+                const char *tiny_env = getenv ("GB200_DOTR_TINY") ;
+                K.tiny = (flat && !(tiny_env != nullptr && atoi (tiny_env) == 0)) ? dotr_tiny_cap (iso) : 0 ;
                 // smaller bitmap parts (a multiple of 32 indices): lets a test reach several parts
                 if (getenv ("GB200_DOTR_BM_BITS"))
                 {
@@ -467,11 +457,16 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 }
                 ga.bm_bits = K.bm_bits ;
                 K.chunk [0] = reg_chunk ; K.chunk [1] = hub_chunk ; K.chunk [2] = hub_chunk ;
-                for (int cls = 2 ; cls >= 0 ; cls--)
+                K.chunk [3] = 256 ;
+                // hubs first (the big items), tiny owners last (they fill the tail of the machine)
+                static const int class_order [4] = { 2, 1, 0, 3 } ;
+                for (int co = 0 ; co < 4 ; co++)
                 {
+                    const int cls = class_order [co] ;
+                    if (cls == 3 && K.tiny == 0) continue ;
                     if (cls == 1 && !flat) continue ;
                     dotg_nchunks_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                        orient ? A : B, Mv, orient, K, cls, otoff.as<int64_t> (), nown, nch.as<int64_t> ()) ;
+                        orient ? A : B, Mv, orient, K, cls, otoff, nown, nch.as<int64_t> ()) ;
                     count_launch () ;
                     GB200_TRY (scan_i64 (nch.as<int64_t> (), ioff.as<int64_t> (), nown)) ;
                     int64_t nitems = 0 ;
@@ -480,7 +475,7 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                     DevBuf items ;
                     GB200_TRY (items.alloc (nitems * sizeof (DotItem))) ;
                     dotg_items_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                        orient ? A : B, Mv, orient, K, cls, otoff.as<int64_t> (), ioff.as<int64_t> (), nown,
+                        orient ? A : B, Mv, orient, K, cls, otoff, ioff.as<int64_t> (), nown,
                         items.as<DotItem> ()) ;
                     count_launch () ;
                     GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 8, c.stream)) ;
@@ -488,6 +483,7 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                     int fam, per_sm, threads ;
                     if (cls == 2) { fam = iso ? FAM_DOTG_HUB_ISO : FAM_DOTG_HUB ; per_sm = 2 ; threads = DOTG_THREADS ; }
                     else if (cls == 1) { fam = iso ? FAM_DOTR_BM_ISO : FAM_DOTR_BM ; per_sm = 1 ; threads = DOTR_BM_THREADS ; }
+                    else if (cls == 3) { fam = iso ? FAM_DOTR_WARP_ISO : FAM_DOTR_WARP ; per_sm = iso ? 3 : 2 ; threads = DOTR_THREADS ; }
                     else if (flat) { fam = iso ? FAM_DOTR_ISO : FAM_DOTR ; per_sm = iso ? 3 : 2 ; threads = DOTR_THREADS ; }
                     else { fam = iso ? FAM_DOTG_ISO : FAM_DOTG ; per_sm = iso ? 3 : 2 ; threads = DOTG_THREADS ; }
                     if (!launch_typed (s.xy_code, fam, s.z_code, s.add_opcode, s.mult_opcode, &ga,

@@ -300,6 +300,7 @@ static gb200_status scan_any (const InT *in, int64_t *out, int64_t n)
 
 gb200_status scan_i64 (const int64_t *in, int64_t *out, int64_t n) { return scan_any<int64_t> (in, out, n) ; }
 gb200_status scan_u8  (const uint8_t *in, int64_t *out, int64_t n) { return scan_any<uint8_t> (in, out, n) ; }
+gb200_status scan_i32 (const int32_t *in, int64_t *out, int64_t n) { return scan_any<int32_t> (in, out, n) ; }
 
 gb200_status read_i64 (const int64_t *dptr, int64_t *host)
 {

@@ -781,7 +781,8 @@ namespace gb200 {
 enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_DOTV = 4,
     FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9,
     FAM_DOTG_ISO = 10, FAM_SPMV_OCC8 = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13,
-    FAM_DOTR = 14, FAM_DOTR_ISO = 15, FAM_DOTR_BM = 16, FAM_DOTR_BM_ISO = 17 } ;
+    FAM_DOTR = 14, FAM_DOTR_ISO = 15, FAM_DOTR_BM = 16, FAM_DOTR_BM_ISO = 17, FAM_DOTR_WARP = 18,
+    FAM_DOTR_WARP_ISO = 19 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -839,6 +840,21 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
             dotr_kernel<S, true, true> <<<cfg.grid, cfg.block, DOTR_BM_SMEM, cfg.stream>>> (ga) ;
         else
             dotr_kernel<S, false, true> <<<cfg.grid, cfg.block, DOTR_BM_SMEM, cfg.stream>>> (ga) ;
+    }
+    else if (family == FAM_DOTR_WARP || family == FAM_DOTR_WARP_ISO)
+    {
+        static bool attr_set = false ;          // one flag per instantiation
+        if (!attr_set)
+        {
+            cudaFuncSetAttribute (dotr_warp_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            cudaFuncSetAttribute (dotr_warp_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            attr_set = true ;
+        }
+        const DotGArgs &ga = *(const DotGArgs *) args ;
+        if (family == FAM_DOTR_WARP_ISO)
+            dotr_warp_kernel<S, true> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+        else
+            dotr_warp_kernel<S, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
     }
     else if (family == FAM_DOTV)
         dotv_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotVArgs *) args) ;

@@ -10,12 +10,8 @@
 //
 //   * a WARP claims a batch of up to 32 tasks with one shared-memory atomic, lane l keeps the
 //     descriptor of task l, and the warp walks the tasks one after another in ROWS of 32 consecutive
-//     indices: one coalesced load, one probe per lane, one vote.  The first two rows of the next task
-//     are requested before the current task is walked, so a warp always has loads in flight although
-//     most tasks are only a few rows long.  Per row: ~16 warp instructions and, for the bitmap, ~5
-//     wavefronts of the L1/shared-memory pipe (measured before: 65 instructions per row in
-//     dotg_kernel's regular walk; 11 wavefronts per 32 probes in its lane-per-task hub walk, whose 32
-//     lanes each load their own 32 bytes).
+//     indices: one coalesced load, one branch-free probe per lane, one vote; four rows per iteration
+//     with their loads in flight.
 //   * regular owners (<= dotg_cap entries): the cuckoo tables of dotg_kernel.  A table that cannot be
 //     built falls back to a binary search of the owner's list in global memory for that item.
 //   * hub owners: a BITMAP over a part of the owner's index range in shared memory -- one shared
@@ -38,7 +34,8 @@ constexpr int DOTR_REBUILDS = 30 ;
 // indices covered by one bitmap part
 __host__ __device__ constexpr int64_t dotr_bm_bits (bool iso)
 {
-    return iso ? (int64_t) DOTR_BM_BYTES * 8 : (int64_t) DOTR_BM_BYTES * 4 ;
+    // one word is kept back: bit `nbits` of a part must exist and be zero (dotr_probe)
+    return iso ? (int64_t) DOTR_BM_BYTES * 8 - 32 : (int64_t) DOTR_BM_BYTES * 4 - 32 ;
 }
 
 enum { DOTR_CUCKOO = 0, DOTR_DENSE = 1, DOTR_BSEARCH = 2, DOTR_BITMAP = 3 } ;
@@ -65,50 +62,98 @@ template <class S> struct DotRCtx
     int32_t hi ;                // lo + nbits
 } ;
 
-// one probe of index kq (NOKEY: a lane past the end of the list, never a hit)
-template <class S, bool ISO, int MODE, class slot_t>
-__device__ __forceinline__ bool dotr_probe (const DotRCtx<S> &g, const void *table, uint32_t kq, uint32_t &pos)
+// The owner's table in shared memory, read through a 32-bit shared-memory address (ld.shared with a
+// register base: no generic-to-shared address arithmetic in the probe).  word = 32-bit word index.
+struct SmemTab
+{
+#ifdef GB200_HOST_EMULATION
+    const uint32_t *base ;
+    __device__ __forceinline__ explicit SmemTab (const void *p) : base ((const uint32_t *) p) { }
+    __device__ __forceinline__ uint32_t ld (uint32_t word) const { return base [word] ; }
+    __device__ __forceinline__ uint64_t ld64 (uint32_t dword) const { return ((const uint64_t *) base) [dword] ; }
+#else
+    uint32_t base ;
+    __device__ __forceinline__ explicit SmemTab (const void *p) : base ((uint32_t) __cvta_generic_to_shared (p)) { }
+    __device__ __forceinline__ uint32_t ld (uint32_t word) const
+    {
+        uint32_t v ;
+        asm volatile ("ld.shared.u32 %0, [%1];" : "=r" (v) : "r" (base + (word << 2))) ;
+        return v ;
+    }
+    __device__ __forceinline__ uint64_t ld64 (uint32_t dword) const
+    {
+        uint64_t v ;
+        asm volatile ("ld.shared.u64 %0, [%1];" : "=l" (v) : "r" (base + (dword << 3))) ;
+        return v ;
+    }
+#endif
+} ;
+
+// what a probe needs, in registers
+struct DotRProbe
+{
+    uint32_t lo, nbits ;                // bitmap part: indices [lo, lo + nbits); bit nbits is zero
+    int32_t hi ;                        // bitmap: lo + nbits, or INT32_MAX for the owner's last part
+    uint32_t c1, c2 ; int sh ;          // cuckoo
+    const int32_t *Oi ; int olen ;      // BSEARCH
+} ;
+
+// one probe of index kq (NOKEY: a lane past the end of the list, never a hit); branch-free for the
+// bitmap and the cuckoo tables
+template <bool ISO, int MODE>
+__device__ __forceinline__ uint32_t dotr_probe (const DotRProbe &q, const SmemTab &tab, const SmemTab &tab2,
+    uint32_t kq, uint32_t &pos)
 {
     constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
     if constexpr (MODE == DOTR_BITMAP)
     {
-        const uint32_t *__restrict__ bm = (const uint32_t *) table ;
-        const uint32_t kk = kq - g.lo ;
-        bool hit = false ;
-        if (kk < g.nbits)
-        {
-            const uint32_t word = bm [kk >> 5] ;
-            hit = (word >> (kk & 31)) & 1u ;
-            if constexpr (!ISO)
-            {
-                const uint32_t *__restrict__ rk = bm + (DOTR_BM_BYTES / 8) ;
-                if (hit) pos = rk [kk >> 5] + __popc (word & ((1u << (kk & 31)) - 1u)) ;
-            }
-        }
+        // an index outside [lo, lo + nbits) lands on bit `nbits`, which is kept zero (no range branch)
+        uint32_t kk = kq - q.lo ;
+        kk = (kk < q.nbits) ? kk : q.nbits ;
+        const uint32_t w = kk >> 5 ;
+        const uint32_t word = tab.ld (w) ;
+        const uint32_t hit = (word >> (kk & 31)) & 1u ;
+        if constexpr (!ISO)
+            if (hit) pos = tab.ld ((DOTR_BM_BYTES / 8) + w) + __popc (word & ((1u << (kk & 31)) - 1u)) ;
         return hit ;
     }
     else if constexpr (MODE == DOTR_CUCKOO)
     {
-        const slot_t *__restrict__ tab = (const slot_t *) table ;
-        return dotg_probe<ISO, false, slot_t> (tab, tab + g.NS, kq, g.sh, g.c1, g.c2, pos) ;
+        if constexpr (ISO)
+        {
+            const uint32_t e1 = tab.ld ((kq * q.c1) >> q.sh) ;
+            const uint32_t e2 = tab2.ld ((kq * q.c2) >> q.sh) ;
+            return ((e1 == kq) | (e2 == kq)) ? 1u : 0u ;
+        }
+        else
+        {
+            const uint64_t e1 = tab.ld64 ((kq * q.c1) >> q.sh) ;
+            const uint64_t e2 = tab2.ld64 ((kq * q.c2) >> q.sh) ;
+            const bool h1 = ((uint32_t) e1 == kq), h2 = ((uint32_t) e2 == kq) ;
+            pos = (uint32_t) ((h1 ? e1 : e2) >> 32) ;
+            return (h1 | h2) ? 1u : 0u ;
+        }
     }
-    else if constexpr (MODE == DOTR_DENSE) { pos = kq ; return (kq != NOKEY) ; }
+    else if constexpr (MODE == DOTR_DENSE) { pos = kq ; return (kq != NOKEY) ? 1u : 0u ; }
     else
     {
-        int l = 0, h = (kq != NOKEY) ? g.olen : 0 ;
+        int l = 0, h = (kq != NOKEY) ? q.olen : 0 ;
         while (l < h)
         {
             const int mid = (l + h) >> 1 ;
-            const uint32_t v = (uint32_t) __ldg (g.Oi + mid) ;
-            if (v == kq) { pos = (uint32_t) mid ; return true ; }
+            const uint32_t v = (uint32_t) __ldg (q.Oi + mid) ;
+            if (v == kq) { pos = (uint32_t) mid ; return 1u ; }
             if (v < kq) l = mid + 1 ; else h = mid ;
         }
-        return false ;
+        return 0u ;
     }
 }
 
-// The warps of the block pull batches of tasks of the item until its counter runs out.
-// s_cur (BITMAP): per task of the item, the row at which the previous part left it.
+// The warps of the block pull batches of tasks of the item until its counter runs out.  A task is
+// walked in rows of 32 consecutive indices, DOTR_U rows per iteration with all their loads in flight.
+// s_cur (BITMAP, several parts): per task of the item, the row at which the previous part left it.
+constexpr int DOTR_U = 4 ;
+
 template <class S, bool ISO, int MODE, class slot_t>
 __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, const void *table,
     int *s_next, uint16_t *s_cur, int nwarps, unsigned long long &nm)
@@ -118,6 +163,13 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
     constexpr unsigned FULL = 0xffffffffu ;
     constexpr bool BITMAP = (MODE == DOTR_BITMAP) ;
     const int lane = threadIdx.x & 31 ;
+    const SmemTab tab (table) ;
+    DotRProbe q ;
+    const SmemTab tab2 ((const char *) table + (size_t) g.NS * sizeof (slot_t)) ;   // cuckoo: the second table
+    q.lo = g.lo ; q.nbits = g.nbits ;
+    q.hi = g.last ? INT32_MAX : g.hi ;
+    q.c1 = g.c1 ; q.c2 = g.c2 ; q.sh = g.sh ; q.Oi = g.Oi ; q.olen = g.olen ;
+    const bool cursors = BITMAP && g.multi ;
     while (true)
     {
         // ---- claim a batch: 32 tasks while the item is long, fewer towards its end (the warps of a
@@ -129,7 +181,7 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
             while (cur < g.ntask)
             {
                 const int rem = g.ntask - cur ;
-                int c = rem / (2 * nwarps) ;
+                int c = (nwarps > 0) ? rem / (2 * nwarps) : 32 ;        // nwarps == 0: the warp is alone
                 c = (c < 2) ? 2 : ((c > 32) ? 32 : c) ;
                 if (c > rem) c = rem ;
                 const int seen = atomicCAS (s_next, cur, cur + c) ;
@@ -140,8 +192,8 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
         t0 = __shfl_sync (FULL, t0, 0) ;
         nb = __shfl_sync (FULL, nb, 0) ;
         if (nb == 0) break ;
-        // ---- lane l keeps task t0 + l ------------------------------------------------------------
-        int len = 0, cur = 0 ;
+        // ---- lane l keeps task t0 + l: lc = its length | the row it resumes at << 16 -----------------
+        uint32_t lc = 0 ;
         int32_t e = 0 ;
         long long w0 = 0 ;
         bool split = false ;
@@ -149,87 +201,76 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
         {
             const DotTask d = g.tasks [t0 + lane] ;
             split = (d.len < 0) ;
-            len = split ? -d.len : d.len ;
+            lc = (uint32_t) (split ? -d.len : d.len) ;          // <= DOTG_SEG
             e = d.e ; w0 = d.w0 ;
-            if constexpr (BITMAP) if (g.multi) cur = (int) s_cur [t0 + lane] ;
+            if (cursors) lc |= ((uint32_t) s_cur [t0 + lane]) << 16 ;
         }
         uint32_t mycnt = 0 ;            // results of the task this lane keeps
         acc_t myacc = Mon::identity () ;
-        int mycur = cur ;
-        // rows 0 and 1 of the first task
-        int tl = __shfl_sync (FULL, len, 0), p0 = __shfl_sync (FULL, cur, 0) ;
-        const int32_t *wp = g.Wi + __shfl_sync (FULL, w0, 0) ;
-        uint32_t kA = NOKEY, kB = NOKEY ;
-        if (p0 + lane < tl) kA = (uint32_t) __ldg (wp + p0 + lane) ;
-        if (p0 + 32 + lane < tl) kB = (uint32_t) __ldg (wp + p0 + 32 + lane) ;
+        uint32_t mycur = lc >> 16 ;
         for (int t = 0 ; t < nb ; t++)
         {
-            // ---- request rows 0 and 1 of the next task before walking this one ------------------
-            int ntl = 0, np0 = 0 ;
-            const int32_t *nwp = wp ;
-            uint32_t nkA = NOKEY, nkB = NOKEY ;
-            if (t + 1 < nb)
-            {
-                ntl = __shfl_sync (FULL, len, t + 1) ; np0 = __shfl_sync (FULL, cur, t + 1) ;
-                nwp = g.Wi + __shfl_sync (FULL, w0, t + 1) ;
-                if (np0 + lane < ntl) nkA = (uint32_t) __ldg (nwp + np0 + lane) ;
-                if (np0 + 32 + lane < ntl) nkB = (uint32_t) __ldg (nwp + np0 + 32 + lane) ;
-            }
-            // ---- walk task t: rows of 32 indices, two per iteration ------------------------------
+            const uint32_t tlc = __shfl_sync (FULL, lc, t) ;
+            const int tl = (int) (tlc & 0xffffu), p0 = (int) (tlc >> 16) ;
+            const long long tw = __shfl_sync (FULL, w0, t) ;
             uint32_t cnt = 0 ;
             acc_t acc = Mon::identity () ;
             bool found = false ;
             int stop = tl ;             // BITMAP: where the next part resumes
-            const T *__restrict__ wx = g.Wx + (wp - g.Wi) ;
             if (p0 < tl)
             {
-                const int32_t *__restrict__ rp = wp + p0 + lane ;   // this lane's index of the row
-                int rem = tl - p0 - lane ;                          // > 32 u: the lane has one in row u
-                for (int p = p0 ; ; )
+                const int32_t *__restrict__ rp = g.Wi + tw + p0 + lane ;    // this lane's index of row 0
+                const T *__restrict__ rx = g.Wx + tw + p0 + lane ;
+                int rem = tl - p0 - lane ;                                  // > 32 u: an index in row u
+                for (int p = p0 ; p < tl ; p += 32 * DOTR_U, rp += 32 * DOTR_U, rx += 32 * DOTR_U, rem -= 32 * DOTR_U)
                 {
-                    bool over = false ;
+                    uint32_t k [DOTR_U] ;
                     #pragma unroll
-                    for (int u = 0 ; u < 2 ; u++)
+                    for (int u = 0 ; u < DOTR_U ; u++)
+                        k [u] = (rem > 32 * u) ? (uint32_t) __ldg (rp + 32 * u) : NOKEY ;
+                    // rows 0 and 1 are probed whatever they hold (a row past the end is all NOKEY: no
+                    // hit); rows 2 and 3 only if the task reaches them
+                    #pragma unroll
+                    for (int u = 0 ; u < DOTR_U ; u++)
                     {
-                        const int pr = p + 32 * u ;
-                        if (u > 0 && (pr >= tl || over)) continue ;         // warp-uniform
-                        const uint32_t kq = u ? kB : kA ;
+                        if (u == 2 && p + 64 >= tl) break ;                     // warp-uniform
                         uint32_t pos = 0 ;
-                        const bool hit = dotr_probe<S, ISO, MODE, slot_t> (g, table, kq, pos) ;
-                        if constexpr (ISO) cnt += hit ? 1u : 0u ;
+                        const uint32_t hit = dotr_probe<ISO, MODE> (q, tab, tab2, k [u], pos) ;
+                        if constexpr (ISO) cnt += hit ;
                         else if (hit)
                         {
-                            const T ov = g.Ox [pos], wv = wx [pr + lane] ;
+                            const T ov = g.Ox [pos], wv = rx [32 * u] ;
                             const acc_t prod = g.orient ? sr.product (ov, wv) : sr.product (wv, ov) ;
                             acc = found ? Mon::combine (acc, prod) : prod ;
                             found = true ; cnt++ ;
                         }
-                        if constexpr (BITMAP)
+                    }
+                    if constexpr (BITMAP)
+                    {
+                        // The lists are sorted: an index at or above hi ends this part's stretch (such an
+                        // index missed by the range test; hi = INT32_MAX in the owner's last part; NOKEY is
+                        // negative).  The next part resumes at the first row that holds one.
+                        int32_t mx = (int32_t) k [0] ;
+                        #pragma unroll
+                        for (int u = 1 ; u < DOTR_U ; u++) mx = ((int32_t) k [u] > mx) ? (int32_t) k [u] : mx ;
+                        if (__any_sync (FULL, mx >= q.hi))
                         {
-                            // the lists are sorted: an index at or above hi ends this part's stretch
-                            if (!g.last && __any_sync (FULL, (int32_t) kq >= g.hi)) { over = true ; stop = pr ; }
+                            stop = p + 32 * (DOTR_U - 1) ;
+                            #pragma unroll
+                            for (int u = DOTR_U - 2 ; u >= 0 ; u--)
+                                if (__any_sync (FULL, (int32_t) k [u] >= q.hi)) stop = p + 32 * u ;
+                            break ;
                         }
                     }
-                    if (over) break ;
                     if constexpr (!ISO)
                         if (Mon::has_terminal ())
                             if (__any_sync (FULL, found && Mon::is_terminal (acc))) break ;   // stop = tl: decided
-                    p += 64 ;
-                    if (p >= tl) break ;
-                    rp += 64 ; rem -= 64 ;
-                    kA = (rem > 0) ? (uint32_t) __ldg (rp) : NOKEY ;
-                    kB = (rem > 32) ? (uint32_t) __ldg (rp + 32) : NOKEY ;
                 }
             }
             // ---- the task's result goes to the lane that keeps it --------------------------------
-            if constexpr (ISO)
+            const uint32_t tot = __reduce_add_sync (FULL, cnt) ;
+            if constexpr (!ISO)
             {
-                const uint32_t tot = __reduce_add_sync (FULL, cnt) ;
-                if (lane == t) { mycnt = tot ; mycur = stop ; }
-            }
-            else
-            {
-                const uint32_t tot = __reduce_add_sync (FULL, cnt) ;
                 if (tot)
                 {
                     // a lane without any match holds the identity; identity (+) t == t for every
@@ -239,14 +280,14 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
                         acc = Mon::combine (acc, __shfl_down_sync (FULL, acc, off)) ;
                     acc = __shfl_sync (FULL, acc, 0) ;
                 }
-                if (lane == t) { mycnt = tot ; myacc = acc ; mycur = stop ; }
+                if (lane == t) myacc = acc ;
             }
-            kA = nkA ; kB = nkB ; tl = ntl ; p0 = np0 ; wp = nwp ;
+            if (lane == t) { mycnt = tot ; mycur = (uint32_t) stop ; }
         }
         // ---- every lane writes the result of its task ----------------------------------------------
         if (lane < nb)
         {
-            if constexpr (BITMAP) if (g.multi) s_cur [t0 + lane] = (uint16_t) mycur ;
+            if (cursors) s_cur [t0 + lane] = (uint16_t) mycur ;
             if (mycnt)
             {
                 if constexpr (ISO) myacc = iso_fold<Mon> (g.ciso, mycnt) ;
@@ -380,7 +421,7 @@ dotr_kernel (DotGArgs a)
             {
                 const int64_t lo = lo0 + (int64_t) part * BITS ;
                 const int64_t hi = (lo + BITS < omax + 1) ? (lo + BITS) : (omax + 1) ;
-                const int nwords = (int) ((hi - lo + 31) >> 5) ;
+                const int nwords = (int) ((hi - lo + 32) >> 5) ;    // with the spare zero bit
                 __syncthreads () ;              // the previous part's walkers are done
                 for (int t = threadIdx.x ; t < nwords ; t += blockDim.x) bm [t] = 0u ;
                 if (!ISO && threadIdx.x == 0)
@@ -426,6 +467,105 @@ dotr_kernel (DotGArgs a)
         }
     }
     for (int off = 16 ; off > 0 ; off >>= 1) nm += __shfl_down_sync (0xffffffffu, nm, off) ;
+    if (lane == 0 && nm) atomicAdd (a.nmatch, nm) ;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TINY owners (DOTG_SMALL <= entries <= dotr_tiny_cap): a WARP, not a block, takes the work item.
+// Such owners have a handful of tasks each (tri, RMAT scale 22: ~280 K of them per orientation, 6 to
+// 60 tasks each), so a block per owner spends its time in barriers and in the latency of the item's
+// set-up (measured: 3.2 warps stalled on the barrier per issued instruction in the block kernel).  Here
+// every warp builds the cuckoo tables of its own owner in its own 1/16 of the block's shared memory
+// (warp-synchronous, no block barrier) and walks the owner's tasks with dotr_walk.
+// ---------------------------------------------------------------------------------------------
+constexpr int DOTR_WARP_BYTES = DOTG_SMEM / (DOTR_THREADS / 32) ;       // table bytes per warp
+
+__host__ __device__ constexpr int dotr_tiny_cap (bool iso) { return (DOTR_WARP_BYTES / (iso ? 4 : 8)) * 3 / 8 ; }
+
+template <class S, bool ISO>
+__global__ void __launch_bounds__ (DOTR_THREADS, ISO ? 3 : 2)
+dotr_warp_kernel (DotGArgs a)
+{
+    using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
+    using slot_t = typename std::conditional<ISO, uint32_t, uint64_t>::type ;
+    constexpr slot_t EMPTY = (slot_t) ~(slot_t) 0 ;
+    constexpr unsigned FULL = 0xffffffffu ;
+    extern __shared__ __align__ (16) unsigned char dotr_raw [] ;
+    __shared__ int s_wnext [DOTR_THREADS / 32] ;
+    const S sr (a.mult_op, a.flip != 0) ;
+    const T *__restrict__ Ax = (const T *) a.A.x ;
+    const T *__restrict__ Bx = (const T *) a.B.x ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5 ;
+    const bool orient = (a.orient != 0) ;
+    const DMat &O = orient ? a.A : a.B ;        // owner matrix (probed)
+    const DMat &W = orient ? a.B : a.A ;        // walked matrix
+    const T *__restrict__ Oxb = orient ? Ax : Bx ;
+    slot_t *tab = (slot_t *) (dotr_raw + warp * DOTR_WARP_BYTES) ;
+    DotRCtx<S> g ;
+    g.Wi = W.i ; g.Wx = orient ? Bx : Ax ;
+    g.vals = (acc_t *) a.vals ; g.flags = a.flags ; g.orient = orient ;
+    g.ciso = Mon::identity () ;
+    if (ISO) g.ciso = sr.product (Ax [0], Bx [0]) ;
+    g.multi = false ; g.last = true ; g.lo = 0 ; g.nbits = 0 ; g.hi = INT32_MAX ;
+    unsigned long long nm = 0 ;
+    while (true)
+    {
+        unsigned long long it = 0 ;
+        if (lane == 0) it = atomicAdd (a.next_item, 1ULL) ;
+        it = __shfl_sync (FULL, it, 0) ;
+        if ((int64_t) it >= a.nitems) break ;
+        const DotItem item = a.items [it] ;
+        int64_t ko = item.owner ;
+        if (!orient) ko = dm_vecpos (a.B, dm_vecname (a.M, item.owner)) ;
+        const int64_t o0 = __ldg (O.p + ko), o1 = __ldg (O.p + ko + 1) ;
+        const int olen = (int) (o1 - o0) ;
+        g.tasks = a.tasks + item.e0 ;
+        g.ntask = (int) (item.e1 - item.e0) ;
+        g.Ox = Oxb + o0 ; g.Oi = O.i + o0 ; g.olen = olen ;
+        // ---- the warp's cuckoo tables: 2^lg slots each, total load between 3/16 and 3/8 ---------------
+        int lg = 3 ;
+        while (3 * (1 << lg) < 4 * olen) lg++ ;
+        const int NS = 1 << lg, sh = 32 - lg ;
+        uint32_t c1 = 0x9E3779B1u, c2 = 0x85EBCA6Bu ;
+        g.mode = DOTR_CUCKOO ;
+        if (olen > dotr_tiny_cap (ISO)) g.mode = DOTR_BSEARCH ;         // never scheduled here; stay correct
+        for (int attempt = 0 ; g.mode == DOTR_CUCKOO ; attempt++)
+        {
+            __syncwarp () ;                     // the previous walk is over
+            for (int t = lane ; t < 2 * NS ; t += 32) tab [t] = EMPTY ;
+            __syncwarp () ;
+            bool bad = false ;
+            for (int q = lane ; q < olen ; q += 32)
+            {
+                slot_t cur ;
+                if constexpr (ISO) cur = (uint32_t) __ldg (g.Oi + q) ;
+                else cur = ((uint64_t) (uint32_t) q << 32) | (uint32_t) __ldg (g.Oi + q) ;
+                int which = 0, n = 0 ;
+                #pragma unroll 1
+                for ( ; n < DOTG_MAXIT ; n++)
+                {
+                    const uint32_t k = (uint32_t) cur ;
+                    const uint32_t loc = which ? (NS + ((k * c2) >> sh)) : ((k * c1) >> sh) ;
+                    if constexpr (ISO) cur = atomicExch (tab + loc, cur) ;
+                    else cur = atomicExch ((unsigned long long *) tab + loc, (unsigned long long) cur) ;
+                    if (cur == EMPTY) break ;
+                    which ^= 1 ;                // the evicted entry moves to its other table
+                }
+                if (n == DOTG_MAXIT) bad = true ;
+            }
+            __syncwarp () ;
+            if (!__any_sync (FULL, bad)) break ;
+            if (attempt >= DOTR_REBUILDS) { g.mode = DOTR_BSEARCH ; break ; }
+            c1 = (c1 * 0x01000193u + 0xFE94F82Au) | 1u ;
+            c2 = (c2 * 0x01000193u + 0x4A8BE922u) | 1u ;
+        }
+        g.NS = NS ; g.sh = sh ; g.c1 = c1 ; g.c2 = c2 ;
+        if (lane == 0) s_wnext [warp] = 0 ;
+        __syncwarp () ;
+        if (g.mode == DOTR_CUCKOO) dotr_walk<S, ISO, DOTR_CUCKOO, slot_t> (sr, g, tab, s_wnext + warp, nullptr, 0, nm) ;
+        else dotr_walk<S, ISO, DOTR_BSEARCH, slot_t> (sr, g, tab, s_wnext + warp, nullptr, 0, nm) ;
+    }
+    for (int off = 16 ; off > 0 ; off >>= 1) nm += __shfl_down_sync (FULL, nm, off) ;
     if (lane == 0 && nm) atomicAdd (a.nmatch, nm) ;
 }
 

@@ -20,6 +20,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 VARIANTS = [
     ("default", {}),
     ("old", {"GB200_DOTR": "0"}),
+    ("notiny", {"GB200_DOTR_TINY": "0"}),
     ("valued_old", {"GB200_DOTR": "0", "GB200_DOTG_ISO": "0"}),
     ("bm_half", {"GB200_DOTR_BM_BITS": "753664"}),
     ("notrim", {"GB200_DOTG_TRIM": "0"}),
@@ -34,7 +35,7 @@ VARIANTS = [
     ("valued_notrim", {"GB200_DOTG_ISO": "0", "GB200_DOTG_TRIM": "0"}),
 ]
 KEYS = ("GB200_DOTG_TRIM", "GB200_DOTG_HUB_CHUNK", "GB200_DOTG_CHUNK", "GB200_DOTG_ISO", "GB200_DOTR",
-        "GB200_DOTR_BM_BITS")
+        "GB200_DOTR_BM_BITS", "GB200_DOTR_TINY")
 # the answer of the first measured run (profiles/r1_trim): a base that is itself wrong is noticed
 KNOWN = {22: (44374678, 2111700731)}
 
