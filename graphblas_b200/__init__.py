@@ -77,6 +77,10 @@ _SIGS = {
     "gb200_host_free": (None, [_VP]),
     "gb200_host_trim": (None, []),
     "gb200_device_trim": (None, []),
+    "gb200_cache_enable": (None, [_I]),
+    "gb200_cache_invalidate": (None, [_VP]),
+    "gb200_cache_clear": (None, []),
+    "gb200_cache_stats": (None, [_VP, _VP, _VP, _VP]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)
@@ -259,6 +263,17 @@ def partition_by_flops(cum: np.ndarray, nparts: int) -> np.ndarray:
                                         bounds.ctypes.data_as(C.c_void_p)),
            "gb200_partition_by_flops")
     return bounds
+
+
+def cache_enable(on: bool) -> None:
+    """operand residency across axb_host calls (gb200_cache_enable)"""
+    lib.gb200_cache_enable(1 if on else 0)
+
+
+def cache_stats() -> dict:
+    v = [C.c_int64() for _ in range(4)]
+    lib.gb200_cache_stats(*[C.byref(x) for x in v])
+    return dict(zip(("hits", "misses", "invalidations", "resident_bytes"), [x.value for x in v]))
 
 
 def kernel_launches() -> int:

@@ -54,6 +54,7 @@ struct Ctx
     std::vector<cudaEvent_t> kev ;
     int kev_used = 0 ;
     int mask_policy = 0 ;               // of the current multiply: 0 reference rule, 1 keep, 2 drop
+    int method_request = 0 ;            // of the current multiply: the GxB_AxB_METHOD asked for
 } ;
 
 Ctx &ctx () ;
@@ -165,6 +166,10 @@ gb200_status flopcount (const DMat *M, const DMat &A, const DMat &B, DevBuf &flo
     int64_t *total) ;
 
 gb200_status ensure_iso (gb200_dmatrix_s *d) ;
+
+// engine_cache.cu: operand residency across calls of the host entry point
+gb200_status cache_acquire (gb200_dmatrix *out, const gb200_matrix *host, bool *cached) ;
+void cache_release (gb200_dmatrix d) ;
 gb200_status cast_values (const void *in, int from, int to, int64_t n, DevBuf &out) ;
 gb200_status launch_mask_pos (const DMat &B, const DMat &M, int64_t *lpos) ;
 

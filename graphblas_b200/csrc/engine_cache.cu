@@ -1,0 +1,280 @@
+// engine_cache.cu -- operand residency across calls of the host entry point (SURVEY.md 8b "Residency",
+// row f3): a device copy of a host operand is kept, keyed on the addresses and shape of its arrays, so
+// that the graph of a BFS / SSSP / k-truss loop crosses PCIe once instead of once per GrB_mxm.
+//
+// The seam is handed borrowed host arrays and nothing in the reference says that an operand is
+// unchanged, so an entry is only trusted while ALL of the following hold:
+//   * none of its arrays has been freed or reallocated -- the gb200_host_* allocator (what the host
+//     application passed to GxB_init) reports every free / realloc to gb200_cache_invalidate;
+//   * no in-place writer of the reference has touched the object -- the shim interposes
+//     GB_setElement, GB_subassign_kernel and GB_wait (reference Source/GB.h:1990, 2048, 1931) and the
+//     GxB_*_import_* entry points (arrays handed back by the user may have new contents) and reports
+//     the object's arrays;
+//   * a sampled fingerprint of the host arrays (first / last 4 KB and 256 blocks in between, of each
+//     array) still matches -- a cheap second line of defence against writers nobody reported.
+// The cache is OFF unless gb200_cache_enable (1) is called or GB200_OPERAND_CACHE=1 is set; vectors
+// (vdim == 1) and small operands are never cached; it can be dropped at any time.
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+#include <atomic>
+#include "engine.cuh"
+#include "semiring.cuh"
+
+namespace gb200 {
+
+struct CacheEntry
+{
+    gb200_matrix key ;              // the host view it was uploaded from
+    int64_t nnz ;
+    gb200_dmatrix_s *d ;
+    uint64_t fp ;
+    size_t bytes ;
+    uint64_t tick ;
+    int pins ;                      // multiplies using it right now
+    bool dead ;                     // invalidated while pinned: freed at the last unpin
+} ;
+
+struct OperandCache
+{
+    std::mutex mu ;
+    std::vector<CacheEntry> entries ;
+    std::unordered_multiset<const void *> ptrs ;        // every array address of every entry
+    std::atomic<int> enabled { -1 } ;                   // -1: read GB200_OPERAND_CACHE on first use
+    std::atomic<int64_t> count { 0 } ;                  // entries.size (), readable without the lock
+    uint64_t tick = 0 ;
+    size_t resident = 0 ;
+    int64_t hits = 0, misses = 0, invalidations = 0 ;
+} ;
+
+static OperandCache &cache () { static OperandCache *c = new OperandCache () ; return *c ; }   // never destroyed
+
+static bool cache_on ()
+{
+    OperandCache &oc = cache () ;
+    int e = oc.enabled.load () ;
+    if (e < 0)
+    {
+        const char *env = getenv ("GB200_OPERAND_CACHE") ;
+        e = (env != nullptr && atoi (env) != 0) ? 1 : 0 ;
+        oc.enabled.store (e) ;
+    }
+    return e != 0 ;
+}
+
+// FNV-1a over sampled blocks of one array
+static uint64_t sample_hash (uint64_t h, const void *base, size_t nbytes)
+{
+    if (base == nullptr || nbytes == 0) return h * 1099511628211ULL + 1 ;
+    const unsigned char *b = (const unsigned char *) base ;
+    auto eat = [&] (size_t off, size_t len)
+    {
+        const uint64_t *w = (const uint64_t *) (b + (off & ~(size_t) 7)) ;
+        for (size_t q = 0 ; q < len / 8 ; q++) { h ^= w [q] ; h *= 1099511628211ULL ; }
+    } ;
+    const size_t edge = 4096, blk = 64 ;
+    if (nbytes <= 2 * edge + 256 * blk) { eat (0, nbytes & ~(size_t) 7) ; return h ^ nbytes ; }
+    eat (0, edge) ;
+    eat ((nbytes - edge) & ~(size_t) 7, edge - 8) ;
+    const size_t step = (nbytes - 2 * edge) / 256 ;
+    for (size_t q = 0 ; q < 256 ; q++) eat (edge + q * step, blk) ;
+    return h ^ nbytes ;
+}
+
+static uint64_t fingerprint (const gb200_matrix *m, int64_t nnz, int tsz)
+{
+    uint64_t h = 1469598103934665603ULL ;
+    h = sample_hash (h, m->p, (size_t) (m->nvec + 1) * 8) ;
+    h = sample_hash (h, m->h, m->h ? (size_t) m->nvec * 8 : 0) ;
+    h = sample_hash (h, m->i, (size_t) nnz * 8) ;
+    h = sample_hash (h, m->x, (size_t) nnz * tsz) ;
+    return h ;
+}
+
+static bool same_key (const gb200_matrix &a, const gb200_matrix &b)
+{
+    return a.p == b.p && a.h == b.h && a.i == b.i && a.x == b.x && a.vlen == b.vlen && a.vdim == b.vdim
+        && a.nvec == b.nvec && a.type_code == b.type_code ;
+}
+
+static void drop_locked (OperandCache &oc, size_t k, std::vector<gb200_dmatrix_s *> &to_free)
+{
+    CacheEntry &e = oc.entries [k] ;
+    for (const void *q : { (const void *) e.key.p, (const void *) e.key.h, (const void *) e.key.i, e.key.x })
+        if (q != nullptr) { auto it = oc.ptrs.find (q) ; if (it != oc.ptrs.end ()) oc.ptrs.erase (it) ; }
+    oc.resident -= e.bytes ;
+    if (e.pins > 0) { e.dead = true ; return ; }        // its user frees it (cache_release)
+    to_free.push_back (e.d) ;
+    oc.entries.erase (oc.entries.begin () + (long) k) ;
+    oc.count.store ((int64_t) oc.entries.size ()) ;
+}
+
+static void free_handles (std::vector<gb200_dmatrix_s *> &v)
+{
+    for (gb200_dmatrix_s *d : v) { gb200_dmatrix dd = d ; gb200_dmatrix_free (&dd) ; }
+}
+
+// the operand `host` resident on the device: from the cache, or uploaded (and remembered if it is
+// cacheable).  *cached: release with cache_release, not gb200_dmatrix_free.
+gb200_status cache_acquire (gb200_dmatrix *out, const gb200_matrix *host, bool *cached)
+{
+    *cached = false ;
+    const int tsz = type_size (host->type_code) ;
+    const int64_t nnz = (host->p != nullptr && host->nvec >= 0) ? host->p [host->nvec] : 0 ;
+    // vectors and small operands are cheaper to upload than to track
+    const bool eligible = cache_on () && host->vdim > 1 && nnz >= (1 << 16) ;
+    if (!eligible) return gb200_upload (out, host) ;
+    OperandCache &oc = cache () ;
+    const uint64_t fp = fingerprint (host, nnz, tsz) ;
+    std::vector<gb200_dmatrix_s *> to_free ;
+    {
+        std::lock_guard<std::mutex> lock (oc.mu) ;
+        for (size_t k = 0 ; k < oc.entries.size () ; k++)
+        {
+            CacheEntry &e = oc.entries [k] ;
+            if (e.dead || !same_key (e.key, *host)) continue ;
+            if (e.nnz == nnz && e.fp == fp)
+            {
+                e.pins++ ; e.tick = ++oc.tick ; oc.hits++ ;
+                *out = e.d ; *cached = true ;
+                return GB200_SUCCESS ;
+            }
+            oc.invalidations++ ;                        // same arrays, other contents
+            drop_locked (oc, k, to_free) ;
+            break ;
+        }
+        oc.misses++ ;
+    }
+    free_handles (to_free) ;
+    to_free.clear () ;
+    GB200_TRY (gb200_upload (out, host)) ;
+    const size_t bytes = (size_t) (host->nvec + 1) * 8 + (host->h ? (size_t) host->nvec * 8 : 0)
+        + (size_t) nnz * (4 + tsz) ;
+    // keep at most a quarter of the device's memory resident (GB200_OPERAND_CACHE_MB overrides)
+    size_t limit = 0 ;
+    {
+        const char *env = getenv ("GB200_OPERAND_CACHE_MB") ;
+        size_t free_b = 0, total_b = 0 ;
+        if (env != nullptr && atoll (env) > 0) limit = (size_t) atoll (env) << 20 ;
+        else if (cudaMemGetInfo (&free_b, &total_b) == cudaSuccess) limit = total_b / 4 ;
+        else { cudaGetLastError () ; limit = (size_t) 16 << 30 ; }
+    }
+    if (bytes > limit) return GB200_SUCCESS ;           // too big to keep: the caller frees it
+    {
+        std::lock_guard<std::mutex> lock (oc.mu) ;
+        while (oc.resident + bytes > limit)
+        {
+            // evict the least recently used entry nobody is using
+            size_t victim = oc.entries.size () ;
+            for (size_t k = 0 ; k < oc.entries.size () ; k++)
+                if (oc.entries [k].pins == 0 && !oc.entries [k].dead
+                    && (victim == oc.entries.size () || oc.entries [k].tick < oc.entries [victim].tick)) victim = k ;
+            if (victim == oc.entries.size ()) break ;
+            drop_locked (oc, victim, to_free) ;
+        }
+        if (oc.resident + bytes <= limit)
+        {
+            CacheEntry e ;
+            e.key = *host ; e.nnz = nnz ; e.d = *out ; e.fp = fp ; e.bytes = bytes ; e.tick = ++oc.tick ;
+            e.pins = 1 ; e.dead = false ;
+            oc.entries.push_back (e) ;
+            oc.count.store ((int64_t) oc.entries.size ()) ;
+            for (const void *q : { (const void *) host->p, (const void *) host->h, (const void *) host->i, host->x })
+                if (q != nullptr) oc.ptrs.insert (q) ;
+            oc.resident += bytes ;
+            *cached = true ;
+        }
+    }
+    free_handles (to_free) ;
+    return GB200_SUCCESS ;
+}
+
+void cache_release (gb200_dmatrix d)
+{
+    OperandCache &oc = cache () ;
+    gb200_dmatrix_s *kill = nullptr ;
+    {
+        std::lock_guard<std::mutex> lock (oc.mu) ;
+        for (size_t k = 0 ; k < oc.entries.size () ; k++)
+        {
+            CacheEntry &e = oc.entries [k] ;
+            if (e.d != d) continue ;
+            if (--e.pins == 0 && e.dead)
+            {
+                kill = e.d ;
+                oc.entries.erase (oc.entries.begin () + (long) k) ;
+                oc.count.store ((int64_t) oc.entries.size ()) ;
+            }
+            break ;
+        }
+    }
+    if (kill != nullptr) { gb200_dmatrix dd = kill ; gb200_dmatrix_free (&dd) ; }
+}
+
+} // namespace gb200
+
+using namespace gb200 ;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+void gb200_cache_enable (int on)
+{
+    cache ().enabled.store (on ? 1 : 0) ;
+    if (!on) gb200_cache_clear () ;
+}
+
+// an array of a host operand was freed, reallocated or written: forget every copy made from it
+void gb200_cache_invalidate (const void *array)
+{
+    OperandCache &oc = cache () ;
+    if (array == nullptr || oc.count.load () == 0) return ;         // the common case: nothing cached
+    std::vector<gb200_dmatrix_s *> to_free ;
+    {
+        std::lock_guard<std::mutex> lock (oc.mu) ;
+        if (oc.ptrs.find (array) == oc.ptrs.end ()) return ;
+        for (size_t k = 0 ; k < oc.entries.size () ; )
+        {
+            const gb200_matrix &m = oc.entries [k].key ;
+            if (!oc.entries [k].dead && (m.p == array || m.h == array || m.i == array || m.x == array))
+            {
+                oc.invalidations++ ;
+                const size_t before = oc.entries.size () ;
+                drop_locked (oc, k, to_free) ;
+                if (oc.entries.size () < before) continue ;
+            }
+            k++ ;
+        }
+    }
+    free_handles (to_free) ;
+}
+
+void gb200_cache_clear (void)
+{
+    OperandCache &oc = cache () ;
+    std::vector<gb200_dmatrix_s *> to_free ;
+    {
+        std::lock_guard<std::mutex> lock (oc.mu) ;
+        for (size_t k = 0 ; k < oc.entries.size () ; )
+        {
+            const size_t before = oc.entries.size () ;
+            if (!oc.entries [k].dead) drop_locked (oc, k, to_free) ;
+            if (oc.entries.size () < before) continue ;
+            k++ ;
+        }
+    }
+    free_handles (to_free) ;
+}
+
+void gb200_cache_stats (int64_t *hits, int64_t *misses, int64_t *invalidations, int64_t *resident_bytes)
+{
+    OperandCache &oc = cache () ;
+    std::lock_guard<std::mutex> lock (oc.mu) ;
+    if (hits) *hits = oc.hits ;
+    if (misses) *misses = oc.misses ;
+    if (invalidations) *invalidations = oc.invalidations ;
+    if (resident_bytes) *resident_bytes = (int64_t) oc.resident ;
+}
+
+#pragma GCC visibility pop
+} // extern "C"

@@ -90,15 +90,44 @@ __global__ void dot_cnt_rect_kernel (const int64_t *__restrict__ pos, int64_t an
 // again, so items are large (measured, tri scale 22: 128: 46.5, 256: 43.8, 512: 42.8, 1024: 42.4 ms)
 constexpr int64_t DOTG_CHUNK = 1024 ;
 
-// Both lists are sorted, so a match can only lie between the owner's first and last index: the walked
-// list is trimmed to that range before it becomes a task (two binary searches per pair).  For
-// C<L>=L*U' every pair keeps only the indices between j and i: 43 % fewer probes on RMAT graphs.
-__device__ __forceinline__ void dotg_trim (const int32_t *__restrict__ Wi, int64_t w0, int64_t w1,
-    int32_t omin, int32_t omax, int64_t &t0, int64_t &t1)
+// Per stored vector: where it starts, how long it is, its first and last index -- one 32-byte record
+// (one DRAM sector), so that the classification of a pair costs one random sector per side instead of
+// three (pointer pair, first index, last index).
+struct __align__ (32) VecInfo { int64_t p0 ; int64_t len ; int32_t first ; int32_t last ; int64_t pad ; } ;
+
+__global__ void vec_info_kernel (DMat X, VecInfo *__restrict__ info)
 {
-    // a side whose end index is already inside the range needs no search (the common case for one side)
+    for (int64_t k = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; k < X.nvec ;
+        k += (int64_t) gridDim.x * blockDim.x)
+    {
+        VecInfo v ;
+        v.p0 = X.p [k] ; v.len = X.p [k+1] - v.p0 ; v.pad = 0 ;
+        v.first = (v.len > 0) ? __ldg (X.i + v.p0) : 0 ;
+        v.last = (v.len > 0) ? __ldg (X.i + v.p0 + v.len - 1) : 0 ;
+        info [k] = v ;
+    }
+}
+
+__device__ __forceinline__ VecInfo load_vec_info (const VecInfo *__restrict__ p)
+{
+    const int4 a = __ldg ((const int4 *) p), b = __ldg (((const int4 *) p) + 1) ;
+    VecInfo v ;
+    v.p0 = ((int64_t) (uint32_t) a.x) | ((int64_t) a.y << 32) ;
+    v.len = ((int64_t) (uint32_t) a.z) | ((int64_t) a.w << 32) ;
+    v.first = b.x ; v.last = b.y ; v.pad = 0 ;
+    return v ;
+}
+
+// Both lists are sorted, so a match can only lie between the owner's first and last index: the walked
+// list is trimmed to that range before it becomes a task (at most two binary searches per pair).  For
+// C<L>=L*U' every pair keeps only the indices between j and i: 43 % fewer probes on RMAT graphs.
+// wfirst / wlast: the walked list's own first and last index (a side whose end is already inside the
+// range needs no search: the common case for one side).
+__device__ __forceinline__ void dotg_trim (const int32_t *__restrict__ Wi, int64_t w0, int64_t w1,
+    int32_t wfirst, int32_t wlast, int32_t omin, int32_t omax, int64_t &t0, int64_t &t1)
+{
     int64_t l = w0, h = w1 ;
-    if (__ldg (Wi + w0) < omin)
+    if (wfirst < omin)
     {
         while (l < h)
         {
@@ -108,7 +137,7 @@ __device__ __forceinline__ void dotg_trim (const int32_t *__restrict__ Wi, int64
     }
     t0 = l ;
     h = w1 ;
-    if (l < w1 && __ldg (Wi + w1 - 1) > omax)
+    if (l < w1 && wlast > omax)
     {
         while (l < h)
         {
@@ -131,7 +160,8 @@ enum { PK_DEAD = 0, PK_SMALL = 1, PK_BOWN = 2, PK_AOWN = 3 } ;
 // pass 1: classification with the trim.  w0 [e] = where the (trimmed) walk starts in the walked matrix,
 // lk [e] = its length | kind << 30, nt0 [e] = tasks of a B-owned pair (else 0), cntA [ka] += tasks of an
 // A-owned pair, slist = the small pairs (any order: they are independent).
-__global__ void dotg_classify_kernel (DMat A, DMat B, DMat M, const int32_t *__restrict__ mvec,
+__global__ void dotg_classify_kernel (DMat A, DMat B, DMat M, const VecInfo *__restrict__ infoA,
+    const VecInfo *__restrict__ infoB, const int32_t *__restrict__ mvec,
     int64_t mnz, int trim, int64_t *__restrict__ w0out, int32_t *__restrict__ lk, int32_t *__restrict__ nt0,
     unsigned long long *__restrict__ cntA, int32_t *__restrict__ slist, unsigned int *__restrict__ nsmall)
 {
@@ -150,8 +180,8 @@ __global__ void dotg_classify_kernel (DMat A, DMat B, DMat M, const int32_t *__r
             const int64_t kb = dm_vecpos (B, dm_vecname (M, mvec [e])) ;
             if (ka >= 0 && kb >= 0)
             {
-                const int64_t pa = A.p [ka], pae = A.p [ka+1], pb = B.p [kb], pbe = B.p [kb+1] ;
-                const int64_t ainz = pae - pa, bjnz = pbe - pb ;
+                const VecInfo va = load_vec_info (infoA + ka), vb = load_vec_info (infoB + kb) ;
+                const int64_t ainz = va.len, bjnz = vb.len ;
                 if (ainz > 0 && bjnz > 0)
                 {
                     const bool walkA = dot_walkA (ainz, bjnz, A.vlen) ;
@@ -159,14 +189,11 @@ __global__ void dotg_classify_kernel (DMat A, DMat B, DMat M, const int32_t *__r
                     if (olen < DOTG_SMALL) kind = PK_SMALL ;
                     else
                     {
-                        const int64_t wa = walkA ? pa : pb, wb = walkA ? pae : pbe ;
-                        int64_t t0 = wa, t1 = wb ;
-                        if (trim)
-                        {
-                            const int32_t *__restrict__ Oi = walkA ? B.i : A.i ;
-                            const int64_t o0 = walkA ? pb : pa, o1 = walkA ? pbe : pae ;
-                            dotg_trim (walkA ? A.i : B.i, wa, wb, __ldg (Oi + o0), __ldg (Oi + o1 - 1), t0, t1) ;
-                        }
+                        const VecInfo &vw = walkA ? va : vb ;       // walked
+                        const VecInfo &vo = walkA ? vb : va ;       // owner
+                        int64_t t0 = vw.p0, t1 = vw.p0 + vw.len ;
+                        if (trim) dotg_trim (walkA ? A.i : B.i, vw.p0, vw.p0 + vw.len, vw.first, vw.last,
+                            vo.first, vo.last, t0, t1) ;
                         len = (int32_t) (t1 - t0) ;
                         wstart = t0 ;
                         if (len > 0)
@@ -380,7 +407,18 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             GB200_CUDA (cudaMemsetAsync (cntA.ptr, 0, cntA.bytes, c.stream)) ;
             GB200_CUDA (cudaMemsetAsync (curA.ptr, 0, curA.bytes, c.stream)) ;
             GB200_CUDA (cudaMemsetAsync (nsmall.ptr, 0, 8, c.stream)) ;
+            DevBuf infoA, infoB ;
+            const bool sameAB = (A.p == B.p && A.i == B.i && A.nvec == B.nvec) ;
+            GB200_TRY (infoA.alloc ((size_t) (anvec > 0 ? anvec : 1) * sizeof (VecInfo))) ;
+            vec_info_kernel <<<grid_cap ((anvec + 255) / 256, 16), 256, 0, c.stream>>> (A, infoA.as<VecInfo> ()) ;
+            if (!sameAB)
+            {
+                GB200_TRY (infoB.alloc ((size_t) (B.nvec > 0 ? B.nvec : 1) * sizeof (VecInfo))) ;
+                vec_info_kernel <<<grid_cap ((B.nvec + 255) / 256, 16), 256, 0, c.stream>>> (B, infoB.as<VecInfo> ()) ;
+            }
+            count_launch (sameAB ? 1 : 2) ;
             dotg_classify_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, B, Mv,
+                infoA.as<VecInfo> (), sameAB ? infoA.as<VecInfo> () : infoB.as<VecInfo> (),
                 mvec.as<int32_t> (), mnz, trim, w0buf.as<int64_t> (), lk.as<int32_t> (), nt0.as<int32_t> (),
                 cntA.as<unsigned long long> (), slist.as<int32_t> (), nsmall.as<unsigned int> ()) ;
             count_launch () ;
@@ -677,6 +715,7 @@ gb200_status gb200_AxB_device (gb200_result *out, gb200_dmatrix M, int mask_comp
     memset (&R->info, 0, sizeof (R->info)) ;
     c.kev_used = 0 ;
     c.mask_policy = mask_policy ;
+    c.method_request = method & 0xffff ;
     cudaEventRecord (c.ev0, c.stream) ;
     gb200_status st ;
     if (vec_shape (A, B) && (M == NULL || (M->v.vdim == 1 && M->v.nvec == 1 && !M->v.hyper)))
@@ -747,18 +786,21 @@ gb200_status gb200_AxB_host (gb200_result *out, const gb200_matrix *M, int mask_
             && X->h == Y->h && X->vlen == Y->vlen && X->vdim == Y->vdim && X->nvec == Y->nvec
             && X->type_code == Y->type_code)) ;
     } ;
-    st = gb200_upload (&dA, A) ;
-    if (st == GB200_SUCCESS) { if (same (A, B)) dB = dA ; else st = gb200_upload (&dB, B) ; }
+    // every distinct operand is resident once: from the residency cache (engine_cache.cu: only if the
+    // host enabled it), else uploaded now and freed after the multiply
+    bool cA = false, cB = false, cM = false ;
+    st = cache_acquire (&dA, A, &cA) ;
+    if (st == GB200_SUCCESS) { if (same (A, B)) dB = dA ; else st = cache_acquire (&dB, B, &cB) ; }
     if (st == GB200_SUCCESS && M != NULL)
     {
-        if (same (M, A)) dM = dA ; else if (same (M, B)) dM = dB ; else st = gb200_upload (&dM, M) ;
+        if (same (M, A)) dM = dA ; else if (same (M, B)) dM = dB ; else st = cache_acquire (&dM, M, &cM) ;
     }
     const double t1 = trace ? now () : 0 ;
     if (st == GB200_SUCCESS) st = gb200_AxB_device (out, dM, mask_comp, dA, dB, semiring, do_adotb, method) ;
     const double t2 = trace ? now () : 0 ;
-    if (dM != dA && dM != dB) gb200_dmatrix_free (&dM) ;
-    if (dB != dA) gb200_dmatrix_free (&dB) ;
-    gb200_dmatrix_free (&dA) ;
+    if (dM != NULL && dM != dA && dM != dB) { if (cM) cache_release (dM) ; else gb200_dmatrix_free (&dM) ; }
+    if (dB != NULL && dB != dA) { if (cB) cache_release (dB) ; else gb200_dmatrix_free (&dB) ; }
+    if (dA != NULL) { if (cA) cache_release (dA) ; else gb200_dmatrix_free (&dA) ; }
     if (trace)
         fprintf (stderr, "gb200_AxB_host: upload %.3f ms, multiply %.3f ms (device %.3f ms), release %.3f ms\n",
             t1 - t0, t2 - t1, (st == GB200_SUCCESS && *out != NULL) ? (*out)->info.device_ms : 0.0,

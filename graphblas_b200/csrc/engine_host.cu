@@ -151,6 +151,7 @@ void *gb200_host_calloc (size_t n, size_t size)
 void gb200_host_free (void *p)
 {
     if (p == nullptr) return ;
+    gb200_cache_invalidate (p) ;        // a device copy made from this array is stale now
     HostPool &hp = pool () ;
     std::vector<void *> drop ;
     bool mine = false ;
@@ -175,6 +176,7 @@ void gb200_host_free (void *p)
 void *gb200_host_realloc (void *p, size_t size)
 {
     if (p == nullptr) return gb200_host_malloc (size) ;
+    gb200_cache_invalidate (p) ;        // the array moves or changes length
     HostPool &hp = pool () ;
     size_t cap = 0 ;
     {

@@ -178,6 +178,30 @@ __global__ void classify_kernel (const int64_t *__restrict__ flops, int64_t nvec
     }
 }
 
+// after the count pass: the vectors of the four shared-memory flop classes again, by their number of
+// ENTRIES -- the fused fill + numeric kernel (saxpy_hash_kernel) keeps (row, accumulator) slots, so
+// what has to fit its table is the pattern, not the flops.  Classes 3 and 4: the pattern is too long
+// for it (flops <= 8 Ki / <= 16 Ki: the two-kernel path with the shared-memory set of that flop class).
+struct CntLimits { int64_t lim [3] ; int64_t mid_flops ; int64_t heavy_flops ; } ;
+
+__global__ void classify_cnt_kernel (const int64_t *__restrict__ flops, const int64_t *__restrict__ Cp,
+    int64_t nvec, CntLimits L, int32_t *__restrict__ lists, unsigned int *__restrict__ counts)
+{
+    for (int64_t kk = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; kk < nvec ;
+        kk += (int64_t) gridDim.x * blockDim.x)
+    {
+        const int64_t f = flops [kk] ;
+        if (f <= 0 || f > L.heavy_flops) continue ;
+        const int64_t cnt = Cp [kk+1] - Cp [kk] ;
+        if (cnt <= 0) continue ;
+        int cl = (f > L.mid_flops) ? 4 : 3 ;        // pattern too long: by flop class again
+        #pragma unroll
+        for (int q = 2 ; q >= 0 ; q--) if (cnt <= L.lim [q]) cl = q ;
+        const unsigned int pos = atomicAdd (counts + cl, 1u) ;
+        lists [(int64_t) cl * nvec + pos] = (int32_t) kk ;
+    }
+}
+
 // =============================================================================================
 // symbolic phase, shared-memory classes: hash set of row indices, then (FILL) compaction + bitonic
 // sort so that the indices of C(:,j) come out ascending (the invariant checked by the reference at
@@ -664,7 +688,10 @@ gb200_status run_saxpy (gb200_result_s *R, const gb200_dmatrix_s *Min, int mask_
     const DMat &B = Bd->v ;
     const int64_t nvec = B.nvec ;
     const int64_t cvlen = A.vlen, cvdim = B.vdim ;
-    R->info.method_used = GB200_METHOD_GUSTAVSON ;
+    // one GPU saxpy serves GUSTAVSON and HEAP requests alike; an explicit HEAP request is reported as
+    // HEAP, as GB_AxB_select.c:139-143 would (its automatic heap choice, :95-128, is a CPU workspace
+    // trade-off that has no analogue here and is reported as GUSTAVSON: INTEGRATION.md)
+    R->info.method_used = (ctx ().method_request == GB200_METHOD_HEAP) ? GB200_METHOD_HEAP : GB200_METHOD_GUSTAVSON ;
     R->info.type_code = s.z_code ;
 
     // ---- mask policy of GB_AxB_sequential.c:76-95 ---------------------------------------------
@@ -770,6 +797,82 @@ gb200_status run_saxpy (gb200_result_s *R, const gb200_dmatrix_s *Min, int mask_
         sa.lp = ccum.as<int64_t> () ; sa.li = Ci.as<int32_t> () ; sa.lpos = nullptr ;
         sa.acc = acc.ptr ; sa.flags = nullptr ; sa.masked = 0 ;
 
+        // Vectors whose pattern fits a shared-memory table (<= 4096 entries): fused fill + numeric with
+        // a shared-memory hash accumulator, binned by entry count.  GB200_SAXPY_HASH=0: the two-kernel
+        // path (pattern first, then a binary search and a global atomic per product) for all of them.
+        // Measured (profiles/r2, one B200): Erdos-Renyi 2^20 10.6 -> 8.0 ms with the two small classes
+        // fused; the third class (<= 4096 entries: a 128 KB table, one block per SM) loses to the
+        // two-kernel path on RMAT 18 (84 -> 102 ms), so it is off unless GB200_SAXPY_HASH=2.
+        const char *henv = getenv ("GB200_SAXPY_HASH") ;
+        const bool fused = !(henv != nullptr && atoi (henv) == 0) ;
+        const bool fuse_mid = (henv != nullptr && atoi (henv) == 2) ;
+        const int64_t hash_limit [3] = { 128, 1024, fuse_mid ? 4096 : 1024 } ;
+        static const int hash_log [3] = { 8, 11, 13 } ;
+        static const int hash_threads [3] = { 32, 128, 512 } ;
+        Bins cb ;                                   // lists 0..2: fused classes; 3: pattern too long
+        if (fused)
+        {
+            GB200_TRY (cb.lists.alloc ((size_t) NCLASS * (nvec > 0 ? nvec : 1) * sizeof (int32_t))) ;
+            GB200_TRY (cb.counts.alloc (NCLASS * sizeof (unsigned int))) ;
+            GB200_CUDA (cudaMemsetAsync (cb.counts.ptr, 0, NCLASS * sizeof (unsigned int), c.stream)) ;
+            CntLimits CL ;
+            for (int q = 0 ; q < 3 ; q++) CL.lim [q] = hash_limit [q] ;
+            CL.mid_flops = class_limit [2] ; CL.heavy_flops = class_limit [3] ;
+            if (nvec > 0)
+            {
+                classify_cnt_kernel <<<grid_cap ((nvec + 255) / 256, 8), 256, 0, c.stream>>> (
+                    flops.as<int64_t> (), ccum.as<int64_t> (), nvec, CL, cb.lists.as<int32_t> (),
+                    cb.counts.as<unsigned int> ()) ;
+                count_launch () ;
+            }
+            GB200_CUDA (cudaMemcpyAsync (c.pinned, cb.counts.ptr, NCLASS * sizeof (unsigned int),
+                cudaMemcpyDeviceToHost, c.stream)) ;
+            GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
+            for (int q = 0 ; q < NCLASS ; q++) cb.n [q] = ((unsigned int *) c.pinned) [q] ;
+            sa.Ci_out = Ci.as<int32_t> () ;
+            const int64_t heavy_nwords = sa.nwords ;
+            for (int cl = 0 ; cl < 3 ; cl++)
+            {
+                if (cb.n [cl] == 0) continue ;
+                sa.cols = cb.list (cl, nvec) ; sa.ncols = cb.n [cl] ; sa.hash_log = hash_log [cl] ;
+                // a vlen-bit bitmap next to the table replaces the sort wherever scanning it costs less
+                // than sorting the vector (same rule as the pattern-only kernels above)
+                sa.nwords = use_bitmap (cl == 0 ? 0 : cl) ? symb_words : 0 ;
+                if (!launch_typed (s.xy_code, FAM_SAXPY_HASH, s.z_code, s.add_opcode, s.mult_opcode, &sa,
+                    grid_cap (cb.n [cl], (cl == 0) ? 32 : ((cl == 1) ? 8 : 1)), hash_threads [cl]))
+                { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+            }
+            sa.nwords = heavy_nwords ;
+            for (int q = 3 ; q <= 4 ; q++)
+            {
+                // longer patterns of the two upper shared-memory flop classes: pattern first (bitmap, or
+                // hash set + sort), then the slot search per product
+                if (cb.n [q] == 0) continue ;
+                const int cl = q - 1 ;              // flop class 2 or 3
+                if (use_bitmap (cl))
+                {
+                    sym_bitmap_kernel<true> <<<grid_cap (cb.n [q], 32), class_threads [cl],
+                        (size_t) symb_words * 4, c.stream>>> (A, B, cb.list (q, nvec), cb.n [q],
+                        symb_words, nullptr, ccum.as<int64_t> (), Ci.as<int32_t> ()) ;
+                }
+                else
+                {
+                    const size_t smem = ((size_t) 4 << class_log [cl]) + ((size_t) 2 << class_log [cl]) ;
+                    if (smem > 48 * 1024)
+                        GB200_CUDA (cudaFuncSetAttribute (sym_hash_kernel<true>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) ;
+                    sym_hash_kernel<true> <<<grid_cap (cb.n [q], 32), class_threads [cl], smem, c.stream>>> (
+                        A, B, cb.list (q, nvec), cb.n [q], class_log [cl], nullptr, ccum.as<int64_t> (),
+                        Ci.as<int32_t> ()) ;
+                }
+                count_launch () ;
+                sa.cols = cb.list (q, nvec) ; sa.ncols = cb.n [q] ;
+                if (!launch_typed (s.xy_code, FAM_SAXPY_LIGHT, s.z_code, s.add_opcode, s.mult_opcode, &sa,
+                    grid_cap (cb.n [q], 32), class_threads [cl]))
+                { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+            }
+        }
+        else
         for (int cl = 0 ; cl < 4 ; cl++)
         {
             if (bins.n [cl] == 0) continue ;

@@ -371,7 +371,10 @@ gb200_status run_saxpyv (gb200_result_s *R, const gb200_dmatrix_s *Min, int mask
     const DMat &A = Ad->v ;
     const DMat &B = Bd->v ;
     const int64_t cvlen = A.vlen ;
-    R->info.method_used = GB200_METHOD_GUSTAVSON ;
+    // one GPU saxpy serves GUSTAVSON and HEAP requests alike; an explicit HEAP request is reported as
+    // HEAP, as GB_AxB_select.c:139-143 would (its automatic heap choice, :95-128, is a CPU workspace
+    // trade-off that has no analogue here and is reported as GUSTAVSON: INTEGRATION.md)
+    R->info.method_used = (ctx ().method_request == GB200_METHOD_HEAP) ? GB200_METHOD_HEAP : GB200_METHOD_GUSTAVSON ;
     R->info.type_code = s.z_code ;
 
     // ---- mask policy ----------------------------------------------------------------------------

@@ -37,7 +37,140 @@ struct SaxpyArgs
     const int32_t *rank ;       // nws arrays of nwords prefix popcounts
     int64_t nwords ;
     int mult_op ; int flip ;
+    // fused symbolic-fill + numeric (saxpy_hash_kernel)
+    int hash_log ;              // the shared-memory table has 2^hash_log slots
+    int32_t *Ci_out ;           // pattern of C, written by the kernel (ascending in every vector)
 } ;
+
+// ---------------------------------------------------------------------------------------------
+// saxpy, fused symbolic fill + numeric phase for vectors of C whose pattern fits a shared-memory hash
+// table (the north star's "shared-memory hash accumulator"; reference behaviour:
+// Source/Template/GB_AxB_Gustavson_symbolic.c:187-233 + GB_AxB_Gustavson_nomask.c:91-158 -- there a
+// dense Work/Mark pair of O(vlen) plus GB_qsort_1, here a table of (row, accumulator) slots).
+// One thread block per vector of B.  Every product A(i,k) (x) B(k,j) claims the slot of row i with one
+// shared atomicCAS and is combined into the slot's accumulator with the monoid's shared atomic; the
+// occupied slots are then compacted, sorted by row with a bitonic network in shared memory and
+// written out coalesced: C's pattern and values leave the SM exactly once, A's entries are read once.
+// When the index range is small (nwords > 0: a vlen-bit bitmap fits shared memory next to the table)
+// the rows are also marked in the bitmap and come out of it ascending by prefix popcount: no sort.
+// The exact number of entries of every vector (lp) comes from the count pass.
+// ---------------------------------------------------------------------------------------------
+template <class S>
+__global__ void saxpy_hash_kernel (SaxpyArgs a)
+{
+    using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
+    extern __shared__ __align__ (16) unsigned char hash_raw [] ;
+    const int LOG = a.hash_log ;
+    const int size = 1 << LOG ;
+    acc_t *vals = (acc_t *) hash_raw ;                          // size accumulators
+    uint64_t *comp = (uint64_t *) (vals + size) ;               // size / 2 (row << 32 | slot) pairs
+    int32_t *keys = (int32_t *) (comp + size / 2) ;             // size rows, -1 = free
+    uint32_t *bm = (uint32_t *) (keys + size) ;                 // nwords words (small index ranges only)
+    const int nwords = (int) a.nwords ;
+    __shared__ int s_n ;
+    __shared__ int64_t s_ws [33] ;
+    const uint32_t mask = (uint32_t) size - 1u ;
+    const S sr (a.mult_op, a.flip != 0) ;
+    const T *__restrict__ Ax = (const T *) a.A.x ;
+    const T *__restrict__ Bx = (const T *) a.B.x ;
+    acc_t *__restrict__ acc = (acc_t *) a.acc ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5 ;
+    for (int64_t c = blockIdx.x ; c < a.ncols ; c += gridDim.x)
+    {
+        const int64_t kk = a.cols [c] ;
+        const int64_t base = a.lp [kk] ;
+        if (a.lp [kk+1] <= base) continue ;                     // block-uniform
+        for (int t = threadIdx.x ; t < size ; t += blockDim.x) { keys [t] = -1 ; vals [t] = Mon::identity () ; }
+        for (int t = threadIdx.x ; t < nwords ; t += blockDim.x) bm [t] = 0u ;
+        if (threadIdx.x == 0) s_n = 0 ;
+        __syncthreads () ;
+        const int64_t pb0 = a.B.p [kk], pb1 = a.B.p [kk+1] ;
+        for (int64_t pb = pb0 + warp ; pb < pb1 ; pb += nwarps)
+        {
+            int64_t pa, pe ;
+            if (!dm_lookup (a.A, a.B.i [pb], pa, pe)) continue ;
+            const T bkj = Bx [pb] ;
+            for (int64_t p = pa + lane ; p < pe ; p += 32)
+            {
+                const int32_t i = __ldg (a.A.i + p) ;
+                const acc_t prod = sr.product (Ax [p], bkj) ;
+                uint32_t h = (hash32 ((uint32_t) i) >> (32 - LOG)) & mask ;
+                while (true)
+                {
+                    const int32_t old = atomicCAS (keys + h, -1, i) ;
+                    if (old == -1 || old == i)
+                    {
+                        Mon::atomic_combine (vals + h, prod) ;
+                        if (old == -1 && nwords > 0) atomicOr (bm + (((uint32_t) i) >> 5), 1u << (i & 31)) ;
+                        break ;
+                    }
+                    h = (h + 1) & mask ;
+                }
+            }
+        }
+        __syncthreads () ;
+        if (nwords > 0)
+        {
+            // small index range: the rows were also marked in a bitmap, which hands them out ascending
+            // (rank = prefix popcount) -- no sort; the value of a row is looked up in the table
+            int64_t run = base ;
+            for (int t0 = 0 ; t0 < nwords ; t0 += blockDim.x)
+            {
+                const int t = t0 + threadIdx.x ;
+                uint32_t word = (t < nwords) ? bm [t] : 0u ;
+                int64_t total ;
+                int64_t q = run + block_excl_scan_i64 (__popc (word), s_ws, total) ;
+                while (word)
+                {
+                    const int32_t key = t * 32 + (__ffs (word) - 1) ;
+                    word &= word - 1 ;
+                    uint32_t h = (hash32 ((uint32_t) key) >> (32 - LOG)) & mask ;
+                    while (keys [h] != key) h = (h + 1) & mask ;
+                    a.Ci_out [q] = key ;
+                    acc [q] = vals [h] ;
+                    q++ ;
+                }
+                run += total ;
+            }
+            __syncthreads () ;
+            continue ;
+        }
+        for (int t = threadIdx.x ; t < size ; t += blockDim.x)
+        {
+            const int32_t key = keys [t] ;
+            if (key >= 0) comp [atomicAdd (&s_n, 1)] = ((uint64_t) (uint32_t) key << 32) | (uint32_t) t ;
+        }
+        __syncthreads () ;
+        const int n = s_n ;
+        int n2 = 1 ; while (n2 < n) n2 <<= 1 ;
+        for (int t = n + threadIdx.x ; t < n2 ; t += blockDim.x) comp [t] = ~0ULL ;
+        __syncthreads () ;
+        for (int k = 2 ; k <= n2 ; k <<= 1)
+        {
+            for (int j = k >> 1 ; j > 0 ; j >>= 1)
+            {
+                for (int t = threadIdx.x ; t < n2 ; t += blockDim.x)
+                {
+                    const int ixj = t ^ j ;
+                    if (ixj > t)
+                    {
+                        const uint64_t x = comp [t], y = comp [ixj] ;
+                        const bool asc = ((t & k) == 0) ;
+                        if ((x > y) == asc) { comp [t] = y ; comp [ixj] = x ; }
+                    }
+                }
+                __syncthreads () ;
+            }
+        }
+        for (int t = threadIdx.x ; t < n ; t += blockDim.x)
+        {
+            const uint64_t v = comp [t] ;
+            a.Ci_out [base + t] = (int32_t) (v >> 32) ;
+            acc [base + t] = vals [(uint32_t) v] ;
+        }
+        __syncthreads () ;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // saxpy numeric, light vectors: one thread block (32..512 threads) per vector of B.  Warps take
@@ -265,14 +398,24 @@ __global__ void dot_kernel (DotArgs a)
             }
         }
         // combine the G partial results (a fixed tree: deterministic for floating point)
-        unsigned fm = __ballot_sync (0xffffffffu, found) ;
-        for (int off = G >> 1 ; off > 0 ; off >>= 1)
+        const unsigned fm0 = __ballot_sync (0xffffffffu, found) ;
         {
-            acc_t other = __shfl_down_sync (0xffffffffu, cij, off, G) ;
-            // a lane without any match holds the identity; identity (+) t == t for every monoid
-            // (bit-for-bit except +0.0 + -0.0), so it can be combined unconditionally
-            if (gl + off < G) cij = Mon::combine (cij, other) ;
+            // only lanes that hold a product take part: the reference copies the first product and
+            // combines the later ones (GB_AxB_dot_cij.c:29-45), so a pair whose only products are NaN is
+            // NaN under MIN / MAX, where combining with the identity would give +-Inf
+            const int wl = threadIdx.x & 31 ;
+            unsigned fm = fm0 ;
+            for (int off = G >> 1 ; off > 0 ; off >>= 1)
+            {
+                acc_t other = __shfl_down_sync (0xffffffffu, cij, off, G) ;
+                const bool of = (gl + off < G) && ((fm >> (wl + off)) & 1u) ;
+                if (of) cij = ((fm >> wl) & 1u) ? Mon::combine (cij, other) : other ;
+                // lane l now also holds what lane l + off held (inside its own group only)
+                fm |= (gl + off < G) ? (((fm >> (wl + off)) & 1u) << wl) : 0u ;
+                fm = __reduce_or_sync (0xffffffffu, fm & (1u << wl)) ;
+            }
         }
+        const unsigned fm = fm0 ;
         if (t < a.npairs && gl == 0)
         {
             const int wl = threadIdx.x & 31 ;
@@ -630,12 +773,14 @@ __device__ __forceinline__ void dotg_walk (const S &sr, const DotGSeg<S> &g, con
             nm += cnt ;
             if (any)
             {
+                // only lanes that hold a product take part (see dot_kernel)
+                unsigned fm = __ballot_sync (0xffffffffu, found) ;
                 for (int off = 16 ; off > 0 ; off >>= 1)
                 {
-                    // a lane without any match holds the identity; identity (+) t == t for every
-                    // monoid (bit-for-bit except +0.0 + -0.0)
                     const acc_t other = __shfl_down_sync (0xffffffffu, cij, off) ;
-                    cij = Mon::combine (cij, other) ;
+                    const bool of = (lane + off < 32) && ((fm >> (lane + off)) & 1u) ;
+                    if (of) cij = ((fm >> lane) & 1u) ? Mon::combine (cij, other) : other ;
+                    fm |= (fm >> off) ;
                 }
             }
         }
@@ -782,7 +927,7 @@ enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_
     FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9,
     FAM_DOTG_ISO = 10, FAM_SPMV_OCC8 = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13,
     FAM_DOTR = 14, FAM_DOTR_ISO = 15, FAM_DOTR_BM = 16, FAM_DOTR_BM_ISO = 17, FAM_DOTR_WARP = 18,
-    FAM_DOTR_WARP_ISO = 19 } ;
+    FAM_DOTR_WARP_ISO = 19, FAM_SAXPY_HASH = 20 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -797,6 +942,19 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
         saxpy_light_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyArgs *) args) ;
     else if (family == FAM_SAXPY_HEAVY)
         saxpy_heavy_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyArgs *) args) ;
+    else if (family == FAM_SAXPY_HASH)
+    {
+        // per slot: accumulator + row + half a (row, slot) pair of the sort
+        const SaxpyArgs &sa = *(const SaxpyArgs *) args ;
+        const size_t smem = ((sizeof (typename S::acc_t) + 8) << sa.hash_log) + (size_t) sa.nwords * 4 ;
+        static size_t attr_smem = 48 * 1024 ;       // one per instantiation
+        if (smem > attr_smem)
+        {
+            cudaFuncSetAttribute (saxpy_hash_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) ;
+            attr_smem = smem ;
+        }
+        saxpy_hash_kernel<S> <<<cfg.grid, cfg.block, smem, cfg.stream>>> (sa) ;
+    }
     else if (family == FAM_DOTG || family == FAM_DOTG_ISO || family == FAM_DOTG_HUB
         || family == FAM_DOTG_HUB_ISO)
     {

@@ -273,11 +273,18 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
             {
                 if (tot)
                 {
-                    // a lane without any match holds the identity; identity (+) t == t for every
-                    // monoid (bit-for-bit except +0.0 + -0.0)
+                    // only lanes that hold a product take part (the reference copies the first product and
+                    // combines the later ones, GB_AxB_dot_cij.c:29-45: a pair whose only products are NaN
+                    // is NaN under MIN / MAX, where combining with the identity would give +-Inf)
+                    unsigned fm = __ballot_sync (FULL, found) ;
                     #pragma unroll
                     for (int off = 16 ; off > 0 ; off >>= 1)
-                        acc = Mon::combine (acc, __shfl_down_sync (FULL, acc, off)) ;
+                    {
+                        const acc_t other = __shfl_down_sync (FULL, acc, off) ;
+                        const bool of = (lane + off < 32) && ((fm >> (lane + off)) & 1u) ;
+                        if (of) acc = ((fm >> lane) & 1u) ? Mon::combine (acc, other) : other ;
+                        fm |= (fm >> off) ;
+                    }
                     acc = __shfl_sync (FULL, acc, 0) ;
                 }
                 if (lane == t) myacc = acc ;
@@ -341,7 +348,7 @@ dotr_kernel (DotGArgs a)
     __shared__ int64_t s_ws [33] ;
     __shared__ int s_next, s_fail ;
     __shared__ unsigned long long s_item ;
-    __shared__ int s_q0 ;
+    __shared__ int s_q0, s_q1 ;
     constexpr int CAP = dotg_cap (ISO) ;
     const S sr (a.mult_op, a.flip != 0) ;
     const T *__restrict__ Ax = (const T *) a.A.x ;
@@ -424,24 +431,35 @@ dotr_kernel (DotGArgs a)
                 const int nwords = (int) ((hi - lo + 32) >> 5) ;    // with the spare zero bit
                 __syncthreads () ;              // the previous part's walkers are done
                 for (int t = threadIdx.x ; t < nwords ; t += blockDim.x) bm [t] = 0u ;
-                if (!ISO && threadIdx.x == 0)
+                if (threadIdx.x < 2)
                 {
-                    // owner entries before this part: the position of a hit counts from the owner's start
+                    // the owner's entries of this part are a contiguous stretch [s_q0, s_q1) of its list
+                    const int64_t bound = threadIdx.x ? hi : lo ;
                     int l = 0, h = olen ;
                     while (l < h)
                     {
                         const int mid = (l + h) >> 1 ;
-                        if ((int64_t) __ldg (g.Oi + mid) < lo) l = mid + 1 ; else h = mid ;
+                        if ((int64_t) __ldg (g.Oi + mid) < bound) l = mid + 1 ; else h = mid ;
                     }
-                    s_q0 = l ;
+                    if (threadIdx.x) s_q1 = l ; else s_q0 = l ;
                 }
                 __syncthreads () ;
-                for (int q = threadIdx.x ; q < olen ; q += blockDim.x)
                 {
-                    const int64_t k = __ldg (g.Oi + q) ;
-                    if (k >= lo && k < hi)
+                    const int q0 = s_q0, q1 = s_q1 ;
+                    const uint32_t ulo = (uint32_t) lo ;
+                    int q = q0 + threadIdx.x ;
+                    // four loads in flight per thread
+                    for ( ; q + 3 * (int) blockDim.x < q1 ; q += 4 * blockDim.x)
                     {
-                        const uint32_t kk = (uint32_t) (k - lo) ;
+                        uint32_t kk [4] ;
+                        #pragma unroll
+                        for (int u = 0 ; u < 4 ; u++) kk [u] = (uint32_t) __ldg (g.Oi + q + u * (int) blockDim.x) - ulo ;
+                        #pragma unroll
+                        for (int u = 0 ; u < 4 ; u++) atomicOr (bm + (kk [u] >> 5), 1u << (kk [u] & 31)) ;
+                    }
+                    for ( ; q < q1 ; q += blockDim.x)
+                    {
+                        const uint32_t kk = (uint32_t) __ldg (g.Oi + q) - ulo ;
                         atomicOr (bm + (kk >> 5), 1u << (kk & 31)) ;
                     }
                 }

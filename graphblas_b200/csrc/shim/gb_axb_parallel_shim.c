@@ -57,6 +57,13 @@ static void shim_report (void)
 }
 
 __attribute__ ((visibility ("default")))
+void gb200_shim_cache (int on, int64_t *hits, int64_t *misses, int64_t *invalidations)
+{
+    if (on >= 0) gb200_cache_enable (on) ;
+    gb200_cache_stats (hits, misses, invalidations, NULL) ;
+}
+
+__attribute__ ((visibility ("default")))
 void gb200_shim_last (double *device_ms, int64_t *flops)
 {
     if (device_ms) *device_ms = g_last_device_ms ;
@@ -248,4 +255,139 @@ GrB_Info GB_AxB_parallel            /* same contract as reference Source/GB.h:15
     g_last_device_ms = f.device_ms ;
     g_last_flops = f.flops ;
     return (GrB_SUCCESS) ;
+}
+
+/* -------------------------------------------------------------------------------------------------
+ * Operand residency (include/gb_b200.h, gb200_cache_*): the library keeps device copies of operands
+ * keyed on their host arrays.  Frees and reallocations reach it through the gb200_host_* allocator;
+ * the reference's IN-PLACE writers are interposed here, the same way as GB_AxB_parallel, and report
+ * the arrays of the object they are about to change before the original runs:
+ *   GB_setElement       Source/GB.h:1990   writes C->x in place when the entry exists
+ *   GB_subassign_kernel Source/GB.h:2048   C(I,J)<M> = accum (C(I,J),A): values and zombies in place
+ *   GB_wait             Source/GB.h:1931   assembles pending tuples / deletes zombies (only ever called
+ *                                          when there is such work, GB_WAIT)
+ *   GxB_Matrix_import_* Include/GraphBLAS.h:5751-5886: arrays handed in by the user may be arrays it
+ *                                          got from an export and rewrote
+ * ------------------------------------------------------------------------------------------------- */
+static void *host_symbol (const char *name, void *self)
+{
+    void *fn = dlsym (RTLD_NEXT, name) ;
+    if (fn == NULL || fn == self)
+    {
+        void *meta = dlsym (RTLD_DEFAULT, "GB_AxB_meta") ;
+        Dl_info di ;
+        fn = NULL ;
+        if (meta != NULL && dladdr (meta, &di) != 0 && di.dli_fname != NULL)
+        {
+            void *h = dlopen (di.dli_fname, RTLD_LAZY | RTLD_NOLOAD) ;
+            if (h != NULL) fn = dlsym (h, name) ;
+        }
+    }
+    return ((fn == self) ? NULL : fn) ;
+}
+
+static void report_write (const GrB_Matrix C)
+{
+    if (C == NULL) return ;
+    gb200_cache_invalidate (C->p) ;
+    gb200_cache_invalidate (C->h) ;
+    gb200_cache_invalidate (C->i) ;
+    gb200_cache_invalidate (C->x) ;
+}
+
+__attribute__ ((visibility ("default")))
+GrB_Info GB_setElement (GrB_Matrix C, const void *scalar, const GrB_Index row, const GrB_Index col,
+    const GB_Type_code scalar_code, GB_Context Context)
+{
+    typedef GrB_Info (*fn_t) (GrB_Matrix, const void *, const GrB_Index, const GrB_Index,
+        const GB_Type_code, GB_Context) ;
+    static fn_t fn = NULL ;
+    if (fn == NULL) fn = (fn_t) host_symbol ("GB_setElement", (void *) GB_setElement) ;
+    if (fn == NULL) return (GrB_PANIC) ;
+    report_write (C) ;
+    return (fn (C, scalar, row, col, scalar_code, Context)) ;
+}
+
+__attribute__ ((visibility ("default")))
+GrB_Info GB_subassign_kernel (GrB_Matrix C, bool C_replace, const GrB_Matrix M, const bool Mask_comp,
+    const GrB_BinaryOp accum, const GrB_Matrix A, const GrB_Index *I, const int64_t ni,
+    const GrB_Index *J, const int64_t nj, const bool scalar_expansion, const void *scalar,
+    const GB_Type_code scalar_code, GB_Context Context)
+{
+    typedef GrB_Info (*fn_t) (GrB_Matrix, bool, const GrB_Matrix, const bool, const GrB_BinaryOp,
+        const GrB_Matrix, const GrB_Index *, const int64_t, const GrB_Index *, const int64_t, const bool,
+        const void *, const GB_Type_code, GB_Context) ;
+    static fn_t fn = NULL ;
+    if (fn == NULL) fn = (fn_t) host_symbol ("GB_subassign_kernel", (void *) GB_subassign_kernel) ;
+    if (fn == NULL) return (GrB_PANIC) ;
+    report_write (C) ;
+    return (fn (C, C_replace, M, Mask_comp, accum, A, I, ni, J, nj, scalar_expansion, scalar,
+        scalar_code, Context)) ;
+}
+
+__attribute__ ((visibility ("default")))
+GrB_Info GB_wait (GrB_Matrix A, GB_Context Context)
+{
+    typedef GrB_Info (*fn_t) (GrB_Matrix, GB_Context) ;
+    static fn_t fn = NULL ;
+    if (fn == NULL) fn = (fn_t) host_symbol ("GB_wait", (void *) GB_wait) ;
+    if (fn == NULL) return (GrB_PANIC) ;
+    report_write (A) ;
+    return (fn (A, Context)) ;
+}
+
+#define GB200_REPORT_ARRAY(pp) { if ((pp) != NULL) gb200_cache_invalidate (*(pp)) ; }
+
+__attribute__ ((visibility ("default")))
+GrB_Info GxB_Matrix_import_CSR (GrB_Matrix *A, const GrB_Type type, GrB_Index nrows, GrB_Index ncols,
+    GrB_Index nvals, int64_t nonempty, GrB_Index **Ap, GrB_Index **Aj, void **Ax, const GrB_Descriptor desc)
+{
+    typedef GrB_Info (*fn_t) (GrB_Matrix *, const GrB_Type, GrB_Index, GrB_Index, GrB_Index, int64_t,
+        GrB_Index **, GrB_Index **, void **, const GrB_Descriptor) ;
+    static fn_t fn = NULL ;
+    if (fn == NULL) fn = (fn_t) host_symbol ("GxB_Matrix_import_CSR", (void *) GxB_Matrix_import_CSR) ;
+    if (fn == NULL) return (GrB_PANIC) ;
+    GB200_REPORT_ARRAY (Ap) ; GB200_REPORT_ARRAY (Aj) ; GB200_REPORT_ARRAY (Ax) ;
+    return (fn (A, type, nrows, ncols, nvals, nonempty, Ap, Aj, Ax, desc)) ;
+}
+
+__attribute__ ((visibility ("default")))
+GrB_Info GxB_Matrix_import_CSC (GrB_Matrix *A, const GrB_Type type, GrB_Index nrows, GrB_Index ncols,
+    GrB_Index nvals, int64_t nonempty, GrB_Index **Ap, GrB_Index **Ai, void **Ax, const GrB_Descriptor desc)
+{
+    typedef GrB_Info (*fn_t) (GrB_Matrix *, const GrB_Type, GrB_Index, GrB_Index, GrB_Index, int64_t,
+        GrB_Index **, GrB_Index **, void **, const GrB_Descriptor) ;
+    static fn_t fn = NULL ;
+    if (fn == NULL) fn = (fn_t) host_symbol ("GxB_Matrix_import_CSC", (void *) GxB_Matrix_import_CSC) ;
+    if (fn == NULL) return (GrB_PANIC) ;
+    GB200_REPORT_ARRAY (Ap) ; GB200_REPORT_ARRAY (Ai) ; GB200_REPORT_ARRAY (Ax) ;
+    return (fn (A, type, nrows, ncols, nvals, nonempty, Ap, Ai, Ax, desc)) ;
+}
+
+__attribute__ ((visibility ("default")))
+GrB_Info GxB_Matrix_import_HyperCSR (GrB_Matrix *A, const GrB_Type type, GrB_Index nrows, GrB_Index ncols,
+    GrB_Index nvals, int64_t nonempty, GrB_Index nvec, GrB_Index **Ah, GrB_Index **Ap, GrB_Index **Aj,
+    void **Ax, const GrB_Descriptor desc)
+{
+    typedef GrB_Info (*fn_t) (GrB_Matrix *, const GrB_Type, GrB_Index, GrB_Index, GrB_Index, int64_t,
+        GrB_Index, GrB_Index **, GrB_Index **, GrB_Index **, void **, const GrB_Descriptor) ;
+    static fn_t fn = NULL ;
+    if (fn == NULL) fn = (fn_t) host_symbol ("GxB_Matrix_import_HyperCSR", (void *) GxB_Matrix_import_HyperCSR) ;
+    if (fn == NULL) return (GrB_PANIC) ;
+    GB200_REPORT_ARRAY (Ah) ; GB200_REPORT_ARRAY (Ap) ; GB200_REPORT_ARRAY (Aj) ; GB200_REPORT_ARRAY (Ax) ;
+    return (fn (A, type, nrows, ncols, nvals, nonempty, nvec, Ah, Ap, Aj, Ax, desc)) ;
+}
+
+__attribute__ ((visibility ("default")))
+GrB_Info GxB_Matrix_import_HyperCSC (GrB_Matrix *A, const GrB_Type type, GrB_Index nrows, GrB_Index ncols,
+    GrB_Index nvals, int64_t nonempty, GrB_Index nvec, GrB_Index **Ah, GrB_Index **Ap, GrB_Index **Ai,
+    void **Ax, const GrB_Descriptor desc)
+{
+    typedef GrB_Info (*fn_t) (GrB_Matrix *, const GrB_Type, GrB_Index, GrB_Index, GrB_Index, int64_t,
+        GrB_Index, GrB_Index **, GrB_Index **, GrB_Index **, void **, const GrB_Descriptor) ;
+    static fn_t fn = NULL ;
+    if (fn == NULL) fn = (fn_t) host_symbol ("GxB_Matrix_import_HyperCSC", (void *) GxB_Matrix_import_HyperCSC) ;
+    if (fn == NULL) return (GrB_PANIC) ;
+    GB200_REPORT_ARRAY (Ah) ; GB200_REPORT_ARRAY (Ap) ; GB200_REPORT_ARRAY (Ai) ; GB200_REPORT_ARRAY (Ax) ;
+    return (fn (A, type, nrows, ncols, nvals, nonempty, nvec, Ah, Ap, Ai, Ax, desc)) ;
 }

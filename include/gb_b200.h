@@ -138,7 +138,7 @@ typedef struct
     int64_t nnz ;
     int32_t is_hyper ;      /* rule of reference Source/GB_AxB_alloc.c:49-50                   */
     int32_t type_code ;     /* == semiring z_code                                             */
-    int32_t method_used ;   /* GB200_METHOD_GUSTAVSON or GB200_METHOD_DOT                     */
+    int32_t method_used ;   /* GB200_METHOD_DOT, or GB200_METHOD_GUSTAVSON (HEAP if HEAP was asked for) */
     int32_t mask_applied ;  /* 1 iff M (including its complement flag) was honoured           */
     int64_t flops ;         /* multiply-add pairs performed (reference GB_AxB_flopcount        */
                             /* definition for saxpy; matched index pairs for dot)             */
@@ -180,6 +180,20 @@ gb200_status gb200_AxB_host
     const gb200_semiring *semiring,
     int do_adotb, int method
 ) ;
+
+/* ---- operand residency across gb200_AxB_host calls (SURVEY.md 8b "Residency") ----------------
+ * With the cache on, gb200_AxB_host keeps the device copy of every matrix operand (not of vectors)
+ * keyed on the addresses and shape of its host arrays, so that the graph of a BFS / SSSP / k-truss
+ * loop crosses PCIe once.  An entry is dropped when one of its arrays is freed or reallocated
+ * (gb200_host_free / gb200_host_realloc report that themselves: use them as the GxB_init allocator),
+ * when the caller reports a write (gb200_cache_invalidate: the shim does so for the reference's
+ * in-place writers GB_setElement, GB_subassign_kernel, GB_wait and for GxB_*_import_*), or when a
+ * sampled fingerprint of the host arrays no longer matches.  Off by default (GB200_OPERAND_CACHE=1 or
+ * gb200_cache_enable (1)); bounded to a quarter of the device's memory (GB200_OPERAND_CACHE_MB). */
+void gb200_cache_enable (int on) ;
+void gb200_cache_invalidate (const void *array) ;    /* any of p, h, i, x of a cached operand       */
+void gb200_cache_clear (void) ;
+void gb200_cache_stats (int64_t *hits, int64_t *misses, int64_t *invalidations, int64_t *resident_bytes) ;
 
 /* ---- GB_AxB_flopcount on the device (reference Source/GB_AxB_flopcount.c:85-316) --------
  * Bflops_out (host, size B->nvec+1, may be NULL) receives the cumulative sum; *total the last

@@ -128,6 +128,14 @@ class GraphBLAS:
         self.shim.gb200_shim_stats(C.byref(a), C.byref(b), C.byref(c))
         return {"gpu_calls": a.value, "forwarded": b.value, "declined": c.value}
 
+    def shim_cache(self, on=None):
+        """operand residency of the library behind the shim: on = True / False switches it, None only
+        reads the counters -> dict(hits, misses, invalidations)"""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.shim.gb200_shim_cache(C.c_int(-1 if on is None else int(bool(on))), C.byref(a), C.byref(b),
+                                   C.byref(c))
+        return {"hits": a.value, "misses": b.value, "invalidations": c.value}
+
     def shim_last(self):
         ms, fl = C.c_double(), C.c_int64()
         self.shim.gb200_shim_last(C.byref(ms), C.byref(fl))
@@ -261,6 +269,29 @@ class GraphBLAS:
 
     def vector_free(self, v):
         self.lib.GrB_Vector_free(C.byref(v))
+
+    def demo_random_matrix(self, nrows: int, ncols: int, ntuples: int, seed=None):
+        """the reference's own generator (Demo/Source/random_matrix.c:26-181 over the LCG of
+        Demo/Source/simple_rand.c:31-64), from the compiled Demo library: a GrB_FP64 matrix.
+        seed: simple_rand_seed (seed) first (None: continue the stream, as consecutive calls in one
+        program do)."""
+        if not hasattr(self, "demo"):
+            self.demo = C.CDLL(DEMO_LIB, mode=C.RTLD_GLOBAL)
+        if seed is not None:
+            self.demo.simple_rand_seed(C.c_uint64(seed))
+        A = C.c_void_p()
+        self.ok(self.demo.random_matrix(C.byref(A), C.c_bool(False), C.c_bool(False), C.c_int64(nrows),
+                                        C.c_int64(ncols), C.c_int64(ntuples), C.c_int(1), C.c_bool(False)),
+                "random_matrix")
+        return A
+
+    def matrix_set_element(self, A, type_: str, i: int, j: int, x) -> None:
+        """GrB_Matrix_setElement_<type> (Include/GraphBLAS.h): A(i,j) = x"""
+        ct = {"FP64": C.c_double, "FP32": C.c_float, "INT64": C.c_int64, "INT32": C.c_int32,
+              "UINT64": C.c_uint64, "UINT32": C.c_uint32, "BOOL": C.c_bool}[type_]
+        fn = getattr(self.lib, "GrB_Matrix_setElement_" + type_)
+        fn.argtypes = [C.c_void_p, ct, C.c_uint64, C.c_uint64]
+        self.ok(fn(A, ct(x), C.c_uint64(i), C.c_uint64(j)), "GrB_Matrix_setElement")
 
     def matrix_nvals(self, A) -> int:
         n = C.c_uint64()

@@ -22,7 +22,7 @@ def _workload(name, scale):
     import torch
     args = argparse.Namespace(workload=name, scale=scale, ef=16, bfs_dir="push")
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    return bench.make_workload(args, dev)
+    return bench.make_workload(gb, args, dev)
 
 
 def _same(a: gb.Matrix, b: gb.Matrix, what):
@@ -47,7 +47,7 @@ def test_tricount_scale20_dot_equals_saxpy_and_slices():
     assert ntri == dot.info["flops"] and ntri > 0
     import bench
     cuts = [0, L.nvec // 3, 2 * L.nvec // 3, L.nvec]
-    parts = [gb.axb_host(bench.slice_vectors(L, cuts[k], cuts[k + 1]), False, U, L, sr, True).matrix
+    parts = [gb.axb_host(bench.slice_vectors(gb, L, cuts[k], cuts[k + 1]), False, U, L, sr, True).matrix
              for k in range(3)]
     assert sum(int(t.x.sum()) for t in parts) == ntri
     p = np.sum([t.p for t in parts], axis=0)

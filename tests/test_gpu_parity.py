@@ -271,3 +271,59 @@ def test_ktruss_iterations(G):
         if nxt.nnz == Cm.nnz or nxt.nnz == 0:
             break
         Cm = nxt
+
+
+# ---------------------------------------------------------------------------------------------
+# config 1 AS WRITTEN (BASELINE.json configs[0]): the reference's own random_matrix,
+# simple_rand_seed (1), n = 16384, 131072 draws for A and again for B; C = A*B over PLUS_TIMES_FP64 has
+# 1,046,459 entries (probe of the reference)
+# ---------------------------------------------------------------------------------------------
+def test_cfg1_exact_input(G):
+    from parity import compare, export_csr
+    n = 16384
+    a = G.demo_random_matrix(n, n, 131072, seed=1)
+    b = G.demo_random_matrix(n, n, 131072)
+    assert (G.matrix_nvals(a), G.matrix_nvals(b)) == (131048, 131043)
+    out = []
+    for gpu in (False, True):
+        c = G.matrix_new("FP64", n, n)
+        G.use_gpu(gpu)
+        before = G.shim_stats()
+        try:
+            G.mxm(c, None, None, "GxB_PLUS_TIMES_FP64", a, b, None)
+            G.matrix_nvals(c)
+        finally:
+            G.use_gpu(False)
+        if gpu:
+            assert G.shim_stats()["gpu_calls"] - before["gpu_calls"] == 1
+        out.append(export_csr(G, c))
+    G.matrix_free(a)
+    G.matrix_free(b)
+    assert out[0]["nvals"] == 1046459
+    ok, why = compare(out[0], out[1], "PLUS")
+    assert ok, why
+
+
+# ---------------------------------------------------------------------------------------------
+# NaN under MIN / MAX in the dot method: the reference copies the first product and fmin / fmax-combines
+# the later ones (GB_AxB_dot_cij.c:29-45), so C(i,j) is NaN exactly when ALL of its products are NaN
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("semiring", ["GxB_MIN_PLUS_FP64", "GxB_MAX_TIMES_FP64", "GxB_MIN_FIRST_FP32"])
+@pytest.mark.parametrize("masked", [True, False])
+def test_dot_nan_only_products(G, semiring, masked):
+    n = 300
+    type_ = semiring.split("_")[-1]
+    rng = np.random.default_rng(77)
+    A = gen.er(n, n, 6 * n, 31).astype(np.float64)
+    B = gen.er(n, n, 6 * n, 32).astype(np.float64)
+    A.data[rng.random(A.nnz) < 0.4] = np.nan
+    B.data[rng.random(B.nnz) < 0.2] = np.nan
+    # a few long (hub) vectors so that the table kernels see NaN too
+    A = A.tolil() ; B = B.tolil()
+    for c in (3, 9):
+        A[c, :] = np.where(rng.random(n) < 0.5, np.nan, 1.5)
+        B[:, c] = np.where(rng.random(n) < 0.5, np.nan, 2.5).reshape(-1, 1)
+    A, B = A.tocsr(), B.tocsr()
+    M = gen.er(n, n, 40 * n, 33, np.bool_) if masked else None
+    ref, got = check_mxm(G, A=A, B=B, M=M, type_=type_, semiring=semiring, method=GxB_AxB_DOT)
+    assert np.isnan(ref["Ax"]).any() and (~np.isnan(ref["Ax"])).any()

@@ -280,3 +280,23 @@ def test_oracle_typecast_vs_reference(G, ta, tb, add, mult, txy, dot):
         ref, used, applied = seam_reference(G, mask, False, A, B, sr, dot, GxB_AxB_GUSTAVSON)
         got = oracle_c.axb(mask, False, A, B, sr, dot)
         same(ref, got, exact=not (txy in ("FP32", "FP64") and add in ("PLUS", "TIMES")))
+
+
+def test_cfg1_exact_input_on_the_reference(G):
+    """BASELINE.json configs[0] as written: random_matrix after simple_rand_seed (1),
+    n = 16384, 131072 draws for A and again for B -> anz 131,048, bnz 131,043, nnz (A*B) 1,046,459; the
+    oracle restatement reproduces the reference's T at the seam on exactly this input"""
+    n = 16384
+    a = G.demo_random_matrix(n, n, 131072, seed=1)
+    b = G.demo_random_matrix(n, n, 131072)
+    assert (G.matrix_nvals(a), G.matrix_nvals(b)) == (131048, 131043)
+    c = G.matrix_new("FP64", n, n)
+    G.mxm(c, None, None, "GxB_PLUS_TIMES_FP64", a, b, None)
+    assert G.matrix_nvals(c) == 1046459
+    ea, eb, ec = (G.matrix_export(x, "CSR") for x in (a, b, c))
+    # CSR C = A*B at the seam: A := B_in, B := A_in, flipxy (SURVEY.md 3.2)
+    Am = gb.Matrix(n, n, eb["Ap"], eb["Ai"], eb["Ax"], None, "FP64")
+    Bm = gb.Matrix(n, n, ea["Ap"], ea["Ai"], ea["Ax"], None, "FP64")
+    T = oracle_c.axb(None, False, Am, Bm, gb.Semiring("PLUS", "TIMES", "FP64", flipxy=True))
+    assert np.array_equal(T.p, ec["Ap"]) and np.array_equal(T.i, ec["Ai"])
+    assert np.abs(T.x - ec["Ax"]).sum() <= 64 * np.finfo(np.float64).eps * np.abs(ec["Ax"]).sum()
