@@ -714,32 +714,25 @@ def measure(args, env, primary=True):
     # slices of w are all-gathered over NCCL every step; T never leaves HBM
     exchange = None
     if world > 1 and sliced_name == "A" and A.vdim >= 1 and B.vdim == 1:
-        cap = int(np.diff(bounds).max())
-        zdt = {"FP64": torch.float64, "FP32": torch.float32, "INT64": torch.int64, "INT32": torch.int32,
-               "BOOL": torch.bool}.get(w["semiring"].ztype, torch.uint8)
-        exchange = {"p": torch.zeros(2, dtype=torch.int64, device=device),
-                    "i": torch.zeros(cap, dtype=torch.int64, device=device),
-                    "x": torch.zeros(cap, dtype=zdt, device=device),
-                    "n": torch.zeros(1, dtype=torch.int64, device=device),
-                    "ai": torch.zeros(cap * world, dtype=torch.int64, device=device),
-                    "ax": torch.zeros(cap * world, dtype=zdt, device=device),
-                    "an": torch.zeros(world, dtype=torch.int64, device=device), "bytes": 0}
+        def allgather_bytes(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        pb = gb.PeerBuf(A.vdim, w["semiring"].ztype, rank, world, allgather_bytes)
+        exchange = {"pb": pb, "bytes": 0}
 
     def step_device():
         out = {"flops": 0, "nnz": 0, "device_ms": 0.0, "kernel_ms": 0.0, "nvec": 0, "infos": []}
         for (_, _, _, dm, da, db) in calls:
             if exchange is not None:
+                # the rank's block of w goes straight into every GPU's dense copy over NVLink peer
+                # memory (gb200_peerbuf_publish: one kernel on the library's stream), then a device-side
+                # wait for all ranks' flags: no NCCL call, no host synchronisation inside the step
                 rh, info = gb.axb_device_keep(dm, w["mask_comp"], da, db, w["semiring"], w["do_adotb"])
-                ex = exchange
-                gb.fetch_into(rh, ex["p"].data_ptr(), 0, ex["i"].data_ptr() if info["nnz"] else 0,
-                              ex["x"].data_ptr() if info["nnz"] else 0)
+                exchange["pb"].publish(rh)
                 gb.free_result(rh)
-                ex["n"][0] = info["nnz"]
-                dist.all_gather_into_tensor(ex["an"], ex["n"])
-                dist.all_gather_into_tensor(ex["ai"], ex["i"])
-                dist.all_gather_into_tensor(ex["ax"], ex["x"])
-                torch.cuda.synchronize()
-                ex["bytes"] = (ex["i"].numel() * 8 + ex["x"].numel() * ex["x"].element_size()) * world
+                exchange["pb"].wait()
+                exchange["bytes"] = info["nnz"] * (np.dtype(gb.TYPES[w["semiring"].ztype][1]).itemsize + 1) * world
             else:
                 info = gb.axb_device(dm, w["mask_comp"], da, db, w["semiring"], w["do_adotb"],
                                      fetch=False).info
@@ -990,8 +983,9 @@ def measure(args, env, primary=True):
                                          f"{world} flop-balanced contiguous slices of "
                                          f"{ {'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors"),
                            "calibration_ms": w.get("calibration_ms"),
-                           "exchange": ("NCCL all-gather of the slices of w every step, "
-                                        f"{exchange['bytes']} B gathered per rank") if exchange else
+                           "exchange": ("in-library: peer stores of the rank's block of w into every GPU's "
+                                        "dense copy over NVLink (gb200_peerbuf_publish / _wait), "
+                                        f"{exchange['bytes']} B stored per rank per step") if exchange else
                                        "none (independent output vectors; scalars all-reduced)"},
                 "parity": parity,
                 "wall_ms_per_step": tt[1].item() / args.steps * 1e3,

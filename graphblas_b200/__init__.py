@@ -77,6 +77,14 @@ _SIGS = {
     "gb200_host_free": (None, [_VP]),
     "gb200_host_trim": (None, []),
     "gb200_device_trim": (None, []),
+    "gb200_peerbuf_create": (_I, [_VP, _I64, _I, _I, _I]),
+    "gb200_peerbuf_handle": (_I, [_VP, _VP]),
+    "gb200_peerbuf_connect": (_I, [_VP, _VP]),
+    "gb200_peerbuf_publish": (_I, [_VP, _VP]),
+    "gb200_peerbuf_wait": (_I, [_VP]),
+    "gb200_peerbuf_view": (_I, [_VP, _VP, _VP, _VP]),
+    "gb200_peerbuf_read": (_I, [_VP, _VP, _VP]),
+    "gb200_peerbuf_free": (_I, [_VP]),
     "gb200_cache_enable": (None, [_I]),
     "gb200_cache_invalidate": (None, [_VP]),
     "gb200_cache_clear": (None, []),
@@ -263,6 +271,48 @@ def partition_by_flops(cum: np.ndarray, nparts: int) -> np.ndarray:
                                         bounds.ctypes.data_as(C.c_void_p)),
            "gb200_partition_by_flops")
     return bounds
+
+
+class PeerBuf:
+    """gb200_peerbuf: a dense copy of an n-vector on every GPU of the box, written by all ranks over
+    NVLink peer memory.  `allgather_bytes(b: bytes) -> list[bytes]` exchanges the 64-byte IPC handles
+    (e.g. torch.distributed.all_gather_object)."""
+
+    def __init__(self, n: int, type_: str, rank: int, world: int, allgather_bytes):
+        self._h = C.c_void_p()
+        self.n, self.type, self.rank, self.world = n, type_, rank, world
+        _check(lib.gb200_peerbuf_create(C.byref(self._h), n, TYPES[type_][0], rank, world),
+               "gb200_peerbuf_create")
+        mine = C.create_string_buffer(64)
+        _check(lib.gb200_peerbuf_handle(self._h, mine), "gb200_peerbuf_handle")
+        everyone = allgather_bytes(mine.raw)
+        blob = C.create_string_buffer(b"".join(everyone), 64 * world)
+        _check(lib.gb200_peerbuf_connect(self._h, blob), "gb200_peerbuf_connect")
+
+    def publish(self, result_handle) -> None:
+        _check(lib.gb200_peerbuf_publish(self._h, result_handle), "gb200_peerbuf_publish")
+
+    def wait(self) -> None:
+        _check(lib.gb200_peerbuf_wait(self._h), "gb200_peerbuf_wait")
+
+    def view(self):
+        """(values device pointer, presence device pointer, tag) of the current epoch; synchronises"""
+        v, p, t = C.c_void_p(), C.c_void_p(), C.c_int()
+        _check(lib.gb200_peerbuf_view(self._h, C.byref(v), C.byref(p), C.byref(t)), "gb200_peerbuf_view")
+        return v.value, p.value, t.value
+
+    def read(self):
+        """(values [n], present [n] bool) of the current epoch on the host"""
+        vals = np.empty(self.n, dtype=TYPES[self.type][1])
+        pres = np.empty(self.n, dtype=np.uint8)
+        _check(lib.gb200_peerbuf_read(self._h, vals.ctypes.data_as(C.c_void_p),
+                                      pres.ctypes.data_as(C.c_void_p)), "gb200_peerbuf_read")
+        return vals, pres != 0
+
+    def free(self):
+        if self._h:
+            lib.gb200_peerbuf_free(C.byref(self._h))
+            self._h = C.c_void_p()
 
 
 def cache_enable(on: bool) -> None:

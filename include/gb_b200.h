@@ -212,6 +212,24 @@ gb200_status gb200_partition_by_flops
     const int64_t *Bflops_cumulative, int64_t nvec, int nparts, int64_t *bounds
 ) ;
 
+/* ---- the exchange step of the vector multiplies on the N GPUs of one box ----------
+ * One process per GPU; every rank owns a block of A's vectors = of w's entries.  A gb200_peerbuf is a
+ * dense copy of w (values + one presence byte per entry) on every GPU, mapped into every process with
+ * CUDA IPC.  publish writes the entries of the rank's T (n-by-1) into ALL copies with peer stores over
+ * NVLink -- one kernel on the library's stream, no staging, no host synchronisation -- and raises the
+ * rank's flag on every GPU; wait returns (on the stream) once every rank has published the same
+ * epoch.  The handles (64 bytes each) are exchanged by the host language (torch.distributed, MPI...). */
+typedef struct gb200_peerbuf_s *gb200_peerbuf ;
+gb200_status gb200_peerbuf_create  (gb200_peerbuf *out, int64_t n, int type_code, int rank, int world) ;
+gb200_status gb200_peerbuf_handle  (gb200_peerbuf pb, void *handle64) ;
+gb200_status gb200_peerbuf_connect (gb200_peerbuf pb, const void *handles /* world x 64 bytes */) ;
+gb200_status gb200_peerbuf_publish (gb200_peerbuf pb, gb200_result T) ;
+gb200_status gb200_peerbuf_wait    (gb200_peerbuf pb) ;
+/* device pointers of the current epoch's whole vector: values [n], presence [n] (== *tag where present) */
+gb200_status gb200_peerbuf_view    (gb200_peerbuf pb, void **values, unsigned char **presence, int *tag) ;
+gb200_status gb200_peerbuf_read    (gb200_peerbuf pb, void *values, unsigned char *presence) ;  /* copies out */
+gb200_status gb200_peerbuf_free    (gb200_peerbuf *pb) ;
+
 /* ---- pinned host memory ---------------------------------------------------------------------
  * A malloc / calloc / realloc / free quartet with the signatures GxB_init takes (reference
  * Include/GraphBLAS.h:330-340).  A host application that starts the reference with

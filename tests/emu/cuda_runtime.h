@@ -104,6 +104,8 @@ static inline void __syncthreads ()
 }
 static inline void __syncwarp (unsigned mask = 0xffffffffu) { emu::group_sync (mask) ; }
 static inline void __threadfence () { __atomic_thread_fence (__ATOMIC_SEQ_CST) ; }
+static inline void __threadfence_system () { __atomic_thread_fence (__ATOMIC_SEQ_CST) ; }
+static inline void __nanosleep (unsigned) { }
 static inline void __trap () { fprintf (stderr, "emu: __trap()\n") ; abort () ; }
 static inline int __popc (unsigned v) { return __builtin_popcount (v) ; }
 static inline int __ffs (unsigned v) { return __builtin_ffs ((int) v) ; }
@@ -302,6 +304,12 @@ struct emuEvent { double ms ; } ;
 typedef emuEvent *cudaEvent_t ;
 static inline double emu_now_ms ()
 { struct timespec ts ; clock_gettime (CLOCK_MONOTONIC, &ts) ; return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6 ; }
+// CUDA IPC has no host stand-in: the peer-memory exchange (engine_peer.cu) reports an error here
+struct cudaIpcMemHandle_t { char reserved [64] ; } ;
+enum { cudaIpcMemLazyEnablePeerAccess = 1 } ;
+static inline cudaError_t cudaIpcGetMemHandle (cudaIpcMemHandle_t *, void *) { return 999 ; }
+static inline cudaError_t cudaIpcOpenMemHandle (void **, cudaIpcMemHandle_t, unsigned) { return 999 ; }
+static inline cudaError_t cudaIpcCloseMemHandle (void *) { return cudaSuccess ; }
 static inline cudaError_t cudaGetDeviceCount (int *n) { *n = 1 ; return cudaSuccess ; }
 static inline cudaError_t cudaSetDevice (int) { return cudaSuccess ; }
 static inline cudaError_t cudaGetDeviceProperties (cudaDeviceProp *p, int)
