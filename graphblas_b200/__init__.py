@@ -77,6 +77,8 @@ _SIGS = {
     "gb200_host_free": (None, [_VP]),
     "gb200_host_trim": (None, []),
     "gb200_device_trim": (None, []),
+    "gb200_select_device": (_I, [_VP, _VP, _I, _I64]),
+    "gb200_select_host": (_I, [_VP, _VP, _I, _I64]),
     "gb200_peerbuf_create": (_I, [_VP, _I64, _I, _I, _I]),
     "gb200_peerbuf_handle": (_I, [_VP, _VP]),
     "gb200_peerbuf_connect": (_I, [_VP, _VP]),
@@ -271,6 +273,18 @@ def partition_by_flops(cum: np.ndarray, nparts: int) -> np.ndarray:
                                         bounds.ctypes.data_as(C.c_void_p)),
            "gb200_partition_by_flops")
     return bounds
+
+
+SELECT_OPS = {"TRIL": 0, "TRIU": 1, "DIAG": 2, "OFFDIAG": 3, "NONZERO": 4}
+
+
+def select_host(A: Matrix, op: str, k: int = 0, pinned: bool = False) -> Result:
+    """GxB_select with a built-in operator on the device (gb200_select_host + fetch); `A` in the
+    CSC-agnostic layout: TRIL keeps (vector - index) <= k, and so on."""
+    rh = C.c_void_p()
+    ca = A.c()
+    _check(lib.gb200_select_host(C.byref(rh), C.byref(ca), SELECT_OPS[op], k), "gb200_select_host")
+    return _fetch(rh, True, pinned)
 
 
 class PeerBuf:

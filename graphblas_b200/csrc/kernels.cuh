@@ -368,7 +368,9 @@ __global__ void dot_kernel (DotArgs a)
                     if (l >= pbe) break ;
                     if (__ldg (a.B.i + l) == k)
                     {
-                        cij = Mon::combine (cij, sr.product (Ax [p], Bx [l])) ;
+                        // sparse case: the first product is copied, later ones combined (dot_cij.c:29-45)
+                        const acc_t prod = sr.product (Ax [p], Bx [l]) ;
+                        cij = found ? Mon::combine (cij, prod) : prod ;
                         found = true ; nm++ ;
                         if (Mon::has_terminal () && Mon::is_terminal (cij)) break ;
                     }
@@ -390,7 +392,8 @@ __global__ void dot_kernel (DotArgs a)
                     if (l >= pe) break ;
                     if (__ldg (a.A.i + l) == k)
                     {
-                        cij = Mon::combine (cij, sr.product (Ax [l], Bx [p])) ;
+                        const acc_t prod = sr.product (Ax [l], Bx [p]) ;
+                        cij = found ? Mon::combine (cij, prod) : prod ;
                         found = true ; nm++ ;
                         if (Mon::has_terminal () && Mon::is_terminal (cij)) break ;
                     }
@@ -782,6 +785,8 @@ __device__ __forceinline__ void dotg_walk (const S &sr, const DotGSeg<S> &g, con
                     if (of) cij = ((fm >> lane) & 1u) ? Mon::combine (cij, other) : other ;
                     fm |= (fm >> off) ;
                 }
+                // a dense owner: the reference starts from the identity there (dot_cij.c:110,125,141)
+                if constexpr (DENSE) cij = Mon::combine (Mon::identity (), cij) ;
             }
         }
         if (any && lane == 0)

@@ -286,6 +286,9 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
                         fm |= (fm >> off) ;
                     }
                     acc = __shfl_sync (FULL, acc, 0) ;
+                    // a dense owner: the reference starts from the identity there (dot_cij.c:110,125,141),
+                    // so NaN products are dropped by fmin / fmax even when there is nothing else
+                    if constexpr (MODE == DOTR_DENSE) acc = Mon::combine (Mon::identity (), acc) ;
                 }
                 if (lane == t) myacc = acc ;
             }

@@ -391,3 +391,92 @@ GrB_Info GxB_Matrix_import_HyperCSC (GrB_Matrix *A, const GrB_Type type, GrB_Ind
     GB200_REPORT_ARRAY (Ah) ; GB200_REPORT_ARRAY (Ap) ; GB200_REPORT_ARRAY (Ai) ; GB200_REPORT_ARRAY (Ax) ;
     return (fn (A, type, nrows, ncols, nvals, nonempty, nvec, Ah, Ap, Ai, Ax, desc)) ;
 }
+
+/* -------------------------------------------------------------------------------------------------
+ * GxB_select with a built-in operator: GB_select (reference Source/GB.h:1185-1197,
+ * body Source/GB_select.c:30-386) is interposed like GB_AxB_parallel.  Only the clean path is taken
+ * here -- built-in operator and type, no pending work, checks passed: T = select (A,k) is computed by
+ * libgb_b200.so (gb200_select_host), built with the reference's GB_create, and handed to the
+ * reference's own GB_accum_mask exactly as GB_select.c:383 does.  Every other call (user-defined
+ * operators, errors to report, the quick-mask case) goes to the reference's own GB_select untouched.
+ * ------------------------------------------------------------------------------------------------- */
+static int64_t g_select_calls = 0 ;
+
+__attribute__ ((visibility ("default")))
+int64_t gb200_shim_select_calls (void) { return (g_select_calls) ; }
+
+typedef GrB_Info (*gb_select_fn) (GrB_Matrix, const bool, const GrB_Matrix, const bool,
+    const GrB_BinaryOp, const GxB_SelectOp, const GrB_Matrix, const void *, const bool, GB_Context) ;
+typedef GrB_Info (*gb_accum_mask_fn) (GrB_Matrix, const GrB_Matrix, const GrB_Matrix, const GrB_BinaryOp,
+    GrB_Matrix *, const bool, const bool, GB_Context) ;
+typedef GrB_Info (*gb_compatible_fn) (const GrB_Type, const GrB_Matrix, const GrB_Matrix,
+    const GrB_BinaryOp, const GrB_Type, GB_Context) ;
+
+__attribute__ ((visibility ("default")))
+GrB_Info GB_select (GrB_Matrix C, const bool C_replace, const GrB_Matrix M, const bool Mask_comp,
+    const GrB_BinaryOp accum, const GxB_SelectOp op, const GrB_Matrix A, const void *k,
+    const bool A_transpose, GB_Context Context)
+{
+    static gb_select_fn orig = NULL ;
+    static gb_accum_mask_fn accum_mask = NULL ;
+    static gb_compatible_fn compatible = NULL ;
+    if (orig == NULL) orig = (gb_select_fn) host_symbol ("GB_select", (void *) GB_select) ;
+    if (accum_mask == NULL) accum_mask = (gb_accum_mask_fn) dlsym (RTLD_DEFAULT, "GB_accum_mask") ;
+    if (compatible == NULL) compatible = (gb_compatible_fn) dlsym (RTLD_DEFAULT, "GB_compatible") ;
+    if (orig == NULL) return (GrB_PANIC) ;
+    if (g_enabled < 0) g_enabled = (getenv ("GB200_SHIM_DISABLE") != NULL) ? 0 : 1 ;
+    int mine = g_enabled && accum_mask != NULL && compatible != NULL && bind_host ()
+        && C != NULL && A != NULL && op != NULL && op->magic == GB_MAGIC && C->magic == GB_MAGIC
+        && A->magic == GB_MAGIC && (M == NULL || M->magic == GB_MAGIC)
+        && (accum == NULL || accum->magic == GB_MAGIC)
+        && op->opcode <= GB_NONZERO_opcode && A->type->code < GB_UCT_code
+        && !(op->opcode < GB_NONZERO_opcode && k == NULL)
+        && !GB_PENDING (A) && !GB_ZOMBIES (A) && !GB_PENDING (M) && !GB_ZOMBIES (M)
+        && !(Mask_comp && M == NULL) ;                                  /* the quick-mask return */
+    if (mine)
+    {
+        /* the checks of GB_select.c:63-93: a failure is reported by the reference itself */
+        int64_t tnrows = (A_transpose) ? GB_NCOLS (A) : GB_NROWS (A) ;
+        int64_t tncols = (A_transpose) ? GB_NROWS (A) : GB_NCOLS (A) ;
+        mine = (compatible (C->type, C, M, accum, A->type, Context) == GrB_SUCCESS)
+            && GB_NROWS (C) == tnrows && GB_NCOLS (C) == tncols ;
+    }
+    if (!mine) return (orig (C, C_replace, M, Mask_comp, accum, op, A, k, A_transpose, Context)) ;
+
+    /* CSR / CSC and the transposed case: the operator is flipped instead (GB_select.c:118-170) */
+    bool A_csc = (A->is_csc == !A_transpose) ;
+    int opcode = op->opcode ;
+    int64_t kk = (opcode < GB_NONZERO_opcode) ? (*((const int64_t *) k)) : 0 ;
+    if (!A_csc && opcode < GB_NONZERO_opcode)
+    {
+        kk = -kk ;
+        if (opcode == GB_TRIL_opcode) opcode = GB_TRIU_opcode ;
+        else if (opcode == GB_TRIU_opcode) opcode = GB_TRIL_opcode ;
+    }
+    gb200_matrix am ;
+    int64_t *tp_a = NULL ;
+    gb200_result r = NULL ;
+    gb200_status st = GB200_OUT_OF_MEMORY ;
+    if (as_abi (&am, A, &tp_a)) st = gb200_select_host (&r, &am, opcode, kk) ;
+    free (tp_a) ;
+    if (st != GB200_SUCCESS)
+    {
+        /* nothing was changed: let the reference do it (and report what there is to report) */
+        return (orig (C, C_replace, M, Mask_comp, accum, op, A, k, A_transpose, Context)) ;
+    }
+    gb200_result_info f ;
+    gb200_result_get_info (r, &f) ;
+    GrB_Matrix T = NULL ;
+    GrB_Info info = host_create (&T, A->type, A->vlen, A->vdim, GB_Ap_malloc, A_csc,
+        GB_SAME_HYPER_AS (f.is_hyper), A->hyper_ratio, (f.nvec > 0) ? f.nvec : 1,
+        (f.nnz > 0) ? f.nnz : 1, true, Context) ;
+    if (info != GrB_SUCCESS) { gb200_result_free (&r) ; return (info) ; }
+    st = gb200_result_fetch (r, T->p, f.is_hyper ? T->h : NULL, T->i, T->x) ;
+    gb200_result_free (&r) ;
+    if (st != GB200_SUCCESS) { host_free (&T) ; return ((st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC) ; }
+    if (f.is_hyper) T->nvec = f.nvec ;
+    T->nvec_nonempty = f.nvec_nonempty ;
+    T->magic = GB_MAGIC ;
+    __atomic_fetch_add (&g_select_calls, 1, __ATOMIC_RELAXED) ;
+    return (accum_mask (C, M, NULL, accum, &T, C_replace, Mask_comp, Context)) ;
+}

@@ -181,6 +181,19 @@ gb200_status gb200_AxB_host
     int do_adotb, int method
 ) ;
 
+/* ---- GxB_select with the built-in operators (reference Source/GB_select.c:219-323:
+ * the step that builds L = tril (A,-1), U = triu (A,1) in front of the triangle-counting multiply).
+ * Codes are numbered like GB_Select_Opcode (Source/GB.h:629-642).  In the CSC-agnostic terms of the
+ * matrix (j = vector, i = index in it): TRIL keeps j - i <= k, TRIU j - i >= k, DIAG j - i == k,
+ * OFFDIAG j - i != k, NONZERO x != 0.  T has A's type, dimensions and hypersparsity. */
+typedef enum
+{
+    GB200_SELECT_TRIL = 0, GB200_SELECT_TRIU = 1, GB200_SELECT_DIAG = 2, GB200_SELECT_OFFDIAG = 3,
+    GB200_SELECT_NONZERO = 4
+} gb200_select_op ;
+gb200_status gb200_select_device (gb200_result *out, gb200_dmatrix A, int select_op, int64_t k) ;
+gb200_status gb200_select_host   (gb200_result *out, const gb200_matrix *A, int select_op, int64_t k) ;
+
 /* ---- operand residency across gb200_AxB_host calls (SURVEY.md 8b "Residency") ----------------
  * With the cache on, gb200_AxB_host keeps the device copy of every matrix operand (not of vectors)
  * keyed on the addresses and shape of its host arrays, so that the graph of a BFS / SSSP / k-truss

@@ -332,6 +332,18 @@ class GraphBLAS:
         self.ok(self.lib.GrB_vxm(w, mask, self.obj(accum) if accum else None, self.obj(semiring), u,
                                  A, desc), "GrB_vxm")
 
+    def select(self, Cm, M, accum, op: str, A, k: int, desc):
+        """GxB_select (Include/GraphBLAS.h:4670-4679) with a built-in operator: op in TRIL, TRIU, DIAG,
+        OFFDIAG, NONZERO"""
+        kk = C.c_int64(k)
+        self.ok(self.lib.GxB_Matrix_select(Cm, M, self.obj(accum) if accum else None,
+                                           self.obj("GxB_" + op), A, C.byref(kk), desc),
+                "GxB_select")
+
+    def shim_select_calls(self) -> int:
+        self.shim.gb200_shim_select_calls.restype = C.c_int64
+        return self.shim.gb200_shim_select_calls()
+
     # ---- the seam itself: the reference's own GB_AxB_parallel (Source/GB.h:1522-1537) ---------
     def seam_axb(self, M, mask_comp: bool, A, B, semiring: str, flipxy: bool, do_adotb: bool,
                  method: int = GxB_DEFAULT):

@@ -10,7 +10,7 @@ import gen
 import grbref
 from grbref import (GxB_DEFAULT, GrB_REPLACE, GrB_SCMP, GrB_TRAN, GxB_AxB_GUSTAVSON, GxB_AxB_HEAP,
                     GxB_AxB_DOT)
-from parity import check_mxm, check_mv
+from parity import check_mxm, check_mv, REF_ONLY
 
 pytestmark = pytest.mark.gpu
 
@@ -327,3 +327,67 @@ def test_dot_nan_only_products(G, semiring, masked):
     M = gen.er(n, n, 40 * n, 33, np.bool_) if masked else None
     ref, got = check_mxm(G, A=A, B=B, M=M, type_=type_, semiring=semiring, method=GxB_AxB_DOT)
     assert np.isnan(ref["Ax"]).any() and (~np.isnan(ref["Ax"])).any()
+
+# ---------------------------------------------------------------------------------------------
+# GxB_select with the built-in operators (row f4): the interposed GB_select computes T = select (A,k)
+# on the device and hands it to the reference's own GB_accum_mask
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("op,k", [("TRIL", -1), ("TRIU", 1), ("TRIL", 0), ("TRIU", -3), ("DIAG", 0),
+                                  ("DIAG", 2), ("OFFDIAG", 0), ("OFFDIAG", -1), ("NONZERO", 0)])
+@pytest.mark.parametrize("fmt", ["CSR", "CSC", "HyperCSR", "HyperCSC"])
+@pytest.mark.parametrize("tran", [GxB_DEFAULT, GrB_TRAN])
+def test_select_builtin(G, op, k, fmt, tran):
+    from parity import compare, export_csr, import_sp
+    rng = np.random.default_rng(5)
+    nr, nc = (300, 420)
+    A = gen.er(nr, nc, 9 * nr, 41).tolil()
+    A[7, :] = 1.5                      # a long vector
+    A[:, 11] = 2.5
+    A = A.tocsr()
+    A.data[rng.random(A.nnz) < 0.2] = 0.0          # explicit zeros (NONZERO drops them)
+    if "Hyper" in fmt:
+        A = A.tolil() ; A[::3, :] = 0 ; A = A.tocsr() ; A.eliminate_zeros()
+        A.data[rng.random(A.nnz) < 0.2] = 0.0
+    out = []
+    for gpu in (False, True):
+        a = import_sp(G, A, "FP64", fmt)
+        shape = (nc, nr) if tran == GrB_TRAN else (nr, nc)
+        c = import_sp(G, sp.csr_matrix(shape), "FP64", "CSR")
+        d = G.descriptor(inp0=tran)
+        G.use_gpu(gpu)
+        before = G.shim_select_calls()
+        try:
+            G.select(c, None, None, op, a, k, d)
+            G.matrix_nvals(c)
+        finally:
+            G.use_gpu(False)
+        if gpu and not REF_ONLY:
+            assert G.shim_select_calls() - before == 1, "the GPU select did not run"
+        out.append(export_csr(G, c))
+        G.matrix_free(a)
+        G.descriptor_free(d)
+    ok, why = compare(out[0], out[1], "MIN")        # values are copies: exact
+    assert ok, why
+
+
+def test_select_with_mask_and_accum(G):
+    from parity import compare, export_csr, import_sp
+    n = 200
+    A = gen.er(n, n, 12 * n, 51)
+    Cinit = gen.er(n, n, 5 * n, 52)
+    M = gen.er(n, n, 20 * n, 53, np.bool_)
+    out = []
+    for gpu in (False, True):
+        a, c, m = import_sp(G, A, "FP64", "CSR"), import_sp(G, Cinit, "FP64", "CSR"), import_sp(G, M, "BOOL", "CSR")
+        d = G.descriptor(mask=GrB_SCMP, outp=GrB_REPLACE)
+        G.use_gpu(gpu)
+        try:
+            G.select(c, m, "GrB_PLUS_FP64", "TRIL", a, -1, d)
+            G.matrix_nvals(c)
+        finally:
+            G.use_gpu(False)
+        out.append(export_csr(G, c))
+        for h in (a, m):
+            G.matrix_free(h)
+    ok, why = compare(out[0], out[1], "MIN")
+    assert ok, why
