@@ -216,7 +216,7 @@ def make_workload(C, args, device):
                       f"edgefactor {args.ef}, n={n}, nnz(L)={L.nnz}",
                  M=L, A=U, B=L, mask_comp=False, do_adotb=True,
                  semiring=C.Semiring("PLUS", "TIMES", "INT64", flipxy=True), dtype="int64",
-                 slice="M")
+                 slice="M", kernel="dotr_kernel x4 + dotr_warp_kernel x2 + dot_kernel (masked dot)")
     elif args.workload == "spgemm":
         import gen
         n = 1 << args.scale
@@ -251,7 +251,8 @@ def make_workload(C, args, device):
         w.update(name=f"GrB_mxv d=A min.+ d MIN_PLUS_FP64 (dot, dense vector), RMAT scale {args.scale} "
                       f"edgefactor {args.ef}, n={n}, nnz(A)={Am.nnz}, one Bellman-Ford relaxation",
                  M=None, A=Am, B=dv, mask_comp=False, do_adotb=True,
-                 semiring=C.Semiring("MIN", "PLUS", "FP64"), dtype="f64", slice="A")
+                 semiring=C.Semiring("MIN", "PLUS", "FP64"), dtype="f64", slice="A",
+                 kernel="spmv_stream_kernel")
     elif args.workload == "bfs":
         # bfs5m level loop (Demo/Source/bfs5m.c:71-82): q<!v> = q*A over LOR_LAND_BOOL, A CSR: the
         # seam sees A*B by saxpy with B = q (n x 1), M = v complemented, flipxy
@@ -263,7 +264,8 @@ def make_workload(C, args, device):
                       f"{args.scale} edgefactor {args.ef}, n={n}, nnz(A)={Am.nnz}",
                  M=None, A=Am, B=None, mask_comp=True, do_adotb=(args.bfs_dir == "pull"),
                  semiring=C.Semiring("LOR", "LAND", "BOOL", flipxy=True), dtype="bool", slice="none",
-                 bfs_source=int(np.argmax(np.diff(Am.p))))
+                 bfs_source=int(np.argmax(np.diff(Am.p))),
+                 kernel="dotv_kernel (pull)" if args.bfs_dir == "pull" else "saxpyv_kernel + saxpyv_long_kernel (push)")
     else:
         raise SystemExit(f"unknown workload {args.workload}")
     sr = w["semiring"]
@@ -1006,8 +1008,8 @@ def measure(args, env, primary=True):
                              "frac": achieved / peak, "traffic": traffic,
                              **({"traffic_note": traffic_note} if traffic_note else {}),
                              **({"traffic_over_algorithmic": traffic / ab} if traffic else {}),
-                             "kernel": w.get("kernel", "dotg_kernel/dot_kernel" if w["do_adotb"]
-                                             else "saxpy_*_kernel"),
+                             "kernel": w.get("kernel", "dot kernels" if w["do_adotb"] else
+                                             "saxpy_hash_kernel / saxpy_light_kernel / saxpy_heavy_kernel"),
                              "kernel_ms": k_ms, "algorithmic_bytes": int(ab), "peak_source": peak_src,
                              "bytes_per_madd": ab / max(r["flops"], 1),
                              "step_algo_gbs": ab / (float(np.mean(dev_ms)) * 1e-3) / 1e9}}

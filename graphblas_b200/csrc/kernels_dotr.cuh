@@ -150,9 +150,11 @@ __device__ __forceinline__ uint32_t dotr_probe (const DotRProbe &q, const SmemTa
 }
 
 // The warps of the block pull batches of tasks of the item until its counter runs out.  A task is
-// walked in rows of 32 consecutive indices, DOTR_U rows per iteration with all their loads in flight.
+// walked in rows of 32 consecutive indices, DOTR_U_* rows per iteration with all their loads in flight.
 // s_cur (BITMAP, several parts): per task of the item, the row at which the previous part left it.
-constexpr int DOTR_U = 4 ;
+constexpr int DOTR_U_TABLE = 4 ;      // rows per iteration against the cuckoo tables (tasks: ~5 rows)
+constexpr int DOTR_U_BITMAP = 8 ;     // ... against a bitmap part (hub tasks: ~17 rows; one CTA per SM, so more
+                                      // loads per warp have to be in flight)
 
 template <class S, bool ISO, int MODE, class slot_t>
 __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, const void *table,
@@ -162,6 +164,7 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
     constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
     constexpr unsigned FULL = 0xffffffffu ;
     constexpr bool BITMAP = (MODE == DOTR_BITMAP) ;
+    constexpr int DOTR_U = BITMAP ? DOTR_U_BITMAP : DOTR_U_TABLE ;
     const int lane = threadIdx.x & 31 ;
     const SmemTab tab (table) ;
     DotRProbe q ;
@@ -229,11 +232,11 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
                     for (int u = 0 ; u < DOTR_U ; u++)
                         k [u] = (rem > 32 * u) ? (uint32_t) __ldg (rp + 32 * u) : NOKEY ;
                     // rows 0 and 1 are probed whatever they hold (a row past the end is all NOKEY: no
-                    // hit); rows 2 and 3 only if the task reaches them
+                    // hit); every later pair of rows only if the task reaches it
                     #pragma unroll
                     for (int u = 0 ; u < DOTR_U ; u++)
                     {
-                        if (u == 2 && p + 64 >= tl) break ;                     // warp-uniform
+                        if (u >= 2 && (u & 1) == 0 && p + 32 * u >= tl) break ;  // warp-uniform
                         uint32_t pos = 0 ;
                         const uint32_t hit = dotr_probe<ISO, MODE> (q, tab, tab2, k [u], pos) ;
                         if constexpr (ISO) cnt += hit ;
