@@ -77,6 +77,9 @@ _SIGS = {
     "gb200_host_free": (None, [_VP]),
     "gb200_host_trim": (None, []),
     "gb200_device_trim": (None, []),
+    "gb200_reduce_device": (_I, [_VP, _I, _VP]),
+    "gb200_reduce_host": (_I, [_VP, _I, _VP]),
+    "gb200_result_adopt": (_I, [_VP, _VP]),
     "gb200_select_device": (_I, [_VP, _VP, _I, _I64]),
     "gb200_select_host": (_I, [_VP, _VP, _I, _I64]),
     "gb200_peerbuf_create": (_I, [_VP, _I64, _I, _I, _I]),
@@ -285,6 +288,15 @@ def select_host(A: Matrix, op: str, k: int = 0, pinned: bool = False) -> Result:
     ca = A.c()
     _check(lib.gb200_select_host(C.byref(rh), C.byref(ca), SELECT_OPS[op], k), "gb200_select_host")
     return _fetch(rh, True, pinned)
+
+
+def reduce_host(A: Matrix, add: str):
+    """GrB_reduce of a matrix to a scalar over a built-in monoid, on the device (gb200_reduce_host)"""
+    out = np.zeros(1, dtype=TYPES[A.type][1])
+    ca = A.c()
+    _check(lib.gb200_reduce_host(C.byref(ca), OPCODES[add], out.ctypes.data_as(C.c_void_p)),
+           "gb200_reduce_host")
+    return out[0]
 
 
 class PeerBuf:

@@ -170,6 +170,7 @@ gb200_status ensure_iso (gb200_dmatrix_s *d) ;
 // engine_cache.cu: operand residency across calls of the host entry point
 gb200_status cache_acquire (gb200_dmatrix *out, const gb200_matrix *host, bool *cached) ;
 void cache_release (gb200_dmatrix d) ;
+bool cache_insert (gb200_dmatrix_s *d, const gb200_matrix *host) ;
 gb200_status cast_values (const void *in, int from, int to, int64_t n, DevBuf &out) ;
 gb200_status launch_mask_pos (const DMat &B, const DMat &M, int64_t *lpos) ;
 

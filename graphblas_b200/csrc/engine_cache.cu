@@ -44,7 +44,7 @@ struct OperandCache
     std::atomic<int64_t> count { 0 } ;                  // entries.size (), readable without the lock
     uint64_t tick = 0 ;
     size_t resident = 0 ;
-    int64_t hits = 0, misses = 0, invalidations = 0 ;
+    int64_t hits = 0, misses = 0, invalidations = 0, adopted = 0 ;
 } ;
 
 static OperandCache &cache () { static OperandCache *c = new OperandCache () ; return *c ; }   // never destroyed
@@ -187,6 +187,64 @@ gb200_status cache_acquire (gb200_dmatrix *out, const gb200_matrix *host, bool *
     }
     free_handles (to_free) ;
     return GB200_SUCCESS ;
+}
+
+// remember `d` (already resident, not pinned) as the copy of `host`; false: not kept (the caller frees d)
+bool cache_insert (gb200_dmatrix_s *d, const gb200_matrix *host)
+{
+    const int tsz = type_size (host->type_code) ;
+    const int64_t nnz = d->v.nnz ;
+    if (!cache_on () || host->vdim <= 1 || nnz < (1 << 16) || host->p == nullptr) return false ;
+    OperandCache &oc = cache () ;
+    const uint64_t fp = fingerprint (host, nnz, tsz) ;
+    const size_t bytes = (size_t) (host->nvec + 1) * 8 + (host->h ? (size_t) host->nvec * 8 : 0)
+        + (size_t) nnz * (4 + tsz) ;
+    size_t limit = 0 ;
+    {
+        const char *env = getenv ("GB200_OPERAND_CACHE_MB") ;
+        size_t free_b = 0, total_b = 0 ;
+        if (env != nullptr && atoll (env) > 0) limit = (size_t) atoll (env) << 20 ;
+        else if (cudaMemGetInfo (&free_b, &total_b) == cudaSuccess) limit = total_b / 4 ;
+        else { cudaGetLastError () ; limit = (size_t) 16 << 30 ; }
+    }
+    if (bytes > limit) return false ;
+    std::vector<gb200_dmatrix_s *> to_free ;
+    bool kept = false ;
+    {
+        std::lock_guard<std::mutex> lock (oc.mu) ;
+        // an older copy of the same arrays is stale by construction
+        for (size_t k = 0 ; k < oc.entries.size () ; )
+        {
+            const size_t before = oc.entries.size () ;
+            if (!oc.entries [k].dead && same_key (oc.entries [k].key, *host)) drop_locked (oc, k, to_free) ;
+            if (oc.entries.size () < before) continue ;
+            k++ ;
+        }
+        while (oc.resident + bytes > limit)
+        {
+            size_t victim = oc.entries.size () ;
+            for (size_t k = 0 ; k < oc.entries.size () ; k++)
+                if (oc.entries [k].pins == 0 && !oc.entries [k].dead
+                    && (victim == oc.entries.size () || oc.entries [k].tick < oc.entries [victim].tick)) victim = k ;
+            if (victim == oc.entries.size ()) break ;
+            drop_locked (oc, victim, to_free) ;
+        }
+        if (oc.resident + bytes <= limit)
+        {
+            CacheEntry e ;
+            e.key = *host ; e.nnz = nnz ; e.d = d ; e.fp = fp ; e.bytes = bytes ; e.tick = ++oc.tick ;
+            e.pins = 0 ; e.dead = false ;
+            oc.entries.push_back (e) ;
+            oc.count.store ((int64_t) oc.entries.size ()) ;
+            for (const void *q : { (const void *) host->p, (const void *) host->h, (const void *) host->i, host->x })
+                if (q != nullptr) oc.ptrs.insert (q) ;
+            oc.resident += bytes ;
+            oc.adopted++ ;
+            kept = true ;
+        }
+    }
+    free_handles (to_free) ;
+    return kept ;
 }
 
 void cache_release (gb200_dmatrix d)

@@ -932,7 +932,7 @@ enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_
     FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9,
     FAM_DOTG_ISO = 10, FAM_SPMV_OCC8 = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13,
     FAM_DOTR = 14, FAM_DOTR_ISO = 15, FAM_DOTR_BM = 16, FAM_DOTR_BM_ISO = 17, FAM_DOTR_WARP = 18,
-    FAM_DOTR_WARP_ISO = 19, FAM_SAXPY_HASH = 20 } ;
+    FAM_DOTR_WARP_ISO = 19, FAM_SAXPY_HASH = 20, FAM_REDUCE = 21 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -947,6 +947,8 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
         saxpy_light_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyArgs *) args) ;
     else if (family == FAM_SAXPY_HEAVY)
         saxpy_heavy_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const SaxpyArgs *) args) ;
+    else if (family == FAM_REDUCE)
+        reduce_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const ReduceArgs *) args) ;
     else if (family == FAM_SAXPY_HASH)
     {
         // per slot: accumulator + row + half a (row, slot) pair of the sort

@@ -426,4 +426,54 @@ saxpyv_long_kernel (SaxpyVArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// reduce to a scalar: s = (+) of all entries of A over a built-in monoid -- the device half of
+// GrB_reduce (reference Source/GB_reduce_to_scalar.c:107-270; SURVEY.md 8f row f3: the call that follows
+// the triangle-counting multiply, Demo/Source/tricount.c:177).  Grid-stride partial results, a fixed
+// shuffle / shared-memory tree per block, and the last block (ticket) combines the blocks' partials in
+// block order: the result is deterministic for a given grid.
+// ---------------------------------------------------------------------------------------------
+struct ReduceArgs
+{
+    const void *x ;             // n values of the monoid's type
+    int64_t n ;
+    void *partial ;             // acc_t per block
+    void *out ;                 // acc_t
+    unsigned int *ticket ;      // zeroed before launch
+} ;
+
+template <class S>
+__global__ void __launch_bounds__ (256)
+reduce_kernel (ReduceArgs a)
+{
+    using Z = typename S::Z ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
+    __shared__ acc_t s_part [8] ;
+    __shared__ bool s_last ;
+    const Z *__restrict__ x = (const Z *) a.x ;
+    acc_t *__restrict__ partial = (acc_t *) a.partial ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5 ;
+    acc_t acc = Mon::identity () ;
+    for (int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; t < a.n ;
+        t += (int64_t) gridDim.x * blockDim.x) acc = Mon::combine (acc, Mon::widen (x [t])) ;
+    for (int off = 16 ; off > 0 ; off >>= 1) acc = Mon::combine (acc, __shfl_down_sync (0xffffffffu, acc, off)) ;
+    if (lane == 0) s_part [warp] = acc ;
+    __syncthreads () ;
+    if (threadIdx.x == 0)
+    {
+        acc_t b = s_part [0] ;
+        for (int w = 1 ; w < (int) (blockDim.x >> 5) ; w++) b = Mon::combine (b, s_part [w]) ;
+        partial [blockIdx.x] = b ;
+        __threadfence () ;
+        s_last = (atomicAdd (a.ticket, 1u) == gridDim.x - 1) ;
+    }
+    __syncthreads () ;
+    if (s_last && threadIdx.x == 0)
+    {
+        __threadfence () ;
+        acc_t r = ((volatile acc_t *) partial) [0] ;
+        for (unsigned int b = 1 ; b < gridDim.x ; b++) r = Mon::combine (r, ((volatile acc_t *) partial) [b]) ;
+        *((acc_t *) a.out) = r ;
+    }
+}
+
 } // namespace gb200

@@ -23,6 +23,7 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "GB.h"
 #include "gb_b200.h"
 
@@ -133,6 +134,19 @@ static int as_abi (gb200_matrix *out, const GrB_Matrix A, int64_t **tmp_p)
     return (1) ;
 }
 
+/* The device copy of a freshly fetched T becomes the resident copy of T's host arrays (a no-op that
+ * frees it unless the residency cache is on): the call that follows on the same object -- GrB_reduce
+ * after the triangle-counting multiply, the next multiply of a k-truss loop -- then starts from HBM.
+ * GB_transplant moves T's arrays into the user's C without copying, so the key survives it. */
+static void adopt_result (gb200_result *r, const GrB_Matrix T, const gb200_result_info *f)
+{
+    gb200_matrix v ;
+    v.vlen = f->vlen ; v.vdim = f->vdim ; v.nvec = f->nvec ;
+    v.p = T->p ; v.h = f->is_hyper ? T->h : NULL ; v.i = T->i ; v.x = T->x ;
+    v.type_code = f->type_code ; v.reserved = 0 ;
+    gb200_result_adopt (r, &v) ;
+}
+
 __attribute__ ((visibility ("default")))
 GrB_Info GB_AxB_parallel            /* same contract as reference Source/GB.h:1522-1537 */
 (
@@ -239,13 +253,14 @@ GrB_Info GB_AxB_parallel            /* same contract as reference Source/GB.h:15
     }
     GrB_Matrix C = (*Chandle) ;
     st = gb200_result_fetch (r, C->p, f.is_hyper ? C->h : NULL, C->i, C->x) ;
-    gb200_result_free (&r) ;
     if (st != GB200_SUCCESS)
     {
+        gb200_result_free (&r) ;
         host_free (Chandle) ;
         (*Chandle) = NULL ;
         return ((st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC) ;
     }
+    adopt_result (&r, C, &f) ;          /* T stays resident if the host switched the residency cache on */
     if (f.is_hyper) C->nvec = f.nvec ;
     C->nvec_nonempty = f.nvec_nonempty ;
     C->magic = GB_MAGIC ;
@@ -472,11 +487,68 @@ GrB_Info GB_select (GrB_Matrix C, const bool C_replace, const GrB_Matrix M, cons
         (f.nnz > 0) ? f.nnz : 1, true, Context) ;
     if (info != GrB_SUCCESS) { gb200_result_free (&r) ; return (info) ; }
     st = gb200_result_fetch (r, T->p, f.is_hyper ? T->h : NULL, T->i, T->x) ;
-    gb200_result_free (&r) ;
-    if (st != GB200_SUCCESS) { host_free (&T) ; return ((st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC) ; }
+    if (st != GB200_SUCCESS)
+    {
+        gb200_result_free (&r) ;
+        host_free (&T) ;
+        return ((st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC) ;
+    }
+    adopt_result (&r, T, &f) ;
     if (f.is_hyper) T->nvec = f.nvec ;
     T->nvec_nonempty = f.nvec_nonempty ;
     T->magic = GB_MAGIC ;
     __atomic_fetch_add (&g_select_calls, 1, __ATOMIC_RELAXED) ;
     return (accum_mask (C, M, NULL, accum, &T, C_replace, Mask_comp, Context)) ;
+}
+
+/* -------------------------------------------------------------------------------------------------
+ * GrB_reduce of a matrix to a scalar: GB_reduce_to_scalar (reference
+ * Source/GB.h, body Source/GB_reduce_to_scalar.c:22-319) is interposed.  The reduction over the entries
+ * runs on the device when the monoid is built-in, A has the monoid's type (no typecast per entry) and no
+ * pending tuples or zombies; the scalar is then put into a 1-by-1 matrix of the same type and handed to
+ * the reference's OWN GB_reduce_to_scalar, which reduces that single entry (identity (+) s = s) and does
+ * everything else itself: the checks, the typecast into c, the accumulator.
+ * ------------------------------------------------------------------------------------------------- */
+static int64_t g_reduce_calls = 0 ;
+
+__attribute__ ((visibility ("default")))
+int64_t gb200_shim_reduce_calls (void) { return (g_reduce_calls) ; }
+
+__attribute__ ((visibility ("default")))
+GrB_Info GB_reduce_to_scalar (void *c, const GrB_Type ctype, const GrB_BinaryOp accum,
+    const GrB_Monoid reduce, const GrB_Matrix A, GB_Context Context)
+{
+    typedef GrB_Info (*fn_t) (void *, const GrB_Type, const GrB_BinaryOp, const GrB_Monoid,
+        const GrB_Matrix, GB_Context) ;
+    static fn_t orig = NULL ;
+    if (orig == NULL) orig = (fn_t) host_symbol ("GB_reduce_to_scalar", (void *) GB_reduce_to_scalar) ;
+    if (orig == NULL) return (GrB_PANIC) ;
+    if (g_enabled < 0) g_enabled = (getenv ("GB200_SHIM_DISABLE") != NULL) ? 0 : 1 ;
+    int mine = g_enabled && bind_host () && c != NULL && ctype != NULL && A != NULL && reduce != NULL
+        && A->magic == GB_MAGIC && reduce->magic == GB_MAGIC && reduce->op != NULL
+        && (accum == NULL || accum->magic == GB_MAGIC)
+        && reduce->op->opcode < GB_USER_C_opcode && A->type->code < GB_UCT_code
+        && A->type == reduce->op->ztype && !GB_PENDING (A) && !GB_ZOMBIES (A)
+        && GB_NNZ (A) >= 4096 ;         /* a short loop over host arrays beats a transfer */
+    if (!mine) return (orig (c, ctype, accum, reduce, A, Context)) ;
+    gb200_matrix am ;
+    int64_t *tp_a = NULL ;
+    char s [16] ;
+    gb200_status st = GB200_OUT_OF_MEMORY ;
+    if (as_abi (&am, A, &tp_a)) st = gb200_reduce_host (&am, reduce->op->opcode, s) ;
+    free (tp_a) ;
+    if (st != GB200_SUCCESS) return (orig (c, ctype, accum, reduce, A, Context)) ;
+    /* S = [s], 1-by-1, one entry */
+    GrB_Matrix S = NULL ;
+    GrB_Info info = host_create (&S, A->type, 1, 1, GB_Ap_malloc, true, GB_SAME_HYPER_AS (false),
+        A->hyper_ratio, 1, 1, true, Context) ;
+    if (info != GrB_SUCCESS) return (orig (c, ctype, accum, reduce, A, Context)) ;
+    S->p [0] = 0 ; S->p [1] = 1 ; S->i [0] = 0 ;
+    memcpy (S->x, s, A->type->size) ;
+    S->nvec_nonempty = 1 ;
+    S->magic = GB_MAGIC ;
+    info = orig (c, ctype, accum, reduce, S, Context) ;
+    host_free (&S) ;
+    __atomic_fetch_add (&g_reduce_calls, 1, __ATOMIC_RELAXED) ;
+    return (info) ;
 }

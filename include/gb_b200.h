@@ -194,6 +194,19 @@ typedef enum
 gb200_status gb200_select_device (gb200_result *out, gb200_dmatrix A, int select_op, int64_t k) ;
 gb200_status gb200_select_host   (gb200_result *out, const gb200_matrix *A, int select_op, int64_t k) ;
 
+/* ---- GrB_reduce of a matrix to a scalar over a built-in monoid (reference
+ * Source/GB_reduce_to_scalar.c:107-270).  add_opcode: a gb200_opcode naming the monoid (MIN MAX PLUS
+ * TIMES, or LOR LAND LXOR EQ for bool; boolean renames as in gb200_semiring_canonical).  *scalar
+ * receives one value of A's type; an empty A gives the monoid's identity.  Entries are taken as they
+ * are: the caller deals with zombies, typecasting and the accumulator (the shim does). */
+gb200_status gb200_reduce_device (gb200_dmatrix A, int add_opcode, void *scalar) ;
+gb200_status gb200_reduce_host   (const gb200_matrix *A, int add_opcode, void *scalar) ;
+
+/* Hand a result over to the residency cache: call after gb200_result_fetch, instead of
+ * gb200_result_free, with the host view (p, h, i, x as fetched) -- the device copy of T then serves the
+ * next call on those arrays.  Always consumes *r; frees it when the cache is off or T is not kept. */
+gb200_status gb200_result_adopt (gb200_result *r, const gb200_matrix *host) ;
+
 /* ---- operand residency across gb200_AxB_host calls (SURVEY.md 8b "Residency") ----------------
  * With the cache on, gb200_AxB_host keeps the device copy of every matrix operand (not of vectors)
  * keyed on the addresses and shape of its host arrays, so that the graph of a BFS / SSSP / k-truss

@@ -63,6 +63,19 @@ def main():
     B2 = B2.tocsr()[:, :]
     b = import_sp(G, B2, "FP64", "CSR")
     check(G, a, b, n, "after an operand was freed and replaced")
+    # T stays resident: GrB_reduce right after the multiply starts from HBM (no upload of T)
+    c = G.matrix_new("FP64", n, n)
+    G.use_gpu(True)
+    try:
+        G.mxm(c, None, None, "GxB_PLUS_TIMES_FP64", a, b, None)
+        s5 = G.shim_cache()
+        got = G.matrix_reduce(c, "FP64", "GxB_MAX_FP64_MONOID")
+        s6 = G.shim_cache()
+    finally:
+        G.use_gpu(False)
+    want = G.matrix_reduce(c, "FP64", "GxB_MAX_FP64_MONOID")
+    assert got == want, (got, want)
+    assert s6["hits"] - s5["hits"] == 1 and s6["misses"] == s5["misses"], (s5, s6)
     G.shim_cache(False)
     print("cache_check: ok", G.shim_cache())
 

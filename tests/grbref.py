@@ -340,6 +340,21 @@ class GraphBLAS:
                                            self.obj("GxB_" + op), A, C.byref(kk), desc),
                 "GxB_select")
 
+    def matrix_reduce(self, A, type_: str, monoid: str, accum=None, init=0):
+        """GrB_Matrix_reduce_<type> (&c, accum, monoid, A, NULL) with c = init: the scalar c"""
+        ct = {"FP64": C.c_double, "FP32": C.c_float, "INT64": C.c_int64, "INT32": C.c_int32,
+              "UINT64": C.c_uint64, "UINT32": C.c_uint32, "INT16": C.c_int16, "UINT16": C.c_uint16,
+              "INT8": C.c_int8, "UINT8": C.c_uint8, "BOOL": C.c_bool}[type_]
+        c = ct(init)
+        fn = getattr(self.lib, "GrB_Matrix_reduce_" + type_)
+        self.ok(fn(C.byref(c), self.obj(accum) if accum else None, self.obj(monoid), A, None),
+                "GrB_Matrix_reduce")
+        return c.value
+
+    def shim_reduce_calls(self) -> int:
+        self.shim.gb200_shim_reduce_calls.restype = C.c_int64
+        return self.shim.gb200_shim_reduce_calls()
+
     def shim_select_calls(self) -> int:
         self.shim.gb200_shim_select_calls.restype = C.c_int64
         return self.shim.gb200_shim_select_calls()

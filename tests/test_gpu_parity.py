@@ -391,3 +391,40 @@ def test_select_with_mask_and_accum(G):
             G.matrix_free(h)
     ok, why = compare(out[0], out[1], "MIN")
     assert ok, why
+
+# ---------------------------------------------------------------------------------------------
+# GrB_reduce of a matrix to a scalar (row f3): the interposed GB_reduce_to_scalar reduces on the device
+# and lets the reference finish (typecast into c, accumulator)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("type_,monoid,accum", [
+    ("INT64", "GxB_PLUS_INT64_MONOID", None), ("INT64", "GxB_MIN_INT64_MONOID", None),
+    ("INT32", "GxB_TIMES_INT32_MONOID", None), ("UINT8", "GxB_MAX_UINT8_MONOID", None),
+    ("INT16", "GxB_PLUS_INT16_MONOID", "GrB_PLUS_INT16"), ("BOOL", "GxB_LXOR_BOOL_MONOID", None),
+    ("BOOL", "GxB_LAND_BOOL_MONOID", None), ("FP64", "GxB_PLUS_FP64_MONOID", "GrB_MIN_FP64"),
+    ("FP64", "GxB_MAX_FP64_MONOID", None), ("FP32", "GxB_PLUS_FP32_MONOID", None)])
+@pytest.mark.parametrize("fmt", ["CSR", "HyperCSC"])
+def test_reduce_to_scalar(G, type_, monoid, accum, fmt):
+    from parity import import_sp
+    n = 400
+    A = gen.er(n, n, 40 * n, 61, NP[type_], lo=-3, hi=4)
+    if type_ == "INT32":
+        A.data[:] = np.where(A.data == 0, 1, A.data)    # a product that stays interesting
+        A.data[np.abs(A.data) > 1] = 1
+        A.data[::7] = -1
+    out = []
+    for gpu in (False, True):
+        a = import_sp(G, A, type_, fmt)
+        G.use_gpu(gpu)
+        before = G.shim_reduce_calls()
+        try:
+            out.append(G.matrix_reduce(a, type_, monoid, accum, init=3))
+        finally:
+            G.use_gpu(False)
+        if gpu and not REF_ONLY:
+            assert G.shim_reduce_calls() - before == 1, "the GPU reduction did not run"
+        G.matrix_free(a)
+    if type_ in ("FP32", "FP64") and "PLUS" in monoid:
+        eps = np.finfo(NP[type_]).eps
+        assert abs(out[0] - out[1]) <= 64 * eps * np.abs(A.data.astype(np.float64)).sum()
+    else:
+        assert out[0] == out[1]
