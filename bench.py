@@ -661,6 +661,29 @@ def measure(args, env, primary=True):
             else:
                 B, dB = mine, dmine
         calls = [(M, A, B, dM, dA, dB)]
+        # ---- C too large for HBM: column slabs (SURVEY.md 7 "hard parts", BASELINE cfg 5) -------------
+        # The flop count runs first (gb200_flopcount_device = GB_AxB_flopcount on the device): nnz (C) <=
+        # flops, so when flops x 16 B (pattern + accumulators + symbolic workspace) exceeds the budget,
+        # this rank's vectors of B are cut into flop-balanced slabs; every slab of C is computed, reduced
+        # to a checksum on the device (gb200_result_reduce) and discarded.
+        slabs = None
+        if args.workload in ("spgemm", "spgemm_rmat") and M is None:
+            cum_b, total_flops = gb.flopcount(None, dA, dB)
+            free_b, _ = torch.cuda.mem_get_info()
+            budget = int(args.slab_gb * 2 ** 30) if args.slab_gb > 0 else int(0.50 * free_b)
+            nslab = int(-(-total_flops * 16 // budget))
+            if nslab > 1:
+                sb = gb.partition_by_flops(cum_b, nslab)
+                parts = [slice_vectors(gb, B, int(sb[k]), int(sb[k + 1])) for k in range(nslab)
+                         if sb[k + 1] > sb[k]]
+                calls = [(None, A, bk, None, dA, gb.DMatrix(bk)) for bk in parts]
+                if dB is not dA:
+                    dB.free()
+                slabs = {"count": len(calls), "flops_total": int(total_flops),
+                         "budget_bytes": budget, "whole_B": B,
+                         "rule": "flops x 16 B per slab <= budget (nnz (C) <= flops); every slab of C "
+                                 "is reduced to a checksum on the device and discarded"}
+                w["config"]["slabs"] = len(calls)
 
     # ---- parity gate (one GPU): the reference on a bounded sample, the GPU's T on the same vectors
     parity = cpu = None
@@ -676,9 +699,21 @@ def measure(args, env, primary=True):
                    "sample": f"unavailable: {e}"}
     if do_cpu and G is not None:
         T = max(1, args.cpu_threads or (os.cpu_count() or 1))
-        first = gb.axb_device(calls[0][3], w["mask_comp"], calls[0][4], calls[0][5], w["semiring"],
-                              w["do_adotb"], fetch=(args.workload != "bfs"))
-        if args.workload == "bfs":
+        first = None
+        if slabs is None:
+            first = gb.axb_device(calls[0][3], w["mask_comp"], calls[0][4], calls[0][5], w["semiring"],
+                                  w["do_adotb"], fetch=(args.workload != "bfs"))
+        if slabs is not None:
+            # the whole T never exists: the GPU computes exactly the output vectors the reference's
+            # sample computes (one multiply with the other vectors of B emptied) and those are compared
+            madds_total = slabs["flops_total"]
+            stride = args.cpu_stride if args.cpu_stride > 0 else pick_stride(args.workload, madds_total, T)
+            sample = api_run(G, args.workload, w, stride, T, keep=True)
+            (sp_, si_, sx_), _ = _interleaved_parts(slabs["whole_B"], stride, 1)[0][0], None
+            Bs = gb.Matrix(B.vlen, B.vdim, sp_, si_, sx_, None, B.type)
+            gpu_T = gb.axb_host(None, False, A, Bs, w["semiring"], w["do_adotb"]).matrix
+            del Bs
+        elif args.workload == "bfs":
             madds_total = int(sum(int(np.diff(A.p)[qm.i].sum()) for qm, _ in levels))
             gpu_T = []
             for (vm, _, qm, dvm, da, dqm) in calls:
@@ -693,8 +728,9 @@ def measure(args, env, primary=True):
         else:
             madds_total = first.info["flops"]
             gpu_T = first.matrix
-        stride = args.cpu_stride if args.cpu_stride > 0 else pick_stride(args.workload, madds_total, T)
-        sample = api_run(G, args.workload, w, stride, T, keep=True)
+        if slabs is None:
+            stride = args.cpu_stride if args.cpu_stride > 0 else pick_stride(args.workload, madds_total, T)
+            sample = api_run(G, args.workload, w, stride, T, keep=True)
         parity = parity_check(args.workload, w, sample, gpu_T)
         cpu = {"value": sample["gflops"], "unit": "GFLOP/s", "cores": sample["threads"],
                "kind": "reference", "sample": sample["desc"], "seconds": sample["seconds"],
@@ -713,6 +749,8 @@ def measure(args, env, primary=True):
         if id(m) not in pinned:
             pinned[id(m)] = m.pinned()
         return pinned[id(m)]
+    if slabs is not None and world > 1:
+        args.no_e2e = True          # the slab-streamed multiply on N GPUs is measured on resident operands
     hcalls = [] if args.no_e2e else [(pin(m), pin(a), pin(b)) for (m, a, b, _, _, _) in calls]
     hfull = hcalls
 
@@ -739,6 +777,10 @@ def measure(args, env, primary=True):
                 gb.free_result(rh)
                 exchange["pb"].wait()
                 exchange["bytes"] = info["nnz"] * (np.dtype(gb.TYPES[w["semiring"].ztype][1]).itemsize + 1) * world
+            elif slabs is not None:
+                rh, info = gb.axb_device_keep(dm, w["mask_comp"], da, db, w["semiring"], w["do_adotb"])
+                out.setdefault("checksums", []).append(float(gb.result_reduce(rh, w["semiring"].ztype, "PLUS")))
+                gb.free_result(rh)                      # the slab of C is discarded
             else:
                 info = gb.axb_device(dm, w["mask_comp"], da, db, w["semiring"], w["do_adotb"],
                                      fetch=False).info
@@ -796,6 +838,18 @@ def measure(args, env, primary=True):
                 for dx in cache.values():
                     dx.free()
             return outs
+        if slabs is not None:
+            # A crosses PCIe once per step, every slab of B once; what comes back is the checksum of
+            # every slab of C (the slab itself is discarded on the device)
+            da = gb.DMatrix(hcalls[0][1])
+            for (m, a, b) in hcalls:
+                db_ = gb.DMatrix(b)
+                rh, info = gb.axb_device_keep(None, False, da, db_, w["semiring"], w["do_adotb"])
+                outs.append((float(gb.result_reduce(rh, w["semiring"].ztype, "PLUS")), info["nnz"]))
+                gb.free_result(rh)
+                db_.free()
+            da.free()
+            return outs
         if args.workload == "bfs":
             da = gb.DMatrix(hcalls[0][1])
             for (m, a, b) in hcalls:
@@ -817,8 +871,12 @@ def measure(args, env, primary=True):
     for _ in range(args.warmup):
         r = step_device()
     launches0 = gb.kernel_launches()
+    # NVML is initialised BEFORE the barrier: eight processes doing it at once serialise in the driver,
+    # and a rank that enters the timed region 30 ms late makes every other rank of a step with an
+    # exchange wait for it (measured: SSSP at N = 8, rank times 3.4 ... 0.4 ms per step)
+    sampler = ClockSampler(local_rank)
     barrier()
-    with ClockSampler(local_rank) as clk:
+    with sampler as clk:
         t0 = time.perf_counter()
         gb.timer_mark(0)
         dev_ms, ker_ms = [], []
@@ -863,13 +921,22 @@ def measure(args, env, primary=True):
         else:
             ab += algo_bytes(read, info["nvec"], info["nnz"], zsize)
 
+    if slabs is not None:
+        # every operand counted once for the whole multiply, whatever the number of slabs
+        Bw = slabs["whole_B"]
+        ab = 8 * (len(A.p) + len(Bw.p) + Bw.nvec + 1) + A.nnz * (8 + A.x.dtype.itemsize) \
+            + Bw.nnz * (8 + Bw.x.dtype.itemsize) + int(r["nnz"]) * (8 + zsize)
+        slabs["checksums"] = r.get("checksums")
+        slabs["checksum_total"] = float(np.sum(r.get("checksums", [0.0])))
+
     # ---- e2e: host buffers in, host T out, every step -----------------------------------------
     t_e2e, h2d, d2h, brk = None, 0, 0, None
     if not args.no_e2e:
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = 1 if slabs is not None else max(1, min(args.steps, 3))
         rh = None
         step_host()
-        step_host()
+        if slabs is None:
+            step_host()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -881,6 +948,10 @@ def measure(args, env, primary=True):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         t_e2e = te[0].item() / e2e_steps
         seen_once = set()
+        if slabs is not None:
+            h2d = nbytes(hcalls[0][1]) + sum(nbytes(b) for (_, _, b) in hcalls)
+            d2h = 8 * len(hcalls)
+            rh = []
         for (m, a, b), res in zip(hcalls, rh):
             mine_x = {"M": m, "A": a, "B": b}.get(sliced_name)
             for x in {id(x): x for x in (m, a, b) if x is not None}.values():
@@ -891,11 +962,11 @@ def measure(args, env, primary=True):
                 # N > 1: a rank uploads its own slice whole and 1/N of every replicated operand
                 h2d += nbytes(x) if (world == 1 or x is mine_x) else -(-nbytes(x) // world)
             d2h += nbytes(res.matrix)
-        del rh, res
+        rh = res = None
         # where one end-to-end step spends its time: the same step through the three entry points
         # gb200_AxB_host is made of (upload, multiply on resident operands, fetch), each synchronous
         brk = {"upload_ms": 0.0, "multiply_ms": 0.0, "fetch_ms": 0.0}
-        if args.workload != "bfs" and world == 1:
+        if args.workload != "bfs" and world == 1 and slabs is None:
             import ctypes as _C
             for (m, a, b) in hcalls:
                 t1 = time.perf_counter()
@@ -921,7 +992,10 @@ def measure(args, env, primary=True):
 
     # ---- t_api: the unmodified reference's GrB_mxm / mxv / vxm with the shim interposed --------
     api = None
-    if G is not None and world == 1 and rank == 0 and not args.no_api:
+    if slabs is not None:
+        api = {"ms": None, "skipped": "the unmodified GrB_mxm needs the whole T in host memory; the slab-"
+                                      "streamed multiply is a caller of the C ABI"}
+    elif G is not None and world == 1 and rank == 0 and not args.no_api:
         try:
             before = G.shim_stats()
             G.use_gpu(True)
@@ -989,6 +1063,7 @@ def measure(args, env, primary=True):
                                          f"{world} flop-balanced contiguous slices of "
                                          f"{ {'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors"),
                            "calibration_ms": w.get("calibration_ms"),
+                           "slabs": None if slabs is None else {k: v for k, v in slabs.items() if k != "whole_B"},
                            "exchange": ("in-library: peer stores of the rank's block of w into every GPU's "
                                         "dense copy over NVLink (gb200_peerbuf_publish / _wait), "
                                         f"{exchange['bytes']} B stored per rank per step") if exchange else
@@ -1098,6 +1173,8 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="only the headline workload")
     ap.add_argument("--secondary-scale", type=int, default=0, help="run the secondary workloads at "
                     "this scale instead of their own (quick checks)")
+    ap.add_argument("--slab-gb", type=float, default=0.0, help="unmasked saxpy: budget (GiB) of one slab "
+                    "of C; 0: 50 %% of the free HBM")
     ap.add_argument("--slice-of", type=int, default=0, help="one GPU: run the slice --slice-rank of a "
                     "K-way partition (what one rank of --gpus K computes), for profiling")
     ap.add_argument("--slice-rank", type=int, default=0)

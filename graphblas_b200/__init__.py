@@ -80,6 +80,7 @@ _SIGS = {
     "gb200_reduce_device": (_I, [_VP, _I, _VP]),
     "gb200_reduce_host": (_I, [_VP, _I, _VP]),
     "gb200_result_adopt": (_I, [_VP, _VP]),
+    "gb200_result_reduce": (_I, [_VP, _I, _VP]),
     "gb200_select_device": (_I, [_VP, _VP, _I, _I64]),
     "gb200_select_host": (_I, [_VP, _VP, _I, _I64]),
     "gb200_peerbuf_create": (_I, [_VP, _I64, _I, _I, _I]),
@@ -288,6 +289,13 @@ def select_host(A: Matrix, op: str, k: int = 0, pinned: bool = False) -> Result:
     ca = A.c()
     _check(lib.gb200_select_host(C.byref(rh), C.byref(ca), SELECT_OPS[op], k), "gb200_select_host")
     return _fetch(rh, True, pinned)
+
+
+def result_reduce(rh, type_: str, add: str = "PLUS"):
+    """monoid reduction of the values of a result that is still on the device (gb200_result_reduce)"""
+    out = np.zeros(1, dtype=TYPES[type_][1])
+    _check(lib.gb200_result_reduce(rh, OPCODES[add], out.ctypes.data_as(C.c_void_p)), "gb200_result_reduce")
+    return out[0]
 
 
 def reduce_host(A: Matrix, add: str):

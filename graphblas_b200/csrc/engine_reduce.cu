@@ -60,6 +60,19 @@ gb200_status gb200_reduce_device (gb200_dmatrix Ad, int add_opcode, void *scalar
     return GB200_SUCCESS ;
 }
 
+// the same over the values of a result that is still on the device: the checksum of a slab of C that is
+// computed, summed and discarded (SURVEY.md 7 "hard parts": C = A*A on RMAT 24 exceeds HBM)
+gb200_status gb200_result_reduce (gb200_result r, int add_opcode, void *scalar)
+{
+    if (r == NULL || scalar == NULL) return GB200_INVALID ;
+    gb200_dmatrix_s view ;                      // borrows the result's value array
+    view.v.x = r->x.ptr ; view.v.nnz = r->info.nnz ; view.v.type_code = r->info.type_code ;
+    view.v.p = nullptr ; view.v.h = nullptr ; view.v.i = nullptr ;
+    view.v.vlen = r->info.vlen ; view.v.vdim = r->info.vdim ; view.v.nvec = r->info.nvec ;
+    view.v.hyper = 0 ; view.v.iso = 0 ; view.is_hyper_flag = 0 ;
+    return gb200_reduce_device (&view, add_opcode, scalar) ;
+}
+
 gb200_status gb200_reduce_host (const gb200_matrix *A, int add_opcode, void *scalar)
 {
     if (A == NULL || scalar == NULL) return GB200_INVALID ;

@@ -201,6 +201,9 @@ gb200_status gb200_select_host   (gb200_result *out, const gb200_matrix *A, int 
  * are: the caller deals with zombies, typecasting and the accumulator (the shim does). */
 gb200_status gb200_reduce_device (gb200_dmatrix A, int add_opcode, void *scalar) ;
 gb200_status gb200_reduce_host   (const gb200_matrix *A, int add_opcode, void *scalar) ;
+/* the same over the values of a result still on the device: the checksum of a slab of C that is
+ * computed, summed and discarded when the whole C would not fit HBM */
+gb200_status gb200_result_reduce (gb200_result r, int add_opcode, void *scalar) ;
 
 /* Hand a result over to the residency cache: call after gb200_result_fetch, instead of
  * gb200_result_free, with the host view (p, h, i, x as fetched) -- the device copy of T then serves the
