@@ -12,19 +12,55 @@ GB200_DECL (uint16) GB200_DECL (int32)  GB200_DECL (uint32) GB200_DECL (int64)
 GB200_DECL (uint64) GB200_DECL (fp32)   GB200_DECL (fp64)
 #undef GB200_DECL
 
-bool launch_typed (int xy_code, int family, int z_code, int add, int mult, const void *args,
-    int grid, int block)
+static void next_kev (Ctx &c)
 {
-    LaunchCfg cfg ;
-    cfg.grid = grid ; cfg.block = block ; cfg.stream = ctx ().stream ;
-    Ctx &c = ctx () ;
     if (c.kev_used + 2 > (int) c.kev.size ())
     {
         cudaEvent_t e0, e1 ;
         cudaEventCreate (&e0) ; cudaEventCreate (&e1) ;
         c.kev.push_back (e0) ; c.kev.push_back (e1) ;
     }
-    cudaEventRecord (c.kev [c.kev_used], c.stream) ;
+}
+
+gb200_status group_begin ()
+{
+    Ctx &c = ctx () ;
+    next_kev (c) ;
+    GB200_CUDA (cudaEventRecord (c.kev [c.kev_used], c.stream)) ;
+    GB200_CUDA (cudaEventRecord (c.fork_ev, c.stream)) ;
+    for (int k = 0 ; k < Ctx::NSIDE ; k++) GB200_CUDA (cudaStreamWaitEvent (c.side [k], c.fork_ev, 0)) ;
+    c.group_stream = c.side [0] ;
+    return GB200_SUCCESS ;
+}
+
+void group_use (int k) { Ctx &c = ctx () ; c.group_stream = c.side [k % Ctx::NSIDE] ; }
+
+gb200_status group_end ()
+{
+    Ctx &c = ctx () ;
+    c.group_stream = nullptr ;
+    for (int k = 0 ; k < Ctx::NSIDE ; k++)
+    {
+        GB200_CUDA (cudaEventRecord (c.side_done [k], c.side [k])) ;
+        GB200_CUDA (cudaStreamWaitEvent (c.stream, c.side_done [k], 0)) ;
+    }
+    GB200_CUDA (cudaEventRecord (c.kev [c.kev_used + 1], c.stream)) ;
+    c.kev_used += 2 ;
+    return GB200_SUCCESS ;
+}
+
+bool launch_typed (int xy_code, int family, int z_code, int add, int mult, const void *args,
+    int grid, int block)
+{
+    LaunchCfg cfg ;
+    Ctx &c = ctx () ;
+    const bool grouped = (c.group_stream != nullptr) ;
+    cfg.grid = grid ; cfg.block = block ; cfg.stream = grouped ? c.group_stream : c.stream ;
+    if (!grouped)
+    {
+        next_kev (c) ;
+        cudaEventRecord (c.kev [c.kev_used], c.stream) ;
+    }
     bool ok = false ;
     switch (xy_code)
     {
@@ -41,8 +77,11 @@ bool launch_typed (int xy_code, int family, int z_code, int add, int mult, const
         case GB200_FP64   : ok = launch_fp64   (family, z_code, add, mult, args, cfg) ; break ;
         default : break ;
     }
-    cudaEventRecord (c.kev [c.kev_used + 1], c.stream) ;
-    c.kev_used += 2 ;
+    if (!grouped)
+    {
+        cudaEventRecord (c.kev [c.kev_used + 1], c.stream) ;
+        c.kev_used += 2 ;
+    }
     if (ok) count_launch () ;
     return ok ;
 }

@@ -53,6 +53,15 @@ struct Ctx
     // CUDA events bracketing every semiring-templated launch of the current multiply
     std::vector<cudaEvent_t> kev ;
     int kev_used = 0 ;
+    // Side streams for kernels of one multiply that are independent of each other (the owner classes
+    // and orientations of the masked dot): forked from `stream` and joined back into it, so that one
+    // kernel's tail is filled by the next one's blocks.  group_stream != nullptr: launch_typed launches
+    // there and leaves the timing events to group_begin / group_end.
+    static constexpr int NSIDE = 4 ;
+    cudaStream_t side [NSIDE] = { nullptr, nullptr, nullptr, nullptr } ;
+    cudaEvent_t side_done [NSIDE] = { nullptr, nullptr, nullptr, nullptr } ;
+    cudaEvent_t fork_ev = nullptr ;
+    cudaStream_t group_stream = nullptr ;
     int mask_policy = 0 ;               // of the current multiply: 0 reference rule, 1 keep, 2 drop
     int method_request = 0 ;            // of the current multiply: the GxB_AxB_METHOD asked for
 } ;
@@ -61,6 +70,13 @@ Ctx &ctx () ;
 gb200_status ensure_init () ;
 
 inline void count_launch (int n = 1) { ctx ().launches += n ; }
+
+// dispatch.cu: a group of independent semiring launches spread over the side streams; everything
+// queued on the main stream before group_begin is visible to them, everything after group_end sees
+// their results.  One pair of timing events brackets the group.
+gb200_status group_begin () ;
+void group_use (int k) ;            // the following launch_typed calls go to side stream k % NSIDE
+gb200_status group_end () ;
 
 // Device workspace comes from a caching allocator of the library's own (engine_util.cu): freed
 // blocks are kept by size class and handed out again.  Everything this library does runs on ONE

@@ -119,35 +119,10 @@ __device__ __forceinline__ VecInfo load_vec_info (const VecInfo *__restrict__ p)
 }
 
 // Both lists are sorted, so a match can only lie between the owner's first and last index: the walked
-// list is trimmed to that range before it becomes a task (at most two binary searches per pair).  For
-// C<L>=L*U' every pair keeps only the indices between j and i: 43 % fewer probes on RMAT graphs.
-// wfirst / wlast: the walked list's own first and last index (a side whose end is already inside the
-// range needs no search: the common case for one side).
-__device__ __forceinline__ void dotg_trim (const int32_t *__restrict__ Wi, int64_t w0, int64_t w1,
-    int32_t wfirst, int32_t wlast, int32_t omin, int32_t omax, int64_t &t0, int64_t &t1)
-{
-    int64_t l = w0, h = w1 ;
-    if (wfirst < omin)
-    {
-        while (l < h)
-        {
-            const int64_t mid = (l + h) >> 1 ;
-            if (__ldg (Wi + mid) < omin) l = mid + 1 ; else h = mid ;
-        }
-    }
-    t0 = l ;
-    h = w1 ;
-    if (l < w1 && wlast > omax)
-    {
-        while (l < h)
-        {
-            const int64_t mid = (l + h) >> 1 ;
-            if (__ldg (Wi + mid) <= omax) l = mid + 1 ; else h = mid ;
-        }
-        t1 = l ;
-    }
-    else t1 = w1 ;
-}
+// list is trimmed to that range before it becomes a task (at most two binary searches per pair, done by
+// dotg_classify_kernel).  For C<L>=L*U' every pair keeps only the indices between j and i: 43 % fewer
+// probes on RMAT graphs.  A side whose end is already inside the range needs no search (the common case
+// for one side).
 
 // ---- set-up of the masked dot: two passes over the mask entries -------------------------------------
 // A pair is DEAD (an empty side, or nothing left after the trim), SMALL (owner shorter than DOTG_SMALL:
@@ -160,63 +135,171 @@ enum { PK_DEAD = 0, PK_SMALL = 1, PK_BOWN = 2, PK_AOWN = 3 } ;
 // pass 1: classification with the trim.  w0 [e] = where the (trimmed) walk starts in the walked matrix,
 // lk [e] = its length | kind << 30, nt0 [e] = tasks of a B-owned pair (else 0), cntA [ka] += tasks of an
 // A-owned pair, slist = the small pairs (any order: they are independent).
-__global__ void dotg_classify_kernel (DMat A, DMat B, DMat M, const VecInfo *__restrict__ infoA,
+// The pass is a chain of dependent random reads per pair (row index -> vector record -> up to two binary
+// searches in the walked list) and was bound by their latency (2.95 ms for 64 M pairs at full
+// occupancy), so a thread carries CLS_U pairs through the chain together: every step issues the loads
+// of all of them before any is used, and the binary searches advance in lockstep.
+// trim: 0 walk whole lists; 1 always search; 2 (default) no search in a walked list of at most 32 indices:
+// it is one row of the walk with or without the trim, and the two searches cost more random DRAM sectors
+// than the rest of the pass -- such a pair is only dropped when the two index ranges do not meet.
+template <int CLS_U>
+__global__ void __launch_bounds__ (256)
+dotg_classify_kernel (DMat A, DMat B, DMat M, const VecInfo *__restrict__ infoA,
     const VecInfo *__restrict__ infoB, const int32_t *__restrict__ mvec,
     int64_t mnz, int trim, int64_t *__restrict__ w0out, int32_t *__restrict__ lk, int32_t *__restrict__ nt0,
     unsigned long long *__restrict__ cntA, int32_t *__restrict__ slist, unsigned int *__restrict__ nsmall)
 {
     const int lane = threadIdx.x & 31 ;
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x ;
-    const int64_t niter = (mnz + stride - 1) / stride ;
-    int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ;
-    for (int64_t itn = 0 ; itn < niter ; itn++, e += stride)
+    const int64_t tile = (int64_t) blockDim.x * CLS_U ;     // consecutive pairs of one block iteration
+    const int64_t ntiles = (mnz + tile - 1) / tile ;
+    for (int64_t tl = blockIdx.x ; tl < ntiles ; tl += gridDim.x)
     {
-        int kind = PK_DEAD ;
-        int32_t len = 0, ntk = 0 ;
-        int64_t wstart = 0 ;
-        if (e < mnz)
+        int64_t e [CLS_U], ka [CLS_U], kb [CLS_U] ;
+        int32_t mi [CLS_U], mv [CLS_U] ;
+        #pragma unroll
+        for (int u = 0 ; u < CLS_U ; u++)
         {
-            const int64_t ka = dm_vecpos (A, M.i [e]) ;
-            const int64_t kb = dm_vecpos (B, dm_vecname (M, mvec [e])) ;
-            if (ka >= 0 && kb >= 0)
+            e [u] = tl * tile + (int64_t) u * blockDim.x + threadIdx.x ;
+            const bool in = (e [u] < mnz) ;
+            mi [u] = in ? __ldg (M.i + e [u]) : 0 ;
+            mv [u] = in ? __ldg (mvec + e [u]) : 0 ;
+        }
+        #pragma unroll
+        for (int u = 0 ; u < CLS_U ; u++)
+        {
+            ka [u] = -1 ; kb [u] = -1 ;
+            if (e [u] < mnz)
             {
-                const VecInfo va = load_vec_info (infoA + ka), vb = load_vec_info (infoB + kb) ;
-                const int64_t ainz = va.len, bjnz = vb.len ;
-                if (ainz > 0 && bjnz > 0)
+                ka [u] = dm_vecpos (A, mi [u]) ;
+                kb [u] = dm_vecpos (B, dm_vecname (M, mv [u])) ;
+            }
+        }
+        VecInfo va [CLS_U], vb [CLS_U] ;
+        #pragma unroll
+        for (int u = 0 ; u < CLS_U ; u++)
+        {
+            va [u].p0 = 0 ; va [u].len = 0 ; va [u].first = 0 ; va [u].last = 0 ; vb [u] = va [u] ;
+            if (ka [u] >= 0 && kb [u] >= 0)
+            {
+                va [u] = load_vec_info (infoA + ka [u]) ;
+                vb [u] = load_vec_info (infoB + kb [u]) ;
+            }
+        }
+        int kind [CLS_U] ;
+        bool walkA [CLS_U] ;
+        // the walked list [l, h) and what is searched in it: first index >= omin, then first index > omax
+        const int32_t *Wi [CLS_U] ;
+        int64_t l [CLS_U], h [CLS_U], w1 [CLS_U] ;
+        int32_t omin [CLS_U], omax [CLS_U], wlast [CLS_U] ;
+        bool live [CLS_U], srch [CLS_U] ;
+        #pragma unroll
+        for (int u = 0 ; u < CLS_U ; u++)
+        {
+            kind [u] = PK_DEAD ; walkA [u] = false ; live [u] = false ; srch [u] = false ;
+            Wi [u] = A.i ; l [u] = 0 ; h [u] = 0 ; w1 [u] = 0 ; omin [u] = 0 ; omax [u] = 0 ; wlast [u] = 0 ;
+            const int64_t ainz = va [u].len, bjnz = vb [u].len ;
+            if (ainz > 0 && bjnz > 0)
+            {
+                walkA [u] = dot_walkA (ainz, bjnz, A.vlen) ;
+                const int64_t olen = walkA [u] ? bjnz : ainz ;
+                if (olen < DOTG_SMALL) kind [u] = PK_SMALL ;
+                else
                 {
-                    const bool walkA = dot_walkA (ainz, bjnz, A.vlen) ;
-                    const int64_t olen = walkA ? bjnz : ainz ;
-                    if (olen < DOTG_SMALL) kind = PK_SMALL ;
-                    else
-                    {
-                        const VecInfo &vw = walkA ? va : vb ;       // walked
-                        const VecInfo &vo = walkA ? vb : va ;       // owner
-                        int64_t t0 = vw.p0, t1 = vw.p0 + vw.len ;
-                        if (trim) dotg_trim (walkA ? A.i : B.i, vw.p0, vw.p0 + vw.len, vw.first, vw.last,
-                            vo.first, vo.last, t0, t1) ;
-                        len = (int32_t) (t1 - t0) ;
-                        wstart = t0 ;
-                        if (len > 0)
-                        {
-                            ntk = (len + DOTG_SEG - 1) / DOTG_SEG ;
-                            if (walkA) kind = PK_BOWN ;
-                            else { kind = PK_AOWN ; atomicAdd (cntA + ka, (unsigned long long) ntk) ; }
-                        }
-                    }
+                    const VecInfo &vw = walkA [u] ? va [u] : vb [u] ;       // walked
+                    const VecInfo &vo = walkA [u] ? vb [u] : va [u] ;       // owner
+                    live [u] = true ;
+                    Wi [u] = walkA [u] ? A.i : B.i ;
+                    l [u] = vw.p0 ; w1 [u] = vw.p0 + vw.len ;
+                    omin [u] = vo.first ; omax [u] = vo.last ; wlast [u] = vw.last ;
+                    srch [u] = (trim == 1) || (trim == 2 && vw.len > 32) ;
+                    if (trim && (vw.last < vo.first || vw.first > vo.last)) { w1 [u] = l [u] ; srch [u] = false ; }
+                    // a side whose end is already inside the owner's range needs no search
+                    h [u] = (srch [u] && vw.first < vo.first) ? w1 [u] : l [u] ;
                 }
             }
-            w0out [e] = wstart ;
-            lk [e] = len | (kind << 30) ;
-            nt0 [e] = (kind == PK_BOWN) ? ntk : 0 ;
         }
-        // the small pairs of the warp are appended with one atomic
-        const unsigned sm = __ballot_sync (0xffffffffu, kind == PK_SMALL) ;
-        if (sm)
+        // lower ends, in lockstep
+        while (true)
         {
-            unsigned int base = 0 ;
-            if (lane == 0) base = atomicAdd (nsmall, (unsigned int) __popc (sm)) ;
-            base = __shfl_sync (0xffffffffu, base, 0) ;
-            if (kind == PK_SMALL) slist [base + __popc (sm & ((1u << lane) - 1u))] = (int32_t) e ;
+            bool any = false ;
+            int64_t mid [CLS_U] ; int32_t v [CLS_U] ;
+            #pragma unroll
+            for (int u = 0 ; u < CLS_U ; u++)
+            {
+                mid [u] = (l [u] + h [u]) >> 1 ;
+                v [u] = (l [u] < h [u]) ? __ldg (Wi [u] + mid [u]) : 0 ;
+            }
+            #pragma unroll
+            for (int u = 0 ; u < CLS_U ; u++)
+                if (l [u] < h [u])
+                {
+                    if (v [u] < omin [u]) l [u] = mid [u] + 1 ; else h [u] = mid [u] ;
+                    any = any || (l [u] < h [u]) ;
+                }
+            if (!any) break ;
+        }
+        int64_t t0 [CLS_U] ;
+        #pragma unroll
+        for (int u = 0 ; u < CLS_U ; u++)
+        {
+            t0 [u] = l [u] ;
+            h [u] = (srch [u] && l [u] < w1 [u] && wlast [u] > omax [u]) ? w1 [u] : l [u] ;
+        }
+        // upper ends
+        bool searched [CLS_U] ;
+        #pragma unroll
+        for (int u = 0 ; u < CLS_U ; u++) searched [u] = (l [u] < h [u]) ;
+        while (true)
+        {
+            bool any = false ;
+            int64_t mid [CLS_U] ; int32_t v [CLS_U] ;
+            #pragma unroll
+            for (int u = 0 ; u < CLS_U ; u++)
+            {
+                mid [u] = (l [u] + h [u]) >> 1 ;
+                v [u] = (l [u] < h [u]) ? __ldg (Wi [u] + mid [u]) : 0 ;
+            }
+            #pragma unroll
+            for (int u = 0 ; u < CLS_U ; u++)
+                if (l [u] < h [u])
+                {
+                    if (v [u] <= omax [u]) l [u] = mid [u] + 1 ; else h [u] = mid [u] ;
+                    any = any || (l [u] < h [u]) ;
+                }
+            if (!any) break ;
+        }
+        #pragma unroll
+        for (int u = 0 ; u < CLS_U ; u++)
+        {
+            int32_t len = 0, ntk = 0 ;
+            int64_t wstart = 0 ;
+            if (live [u])
+            {
+                const int64_t t1 = searched [u] ? l [u] : w1 [u] ;
+                len = (int32_t) (t1 - t0 [u]) ;
+                wstart = t0 [u] ;
+                if (len > 0)
+                {
+                    ntk = (len + DOTG_SEG - 1) / DOTG_SEG ;
+                    if (walkA [u]) kind [u] = PK_BOWN ;
+                    else { kind [u] = PK_AOWN ; atomicAdd (cntA + ka [u], (unsigned long long) ntk) ; }
+                }
+            }
+            if (e [u] < mnz)
+            {
+                w0out [e [u]] = wstart ;
+                lk [e [u]] = len | (kind [u] << 30) ;
+                nt0 [e [u]] = (kind [u] == PK_BOWN) ? ntk : 0 ;
+            }
+            // the small pairs of the warp are appended with one atomic
+            const unsigned sm = __ballot_sync (0xffffffffu, kind [u] == PK_SMALL) ;
+            if (sm)
+            {
+                unsigned int base = 0 ;
+                if (lane == 0) base = atomicAdd (nsmall, (unsigned int) __popc (sm)) ;
+                base = __shfl_sync (0xffffffffu, base, 0) ;
+                if (kind [u] == PK_SMALL) slist [base + __popc (sm & ((1u << lane) - 1u))] = (int32_t) e [u] ;
+            }
         }
     }
 }
@@ -386,7 +469,11 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             const int64_t cap = dotg_cap (iso) ;
             // 0: walk the whole list of every pair (for A/B measurements)
             const char *trim_env = getenv ("GB200_DOTG_TRIM") ;
-            const int trim = (trim_env != nullptr && atoi (trim_env) == 0) ? 0 : 1 ;
+            int trim = (trim_env != nullptr) ? atoi (trim_env) : 2 ;
+            if (trim < 0 || trim > 2) trim = 2 ;
+            // pairs a thread of the classification carries together (1 or 4; for A/B runs)
+            const char *clsu_env = getenv ("GB200_CLS_U") ;
+            const int cls_u = (clsu_env != nullptr && atoi (clsu_env) == 1) ? 1 : 4 ;
             // 0: warp per task / lane per task (dotg_kernel) instead of the row walk (kernels_dotr.cuh)
             const char *flat_env = getenv ("GB200_DOTR") ;
             const bool flat = !(flat_env != nullptr && atoi (flat_env) == 0) ;
@@ -414,7 +501,13 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 vec_info_kernel <<<grid_cap ((B.nvec + 255) / 256, 16), 256, 0, c.stream>>> (B, infoB.as<VecInfo> ()) ;
             }
             count_launch (sameAB ? 1 : 2) ;
-            dotg_classify_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, B, Mv,
+            if (cls_u == 1)
+                dotg_classify_kernel<1> <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, B, Mv,
+                infoA.as<VecInfo> (), sameAB ? infoA.as<VecInfo> () : infoB.as<VecInfo> (),
+                mvec.as<int32_t> (), mnz, trim, w0buf.as<int64_t> (), lk.as<int32_t> (), nt0.as<int32_t> (),
+                cntA.as<unsigned long long> (), slist.as<int32_t> (), nsmall.as<unsigned int> ()) ;
+            else
+                dotg_classify_kernel<4> <<<grid_cap ((mnz + 1023) / 1024, 16), 256, 0, c.stream>>> (A, B, Mv,
                 infoA.as<VecInfo> (), sameAB ? infoA.as<VecInfo> () : infoB.as<VecInfo> (),
                 mvec.as<int32_t> (), mnz, trim, w0buf.as<int64_t> (), lk.as<int32_t> (), nt0.as<int32_t> (),
                 cntA.as<unsigned long long> (), slist.as<int32_t> (), nsmall.as<unsigned int> ()) ;
@@ -435,26 +528,24 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             dot_cum_list_kernel <<<grid_cap ((Mv.nvec + 256) / 256, 8), 256, 0, c.stream>>> (Mv.p,
                 toff0.as<int64_t> (), Mv.nvec, off0.as<int64_t> ()) ;
             count_launch (2) ;
-            if (ns > 0)
-            {
-                // short owner, shorter walk: a group of 4 lanes per pair, no table
-                da.mode = DOT_MASK ; da.mvec = mvec.as<int32_t> () ; da.plist = slist.as<int32_t> () ;
-                da.npairs = ns ; da.vals = vals.ptr ; da.flags = flags.as<uint8_t> () ; da.G = 4 ;
-                if (!launch_typed (s.xy_code, FAM_DOT, s.z_code, s.add_opcode, s.mult_opcode, &da,
-                    grid_cap ((ns + 63) / 64, 16), 256))
-                { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
-            }
             DotGArgs ga ;
             memset (&ga, 0, sizeof (ga)) ;
+            // one work-item counter per launch (two orientations x four classes), then the failure flag
             DevBuf next_item ;
-            GB200_TRY (next_item.alloc (16)) ;
-            GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 16, c.stream)) ;
-            ga.next_item = next_item.as<unsigned long long> () ;
-            ga.failed = (unsigned int *) (next_item.as<unsigned long long> () + 1) ;
+            GB200_TRY (next_item.alloc (16 * sizeof (unsigned long long))) ;
+            GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 16 * sizeof (unsigned long long), c.stream)) ;
+            ga.failed = (unsigned int *) (next_item.as<unsigned long long> () + 8) ;
             ga.A = A ; ga.B = B ; ga.M = Mv ;
             ga.vals = vals.ptr ; ga.flags = flags.as<uint8_t> () ;
             ga.nmatch = nmatch.as<unsigned long long> () ;
             ga.mult_op = s.mult_opcode ; ga.flip = s.flipxy ;
+            // ---- the owners' task runs of both orientations are cut into work items, one list per
+            // owner class (hubs get big items) -----------------------------------------------------
+            DotgClasses K [2] ;
+            DevBuf itembuf [2][4], icount ;
+            DotgItemLists IL [2] ;
+            GB200_TRY (icount.alloc (8 * sizeof (unsigned long long))) ;
+            GB200_CUDA (cudaMemsetAsync (icount.ptr, 0, 8 * sizeof (unsigned long long), c.stream)) ;
             for (int orient = 0 ; orient < 2 ; orient++)
             {
                 const int64_t ntasks = orient ? nt_a : nt_b ;   // tasks of this orientation
@@ -462,8 +553,6 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 // task range of owner v: [otoff [v], otoff [v+1]) of this orientation's tasks
                 const int64_t *otoff = orient ? offA.as<int64_t> () : off0.as<int64_t> () ;
                 const int64_t nown = orient ? anvec : Mv.nvec ;
-                ga.tasks = tasks.as<DotTask> () + (orient ? nt_b : 0) ; ga.orient = orient ;
-                // the owners' task ranges are cut into work items: hub owners first (the big items)
                 // Tasks per hub item: big items amortise the owner's table, but there must also be
                 // several items per resident block or a few big hubs serialise the launch (one rank of
                 // an 8-GPU run holds an eighth of the hubs)
@@ -476,65 +565,95 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                 int64_t reg_chunk = DOTG_CHUNK ;
                 if (getenv ("GB200_DOTG_CHUNK")) reg_chunk = atoll (getenv ("GB200_DOTG_CHUNK")) ;
                 if (reg_chunk < 1) reg_chunk = DOTG_CHUNK ;
-                DotgClasses K ;
-                K.cap = cap ; K.bm_bits = dotr_bm_bits (iso) ; K.flat = flat ? 1 : 0 ;
+                DotgClasses &Ko = K [orient] ;
+                Ko.cap = cap ; Ko.bm_bits = dotr_bm_bits (iso) ; Ko.flat = flat ? 1 : 0 ;
                 // 0: no warp items (tiny owners go to the block kernel), for A/B runs
                 const char *tiny_env = getenv ("GB200_DOTR_TINY") ;
-                K.tiny = (flat && !(tiny_env != nullptr && atoi (tiny_env) == 0)) ? dotr_tiny_cap (iso) : 0 ;
+                Ko.tiny = (flat && !(tiny_env != nullptr && atoi (tiny_env) == 0)) ? dotr_tiny_cap (iso) : 0 ;
                 // smaller bitmap parts (a multiple of 32 indices): lets a test reach several parts
                 if (getenv ("GB200_DOTR_BM_BITS"))
                 {
                     const int64_t bb = (atoll (getenv ("GB200_DOTR_BM_BITS")) / 32) * 32 ;
-                    if (bb >= 32 && bb <= K.bm_bits) K.bm_bits = bb ;
+                    if (bb >= 32 && bb <= Ko.bm_bits) Ko.bm_bits = bb ;
                 }
-                ga.bm_bits = K.bm_bits ;
-                K.chunk [0] = reg_chunk ; K.chunk [1] = hub_chunk ; K.chunk [2] = hub_chunk ;
-                K.chunk [3] = 256 ;
-                // one pass builds the item lists of all four classes; capacities: a class cannot hold more
-                // items than ntasks / chunk + one per owner that has tasks
-                DevBuf itembuf [4], icount ;
-                DotgItemLists IL ;
+                Ko.chunk [0] = reg_chunk ; Ko.chunk [1] = hub_chunk ; Ko.chunk [2] = hub_chunk ;
+                Ko.chunk [3] = 256 ;
+                // capacities: a class cannot hold more items than ntasks / chunk + one per owner with tasks
                 const int64_t owners_max = (nown < ntasks) ? nown : ntasks ;
                 for (int q = 0 ; q < 4 ; q++)
                 {
-                    GB200_TRY (itembuf [q].alloc ((size_t) (ntasks / K.chunk [q] + owners_max + 1) * sizeof (DotItem))) ;
-                    IL.items [q] = itembuf [q].as<DotItem> () ;
+                    GB200_TRY (itembuf [orient][q].alloc ((size_t) (ntasks / Ko.chunk [q] + owners_max + 1) * sizeof (DotItem))) ;
+                    IL [orient].items [q] = itembuf [orient][q].as<DotItem> () ;
                 }
-                GB200_TRY (icount.alloc (4 * sizeof (unsigned long long))) ;
-                GB200_CUDA (cudaMemsetAsync (icount.ptr, 0, 4 * sizeof (unsigned long long), c.stream)) ;
-                IL.count = icount.as<unsigned long long> () ;
+                IL [orient].count = icount.as<unsigned long long> () + 4 * orient ;
                 dotg_items_all_kernel <<<grid_cap ((nown + 255) / 256, 8), 256, 0, c.stream>>> (
-                    orient ? A : B, Mv, orient, K, otoff, nown, IL) ;
+                    orient ? A : B, Mv, orient, Ko, otoff, nown, IL [orient]) ;
                 count_launch () ;
-                int64_t nitems_of [4] ;
-                GB200_CUDA (cudaMemcpyAsync (c.pinned, icount.ptr, 4 * sizeof (unsigned long long),
-                    cudaMemcpyDeviceToHost, c.stream)) ;
-                GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
-                for (int q = 0 ; q < 4 ; q++) nitems_of [q] = (int64_t) ((unsigned long long *) c.pinned) [q] ;
-                // hubs first (the big items), tiny owners last (they fill the tail of the machine)
-                static const int class_order [4] = { 2, 1, 0, 3 } ;
-                for (int co = 0 ; co < 4 ; co++)
+            }
+            int64_t nitems_of [2][4] ;
+            GB200_CUDA (cudaMemcpyAsync (c.pinned, icount.ptr, 8 * sizeof (unsigned long long),
+                cudaMemcpyDeviceToHost, c.stream)) ;
+            GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
+            for (int q = 0 ; q < 8 ; q++) nitems_of [q >> 2][q & 3] = (int64_t) ((unsigned long long *) c.pinned) [q] ;
+            // ---- the semiring kernels: independent of each other (disjoint pairs; pieces of a split
+            // pair meet through the monoid's atomic), so they go to the side streams and one kernel's
+            // tail is filled by the next one's blocks.  Hubs first (the big items), tiny owners and the
+            // table-free small pairs last.  GB200_DOT_STREAMS=0: one after another on the main stream.
+            const char *str_env = getenv ("GB200_DOT_STREAMS") ;
+            const bool streams = !(str_env != nullptr && atoi (str_env) == 0) ;
+            // L2 prefetch distance of the row-walk kernels, per owner class (hub, regular, tiny), in tasks
+            auto pf_of = [] (const char *name, int dflt)
+            {
+                const char *e = getenv (name) ;
+                int v = (e != nullptr) ? atoi (e) : dflt ;
+                return (v < 0) ? 0 : ((v > 8) ? 8 : v) ;
+            } ;
+            const int pf_hub = pf_of ("GB200_DOTR_PF_HUB", 2), pf_reg = pf_of ("GB200_DOTR_PF_REG", 2),
+                pf_tiny = pf_of ("GB200_DOTR_PF_TINY", 2) ;
+            if (streams) GB200_TRY (group_begin ()) ;
+            int nlaunch = 0 ;
+            static const int class_order [4] = { 2, 1, 0, 3 } ;
+            for (int co = 0 ; co < 4 ; co++)
+            {
+                const int cls = class_order [co] ;
+                for (int orient = 0 ; orient < 2 ; orient++)
                 {
-                    const int cls = class_order [co] ;
-                    const int64_t nitems = nitems_of [cls] ;
+                    const int64_t ntasks = orient ? nt_a : nt_b ;
+                    const int64_t nitems = (ntasks > 0) ? nitems_of [orient][cls] : 0 ;
                     if (nitems == 0) continue ;
-                    GB200_CUDA (cudaMemsetAsync (next_item.ptr, 0, 8, c.stream)) ;
-                    ga.items = IL.items [cls] ; ga.nitems = nitems ;
+                    ga.tasks = tasks.as<DotTask> () + (orient ? nt_b : 0) ; ga.orient = orient ;
+                    ga.bm_bits = K [orient].bm_bits ;
+                    ga.next_item = next_item.as<unsigned long long> () + 4 * orient + cls ;
+                    ga.items = IL [orient].items [cls] ; ga.nitems = nitems ;
+                    ga.prefetch = (cls == 1) ? pf_hub : ((cls == 3) ? pf_tiny : pf_reg) ;
                     int fam, per_sm, threads ;
                     if (cls == 2) { fam = iso ? FAM_DOTG_HUB_ISO : FAM_DOTG_HUB ; per_sm = 2 ; threads = DOTG_THREADS ; }
                     else if (cls == 1) { fam = iso ? FAM_DOTR_BM_ISO : FAM_DOTR_BM ; per_sm = 1 ; threads = DOTR_BM_THREADS ; }
                     else if (cls == 3) { fam = iso ? FAM_DOTR_WARP_ISO : FAM_DOTR_WARP ; per_sm = iso ? 3 : 2 ; threads = DOTR_THREADS ; }
                     else if (flat) { fam = iso ? FAM_DOTR_ISO : FAM_DOTR ; per_sm = iso ? 3 : 2 ; threads = DOTR_THREADS ; }
                     else { fam = iso ? FAM_DOTG_ISO : FAM_DOTG ; per_sm = iso ? 3 : 2 ; threads = DOTG_THREADS ; }
+                    if (streams) group_use (nlaunch++) ;
                     if (!launch_typed (s.xy_code, fam, s.z_code, s.add_opcode, s.mult_opcode, &ga,
                         grid_cap (nitems, per_sm), threads))
-                    { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+                    { if (streams) group_end () ; set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
                 }
-                // the item lists are released in stream order, after the kernels that read them
             }
+            if (ns > 0)
+            {
+                // short owner, shorter walk: a group of 4 lanes per pair, no table
+                da.mode = DOT_MASK ; da.mvec = mvec.as<int32_t> () ; da.plist = slist.as<int32_t> () ;
+                da.npairs = ns ; da.vals = vals.ptr ; da.flags = flags.as<uint8_t> () ; da.G = 4 ;
+                if (streams) group_use (nlaunch++) ;
+                if (!launch_typed (s.xy_code, FAM_DOT, s.z_code, s.add_opcode, s.mult_opcode, &da,
+                    grid_cap ((ns + 63) / 64, 16), 256))
+                { if (streams) group_end () ; set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+            }
+            // joined before any buffer of this multiply is released (the block cache is stream-ordered
+            // on the main stream)
+            if (streams) GB200_TRY (group_end ()) ;
             // an owner whose cuckoo tables could not be built (never seen): every pair again, table-free
             int64_t failed = 0 ;
-            GB200_TRY (read_i64 (next_item.as<int64_t> () + 1, &failed)) ;
+            GB200_TRY (read_i64 (next_item.as<int64_t> () + 8, &failed)) ;
             if (failed != 0)
             {
                 GB200_CUDA (cudaMemsetAsync (flags.ptr, 0, flags.bytes, c.stream)) ;

@@ -57,6 +57,12 @@ static gb200_status do_init (int device)
     GB200_CUDA (cudaStreamCreateWithFlags (&c.stream, cudaStreamNonBlocking)) ;
     GB200_CUDA (cudaEventCreate (&c.ev0)) ;
     GB200_CUDA (cudaEventCreate (&c.ev1)) ;
+    GB200_CUDA (cudaEventCreateWithFlags (&c.fork_ev, cudaEventDisableTiming)) ;
+    for (int k = 0 ; k < Ctx::NSIDE ; k++)
+    {
+        GB200_CUDA (cudaStreamCreateWithFlags (&c.side [k], cudaStreamNonBlocking)) ;
+        GB200_CUDA (cudaEventCreateWithFlags (&c.side_done [k], cudaEventDisableTiming)) ;
+    }
     c.pinned_bytes = 1 << 16 ;
     GB200_CUDA (cudaMallocHost (&c.pinned, c.pinned_bytes)) ;
     c.ready = true ;
@@ -659,6 +665,15 @@ gb200_status gb200_finalize (void)
     dev_pool_trim () ;
     cudaFreeHost (c.pinned) ; c.pinned = nullptr ;
     cudaEventDestroy (c.ev0) ; cudaEventDestroy (c.ev1) ;
+    cudaEventDestroy (c.fork_ev) ; c.fork_ev = nullptr ;
+    for (int k = 0 ; k < Ctx::NSIDE ; k++)
+    {
+        cudaStreamSynchronize (c.side [k]) ;
+        cudaStreamDestroy (c.side [k]) ; c.side [k] = nullptr ;
+        cudaEventDestroy (c.side_done [k]) ; c.side_done [k] = nullptr ;
+    }
+    for (cudaEvent_t e : c.kev) cudaEventDestroy (e) ;
+    c.kev.clear () ; c.kev_used = 0 ;
     cudaStreamDestroy (c.stream) ; c.stream = nullptr ;
     c.ready = false ;
     return GB200_SUCCESS ;

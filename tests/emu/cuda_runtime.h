@@ -336,6 +336,9 @@ static inline cudaError_t cudaStreamCreateWithFlags (cudaStream_t *s, unsigned) 
 static inline cudaError_t cudaStreamSynchronize (cudaStream_t) { return cudaSuccess ; }
 static inline cudaError_t cudaStreamDestroy (cudaStream_t) { return cudaSuccess ; }
 static inline cudaError_t cudaEventCreate (cudaEvent_t *e) { *e = new emuEvent () ; (*e)->ms = 0 ; return cudaSuccess ; }
+enum { cudaEventDisableTiming = 2 } ;
+static inline cudaError_t cudaEventCreateWithFlags (cudaEvent_t *e, unsigned) { *e = new emuEvent () ; (*e)->ms = 0 ; return cudaSuccess ; }
+static inline cudaError_t cudaStreamWaitEvent (cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess ; }
 static inline cudaError_t cudaEventDestroy (cudaEvent_t e) { delete e ; return cudaSuccess ; }
 static inline cudaError_t cudaEventRecord (cudaEvent_t e, cudaStream_t = nullptr) { e->ms = emu_now_ms () ; return cudaSuccess ; }
 static inline cudaError_t cudaEventSynchronize (cudaEvent_t) { return cudaSuccess ; }

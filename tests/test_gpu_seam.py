@@ -315,6 +315,31 @@ def test_masked_dot_hub_variants(monkeypatch, iso, bits):
         test_masked_dot_hubs(iso, add, mult, t)
 
 
+@pytest.mark.parametrize("iso", [True, False])
+@pytest.mark.parametrize("env", [{"GB200_DOTG_TRIM": "0"}, {"GB200_DOTG_TRIM": "1", "GB200_CLS_U": "1"},
+                                 {"GB200_DOTG_TRIM": "2", "GB200_CLS_U": "4"}, {"GB200_DOT_STREAMS": "0"},
+                                 {"GB200_DOTR_PF_HUB": "0", "GB200_DOTR_PF_REG": "0", "GB200_DOTR_PF_TINY": "0"},
+                                 {"GB200_DOTR_PF_HUB": "8", "GB200_DOTR_PF_REG": "5", "GB200_DOTR_PF_TINY": "1",
+                                  "GB200_DOTR_BM_BITS": "4096"}])
+def test_masked_dot_setup_and_launch_variants(monkeypatch, iso, env):
+    """the trim modes of the classification (none / always searched / not searched in a walked list of one
+    row), one or four pairs per thread, the semiring kernels on side streams or one after another, the
+    L2 prefetch distance of the row walk: every variant returns the oracle's T"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for add, mult, t in (("PLUS", "TIMES", "INT64"), ("MIN", "PLUS", "FP64")):
+        test_masked_dot_hubs(iso, add, mult, t)
+    # longer walked lists on both sides (the searches of the trim run on real ranges)
+    A = gen.rmat_scipy(13, 16, dtype=np.int64)
+    if not iso:
+        A.data[:] = np.random.default_rng(5).integers(1, 9, A.nnz)
+    L, U = gb.Matrix.from_scipy(sp.tril(A, -1).tocsr()), gb.Matrix.from_scipy(sp.triu(A, 1).tocsr())
+    sr = gb.Semiring("PLUS", "TIMES", "INT64", True)
+    ref = oracle_c.axb(L, False, U, L, sr, True)
+    got = gb.axb_host(L, False, U, L, sr, True)
+    assert_same(ref, got.matrix, "PLUS", f"tri {env}")
+
+
 def test_masked_dot_general_path_on_iso_input(monkeypatch):
     """GB200_DOTG_ISO=0 sends pattern-only operands through the valued kernel: same T"""
     A = gen.rmat_scipy(13, 8, dtype=np.int64)
