@@ -90,39 +90,90 @@ __global__ void dot_cnt_rect_kernel (const int64_t *__restrict__ pos, int64_t an
 // again, so items are large (measured, tri scale 22: 128: 46.5, 256: 43.8, 512: 42.8, 1024: 42.4 ms)
 constexpr int64_t DOTG_CHUNK = 1024 ;
 
-// Per stored vector: where it starts, how long it is, its first and last index -- one 32-byte record
-// (one DRAM sector), so that the classification of a pair costs one random sector per side instead of
-// three (pointer pair, first index, last index).
-struct __align__ (32) VecInfo { int64_t p0 ; int64_t len ; int32_t first ; int32_t last ; int64_t pad ; } ;
+// Per stored vector: where it starts, how long it is, its first and last index -- one record, so that
+// the classification of a pair costs one random sector per side instead of three (pointer pair, first
+// index, last index).  16 bytes while positions fit 32 bits (two records per sector, and the table of a
+// 4 M-vector operand is 67 MB: it stays in L2), 32 bytes otherwise.
+struct VecRec { int64_t p0 ; int64_t len ; int32_t first ; int32_t last ; } ;
+struct __align__ (16) VecInfo16
+{
+    uint32_t p0 ; uint32_t len ; int32_t first ; int32_t last ;
+    __device__ __forceinline__ static void store (VecInfo16 *q, const VecRec &v)
+    {
+        *(int4 *) q = make_int4 ((int) (uint32_t) v.p0, (int) (uint32_t) v.len, v.first, v.last) ;
+    }
+    __device__ __forceinline__ static VecRec load (const VecInfo16 *__restrict__ q)
+    {
+        const int4 a = __ldg ((const int4 *) q) ;
+        VecRec v ;
+        v.p0 = (int64_t) (uint32_t) a.x ; v.len = (int64_t) (uint32_t) a.y ; v.first = a.z ; v.last = a.w ;
+        return v ;
+    }
+} ;
+struct __align__ (32) VecInfo32
+{
+    int64_t p0 ; int64_t len ; int32_t first ; int32_t last ; int64_t pad ;
+    __device__ __forceinline__ static void store (VecInfo32 *q, const VecRec &v)
+    {
+        VecInfo32 w ;
+        w.p0 = v.p0 ; w.len = v.len ; w.first = v.first ; w.last = v.last ; w.pad = 0 ;
+        *q = w ;
+    }
+    __device__ __forceinline__ static VecRec load (const VecInfo32 *__restrict__ q)
+    {
+        const int4 a = __ldg ((const int4 *) q), b = __ldg (((const int4 *) q) + 1) ;
+        VecRec v ;
+        v.p0 = ((int64_t) (uint32_t) a.x) | ((int64_t) a.y << 32) ;
+        v.len = ((int64_t) (uint32_t) a.z) | ((int64_t) a.w << 32) ;
+        v.first = b.x ; v.last = b.y ;
+        return v ;
+    }
+} ;
 
-__global__ void vec_info_kernel (DMat X, VecInfo *__restrict__ info)
+template <class VI>
+__global__ void vec_info_kernel (DMat X, VI *__restrict__ info)
 {
     for (int64_t k = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; k < X.nvec ;
         k += (int64_t) gridDim.x * blockDim.x)
     {
-        VecInfo v ;
-        v.p0 = X.p [k] ; v.len = X.p [k+1] - v.p0 ; v.pad = 0 ;
+        VecRec v ;
+        v.p0 = X.p [k] ; v.len = X.p [k+1] - v.p0 ;
         v.first = (v.len > 0) ? __ldg (X.i + v.p0) : 0 ;
         v.last = (v.len > 0) ? __ldg (X.i + v.p0 + v.len - 1) : 0 ;
-        info [k] = v ;
+        VI::store (info + k, v) ;
     }
 }
 
-__device__ __forceinline__ VecInfo load_vec_info (const VecInfo *__restrict__ p)
-{
-    const int4 a = __ldg ((const int4 *) p), b = __ldg (((const int4 *) p) + 1) ;
-    VecInfo v ;
-    v.p0 = ((int64_t) (uint32_t) a.x) | ((int64_t) a.y << 32) ;
-    v.len = ((int64_t) (uint32_t) a.z) | ((int64_t) a.w << 32) ;
-    v.first = b.x ; v.last = b.y ; v.pad = 0 ;
-    return v ;
-}
-
 // Both lists are sorted, so a match can only lie between the owner's first and last index: the walked
-// list is trimmed to that range before it becomes a task (at most two binary searches per pair, done by
-// dotg_classify_kernel).  For C<L>=L*U' every pair keeps only the indices between j and i: 43 % fewer
-// probes on RMAT graphs.  A side whose end is already inside the range needs no search (the common case
-// for one side).
+// list is trimmed to that range before it becomes a task (at most two binary searches per pair).  For
+// C<L>=L*U' every pair keeps only the indices between j and i: 43 % fewer probes on RMAT graphs.
+// wfirst / wlast: the walked list's own first and last index (a side whose end is already inside the
+// range needs no search: the common case for one side).
+__device__ __forceinline__ void dotg_trim (const int32_t *__restrict__ Wi, int64_t w0, int64_t w1,
+    int32_t wfirst, int32_t wlast, int32_t omin, int32_t omax, int64_t &t0, int64_t &t1)
+{
+    int64_t l = w0, h = w1 ;
+    if (wfirst < omin)
+    {
+        while (l < h)
+        {
+            const int64_t mid = (l + h) >> 1 ;
+            if (__ldg (Wi + mid) < omin) l = mid + 1 ; else h = mid ;
+        }
+    }
+    t0 = l ;
+    h = w1 ;
+    if (l < w1 && wlast > omax)
+    {
+        while (l < h)
+        {
+            const int64_t mid = (l + h) >> 1 ;
+            if (__ldg (Wi + mid) <= omax) l = mid + 1 ; else h = mid ;
+        }
+        t1 = l ;
+    }
+    else t1 = w1 ;
+}
 
 // ---- set-up of the masked dot: two passes over the mask entries -------------------------------------
 // A pair is DEAD (an empty side, or nothing left after the trim), SMALL (owner shorter than DOTG_SMALL:
@@ -135,171 +186,69 @@ enum { PK_DEAD = 0, PK_SMALL = 1, PK_BOWN = 2, PK_AOWN = 3 } ;
 // pass 1: classification with the trim.  w0 [e] = where the (trimmed) walk starts in the walked matrix,
 // lk [e] = its length | kind << 30, nt0 [e] = tasks of a B-owned pair (else 0), cntA [ka] += tasks of an
 // A-owned pair, slist = the small pairs (any order: they are independent).
-// The pass is a chain of dependent random reads per pair (row index -> vector record -> up to two binary
-// searches in the walked list) and was bound by their latency (2.95 ms for 64 M pairs at full
-// occupancy), so a thread carries CLS_U pairs through the chain together: every step issues the loads
-// of all of them before any is used, and the binary searches advance in lockstep.
 // trim: 0 walk whole lists; 1 always search; 2 (default) no search in a walked list of at most 32 indices:
-// it is one row of the walk with or without the trim, and the two searches cost more random DRAM sectors
-// than the rest of the pass -- such a pair is only dropped when the two index ranges do not meet.
-template <int CLS_U>
-__global__ void __launch_bounds__ (256)
-dotg_classify_kernel (DMat A, DMat B, DMat M, const VecInfo *__restrict__ infoA,
-    const VecInfo *__restrict__ infoB, const int32_t *__restrict__ mvec,
+// it is one row of the walk with or without the trim -- such a pair is only dropped when the two index
+// ranges do not meet.
+template <class VI>
+__global__ void dotg_classify_kernel (DMat A, DMat B, DMat M, const VI *__restrict__ infoA,
+    const VI *__restrict__ infoB, const int32_t *__restrict__ mvec,
     int64_t mnz, int trim, int64_t *__restrict__ w0out, int32_t *__restrict__ lk, int32_t *__restrict__ nt0,
     unsigned long long *__restrict__ cntA, int32_t *__restrict__ slist, unsigned int *__restrict__ nsmall)
 {
     const int lane = threadIdx.x & 31 ;
-    const int64_t tile = (int64_t) blockDim.x * CLS_U ;     // consecutive pairs of one block iteration
-    const int64_t ntiles = (mnz + tile - 1) / tile ;
-    for (int64_t tl = blockIdx.x ; tl < ntiles ; tl += gridDim.x)
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x ;
+    const int64_t niter = (mnz + stride - 1) / stride ;
+    int64_t e = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ;
+    for (int64_t itn = 0 ; itn < niter ; itn++, e += stride)
     {
-        int64_t e [CLS_U], ka [CLS_U], kb [CLS_U] ;
-        int32_t mi [CLS_U], mv [CLS_U] ;
-        #pragma unroll
-        for (int u = 0 ; u < CLS_U ; u++)
+        int kind = PK_DEAD ;
+        int32_t len = 0, ntk = 0 ;
+        int64_t wstart = 0 ;
+        if (e < mnz)
         {
-            e [u] = tl * tile + (int64_t) u * blockDim.x + threadIdx.x ;
-            const bool in = (e [u] < mnz) ;
-            mi [u] = in ? __ldg (M.i + e [u]) : 0 ;
-            mv [u] = in ? __ldg (mvec + e [u]) : 0 ;
-        }
-        #pragma unroll
-        for (int u = 0 ; u < CLS_U ; u++)
-        {
-            ka [u] = -1 ; kb [u] = -1 ;
-            if (e [u] < mnz)
+            const int64_t ka = dm_vecpos (A, M.i [e]) ;
+            const int64_t kb = dm_vecpos (B, dm_vecname (M, mvec [e])) ;
+            if (ka >= 0 && kb >= 0)
             {
-                ka [u] = dm_vecpos (A, mi [u]) ;
-                kb [u] = dm_vecpos (B, dm_vecname (M, mv [u])) ;
-            }
-        }
-        VecInfo va [CLS_U], vb [CLS_U] ;
-        #pragma unroll
-        for (int u = 0 ; u < CLS_U ; u++)
-        {
-            va [u].p0 = 0 ; va [u].len = 0 ; va [u].first = 0 ; va [u].last = 0 ; vb [u] = va [u] ;
-            if (ka [u] >= 0 && kb [u] >= 0)
-            {
-                va [u] = load_vec_info (infoA + ka [u]) ;
-                vb [u] = load_vec_info (infoB + kb [u]) ;
-            }
-        }
-        int kind [CLS_U] ;
-        bool walkA [CLS_U] ;
-        // the walked list [l, h) and what is searched in it: first index >= omin, then first index > omax
-        const int32_t *Wi [CLS_U] ;
-        int64_t l [CLS_U], h [CLS_U], w1 [CLS_U] ;
-        int32_t omin [CLS_U], omax [CLS_U], wlast [CLS_U] ;
-        bool live [CLS_U], srch [CLS_U] ;
-        #pragma unroll
-        for (int u = 0 ; u < CLS_U ; u++)
-        {
-            kind [u] = PK_DEAD ; walkA [u] = false ; live [u] = false ; srch [u] = false ;
-            Wi [u] = A.i ; l [u] = 0 ; h [u] = 0 ; w1 [u] = 0 ; omin [u] = 0 ; omax [u] = 0 ; wlast [u] = 0 ;
-            const int64_t ainz = va [u].len, bjnz = vb [u].len ;
-            if (ainz > 0 && bjnz > 0)
-            {
-                walkA [u] = dot_walkA (ainz, bjnz, A.vlen) ;
-                const int64_t olen = walkA [u] ? bjnz : ainz ;
-                if (olen < DOTG_SMALL) kind [u] = PK_SMALL ;
-                else
+                const VecRec va = VI::load (infoA + ka), vb = VI::load (infoB + kb) ;
+                const int64_t ainz = va.len, bjnz = vb.len ;
+                if (ainz > 0 && bjnz > 0)
                 {
-                    const VecInfo &vw = walkA [u] ? va [u] : vb [u] ;       // walked
-                    const VecInfo &vo = walkA [u] ? vb [u] : va [u] ;       // owner
-                    live [u] = true ;
-                    Wi [u] = walkA [u] ? A.i : B.i ;
-                    l [u] = vw.p0 ; w1 [u] = vw.p0 + vw.len ;
-                    omin [u] = vo.first ; omax [u] = vo.last ; wlast [u] = vw.last ;
-                    srch [u] = (trim == 1) || (trim == 2 && vw.len > 32) ;
-                    if (trim && (vw.last < vo.first || vw.first > vo.last)) { w1 [u] = l [u] ; srch [u] = false ; }
-                    // a side whose end is already inside the owner's range needs no search
-                    h [u] = (srch [u] && vw.first < vo.first) ? w1 [u] : l [u] ;
+                    const bool walkA = dot_walkA (ainz, bjnz, A.vlen) ;
+                    const int64_t olen = walkA ? bjnz : ainz ;
+                    if (olen < DOTG_SMALL) kind = PK_SMALL ;
+                    else
+                    {
+                        const VecRec &vw = walkA ? va : vb ;        // walked
+                        const VecRec &vo = walkA ? vb : va ;        // owner
+                        int64_t t0 = vw.p0, t1 = vw.p0 + vw.len ;
+                        if (trim && (vw.last < vo.first || vw.first > vo.last)) t1 = t0 ;
+                        else if (trim == 1 || (trim == 2 && vw.len > 32))
+                            dotg_trim (walkA ? A.i : B.i, vw.p0, vw.p0 + vw.len, vw.first, vw.last,
+                                vo.first, vo.last, t0, t1) ;
+                        len = (int32_t) (t1 - t0) ;
+                        wstart = t0 ;
+                        if (len > 0)
+                        {
+                            ntk = (len + DOTG_SEG - 1) / DOTG_SEG ;
+                            if (walkA) kind = PK_BOWN ;
+                            else { kind = PK_AOWN ; atomicAdd (cntA + ka, (unsigned long long) ntk) ; }
+                        }
+                    }
                 }
             }
+            w0out [e] = wstart ;
+            lk [e] = len | (kind << 30) ;
+            nt0 [e] = (kind == PK_BOWN) ? ntk : 0 ;
         }
-        // lower ends, in lockstep
-        while (true)
+        // the small pairs of the warp are appended with one atomic
+        const unsigned sm = __ballot_sync (0xffffffffu, kind == PK_SMALL) ;
+        if (sm)
         {
-            bool any = false ;
-            int64_t mid [CLS_U] ; int32_t v [CLS_U] ;
-            #pragma unroll
-            for (int u = 0 ; u < CLS_U ; u++)
-            {
-                mid [u] = (l [u] + h [u]) >> 1 ;
-                v [u] = (l [u] < h [u]) ? __ldg (Wi [u] + mid [u]) : 0 ;
-            }
-            #pragma unroll
-            for (int u = 0 ; u < CLS_U ; u++)
-                if (l [u] < h [u])
-                {
-                    if (v [u] < omin [u]) l [u] = mid [u] + 1 ; else h [u] = mid [u] ;
-                    any = any || (l [u] < h [u]) ;
-                }
-            if (!any) break ;
-        }
-        int64_t t0 [CLS_U] ;
-        #pragma unroll
-        for (int u = 0 ; u < CLS_U ; u++)
-        {
-            t0 [u] = l [u] ;
-            h [u] = (srch [u] && l [u] < w1 [u] && wlast [u] > omax [u]) ? w1 [u] : l [u] ;
-        }
-        // upper ends
-        bool searched [CLS_U] ;
-        #pragma unroll
-        for (int u = 0 ; u < CLS_U ; u++) searched [u] = (l [u] < h [u]) ;
-        while (true)
-        {
-            bool any = false ;
-            int64_t mid [CLS_U] ; int32_t v [CLS_U] ;
-            #pragma unroll
-            for (int u = 0 ; u < CLS_U ; u++)
-            {
-                mid [u] = (l [u] + h [u]) >> 1 ;
-                v [u] = (l [u] < h [u]) ? __ldg (Wi [u] + mid [u]) : 0 ;
-            }
-            #pragma unroll
-            for (int u = 0 ; u < CLS_U ; u++)
-                if (l [u] < h [u])
-                {
-                    if (v [u] <= omax [u]) l [u] = mid [u] + 1 ; else h [u] = mid [u] ;
-                    any = any || (l [u] < h [u]) ;
-                }
-            if (!any) break ;
-        }
-        #pragma unroll
-        for (int u = 0 ; u < CLS_U ; u++)
-        {
-            int32_t len = 0, ntk = 0 ;
-            int64_t wstart = 0 ;
-            if (live [u])
-            {
-                const int64_t t1 = searched [u] ? l [u] : w1 [u] ;
-                len = (int32_t) (t1 - t0 [u]) ;
-                wstart = t0 [u] ;
-                if (len > 0)
-                {
-                    ntk = (len + DOTG_SEG - 1) / DOTG_SEG ;
-                    if (walkA [u]) kind [u] = PK_BOWN ;
-                    else { kind [u] = PK_AOWN ; atomicAdd (cntA + ka [u], (unsigned long long) ntk) ; }
-                }
-            }
-            if (e [u] < mnz)
-            {
-                w0out [e [u]] = wstart ;
-                lk [e [u]] = len | (kind [u] << 30) ;
-                nt0 [e [u]] = (kind [u] == PK_BOWN) ? ntk : 0 ;
-            }
-            // the small pairs of the warp are appended with one atomic
-            const unsigned sm = __ballot_sync (0xffffffffu, kind [u] == PK_SMALL) ;
-            if (sm)
-            {
-                unsigned int base = 0 ;
-                if (lane == 0) base = atomicAdd (nsmall, (unsigned int) __popc (sm)) ;
-                base = __shfl_sync (0xffffffffu, base, 0) ;
-                if (kind [u] == PK_SMALL) slist [base + __popc (sm & ((1u << lane) - 1u))] = (int32_t) e [u] ;
-            }
+            unsigned int base = 0 ;
+            if (lane == 0) base = atomicAdd (nsmall, (unsigned int) __popc (sm)) ;
+            base = __shfl_sync (0xffffffffu, base, 0) ;
+            if (kind == PK_SMALL) slist [base + __popc (sm & ((1u << lane) - 1u))] = (int32_t) e ;
         }
     }
 }
@@ -471,9 +420,6 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             const char *trim_env = getenv ("GB200_DOTG_TRIM") ;
             int trim = (trim_env != nullptr) ? atoi (trim_env) : 2 ;
             if (trim < 0 || trim > 2) trim = 2 ;
-            // pairs a thread of the classification carries together (1 or 4; for A/B runs)
-            const char *clsu_env = getenv ("GB200_CLS_U") ;
-            const int cls_u = (clsu_env != nullptr && atoi (clsu_env) == 1) ? 1 : 4 ;
             // 0: warp per task / lane per task (dotg_kernel) instead of the row walk (kernels_dotr.cuh)
             const char *flat_env = getenv ("GB200_DOTR") ;
             const bool flat = !(flat_env != nullptr && atoi (flat_env) == 0) ;
@@ -493,33 +439,45 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             GB200_CUDA (cudaMemsetAsync (nsmall.ptr, 0, 8, c.stream)) ;
             DevBuf infoA, infoB ;
             const bool sameAB = (A.p == B.p && A.i == B.i && A.nvec == B.nvec) ;
-            GB200_TRY (infoA.alloc ((size_t) (anvec > 0 ? anvec : 1) * sizeof (VecInfo))) ;
-            vec_info_kernel <<<grid_cap ((anvec + 255) / 256, 16), 256, 0, c.stream>>> (A, infoA.as<VecInfo> ()) ;
-            if (!sameAB)
+            const bool wide = (A.nnz >= (1LL << 32) || B.nnz >= (1LL << 32)) ;
+            const size_t recsz = wide ? sizeof (VecInfo32) : sizeof (VecInfo16) ;
+            GB200_TRY (infoA.alloc ((size_t) (anvec > 0 ? anvec : 1) * recsz)) ;
+            if (!sameAB) GB200_TRY (infoB.alloc ((size_t) (B.nvec > 0 ? B.nvec : 1) * recsz)) ;
+            const void *infoBp = sameAB ? infoA.ptr : infoB.ptr ;
+            const int vgA = grid_cap ((anvec + 255) / 256, 16), vgB = grid_cap ((B.nvec + 255) / 256, 16) ;
+            const int cg = grid_cap ((mnz + 255) / 256, 16) ;
+            if (wide)
             {
-                GB200_TRY (infoB.alloc ((size_t) (B.nvec > 0 ? B.nvec : 1) * sizeof (VecInfo))) ;
-                vec_info_kernel <<<grid_cap ((B.nvec + 255) / 256, 16), 256, 0, c.stream>>> (B, infoB.as<VecInfo> ()) ;
+                vec_info_kernel<VecInfo32> <<<vgA, 256, 0, c.stream>>> (A, infoA.as<VecInfo32> ()) ;
+                if (!sameAB) vec_info_kernel<VecInfo32> <<<vgB, 256, 0, c.stream>>> (B, infoB.as<VecInfo32> ()) ;
+                dotg_classify_kernel<VecInfo32> <<<cg, 256, 0, c.stream>>> (A, B, Mv, infoA.as<VecInfo32> (),
+                    (const VecInfo32 *) infoBp, mvec.as<int32_t> (), mnz, trim, w0buf.as<int64_t> (),
+                    lk.as<int32_t> (), nt0.as<int32_t> (), cntA.as<unsigned long long> (), slist.as<int32_t> (),
+                    nsmall.as<unsigned int> ()) ;
             }
-            count_launch (sameAB ? 1 : 2) ;
-            if (cls_u == 1)
-                dotg_classify_kernel<1> <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, B, Mv,
-                infoA.as<VecInfo> (), sameAB ? infoA.as<VecInfo> () : infoB.as<VecInfo> (),
-                mvec.as<int32_t> (), mnz, trim, w0buf.as<int64_t> (), lk.as<int32_t> (), nt0.as<int32_t> (),
-                cntA.as<unsigned long long> (), slist.as<int32_t> (), nsmall.as<unsigned int> ()) ;
             else
-                dotg_classify_kernel<4> <<<grid_cap ((mnz + 1023) / 1024, 16), 256, 0, c.stream>>> (A, B, Mv,
-                infoA.as<VecInfo> (), sameAB ? infoA.as<VecInfo> () : infoB.as<VecInfo> (),
-                mvec.as<int32_t> (), mnz, trim, w0buf.as<int64_t> (), lk.as<int32_t> (), nt0.as<int32_t> (),
-                cntA.as<unsigned long long> (), slist.as<int32_t> (), nsmall.as<unsigned int> ()) ;
-            count_launch () ;
+            {
+                vec_info_kernel<VecInfo16> <<<vgA, 256, 0, c.stream>>> (A, infoA.as<VecInfo16> ()) ;
+                if (!sameAB) vec_info_kernel<VecInfo16> <<<vgB, 256, 0, c.stream>>> (B, infoB.as<VecInfo16> ()) ;
+                dotg_classify_kernel<VecInfo16> <<<cg, 256, 0, c.stream>>> (A, B, Mv, infoA.as<VecInfo16> (),
+                    (const VecInfo16 *) infoBp, mvec.as<int32_t> (), mnz, trim, w0buf.as<int64_t> (),
+                    lk.as<int32_t> (), nt0.as<int32_t> (), cntA.as<unsigned long long> (), slist.as<int32_t> (),
+                    nsmall.as<unsigned int> ()) ;
+            }
+            count_launch (sameAB ? 2 : 3) ;
             // B-owned pairs keep the mask's order (a scan of their task counts); A-owned: counting sort by i
             GB200_TRY (scan_i32 (nt0.as<int32_t> (), toff0.as<int64_t> (), mnz)) ;
             GB200_TRY (scan_i64 (cntA.as<int64_t> (), offA.as<int64_t> (), anvec)) ;
             int64_t nt_b = 0, nt_a = 0, ns = 0 ;
-            GB200_TRY (read_i64 (toff0.as<int64_t> () + mnz, &nt_b)) ;
-            GB200_TRY (read_i64 (offA.as<int64_t> () + anvec, &nt_a)) ;
-            GB200_TRY (read_i64 (nsmall.as<int64_t> (), &ns)) ;
-            ns &= 0xffffffffLL ;
+            {
+                // the three totals in one round trip
+                int64_t *hp = (int64_t *) c.pinned ;
+                GB200_CUDA (cudaMemcpyAsync (hp, toff0.as<int64_t> () + mnz, 8, cudaMemcpyDeviceToHost, c.stream)) ;
+                GB200_CUDA (cudaMemcpyAsync (hp + 1, offA.as<int64_t> () + anvec, 8, cudaMemcpyDeviceToHost, c.stream)) ;
+                GB200_CUDA (cudaMemcpyAsync (hp + 2, nsmall.ptr, 8, cudaMemcpyDeviceToHost, c.stream)) ;
+                GB200_CUDA (cudaStreamSynchronize (c.stream)) ;
+                nt_b = hp [0] ; nt_a = hp [1] ; ns = hp [2] & 0xffffffffLL ;
+            }
             GB200_TRY (tasks.alloc ((nt_b + nt_a + 1) * sizeof (DotTask))) ;
             dotg_scatter_kernel <<<grid_cap ((mnz + 255) / 256, 16), 256, 0, c.stream>>> (A, Mv, mnz,
                 w0buf.as<int64_t> (), lk.as<int32_t> (), toff0.as<int64_t> (), offA.as<int64_t> (),
@@ -601,15 +559,6 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             // table-free small pairs last.  GB200_DOT_STREAMS=0: one after another on the main stream.
             const char *str_env = getenv ("GB200_DOT_STREAMS") ;
             const bool streams = !(str_env != nullptr && atoi (str_env) == 0) ;
-            // L2 prefetch distance of the row-walk kernels, per owner class (hub, regular, tiny), in tasks
-            auto pf_of = [] (const char *name, int dflt)
-            {
-                const char *e = getenv (name) ;
-                int v = (e != nullptr) ? atoi (e) : dflt ;
-                return (v < 0) ? 0 : ((v > 8) ? 8 : v) ;
-            } ;
-            const int pf_hub = pf_of ("GB200_DOTR_PF_HUB", 2), pf_reg = pf_of ("GB200_DOTR_PF_REG", 2),
-                pf_tiny = pf_of ("GB200_DOTR_PF_TINY", 2) ;
             if (streams) GB200_TRY (group_begin ()) ;
             int nlaunch = 0 ;
             static const int class_order [4] = { 2, 1, 0, 3 } ;
@@ -625,7 +574,6 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
                     ga.bm_bits = K [orient].bm_bits ;
                     ga.next_item = next_item.as<unsigned long long> () + 4 * orient + cls ;
                     ga.items = IL [orient].items [cls] ; ga.nitems = nitems ;
-                    ga.prefetch = (cls == 1) ? pf_hub : ((cls == 3) ? pf_tiny : pf_reg) ;
                     int fam, per_sm, threads ;
                     if (cls == 2) { fam = iso ? FAM_DOTG_HUB_ISO : FAM_DOTG_HUB ; per_sm = 2 ; threads = DOTG_THREADS ; }
                     else if (cls == 1) { fam = iso ? FAM_DOTR_BM_ISO : FAM_DOTR_BM ; per_sm = 1 ; threads = DOTR_BM_THREADS ; }

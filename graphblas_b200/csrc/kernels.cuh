@@ -482,7 +482,6 @@ struct DotGArgs
                                         // host then recomputes the pairs with the table-free dot_kernel
     int64_t bm_bits ;                   // dotr_kernel<BITMAP>: indices per bitmap part (a multiple of 32)
     int mult_op ; int flip ;
-    int prefetch ;                      // dotr kernels: L2 prefetch distance in tasks (0: off)
 } ;
 
 // stored-vector position of vector `name`, or -1

@@ -60,7 +60,6 @@ template <class S> struct DotRCtx
     uint32_t c1, c2 ;
     uint32_t lo, nbits ;        // bitmap part: indices [lo, lo + nbits)
     int32_t hi ;                // lo + nbits
-    int pf ;                    // L2 prefetch distance in tasks (0: off)
 } ;
 
 // The owner's table in shared memory, read through a 32-bit shared-memory address (ld.shared with a
@@ -89,25 +88,6 @@ struct SmemTab
     }
 #endif
 } ;
-
-// The walked list of the task that comes `pf` tasks later is asked into L2 while the current one is
-// probed: lane l touches the l-th 128-byte line of it (a task is at most DOTG_SEG = 1024 indices = 32
-// lines).  The walk is bound by the latency of these lists (ncu: the first use of a loaded index is the
-// top stall, L2 hit 53-57 %), and a task is too short (5-17 rows) for its own loads to hide it.
-__device__ __forceinline__ void dotr_prefetch (const int32_t *__restrict__ Wi, long long w0, uint32_t lc, int lane)
-{
-#ifndef GB200_HOST_EMULATION
-    const int len = (int) (lc & 0xffffu) ;
-    int idx = (int) (lc >> 16) + 32 * lane ;
-    if (idx < len + 32)
-    {
-        idx = (idx < len) ? idx : (len - 1) ;
-        if (idx >= 0) asm volatile ("prefetch.global.L2 [%0];" :: "l" (Wi + w0 + idx)) ;
-    }
-#else
-    (void) Wi ; (void) w0 ; (void) lc ; (void) lane ;
-#endif
-}
 
 // what a probe needs, in registers
 struct DotRProbe
@@ -184,8 +164,7 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
     constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
     constexpr unsigned FULL = 0xffffffffu ;
     constexpr bool BITMAP = (MODE == DOTR_BITMAP) ;
-    // valued operands keep two values per row and lane in registers: four rows against a bitmap, too
-    constexpr int DOTR_U = (BITMAP && ISO) ? DOTR_U_BITMAP : DOTR_U_TABLE ;
+    constexpr int DOTR_U = BITMAP ? DOTR_U_BITMAP : DOTR_U_TABLE ;
     const int lane = threadIdx.x & 31 ;
     const SmemTab tab (table) ;
     DotRProbe q ;
@@ -232,13 +211,8 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
         uint32_t mycnt = 0 ;            // results of the task this lane keeps
         acc_t myacc = Mon::identity () ;
         uint32_t mycur = lc >> 16 ;
-        if (g.pf > 0)
-            for (int tp = 1 ; tp < g.pf && tp < nb ; tp++)
-                dotr_prefetch (g.Wi, __shfl_sync (FULL, w0, tp), __shfl_sync (FULL, lc, tp), lane) ;
         for (int t = 0 ; t < nb ; t++)
         {
-            if (g.pf > 0 && t + g.pf < nb)
-                dotr_prefetch (g.Wi, __shfl_sync (FULL, w0, t + g.pf), __shfl_sync (FULL, lc, t + g.pf), lane) ;
             const uint32_t tlc = __shfl_sync (FULL, lc, t) ;
             const int tl = (int) (tlc & 0xffffu), p0 = (int) (tlc >> 16) ;
             const long long tw = __shfl_sync (FULL, w0, t) ;
@@ -259,42 +233,20 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
                         k [u] = (rem > 32 * u) ? (uint32_t) __ldg (rp + 32 * u) : NOKEY ;
                     // rows 0 and 1 are probed whatever they hold (a row past the end is all NOKEY: no
                     // hit); every later pair of rows only if the task reaches it
-                    if constexpr (ISO)
+                    #pragma unroll
+                    for (int u = 0 ; u < DOTR_U ; u++)
                     {
-                        #pragma unroll
-                        for (int u = 0 ; u < DOTR_U ; u++)
+                        if (u >= 2 && (u & 1) == 0 && p + 32 * u >= tl) break ;  // warp-uniform
+                        uint32_t pos = 0 ;
+                        const uint32_t hit = dotr_probe<ISO, MODE> (q, tab, tab2, k [u], pos) ;
+                        if constexpr (ISO) cnt += hit ;
+                        else if (hit)
                         {
-                            if (u >= 2 && (u & 1) == 0 && p + 32 * u >= tl) break ;  // warp-uniform
-                            uint32_t pos = 0 ;
-                            cnt += dotr_probe<ISO, MODE> (q, tab, tab2, k [u], pos) ;
+                            const T ov = g.Ox [pos], wv = rx [32 * u] ;
+                            const acc_t prod = g.orient ? sr.product (ov, wv) : sr.product (wv, ov) ;
+                            acc = found ? Mon::combine (acc, prod) : prod ;
+                            found = true ; cnt++ ;
                         }
-                    }
-                    else
-                    {
-                        // valued operands: all probes of the iteration first, then the value loads of
-                        // all hits together (two independent loads per hit, all in flight), then the
-                        // products -- not probe / load / wait / combine row after row
-                        uint32_t hit [DOTR_U], pos [DOTR_U] ;
-                        #pragma unroll
-                        for (int u = 0 ; u < DOTR_U ; u++) { hit [u] = 0 ; pos [u] = 0 ; }
-                        #pragma unroll
-                        for (int u = 0 ; u < DOTR_U ; u++)
-                        {
-                            if (u >= 2 && (u & 1) == 0 && p + 32 * u >= tl) break ;  // warp-uniform
-                            hit [u] = dotr_probe<ISO, MODE> (q, tab, tab2, k [u], pos [u]) ;
-                        }
-                        T ov [DOTR_U], wv [DOTR_U] ;
-                        #pragma unroll
-                        for (int u = 0 ; u < DOTR_U ; u++)
-                            if (hit [u]) { ov [u] = g.Ox [pos [u]] ; wv [u] = rx [32 * u] ; }
-                        #pragma unroll
-                        for (int u = 0 ; u < DOTR_U ; u++)
-                            if (hit [u])
-                            {
-                                const acc_t prod = g.orient ? sr.product (ov [u], wv [u]) : sr.product (wv [u], ov [u]) ;
-                                acc = found ? Mon::combine (acc, prod) : prod ;
-                                found = true ; cnt++ ;
-                            }
                     }
                     if constexpr (BITMAP)
                     {
@@ -420,7 +372,6 @@ dotr_kernel (DotGArgs a)
     g.ciso = Mon::identity () ;
     if (ISO) g.ciso = sr.product (Ax [0], Bx [0]) ;
     g.multi = false ; g.last = true ; g.lo = 0 ; g.nbits = 0 ; g.hi = INT32_MAX ;
-    g.pf = a.prefetch ;
     g.mode = DOTR_CUCKOO ; g.NS = 0 ; g.sh = 0 ; g.c1 = 0 ; g.c2 = 0 ;
     unsigned long long nm = 0 ;
     while (true)
@@ -580,7 +531,6 @@ dotr_warp_kernel (DotGArgs a)
     g.ciso = Mon::identity () ;
     if (ISO) g.ciso = sr.product (Ax [0], Bx [0]) ;
     g.multi = false ; g.last = true ; g.lo = 0 ; g.nbits = 0 ; g.hi = INT32_MAX ;
-    g.pf = a.prefetch ;
     unsigned long long nm = 0 ;
     while (true)
     {

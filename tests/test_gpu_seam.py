@@ -316,15 +316,11 @@ def test_masked_dot_hub_variants(monkeypatch, iso, bits):
 
 
 @pytest.mark.parametrize("iso", [True, False])
-@pytest.mark.parametrize("env", [{"GB200_DOTG_TRIM": "0"}, {"GB200_DOTG_TRIM": "1", "GB200_CLS_U": "1"},
-                                 {"GB200_DOTG_TRIM": "2", "GB200_CLS_U": "4"}, {"GB200_DOT_STREAMS": "0"},
-                                 {"GB200_DOTR_PF_HUB": "0", "GB200_DOTR_PF_REG": "0", "GB200_DOTR_PF_TINY": "0"},
-                                 {"GB200_DOTR_PF_HUB": "8", "GB200_DOTR_PF_REG": "5", "GB200_DOTR_PF_TINY": "1",
-                                  "GB200_DOTR_BM_BITS": "4096"}])
+@pytest.mark.parametrize("env", [{"GB200_DOTG_TRIM": "0"}, {"GB200_DOTG_TRIM": "1"}, {"GB200_DOTG_TRIM": "2"},
+                                 {"GB200_DOT_STREAMS": "0"}, {"GB200_DOT_STREAMS": "1", "GB200_DOTR_BM_BITS": "4096"}])
 def test_masked_dot_setup_and_launch_variants(monkeypatch, iso, env):
     """the trim modes of the classification (none / always searched / not searched in a walked list of one
-    row), one or four pairs per thread, the semiring kernels on side streams or one after another, the
-    L2 prefetch distance of the row walk: every variant returns the oracle's T"""
+    row), the semiring kernels on side streams or one after another: every variant returns the oracle's T"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     for add, mult, t in (("PLUS", "TIMES", "INT64"), ("MIN", "PLUS", "FP64")):

@@ -33,23 +33,13 @@ VARIANTS = [
     ("hub16384", {"GB200_DOTG_HUB_CHUNK": "16384"}),
     ("valued", {"GB200_DOTG_ISO": "0"}),
     ("valued_notrim", {"GB200_DOTG_ISO": "0", "GB200_DOTG_TRIM": "0"}),
-    # round 2, second half: side streams, L2 prefetch of the coming tasks, short-list trim skip
-    ("r2m", {"GB200_DOT_STREAMS": "0", "GB200_DOTR_PF_HUB": "0", "GB200_DOTR_PF_REG": "0",
-             "GB200_DOTR_PF_TINY": "0", "GB200_DOTG_TRIM": "1", "GB200_CLS_U": "1"}),
+    # round 2, second half: side streams, short-list trim skip
     ("nostreams", {"GB200_DOT_STREAMS": "0"}),
-    ("nopf", {"GB200_DOTR_PF_HUB": "0", "GB200_DOTR_PF_REG": "0", "GB200_DOTR_PF_TINY": "0"}),
-    ("pf_hub_only", {"GB200_DOTR_PF_REG": "0", "GB200_DOTR_PF_TINY": "0"}),
-    ("pf1", {"GB200_DOTR_PF_HUB": "1", "GB200_DOTR_PF_REG": "1", "GB200_DOTR_PF_TINY": "1"}),
-    ("pf4", {"GB200_DOTR_PF_HUB": "4", "GB200_DOTR_PF_REG": "4", "GB200_DOTR_PF_TINY": "4"}),
-    ("pf8", {"GB200_DOTR_PF_HUB": "8", "GB200_DOTR_PF_REG": "8", "GB200_DOTR_PF_TINY": "8"}),
     ("trim1", {"GB200_DOTG_TRIM": "1"}),
-    ("clsu1", {"GB200_CLS_U": "1"}),
-    ("valued_r2m", {"GB200_DOTG_ISO": "0", "GB200_DOT_STREAMS": "0", "GB200_DOTR_PF_HUB": "0",
-                    "GB200_DOTR_PF_REG": "0", "GB200_DOTR_PF_TINY": "0", "GB200_DOTG_TRIM": "1", "GB200_CLS_U": "1"}),
+    ("nostreams_trim1", {"GB200_DOT_STREAMS": "0", "GB200_DOTG_TRIM": "1"}),
 ]
 KEYS = ("GB200_DOTG_TRIM", "GB200_DOTG_HUB_CHUNK", "GB200_DOTG_CHUNK", "GB200_DOTG_ISO", "GB200_DOTR",
-        "GB200_DOTR_BM_BITS", "GB200_DOTR_TINY", "GB200_DOT_STREAMS", "GB200_DOTR_PF_HUB", "GB200_DOTR_PF_REG",
-        "GB200_DOTR_PF_TINY", "GB200_CLS_U")
+        "GB200_DOTR_BM_BITS", "GB200_DOTR_TINY", "GB200_DOT_STREAMS")
 # the answer of the first measured run (profiles/r1_trim): a base that is itself wrong is noticed
 KNOWN = {22: (44374678, 2111700731)}
 
