@@ -85,29 +85,23 @@ __global__ void saxpy_hash_kernel (SaxpyArgs a)
         if (threadIdx.x == 0) s_n = 0 ;
         __syncthreads () ;
         const int64_t pb0 = a.B.p [kk], pb1 = a.B.p [kk+1] ;
-        for (int64_t pb = pb0 + warp ; pb < pb1 ; pb += nwarps)
+        for_each_product (a.A, a.B, pb0, pb1, [&] (int64_t p, int64_t pb)
         {
-            int64_t pa, pe ;
-            if (!dm_lookup (a.A, a.B.i [pb], pa, pe)) continue ;
-            const T bkj = Bx [pb] ;
-            for (int64_t p = pa + lane ; p < pe ; p += 32)
+            const int32_t i = __ldg (a.A.i + p) ;
+            const acc_t prod = sr.product (Ax [p], Bx [pb]) ;
+            uint32_t h = (hash32 ((uint32_t) i) >> (32 - LOG)) & mask ;
+            while (true)
             {
-                const int32_t i = __ldg (a.A.i + p) ;
-                const acc_t prod = sr.product (Ax [p], bkj) ;
-                uint32_t h = (hash32 ((uint32_t) i) >> (32 - LOG)) & mask ;
-                while (true)
+                const int32_t old = atomicCAS (keys + h, -1, i) ;
+                if (old == -1 || old == i)
                 {
-                    const int32_t old = atomicCAS (keys + h, -1, i) ;
-                    if (old == -1 || old == i)
-                    {
-                        Mon::atomic_combine (vals + h, prod) ;
-                        if (old == -1 && nwords > 0) atomicOr (bm + (((uint32_t) i) >> 5), 1u << (i & 31)) ;
-                        break ;
-                    }
-                    h = (h + 1) & mask ;
+                    Mon::atomic_combine (vals + h, prod) ;
+                    if (old == -1 && nwords > 0) atomicOr (bm + (((uint32_t) i) >> 5), 1u << (i & 31)) ;
+                    break ;
                 }
+                h = (h + 1) & mask ;
             }
-        }
+        }) ;
         __syncthreads () ;
         if (nwords > 0)
         {
@@ -193,21 +187,14 @@ __global__ void saxpy_light_kernel (SaxpyArgs a)
         const int64_t l0 = a.lp [lv], l1 = a.lp [lv+1] ;
         if (l1 <= l0) continue ;
         const int64_t pb0 = a.B.p [kk], pb1 = a.B.p [kk+1] ;
-        for (int64_t pb = pb0 + warp ; pb < pb1 ; pb += nwarps)
+        for_each_product (a.A, a.B, pb0, pb1, [&] (int64_t p, int64_t pb)
         {
-            const int64_t k = a.B.i [pb] ;
-            int64_t pa, pe ;
-            if (!dm_lookup (a.A, k, pa, pe)) continue ;
-            const T bkj = Bx [pb] ;
-            for (int64_t p = pa + lane ; p < pe ; p += 32)
-            {
-                const int32_t i = __ldg (a.A.i + p) ;
-                const int64_t slot = bsearch_i32 (a.li, l0, l1, i) ;
-                if (slot < 0) continue ;            // only possible when masked
-                Mon::atomic_combine (acc + slot, sr.product (Ax [p], bkj)) ;
-                if (a.flags) a.flags [slot] = 1 ;
-            }
-        }
+            const int32_t i = __ldg (a.A.i + p) ;
+            const int64_t slot = bsearch_i32 (a.li, l0, l1, i) ;
+            if (slot < 0) return ;                  // only possible when masked
+            Mon::atomic_combine (acc + slot, sr.product (Ax [p], Bx [pb])) ;
+            if (a.flags) a.flags [slot] = 1 ;
+        }) ;
     }
 }
 
