@@ -74,6 +74,7 @@ template <class F>
 __device__ __forceinline__ void for_each_product (const DMat &A, const DMat &B, int64_t pb0, int64_t pb1, F &&f)
 {
     constexpr unsigned FULL = 0xffffffffu ;
+    constexpr int LONG = 64 ;       // a vector of A this long is walked by the whole warp on its own
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5 ;
     int64_t cs = (pb1 - pb0 + nwarps - 1) / nwarps ;       // entries of B per chunk: every warp gets some
     cs = (cs < 1) ? 1 : ((cs > 32) ? 32 : cs) ;
@@ -82,27 +83,37 @@ __device__ __forceinline__ void for_each_product (const DMat &A, const DMat &B, 
         const int64_t pb = c0 + lane ;
         int64_t pa = 0, pe = 0 ;
         if (lane < cs && pb < pb1) { if (!dm_lookup (A, __ldg (B.i + pb), pa, pe)) { pa = 0 ; pe = 0 ; } }
-        const int64_t len = pe - pa ;
-        int64_t incl = len ;
+        // long vectors of A: one after another, lanes striding (coalesced, no search)
+        unsigned lm = __ballot_sync (FULL, pe - pa >= LONG) ;
+        while (lm)
+        {
+            const int e = __ffs (lm) - 1 ;
+            lm &= lm - 1 ;
+            const int64_t pae = __shfl_sync (FULL, pa, e), pee = __shfl_sync (FULL, pe, e) ;
+            for (int64_t p = pae + lane ; p < pee ; p += 32) f (p, c0 + e) ;
+        }
+        // the short ones end to end (fewer than 32 * LONG products: 32-bit offsets)
+        const int len = (pe - pa >= LONG) ? 0 : (int) (pe - pa) ;
+        int incl = len ;
         #pragma unroll
         for (int o = 1 ; o < 32 ; o <<= 1)
         {
-            const int64_t y = __shfl_up_sync (FULL, incl, o) ;
+            const int y = __shfl_up_sync (FULL, incl, o) ;
             if (lane >= o) incl += y ;
         }
-        const int64_t total = __shfl_sync (FULL, incl, 31) ;
-        const int64_t off = incl - len ;                    // non-decreasing over the lanes
-        for (int64_t t0 = 0 ; t0 < total ; t0 += 32)
+        const int total = __shfl_sync (FULL, incl, 31) ;
+        const int off = incl - len ;                        // non-decreasing over the lanes
+        for (int t0 = 0 ; t0 < total ; t0 += 32)
         {
-            const int64_t t = t0 + lane ;
+            const int t = t0 + lane ;
             int e = 0 ;                                     // the last entry whose products start at or before t
             #pragma unroll
             for (int sft = 16 ; sft > 0 ; sft >>= 1)
             {
-                const int64_t o = __shfl_sync (FULL, off, e + sft) ;
+                const int o = __shfl_sync (FULL, off, e + sft) ;
                 if (o <= t) e += sft ;
             }
-            const int64_t oe = __shfl_sync (FULL, off, e) ;
+            const int oe = __shfl_sync (FULL, off, e) ;
             const int64_t pae = __shfl_sync (FULL, pa, e) ;
             if (t < total) f (pae + (t - oe), c0 + e) ;
         }

@@ -129,10 +129,60 @@ __global__ void saxpy_hash_kernel (SaxpyArgs a)
             __syncthreads () ;
             continue ;
         }
-        for (int t = threadIdx.x ; t < size ; t += blockDim.x)
+        if (blockDim.x == 32)
         {
-            const int32_t key = keys [t] ;
-            if (key >= 0) comp [atomicAdd (&s_n, 1)] = ((uint64_t) (uint32_t) key << 32) | (uint32_t) t ;
+            // one warp per vector: the occupied slots are counted with votes, and up to 64 of them are
+            // sorted in registers (two per lane, a bitonic network of shuffles: no shared-memory round
+            // trips, no barriers)
+            constexpr unsigned FULL = 0xffffffffu ;
+            int n = 0 ;
+            for (int t0 = 0 ; t0 < size ; t0 += 32)
+            {
+                const int32_t key = keys [t0 + lane] ;
+                const unsigned occ = __ballot_sync (FULL, key >= 0) ;
+                if (key >= 0) comp [n + __popc (occ & ((1u << lane) - 1u))] = ((uint64_t) (uint32_t) key << 32) | (uint32_t) (t0 + lane) ;
+                n += __popc (occ) ;
+            }
+            __syncwarp () ;
+            if (n <= 64)
+            {
+                uint64_t x0 = (lane < n) ? comp [lane] : ~0ULL ;
+                uint64_t x1 = (lane + 32 < n) ? comp [lane + 32] : ~0ULL ;
+                #pragma unroll
+                for (int k = 2 ; k <= 64 ; k <<= 1)
+                {
+                    #pragma unroll
+                    for (int j = k >> 1 ; j > 0 ; j >>= 1)
+                    {
+                        if (j == 32)
+                        {
+                            if (x0 > x1) { const uint64_t y = x0 ; x0 = x1 ; x1 = y ; }
+                        }
+                        else
+                        {
+                            const uint64_t y0 = __shfl_xor_sync (FULL, x0, j), y1 = __shfl_xor_sync (FULL, x1, j) ;
+                            const bool low = ((lane & j) == 0) ;            // this lane holds the pair's lower index
+                            const bool asc0 = ((lane & k) == 0), asc1 = (((lane + 32) & k) == 0) ;
+                            // the lower index keeps the minimum of an ascending pair
+                            x0 = ((x0 < y0) == (low == asc0)) ? x0 : y0 ;
+                            x1 = ((x1 < y1) == (low == asc1)) ? x1 : y1 ;
+                        }
+                    }
+                }
+                if (lane < n) { a.Ci_out [base + lane] = (int32_t) (x0 >> 32) ; acc [base + lane] = vals [(uint32_t) x0] ; }
+                if (lane + 32 < n) { a.Ci_out [base + lane + 32] = (int32_t) (x1 >> 32) ; acc [base + lane + 32] = vals [(uint32_t) x1] ; }
+                __syncwarp () ;
+                continue ;
+            }
+            if (lane == 0) s_n = n ;
+        }
+        else
+        {
+            for (int t = threadIdx.x ; t < size ; t += blockDim.x)
+            {
+                const int32_t key = keys [t] ;
+                if (key >= 0) comp [atomicAdd (&s_n, 1)] = ((uint64_t) (uint32_t) key << 32) | (uint32_t) t ;
+            }
         }
         __syncthreads () ;
         const int n = s_n ;

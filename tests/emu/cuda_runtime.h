@@ -133,6 +133,12 @@ template <class T> static inline T __shfl_up_sync (unsigned mask, T v, unsigned 
     if (!((mask >> src) & 1u)) src = emu::t_lane ;
     return emu::unbits<T> (emu::exchange (mask, emu::bits (v), src)) ;
 }
+template <class T> static inline T __shfl_xor_sync (unsigned mask, T v, int lanemask, int width = 32)
+{
+    int src = emu::t_lane ^ lanemask ;
+    if ((src & ~(width - 1)) != (emu::t_lane & ~(width - 1)) || !((mask >> src) & 1u)) src = emu::t_lane ;
+    return emu::unbits<T> (emu::exchange (mask, emu::bits (v), src)) ;
+}
 static inline unsigned __ballot_sync (unsigned mask, int pred)
 {
     emu::t_warp->slot [emu::t_lane] = pred ? 1 : 0 ;
