@@ -597,11 +597,31 @@ def measure(args, env, primary=True):
 
     # ---- the multiplies of one step: (M, A, B) host triples + their resident handles ------------
     if args.workload == "bfs":
-        if world > 1:
-            raise SystemExit("the vector push step needs an exchange of the frontier (SURVEY.md 8e); "
-                             "bench.py runs it on one GPU")
         levels = bfs_levels(gb, w, dA)
-        calls = [(vm, A, qm, gb.DMatrix(vm), dA, gb.DMatrix(qm)) for qm, vm in levels]
+        nslices, srank = (args.slice_of, args.slice_rank) if (world == 1 and args.slice_of > 1) else (world, rank)
+        if nslices > 1:
+            # vector push on N GPUs: a rank owns a block of vertices = of A's vectors (balanced by their
+            # entries) and pushes the frontier entries of its block; the partial frontiers meet in every
+            # GPU's dense copy of w (gb200_peerbuf_publish: every rank stores the same value `true`, so
+            # overlapping stores of LOR need no atomic), SURVEY.md 8e
+            if w["do_adotb"]:
+                raise SystemExit("bench.py shards the BFS push step; use --bfs-dir push for N > 1")
+            bounds = gb.partition_by_flops(A.p, nslices)
+            lo, hi = int(bounds[srank]), int(bounds[srank + 1])
+            A_r = slice_vectors(gb, A, lo, hi)
+            dA_r = gb.DMatrix(A_r)
+
+            def q_slice(qm):
+                qi = qm.i[(qm.i >= lo) & (qm.i < hi)]
+                return gb.Matrix(A.vlen, 1, np.array([0, len(qi)]), qi, np.ones(len(qi), np.bool_), None, "BOOL")
+            calls = []
+            for qm, vm in levels:
+                qr = q_slice(qm)
+                calls.append((vm, A_r, qr, gb.DMatrix(vm), dA_r, gb.DMatrix(qr)))
+            dA.free()
+            w["partition"] = f"{nslices} blocks of A's vectors (vertices) balanced by entries; every level's frontier cut at the same bounds"
+        else:
+            calls = [(vm, A, qm, gb.DMatrix(vm), dA, gb.DMatrix(qm)) for qm, vm in levels]
         w["name"] += f", {len(levels)} levels from vertex {w['bfs_source']}"
         w["config"]["workload"] = w["name"]
     else:
@@ -751,18 +771,22 @@ def measure(args, env, primary=True):
         return pinned[id(m)]
     if slabs is not None and world > 1:
         args.no_e2e = True          # the slab-streamed multiply on N GPUs is measured on resident operands
+    if world > 1 and args.workload == "bfs":
+        args.no_e2e = True          # the sharded level loop is measured on resident operands
     hcalls = [] if args.no_e2e else [(pin(m), pin(a), pin(b)) for (m, a, b, _, _, _) in calls]
     hfull = hcalls
 
     # vector pull on N > 1 GPUs: every rank owns a block of A's vectors = of w's entries, and the
     # slices of w are all-gathered over NCCL every step; T never leaves HBM
     exchange = None
-    if world > 1 and sliced_name == "A" and A.vdim >= 1 and B.vdim == 1:
+    if world > 1 and ((sliced_name == "A" and A.vdim >= 1 and B is not None and B.vdim == 1)
+                      or args.workload == "bfs"):
         def allgather_bytes(b):
             out = [None] * world
             dist.all_gather_object(out, b)
             return out
-        pb = gb.PeerBuf(A.vdim, w["semiring"].ztype, rank, world, allgather_bytes)
+        pb = gb.PeerBuf(A.vlen if args.workload == "bfs" else A.vdim, w["semiring"].ztype, rank, world,
+                        allgather_bytes)
         exchange = {"pb": pb, "bytes": 0}
 
     def step_device():
@@ -889,6 +913,22 @@ def measure(args, env, primary=True):
         torch.cuda.synchronize()
         t_wall = time.perf_counter() - t0
     launches = gb.kernel_launches() - launches0
+    if exchange is not None and args.workload == "bfs":
+        # outside the timed region: every rank's dense copy of every level's w equals the next frontier
+        # of the single-GPU level loop
+        for lv, (_, _, _, dm, da, db) in enumerate(calls):
+            rh, info = gb.axb_device_keep(dm, w["mask_comp"], da, db, w["semiring"], w["do_adotb"])
+            if not info["mask_applied"]:
+                raise SystemExit("BFS push on N GPUs expects the fused <!v> (mask_applied)")
+            exchange["pb"].publish(rh)
+            gb.free_result(rh)
+            exchange["pb"].wait()
+            _, pres = exchange["pb"].read()
+            want = levels[lv + 1][0].i if lv + 1 < len(levels) else np.zeros(0, dtype=np.int64)
+            if not np.array_equal(np.nonzero(pres)[0], np.sort(want)):
+                sys.stderr.write(f"BFS exchange check FAILED on rank {rank}, level {lv}\n")
+                sys.exit(3)
+        w["exchange_check"] = f"every rank's dense copy of w equals the next frontier at all {len(calls)} levels"
     tt = torch.tensor([t_events, t_wall], dtype=torch.float64, device=device)
     rank_ms = [t_events / args.steps * 1e3]
     if world > 1:
@@ -1056,13 +1096,14 @@ def measure(args, env, primary=True):
                 "detail": {"madds_per_step": madds, "nnz_T": cnz, "multiplies_per_step": len(calls),
                            "timing": "CUDA events on the library's launching stream around the K "
                                      "steps, max over ranks; wall clock alongside",
-                           "partition": "none (one GPU)" if world == 1 else
+                           "partition": "none (one GPU)" if world == 1 else w["partition"] if "partition" in w else
                                         (f"{world} parts of the mask's entries by owner vector (B(:,j) with j in "
                                          "the rank's range, or A(:,i) with i in it), balanced by walk length"
                                          if sliced_name == "M" else
                                          f"{world} flop-balanced contiguous slices of "
                                          f"{ {'B': 'B', 'A': 'A', 'none': 'nothing'}[sliced_name]}'s vectors"),
                            "calibration_ms": w.get("calibration_ms"),
+                           "exchange_check": w.get("exchange_check"),
                            "slabs": None if slabs is None else {k: v for k, v in slabs.items() if k != "whole_B"},
                            "exchange": ("in-library: peer stores of the rank's block of w into every GPU's "
                                         "dense copy over NVLink (gb200_peerbuf_publish / _wait), "

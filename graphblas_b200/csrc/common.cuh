@@ -76,7 +76,9 @@ __device__ __forceinline__ void for_each_product (const DMat &A, const DMat &B, 
     constexpr unsigned FULL = 0xffffffffu ;
     constexpr int LONG = 64 ;       // a vector of A this long is walked by the whole warp on its own
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5 ;
-    int64_t cs = (pb1 - pb0 + nwarps - 1) / nwarps ;       // entries of B per chunk: every warp gets some
+    // entries of B per chunk: a lone warp takes up to 32 at a time; the warps of a larger block get about
+    // four chunks each, dealt round-robin, so that one chunk of long vectors does not hold the block up
+    int64_t cs = (nwarps == 1) ? 32 : (pb1 - pb0 + 4 * nwarps - 1) / (4 * nwarps) ;
     cs = (cs < 1) ? 1 : ((cs > 32) ? 32 : cs) ;
     for (int64_t c0 = pb0 + warp * cs ; c0 < pb1 ; c0 += nwarps * cs)
     {
