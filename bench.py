@@ -596,6 +596,7 @@ def measure(args, env, primary=True):
     do_cpu = (world == 1 and not args.no_cpu and rank == 0)
 
     # ---- the multiplies of one step: (M, A, B) host triples + their resident handles ------------
+    slabs = None
     if args.workload == "bfs":
         levels = bfs_levels(gb, w, dA)
         nslices, srank = (args.slice_of, args.slice_rank) if (world == 1 and args.slice_of > 1) else (world, rank)
