@@ -1027,9 +1027,9 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
         static bool attr_set = false ;          // one flag per instantiation
         if (!attr_set)
         {
-            cudaFuncSetAttribute (dotr_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            cudaFuncSetAttribute (dotr_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM + (DOTR_THREADS / 32) * DOTR_HIT_BYTES) ;
             cudaFuncSetAttribute (dotr_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
-            cudaFuncSetAttribute (dotr_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTR_BM_SMEM) ;
+            cudaFuncSetAttribute (dotr_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTR_BM_SMEM + (DOTR_BM_THREADS / 32) * DOTR_HIT_BYTES) ;
             cudaFuncSetAttribute (dotr_kernel<S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTR_BM_SMEM) ;
             attr_set = true ;
         }
@@ -1037,18 +1037,18 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
         if (family == FAM_DOTR_ISO)
             dotr_kernel<S, true, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
         else if (family == FAM_DOTR)
-            dotr_kernel<S, false, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+            dotr_kernel<S, false, false> <<<cfg.grid, cfg.block, DOTG_SMEM + (DOTR_THREADS / 32) * DOTR_HIT_BYTES, cfg.stream>>> (ga) ;
         else if (family == FAM_DOTR_BM_ISO)
             dotr_kernel<S, true, true> <<<cfg.grid, cfg.block, DOTR_BM_SMEM, cfg.stream>>> (ga) ;
         else
-            dotr_kernel<S, false, true> <<<cfg.grid, cfg.block, DOTR_BM_SMEM, cfg.stream>>> (ga) ;
+            dotr_kernel<S, false, true> <<<cfg.grid, cfg.block, DOTR_BM_SMEM + (DOTR_BM_THREADS / 32) * DOTR_HIT_BYTES, cfg.stream>>> (ga) ;
     }
     else if (family == FAM_DOTR_WARP || family == FAM_DOTR_WARP_ISO)
     {
         static bool attr_set = false ;          // one flag per instantiation
         if (!attr_set)
         {
-            cudaFuncSetAttribute (dotr_warp_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
+            cudaFuncSetAttribute (dotr_warp_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM + (DOTR_THREADS / 32) * DOTR_HIT_BYTES) ;
             cudaFuncSetAttribute (dotr_warp_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DOTG_SMEM) ;
             attr_set = true ;
         }
@@ -1056,7 +1056,7 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
         if (family == FAM_DOTR_WARP_ISO)
             dotr_warp_kernel<S, true> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
         else
-            dotr_warp_kernel<S, false> <<<cfg.grid, cfg.block, DOTG_SMEM, cfg.stream>>> (ga) ;
+            dotr_warp_kernel<S, false> <<<cfg.grid, cfg.block, DOTG_SMEM + (DOTR_THREADS / 32) * DOTR_HIT_BYTES, cfg.stream>>> (ga) ;
     }
     else if (family == FAM_DOTV)
         dotv_kernel<S> <<<cfg.grid, cfg.block, 0, cfg.stream>>> (*(const DotVArgs *) args) ;

@@ -28,6 +28,8 @@ constexpr int DOTR_BM_THREADS = 1024 ;          // bitmap instantiation (one blo
 constexpr int DOTR_BM_BYTES = 184 * 1024 ;      // bitmap (pattern-only) or bitmap + rank (valued)
 constexpr int DOTR_CUR_TASKS = DOTG_HUB_TASKS ; // cursors of one hub item: 2 bytes each
 constexpr int DOTR_BM_SMEM = DOTR_BM_BYTES + 2 * DOTR_CUR_TASKS ;
+constexpr int DOTR_HITS = 32 ;                  // valued operands: hits a warp collects before it loads their values
+constexpr int DOTR_HIT_BYTES = DOTR_HITS * 8 ;  // per warp: (position in the owner, offset in the walk) pairs
 constexpr int DOTR_MAXPARTS = 16 ;              // hub owners whose range needs more parts: dotg_kernel<HUB>
 constexpr int DOTR_REBUILDS = 30 ;
 
@@ -158,7 +160,7 @@ constexpr int DOTR_U_BITMAP = 8 ;     // ... against a bitmap part (hub tasks: ~
 
 template <class S, bool ISO, int MODE, class slot_t>
 __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, const void *table,
-    int *s_next, uint16_t *s_cur, int nwarps, unsigned long long &nm)
+    int *s_next, uint16_t *s_cur, uint2 *hb, int nwarps, unsigned long long &nm)
 {
     using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
     constexpr uint32_t NOKEY = 0xFFFFFFFEu ;
@@ -220,12 +222,29 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
             acc_t acc = Mon::identity () ;
             bool found = false ;
             int stop = tl ;             // BITMAP: where the next part resumes
+            int nbuf = 0 ;              // valued operands: hits noted in hb
+            // the noted hits' values: lane l loads the pair of hit l and keeps its product
+            auto flush = [&] (int n)
+            {
+                if constexpr (!ISO)
+                {
+                    __syncwarp () ;
+                    if (lane < n)
+                    {
+                        const uint2 h = hb [lane] ;
+                        const T ov = g.Ox [h.x], wv = g.Wx [tw + h.y] ;
+                        const acc_t prod = g.orient ? sr.product (ov, wv) : sr.product (wv, ov) ;
+                        acc = found ? Mon::combine (acc, prod) : prod ;
+                        found = true ;
+                    }
+                    __syncwarp () ;
+                }
+            } ;
             if (p0 < tl)
             {
                 const int32_t *__restrict__ rp = g.Wi + tw + p0 + lane ;    // this lane's index of row 0
-                const T *__restrict__ rx = g.Wx + tw + p0 + lane ;
                 int rem = tl - p0 - lane ;                                  // > 32 u: an index in row u
-                for (int p = p0 ; p < tl ; p += 32 * DOTR_U, rp += 32 * DOTR_U, rx += 32 * DOTR_U, rem -= 32 * DOTR_U)
+                for (int p = p0 ; p < tl ; p += 32 * DOTR_U, rp += 32 * DOTR_U, rem -= 32 * DOTR_U)
                 {
                     uint32_t k [DOTR_U] ;
                     #pragma unroll
@@ -239,13 +258,21 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
                         if (u >= 2 && (u & 1) == 0 && p + 32 * u >= tl) break ;  // warp-uniform
                         uint32_t pos = 0 ;
                         const uint32_t hit = dotr_probe<ISO, MODE> (q, tab, tab2, k [u], pos) ;
-                        if constexpr (ISO) cnt += hit ;
-                        else if (hit)
+                        cnt += hit ;
+                        if constexpr (!ISO)
                         {
-                            const T ov = g.Ox [pos], wv = rx [32 * u] ;
-                            const acc_t prod = g.orient ? sr.product (ov, wv) : sr.product (wv, ov) ;
-                            acc = found ? Mon::combine (acc, prod) : prod ;
-                            found = true ; cnt++ ;
+                            // valued operands: a hit is only NOTED here (where it is in the owner, where in
+                            // the walk); the values of up to 32 hits are loaded together by flush below.
+                            // Loading them row by row stalls the warp on two dependent loads per row with
+                            // ~4 of 32 lanes at work (measured: 3x the pattern-only time).
+                            const unsigned hm = __ballot_sync (FULL, hit) ;
+                            if (hm)
+                            {
+                                const int c = __popc (hm) ;
+                                if (nbuf + c > DOTR_HITS) { flush (nbuf) ; nbuf = 0 ; }
+                                if (hit) hb [nbuf + __popc (hm & ((1u << lane) - 1u))] = make_uint2 (pos, (uint32_t) (p + 32 * u + lane)) ;
+                                nbuf += c ;
+                            }
                         }
                     }
                     if constexpr (BITMAP)
@@ -267,10 +294,14 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
                     }
                     if constexpr (!ISO)
                         if (Mon::has_terminal ())
+                        {
+                            if (nbuf > 0) { flush (nbuf) ; nbuf = 0 ; }
                             if (__any_sync (FULL, found && Mon::is_terminal (acc))) break ;   // stop = tl: decided
+                        }
                 }
             }
             // ---- the task's result goes to the lane that keeps it --------------------------------
+            if constexpr (!ISO) { if (nbuf > 0) flush (nbuf) ; }
             const uint32_t tot = __reduce_add_sync (FULL, cnt) ;
             if constexpr (!ISO)
             {
@@ -366,6 +397,8 @@ dotr_kernel (DotGArgs a)
     const T *__restrict__ Oxb = orient ? Ax : Bx ;
     const int64_t vlen = a.A.vlen ;
     uint16_t *s_cur = (uint16_t *) (dotr_raw + DOTR_BM_BYTES) ;         // BITMAP only
+    // valued operands: the warp's hit buffer, behind the table (and the cursors)
+    uint2 *hb = ISO ? nullptr : (uint2 *) (dotr_raw + (BITMAP ? DOTR_BM_SMEM : DOTG_SMEM) + (threadIdx.x >> 5) * DOTR_HIT_BYTES) ;
     DotRCtx<S> g ;
     g.Wi = W.i ; g.Wx = orient ? Bx : Ax ;
     g.vals = (acc_t *) a.vals ; g.flags = a.flags ; g.orient = orient ;
@@ -415,9 +448,9 @@ dotr_kernel (DotGArgs a)
             }
             if (threadIdx.x == 0) s_next = 0 ;
             __syncthreads () ;
-            if (g.mode == DOTR_CUCKOO) dotr_walk<S, ISO, DOTR_CUCKOO, slot_t> (sr, g, dotr_raw, &s_next, nullptr, NW, nm) ;
-            else if (g.mode == DOTR_DENSE) dotr_walk<S, ISO, DOTR_DENSE, slot_t> (sr, g, dotr_raw, &s_next, nullptr, NW, nm) ;
-            else dotr_walk<S, ISO, DOTR_BSEARCH, slot_t> (sr, g, dotr_raw, &s_next, nullptr, NW, nm) ;
+            if (g.mode == DOTR_CUCKOO) dotr_walk<S, ISO, DOTR_CUCKOO, slot_t> (sr, g, dotr_raw, &s_next, nullptr, hb, NW, nm) ;
+            else if (g.mode == DOTR_DENSE) dotr_walk<S, ISO, DOTR_DENSE, slot_t> (sr, g, dotr_raw, &s_next, nullptr, hb, NW, nm) ;
+            else dotr_walk<S, ISO, DOTR_BSEARCH, slot_t> (sr, g, dotr_raw, &s_next, nullptr, hb, NW, nm) ;
         }
         else
         {
@@ -486,7 +519,7 @@ dotr_kernel (DotGArgs a)
                 __syncthreads () ;
                 g.lo = (uint32_t) lo ; g.nbits = (uint32_t) (hi - lo) ; g.hi = (int32_t) hi ;
                 g.last = (part == nparts - 1) ;
-                dotr_walk<S, ISO, DOTR_BITMAP, slot_t> (sr, g, dotr_raw, &s_next, s_cur, NW, nm) ;
+                dotr_walk<S, ISO, DOTR_BITMAP, slot_t> (sr, g, dotr_raw, &s_next, s_cur, hb, NW, nm) ;
             }
         }
     }
@@ -525,6 +558,7 @@ dotr_warp_kernel (DotGArgs a)
     const DMat &W = orient ? a.B : a.A ;        // walked matrix
     const T *__restrict__ Oxb = orient ? Ax : Bx ;
     slot_t *tab = (slot_t *) (dotr_raw + warp * DOTR_WARP_BYTES) ;
+    uint2 *hb = ISO ? nullptr : (uint2 *) (dotr_raw + DOTG_SMEM + warp * DOTR_HIT_BYTES) ;
     DotRCtx<S> g ;
     g.Wi = W.i ; g.Wx = orient ? Bx : Ax ;
     g.vals = (acc_t *) a.vals ; g.flags = a.flags ; g.orient = orient ;
@@ -586,8 +620,8 @@ dotr_warp_kernel (DotGArgs a)
         g.NS = NS ; g.sh = sh ; g.c1 = c1 ; g.c2 = c2 ;
         if (lane == 0) s_wnext [warp] = 0 ;
         __syncwarp () ;
-        if (g.mode == DOTR_CUCKOO) dotr_walk<S, ISO, DOTR_CUCKOO, slot_t> (sr, g, tab, s_wnext + warp, nullptr, 0, nm) ;
-        else dotr_walk<S, ISO, DOTR_BSEARCH, slot_t> (sr, g, tab, s_wnext + warp, nullptr, 0, nm) ;
+        if (g.mode == DOTR_CUCKOO) dotr_walk<S, ISO, DOTR_CUCKOO, slot_t> (sr, g, tab, s_wnext + warp, nullptr, hb, 0, nm) ;
+        else dotr_walk<S, ISO, DOTR_BSEARCH, slot_t> (sr, g, tab, s_wnext + warp, nullptr, hb, 0, nm) ;
     }
     for (int off = 16 ; off > 0 ; off >>= 1) nm += __shfl_down_sync (FULL, nm, off) ;
     if (lane == 0 && nm) atomicAdd (a.nmatch, nm) ;

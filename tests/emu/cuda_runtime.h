@@ -41,6 +41,8 @@ using std::isinf ;
 
 struct uint3 { unsigned x, y, z ; } ;
 struct dim3 { unsigned x, y, z ; dim3 (unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x (x_), y (y_), z (z_) { } } ;
+struct uint2 { unsigned x, y ; } ;
+static inline uint2 make_uint2 (unsigned x, unsigned y) { uint2 r = { x, y } ; return r ; }
 struct int4 { int x, y, z, w ; } ;
 static inline int4 make_int4 (int x, int y, int z, int w) { int4 r = { x, y, z, w } ; return r ; }
 typedef void *cudaStream_t ;
