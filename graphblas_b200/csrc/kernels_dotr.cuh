@@ -97,6 +97,7 @@ struct DotRProbe
     uint32_t lo, nbits ;                // bitmap part: indices [lo, lo + nbits); bit nbits is zero
     int32_t hi ;                        // bitmap: lo + nbits, or INT32_MAX for the owner's last part
     uint32_t c1, c2 ; int sh ;          // cuckoo
+    uint32_t NS ;                       // cuckoo: slots per table (the position tables start at 2 NS)
     const int32_t *Oi ; int olen ;      // BSEARCH
 } ;
 
@@ -129,11 +130,15 @@ __device__ __forceinline__ uint32_t dotr_probe (const DotRProbe &q, const SmemTa
         }
         else
         {
-            const uint64_t e1 = tab.ld64 ((kq * q.c1) >> q.sh) ;
-            const uint64_t e2 = tab2.ld64 ((kq * q.c2) >> q.sh) ;
-            const bool h1 = ((uint32_t) e1 == kq), h2 = ((uint32_t) e2 == kq) ;
-            pos = (uint32_t) ((h1 ? e1 : e2) >> 32) ;
-            return (h1 | h2) ? 1u : 0u ;
+            // valued operands: the same two key tables, and behind them two tables of positions that are
+            // read on a hit only (64-bit (index, position) slots doubled the shared-memory traffic of
+            // every probe, of which one in seven is a hit)
+            const uint32_t h1 = (kq * q.c1) >> q.sh, h2 = (kq * q.c2) >> q.sh ;
+            const uint32_t e1 = tab.ld (h1) ;
+            const uint32_t e2 = tab2.ld (h2) ;
+            const bool m1 = (e1 == kq), m2 = (e2 == kq) ;
+            if (m1 | m2) pos = tab.ld (2u * q.NS + (m1 ? h1 : (q.NS + h2))) ;
+            return (m1 | m2) ? 1u : 0u ;
         }
     }
     else if constexpr (MODE == DOTR_DENSE) { pos = kq ; return (kq != NOKEY) ? 1u : 0u ; }
@@ -170,10 +175,10 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
     const int lane = threadIdx.x & 31 ;
     const SmemTab tab (table) ;
     DotRProbe q ;
-    const SmemTab tab2 ((const char *) table + (size_t) g.NS * sizeof (slot_t)) ;   // cuckoo: the second table
+    const SmemTab tab2 ((const char *) table + (size_t) g.NS * sizeof (uint32_t)) ;  // cuckoo: the second table
     q.lo = g.lo ; q.nbits = g.nbits ;
     q.hi = g.last ? INT32_MAX : g.hi ;
-    q.c1 = g.c1 ; q.c2 = g.c2 ; q.sh = g.sh ; q.Oi = g.Oi ; q.olen = g.olen ;
+    q.c1 = g.c1 ; q.c2 = g.c2 ; q.sh = g.sh ; q.NS = (uint32_t) g.NS ; q.Oi = g.Oi ; q.olen = g.olen ;
     const bool cursors = BITMAP && g.multi ;
     while (true)
     {
@@ -344,28 +349,23 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
     }
 }
 
-// one pass of the cuckoo build (the same as dotg_kernel's); returns through *s_fail
-template <bool ISO, class slot_t>
-__device__ __forceinline__ void dotr_cuckoo_pass (slot_t *tab, const int32_t *__restrict__ Oi, int slen,
+// one pass of the cuckoo build (keys only: two tables of NS 32-bit slots); returns through *s_fail
+__device__ __forceinline__ void dotr_cuckoo_pass (uint32_t *tab, const int32_t *__restrict__ Oi, int slen,
     int NS, int sh, uint32_t c1, uint32_t c2, int *s_fail)
 {
-    constexpr slot_t EMPTY = (slot_t) ~(slot_t) 0 ;
+    constexpr uint32_t EMPTY = ~0u ;
     for (int t = threadIdx.x ; t < 2 * NS ; t += blockDim.x) tab [t] = EMPTY ;
     if (threadIdx.x == 0) *s_fail = 0 ;
     __syncthreads () ;
     for (int q = threadIdx.x ; q < slen ; q += blockDim.x)
     {
-        slot_t cur ;
-        if constexpr (ISO) cur = (uint32_t) __ldg (Oi + q) ;
-        else cur = ((uint64_t) (uint32_t) q << 32) | (uint32_t) __ldg (Oi + q) ;
+        uint32_t cur = (uint32_t) __ldg (Oi + q) ;
         int which = 0, n = 0 ;
         #pragma unroll 1
         for ( ; n < DOTG_MAXIT ; n++)
         {
-            const uint32_t k = (uint32_t) cur ;
-            const uint32_t loc = which ? (NS + ((k * c2) >> sh)) : ((k * c1) >> sh) ;
-            if constexpr (ISO) cur = atomicExch (tab + loc, cur) ;
-            else cur = atomicExch ((unsigned long long *) tab + loc, (unsigned long long) cur) ;
+            const uint32_t loc = which ? (NS + ((cur * c2) >> sh)) : ((cur * c1) >> sh) ;
+            cur = atomicExch (tab + loc, cur) ;
             if (cur == EMPTY) break ;
             which ^= 1 ;                        // the evicted entry moves to its other table
         }
@@ -374,12 +374,26 @@ __device__ __forceinline__ void dotr_cuckoo_pass (slot_t *tab, const int32_t *__
     __syncthreads () ;
 }
 
+// valued operands: once the keys have settled, entry q of the owner writes its position next to the slot
+// its key ended up in (tables 3 and 4: tab [2 NS + slot]); `stride` threads starting at `first` share the work
+__device__ __forceinline__ void dotr_cuckoo_positions (uint32_t *tab, const int32_t *__restrict__ Oi, int slen,
+    int NS, int sh, uint32_t c1, uint32_t c2, int first, int stride)
+{
+    for (int q = first ; q < slen ; q += stride)
+    {
+        const uint32_t k = (uint32_t) __ldg (Oi + q) ;
+        const uint32_t h1 = (k * c1) >> sh ;
+        const uint32_t slot = (tab [h1] == k) ? h1 : (NS + ((k * c2) >> sh)) ;
+        tab [2 * NS + slot] = (uint32_t) q ;
+    }
+}
+
 template <class S, bool ISO, bool BITMAP>
 __global__ void __launch_bounds__ (BITMAP ? DOTR_BM_THREADS : DOTR_THREADS, BITMAP ? 1 : (ISO ? 3 : 2))
 dotr_kernel (DotGArgs a)
 {
     using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
-    using slot_t = typename std::conditional<ISO, uint32_t, uint64_t>::type ;
+    using slot_t = uint32_t ;
     constexpr int NW = (BITMAP ? DOTR_BM_THREADS : DOTR_THREADS) / 32 ;
     extern __shared__ __align__ (16) unsigned char dotr_raw [] ;
     __shared__ int64_t s_ws [33] ;
@@ -436,7 +450,7 @@ dotr_kernel (DotGArgs a)
                 uint32_t c1 = 0x9E3779B1u, c2 = 0x85EBCA6Bu ;
                 for (int attempt = 0 ; ; attempt++)
                 {
-                    dotr_cuckoo_pass<ISO, slot_t> ((slot_t *) dotr_raw, g.Oi, olen, NS, sh, c1, c2, &s_fail) ;
+                    dotr_cuckoo_pass ((uint32_t *) dotr_raw, g.Oi, olen, NS, sh, c1, c2, &s_fail) ;
                     const bool failed = (s_fail != 0) ;
                     __syncthreads () ;          // everyone has read s_fail before it is reset
                     if (!failed) break ;
@@ -445,6 +459,9 @@ dotr_kernel (DotGArgs a)
                     c2 = (c2 * 0x01000193u + 0x4A8BE922u) | 1u ;
                 }
                 g.NS = NS ; g.sh = sh ; g.c1 = c1 ; g.c2 = c2 ;
+                if constexpr (!ISO)
+                    if (g.mode == DOTR_CUCKOO)
+                        dotr_cuckoo_positions ((uint32_t *) dotr_raw, g.Oi, olen, NS, sh, c1, c2, threadIdx.x, blockDim.x) ;
             }
             if (threadIdx.x == 0) s_next = 0 ;
             __syncthreads () ;
@@ -544,8 +561,8 @@ __global__ void __launch_bounds__ (DOTR_THREADS, ISO ? 3 : 2)
 dotr_warp_kernel (DotGArgs a)
 {
     using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
-    using slot_t = typename std::conditional<ISO, uint32_t, uint64_t>::type ;
-    constexpr slot_t EMPTY = (slot_t) ~(slot_t) 0 ;
+    using slot_t = uint32_t ;
+    constexpr slot_t EMPTY = ~0u ;
     constexpr unsigned FULL = 0xffffffffu ;
     extern __shared__ __align__ (16) unsigned char dotr_raw [] ;
     __shared__ int s_wnext [DOTR_THREADS / 32] ;
@@ -595,17 +612,13 @@ dotr_warp_kernel (DotGArgs a)
             bool bad = false ;
             for (int q = lane ; q < olen ; q += 32)
             {
-                slot_t cur ;
-                if constexpr (ISO) cur = (uint32_t) __ldg (g.Oi + q) ;
-                else cur = ((uint64_t) (uint32_t) q << 32) | (uint32_t) __ldg (g.Oi + q) ;
+                uint32_t cur = (uint32_t) __ldg (g.Oi + q) ;
                 int which = 0, n = 0 ;
                 #pragma unroll 1
                 for ( ; n < DOTG_MAXIT ; n++)
                 {
-                    const uint32_t k = (uint32_t) cur ;
-                    const uint32_t loc = which ? (NS + ((k * c2) >> sh)) : ((k * c1) >> sh) ;
-                    if constexpr (ISO) cur = atomicExch (tab + loc, cur) ;
-                    else cur = atomicExch ((unsigned long long *) tab + loc, (unsigned long long) cur) ;
+                    const uint32_t loc = which ? (NS + ((cur * c2) >> sh)) : ((cur * c1) >> sh) ;
+                    cur = atomicExch (tab + loc, cur) ;
                     if (cur == EMPTY) break ;
                     which ^= 1 ;                // the evicted entry moves to its other table
                 }
@@ -618,6 +631,8 @@ dotr_warp_kernel (DotGArgs a)
             c2 = (c2 * 0x01000193u + 0x4A8BE922u) | 1u ;
         }
         g.NS = NS ; g.sh = sh ; g.c1 = c1 ; g.c2 = c2 ;
+        if constexpr (!ISO)
+            if (g.mode == DOTR_CUCKOO) dotr_cuckoo_positions (tab, g.Oi, olen, NS, sh, c1, c2, lane, 32) ;
         if (lane == 0) s_wnext [warp] = 0 ;
         __syncwarp () ;
         if (g.mode == DOTR_CUCKOO) dotr_walk<S, ISO, DOTR_CUCKOO, slot_t> (sr, g, tab, s_wnext + warp, nullptr, hb, 0, nm) ;
