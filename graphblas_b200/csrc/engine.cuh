@@ -86,6 +86,7 @@ gb200_status group_end () ;
 void *dev_pool_alloc (size_t nbytes, size_t *capacity) ;     // nullptr: out of device memory
 void dev_pool_free (void *ptr, size_t capacity) ;
 void dev_pool_trim () ;                                      // give every cached block back to the driver
+void dev_pool_stats (int64_t *mallocs, int64_t *malloc_us) ; // trips to the driver so far
 
 struct DevBuf
 {

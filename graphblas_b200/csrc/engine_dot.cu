@@ -783,6 +783,9 @@ gb200_status gb200_AxB_device (gb200_result *out, gb200_dmatrix M, int mask_comp
     if (R == NULL) return GB200_OUT_OF_MEMORY ;
     memset (&R->info, 0, sizeof (R->info)) ;
     c.kev_used = 0 ;
+    int64_t pm0 = 0, pu0 = 0 ;
+    dev_pool_stats (&pm0, &pu0) ;
+    const auto tw0 = std::chrono::steady_clock::now () ;
     c.mask_policy = mask_policy ;
     c.method_request = method & 0xffff ;
     cudaEventRecord (c.ev0, c.stream) ;
@@ -812,6 +815,15 @@ gb200_status gb200_AxB_device (gb200_result *out, gb200_dmatrix M, int mask_comp
                 if (cudaEventElapsedTime (&t, c.kev [q], c.kev [q+1]) == cudaSuccess) kms += t ;
             }
             R->info.kernel_ms = kms ;
+            if (getenv ("GB200_TRACE") != nullptr)
+            {
+                int64_t pm1 = 0, pu1 = 0 ;
+                dev_pool_stats (&pm1, &pu1) ;
+                fprintf (stderr, "gb200_AxB_device: device %.3f ms (semiring kernels %.3f), host wall %.3f ms, "
+                    "%lld cudaMalloc calls taking %.3f ms\n", (double) ms, kms,
+                    std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - tw0).count (),
+                    (long long) (pm1 - pm0), (pu1 - pu0) * 1e-3) ;
+            }
         }
     }
     if (st != GB200_SUCCESS)
