@@ -497,10 +497,6 @@ gb200_status run_dot (gb200_result_s *R, const gb200_dmatrix_s *M, int mask_comp
             ga.vals = vals.ptr ; ga.flags = flags.as<uint8_t> () ;
             ga.nmatch = nmatch.as<unsigned long long> () ;
             ga.mult_op = s.mult_opcode ; ga.flip = s.flipxy ;
-            {
-                const char *pe = getenv ("GB200_DOTR_PIPE") ;
-                ga.pipe = (pe != nullptr && atoi (pe) == 0) ? 0 : 1 ;
-            }
             // ---- the owners' task runs of both orientations are cut into work items, one list per
             // owner class (hubs get big items) -----------------------------------------------------
             DotgClasses K [2] ;

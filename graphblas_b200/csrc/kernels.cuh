@@ -519,7 +519,6 @@ struct DotGArgs
                                         // host then recomputes the pairs with the table-free dot_kernel
     int64_t bm_bits ;                   // dotr_kernel<BITMAP>: indices per bitmap part (a multiple of 32)
     int mult_op ; int flip ;
-    int pipe ;                          // dotr_kernel<ISO, BITMAP>: software-pipelined row groups (GB200_DOTR_PIPE)
 } ;
 
 // stored-vector position of vector `name`, or -1

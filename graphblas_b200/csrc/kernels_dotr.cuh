@@ -62,7 +62,6 @@ template <class S> struct DotRCtx
     uint32_t c1, c2 ;
     uint32_t lo, nbits ;        // bitmap part: indices [lo, lo + nbits)
     int32_t hi ;                // lo + nbits
-    int pipe ;                  // bitmap, pattern-only: software-pipelined groups of rows
 } ;
 
 // The owner's table in shared memory, read through a 32-bit shared-memory address (ld.shared with a
@@ -246,46 +245,7 @@ __device__ __forceinline__ void dotr_walk (const S &sr, const DotRCtx<S> &g, con
                     __syncwarp () ;
                 }
             } ;
-            if (BITMAP && ISO && g.pipe && p0 < tl)
-            {
-                // hub owners, pattern-only: groups of DOTR_UP rows, the NEXT group's loads issued before the
-                // current group is probed, so that inside a task (17 rows on average) the latency of the
-                // walked list is paid once, not once per iteration
-                constexpr int DOTR_UP = 4 ;
-                const int32_t *__restrict__ rp = g.Wi + tw + p0 + lane ;
-                int rem = tl - p0 - lane ;
-                uint32_t k [DOTR_UP], kn [DOTR_UP] ;
-                #pragma unroll
-                for (int u = 0 ; u < DOTR_UP ; u++)
-                    k [u] = (rem > 32 * u) ? (uint32_t) __ldg (rp + 32 * u) : NOKEY ;
-                for (int p = p0 ; p < tl ; p += 32 * DOTR_UP, rp += 32 * DOTR_UP, rem -= 32 * DOTR_UP)
-                {
-                    #pragma unroll
-                    for (int u = 0 ; u < DOTR_UP ; u++)
-                        kn [u] = (rem > 32 * (DOTR_UP + u)) ? (uint32_t) __ldg (rp + 32 * (DOTR_UP + u)) : NOKEY ;
-                    #pragma unroll
-                    for (int u = 0 ; u < DOTR_UP ; u++)
-                    {
-                        if (u >= 2 && (u & 1) == 0 && p + 32 * u >= tl) break ;  // warp-uniform
-                        uint32_t pos = 0 ;
-                        cnt += dotr_probe<ISO, MODE> (q, tab, tab2, k [u], pos) ;
-                    }
-                    int32_t mx = (int32_t) k [0] ;
-                    #pragma unroll
-                    for (int u = 1 ; u < DOTR_UP ; u++) mx = ((int32_t) k [u] > mx) ? (int32_t) k [u] : mx ;
-                    if (__any_sync (FULL, mx >= q.hi))
-                    {
-                        stop = p + 32 * (DOTR_UP - 1) ;
-                        #pragma unroll
-                        for (int u = DOTR_UP - 2 ; u >= 0 ; u--)
-                            if (__any_sync (FULL, (int32_t) k [u] >= q.hi)) stop = p + 32 * u ;
-                        break ;
-                    }
-                    #pragma unroll
-                    for (int u = 0 ; u < DOTR_UP ; u++) k [u] = kn [u] ;
-                }
-            }
-            else if (p0 < tl)
+            if (p0 < tl)
             {
                 const int32_t *__restrict__ rp = g.Wi + tw + p0 + lane ;    // this lane's index of row 0
                 int rem = tl - p0 - lane ;                                  // > 32 u: an index in row u
@@ -459,7 +419,6 @@ dotr_kernel (DotGArgs a)
     g.ciso = Mon::identity () ;
     if (ISO) g.ciso = sr.product (Ax [0], Bx [0]) ;
     g.multi = false ; g.last = true ; g.lo = 0 ; g.nbits = 0 ; g.hi = INT32_MAX ;
-    g.pipe = a.pipe ;
     g.mode = DOTR_CUCKOO ; g.NS = 0 ; g.sh = 0 ; g.c1 = 0 ; g.c2 = 0 ;
     unsigned long long nm = 0 ;
     while (true)
@@ -622,7 +581,7 @@ dotr_warp_kernel (DotGArgs a)
     g.vals = (acc_t *) a.vals ; g.flags = a.flags ; g.orient = orient ;
     g.ciso = Mon::identity () ;
     if (ISO) g.ciso = sr.product (Ax [0], Bx [0]) ;
-    g.multi = false ; g.last = true ; g.lo = 0 ; g.nbits = 0 ; g.hi = INT32_MAX ; g.pipe = 0 ;
+    g.multi = false ; g.last = true ; g.lo = 0 ; g.nbits = 0 ; g.hi = INT32_MAX ;
     unsigned long long nm = 0 ;
     while (true)
     {

@@ -37,10 +37,9 @@ VARIANTS = [
     ("nostreams", {"GB200_DOT_STREAMS": "0"}),
     ("trim1", {"GB200_DOTG_TRIM": "1"}),
     ("nostreams_trim1", {"GB200_DOT_STREAMS": "0", "GB200_DOTG_TRIM": "1"}),
-    ("nopipe", {"GB200_DOTR_PIPE": "0"}),
 ]
 KEYS = ("GB200_DOTG_TRIM", "GB200_DOTG_HUB_CHUNK", "GB200_DOTG_CHUNK", "GB200_DOTG_ISO", "GB200_DOTR",
-        "GB200_DOTR_BM_BITS", "GB200_DOTR_TINY", "GB200_DOT_STREAMS", "GB200_DOTR_PIPE")
+        "GB200_DOTR_BM_BITS", "GB200_DOTR_TINY", "GB200_DOT_STREAMS")
 # the answer of the first measured run (profiles/r1_trim): a base that is itself wrong is noticed
 KNOWN = {22: (44374678, 2111700731)}
 
