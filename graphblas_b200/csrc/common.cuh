@@ -70,12 +70,14 @@ __device__ __forceinline__ int64_t bsearch_i32 (const int32_t *__restrict__ idx,
 // chain of dependent loads (B's index -> A's pointers -> A's entries) PER ENTRY and keeps as many lanes
 // busy as A's vector is long (Erdos-Renyi, 8 per vector: 8 lanes, 8 chains one after another; measured
 // 4.6 ms of a 8.0 ms multiply).  Must be called by all threads of the block; blockDim.x a multiple of 32.
+// warp, nwarps: which of how many warps share the vector (a warp on its own: 0 of 1)
 template <class F>
-__device__ __forceinline__ void for_each_product (const DMat &A, const DMat &B, int64_t pb0, int64_t pb1, F &&f)
+__device__ __forceinline__ void for_each_product_w (const DMat &A, const DMat &B, int64_t pb0, int64_t pb1,
+    int warp, int nwarps, F &&f)
 {
     constexpr unsigned FULL = 0xffffffffu ;
     constexpr int LONG = 64 ;       // a vector of A this long is walked by the whole warp on its own
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5 ;
+    const int lane = threadIdx.x & 31 ;
     // entries of B per chunk: a lone warp takes up to 32 at a time; the warps of a larger block get about
     // four chunks each, dealt round-robin, so that one chunk of long vectors does not hold the block up
     int64_t cs = (nwarps == 1) ? 32 : (pb1 - pb0 + 4 * nwarps - 1) / (4 * nwarps) ;
@@ -120,6 +122,12 @@ __device__ __forceinline__ void for_each_product (const DMat &A, const DMat &B, 
             if (t < total) f (pae + (t - oe), c0 + e) ;
         }
     }
+}
+
+template <class F>
+__device__ __forceinline__ void for_each_product (const DMat &A, const DMat &B, int64_t pb0, int64_t pb1, F &&f)
+{
+    for_each_product_w (A, B, pb0, pb1, (int) (threadIdx.x >> 5), (int) (blockDim.x >> 5), f) ;
 }
 
 __device__ __forceinline__ uint32_t hash32 (uint32_t k) { return k * 0x9E3779B1u ; }

@@ -862,9 +862,16 @@ gb200_status run_saxpy (gb200_result_s *R, const gb200_dmatrix_s *Min, int mask_
                 // a vlen-bit bitmap next to the table replaces the sort wherever scanning it costs less
                 // than sorting the vector (same rule as the pattern-only kernels above)
                 sa.nwords = use_bitmap (cl == 0 ? 0 : cl) ? symb_words : 0 ;
-                if (!launch_typed (s.xy_code, FAM_SAXPY_HASH, s.z_code, s.add_opcode, s.mult_opcode, &sa,
-                    grid_cap (cb.n [cl], (cl == 0) ? 32 : ((cl == 1) ? 8 : 1)), hash_threads [cl]))
-                { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
+                // the smallest class without a bitmap: a warp per vector, three warps per block
+                const char *hw_env = getenv ("GB200_SAXPY_HASH_WARP") ;
+                const bool warp_class = (cl == 0 && sa.nwords == 0 && hash_log [0] == HASHW_LOG
+                    && !(hw_env != nullptr && atoi (hw_env) == 0)) ;
+                const bool ok = warp_class
+                    ? launch_typed (s.xy_code, FAM_SAXPY_HASH_WARP, s.z_code, s.add_opcode, s.mult_opcode, &sa,
+                        grid_cap ((cb.n [cl] + HASHW_WARPS - 1) / HASHW_WARPS, 16), 32 * HASHW_WARPS)
+                    : launch_typed (s.xy_code, FAM_SAXPY_HASH, s.z_code, s.add_opcode, s.mult_opcode, &sa,
+                        grid_cap (cb.n [cl], (cl == 0) ? 32 : ((cl == 1) ? 8 : 1)), hash_threads [cl]) ;
+                if (!ok) { set_error ("no kernel for this semiring") ; return GB200_NOT_SUPPORTED ; }
             }
             sa.nwords = heavy_nwords ;
             for (int q = 3 ; q <= 4 ; q++)

@@ -217,6 +217,131 @@ __global__ void saxpy_hash_kernel (SaxpyArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same for vectors of C with at most 128 entries when no bitmap is used: a WARP per vector, several
+// independent warps per block.  With one 32-thread block per vector an SM holds 32 warps (the limit on
+// resident blocks), each running the chain B's pointers -> B's entries -> A's pointers -> A's entries ->
+// table -> sort -> write for one vector at a time; three warps per block and 16 blocks per SM give it
+// 48.  Everything is warp-synchronous (no block barrier); a warp's table is its own 4 KB of the block's
+// shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int HASHW_WARPS = 3 ;
+constexpr int HASHW_LOG = 8 ;
+
+template <class S> __host__ __device__ constexpr int hashw_bytes ()
+{
+    return (int) ((sizeof (typename S::acc_t) + 8) << HASHW_LOG) ;      // accumulators + keys + sort pairs
+}
+
+template <class S>
+__global__ void __launch_bounds__ (32 * HASHW_WARPS, 16)
+saxpy_hash_warp_kernel (SaxpyArgs a)
+{
+    using T = typename S::T ; using acc_t = typename S::acc_t ; using Mon = typename S::Mon ;
+    constexpr unsigned FULL = 0xffffffffu ;
+    constexpr int LOG = HASHW_LOG, size = 1 << LOG ;
+    constexpr uint32_t mask = (uint32_t) size - 1u ;
+    extern __shared__ __align__ (16) unsigned char hashw_raw [] ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5 ;
+    unsigned char *mine = hashw_raw + warp * hashw_bytes<S> () ;
+    acc_t *vals = (acc_t *) mine ;                              // size accumulators
+    uint64_t *comp = (uint64_t *) (vals + size) ;               // size / 2 (row << 32 | slot) pairs
+    int32_t *keys = (int32_t *) (comp + size / 2) ;             // size rows, -1 = free
+    const S sr (a.mult_op, a.flip != 0) ;
+    const T *__restrict__ Ax = (const T *) a.A.x ;
+    const T *__restrict__ Bx = (const T *) a.B.x ;
+    acc_t *__restrict__ acc = (acc_t *) a.acc ;
+    for (int64_t c = (int64_t) blockIdx.x * HASHW_WARPS + warp ; c < a.ncols ; c += (int64_t) gridDim.x * HASHW_WARPS)
+    {
+        const int64_t kk = a.cols [c] ;
+        const int64_t base = a.lp [kk] ;
+        if (a.lp [kk+1] <= base) continue ;                     // warp-uniform
+        for (int t = lane ; t < size ; t += 32) { keys [t] = -1 ; vals [t] = Mon::identity () ; }
+        __syncwarp () ;
+        for_each_product_w (a.A, a.B, a.B.p [kk], a.B.p [kk+1], 0, 1, [&] (int64_t p, int64_t pb)
+        {
+            const int32_t i = __ldg (a.A.i + p) ;
+            const acc_t prod = sr.product (Ax [p], Bx [pb]) ;
+            uint32_t h = (hash32 ((uint32_t) i) >> (32 - LOG)) & mask ;
+            while (true)
+            {
+                const int32_t old = atomicCAS (keys + h, -1, i) ;
+                if (old == -1 || old == i) { Mon::atomic_combine (vals + h, prod) ; break ; }
+                h = (h + 1) & mask ;
+            }
+        }) ;
+        __syncwarp () ;
+        // the occupied slots, counted with votes
+        int n = 0 ;
+        for (int t0 = 0 ; t0 < size ; t0 += 32)
+        {
+            const int32_t key = keys [t0 + lane] ;
+            const unsigned occ = __ballot_sync (FULL, key >= 0) ;
+            if (key >= 0) comp [n + __popc (occ & ((1u << lane) - 1u))] = ((uint64_t) (uint32_t) key << 32) | (uint32_t) (t0 + lane) ;
+            n += __popc (occ) ;
+        }
+        __syncwarp () ;
+        if (n <= 64)
+        {
+            // two per lane, sorted by a bitonic network of shuffles
+            uint64_t x0 = (lane < n) ? comp [lane] : ~0ULL ;
+            uint64_t x1 = (lane + 32 < n) ? comp [lane + 32] : ~0ULL ;
+            #pragma unroll
+            for (int k = 2 ; k <= 64 ; k <<= 1)
+            {
+                #pragma unroll
+                for (int j = k >> 1 ; j > 0 ; j >>= 1)
+                {
+                    if (j == 32)
+                    {
+                        if (x0 > x1) { const uint64_t y = x0 ; x0 = x1 ; x1 = y ; }
+                    }
+                    else
+                    {
+                        const uint64_t y0 = __shfl_xor_sync (FULL, x0, j), y1 = __shfl_xor_sync (FULL, x1, j) ;
+                        const bool low = ((lane & j) == 0) ;
+                        const bool asc0 = ((lane & k) == 0), asc1 = (((lane + 32) & k) == 0) ;
+                        x0 = ((x0 < y0) == (low == asc0)) ? x0 : y0 ;
+                        x1 = ((x1 < y1) == (low == asc1)) ? x1 : y1 ;
+                    }
+                }
+            }
+            if (lane < n) { a.Ci_out [base + lane] = (int32_t) (x0 >> 32) ; acc [base + lane] = vals [(uint32_t) x0] ; }
+            if (lane + 32 < n) { a.Ci_out [base + lane + 32] = (int32_t) (x1 >> 32) ; acc [base + lane + 32] = vals [(uint32_t) x1] ; }
+        }
+        else
+        {
+            // 65 .. 128 entries: the bitonic network over the warp's shared memory
+            for (int t = n + lane ; t < 128 ; t += 32) comp [t] = ~0ULL ;
+            __syncwarp () ;
+            for (int k = 2 ; k <= 128 ; k <<= 1)
+            {
+                for (int j = k >> 1 ; j > 0 ; j >>= 1)
+                {
+                    for (int t = lane ; t < 128 ; t += 32)
+                    {
+                        const int ixj = t ^ j ;
+                        if (ixj > t)
+                        {
+                            const uint64_t x = comp [t], y = comp [ixj] ;
+                            const bool asc = ((t & k) == 0) ;
+                            if ((x > y) == asc) { comp [t] = y ; comp [ixj] = x ; }
+                        }
+                    }
+                    __syncwarp () ;
+                }
+            }
+            for (int t = lane ; t < n ; t += 32)
+            {
+                const uint64_t v = comp [t] ;
+                a.Ci_out [base + t] = (int32_t) (v >> 32) ;
+                acc [base + t] = vals [(uint32_t) v] ;
+            }
+        }
+        __syncwarp () ;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // saxpy numeric, light vectors: one thread block (32..512 threads) per vector of B.  Warps take
 // entries B(k,j) round-robin, lanes stride over A(:,k).
 // ---------------------------------------------------------------------------------------------
@@ -969,7 +1094,7 @@ enum { FAM_SAXPY_LIGHT = 0, FAM_SAXPY_HEAVY = 1, FAM_DOT = 2, FAM_DOTG = 3, FAM_
     FAM_DOTV_LONG = 5, FAM_SAXPYV = 6, FAM_SAXPYV_LONG = 7, FAM_SPMV = 8, FAM_SPMV_PRES = 9,
     FAM_DOTG_ISO = 10, FAM_SPMV_OCC8 = 11, FAM_DOTG_HUB = 12, FAM_DOTG_HUB_ISO = 13,
     FAM_DOTR = 14, FAM_DOTR_ISO = 15, FAM_DOTR_BM = 16, FAM_DOTR_BM_ISO = 17, FAM_DOTR_WARP = 18,
-    FAM_DOTR_WARP_ISO = 19, FAM_SAXPY_HASH = 20, FAM_REDUCE = 21 } ;
+    FAM_DOTR_WARP_ISO = 19, FAM_SAXPY_HASH = 20, FAM_REDUCE = 21, FAM_SAXPY_HASH_WARP = 22 } ;
 
 struct LaunchCfg { int grid ; int block ; cudaStream_t stream ; } ;
 
@@ -998,6 +1123,16 @@ inline void launch_family (int family, const void *args, LaunchCfg cfg)
             attr_smem = smem ;
         }
         saxpy_hash_kernel<S> <<<cfg.grid, cfg.block, smem, cfg.stream>>> (sa) ;
+    }
+    else if (family == FAM_SAXPY_HASH_WARP)
+    {
+        static bool attr_set = false ;          // one flag per instantiation
+        if (!attr_set)
+        {
+            cudaFuncSetAttribute (saxpy_hash_warp_kernel<S>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) ;
+            attr_set = true ;
+        }
+        saxpy_hash_warp_kernel<S> <<<cfg.grid, cfg.block, HASHW_WARPS * hashw_bytes<S> (), cfg.stream>>> (*(const SaxpyArgs *) args) ;
     }
     else if (family == FAM_DOTG || family == FAM_DOTG_ISO || family == FAM_DOTG_HUB
         || family == FAM_DOTG_HUB_ISO)

@@ -306,7 +306,7 @@ typedef int cudaError_t ;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInsufficientDriver = 35, cudaErrorNoDevice = 100 } ;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault } ;
 enum { cudaStreamNonBlocking = 1 } ;
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 } ;
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 } ;
 struct cudaDeviceProp { char name [256] ; int major, minor, multiProcessorCount ; size_t totalGlobalMem ; } ;
 struct emuEvent { double ms ; } ;
 typedef emuEvent *cudaEvent_t ;

@@ -37,6 +37,9 @@ VARIANTS = [
     ("nostreams", {"GB200_DOT_STREAMS": "0"}),
     ("trim1", {"GB200_DOTG_TRIM": "1"}),
     ("nostreams_trim1", {"GB200_DOT_STREAMS": "0", "GB200_DOTG_TRIM": "1"}),
+    # the same T by the reference's other triangle-counting formulation: C<L> = L*L, masked saxpy
+    # (the "outer product" lines of BASELINE.md 1); SAXPY is read by this script, not by the library
+    ("masked_saxpy", {"SAXPY": "1"}),
 ]
 KEYS = ("GB200_DOTG_TRIM", "GB200_DOTG_HUB_CHUNK", "GB200_DOTG_CHUNK", "GB200_DOTG_ISO", "GB200_DOTR",
         "GB200_DOTR_BM_BITS", "GB200_DOTR_TINY", "GB200_DOT_STREAMS")
@@ -75,15 +78,18 @@ def main():
             continue
         for k in KEYS:
             os.environ.pop(k, None)
-        os.environ.update(env)
+        saxpy = env.get("SAXPY") == "1"
+        os.environ.update({k: v for k, v in env.items() if k != "SAXPY"})
         row = {"name": name, "env": env}
         try:
             ms, kms = [], []
+            mult = (lambda fetch: gb.axb_device(dL, False, dL, dL, sr, False, fetch=fetch)) if saxpy else \
+                   (lambda fetch: gb.axb_device(dL, False, dU, dL, sr, True, fetch=fetch))
             for _ in range(args.reps):
-                info = gb.axb_device(dL, False, dU, dL, sr, True, fetch=False).info
+                info = mult(False).info
                 ms.append(info["device_ms"])
                 kms.append(info["kernel_ms"])
-            res = gb.axb_device(dL, False, dU, dL, sr, True, fetch=True)
+            res = mult(True)
             T = res.matrix
             row.update(device_ms=ms, kernel_ms=kms, best_ms=min(ms), nnz_T=T.nnz,
                        madds=res.info["flops"], ntri=int(T.x.sum()))
