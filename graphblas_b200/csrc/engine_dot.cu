@@ -318,20 +318,44 @@ __device__ __forceinline__ int dotg_class_of (const DMat &O, const DMat &M, int 
 // set-up of one rank of an 8-GPU run.
 struct DotgItemLists { DotItem *items [4] ; unsigned long long *count ; } ;
 
-__global__ void dotg_items_all_kernel (DMat O, DMat M, int orient, DotgClasses K,
+__global__ void __launch_bounds__ (256)
+dotg_items_all_kernel (DMat O, DMat M, int orient, DotgClasses K,
     const int64_t *__restrict__ start, int64_t n, DotgItemLists L)
 {
-    for (int64_t v = blockIdx.x * (int64_t) blockDim.x + threadIdx.x ; v < n ;
-        v += (int64_t) gridDim.x * blockDim.x)
+    // A block takes 256 consecutive owners at a time and claims the room of their items with ONE atomic
+    // per class, so that inside such a stretch the items keep the owners' order (the items of one owner
+    // are contiguous, neighbouring owners are neighbours in the list): handing the items out in the
+    // order the threads' atomics arrived cost 28 % more DRAM traffic in the walk (36.1 GB against
+    // 28.3 GB per step; L2 hit 50 % against 56 %).
+    __shared__ int64_t s_ws [33] ;
+    __shared__ int64_t s_base [4] ;
+    const int64_t nblk = (n + blockDim.x - 1) / blockDim.x ;
+    for (int64_t blk = blockIdx.x ; blk < nblk ; blk += gridDim.x)
     {
-        const int64_t s0 = start [v], s1 = start [v+1] ;
-        if (s1 <= s0) continue ;
-        int cls = dotg_class_of (O, M, orient, v, K) ;
-        if (cls == 3 && K.tiny == 0) cls = 0 ;
-        if (cls == 1 && !K.flat) cls = 2 ;
-        const int64_t ch = K.chunk [cls] ;
-        const int64_t nch = (s1 - s0 + ch - 1) / ch ;
-        int64_t q = (int64_t) atomicAdd (L.count + cls, (unsigned long long) nch) ;
+        const int64_t v = blk * blockDim.x + threadIdx.x ;
+        int64_t s0 = 0, s1 = 0 ;
+        if (v < n) { s0 = start [v] ; s1 = start [v+1] ; }
+        int cls = -1 ;
+        int64_t ch = 1, nch = 0 ;
+        if (s1 > s0)
+        {
+            cls = dotg_class_of (O, M, orient, v, K) ;
+            if (cls == 3 && K.tiny == 0) cls = 0 ;
+            if (cls == 1 && !K.flat) cls = 2 ;
+            ch = K.chunk [cls] ;
+            nch = (s1 - s0 + ch - 1) / ch ;
+        }
+        int64_t q = 0 ;
+        for (int c = 0 ; c < 4 ; c++)
+        {
+            int64_t total ;
+            const int64_t off = block_excl_scan_i64 ((cls == c) ? nch : 0, s_ws, total) ;
+            if (threadIdx.x == 0 && total > 0)
+                s_base [c] = (int64_t) atomicAdd (L.count + c, (unsigned long long) total) ;
+            __syncthreads () ;
+            if (cls == c) q = s_base [c] + off ;
+            __syncthreads () ;
+        }
         for (int64_t e0 = s0 ; e0 < s1 ; e0 += ch, q++)
         {
             DotItem it ;
