@@ -322,17 +322,22 @@ __global__ void __launch_bounds__ (256)
 dotg_items_all_kernel (DMat O, DMat M, int orient, DotgClasses K,
     const int64_t *__restrict__ start, int64_t n, DotgItemLists L)
 {
-    // A warp takes 32 consecutive owners at a time and claims the room of their items with ONE atomic
-    // per class, so that the items of one owner are contiguous and neighbouring owners are neighbours in
-    // the list: handing the items out in the order the threads' atomics arrived cost DRAM traffic in the
-    // walk (36.1 GB per step against 32.5 GB with ordered stretches; L2 hit 50 % against 53 %).
+    // A block takes 256 consecutive owners at a time and claims the room of their items with ONE atomic
+    // per class, so that inside such a stretch the items keep the owners' order (the items of one owner
+    // are contiguous, neighbouring owners are neighbours in the list).  Handing the items out in the
+    // order the threads' (or warps') atomics arrived cost DRAM traffic and time in the walk: 36.1 GB and
+    // 21.9 ms per step against 32.5 GB and 21.7 ms (profiles/r2/tri_s22_dram_*.csv).  Stretches without
+    // tasks (most of them on one rank of an N-GPU run) and classes nobody holds cost two barriers.
     constexpr unsigned FULL = 0xffffffffu ;
+    __shared__ int64_t s_ws [33] ;
+    __shared__ int64_t s_base [4] ;
+    __shared__ unsigned s_mask [2] ;
     const int lane = threadIdx.x & 31 ;
-    const int64_t wid = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5 ;
-    const int64_t nw = ((int64_t) gridDim.x * blockDim.x) >> 5 ;
-    for (int64_t v0 = wid * 32 ; v0 < n ; v0 += nw * 32)
+    const int64_t nblk = (n + blockDim.x - 1) / blockDim.x ;
+    int par = 0 ;
+    for (int64_t blk = blockIdx.x ; blk < nblk ; blk += gridDim.x, par ^= 1)
     {
-        const int64_t v = v0 + lane ;
+        const int64_t v = blk * blockDim.x + threadIdx.x ;
         int64_t s0 = 0, s1 = 0 ;
         if (v < n) { s0 = start [v] ; s1 = start [v+1] ; }
         int cls = -1 ;
@@ -345,24 +350,24 @@ dotg_items_all_kernel (DMat O, DMat M, int orient, DotgClasses K,
             ch = K.chunk [cls] ;
             nch = (s1 - s0 + ch - 1) / ch ;
         }
-        if (!__any_sync (FULL, cls >= 0)) continue ;
+        // which classes does the stretch hold (s_mask alternates between two words, so that a thread that
+        // is already in the next stretch does not clear the word a slower one still reads)
+        if (threadIdx.x == 0) s_mask [par] = 0u ;
+        __syncthreads () ;
+        const unsigned wm = __reduce_or_sync (FULL, (cls >= 0) ? (1u << cls) : 0u) ;
+        if (lane == 0 && wm) atomicOr (&s_mask [par], wm) ;
+        __syncthreads () ;
+        const unsigned present = s_mask [par] ;
+        if (!present) continue ;
         int64_t q = 0 ;
         for (int c = 0 ; c < 4 ; c++)
         {
-            if (!__any_sync (FULL, cls == c)) continue ;
-            const int64_t mine = (cls == c) ? nch : 0 ;
-            int64_t incl = mine ;
-            #pragma unroll
-            for (int o = 1 ; o < 32 ; o <<= 1)
-            {
-                const int64_t y = __shfl_up_sync (FULL, incl, o) ;
-                if (lane >= o) incl += y ;
-            }
-            const int64_t total = __shfl_sync (FULL, incl, 31) ;
-            int64_t base = 0 ;
-            if (lane == 0) base = (int64_t) atomicAdd (L.count + c, (unsigned long long) total) ;
-            base = __shfl_sync (FULL, base, 0) ;
-            if (cls == c) q = base + incl - mine ;
+            if (!((present >> c) & 1u)) continue ;
+            int64_t total ;
+            const int64_t off = block_excl_scan_i64 ((cls == c) ? nch : 0, s_ws, total) ;
+            if (threadIdx.x == 0) s_base [c] = (int64_t) atomicAdd (L.count + c, (unsigned long long) total) ;
+            __syncthreads () ;
+            if (cls == c) q = s_base [c] + off ;
         }
         for (int64_t e0 = s0 ; e0 < s1 ; e0 += ch, q++)
         {
