@@ -83,6 +83,8 @@ _SIGS = {
     "gb200_result_reduce": (_I, [_VP, _I, _VP]),
     "gb200_select_device": (_I, [_VP, _VP, _I, _I64]),
     "gb200_select_host": (_I, [_VP, _VP, _I, _I64]),
+    "gb200_transpose_device": (_I, [_VP, _VP, _I, _I, C.c_double]),
+    "gb200_transpose_host": (_I, [_VP, _VP, _I, _I, C.c_double]),
     "gb200_peerbuf_create": (_I, [_VP, _I64, _I, _I, _I]),
     "gb200_peerbuf_handle": (_I, [_VP, _VP]),
     "gb200_peerbuf_connect": (_I, [_VP, _VP]),
@@ -289,6 +291,29 @@ def select_host(A: Matrix, op: str, k: int = 0, pinned: bool = False) -> Result:
     ca = A.c()
     _check(lib.gb200_select_host(C.byref(rh), C.byref(ca), SELECT_OPS[op], k), "gb200_select_host")
     return _fetch(rh, True, pinned)
+
+
+def transpose_host(A: Matrix, ctype: Optional[str] = None, hyper: bool = False, hyper_ratio: float = -1.0,
+                   pinned: bool = False) -> Result:
+    """C = (ctype) A' on the device (gb200_transpose_host + fetch), reference Source/GB_transpose.c: in the
+    CSC-agnostic layout entry i of vector j becomes entry j of vector i; hyper: C lists only its
+    non-empty vectors; hyper_ratio >= 0: that form is then conformed as GB_to_hyper_conform would."""
+    rh = C.c_void_p()
+    ca = A.c()
+    code = TYPES[ctype][0] if ctype is not None else ca.type_code
+    _check(lib.gb200_transpose_host(C.byref(rh), C.byref(ca), code, int(hyper), float(hyper_ratio)),
+           "gb200_transpose_host")
+    return _fetch(rh, True, pinned)
+
+
+def transpose_device(A: DMatrix, ctype: Optional[str] = None, hyper: bool = False, hyper_ratio: float = -1.0,
+                     fetch: bool = True, pinned: bool = False) -> Result:
+    """the same with A already resident in HBM (gb200_transpose_device); fetch=False: timing only"""
+    rh = C.c_void_p()
+    code = TYPES[ctype][0] if ctype is not None else TYPES[A.host.type][0]
+    _check(lib.gb200_transpose_device(C.byref(rh), A._h, code, int(hyper), float(hyper_ratio)),
+           "gb200_transpose_device")
+    return _fetch(rh, fetch, pinned)
 
 
 def result_reduce(rh, type_: str, add: str = "PLUS"):

@@ -552,3 +552,117 @@ GrB_Info GB_reduce_to_scalar (void *c, const GrB_Type ctype, const GrB_BinaryOp 
     __atomic_fetch_add (&g_reduce_calls, 1, __ATOMIC_RELAXED) ;
     return (info) ;
 }
+
+/* -------------------------------------------------------------------------------------------------
+ * C = (ctype) A' (SURVEY.md 8f row f2): GB_transpose (reference Source/GB.h:2153-2162, body
+ * Source/GB_transpose.c:38-985) is interposed.  It is what GB_AxB_meta runs IN FRONT of the multiply for
+ * a transposed operand or a mask held in the other format (Source/GB_AxB_meta.c:203,247,311,328-337,355),
+ * and what GrB_transpose, GB_accum_mask, GB_eWise ... run for their own transposes.  Taken here: the
+ * out-of-place call C = A' (Chandle and A_in both given and different, GB_transpose.c:97-113) of the
+ * general case (avlen > 1, avdim > 1, anz > 0, :470) without an operator (or with the identity of A's own
+ * type, which the reference drops too, :213-220), built-in types, no pending work.  T comes from the
+ * device in the form the reference's method would have produced (quicksort: hypersparse, bucket: not;
+ * the memory estimate of :497-606 restated) already conformed by the rule of GB_to_hyper_conform; the
+ * reference's own GB_to_hyper_conform is then run on it as :968-975 does (it finds nothing to change).
+ * Everything else -- transposes in place, vectors, empty matrices, operators, user-defined types --
+ * goes to the reference's own GB_transpose untouched.
+ * ------------------------------------------------------------------------------------------------- */
+static int64_t g_transpose_calls = 0 ;
+static int64_t g_transpose_min = -1 ;       /* fewer entries than this: the host's own loop is faster */
+
+__attribute__ ((visibility ("default")))
+int64_t gb200_shim_transpose_calls (void) { return (g_transpose_calls) ; }
+
+__attribute__ ((visibility ("default")))
+void gb200_shim_transpose_min (int64_t nnz) { g_transpose_min = (nnz < 0) ? 0 : nnz ; }
+
+__attribute__ ((visibility ("default")))
+GrB_Info GB_transpose (GrB_Matrix *Chandle, GrB_Type ctype, const bool C_is_csc, const GrB_Matrix A_in,
+    const GrB_UnaryOp op_in, GB_Context Context)
+{
+    typedef GrB_Info (*fn_t) (GrB_Matrix *, GrB_Type, const bool, const GrB_Matrix, const GrB_UnaryOp,
+        GB_Context) ;
+    typedef GrB_Info (*conform_fn) (GrB_Matrix, GB_Context) ;
+    static fn_t orig = NULL ;
+    static conform_fn conform = NULL ;
+    if (orig == NULL) orig = (fn_t) host_symbol ("GB_transpose", (void *) GB_transpose) ;
+    if (conform == NULL) conform = (conform_fn) dlsym (RTLD_DEFAULT, "GB_to_hyper_conform") ;
+    if (orig == NULL) return (GrB_PANIC) ;
+    if (g_enabled < 0) g_enabled = (getenv ("GB200_SHIM_DISABLE") != NULL) ? 0 : 1 ;
+    if (g_transpose_min < 0)
+    {
+        const char *env = getenv ("GB200_TRANSPOSE_MIN_NNZ") ;
+        g_transpose_min = (env != NULL && atoll (env) >= 0) ? atoll (env) : 4096 ;
+    }
+    const GrB_Matrix A = A_in ;
+    int mine = g_enabled && conform != NULL && bind_host () && Chandle != NULL && A != NULL
+        && (*Chandle) != A && A->magic == GB_MAGIC && A->type != NULL && A->type->code < GB_UCT_code
+        && (ctype == NULL || ctype->code < GB_UCT_code)
+        && (op_in == NULL || (op_in->opcode == GB_IDENTITY_opcode && A->type == op_in->xtype))
+        && !GB_PENDING (A) && !GB_ZOMBIES (A) && A->vlen > 1 && A->vdim > 1
+        && GB_NNZ (A) > 0 && GB_NNZ (A) >= g_transpose_min ;
+    if (!mine) return (orig (Chandle, ctype, C_is_csc, A_in, op_in, Context)) ;
+    if (ctype == NULL || op_in != NULL) ctype = A->type ;          /* GB_transpose.c:203-220 */
+
+    /* which of the reference's two methods would run decides the form T starts out in (:482-606) */
+    int via_qsort = 1 ;
+    if (!A->is_hyper)
+    {
+        const int64_t anz = GB_NNZ (A), avlen = A->vlen ;
+        const size_t csize = ctype->size ;
+        double qusage = 0, qsort_memory = 0 ;
+        qusage += GBYTES (anz, sizeof (int64_t)) ;              /* Tj (A->i is not recycled) */
+        qusage += GBYTES (anz, sizeof (int64_t)) ;              /* Ti */
+        qsort_memory = qusage ;
+        qusage += GBYTES (anz, sizeof (int64_t)) ;              /* kwork of GB_builder */
+        qsort_memory = GB_IMAX (qsort_memory, qusage) ;
+        qusage -= GBYTES (anz, sizeof (int64_t)) ;              /* Tj freed */
+        qusage += GBYTES (anz, csize) ;                         /* T->x */
+        qsort_memory = GB_IMAX (qsort_memory, qusage) ;
+        double bucket_memory = GBYTES (avlen, sizeof (int64_t)) + GBYTES (anz, sizeof (int64_t))
+            + GBYTES (anz, csize) + GBYTES (avlen, sizeof (int64_t)) ;
+        via_qsort = (qsort_memory < bucket_memory) ;
+    }
+
+    gb200_matrix am ;
+    int64_t *tp_a = NULL ;
+    gb200_result r = NULL ;
+    gb200_status st = GB200_OUT_OF_MEMORY ;
+    if (as_abi (&am, A, &tp_a)) st = gb200_transpose_host (&r, &am, ctype->code, via_qsort, A->hyper_ratio) ;
+    free (tp_a) ;
+    /* nothing was changed: let the reference do it (and report what there is to report) */
+    if (st != GB200_SUCCESS) return (orig (Chandle, ctype, C_is_csc, A_in, op_in, Context)) ;
+    gb200_result_info f ;
+    gb200_result_get_info (r, &f) ;
+    GrB_Matrix T = NULL ;
+    (*Chandle) = NULL ;
+    GrB_Info info = host_create (&T, ctype, f.vlen, f.vdim, GB_Ap_malloc, C_is_csc,
+        GB_SAME_HYPER_AS (f.is_hyper), A->hyper_ratio, (f.nvec > 0) ? f.nvec : 1,
+        (f.nnz > 0) ? f.nnz : 1, true, Context) ;
+    if (info != GrB_SUCCESS) { gb200_result_free (&r) ; return (info) ; }
+    st = gb200_result_fetch (r, T->p, f.is_hyper ? T->h : NULL, T->i, T->x) ;
+    if (st != GB200_SUCCESS)
+    {
+        gb200_result_free (&r) ;
+        host_free (&T) ;
+        return ((st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC) ;
+    }
+    if (f.is_hyper) T->nvec = f.nvec ;
+    T->nvec_nonempty = f.nvec_nonempty ;
+    T->magic = GB_MAGIC ;
+    const int64_t *p_fetched = T->p ;
+    info = conform (T, Context) ;                                   /* GB_transpose.c:968-975 */
+    if (info != GrB_SUCCESS)
+    {
+        gb200_result_free (&r) ;
+        host_free (&T) ;
+        return (info) ;
+    }
+    /* the device copy of A' serves the multiply that follows (residency cache on), unless the
+     * reference's conform disagreed with the form T arrived in */
+    if (T->p == p_fetched && (T->is_hyper ? 1 : 0) == f.is_hyper) adopt_result (&r, T, &f) ;
+    else gb200_result_free (&r) ;
+    (*Chandle) = T ;
+    __atomic_fetch_add (&g_transpose_calls, 1, __ATOMIC_RELAXED) ;
+    return (GrB_SUCCESS) ;
+}

@@ -194,6 +194,22 @@ typedef enum
 gb200_status gb200_select_device (gb200_result *out, gb200_dmatrix A, int select_op, int64_t k) ;
 gb200_status gb200_select_host   (gb200_result *out, const gb200_matrix *A, int select_op, int64_t k) ;
 
+/* ---- C = (ctype) A' (reference Source/GB_transpose.c:38-985, the general case
+ * :470-985 with no operator: what Source/GB_AxB_meta.c:203,247,311,328-337,355 calls in front of the
+ * multiply for a transposed operand or a mask held in the other format).  In the CSC-agnostic terms of
+ * the matrix: entry i of vector j of A becomes entry j of vector i of C; C has vlen = A's vdim and
+ * vdim = A's vlen, ascending indices in every vector, A's values cast to ctype_code (a gb200_type_code
+ * of a built-in type) by the rule of GB_cast_array.  result_hyper: 1 = C hypersparse (only its non-empty
+ * vectors listed, what GB_builder returns in the quicksort method, GB_transpose.c:847-862), 0 = standard
+ * form (the bucket method, GB_transpose_bucket.c).  hyper_ratio >= 0: that form is then conformed by the
+ * rule of GB_to_hyper_conform (GB_transpose.c:968-975; Source/GB_to_hyper_test.c, GB_to_nonhyper_test.c)
+ * with this hyper_ratio, so that T arrives in its final form; hyper_ratio < 0: left as asked.  Jumbled
+ * vectors of A are fine.  A with 2^32-1 or more entries is declined (GB200_NOT_SUPPORTED). */
+gb200_status gb200_transpose_device (gb200_result *out, gb200_dmatrix A, int ctype_code, int result_hyper,
+    double hyper_ratio) ;
+gb200_status gb200_transpose_host   (gb200_result *out, const gb200_matrix *A, int ctype_code, int result_hyper,
+    double hyper_ratio) ;
+
 /* ---- GrB_reduce of a matrix to a scalar over a built-in monoid (reference
  * Source/GB_reduce_to_scalar.c:107-270).  add_opcode: a gb200_opcode naming the monoid (MIN MAX PLUS
  * TIMES, or LOR LAND LXOR EQ for bool; boolean renames as in gb200_semiring_canonical).  *scalar

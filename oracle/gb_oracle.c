@@ -616,6 +616,88 @@ int oracle_AxB (oresult *R, const omat *M, int mask_comp, const omat *A, const o
     return ok ? 0 : 1 ;
 }
 
+/* ---- GB_transpose, the general out-of-place case without an operator (Source/GB_transpose.c:470-985):
+ * C = (ctype) A'.  The entries are those of the bucket method (Source/GB_transpose_bucket.c: count the
+ * entries per index, cumulative sum, then walk A's vectors in order so that every vector of C comes out
+ * ascending); the form of C is the one the reference ends with: the method chosen by the memory estimate
+ * of GB_transpose.c:497-606 (quicksort -> GB_builder's hypersparse T, bucket -> standard) followed by
+ * GB_to_hyper_conform (Source/GB_to_hyper_conform.c:38-58, tests in GB_to_hyper_test.c and
+ * GB_to_nonhyper_test.c, in single precision as there).  Returns 0 on success, 1 out of memory. */
+int oracle_transpose (oresult *R, const omat *A, int ctype, double hyper_ratio)
+{
+    memset (R, 0, sizeof (*R)) ;
+    const int64_t anz = A->p [A->nvec], avlen = A->vlen, avdim = A->vdim ;
+    const size_t csize = tsize [ctype] ;
+    /* the form C starts out in */
+    bool c_hyper = true ;
+    if (!A->is_hyper)
+    {
+        double q = 0, qmax = 0 ;
+        q += ((double) anz * 8.0) / 1e9 ; q += ((double) anz * 8.0) / 1e9 ; qmax = q ;
+        q += ((double) anz * 8.0) / 1e9 ; if (q > qmax) qmax = q ;
+        q -= ((double) anz * 8.0) / 1e9 ; q += ((double) anz * (double) csize) / 1e9 ; if (q > qmax) qmax = q ;
+        double b = ((double) avlen * 8.0) / 1e9 + ((double) anz * 8.0) / 1e9
+            + ((double) anz * (double) csize) / 1e9 + ((double) avlen * 8.0) / 1e9 ;
+        c_hyper = (qmax < b) ;
+    }
+    int64_t *cnt = calloc ((size_t) avlen + 1, sizeof (int64_t)) ;
+    int64_t *w = malloc (((size_t) avlen + 1) * sizeof (int64_t)) ;
+    int64_t *Ci = malloc ((size_t) (anz > 0 ? anz : 1) * sizeof (int64_t)) ;
+    int64_t *src = malloc ((size_t) (anz > 0 ? anz : 1) * sizeof (int64_t)) ;
+    if (!cnt || !w || !Ci || !src) { free (cnt) ; free (w) ; free (Ci) ; free (src) ; return 1 ; }
+    for (int64_t p = 0 ; p < anz ; p++) cnt [A->i [p]]++ ;
+    int64_t run = 0, nonempty = 0 ;
+    for (int64_t i = 0 ; i < avlen ; i++) { w [i] = run ; run += cnt [i] ; if (cnt [i] > 0) nonempty++ ; }
+    for (int64_t k = 0 ; k < A->nvec ; k++)
+    {
+        const int64_t j = vecname (A, k) ;
+        for (int64_t p = A->p [k] ; p < A->p [k+1] ; p++)
+        {
+            const int64_t q = w [A->i [p]]++ ;
+            Ci [q] = j ; src [q] = p ;
+        }
+    }
+    /* values, cast entry by entry (GB_cast_array) */
+    void *cast = (ctype != A->type_code) ? cast_array (A->x, A->type_code, ctype, anz) : NULL ;
+    char *Cx = malloc ((size_t) (anz > 0 ? anz : 1) * csize) ;
+    if (Cx == NULL || (ctype != A->type_code && cast == NULL))
+    { free (cnt) ; free (w) ; free (Ci) ; free (src) ; free (cast) ; free (Cx) ; return 1 ; }
+    const char *from = (cast != NULL) ? (const char *) cast : (const char *) A->x ;
+    for (int64_t q = 0 ; q < anz ; q++) memcpy (Cx + q * csize, from + src [q] * csize, csize) ;
+    free (cast) ; free (src) ; free (w) ;
+    /* GB_to_hyper_conform */
+    {
+        const float n = (float) avlen, r = (float) hyper_ratio ;
+        const float k = (float) nonempty ;
+        if (!c_hyper) { if (n > 1 && k <= n * r) c_hyper = true ; }
+        else if (n <= 1 || k > n * r * 2) c_hyper = false ;
+    }
+    R->vlen = avdim ; R->vdim = avlen ; R->nnz = anz ; R->is_hyper = c_hyper ; R->type_code = ctype ;
+    R->i = Ci ; R->x = Cx ; R->nvec_nonempty = nonempty ;
+    if (c_hyper)
+    {
+        R->nvec = nonempty ;
+        R->p = malloc (((size_t) nonempty + 1) * sizeof (int64_t)) ;
+        R->h = malloc (((size_t) nonempty + 1) * sizeof (int64_t)) ;
+        if (!R->p || !R->h) { free (cnt) ; return 1 ; }
+        int64_t q = 0 ; run = 0 ;
+        for (int64_t i = 0 ; i < avlen ; i++)
+            if (cnt [i] > 0) { R->h [q] = i ; R->p [q++] = run ; run += cnt [i] ; }
+        R->p [q] = run ;
+    }
+    else
+    {
+        R->nvec = avlen ;
+        R->p = malloc (((size_t) avlen + 1) * sizeof (int64_t)) ;
+        if (!R->p) { free (cnt) ; return 1 ; }
+        run = 0 ;
+        for (int64_t i = 0 ; i < avlen ; i++) { R->p [i] = run ; run += cnt [i] ; }
+        R->p [avlen] = run ;
+    }
+    free (cnt) ;
+    return 0 ;
+}
+
 void oracle_free (oresult *R)
 {
     free (R->p) ; free (R->h) ; free (R->i) ; free (R->x) ;

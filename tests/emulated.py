@@ -14,7 +14,7 @@ _FUNCS = ("gb200_last_error", "gb200_version", "gb200_kernel_launches", "gb200_m
           "gb200_AxB_host", "gb200_result_get_info", "gb200_result_fetch", "gb200_result_free",
           "gb200_flopcount_device", "gb200_partition_by_flops", "gb200_semiring_canonical",
           "gb200_device_count", "gb200_timer_mark", "gb200_timer_elapsed_ms", "gb200_host_malloc",
-          "gb200_host_free", "gb200_host_trim")
+          "gb200_host_free", "gb200_host_trim", "gb200_select_host", "gb200_transpose_host")
 _lib = None
 
 
@@ -65,7 +65,9 @@ def swapped():
     """graphblas_b200.lib -> the emulated library, inside the with block"""
     import graphblas_b200 as gb
     emu, real = library(), gb.lib
-    for name in _FUNCS:
+    for name in tuple(_FUNCS) + tuple(getattr(gb, "_SIGS", {})):
+        if not hasattr(emu, name):
+            continue
         f, g = getattr(real, name), getattr(emu, name)
         g.restype = f.restype
         if f.argtypes is not None:

@@ -359,21 +359,8 @@ class GraphBLAS:
         self.shim.gb200_shim_select_calls.restype = C.c_int64
         return self.shim.gb200_shim_select_calls()
 
-    # ---- the seam itself: the reference's own GB_AxB_parallel (Source/GB.h:1522-1537) ---------
-    def seam_axb(self, M, mask_comp: bool, A, B, semiring: str, flipxy: bool, do_adotb: bool,
-                 method: int = GxB_DEFAULT):
-        """Calls the reference library's internal GB_AxB_parallel directly on GrB_Matrix handles and
-        returns (T as dict in the CSC-agnostic layout, method_used, mask_applied).  M, A, B must be
-        stored by column (import_CSC / import_HyperCSC) so that the handle's vectors are exactly the
-        seam's vectors."""
-        T = C.c_void_p()
-        used = C.c_int(0)
-        applied = C.c_bool(False)
-        fn = self.lib.GB_AxB_parallel
-        fn.restype = C.c_int
-        info = fn(C.byref(T), M, C.c_bool(mask_comp), A, B, self.obj(semiring), C.c_bool(flipxy),
-                  C.c_bool(do_adotb), C.c_int(method), C.byref(used), C.byref(applied), None)
-        self.ok(info, "GB_AxB_parallel")
+    def raw(self, T) -> dict:
+        """the raw content of a GrB_Matrix in the CSC-agnostic layout (header fields, p, h, i, x)"""
         hdr = _MatrixHeader.from_address(T.value)
         out = {"vlen": hdr.vlen, "vdim": hdr.vdim, "nvec": hdr.nvec, "is_hyper": bool(hdr.is_hyper),
                "nvec_nonempty": hdr.nvec_nonempty}
@@ -394,6 +381,53 @@ class GraphBLAS:
                     if nnz else np.zeros(0, dtype=np.int64))
         out["x"] = (np.frombuffer((C.c_char * (nnz * dt.itemsize)).from_address(hdr.x), dtype=dt,
                                   count=nnz).copy() if nnz else np.zeros(0, dtype=dt))
+        return out
+
+    # ---- GB_transpose (Source/GB.h:2153-2162), found through the GLOBAL symbol scope -------------
+    def seam_transpose(self, A, ctype, c_is_csc: bool):
+        """GB_transpose (&T, ctype, C_is_csc, A, NULL, NULL) as the reference's own callers reach it: the
+        shim's interposer when the shim is loaded (it forwards to the reference while switched off), the
+        reference's otherwise.  Returns the raw T."""
+        T = C.c_void_p()
+        fn = C.CDLL(None).GB_transpose
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_bool, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.ok(fn(C.byref(T), self.obj("GrB_" + ctype) if ctype else None, c_is_csc, A, None, None),
+                "GB_transpose")
+        out = self.raw(T)
+        out["is_csc"] = bool(_MatrixHeader.from_address(T.value).is_csc)
+        self.matrix_free(T)
+        return out
+
+    def transpose(self, Cm, M, accum, A, desc):
+        """GrB_transpose (Include/GraphBLAS.h): C<M> = accum (C, A')"""
+        self.ok(self.lib.GrB_transpose(Cm, M, self.obj(accum) if accum else None, A, desc), "GrB_transpose")
+
+    def shim_transpose_calls(self) -> int:
+        self.shim.gb200_shim_transpose_calls.restype = C.c_int64
+        return self.shim.gb200_shim_transpose_calls()
+
+    def shim_transpose_min(self, nnz: int) -> None:
+        """matrices with fewer entries are transposed by the host (default 4096)"""
+        self.shim.gb200_shim_transpose_min.argtypes = [C.c_int64]
+        self.shim.gb200_shim_transpose_min(nnz)
+
+    # ---- the seam itself: the reference's own GB_AxB_parallel (Source/GB.h:1522-1537) ---------
+    def seam_axb(self, M, mask_comp: bool, A, B, semiring: str, flipxy: bool, do_adotb: bool,
+                 method: int = GxB_DEFAULT):
+        """Calls the reference library's internal GB_AxB_parallel directly on GrB_Matrix handles and
+        returns (T as dict in the CSC-agnostic layout, method_used, mask_applied).  M, A, B must be
+        stored by column (import_CSC / import_HyperCSC) so that the handle's vectors are exactly the
+        seam's vectors."""
+        T = C.c_void_p()
+        used = C.c_int(0)
+        applied = C.c_bool(False)
+        fn = self.lib.GB_AxB_parallel
+        fn.restype = C.c_int
+        info = fn(C.byref(T), M, C.c_bool(mask_comp), A, B, self.obj(semiring), C.c_bool(flipxy),
+                  C.c_bool(do_adotb), C.c_int(method), C.byref(used), C.byref(applied), None)
+        self.ok(info, "GB_AxB_parallel")
+        out = self.raw(T)
         self.matrix_free(T)
         return out, used.value, bool(applied.value)
 

@@ -72,6 +72,24 @@ def axb(M, mask_comp, A, B, semiring: gb.Semiring, do_adotb=False, info=None) ->
     return out
 
 
+def transpose(A, ctype=None, hyper_ratio=0.0625, info=None) -> gb.Matrix:
+    """GB_transpose (&T, ctype, csc, A, NULL) restated: T in the form the reference ends with"""
+    r = _ORes()
+    ca = _om(A)
+    code = gb.TYPES[ctype][0] if ctype is not None else ca.type_code
+    lib().oracle_transpose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+    rc = lib().oracle_transpose(C.byref(r), C.byref(ca), code, hyper_ratio)
+    if rc != 0:
+        raise RuntimeError(f"oracle_transpose failed: {rc}")
+    tname, dt = gb.TYPE_BY_CODE[r.type_code]
+    out = gb.Matrix(r.vlen, r.vdim, _copy(r.p, r.nvec + 1, np.int64), _copy(r.i, r.nnz, np.int64),
+                    _copy(r.x, r.nnz, dt), _copy(r.h, r.nvec, np.int64) if r.is_hyper else None, tname)
+    if info is not None:
+        info.update(nvec_nonempty=r.nvec_nonempty, is_hyper=r.is_hyper)
+    lib().oracle_free(C.byref(r))
+    return out
+
+
 def flopcount(M, A, B):
     out = np.empty(B.nvec + 1, dtype=np.int64)
     cm = _om(M) if M is not None else None

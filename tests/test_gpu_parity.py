@@ -428,3 +428,128 @@ def test_reduce_to_scalar(G, type_, monoid, accum, fmt):
         assert abs(out[0] - out[1]) <= 64 * eps * np.abs(A.data.astype(np.float64)).sum()
     else:
         assert out[0] == out[1]
+
+# ---------------------------------------------------------------------------------------------
+# C = (ctype) A' on the device (row f2): the interposed GB_transpose sorts the entries on the GPU and
+# returns T in the form (hypersparse or not) the reference's own method + GB_to_hyper_conform produce
+# ---------------------------------------------------------------------------------------------
+def _transpose_cases():
+    """(name, scipy matrix held by column: vectors = columns, vlen = rows)"""
+    rng = np.random.default_rng(77)
+    out = [("er", gen.er(300, 420, 3000, 61)),
+           ("tall", gen.er(70000, 300, 5000, 62)),              # three radix passes; T hypersparse
+           ("wide", gen.er(40, 5000, 900, 63)),                 # one pass
+           ("wide_long", gen.er(2, 3000, 2500, 64))]
+    n = 1500
+    band = sp.diags([np.arange(1, n + 1.0), np.full(n - 1, 2.0), np.full(n - 7, 3.0)], [0, 1, -7], format="lil")
+    band[17, :] = 4.5                                           # a full row and a full column
+    band[:, 33] = 5.5
+    out.append(("band", band.tocsc()))
+    # between the two thresholds of GB_to_hyper_conform (n/16 < non-empty vectors of T <= n/8, n = 1600): T
+    # keeps the form its method gave it -- quicksort (few entries: hypersparse), bucket (many: not)
+    for name, nnz in (("between_qsort", 3000), ("between_bucket", 6000)):
+        rows = rng.choice(1600, 150, replace=False)
+        i = rows[rng.integers(0, 150, nnz)]
+        i[:150] = rows
+        j = rng.integers(0, 900, nnz)
+        m = sp.coo_matrix((rng.random(nnz) + 0.5, (i, j)), shape=(1600, 900)).tocsc()
+        m.sum_duplicates()
+        out.append((name, m))
+    return out
+
+
+@pytest.mark.parametrize("case", _transpose_cases(), ids=lambda c: c[0])
+@pytest.mark.parametrize("fmt", ["CSC", "HyperCSC"])
+@pytest.mark.parametrize("ctype", [None, "INT32", "BOOL"])
+def test_transpose_seam(G, case, fmt, ctype):
+    """raw T of GB_transpose (Source/GB.h:2153): form, vector list, pointers, pattern, values, type"""
+    from parity import import_sp
+    A = case[1].copy()
+    if "Hyper" in fmt:
+        A = A.tolil() ; A[:, ::3] = 0 ; A = A.tocsc() ; A.eliminate_zeros()
+    A.data = np.round(A.data * 3 - 2, 1)                         # negatives, fractions, some zeros for BOOL
+    out = []
+    for gpu in (False, True):
+        a = import_sp(G, A, "FP64", fmt)
+        if not REF_ONLY:
+            G.shim_transpose_min(0)
+        G.use_gpu(gpu and not REF_ONLY)
+        before = 0 if REF_ONLY else G.shim_transpose_calls()
+        try:
+            t = G.seam_transpose(a, ctype, True)
+        finally:
+            G.use_gpu(False)
+            if not REF_ONLY:
+                G.shim_transpose_min(4096)
+        if not REF_ONLY:
+            assert G.shim_transpose_calls() - before == (1 if gpu else 0), "the GPU transpose did not run"
+        G.matrix_free(a)
+        out.append(t)
+    ref, got = out
+    for k in ("vlen", "vdim", "is_hyper", "nvec", "nvec_nonempty", "type", "is_csc"):
+        assert ref[k] == got[k], f"{k}: ref {ref[k]} got {got[k]}"
+    assert np.array_equal(ref["p"], got["p"]), "vector pointers differ"
+    if ref["is_hyper"]:
+        assert np.array_equal(ref["h"], got["h"]), "vector list differs"
+    assert np.array_equal(ref["i"], got["i"]), "pattern differs"
+    assert np.array_equal(ref["x"], got["x"]), "values differ"
+    if case[0].startswith("between") and "Hyper" not in fmt and ctype is None:
+        assert ref["is_hyper"] == (case[0] == "between_qsort")
+
+
+@pytest.mark.parametrize("fmt,cfmt", [("CSR", "CSR"), ("CSC", "CSR"), ("HyperCSR", "CSC"), ("CSC", "HyperCSC")])
+def test_grb_transpose_with_mask_and_accum(G, fmt, cfmt):
+    """GrB_transpose C<!M> += A' through the unmodified API (Source/GrB_transpose.c:98-108 -> GB_transpose)"""
+    from parity import compare, export_csr, import_sp
+    A = gen.er(260, 340, 5000, 71)
+    Cinit = gen.er(340, 260, 1500, 72)
+    M = gen.er(340, 260, 9000, 73, np.bool_)
+    out = []
+    for gpu in (False, True):
+        a, c, m = import_sp(G, A, "FP32", fmt), import_sp(G, Cinit, "FP64", cfmt), import_sp(G, M, "BOOL", fmt)
+        d = G.descriptor(mask=GrB_SCMP)
+        G.use_gpu(gpu and not REF_ONLY)
+        before = 0 if REF_ONLY else G.shim_transpose_calls()
+        try:
+            G.transpose(c, m, "GrB_PLUS_FP64", a, d)
+            G.matrix_nvals(c)
+        finally:
+            G.use_gpu(False)
+        if gpu and not REF_ONLY:
+            assert G.shim_transpose_calls() - before >= 1, "the GPU transpose did not run"
+        out.append(export_csr(G, c))
+        for h in (a, m):
+            G.matrix_free(h)
+        G.descriptor_free(d)
+    ok, why = compare(out[0], out[1], "MIN")
+    assert ok, why
+
+
+@pytest.mark.parametrize("inp0,inp1", [(GrB_TRAN, GxB_DEFAULT), (GxB_DEFAULT, GrB_TRAN), (GrB_TRAN, GrB_TRAN)])
+@pytest.mark.parametrize("method", [GxB_AxB_GUSTAVSON, GxB_AxB_DOT])
+@pytest.mark.parametrize("fmt", ["CSR", "CSC"])
+def test_mxm_transposed_operands_on_device(G, inp0, inp1, method, fmt):
+    """the transposes GB_AxB_meta runs in front of the multiply (GB_AxB_meta.c:203-355), mask in the other
+    format included, on the device as well"""
+    n = 220
+    A = gen.er(n, n, 6000, 81, np.float64)
+    B = gen.er(n, n, 5500, 82, np.float64)
+    M = gen.er(n, n, 9000, 83, np.bool_)
+    if not REF_ONLY:
+        G.shim_transpose_min(0)
+    try:
+        before = 0 if REF_ONLY else G.shim_transpose_calls()
+        check_mxm(G, A=A, B=B, type_="FP64", semiring="GxB_PLUS_TIMES_FP64", M=M, fmt=fmt, inp0=inp0,
+                  inp1=inp1, method=method, cfmt="CSC" if fmt == "CSR" else "CSR")
+        calls = 0 if REF_ONLY else G.shim_transpose_calls() - before
+    finally:
+        if not REF_ONLY:
+            G.shim_transpose_min(4096)
+    # not every fold transposes (A'*B by dot products needs none): the whole parametrisation does
+    test_mxm_transposed_operands_on_device.calls = getattr(test_mxm_transposed_operands_on_device, "calls", 0) + calls
+
+
+def test_mxm_transposed_operands_used_the_device(G):
+    if REF_ONLY:
+        pytest.skip("reference only")
+    assert getattr(test_mxm_transposed_operands_on_device, "calls", 0) > 0

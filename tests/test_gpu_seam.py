@@ -400,3 +400,43 @@ def test_masked_dot_edge_cases():
     m13 = gb.Matrix.from_scipy(sp.csc_matrix(np.ones((1, 3), dtype=np.bool_)))
     assert_same(oracle_c.axb(m13, False, row, col, sr, True), gb.axb_host(m13, False, row, col, sr, True).matrix,
                 "PLUS", "1-by-3 result")
+
+
+# ---------------------------------------------------------------------------------------------
+# C = (ctype) A' through the C ABI (gb200_transpose_host, row f2) against the pinned restatement
+# ---------------------------------------------------------------------------------------------
+def _start_form(A: gb.Matrix, ctype) -> bool:
+    """the form the reference's method leaves T in before GB_to_hyper_conform (GB_transpose.c:482-606)"""
+    if A.h is not None:
+        return True
+    anz, csize = int(A.p[-1]), np.dtype(NPT[ctype or A.type]).itemsize
+    return max(24.0 * anz, (16.0 + csize) * anz) < 16.0 * A.vlen + (8.0 + csize) * anz
+
+
+@pytest.mark.parametrize("hyper", [False, True])
+@pytest.mark.parametrize("ctype", [None, "INT16", "BOOL", "FP32", "UINT64"])
+def test_transpose_matches_oracle(hyper, ctype):
+    from test_oracle import transpose_inputs
+    for name, S in transpose_inputs():
+        S = S.copy()
+        S.data = np.round(S.data * 300 - 150, 1)
+        S.data[::7] = np.inf
+        S.data[3::11] = np.nan
+        A = gb.Matrix.from_scipy(S.tocsc(), "FP64")
+        if hyper:
+            A = A.to_hyper()
+        ref = oracle_c.transpose(A, ctype)
+        got = gb.transpose_host(A, ctype, hyper=_start_form(A, ctype), hyper_ratio=0.0625)
+        assert_same(ref, got.matrix, "MIN", f"transpose {name}")
+        assert got.info["nvec_nonempty"] == int(np.count_nonzero(np.diff(ref.p)))
+
+
+def test_transpose_properties_rmat():
+    """at a size the oracle does not run at: (A')' == A bit for bit, and A' == A for the symmetric graph"""
+    A = gb.Matrix.from_scipy(gen.rmat_scipy(16, 16, weighted=True).tocsc(), "FP64")
+    L = gb.select_host(A, "TRIL", -1).matrix                        # not symmetric
+    T = gb.transpose_host(L, None, hyper=False).matrix
+    TT = gb.transpose_host(T, None, hyper=False).matrix
+    assert_same(L, TT, "MIN", "(L')'")
+    U = gb.select_host(A, "TRIU", 1).matrix
+    assert np.array_equal(T.p, U.p) and np.array_equal(T.i, U.i), "tril (A)' != triu (A) of a symmetric A"

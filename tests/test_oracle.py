@@ -300,3 +300,43 @@ def test_cfg1_exact_input_on_the_reference(G):
     T = oracle_c.axb(None, False, Am, Bm, gb.Semiring("PLUS", "TIMES", "FP64", flipxy=True))
     assert np.array_equal(T.p, ec["Ap"]) and np.array_equal(T.i, ec["Ai"])
     assert np.abs(T.x - ec["Ax"]).sum() <= 64 * np.finfo(np.float64).eps * np.abs(ec["Ax"]).sum()
+
+
+# ---------------------------------------------------------------------------------------------
+# GB_transpose (row f2): the restatement against the reference's own GB_transpose, raw T compared
+# ---------------------------------------------------------------------------------------------
+def transpose_inputs():
+    """(name, gb.Matrix held by column) -- the shapes the two methods and the conform rule split on"""
+    rng = np.random.default_rng(77)
+    out = [("er", gen.er(300, 420, 3000, 61)), ("tall", gen.er(70000, 300, 5000, 62)),
+           ("wide", gen.er(40, 5000, 900, 63)), ("two_rows", gen.er(2, 3000, 2500, 64))]
+    for name, nnz in (("between_qsort", 3000), ("between_bucket", 6000)):
+        rows = rng.choice(1600, 150, replace=False)
+        i = rows[rng.integers(0, 150, nnz)]
+        i[:150] = rows
+        m = sp.coo_matrix((rng.random(nnz) + 0.5, (i, rng.integers(0, 900, nnz))), shape=(1600, 900)).tocsc()
+        m.sum_duplicates()
+        out.append((name, m))
+    return out
+
+
+@pytest.mark.parametrize("case", transpose_inputs(), ids=lambda c: c[0])
+@pytest.mark.parametrize("hyper", [False, True])
+@pytest.mark.parametrize("ctype", [None, "INT16", "BOOL", "FP32"])
+def test_oracle_transpose_vs_reference(G, case, hyper, ctype):
+    S = case[1].copy()
+    S.data = np.round(S.data * 300 - 150, 1)            # beyond INT16's range never, fractions and signs yes
+    S.data[::7] = np.inf
+    S.data[3::11] = np.nan
+    A = gb.Matrix.from_scipy(S.tocsc(), "FP64")
+    if hyper:
+        A = A.to_hyper()
+    a = to_ref(G, A)
+    ref = G.seam_transpose(a, ctype, True)
+    G.matrix_free(a)
+    info = {}
+    got = oracle_c.transpose(A, ctype, info=info)
+    same(ref, got)
+    assert ref["nvec_nonempty"] == info["nvec_nonempty"]
+    if not hyper and ctype is None and case[0].startswith("between"):
+        assert ref["is_hyper"] == (case[0] == "between_qsort")
