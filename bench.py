@@ -32,6 +32,8 @@ GrB_mxm(C, L, NULL, GxB_PLUS_TIMES_INT64, L, U, desc{INP1=TRAN}) hands to GB_AxB
           reference is thread-safe for that, Demo/Program/pthread_demo.c)
   secondary : the same {value, roofline, e2e, t_api, parity, cpu_baseline} for the other configs of
           BASELINE.json on one GPU: unmasked C=A*A (saxpy) on RMAT, SSSP (mxv) and BFS (vxm) at scale 22
+  neighbours : lines of the components next to the path, each measured by its own tool in a
+          process of its own after everything else: the device transpose (row f2, tools/transpose_bench.py)
 
 N > 1 (torchrun, one rank per GPU): the mask's entries are split into N owner-aligned parts (the
 reference's own plan, GB_AxB_parallel.c:52); A and B are replicated; no data-path collective; the
@@ -1159,6 +1161,21 @@ SECONDARY = [
 # ---------------------------------------------------------------------------------------------
 # the reference arm: the compiled reference on the box's host cores, nothing of ours mapped
 # ---------------------------------------------------------------------------------------------
+def neighbour_transpose(args):
+    """SURVEY.md 8f row f2 beside the path: tools/transpose_bench.py (C = A' of L = tril (A,-1) of the headline
+    graph on the device: time, roofline, L' == U and (L')' == L bit for bit, oracle parity at scale 14) in a
+    process of its own, so that nothing it does can take the headline line down"""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "transpose_bench.py"), "--scale", str(args.scale),
+           "--ef", str(args.ef), "--check-scale", str(min(14, args.scale))]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            return {"metric": "GB_transpose on the device", "error": (r.stderr or r.stdout)[-400:]}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"metric": "GB_transpose on the device", "error": repr(e)}
+
+
 def reference_arm(args):
     import grbref
     C = pure_containers()
@@ -1213,6 +1230,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-api", action="store_true", help="skip the t_api leg")
     ap.add_argument("--no-secondary", action="store_true", help="only the headline workload")
+    ap.add_argument("--no-neighbours", action="store_true", help="skip the lines of the path's neighbours "
+                    "(the device transpose, SURVEY.md 8f row f2)")
     ap.add_argument("--secondary-scale", type=int, default=0, help="run the secondary workloads at "
                     "this scale instead of their own (quick checks)")
     ap.add_argument("--slab-gb", type=float, default=0.0, help="unmasked saxpy: budget (GiB) of one slab "
@@ -1275,6 +1294,8 @@ def main():
             except Exception as e:      # a secondary line must not take the headline down
                 sec.append({"config": cfg, "error": repr(e)})
         line["secondary"] = sec
+        if not args.no_neighbours:
+            line["neighbours"] = [neighbour_transpose(args)]
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
