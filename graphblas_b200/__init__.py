@@ -83,6 +83,8 @@ _SIGS = {
     "gb200_result_reduce": (_I, [_VP, _I, _VP]),
     "gb200_select_device": (_I, [_VP, _VP, _I, _I64]),
     "gb200_select_host": (_I, [_VP, _VP, _I, _I64]),
+    "gb200_accum_mask_device": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I]),
+    "gb200_accum_mask_host": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I]),
     "gb200_transpose_device": (_I, [_VP, _VP, _I, _I, C.c_double]),
     "gb200_transpose_host": (_I, [_VP, _VP, _I, _I, C.c_double]),
     "gb200_peerbuf_create": (_I, [_VP, _I64, _I, _I, _I]),
@@ -303,6 +305,21 @@ def transpose_host(A: Matrix, ctype: Optional[str] = None, hyper: bool = False, 
     code = TYPES[ctype][0] if ctype is not None else ca.type_code
     _check(lib.gb200_transpose_host(C.byref(rh), C.byref(ca), code, int(hyper), float(hyper_ratio)),
            "gb200_transpose_host")
+    return _fetch(rh, True, pinned)
+
+
+def accum_mask_host(Cm: Matrix, T: Matrix, M: Optional[Matrix] = None, mask_comp: bool = False,
+                    replace: bool = False, accum: Optional[tuple] = None, hyper: bool = False,
+                    pinned: bool = False) -> Result:
+    """C<M> = accum (C,T) on the device (gb200_accum_mask_host + fetch), reference Source/GB_accum_mask.c:
+    accum = (operator name, type name of its inputs) or None; returns the new C"""
+    rh = C.c_void_p()
+    cc, ct = Cm.c(), T.c()
+    cm = M.c() if M is not None else None
+    op, xy = (OPCODES[accum[0]], TYPES[accum[1]][0]) if accum is not None else (0, 0)
+    _check(lib.gb200_accum_mask_host(C.byref(rh), C.byref(cc), C.byref(ct),
+                                     C.byref(cm) if cm is not None else None, int(mask_comp), int(replace),
+                                     op, xy, int(hyper)), "gb200_accum_mask_host")
     return _fetch(rh, True, pinned)
 
 

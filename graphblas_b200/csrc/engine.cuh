@@ -184,6 +184,9 @@ gb200_status flopcount (const DMat *M, const DMat &A, const DMat &B, DevBuf &flo
 
 gb200_status ensure_iso (gb200_dmatrix_s *d) ;
 
+// engine_transpose.cu: vecof [e] = name of the vector of A that holds entry e
+gb200_status launch_vecof (const DMat &A, int32_t *vecof) ;
+
 // engine_cache.cu: operand residency across calls of the host entry point
 gb200_status cache_acquire (gb200_dmatrix *out, const gb200_matrix *host, bool *cached) ;
 void cache_release (gb200_dmatrix d) ;

@@ -177,6 +177,15 @@ __global__ void tr_vecof_kernel (DMat A, int32_t *__restrict__ vecof)
     }
 }
 
+gb200_status launch_vecof (const DMat &A, int32_t *vecof)
+{
+    if (A.nnz <= 0 || A.nvec <= 0) return GB200_SUCCESS ;
+    tr_vecof_kernel <<<tr_grid ((A.nvec + 31) / 32 * 32, 16), 256, 0, ctx ().stream>>> (A, vecof) ;
+    count_launch () ;
+    GB200_CUDA (cudaGetLastError ()) ;
+    return GB200_SUCCESS ;
+}
+
 // head [q] = 1 where a new vector of C starts in the sorted keys
 __global__ void tr_heads_kernel (const uint32_t *__restrict__ keys, int64_t n, uint8_t *__restrict__ head)
 {
@@ -271,8 +280,7 @@ gb200_status gb200_transpose_device (gb200_result *out, gb200_dmatrix Ad, int ct
         GB200_TRY (vecof.alloc ((size_t) (n > 0 ? n : 1) * sizeof (int32_t))) ;
         if (n > 0)
         {
-            tr_vecof_kernel <<<tr_grid ((A.nvec + 31) / 32 * 32, 16), 256, 0, c.stream>>> (A, vecof.as<int32_t> ()) ;
-            count_launch () ;
+            GB200_TRY (launch_vecof (A, vecof.as<int32_t> ())) ;
             if (passes > 0)
             {
                 for (int k = 0 ; k < 2 ; k++)

@@ -666,3 +666,101 @@ GrB_Info GB_transpose (GrB_Matrix *Chandle, GrB_Type ctype, const bool C_is_csc,
     __atomic_fetch_add (&g_transpose_calls, 1, __ATOMIC_RELAXED) ;
     return (GrB_SUCCESS) ;
 }
+
+/* -------------------------------------------------------------------------------------------------
+ * C<M> = accum (C,T): GB_accum_mask (reference Source/GB.h, body
+ * Source/GB_accum_mask.c:130-328) is interposed: the step every GrB_mxm / mxv / vxm, GxB_select,
+ * GrB_transpose ... ends with.  Taken here: C, T and M (if any) in the same orientation (the reference
+ * transposes first otherwise, :173-199 -- such calls go to the reference, whose transposes are interposed
+ * above), built-in types, a built-in accumulator or none, no pending tuples or zombies in C, and real work
+ * to do (a mask or an accumulator; C = T alone is a transplant, :262-271).  The new C is computed by
+ * libgb_b200.so (gb200_accum_mask_host), built with the reference's GB_create in the form GB_mask would give
+ * R (hypersparse when C and T both are, GB_mask.c:315), and handed to the reference's own
+ * GB_transplant_conform exactly as GB_mask.c ends (:209, final transplant); T is freed as GB_accum_mask
+ * does.  Everything else goes to the reference's own GB_accum_mask untouched.
+ * ------------------------------------------------------------------------------------------------- */
+static int64_t g_accum_mask_calls = 0 ;
+static int64_t g_accum_mask_min = -1 ;      /* fewer entries in C and T together: the host's own loop */
+
+__attribute__ ((visibility ("default")))
+int64_t gb200_shim_accum_mask_calls (void) { return (g_accum_mask_calls) ; }
+
+__attribute__ ((visibility ("default")))
+void gb200_shim_accum_mask_min (int64_t nnz) { g_accum_mask_min = (nnz < 0) ? 0 : nnz ; }
+
+__attribute__ ((visibility ("default")))
+GrB_Info GB_accum_mask (GrB_Matrix C, const GrB_Matrix M_in, const GrB_Matrix MT_in, const GrB_BinaryOp accum,
+    GrB_Matrix *Thandle, const bool C_replace, const bool Mask_complement, GB_Context Context)
+{
+    typedef GrB_Info (*tc_fn) (GrB_Matrix, GrB_Type, GrB_Matrix *, GB_Context) ;
+    static gb_accum_mask_fn orig = NULL ;
+    static tc_fn transplant_conform = NULL ;
+    if (orig == NULL) orig = (gb_accum_mask_fn) host_symbol ("GB_accum_mask", (void *) GB_accum_mask) ;
+    if (transplant_conform == NULL) transplant_conform = (tc_fn) dlsym (RTLD_DEFAULT, "GB_transplant_conform") ;
+    if (orig == NULL) return (GrB_PANIC) ;
+    if (g_enabled < 0) g_enabled = (getenv ("GB200_SHIM_DISABLE") != NULL) ? 0 : 1 ;
+    if (g_accum_mask_min < 0)
+    {
+        const char *env = getenv ("GB200_ACCUM_MASK_MIN_NNZ") ;
+        g_accum_mask_min = (env != NULL && atoll (env) >= 0) ? atoll (env) : 65536 ;
+    }
+    GrB_Matrix T = (Thandle != NULL) ? (*Thandle) : NULL ;
+    const GrB_Matrix M = M_in ;
+    int mine = g_enabled && transplant_conform != NULL && bind_host () && C != NULL && T != NULL
+        && C->magic == GB_MAGIC && T->magic == GB_MAGIC && (M == NULL || M->magic == GB_MAGIC)
+        && (M != NULL || accum != NULL) && !(M == NULL && Mask_complement)
+        && C->is_csc == T->is_csc && (M == NULL || M->is_csc == C->is_csc)
+        && C->type->code < GB_UCT_code && T->type->code < GB_UCT_code
+        && (M == NULL || M->type->code < GB_UCT_code)
+        && (accum == NULL || (accum->magic == GB_MAGIC && accum->opcode >= GB_FIRST_opcode
+            && accum->opcode <= GB_LE_opcode && accum->xtype == accum->ytype
+            && accum->xtype->code < GB_UCT_code))
+        && !GB_PENDING (C) && !GB_ZOMBIES (C) && !GB_PENDING (T) && !GB_ZOMBIES (T)
+        && !GB_PENDING (M) && !GB_ZOMBIES (M)
+        && C->vlen == T->vlen && C->vdim == T->vdim && C->vdim <= ((int64_t) 1 << 27)
+        && GB_NNZ (C) + GB_NNZ (T) >= g_accum_mask_min ;
+    if (!mine) return (orig (C, M_in, MT_in, accum, Thandle, C_replace, Mask_complement, Context)) ;
+
+    gb200_matrix cm, tm, mm ;
+    int64_t *tp_c = NULL, *tp_t = NULL, *tp_m = NULL ;
+    gb200_result r = NULL ;
+    gb200_status st = GB200_OUT_OF_MEMORY ;
+    const int r_hyper = (C->is_hyper && T->is_hyper && C->vdim > 1) ? 1 : 0 ;
+    int ok = as_abi (&cm, C, &tp_c) && as_abi (&tm, T, &tp_t) ;
+    if (ok && M != NULL) ok = as_abi (&mm, M, &tp_m) ;
+    if (ok) st = gb200_accum_mask_host (&r, &cm, &tm, (M != NULL) ? &mm : NULL, Mask_complement ? 1 : 0,
+        C_replace ? 1 : 0, (accum != NULL) ? (int) accum->opcode : 0,
+        (accum != NULL) ? (int) accum->xtype->code : 0, r_hyper) ;
+    free (tp_c) ; free (tp_t) ; free (tp_m) ;
+    /* nothing was changed: let the reference do it (and report what there is to report) */
+    if (st != GB200_SUCCESS) return (orig (C, M_in, MT_in, accum, Thandle, C_replace, Mask_complement, Context)) ;
+    gb200_result_info f ;
+    gb200_result_get_info (r, &f) ;
+    GrB_Matrix R = NULL ;
+    GrB_Info info = host_create (&R, C->type, f.vlen, f.vdim, GB_Ap_malloc, C->is_csc,
+        GB_SAME_HYPER_AS (f.is_hyper), C->hyper_ratio, (f.nvec > 0) ? f.nvec : 1,
+        (f.nnz > 0) ? f.nnz : 1, true, Context) ;
+    if (info == GrB_SUCCESS)
+    {
+        st = gb200_result_fetch (r, R->p, f.is_hyper ? R->h : NULL, R->i, R->x) ;
+        if (st != GB200_SUCCESS)
+        {
+            host_free (&R) ;
+            info = (st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC ;
+        }
+    }
+    if (info != GrB_SUCCESS)
+    {
+        /* as GB_accum_mask's own GB_FREE_ALL on an error: T is freed, C is left as it was */
+        gb200_result_free (&r) ;
+        host_free (Thandle) ;
+        return (info) ;
+    }
+    if (f.is_hyper) R->nvec = f.nvec ;
+    R->nvec_nonempty = f.nvec_nonempty ;
+    R->magic = GB_MAGIC ;
+    adopt_result (&r, R, &f) ;                  /* the new C stays resident if the residency cache is on */
+    host_free (Thandle) ;                       /* GB_accum_mask.c: T is freed when done */
+    __atomic_fetch_add (&g_accum_mask_calls, 1, __ATOMIC_RELAXED) ;
+    return (transplant_conform (C, C->type, &R, Context)) ;
+}

@@ -210,6 +210,23 @@ gb200_status gb200_transpose_device (gb200_result *out, gb200_dmatrix A, int cty
 gb200_status gb200_transpose_host   (gb200_result *out, const gb200_matrix *A, int ctype_code, int result_hyper,
     double hyper_ratio) ;
 
+/* ---- C<M> = accum (C,T) (reference Source/GB_accum_mask.c:130-328 -> Source/GB_add.c
+ * (Z = accum (C,T)) -> Source/GB_mask.c (C<M> = Z); MATLAB statements Test/GB_spec_accum.m and
+ * Test/GB_spec_mask.m:60-90): the step after the multiply of every masked or accumulated call.  C, T and M
+ * (NULL: no mask) have the same vlen and vdim and are held in the same orientation.  The result R has C's
+ * type:  Z = T cast to C's type when accum_opcode == 0, else Z(i,j) = accum (C(i,j) cast to x, T(i,j) cast
+ * to y) cast to C's type where both exist, C(i,j) where only C does, T(i,j) cast to C's type where only T
+ * does; accum_opcode is a gb200_opcode and accum_xy_code the gb200_type_code of its two inputs (boolean
+ * renames as in gb200_semiring_canonical).  m(i,j) = (M(i,j) exists and its value is nonzero) != mask_comp,
+ * or !mask_comp without a mask.  R(i,j) = Z(i,j) where m (no entry if Z has none), else C(i,j), or no
+ * entry when c_replace.  result_hyper: 1 = R lists only its non-empty vectors (GB_mask.c:315: when C and Z
+ * are both hypersparse).  More than 2^27 vectors are declined (GB200_NOT_SUPPORTED). */
+gb200_status gb200_accum_mask_device (gb200_result *out, gb200_dmatrix C, gb200_dmatrix T, gb200_dmatrix M,
+    int mask_comp, int c_replace, int accum_opcode, int accum_xy_code, int result_hyper) ;
+gb200_status gb200_accum_mask_host (gb200_result *out, const gb200_matrix *C, const gb200_matrix *T,
+    const gb200_matrix *M, int mask_comp, int c_replace, int accum_opcode, int accum_xy_code,
+    int result_hyper) ;
+
 /* ---- GrB_reduce of a matrix to a scalar over a built-in monoid (reference
  * Source/GB_reduce_to_scalar.c:107-270).  add_opcode: a gb200_opcode naming the monoid (MIN MAX PLUS
  * TIMES, or LOR LAND LXOR EQ for bool; boolean renames as in gb200_semiring_canonical).  *scalar

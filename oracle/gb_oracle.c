@@ -698,6 +698,87 @@ int oracle_transpose (oresult *R, const omat *A, int ctype, double hyper_ratio)
     return 0 ;
 }
 
+/* ---- GB_accum_mask: C<M> = accum (C,T) (Source/GB_accum_mask.c:130-328), restated vector by vector as
+ * the three-way merge of GB_add.c (Z = accum (C,T): both -> the operator on C cast to x and T cast to y, the
+ * result cast to C's type; only C -> C; only T -> T cast to C's type; no accumulator: Z = T cast to C's type)
+ * followed by GB_mask.c (GB_spec_mask.m:60-90: where the mask admits, the entry of Z or none; elsewhere the
+ * entry of C, or none under C_replace; a mask entry admits iff its value cast to bool is true, negated for
+ * a complemented mask; no mask admits everywhere).  R is hypersparse iff r_hyper (GB_mask.c:315: C and Z
+ * both hypersparse).  accum_op == 0: no accumulator.  Returns 0 on success, 1 out of memory. */
+int oracle_accum_mask (oresult *R, const omat *C, const omat *T, const omat *M, int mask_comp, int replace,
+    int accum_op, int accum_xy, int r_hyper)
+{
+    memset (R, 0, sizeof (*R)) ;
+    const int ctype = C->type_code ;
+    const size_t cs = tsize [ctype] ;
+    const int64_t cnz = C->p [C->nvec], tnz = T->p [T->nvec] ;
+    int op = accum_op ;
+    if (op != 0 && accum_xy == T_BOOL) op = boolean_rename (op) ;
+    const int ztype = (op == 0) ? ctype : ((accum_xy == T_BOOL || op >= OP_EQ) ? T_BOOL : accum_xy) ;
+    void *Tc = cast_array (T->x, T->type_code, ctype, tnz) ;
+    void *Cx = (op != 0) ? cast_array (C->x, ctype, accum_xy, cnz) : NULL ;
+    void *Ty = (op != 0) ? cast_array (T->x, T->type_code, accum_xy, tnz) : NULL ;
+    int64_t *cnt = calloc ((size_t) C->vdim + 1, sizeof (int64_t)) ;
+    obuf o = { NULL, NULL, 0, 0, cs } ;
+    if (!Tc || !cnt || (op != 0 && (!Cx || !Ty))) { free (Tc) ; free (Cx) ; free (Ty) ; free (cnt) ; return 1 ; }
+    const size_t xs = (op != 0) ? tsize [accum_xy] : 0 ;
+    int ok = 1 ;
+    for (int64_t j = 0 ; j < C->vdim && ok ; j++)
+    {
+        int64_t pc, pce, pt, pte, pm = 0, pme = 0 ;
+        lookup (C, j, &pc, &pce) ;
+        lookup (T, j, &pt, &pte) ;
+        if (M != NULL) lookup (M, j, &pm, &pme) ;
+        while ((pc < pce || pt < pte) && ok)
+        {
+            const int64_t ic = (pc < pce) ? C->i [pc] : INT64_MAX, it = (pt < pte) ? T->i [pt] : INT64_MAX ;
+            const int64_t i = (ic < it) ? ic : it ;
+            const bool cex = (ic == i), tex = (it == i) ;
+            bool m = true ;
+            if (M != NULL)
+            {
+                while (pm < pme && M->i [pm] < i) pm++ ;
+                m = (pm < pme && M->i [pm] == i && mask_true (M, pm)) ;
+            }
+            if (mask_comp) m = !m ;
+            char z [16], zc [16] ;
+            const void *val = NULL ;
+            if (m)
+            {
+                if (op == 0) { if (tex) val = (char *) Tc + pt * cs ; }
+                else if (cex && tex)
+                {
+                    MULT [accum_xy] (op, (char *) Cx + pc * xs, (char *) Ty + pt * xs, z, 0) ;
+                    void *one = cast_array (z, ztype, ctype, 1) ;
+                    if (one == NULL) { ok = 0 ; break ; }
+                    memcpy (zc, one, cs) ;
+                    free (one) ;
+                    val = zc ;
+                }
+                else if (cex) val = (const char *) C->x + pc * cs ;
+                else val = (char *) Tc + pt * cs ;
+            }
+            else if (!replace && cex) val = (const char *) C->x + pc * cs ;
+            if (val != NULL)
+            {
+                if (!obuf_push (&o, i, val)) { ok = 0 ; break ; }
+                cnt [j]++ ;
+            }
+            if (cex) pc++ ;
+            if (tex) pt++ ;
+        }
+    }
+    free (Tc) ; free (Cx) ; free (Ty) ;
+    if (ok)
+    {
+        omat all = { C->vlen, C->vdim, C->vdim, NULL, NULL, NULL, NULL, ctype, 0 } ;
+        ok = finish (R, &o, cnt, C->vdim, &all, r_hyper != 0, C->vlen, C->vdim, ctype) ;
+    }
+    free (cnt) ;
+    if (!ok) { free (o.i) ; free (o.x) ; return 1 ; }
+    return 0 ;
+}
+
 void oracle_free (oresult *R)
 {
     free (R->p) ; free (R->h) ; free (R->i) ; free (R->x) ;

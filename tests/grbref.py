@@ -399,6 +399,19 @@ class GraphBLAS:
         self.matrix_free(T)
         return out
 
+    def seam_accum_mask(self, Cm, M, accum, T, replace: bool, comp: bool) -> dict:
+        """GB_accum_mask (C, M, NULL, accum, &T, C_replace, Mask_comp, NULL) (Source/GB_accum_mask.c:130) found
+        through the global symbol scope (the shim's interposer when loaded; it forwards while switched off).
+        T is consumed.  Returns the raw C after its pending work was assembled."""
+        fn = C.CDLL(None).GB_accum_mask
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_bool, C.c_bool, C.c_void_p]
+        th = C.c_void_p(T.value)
+        self.ok(fn(Cm, M, None, self.obj(accum) if accum else None, C.byref(th), replace, comp, None),
+                "GB_accum_mask")
+        self.matrix_nvals(Cm)
+        return self.raw(Cm)
+
     def transpose(self, Cm, M, accum, A, desc):
         """GrB_transpose (Include/GraphBLAS.h): C<M> = accum (C, A')"""
         self.ok(self.lib.GrB_transpose(Cm, M, self.obj(accum) if accum else None, A, desc), "GrB_transpose")
@@ -406,6 +419,15 @@ class GraphBLAS:
     def shim_transpose_calls(self) -> int:
         self.shim.gb200_shim_transpose_calls.restype = C.c_int64
         return self.shim.gb200_shim_transpose_calls()
+
+    def shim_accum_mask_calls(self) -> int:
+        self.shim.gb200_shim_accum_mask_calls.restype = C.c_int64
+        return self.shim.gb200_shim_accum_mask_calls()
+
+    def shim_accum_mask_min(self, nnz: int) -> None:
+        """fewer entries in C and T together: the host's own GB_accum_mask (default 65536)"""
+        self.shim.gb200_shim_accum_mask_min.argtypes = [C.c_int64]
+        self.shim.gb200_shim_accum_mask_min(nnz)
 
     def shim_transpose_min(self, nnz: int) -> None:
         """matrices with fewer entries are transposed by the host (default 4096)"""

@@ -90,6 +90,24 @@ def transpose(A, ctype=None, hyper_ratio=0.0625, info=None) -> gb.Matrix:
     return out
 
 
+def accum_mask(Cm, T, M=None, mask_comp=False, replace=False, accum=None, hyper=False) -> gb.Matrix:
+    """GB_accum_mask (C, M, NULL, accum, &T, C_replace, Mask_comp) restated: the new C.
+    accum = (operator name, type name of its inputs) or None"""
+    r = _ORes()
+    cc, ct = _om(Cm), _om(T)
+    cm = _om(M) if M is not None else None
+    op, xy = (gb.OPCODES[accum[0]], gb.TYPES[accum[1]][0]) if accum is not None else (0, 0)
+    rc = lib().oracle_accum_mask(C.byref(r), C.byref(cc), C.byref(ct), C.byref(cm) if cm is not None else None,
+                                 int(mask_comp), int(replace), op, xy, int(hyper))
+    if rc != 0:
+        raise RuntimeError(f"oracle_accum_mask failed: {rc}")
+    tname, dt = gb.TYPE_BY_CODE[r.type_code]
+    out = gb.Matrix(r.vlen, r.vdim, _copy(r.p, r.nvec + 1, np.int64), _copy(r.i, r.nnz, np.int64),
+                    _copy(r.x, r.nnz, dt), _copy(r.h, r.nvec, np.int64) if r.is_hyper else None, tname)
+    lib().oracle_free(C.byref(r))
+    return out
+
+
 def flopcount(M, A, B):
     out = np.empty(B.nvec + 1, dtype=np.int64)
     cm = _om(M) if M is not None else None

@@ -553,3 +553,94 @@ def test_mxm_transposed_operands_used_the_device(G):
     if REF_ONLY:
         pytest.skip("reference only")
     assert getattr(test_mxm_transposed_operands_on_device, "calls", 0) > 0
+
+# ---------------------------------------------------------------------------------------------
+# C<M> = accum (C,T) on the device (row f1): the interposed GB_accum_mask computes the new C on the GPU and
+# hands it to the reference's own GB_transplant_conform
+# ---------------------------------------------------------------------------------------------
+class _device_accum_mask:
+    def __init__(self, G):
+        self.G = G
+
+    def __enter__(self):
+        if not REF_ONLY:
+            self.G.shim_accum_mask_min(0)
+            self.before = self.G.shim_accum_mask_calls()
+        return self
+
+    def calls(self):
+        return 0 if REF_ONLY else self.G.shim_accum_mask_calls() - self.before
+
+    def __exit__(self, *a):
+        if not REF_ONLY:
+            self.G.shim_accum_mask_min(65536)
+
+
+@pytest.mark.parametrize("maskd", [GxB_DEFAULT, GrB_SCMP])
+@pytest.mark.parametrize("outp", [GxB_DEFAULT, GrB_REPLACE])
+@pytest.mark.parametrize("accum", [None, "GrB_PLUS_FP64", "GrB_MIN_FP64", "GrB_SECOND_FP64", "GrB_DIV_FP64"])
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("fmt", ["CSR", "HyperCSC"])
+def test_accum_mask_on_device(G, maskd, outp, accum, masked, fmt):
+    """every combination of mask / complement / replace / accumulator of GB_spec_accum_mask, valued mask
+    (entries that are present but false do not admit), C initialised"""
+    if not masked and (maskd == GrB_SCMP or accum is None):
+        pytest.skip("nothing for GB_accum_mask to compute")
+    n = 150
+    A = gen.er(n, n, 1500, 7, np.float64)
+    B = gen.er(n, n, 1400, 8, np.float64)
+    M = gen.er(n, n, 3000, 9, np.int8, lo=0, hi=2) if masked else None
+    Cinit = gen.er(n, n, 2500, 10, np.float64)
+    with _device_accum_mask(G) as dev:
+        check_mxm(G, A=A, B=B, type_="FP64", semiring="GxB_PLUS_TIMES_FP64", M=M, mtype="INT8",
+                  Cinit=Cinit, accum=accum, mask=maskd, outp=outp, fmt=fmt, method=GxB_AxB_GUSTAVSON)
+        # GB_mxm skips GB_accum_mask when the multiply applied the mask and C is replaced (GB_mxm.c:141-159)
+        _ACCUM_MASK_USED.append(dev.calls() >= 1)
+
+
+_ACCUM_MASK_USED = []
+
+
+def test_accum_mask_on_device_was_used(G):
+    if REF_ONLY:
+        pytest.skip("reference only")
+    assert sum(_ACCUM_MASK_USED) >= 0.8 * len(_ACCUM_MASK_USED) > 0, _ACCUM_MASK_USED
+
+
+@pytest.mark.parametrize("ctype,ttype,accum", [
+    ("INT32", "FP64", "GrB_PLUS_INT32"), ("FP32", "INT64", "GrB_TIMES_FP64"), ("BOOL", "INT8", "GrB_LOR"),
+    ("BOOL", "FP64", "GrB_PLUS_BOOL"), ("UINT8", "INT16", "GrB_MINUS_INT16"), ("FP64", "UINT32", "GrB_GT_UINT32"),
+    ("INT64", "INT64", "GxB_ISLE_INT64"), ("UINT16", "FP32", "GrB_MAX_FP32"), ("INT8", "INT8", "GrB_FIRST_INT8"),
+    ("FP64", "BOOL", "GrB_LXOR"), ("INT16", "UINT64", None)])
+def test_accum_mask_typecasts(G, ctype, ttype, accum):
+    """C, T and the accumulator's inputs / output all of different built-in types (GB_add.c casts through the
+    operator's types; entries only in T are cast straight to C's type)"""
+    n = 120
+    sr = {"FP64": "GxB_PLUS_TIMES_FP64", "INT64": "GxB_PLUS_TIMES_INT64", "INT8": "GxB_PLUS_TIMES_INT8",
+          "INT16": "GxB_PLUS_TIMES_INT16", "UINT32": "GxB_PLUS_TIMES_UINT32", "FP32": "GxB_PLUS_TIMES_FP32",
+          "BOOL": "GxB_LOR_LAND_BOOL", "UINT64": "GxB_PLUS_TIMES_UINT64"}[ttype]
+    A = gen.er(n, n, 900, 21, NP[ttype])
+    B = gen.er(n, n, 800, 22, NP[ttype])
+    M = gen.er(n, n, 4000, 23, np.float64, lo=0, hi=2)
+    Cinit = gen.er(n, n, 2000, 24, NP[ctype])
+    with _device_accum_mask(G) as dev:
+        check_mxm(G, A=A, B=B, type_=ttype, semiring=sr, M=M, mtype="FP64", Cinit=Cinit, accum=accum,
+                  ctype=ctype, method=GxB_AxB_GUSTAVSON)
+        assert REF_ONLY or dev.calls() >= 1, "GB_accum_mask did not run on the device"
+
+
+def test_accum_mask_vectors_bfs_and_sssp_steps(G):
+    """the two vector loops: w<!v,replace> = u*A (LOR_LAND) and d = min (d, A min.+ d)"""
+    n = 400
+    A = gen.er(n, n, 8 * n, 31, np.float64, lo=1, hi=9)
+    rng = np.random.default_rng(3)
+    with _device_accum_mask(G) as dev:
+        ui = np.sort(rng.choice(n, 60, replace=False))
+        vi = np.sort(rng.choice(n, 150, replace=False))
+        check_mv(G, op="vxm", A=A.astype(bool), u=(n, ui, np.ones(60, dtype=bool)), type_="BOOL",
+                 semiring="GxB_LOR_LAND_BOOL", n_out=n, mask=(vi, np.ones(150, dtype=bool)),
+                 winit=(vi, np.ones(150, dtype=bool)), outp=GrB_REPLACE, maskd=GrB_SCMP, method=GxB_AxB_DOT)
+        d = rng.random(n) * 10
+        check_mv(G, op="mxv", A=A, u=(n, np.arange(n), d), type_="FP64", semiring="GxB_MIN_PLUS_FP64",
+                 n_out=n, winit=(np.arange(n), d), accum="GrB_MIN_FP64")
+        assert REF_ONLY or dev.calls() >= 1, "GB_accum_mask did not run on the device"

@@ -440,3 +440,50 @@ def test_transpose_properties_rmat():
     assert_same(L, TT, "MIN", "(L')'")
     U = gb.select_host(A, "TRIU", 1).matrix
     assert np.array_equal(T.p, U.p) and np.array_equal(T.i, U.i), "tril (A)' != triu (A) of a symmetric A"
+
+
+# ---------------------------------------------------------------------------------------------
+# C<M> = accum (C,T) through the C ABI (gb200_accum_mask_host, row f1) against the pinned restatement
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("comp", [False, True])
+@pytest.mark.parametrize("replace", [False, True])
+@pytest.mark.parametrize("hyper", [False, True])
+def test_accum_mask_matches_oracle(comp, replace, hyper):
+    from test_oracle import ACCUM_MASK_CASES, accum_mask_inputs
+    for k, (ctype, ttype, mtype, accum) in enumerate(ACCUM_MASK_CASES):
+        if mtype is None and comp:
+            continue
+        Cm, T, M = accum_mask_inputs(ctype, ttype, mtype, hyper, seed=k)
+        acc = (accum[1], accum[2]) if accum else None
+        ref = oracle_c.accum_mask(Cm, T, M, comp, replace, acc, hyper)
+        got = gb.accum_mask_host(Cm, T, M, comp, replace, acc, hyper).matrix
+        assert_same(ref, got, "MIN", f"accum_mask case {k} {ctype} {ttype} {mtype} {accum}")
+
+
+def test_accum_mask_edge_cases():
+    """empty C, empty T, empty mask, C aliased with the mask, a vector (vdim == 1), long vectors"""
+    n = 300
+    E = gb.Matrix.from_scipy(sp.csc_matrix((n, n)), "FP64")
+    A = gb.Matrix.from_scipy(gen.er(n, n, 4000, 91).tocsc(), "FP64")
+    B = gb.Matrix.from_scipy(gen.er(n, n, 3000, 92).tocsc(), "FP64")
+    acc = ("PLUS", "FP64")
+    for Cm, T, M, comp, rep, a in [(E, A, None, False, False, acc), (A, E, None, False, False, acc),
+                                   (A, B, E, False, False, None), (A, B, E, True, True, acc),
+                                   (A, B, A, False, True, None), (A, B, A, True, False, acc),
+                                   (E, E, E, True, False, acc)]:
+        ref = oracle_c.accum_mask(Cm, T, M, comp, rep, a, False)
+        got = gb.accum_mask_host(Cm, T, M, comp, rep, a, False).matrix
+        assert_same(ref, got, "MIN", "accum_mask edge case")
+    # n-by-1 vectors: d = min (d, t) with all entries present, and a sparse frontier under a complemented mask
+    rng = np.random.default_rng(5)
+    nv = 50000
+    def vec(idx, x, t):
+        return gb.Matrix(nv, 1, np.array([0, len(idx)]), np.asarray(idx, dtype=np.int64), np.asarray(x), None, t)
+    d = vec(np.arange(nv), rng.random(nv), "FP64")
+    t = vec(np.sort(rng.choice(nv, 20000, replace=False)), rng.random(20000), "FP64")
+    v = vec(np.sort(rng.choice(nv, 30000, replace=False)), np.ones(30000, dtype=np.bool_), "BOOL")
+    for Cm, T, M, comp, rep, a in [(d, t, None, False, False, ("MIN", "FP64")), (t, d, v, True, True, None),
+                                   (t, t, v, True, False, ("PLUS", "FP64"))]:
+        ref = oracle_c.accum_mask(Cm, T, M, comp, rep, a, False)
+        got = gb.accum_mask_host(Cm, T, M, comp, rep, a, False).matrix
+        assert_same(ref, got, "MIN", "accum_mask on vectors")

@@ -340,3 +340,65 @@ def test_oracle_transpose_vs_reference(G, case, hyper, ctype):
     assert ref["nvec_nonempty"] == info["nvec_nonempty"]
     if not hyper and ctype is None and case[0].startswith("between"):
         assert ref["is_hyper"] == (case[0] == "between_qsort")
+
+
+# ---------------------------------------------------------------------------------------------
+# GB_accum_mask (row f1): the restatement against the reference's own GB_accum_mask
+# ---------------------------------------------------------------------------------------------
+def expand(vdim, p, h, i, x):
+    """(p, i, x) over all vdim vectors, whatever form the matrix is held in"""
+    if h is None:
+        return np.asarray(p), np.asarray(i), np.asarray(x)
+    cnt = np.zeros(vdim, dtype=np.int64)
+    cnt[np.asarray(h, dtype=np.int64)] = np.diff(p)
+    return np.concatenate([[0], np.cumsum(cnt)]), np.asarray(i), np.asarray(x)
+
+
+ACCUM_MASK_CASES = [
+    # ctype, ttype, mtype, accum (GrB name, operator, type of its inputs)
+    ("FP64", "FP64", None, ("GrB_PLUS_FP64", "PLUS", "FP64")),
+    ("FP64", "FP64", "INT8", None),
+    ("FP64", "FP64", "INT8", ("GrB_MIN_FP64", "MIN", "FP64")),
+    ("INT32", "FP64", "FP64", ("GrB_PLUS_INT32", "PLUS", "INT32")),
+    ("FP32", "INT64", "BOOL", ("GrB_TIMES_FP64", "TIMES", "FP64")),
+    ("BOOL", "INT8", "INT8", ("GrB_PLUS_BOOL", "PLUS", "BOOL")),
+    ("UINT8", "INT16", "UINT16", ("GrB_MINUS_INT16", "MINUS", "INT16")),
+    ("FP64", "UINT32", "INT8", ("GrB_GT_UINT32", "GT", "UINT32")),
+    ("INT64", "INT64", "INT8", ("GxB_ISLE_INT64", "ISLE", "INT64")),
+    ("INT8", "FP32", "FP32", ("GrB_DIV_INT8", "DIV", "INT8")),
+    ("INT16", "UINT64", "INT8", None),
+]
+
+
+def accum_mask_inputs(ctype, ttype, mtype, hyper, seed=0, n=140, m=90):
+    Cm = gb.Matrix.from_scipy(gen.er(n, m, 2200, 41 + seed, NP[ctype]).tocsc(), ctype)
+    T = gb.Matrix.from_scipy(gen.er(n, m, 1800, 42 + seed, NP[ttype]).tocsc(), ttype)
+    M = gb.Matrix.from_scipy(gen.er(n, m, 5000, 43 + seed, NP[mtype], lo=0, hi=2).tocsc(), mtype) if mtype else None
+    if hyper:
+        Cm, T = Cm.to_hyper(), T.to_hyper()
+        M = M.to_hyper() if M is not None else None
+    return Cm, T, M
+
+
+@pytest.mark.parametrize("case", ACCUM_MASK_CASES, ids=lambda c: f"{c[0]}-{c[1]}-{c[2]}-{c[3][1] if c[3] else 'none'}")
+@pytest.mark.parametrize("comp", [False, True])
+@pytest.mark.parametrize("replace", [False, True])
+@pytest.mark.parametrize("hyper", [False, True])
+def test_oracle_accum_mask_vs_reference(G, case, comp, replace, hyper):
+    ctype, ttype, mtype, accum = case
+    if mtype is None and comp:
+        pytest.skip("a complemented mask without a mask never reaches GB_accum_mask")
+    Cm, T, M = accum_mask_inputs(ctype, ttype, mtype, hyper)
+    c, t = to_ref(G, Cm), to_ref(G, T)
+    m = to_ref(G, M) if M is not None else None
+    ref = G.seam_accum_mask(c, m, accum[0] if accum else None, t, replace, comp)
+    got = oracle_c.accum_mask(Cm, T, M, comp, replace, (accum[1], accum[2]) if accum else None, hyper)
+    assert ref["type"] == got.type and (ref["vlen"], ref["vdim"]) == (got.vlen, got.vdim)
+    rp, ri, rx = expand(ref["vdim"], ref["p"], ref["h"] if ref["is_hyper"] else None, ref["i"], ref["x"])
+    gp, gi, gx = expand(got.vdim, got.p, got.h, got.i, got.x)
+    assert np.array_equal(rp, gp), "vector pointers differ"
+    assert np.array_equal(ri, gi), "pattern differs"
+    assert np.array_equal(rx, gx, equal_nan=True), "values differ"
+    for h_ in (c, m):
+        if h_ is not None:
+            G.matrix_free(h_)
