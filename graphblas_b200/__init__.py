@@ -96,6 +96,7 @@ _SIGS = {
     "gb200_peerbuf_read": (_I, [_VP, _VP, _VP]),
     "gb200_peerbuf_free": (_I, [_VP]),
     "gb200_cache_enable": (None, [_I]),
+    "gb200_cache_enabled": (_I, []),
     "gb200_cache_invalidate": (None, [_VP]),
     "gb200_cache_clear": (None, []),
     "gb200_cache_stats": (None, [_VP, _VP, _VP, _VP]),

@@ -276,6 +276,8 @@ using namespace gb200 ;
 extern "C" {
 #pragma GCC visibility push(default)
 
+int gb200_cache_enabled (void) { return cache_on () ? 1 : 0 ; }
+
 void gb200_cache_enable (int on)
 {
     cache ().enabled.store (on ? 1 : 0) ;

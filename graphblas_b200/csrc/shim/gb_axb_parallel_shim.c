@@ -592,7 +592,7 @@ GrB_Info GB_transpose (GrB_Matrix *Chandle, GrB_Type ctype, const bool C_is_csc,
     if (g_transpose_min < 0)
     {
         const char *env = getenv ("GB200_TRANSPOSE_MIN_NNZ") ;
-        g_transpose_min = (env != NULL && atoll (env) >= 0) ? atoll (env) : 4096 ;
+        g_transpose_min = (env != NULL && atoll (env) >= 0) ? atoll (env) : 65536 ;
     }
     const GrB_Matrix A = A_in ;
     int mine = g_enabled && conform != NULL && bind_host () && Chandle != NULL && A != NULL
@@ -680,13 +680,18 @@ GrB_Info GB_transpose (GrB_Matrix *Chandle, GrB_Type ctype, const bool C_is_csc,
  * does.  Everything else goes to the reference's own GB_accum_mask untouched.
  * ------------------------------------------------------------------------------------------------- */
 static int64_t g_accum_mask_calls = 0 ;
-static int64_t g_accum_mask_min = -1 ;      /* fewer entries in C and T together: the host's own loop */
+/* Fewer entries in C and T together than this: the reference's own host loop.  Unless set (environment
+ * GB200_ACCUM_MASK_MIN_NNZ or gb200_shim_accum_mask_min) the device is used from 65536 entries on while the
+ * residency cache is on -- T was just adopted by it and C usually is a result adopted earlier, so only the
+ * new C crosses PCIe -- and not at all while it is off: T and C would both be uploaded again right after T
+ * was fetched, which was not measured against the host's merge this round. */
+static int64_t g_accum_mask_min = -1 ;
 
 __attribute__ ((visibility ("default")))
 int64_t gb200_shim_accum_mask_calls (void) { return (g_accum_mask_calls) ; }
 
 __attribute__ ((visibility ("default")))
-void gb200_shim_accum_mask_min (int64_t nnz) { g_accum_mask_min = (nnz < 0) ? 0 : nnz ; }
+void gb200_shim_accum_mask_min (int64_t nnz) { g_accum_mask_min = nnz ; }    /* < 0: back to the default rule */
 
 __attribute__ ((visibility ("default")))
 GrB_Info GB_accum_mask (GrB_Matrix C, const GrB_Matrix M_in, const GrB_Matrix MT_in, const GrB_BinaryOp accum,
@@ -699,10 +704,12 @@ GrB_Info GB_accum_mask (GrB_Matrix C, const GrB_Matrix M_in, const GrB_Matrix MT
     if (transplant_conform == NULL) transplant_conform = (tc_fn) dlsym (RTLD_DEFAULT, "GB_transplant_conform") ;
     if (orig == NULL) return (GrB_PANIC) ;
     if (g_enabled < 0) g_enabled = (getenv ("GB200_SHIM_DISABLE") != NULL) ? 0 : 1 ;
-    if (g_accum_mask_min < 0)
+    int64_t min_nnz = g_accum_mask_min ;
+    if (min_nnz < 0)
     {
         const char *env = getenv ("GB200_ACCUM_MASK_MIN_NNZ") ;
-        g_accum_mask_min = (env != NULL && atoll (env) >= 0) ? atoll (env) : 65536 ;
+        if (env != NULL && atoll (env) >= 0) g_accum_mask_min = min_nnz = atoll (env) ;
+        else min_nnz = gb200_cache_enabled () ? 65536 : INT64_MAX ;
     }
     GrB_Matrix T = (Thandle != NULL) ? (*Thandle) : NULL ;
     const GrB_Matrix M = M_in ;
@@ -718,7 +725,7 @@ GrB_Info GB_accum_mask (GrB_Matrix C, const GrB_Matrix M_in, const GrB_Matrix MT
         && !GB_PENDING (C) && !GB_ZOMBIES (C) && !GB_PENDING (T) && !GB_ZOMBIES (T)
         && !GB_PENDING (M) && !GB_ZOMBIES (M)
         && C->vlen == T->vlen && C->vdim == T->vdim && C->vdim <= ((int64_t) 1 << 27)
-        && GB_NNZ (C) + GB_NNZ (T) >= g_accum_mask_min ;
+        && GB_NNZ (C) + GB_NNZ (T) >= min_nnz ;
     if (!mine) return (orig (C, M_in, MT_in, accum, Thandle, C_replace, Mask_complement, Context)) ;
 
     gb200_matrix cm, tm, mm ;

@@ -253,6 +253,7 @@ gb200_status gb200_result_adopt (gb200_result *r, const gb200_matrix *host) ;
  * sampled fingerprint of the host arrays no longer matches.  Off by default (GB200_OPERAND_CACHE=1 or
  * gb200_cache_enable (1)); bounded to a quarter of the device's memory (GB200_OPERAND_CACHE_MB). */
 void gb200_cache_enable (int on) ;
+int  gb200_cache_enabled (void) ;
 void gb200_cache_invalidate (const void *array) ;    /* any of p, h, i, x of a cached operand       */
 void gb200_cache_clear (void) ;
 void gb200_cache_stats (int64_t *hits, int64_t *misses, int64_t *invalidations, int64_t *resident_bytes) ;

@@ -94,7 +94,7 @@ def main():
     G.matrix_set_element(b, "FP64", int(B2.nonzero()[0][3]), int(B2.nonzero()[1][3]), 17.25)
     for k, d in enumerate(descs):
         check(G, a, b, n, f"transposed operands after setElement, descriptor {k}", d)
-    G.shim_transpose_min(4096)
+    G.shim_transpose_min(65536)
     G.shim_cache(False)
     print("cache_check: ok", G.shim_cache(), "device transposes", G.shim_transpose_calls() - t0)
 

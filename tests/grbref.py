@@ -425,12 +425,13 @@ class GraphBLAS:
         return self.shim.gb200_shim_accum_mask_calls()
 
     def shim_accum_mask_min(self, nnz: int) -> None:
-        """fewer entries in C and T together: the host's own GB_accum_mask (default 65536)"""
+        """fewer entries in C and T together: the host's own GB_accum_mask; < 0: the default rule (65536 while
+        the residency cache is on, never while it is off)"""
         self.shim.gb200_shim_accum_mask_min.argtypes = [C.c_int64]
         self.shim.gb200_shim_accum_mask_min(nnz)
 
     def shim_transpose_min(self, nnz: int) -> None:
-        """matrices with fewer entries are transposed by the host (default 4096)"""
+        """matrices with fewer entries are transposed by the host (default 65536)"""
         self.shim.gb200_shim_transpose_min.argtypes = [C.c_int64]
         self.shim.gb200_shim_transpose_min(nnz)
 

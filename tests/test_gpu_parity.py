@@ -480,7 +480,7 @@ def test_transpose_seam(G, case, fmt, ctype):
         finally:
             G.use_gpu(False)
             if not REF_ONLY:
-                G.shim_transpose_min(4096)
+                G.shim_transpose_min(65536)
         if not REF_ONLY:
             assert G.shim_transpose_calls() - before == (1 if gpu else 0), "the GPU transpose did not run"
         G.matrix_free(a)
@@ -508,6 +508,8 @@ def test_grb_transpose_with_mask_and_accum(G, fmt, cfmt):
     for gpu in (False, True):
         a, c, m = import_sp(G, A, "FP32", fmt), import_sp(G, Cinit, "FP64", cfmt), import_sp(G, M, "BOOL", fmt)
         d = G.descriptor(mask=GrB_SCMP)
+        if not REF_ONLY:
+            G.shim_transpose_min(0)
         G.use_gpu(gpu and not REF_ONLY)
         before = 0 if REF_ONLY else G.shim_transpose_calls()
         try:
@@ -515,6 +517,8 @@ def test_grb_transpose_with_mask_and_accum(G, fmt, cfmt):
             G.matrix_nvals(c)
         finally:
             G.use_gpu(False)
+            if not REF_ONLY:
+                G.shim_transpose_min(65536)
         if gpu and not REF_ONLY:
             assert G.shim_transpose_calls() - before >= 1, "the GPU transpose did not run"
         out.append(export_csr(G, c))
@@ -544,7 +548,7 @@ def test_mxm_transposed_operands_on_device(G, inp0, inp1, method, fmt):
         calls = 0 if REF_ONLY else G.shim_transpose_calls() - before
     finally:
         if not REF_ONLY:
-            G.shim_transpose_min(4096)
+            G.shim_transpose_min(65536)
     # not every fold transposes (A'*B by dot products needs none): the whole parametrisation does
     test_mxm_transposed_operands_on_device.calls = getattr(test_mxm_transposed_operands_on_device, "calls", 0) + calls
 
@@ -573,7 +577,7 @@ class _device_accum_mask:
 
     def __exit__(self, *a):
         if not REF_ONLY:
-            self.G.shim_accum_mask_min(65536)
+            self.G.shim_accum_mask_min(-1)
 
 
 @pytest.mark.parametrize("maskd", [GxB_DEFAULT, GrB_SCMP])
