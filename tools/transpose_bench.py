@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--check-scale", type=int, default=14)
     ap.add_argument("--out", default="")
+    ap.add_argument("--ab", action="store_true", help="also time the variants the environment switches select "
+                    "(GB200_TR_STAGED=0: direct scatter; GB200_TR_ISO=0: values gathered even for a pattern)")
     args = ap.parse_args()
     import graphblas_b200 as gb
     import bench
@@ -67,6 +69,23 @@ def main():
     T = gb.transpose_device(dL, None, hyper=False, fetch=True).matrix
     if not (np.array_equal(T.p, Up) and np.array_equal(T.i, Ui)):
         raise SystemExit("tril (A)' != triu (A) of the symmetric graph")
+    if args.ab:
+        variants = {}
+        for name, env in (("direct_scatter", {"GB200_TR_STAGED": "0"}), ("no_iso_shortcut", {"GB200_TR_ISO": "0"}),
+                          ("round_start", {"GB200_TR_STAGED": "0", "GB200_TR_ISO": "0"})):
+            os.environ.update(env)
+            t = []
+            for r in range(args.reps + 1):
+                res = gb.transpose_device(dL, None, hyper=False, fetch=(r == 0))
+                if r == 0:
+                    same = np.array_equal(res.matrix.p, T.p) and np.array_equal(res.matrix.i, T.i) \
+                        and np.array_equal(res.matrix.x, T.x)
+                else:
+                    t.append(res.info["device_ms"])
+            for k in env:
+                del os.environ[k]
+            variants[name] = {"env": env, "best_ms": min(t), "identical_T": bool(same)}
+        line["variants"] = variants
     dT = gb.DMatrix(T)
     TT = gb.transpose_device(dT, None, hyper=False, fetch=True).matrix
     if not (np.array_equal(TT.p, Lp) and np.array_equal(TT.i, Li) and np.array_equal(TT.x, Lx)):
