@@ -34,6 +34,7 @@ GrB_mxm(C, L, NULL, GxB_PLUS_TIMES_INT64, L, U, desc{INP1=TRAN}) hands to GB_AxB
           BASELINE.json on one GPU: unmasked C=A*A (saxpy) on RMAT, SSSP (mxv) and BFS (vxm) at scale 22
   neighbours : lines of the components next to the path, each measured by its own tool in a
           process of its own after everything else: the device transpose (row f2, tools/transpose_bench.py)
+          and the device accum / mask step (row f1, tools/accum_mask_bench.py)
 
 N > 1 (torchrun, one rank per GPU): the mask's entries are split into N owner-aligned parts (the
 reference's own plan, GB_AxB_parallel.c:52); A and B are replicated; no data-path collective; the
@@ -1161,19 +1162,26 @@ SECONDARY = [
 # ---------------------------------------------------------------------------------------------
 # the reference arm: the compiled reference on the box's host cores, nothing of ours mapped
 # ---------------------------------------------------------------------------------------------
-def neighbour_transpose(args):
-    """SURVEY.md 8f row f2 beside the path: tools/transpose_bench.py (C = A' of L = tril (A,-1) of the headline
-    graph on the device: time, roofline, L' == U and (L')' == L bit for bit, oracle parity at scale 14) in a
-    process of its own, so that nothing it does can take the headline line down"""
-    cmd = [sys.executable, os.path.join(ROOT, "tools", "transpose_bench.py"), "--scale", str(args.scale),
-           "--ef", str(args.ef), "--check-scale", str(min(14, args.scale))]
-    try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-        if r.returncode != 0:
-            return {"metric": "GB_transpose on the device", "error": (r.stderr or r.stdout)[-400:]}
-        return json.loads(r.stdout.strip().splitlines()[-1])
-    except Exception as e:
-        return {"metric": "GB_transpose on the device", "error": repr(e)}
+def neighbour_lines(args):
+    """SURVEY.md 8f rows f2 and f1 beside the path, each measured by its own tool in a process of its own (so
+    that nothing it does can take the headline line down): tools/transpose_bench.py (C = A' of L = tril (A,-1) of
+    the headline graph on the device: time, roofline, L' == U and (L')' == L bit for bit, oracle parity at scale
+    14, the reference's GB_transpose on the host at scale 20) and tools/accum_mask_bench.py (C<M> = accum (C,T):
+    three cases on resident operands, results checked, oracle parity, the reference's GB_accum_mask on the host)"""
+    out = []
+    for tool, metric in (("transpose_bench.py", "GB_transpose on the device"),
+                         ("accum_mask_bench.py", "GB_accum_mask on the device")):
+        cmd = [sys.executable, os.path.join(ROOT, "tools", tool), "--scale", str(args.scale),
+               "--ef", str(args.ef), "--check-scale", str(min(14, args.scale))]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            if r.returncode != 0:
+                out.append({"metric": metric, "error": (r.stderr or r.stdout)[-400:]})
+            else:
+                out.append(json.loads(r.stdout.strip().splitlines()[-1]))
+        except Exception as e:
+            out.append({"metric": metric, "error": repr(e)})
+    return out
 
 
 def reference_arm(args):
@@ -1295,7 +1303,7 @@ def main():
                 sec.append({"config": cfg, "error": repr(e)})
         line["secondary"] = sec
         if not args.no_neighbours:
-            line["neighbours"] = [neighbour_transpose(args)]
+            line["neighbours"] = neighbour_lines(args)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

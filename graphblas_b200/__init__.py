@@ -324,6 +324,18 @@ def accum_mask_host(Cm: Matrix, T: Matrix, M: Optional[Matrix] = None, mask_comp
     return _fetch(rh, True, pinned)
 
 
+def accum_mask_device(Cm: DMatrix, T: DMatrix, M: Optional[DMatrix] = None, mask_comp: bool = False,
+                      replace: bool = False, accum: Optional[tuple] = None, hyper: bool = False,
+                      fetch: bool = True, pinned: bool = False) -> Result:
+    """the same with C, T and M already resident in HBM (gb200_accum_mask_device); fetch=False: timing only"""
+    rh = C.c_void_p()
+    op, xy = (OPCODES[accum[0]], TYPES[accum[1]][0]) if accum is not None else (0, 0)
+    _check(lib.gb200_accum_mask_device(C.byref(rh), Cm._h, T._h, M._h if M is not None else None,
+                                       int(mask_comp), int(replace), op, xy, int(hyper)),
+           "gb200_accum_mask_device")
+    return _fetch(rh, fetch, pinned)
+
+
 def transpose_device(A: DMatrix, ctype: Optional[str] = None, hyper: bool = False, hyper_ratio: float = -1.0,
                      fetch: bool = True, pinned: bool = False) -> Result:
     """the same with A already resident in HBM (gb200_transpose_device); fetch=False: timing only"""

@@ -25,6 +25,36 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def cpu_reference(bench, scale, ef, dev, gpu_ms, gpu_nnz):
+    """the compiled reference's own GB_transpose (oracle/_ref, one thread: it is sequential,
+    Source/GB_transpose_bucket.c) on L at `scale`, timed alone"""
+    import ctypes as C
+    import time
+    import grbref
+    if not grbref.available():
+        return {"unavailable": "oracle/_ref not built"}
+    G = grbref.GraphBLAS.get(with_shim=False)
+    g = bench.build_rmat(scale, ef, dev)
+    (n, Lp, Li, Lx), _ = bench.tri_operands(g)
+    a = G.matrix_import("CSC", "INT64", n, n, Lp, Li, Lx)
+    fn = G.lib.GB_transpose
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_bool, C.c_void_p, C.c_void_p, C.c_void_p]
+    best = None
+    for _ in range(2):
+        T = C.c_void_p()
+        t0 = time.perf_counter()
+        G.ok(fn(C.byref(T), None, True, a, None, None), "GB_transpose")
+        dt = time.perf_counter() - t0
+        G.matrix_free(T)
+        best = dt if best is None else min(best, dt)
+    G.matrix_free(a)
+    nnz = int(Lp[-1])
+    return {"value": best * 1e3, "unit": "ms", "cores": 1, "kind": "reference",
+            "sample": f"GB_transpose of L at scale {scale} ({nnz} entries), best of 2",
+            "ns_per_entry": best * 1e9 / nnz, "gpu_ns_per_entry": gpu_ms * 1e6 / gpu_nnz}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=int, default=22)
@@ -32,6 +62,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--check-scale", type=int, default=14)
     ap.add_argument("--out", default="")
+    ap.add_argument("--cpu-scale", type=int, default=20, help="the reference's own GB_transpose on the host, on "
+                    "the same L at this scale (0: skip)")
     ap.add_argument("--ab", action="store_true", help="also time the variants the environment switches select "
                     "(GB200_TR_STAGED=0: direct scatter; GB200_TR_ISO=0: values gathered even for a pattern)")
     args = ap.parse_args()
@@ -102,6 +134,8 @@ def main():
                 roofline={"bound": "hbm", "achieved": algo / best / 1e6, "peak": peak_gbs, "unit": "GB/s",
                           "frac": algo / best / 1e6 / peak_gbs, "algorithmic_bytes": algo,
                           "moved_bytes_estimate": moved, "peak_source": peak_source})
+    if args.cpu_scale > 0:
+        line["cpu_baseline"] = cpu_reference(bench, min(args.cpu_scale, args.scale), args.ef, dev, best, nnz)
     out = json.dumps(line)
     print(out)
     if args.out:
