@@ -271,6 +271,12 @@ __global__ void tr_vecof_kernel (DMat A, int32_t *__restrict__ vecof)
 gb200_status launch_vecof (const DMat &A, int32_t *vecof)
 {
     if (A.nnz <= 0 || A.nvec <= 0) return GB200_SUCCESS ;
+    if (A.nvec == 1 && !A.hyper)
+    {
+        // an n-by-1 vector: every entry belongs to vector 0 (one warp would walk all of them in the kernel)
+        GB200_CUDA (cudaMemsetAsync (vecof, 0, (size_t) A.nnz * sizeof (int32_t), ctx ().stream)) ;
+        return GB200_SUCCESS ;
+    }
     tr_vecof_kernel <<<tr_grid ((A.nvec + 31) / 32 * 32, 16), 256, 0, ctx ().stream>>> (A, vecof) ;
     count_launch () ;
     GB200_CUDA (cudaGetLastError ()) ;
