@@ -408,6 +408,39 @@ GrB_Info GxB_Matrix_import_HyperCSC (GrB_Matrix *A, const GrB_Type type, GrB_Ind
 }
 
 /* -------------------------------------------------------------------------------------------------
+ * The neighbours of the multiply below (GB_select, GB_reduce_to_scalar, GB_transpose, GB_accum_mask) follow
+ * the decline rule of the seam: a call the device library does not take (GB200_NOT_SUPPORTED: outside the
+ * built-in space it implements -- nothing was done) goes to the reference's own function; a call it took
+ * and FAILED on (no device, a CUDA error, out of device memory) fails loudly with GrB_PANIC /
+ * GrB_OUT_OF_MEMORY and a message, exactly as GB_AxB_parallel above -- nothing is computed on the host
+ * behind the caller's back.  GB200_SHIM_FORWARD=1 turns that failure into a delegation (counted).
+ * Returns 1 when the caller is to forward the call to the reference, else 0 with *info set.
+ * ------------------------------------------------------------------------------------------------- */
+static int64_t g_neighbour_failed = 0, g_neighbour_forwarded = 0 ;
+
+__attribute__ ((visibility ("default")))
+void gb200_shim_neighbour_stats (int64_t *failed, int64_t *forwarded)
+{
+    if (failed) *failed = g_neighbour_failed ;
+    if (forwarded) *forwarded = g_neighbour_forwarded ;
+}
+
+static int neighbour_forward (const char *who, gb200_status st, GrB_Info *info)
+{
+    if (st == GB200_NOT_SUPPORTED) return (1) ;
+    __atomic_fetch_add (&g_neighbour_failed, 1, __ATOMIC_RELAXED) ;
+    if (getenv ("GB200_SHIM_FORWARD") != NULL)
+    {
+        __atomic_fetch_add (&g_neighbour_forwarded, 1, __ATOMIC_RELAXED) ;
+        return (1) ;
+    }
+    fprintf (stderr, "[gb_b200 shim] %s failed on the device (%s); set GB200_SHIM_FORWARD=1 to delegate such "
+        "calls to the host library\n", who, gb200_last_error ()) ;
+    (*info) = (st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC ;
+    return (0) ;
+}
+
+/* -------------------------------------------------------------------------------------------------
  * GxB_select with a built-in operator: GB_select (reference Source/GB.h:1185-1197,
  * body Source/GB_select.c:30-386) is interposed like GB_AxB_parallel.  Only the clean path is taken
  * here -- built-in operator and type, no pending work, checks passed: T = select (A,k) is computed by
@@ -476,7 +509,8 @@ GrB_Info GB_select (GrB_Matrix C, const bool C_replace, const GrB_Matrix M, cons
     free (tp_a) ;
     if (st != GB200_SUCCESS)
     {
-        /* nothing was changed: let the reference do it (and report what there is to report) */
+        GrB_Info fail = GrB_PANIC ;
+        if (!neighbour_forward ("GB_select", st, &fail)) return (fail) ;
         return (orig (C, C_replace, M, Mask_comp, accum, op, A, k, A_transpose, Context)) ;
     }
     gb200_result_info f ;
@@ -537,7 +571,12 @@ GrB_Info GB_reduce_to_scalar (void *c, const GrB_Type ctype, const GrB_BinaryOp 
     gb200_status st = GB200_OUT_OF_MEMORY ;
     if (as_abi (&am, A, &tp_a)) st = gb200_reduce_host (&am, reduce->op->opcode, s) ;
     free (tp_a) ;
-    if (st != GB200_SUCCESS) return (orig (c, ctype, accum, reduce, A, Context)) ;
+    if (st != GB200_SUCCESS)
+    {
+        GrB_Info fail = GrB_PANIC ;
+        if (!neighbour_forward ("GB_reduce_to_scalar", st, &fail)) return (fail) ;
+        return (orig (c, ctype, accum, reduce, A, Context)) ;
+    }
     /* S = [s], 1-by-1, one entry */
     GrB_Matrix S = NULL ;
     GrB_Info info = host_create (&S, A->type, 1, 1, GB_Ap_malloc, true, GB_SAME_HYPER_AS (false),
@@ -630,8 +669,12 @@ GrB_Info GB_transpose (GrB_Matrix *Chandle, GrB_Type ctype, const bool C_is_csc,
     gb200_status st = GB200_OUT_OF_MEMORY ;
     if (as_abi (&am, A, &tp_a)) st = gb200_transpose_host (&r, &am, ctype->code, via_qsort, A->hyper_ratio) ;
     free (tp_a) ;
-    /* nothing was changed: let the reference do it (and report what there is to report) */
-    if (st != GB200_SUCCESS) return (orig (Chandle, ctype, C_is_csc, A_in, op_in, Context)) ;
+    if (st != GB200_SUCCESS)
+    {
+        GrB_Info fail = GrB_PANIC ;
+        if (!neighbour_forward ("GB_transpose", st, &fail)) { (*Chandle) = NULL ; return (fail) ; }
+        return (orig (Chandle, ctype, C_is_csc, A_in, op_in, Context)) ;
+    }
     gb200_result_info f ;
     gb200_result_get_info (r, &f) ;
     GrB_Matrix T = NULL ;
@@ -739,8 +782,16 @@ GrB_Info GB_accum_mask (GrB_Matrix C, const GrB_Matrix M_in, const GrB_Matrix MT
         C_replace ? 1 : 0, (accum != NULL) ? (int) accum->opcode : 0,
         (accum != NULL) ? (int) accum->xtype->code : 0, r_hyper) ;
     free (tp_c) ; free (tp_t) ; free (tp_m) ;
-    /* nothing was changed: let the reference do it (and report what there is to report) */
-    if (st != GB200_SUCCESS) return (orig (C, M_in, MT_in, accum, Thandle, C_replace, Mask_complement, Context)) ;
+    if (st != GB200_SUCCESS)
+    {
+        GrB_Info fail = GrB_PANIC ;
+        if (!neighbour_forward ("GB_accum_mask", st, &fail))
+        {
+            host_free (Thandle) ;       /* as GB_accum_mask's own GB_FREE_ALL on an error */
+            return (fail) ;
+        }
+        return (orig (C, M_in, MT_in, accum, Thandle, C_replace, Mask_complement, Context)) ;
+    }
     gb200_result_info f ;
     gb200_result_get_info (r, &f) ;
     GrB_Matrix R = NULL ;

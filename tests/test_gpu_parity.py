@@ -648,3 +648,14 @@ def test_accum_mask_vectors_bfs_and_sssp_steps(G):
         check_mv(G, op="mxv", A=A, u=(n, np.arange(n), d), type_="FP64", semiring="GxB_MIN_PLUS_FP64",
                  n_out=n, winit=(np.arange(n), d), accum="GrB_MIN_FP64")
         assert REF_ONLY or dev.calls() >= 1, "GB_accum_mask did not run on the device"
+
+
+def test_no_neighbour_call_failed_on_the_device(G):
+    """every GB_select / GB_reduce_to_scalar / GB_transpose / GB_accum_mask call the shim took in this
+    process ran on the device: none failed, none was delegated to the host"""
+    import ctypes as C
+    if REF_ONLY:
+        pytest.skip("reference only")
+    f, w = C.c_int64(), C.c_int64()
+    G.shim.gb200_shim_neighbour_stats(C.byref(f), C.byref(w))
+    assert (f.value, w.value) == (0, 0)
