@@ -126,3 +126,14 @@ def test_concurrent_callers(emu):
         for k in range(4):
             T.assert_same(want[k][0], got[k][0], "PLUS", f"thread {k} masked saxpy")
             T.assert_same(want[k][1], got[k][1], "PLUS", f"thread {k} masked dot")
+
+
+def test_transpose_and_accum_mask_against_the_oracle(emu):
+    """rows f2 / f1 through the C ABI: gb200_transpose_host and gb200_accum_mask_host against the pinned
+    restatements (a sample of tests/test_gpu_seam.py)"""
+    with emu.swapped():
+        T.test_transpose_matches_oracle(True, "INT16")
+        T.test_transpose_matches_oracle(False, None)
+        T.test_accum_mask_matches_oracle(True, True, True)
+        T.test_accum_mask_matches_oracle(False, False, False)
+        T.test_accum_mask_edge_cases()

@@ -38,3 +38,13 @@ def test_grb_api_parity_on_the_host():
 def test_reference_demo_programs_on_the_host():
     """tri_demo, bfs_demo, mis_demo of the reference, unmodified, under LD_PRELOAD of the emulated shim"""
     _run(["tests/test_demo_programs.py"], "args0 or args1")       # the small inputs: Wathen 4x4, random 5x5
+
+
+def test_neighbours_of_the_multiply_on_the_host():
+    """rows f1 / f2: the interposed GB_transpose and GB_accum_mask (device transpose by radix sort, device
+    accum / mask) against the reference through GrB_transpose / GrB_mxm, a sample"""
+    out = _run(["tests/test_gpu_parity.py"],
+               "test_transpose_seam and between or test_grb_transpose_with_mask_and_accum or "
+               "test_accum_mask_typecasts or test_accum_mask_vectors_bfs_and_sssp_steps or "
+               "test_no_neighbour_call_failed_on_the_device")
+    assert "deselected" in out
