@@ -85,6 +85,8 @@ _SIGS = {
     "gb200_select_host": (_I, [_VP, _VP, _I, _I64]),
     "gb200_accum_mask_device": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I]),
     "gb200_accum_mask_host": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I]),
+    "gb200_assign_scalar_device": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _I, _I]),
+    "gb200_assign_scalar_host": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _I, _I]),
     "gb200_transpose_device": (_I, [_VP, _VP, _I, _I, C.c_double]),
     "gb200_transpose_host": (_I, [_VP, _VP, _I, _I, C.c_double]),
     "gb200_peerbuf_create": (_I, [_VP, _I64, _I, _I, _I]),
@@ -321,6 +323,20 @@ def accum_mask_host(Cm: Matrix, T: Matrix, M: Optional[Matrix] = None, mask_comp
     _check(lib.gb200_accum_mask_host(C.byref(rh), C.byref(cc), C.byref(ct),
                                      C.byref(cm) if cm is not None else None, int(mask_comp), int(replace),
                                      op, xy, int(hyper)), "gb200_accum_mask_host")
+    return _fetch(rh, True, pinned)
+
+
+def assign_scalar_host(Cm: Matrix, M: Matrix, scalar, scalar_type: str, replace: bool = False,
+                       accum: Optional[tuple] = None, hyper: bool = False, pinned: bool = False) -> Result:
+    """C<M> = accum (C, scalar) over all of C on the device (gb200_assign_scalar_host + fetch), reference
+    GrB_assign with GrB_ALL and a scalar (Source/GB_assign_scalar.c); returns the new C"""
+    rh = C.c_void_p()
+    cc, cm = Cm.c(), M.c()
+    x = np.array([scalar], dtype=TYPES[scalar_type][1])
+    op, xy = (OPCODES[accum[0]], TYPES[accum[1]][0]) if accum is not None else (0, 0)
+    _check(lib.gb200_assign_scalar_host(C.byref(rh), C.byref(cc), C.byref(cm), int(replace), op, xy,
+                                        x.ctypes.data_as(C.c_void_p), TYPES[scalar_type][0], int(hyper)),
+           "gb200_assign_scalar_host")
     return _fetch(rh, True, pinned)
 
 

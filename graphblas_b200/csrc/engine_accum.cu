@@ -424,5 +424,61 @@ gb200_status gb200_accum_mask_host (gb200_result *out, const gb200_matrix *C, co
     return st ;
 }
 
+gb200_status gb200_assign_scalar_device (gb200_result *out, gb200_dmatrix Cd, gb200_dmatrix Md, int c_replace,
+    int accum_opcode, int accum_xy_code, const void *scalar, int scalar_code, int result_hyper)
+{
+    if (out == NULL || Cd == NULL || Md == NULL || scalar == NULL) return GB200_INVALID ;
+    *out = NULL ;
+    if (scalar_code < GB200_BOOL || scalar_code > GB200_FP64)
+    {
+        set_error ("scalar of a user-defined type") ;
+        return GB200_NOT_SUPPORTED ;
+    }
+    GB200_TRY (ensure_init ()) ;
+    Ctx &c = ctx () ;
+    std::lock_guard<std::recursive_mutex> lock (c.mu) ;
+    // T = the scalar on the pattern of the mask's true entries: the expanded scalar is dense, but C<M> = Z only
+    // ever looks at it where the mask admits
+    DMat Mv ;
+    DevBuf Mp2, Mi2, Tx ;
+    GB200_TRY (filter_mask (Md, Mv, Mp2, Mi2)) ;
+    const int tsz = type_size (scalar_code) ;
+    GB200_TRY (Tx.alloc ((size_t) (Mv.nnz > 0 ? Mv.nnz : 1) * tsz)) ;
+    uint64_t bits = 0 ;
+    memcpy (&bits, scalar, tsz) ;
+    GB200_TRY (fill_bits (Tx.ptr, tsz, bits, Mv.nnz)) ;
+    gb200_dmatrix_s Tt ;
+    Tt.v = Mv ;
+    Tt.v.x = Tx.ptr ;
+    Tt.v.type_code = scalar_code ;
+    Tt.v.iso = 1 ;
+    Tt.is_hyper_flag = Md->is_hyper_flag ;
+    Tt.iso_known = 1 ;
+    return gb200_accum_mask_device (out, Cd, &Tt, Md, 0, c_replace, accum_opcode, accum_xy_code, result_hyper) ;
+}
+
+gb200_status gb200_assign_scalar_host (gb200_result *out, const gb200_matrix *C, const gb200_matrix *M,
+    int c_replace, int accum_opcode, int accum_xy_code, const void *scalar, int scalar_code, int result_hyper)
+{
+    if (out == NULL || C == NULL || M == NULL || scalar == NULL) return GB200_INVALID ;
+    *out = NULL ;
+    if (C->type_code < GB200_BOOL || C->type_code > GB200_FP64 || M->type_code < GB200_BOOL
+        || M->type_code > GB200_FP64)
+    {
+        set_error ("operand of a user-defined type") ;
+        return GB200_NOT_SUPPORTED ;
+    }
+    gb200_dmatrix dC = NULL, dM = NULL ;
+    bool cached_c = false, cached_m = false ;
+    GB200_TRY (cache_acquire (&dC, C, &cached_c)) ;
+    gb200_status st = cache_acquire (&dM, M, &cached_m) ;
+    if (st == GB200_SUCCESS)
+        st = gb200_assign_scalar_device (out, dC, dM, c_replace, accum_opcode, accum_xy_code, scalar, scalar_code,
+            result_hyper) ;
+    if (dM != NULL) { if (cached_m) cache_release (dM) ; else gb200_dmatrix_free (&dM) ; }
+    if (cached_c) cache_release (dC) ; else gb200_dmatrix_free (&dC) ;
+    return st ;
+}
+
 #pragma GCC visibility pop
 } // extern "C"

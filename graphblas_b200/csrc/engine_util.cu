@@ -244,6 +244,7 @@ gb200_status fill_bits (void *dst, int elem_size, uint64_t bits, int64_t n)
     if (elem_size == 4) fill_kernel<uint32_t> <<<grid_for (n), 256, 0, st>>> ((uint32_t *) dst, (uint32_t) bits, n) ;
     else if (elem_size == 8) fill_kernel<uint64_t> <<<grid_for (n), 256, 0, st>>> ((uint64_t *) dst, bits, n) ;
     else if (elem_size == 1) fill_kernel<uint8_t> <<<grid_for (n), 256, 0, st>>> ((uint8_t *) dst, (uint8_t) bits, n) ;
+    else if (elem_size == 2) fill_kernel<uint16_t> <<<grid_for (n), 256, 0, st>>> ((uint16_t *) dst, (uint16_t) bits, n) ;
     else { set_error ("fill_bits: bad element size %d", elem_size) ; return GB200_INVALID ; }
     count_launch () ;
     GB200_CUDA (cudaGetLastError ()) ;

@@ -822,3 +822,101 @@ GrB_Info GB_accum_mask (GrB_Matrix C, const GrB_Matrix M_in, const GrB_Matrix MT
     __atomic_fetch_add (&g_accum_mask_calls, 1, __ATOMIC_RELAXED) ;
     return (transplant_conform (C, C->type, &R, Context)) ;
 }
+
+/* -------------------------------------------------------------------------------------------------
+ * C<M> = accum (C, scalar) over all of C (`v<q> = level`, the other call of the BFS
+ * loop, Demo/Source/bfs5m.c:74): GB_assign (reference Source/GB.h:2026-2046, body Source/GB_assign.c) is
+ * interposed.  Taken here: scalar expansion with Rows = Cols = GrB_ALL (not a row or column assign), a mask
+ * that is neither complemented nor transposed and is held like C, built-in types and accumulator, no
+ * pending work, the same size policy as GB_accum_mask above.  The new C is computed by libgb_b200.so
+ * (gb200_assign_scalar_host: the scalar on the pattern of the mask's true entries, then the accum / mask
+ * kernels) and handed to the reference's own GB_transplant_conform.  Everything else -- index lists, matrix
+ * operands, complemented masks (a dense result), errors to report -- goes to the reference's own GB_assign.
+ * ------------------------------------------------------------------------------------------------- */
+static int64_t g_assign_calls = 0 ;
+
+__attribute__ ((visibility ("default")))
+int64_t gb200_shim_assign_calls (void) { return (g_assign_calls) ; }
+
+__attribute__ ((visibility ("default")))
+GrB_Info GB_assign (GrB_Matrix C, const bool C_replace, const GrB_Matrix M_in, const bool Mask_comp,
+    bool M_transpose, const GrB_BinaryOp accum, const GrB_Matrix A_in, bool A_transpose,
+    const GrB_Index *Rows, const GrB_Index nRows_in, const GrB_Index *Cols, const GrB_Index nCols_in,
+    const bool scalar_expansion, const void *scalar, const GB_Type_code scalar_code, const bool col_assign,
+    const bool row_assign, GB_Context Context)
+{
+    typedef GrB_Info (*fn_t) (GrB_Matrix, const bool, const GrB_Matrix, const bool, bool, const GrB_BinaryOp,
+        const GrB_Matrix, bool, const GrB_Index *, const GrB_Index, const GrB_Index *, const GrB_Index,
+        const bool, const void *, const GB_Type_code, const bool, const bool, GB_Context) ;
+    typedef GrB_Info (*tc_fn) (GrB_Matrix, GrB_Type, GrB_Matrix *, GB_Context) ;
+    static fn_t orig = NULL ;
+    static tc_fn transplant_conform = NULL ;
+    static const GrB_Index **all = NULL ;
+    if (orig == NULL) orig = (fn_t) host_symbol ("GB_assign", (void *) GB_assign) ;
+    if (transplant_conform == NULL) transplant_conform = (tc_fn) dlsym (RTLD_DEFAULT, "GB_transplant_conform") ;
+    if (all == NULL) all = (const GrB_Index **) dlsym (RTLD_DEFAULT, "GrB_ALL") ;
+    if (orig == NULL) return (GrB_PANIC) ;
+    if (g_enabled < 0) g_enabled = (getenv ("GB200_SHIM_DISABLE") != NULL) ? 0 : 1 ;
+    int64_t min_nnz = g_accum_mask_min ;
+    if (min_nnz < 0)
+    {
+        const char *env = getenv ("GB200_ACCUM_MASK_MIN_NNZ") ;
+        if (env != NULL && atoll (env) >= 0) g_accum_mask_min = min_nnz = atoll (env) ;
+        else min_nnz = gb200_cache_enabled () ? 65536 : INT64_MAX ;
+    }
+    const GrB_Matrix M = M_in ;
+    int mine = g_enabled && transplant_conform != NULL && all != NULL && bind_host ()
+        && scalar_expansion && scalar != NULL && A_in == NULL && !col_assign && !row_assign
+        && Rows == (*all) && Cols == (*all) && M != NULL && !Mask_comp && !M_transpose
+        && C != NULL && C->magic == GB_MAGIC && M->magic == GB_MAGIC && C->is_csc == M->is_csc
+        && C->vlen == M->vlen && C->vdim == M->vdim && C->vdim <= ((int64_t) 1 << 27)
+        && C->type->code < GB_UCT_code && M->type->code < GB_UCT_code && scalar_code < GB_UCT_code
+        && (accum == NULL || (accum->magic == GB_MAGIC && accum->opcode >= GB_FIRST_opcode
+            && accum->opcode <= GB_LE_opcode && accum->xtype == accum->ytype
+            && accum->xtype->code < GB_UCT_code))
+        && !GB_PENDING (C) && !GB_ZOMBIES (C) && !GB_PENDING (M) && !GB_ZOMBIES (M)
+        && GB_NNZ (C) + GB_NNZ (M) >= min_nnz ;
+    if (!mine) return (orig (C, C_replace, M_in, Mask_comp, M_transpose, accum, A_in, A_transpose, Rows, nRows_in,
+        Cols, nCols_in, scalar_expansion, scalar, scalar_code, col_assign, row_assign, Context)) ;
+
+    gb200_matrix cm, mm ;
+    int64_t *tp_c = NULL, *tp_m = NULL ;
+    gb200_result r = NULL ;
+    gb200_status st = GB200_OUT_OF_MEMORY ;
+    /* R as GB_mask would build it: hypersparse when C and Z both are; Z = accum (C,T) is when C and T (the mask's
+     * pattern) are, Z = T alone when the mask is */
+    const int r_hyper = (C->is_hyper && M->is_hyper && C->vdim > 1) ? 1 : 0 ;
+    if (as_abi (&cm, C, &tp_c) && as_abi (&mm, M, &tp_m))
+        st = gb200_assign_scalar_host (&r, &cm, &mm, C_replace ? 1 : 0, (accum != NULL) ? (int) accum->opcode : 0,
+            (accum != NULL) ? (int) accum->xtype->code : 0, scalar, (int) scalar_code, r_hyper) ;
+    free (tp_c) ; free (tp_m) ;
+    if (st != GB200_SUCCESS)
+    {
+        GrB_Info fail = GrB_PANIC ;
+        if (!neighbour_forward ("GB_assign", st, &fail)) return (fail) ;
+        return (orig (C, C_replace, M_in, Mask_comp, M_transpose, accum, A_in, A_transpose, Rows, nRows_in,
+            Cols, nCols_in, scalar_expansion, scalar, scalar_code, col_assign, row_assign, Context)) ;
+    }
+    gb200_result_info f ;
+    gb200_result_get_info (r, &f) ;
+    GrB_Matrix R = NULL ;
+    GrB_Info info = host_create (&R, C->type, f.vlen, f.vdim, GB_Ap_malloc, C->is_csc,
+        GB_SAME_HYPER_AS (f.is_hyper), C->hyper_ratio, (f.nvec > 0) ? f.nvec : 1,
+        (f.nnz > 0) ? f.nnz : 1, true, Context) ;
+    if (info == GrB_SUCCESS)
+    {
+        st = gb200_result_fetch (r, R->p, f.is_hyper ? R->h : NULL, R->i, R->x) ;
+        if (st != GB200_SUCCESS)
+        {
+            host_free (&R) ;
+            info = (st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC ;
+        }
+    }
+    if (info != GrB_SUCCESS) { gb200_result_free (&r) ; return (info) ; }       /* C is left as it was */
+    if (f.is_hyper) R->nvec = f.nvec ;
+    R->nvec_nonempty = f.nvec_nonempty ;
+    R->magic = GB_MAGIC ;
+    adopt_result (&r, R, &f) ;
+    __atomic_fetch_add (&g_assign_calls, 1, __ATOMIC_RELAXED) ;
+    return (transplant_conform (C, C->type, &R, Context)) ;
+}

@@ -227,6 +227,18 @@ gb200_status gb200_accum_mask_host (gb200_result *out, const gb200_matrix *C, co
     const gb200_matrix *M, int mask_comp, int c_replace, int accum_opcode, int accum_xy_code,
     int result_hyper) ;
 
+/* ---- C<M> = accum (C, scalar) over all of C (`v<q> = level`, the other call of the
+ * BFS loop, reference Demo/Source/bfs5m.c:74 -> Source/GB_assign_scalar.c -> Source/GB_assign.c with
+ * I = J = GrB_ALL and a non-complemented mask).  The expanded scalar is dense, but C<M> = Z only looks at it
+ * where the mask admits: T = the scalar (a value of type scalar_code) on the pattern of M's true entries,
+ * then exactly gb200_accum_mask_* above with mask_comp = 0.  R has C's type: where M admits, accum (C, scalar)
+ * (the scalar alone where C has no entry or there is no accumulator); elsewhere C's entry, or none when
+ * c_replace. */
+gb200_status gb200_assign_scalar_device (gb200_result *out, gb200_dmatrix C, gb200_dmatrix M, int c_replace,
+    int accum_opcode, int accum_xy_code, const void *scalar, int scalar_code, int result_hyper) ;
+gb200_status gb200_assign_scalar_host (gb200_result *out, const gb200_matrix *C, const gb200_matrix *M,
+    int c_replace, int accum_opcode, int accum_xy_code, const void *scalar, int scalar_code, int result_hyper) ;
+
 /* ---- GrB_reduce of a matrix to a scalar over a built-in monoid (reference
  * Source/GB_reduce_to_scalar.c:107-270).  add_opcode: a gb200_opcode naming the monoid (MIN MAX PLUS
  * TIMES, or LOR LAND LXOR EQ for bool; boolean renames as in gb200_semiring_canonical).  *scalar

@@ -412,6 +412,29 @@ class GraphBLAS:
         self.matrix_nvals(Cm)
         return self.raw(Cm)
 
+    def assign_scalar(self, Cm, M, accum, type_: str, x, desc, nrows: int, ncols=None):
+        """GrB_Matrix_assign_<type> (C, Mask, accum, x, GrB_ALL, nrows, GrB_ALL, ncols, desc), or
+        GrB_Vector_assign_<type> (w, mask, accum, x, GrB_ALL, n, desc) when ncols is None
+        (Include/GraphBLAS.h:4260, 4477; Demo/Source/bfs5m.c:74)"""
+        ct = {"FP64": C.c_double, "FP32": C.c_float, "INT64": C.c_int64, "INT32": C.c_int32,
+              "UINT64": C.c_uint64, "UINT32": C.c_uint32, "INT16": C.c_int16, "UINT16": C.c_uint16,
+              "INT8": C.c_int8, "UINT8": C.c_uint8, "BOOL": C.c_bool}[type_]
+        all_ = C.c_void_p.in_dll(self.lib, "GrB_ALL")
+        acc = self.obj(accum) if accum else None
+        if ncols is None:
+            fn = getattr(self.lib, "GrB_Vector_assign_" + type_)
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, ct, C.c_void_p, C.c_uint64, C.c_void_p]
+            self.ok(fn(Cm, M, acc, x, all_, nrows, desc), "GrB_Vector_assign")
+        else:
+            fn = getattr(self.lib, "GrB_Matrix_assign_" + type_)
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, ct, C.c_void_p, C.c_uint64, C.c_void_p,
+                           C.c_uint64, C.c_void_p]
+            self.ok(fn(Cm, M, acc, x, all_, nrows, all_, ncols, desc), "GrB_Matrix_assign")
+
+    def shim_assign_calls(self) -> int:
+        self.shim.gb200_shim_assign_calls.restype = C.c_int64
+        return self.shim.gb200_shim_assign_calls()
+
     def transpose(self, Cm, M, accum, A, desc):
         """GrB_transpose (Include/GraphBLAS.h): C<M> = accum (C, A')"""
         self.ok(self.lib.GrB_transpose(Cm, M, self.obj(accum) if accum else None, A, desc), "GrB_transpose")

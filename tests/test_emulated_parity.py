@@ -46,5 +46,6 @@ def test_neighbours_of_the_multiply_on_the_host():
     out = _run(["tests/test_gpu_parity.py"],
                "test_transpose_seam and between or test_grb_transpose_with_mask_and_accum or "
                "test_accum_mask_typecasts or test_accum_mask_vectors_bfs_and_sssp_steps or "
+               "test_assign_scalar_bfs_level_step or "
                "test_no_neighbour_call_failed_on_the_device")
     assert "deselected" in out

@@ -650,6 +650,69 @@ def test_accum_mask_vectors_bfs_and_sssp_steps(G):
         assert REF_ONLY or dev.calls() >= 1, "GB_accum_mask did not run on the device"
 
 
+# ---------------------------------------------------------------------------------------------
+# GrB_assign of a scalar over all of C under a mask (row f3, `v<q> = level` of bfs5m.c:74): the interposed
+# GB_assign computes the new C on the device
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("replace", [False, True])
+@pytest.mark.parametrize("shape", ["matrix", "hyper"])
+@pytest.mark.parametrize("k", range(6))
+def test_assign_scalar_on_device(G, k, shape, replace):
+    from parity import compare, export_csr, import_sp
+    from test_oracle import ASSIGN_CASES
+    ctype, mtype, stype, scalar, accum = ASSIGN_CASES[k]
+    n, m = 140, 90
+    Cs = gen.er(n, m, 2200, 48 + k, NP[ctype])
+    Ms = gen.er(n, m, 5000, 50 + k, NP[mtype], lo=0, hi=2)
+    fmt = "CSC" if shape == "matrix" else "HyperCSR"
+    out = []
+    for gpu in (False, True):
+        c, mh = import_sp(G, Cs, ctype, fmt), import_sp(G, Ms, mtype, fmt)
+        d = G.descriptor(outp=GrB_REPLACE) if replace else None
+        with _device_accum_mask(G):
+            G.use_gpu(gpu and not REF_ONLY)
+            before = 0 if REF_ONLY else G.shim_assign_calls()
+            try:
+                G.assign_scalar(c, mh, accum[0] if accum else None, stype, scalar, d, n, m)
+                G.matrix_nvals(c)
+            finally:
+                G.use_gpu(False)
+            if gpu and not REF_ONLY:
+                assert G.shim_assign_calls() - before == 1, "GB_assign did not run on the device"
+        out.append(export_csr(G, c))
+        G.matrix_free(mh)
+        G.descriptor_free(d)
+    ok, why = compare(out[0], out[1], "MIN")
+    assert ok, why
+
+
+def test_assign_scalar_bfs_level_step(G):
+    """v<q> = level on GrB_Vectors, INT32 levels under a BOOL frontier, over three levels as bfs5m does"""
+    n = 5000
+    rng = np.random.default_rng(9)
+    out = []
+    for gpu in (False, True):
+        v = G.vector_new("INT32", n)
+        with _device_accum_mask(G):
+            G.use_gpu(gpu and not REF_ONLY)
+            before = 0 if REF_ONLY else G.shim_assign_calls()
+            try:
+                r2 = np.random.default_rng(9)
+                for level in (1, 2, 3):
+                    qi = np.sort(r2.choice(n, 700 * level, replace=False))
+                    q = G.vector_import("BOOL", n, qi, r2.random(len(qi)) < 0.9)     # some entries false
+                    G.assign_scalar(v, q, None, "INT32", level, None, n)
+                    G.vector_nvals(v)
+                    G.vector_free(q)
+            finally:
+                G.use_gpu(False)
+            if gpu and not REF_ONLY:
+                assert G.shim_assign_calls() - before == 3, "GB_assign did not run on the device"
+        out.append(G.vector_export(v))
+    assert out[0]["n"] == out[1]["n"] and out[0]["type"] == out[1]["type"]
+    assert np.array_equal(out[0]["vi"], out[1]["vi"]) and np.array_equal(out[0]["vx"], out[1]["vx"])
+
+
 def test_no_neighbour_call_failed_on_the_device(G):
     """every GB_select / GB_reduce_to_scalar / GB_transpose / GB_accum_mask call the shim took in this
     process ran on the device: none failed, none was delegated to the host"""
@@ -659,3 +722,4 @@ def test_no_neighbour_call_failed_on_the_device(G):
     f, w = C.c_int64(), C.c_int64()
     G.shim.gb200_shim_neighbour_stats(C.byref(f), C.byref(w))
     assert (f.value, w.value) == (0, 0)
+

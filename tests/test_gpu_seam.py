@@ -487,3 +487,21 @@ def test_accum_mask_edge_cases():
         ref = oracle_c.accum_mask(Cm, T, M, comp, rep, a, False)
         got = gb.accum_mask_host(Cm, T, M, comp, rep, a, False).matrix
         assert_same(ref, got, "MIN", "accum_mask on vectors")
+
+
+@pytest.mark.parametrize("replace", [False, True])
+@pytest.mark.parametrize("shape", ["matrix", "hyper", "vector"])
+def test_assign_scalar_matches_oracle(replace, shape):
+    """gb200_assign_scalar_host (row f3) against the pinned restatement: GB_accum_mask with T = the scalar on
+    the pattern of the mask's true entries (pinned against GrB_*_assign in tests/test_oracle.py)"""
+    from test_oracle import ASSIGN_CASES, accum_mask_inputs, scalar_on_mask
+    for k, (ctype, mtype, stype, scalar, accum) in enumerate(ASSIGN_CASES):
+        if shape == "vector":
+            Cm = gb.Matrix.from_scipy(gen.er(3000, 1, 900, 61 + k, NPT[ctype]).tocsc(), ctype)
+            M = gb.Matrix.from_scipy(gen.er(3000, 1, 1500, 62 + k, NPT[mtype], lo=0, hi=2).tocsc(), mtype)
+        else:
+            Cm, _, M = accum_mask_inputs(ctype, ctype, mtype, shape == "hyper", seed=k)
+        acc = (accum[1], accum[2]) if accum else None
+        ref = oracle_c.accum_mask(Cm, scalar_on_mask(M, scalar, stype), M, False, replace, acc, shape == "hyper")
+        got = gb.assign_scalar_host(Cm, M, scalar, stype, replace, acc, shape == "hyper").matrix
+        assert_same(ref, got, "MIN", f"assign case {k} {shape}")

@@ -402,3 +402,53 @@ def test_oracle_accum_mask_vs_reference(G, case, comp, replace, hyper):
     for h_ in (c, m):
         if h_ is not None:
             G.matrix_free(h_)
+
+
+# ---------------------------------------------------------------------------------------------
+# GrB_assign of a scalar over all of C under a mask (row f3, bfs5m.c:74): the claim the device path rests
+# on -- C<M> = accum (C, scalar) equals GB_accum_mask with T = the scalar on the pattern of M's true entries --
+# pinned against the reference's own GrB_Matrix_assign_<type> / GrB_Vector_assign_<type>
+# ---------------------------------------------------------------------------------------------
+def scalar_on_mask(M: gb.Matrix, scalar, type_: str) -> gb.Matrix:
+    keep = np.asarray(M.x) != 0
+    cnt = np.add.reduceat(keep, M.p[:-1]) if len(M.i) else np.zeros(M.nvec, dtype=np.int64)
+    cnt = np.where(np.diff(M.p) > 0, cnt, 0)
+    p = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    return gb.Matrix(M.vlen, M.vdim, p, np.asarray(M.i)[keep], np.full(int(keep.sum()), scalar, dtype=NP[type_]),
+                     M.h, type_)
+
+
+ASSIGN_CASES = [("FP64", "INT8", "FP64", 2.5, None), ("INT32", "BOOL", "INT32", 7, None),
+                ("INT32", "FP64", "FP64", -3.75, ("GrB_PLUS_INT32", "PLUS", "INT32")),
+                ("FP32", "INT8", "INT64", 9, ("GrB_MIN_FP32", "MIN", "FP32")),
+                ("BOOL", "INT8", "BOOL", True, ("GrB_LOR", "LOR", "BOOL")),
+                ("UINT8", "UINT16", "INT16", 300, ("GrB_TIMES_INT16", "TIMES", "INT16"))]
+
+
+@pytest.mark.parametrize("case", ASSIGN_CASES, ids=lambda c: "-".join(map(str, c[:3])))
+@pytest.mark.parametrize("replace", [False, True])
+@pytest.mark.parametrize("shape", ["matrix", "hyper", "vector"])
+def test_oracle_assign_scalar_vs_reference(G, case, replace, shape):
+    from grbref import GrB_REPLACE
+    ctype, mtype, stype, scalar, accum = case
+    if shape == "vector":
+        n, m = 3000, 1
+        Cm = gb.Matrix.from_scipy(gen.er(n, m, 900, 61, NP[ctype]).tocsc(), ctype)
+        M = gb.Matrix.from_scipy(gen.er(n, m, 1500, 62, NP[mtype], lo=0, hi=2).tocsc(), mtype)
+    else:
+        Cm, _, M = accum_mask_inputs(ctype, ctype, mtype, shape == "hyper", seed=7)
+    c, mh = to_ref(G, Cm), to_ref(G, M)
+    d = G.descriptor(outp=GrB_REPLACE) if replace else None
+    G.assign_scalar(c, mh, accum[0] if accum else None, stype, scalar, d, Cm.vlen, Cm.vdim)
+    G.matrix_nvals(c)
+    ref = G.raw(c)
+    T = scalar_on_mask(M, scalar, stype)
+    got = oracle_c.accum_mask(Cm, T, M, False, replace, (accum[1], accum[2]) if accum else None, False)
+    rp, ri, rx = expand(ref["vdim"], ref["p"], ref["h"] if ref["is_hyper"] else None, ref["i"], ref["x"])
+    gp, gi, gx = expand(got.vdim, got.p, got.h, got.i, got.x)
+    assert ref["type"] == got.type
+    assert np.array_equal(rp, gp) and np.array_equal(ri, gi), "pattern differs"
+    assert np.array_equal(rx, gx, equal_nan=True), "values differ"
+    G.matrix_free(c)
+    G.matrix_free(mh)
+    G.descriptor_free(d)
