@@ -1,14 +1,16 @@
 /* gb_oracle.c -- TEST INFRASTRUCTURE, not product code.
  *
  * A plain-C CPU restatement of the reference's masked semiring multiply at the GB_AxB_parallel seam
- * (SuiteSparse:GraphBLAS v2.3.3), used only as the checker by tests/, __graft_entry__.smoke() and
- * bench.py's cpu_baseline leg.  Nothing in graphblas_b200/ links, loads or calls it.
+ * (SuiteSparse:GraphBLAS v2.3.3) and of its neighbours GB_transpose and GB_accum_mask, used only as the
+ * checker by tests/, __graft_entry__.smoke(), bench.py's cpu_baseline leg and the parity legs of the tools
+ * behind bench.py's `neighbours` entry.  Nothing in graphblas_b200/ links, loads or calls it.
  *
  * Parity is PINNED: tests/test_oracle.py checks this file against (a) the compiled reference
  * itself (oracle/_ref, built by Makefile.ref from the unmodified sources) on seeded inputs over every
  * method / mask / format combination, (b) committed golden vectors generated from that reference
  * (tests/golden/, script tests/golden/make_golden.py), and (c) the triangle counts printed in the
- * reference's own Demo/Output/tri_demo.out.
+ * reference's own Demo/Output/tri_demo.out; oracle_transpose and oracle_accum_mask are pinned against the
+ * reference's own GB_transpose / GB_accum_mask / GrB_Matrix_assign called directly.
  *
  * Each function cites the reference code it restates.  The algorithms follow the reference's order
  * of operations exactly (ascending k, identity-or-first-product start), so floating-point results
