@@ -596,15 +596,17 @@ GrB_Info GB_reduce_to_scalar (void *c, const GrB_Type ctype, const GrB_BinaryOp 
  * C = (ctype) A' (SURVEY.md 8f row f2): GB_transpose (reference Source/GB.h:2153-2162, body
  * Source/GB_transpose.c:38-985) is interposed.  It is what GB_AxB_meta runs IN FRONT of the multiply for
  * a transposed operand or a mask held in the other format (Source/GB_AxB_meta.c:203,247,311,328-337,355),
- * and what GrB_transpose, GB_accum_mask, GB_eWise ... run for their own transposes.  Taken here: the
- * out-of-place call C = A' (Chandle and A_in both given and different, GB_transpose.c:97-113) of the
- * general case (avlen > 1, avdim > 1, anz > 0, :470) without an operator (or with the identity of A's own
+ * and what GrB_transpose, GB_accum_mask, GB_eWise ... run for their own transposes, and what a change of
+ * format (GxB_Matrix_export_CSR of a matrix held by column, GxB_Matrix_Option_set FORMAT) runs in place.
+ * Taken here: all three call forms (GB_transpose.c:55-113: C = A' out of place, C = C' in place of the
+ * handle, A = A' in place of the header -- the in-place forms compute T from the intact input and only then
+ * swap it in, as the reference's own bucket method does, :913-950) of the general case (avlen > 1, avdim > 1, anz > 0, :470) without an operator (or with the identity of A's own
  * type, which the reference drops too, :213-220), built-in types, no pending work.  T comes from the
  * device in the form the reference's method would have produced (quicksort: hypersparse, bucket: not;
  * the memory estimate of :497-606 restated) already conformed by the rule of GB_to_hyper_conform; the
  * reference's own GB_to_hyper_conform is then run on it as :968-975 does (it finds nothing to change).
- * Everything else -- transposes in place, vectors, empty matrices, operators, user-defined types --
- * goes to the reference's own GB_transpose untouched.
+ * Everything else -- vectors, empty matrices, operators, user-defined types -- goes to the reference's own
+ * GB_transpose untouched.
  * ------------------------------------------------------------------------------------------------- */
 static int64_t g_transpose_calls = 0 ;
 static int64_t g_transpose_min = -1 ;       /* fewer entries than this: the host's own loop is faster */
@@ -622,10 +624,13 @@ GrB_Info GB_transpose (GrB_Matrix *Chandle, GrB_Type ctype, const bool C_is_csc,
     typedef GrB_Info (*fn_t) (GrB_Matrix *, GrB_Type, const bool, const GrB_Matrix, const GrB_UnaryOp,
         GB_Context) ;
     typedef GrB_Info (*conform_fn) (GrB_Matrix, GB_Context) ;
+    typedef GrB_Info (*transplant_fn) (GrB_Matrix, const GrB_Type, GrB_Matrix *, GB_Context) ;
     static fn_t orig = NULL ;
     static conform_fn conform = NULL ;
+    static transplant_fn transplant = NULL ;
     if (orig == NULL) orig = (fn_t) host_symbol ("GB_transpose", (void *) GB_transpose) ;
     if (conform == NULL) conform = (conform_fn) dlsym (RTLD_DEFAULT, "GB_to_hyper_conform") ;
+    if (transplant == NULL) transplant = (transplant_fn) dlsym (RTLD_DEFAULT, "GB_transplant") ;
     if (orig == NULL) return (GrB_PANIC) ;
     if (g_enabled < 0) g_enabled = (getenv ("GB200_SHIM_DISABLE") != NULL) ? 0 : 1 ;
     if (g_transpose_min < 0)
@@ -633,15 +638,19 @@ GrB_Info GB_transpose (GrB_Matrix *Chandle, GrB_Type ctype, const bool C_is_csc,
         const char *env = getenv ("GB200_TRANSPOSE_MIN_NNZ") ;
         g_transpose_min = (env != NULL && atoll (env) >= 0) ? atoll (env) : 65536 ;
     }
-    const GrB_Matrix A = A_in ;
-    int mine = g_enabled && conform != NULL && bind_host () && Chandle != NULL && A != NULL
-        && (*Chandle) != A && A->magic == GB_MAGIC && A->type != NULL && A->type->code < GB_UCT_code
+    /* the three call forms of GB_transpose.c:55-113 */
+    const int in_place_C = (A_in == NULL) ;                                 /* C = C': *Chandle replaced */
+    const int in_place_A = (A_in != NULL && (Chandle == NULL || (*Chandle) == A_in)) ;  /* A = A', header kept */
+    const GrB_Matrix A = in_place_C ? ((Chandle != NULL) ? (*Chandle) : NULL) : A_in ;
+    int mine = g_enabled && conform != NULL && transplant != NULL && bind_host () && A != NULL
+        && A->magic == GB_MAGIC && A->type != NULL && A->type->code < GB_UCT_code
         && (ctype == NULL || ctype->code < GB_UCT_code)
         && (op_in == NULL || (op_in->opcode == GB_IDENTITY_opcode && A->type == op_in->xtype))
         && !GB_PENDING (A) && !GB_ZOMBIES (A) && A->vlen > 1 && A->vdim > 1
         && GB_NNZ (A) > 0 && GB_NNZ (A) >= g_transpose_min ;
     if (!mine) return (orig (Chandle, ctype, C_is_csc, A_in, op_in, Context)) ;
     if (ctype == NULL || op_in != NULL) ctype = A->type ;          /* GB_transpose.c:203-220 */
+    const double A_hyper_ratio = A->hyper_ratio ;
 
     /* which of the reference's two methods would run decides the form T starts out in (:482-606) */
     int via_qsort = 1 ;
@@ -649,10 +658,13 @@ GrB_Info GB_transpose (GrB_Matrix *Chandle, GrB_Type ctype, const bool C_is_csc,
     {
         const int64_t anz = GB_NNZ (A), avlen = A->vlen ;
         const size_t csize = ctype->size ;
+        const int in_place = in_place_A || in_place_C ;
+        const int recycle_Ai = in_place && !A->i_shallow ;
         double qusage = 0, qsort_memory = 0 ;
-        qusage += GBYTES (anz, sizeof (int64_t)) ;              /* Tj (A->i is not recycled) */
+        if (!recycle_Ai) qusage += GBYTES (anz, sizeof (int64_t)) ;    /* Tj, unless A->i is recycled */
         qusage += GBYTES (anz, sizeof (int64_t)) ;              /* Ti */
         qsort_memory = qusage ;
+        if (in_place && !A->p_shallow) qusage -= GBYTES (A->plen+1, sizeof (int64_t)) ;    /* Ap freed early */
         qusage += GBYTES (anz, sizeof (int64_t)) ;              /* kwork of GB_builder */
         qsort_memory = GB_IMAX (qsort_memory, qusage) ;
         qusage -= GBYTES (anz, sizeof (int64_t)) ;              /* Tj freed */
@@ -667,46 +679,61 @@ GrB_Info GB_transpose (GrB_Matrix *Chandle, GrB_Type ctype, const bool C_is_csc,
     int64_t *tp_a = NULL ;
     gb200_result r = NULL ;
     gb200_status st = GB200_OUT_OF_MEMORY ;
-    if (as_abi (&am, A, &tp_a)) st = gb200_transpose_host (&r, &am, ctype->code, via_qsort, A->hyper_ratio) ;
+    if (as_abi (&am, A, &tp_a)) st = gb200_transpose_host (&r, &am, ctype->code, via_qsort, A_hyper_ratio) ;
     free (tp_a) ;
+    GrB_Info info = GrB_SUCCESS ;
+    GrB_Matrix T = NULL ;
     if (st != GB200_SUCCESS)
     {
         GrB_Info fail = GrB_PANIC ;
-        if (!neighbour_forward ("GB_transpose", st, &fail)) { (*Chandle) = NULL ; return (fail) ; }
-        return (orig (Chandle, ctype, C_is_csc, A_in, op_in, Context)) ;
+        if (neighbour_forward ("GB_transpose", st, &fail))
+            return (orig (Chandle, ctype, C_is_csc, A_in, op_in, Context)) ;
+        info = fail ;
     }
     gb200_result_info f ;
-    gb200_result_get_info (r, &f) ;
-    GrB_Matrix T = NULL ;
-    (*Chandle) = NULL ;
-    GrB_Info info = host_create (&T, ctype, f.vlen, f.vdim, GB_Ap_malloc, C_is_csc,
-        GB_SAME_HYPER_AS (f.is_hyper), A->hyper_ratio, (f.nvec > 0) ? f.nvec : 1,
-        (f.nnz > 0) ? f.nnz : 1, true, Context) ;
-    if (info != GrB_SUCCESS) { gb200_result_free (&r) ; return (info) ; }
-    st = gb200_result_fetch (r, T->p, f.is_hyper ? T->h : NULL, T->i, T->x) ;
-    if (st != GB200_SUCCESS)
+    if (info == GrB_SUCCESS)
     {
-        gb200_result_free (&r) ;
-        host_free (&T) ;
-        return ((st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC) ;
+        gb200_result_get_info (r, &f) ;
+        info = host_create (&T, ctype, f.vlen, f.vdim, GB_Ap_malloc, C_is_csc,
+            GB_SAME_HYPER_AS (f.is_hyper), A_hyper_ratio, (f.nvec > 0) ? f.nvec : 1,
+            (f.nnz > 0) ? f.nnz : 1, true, Context) ;
     }
-    if (f.is_hyper) T->nvec = f.nvec ;
-    T->nvec_nonempty = f.nvec_nonempty ;
-    T->magic = GB_MAGIC ;
-    const int64_t *p_fetched = T->p ;
-    info = conform (T, Context) ;                                   /* GB_transpose.c:968-975 */
+    if (info == GrB_SUCCESS)
+    {
+        st = gb200_result_fetch (r, T->p, f.is_hyper ? T->h : NULL, T->i, T->x) ;
+        if (st != GB200_SUCCESS) info = (st == GB200_OUT_OF_MEMORY) ? GrB_OUT_OF_MEMORY : GrB_PANIC ;
+    }
+    const int64_t *p_fetched = NULL ;
+    if (info == GrB_SUCCESS)
+    {
+        if (f.is_hyper) T->nvec = f.nvec ;
+        T->nvec_nonempty = f.nvec_nonempty ;
+        T->magic = GB_MAGIC ;
+        p_fetched = T->p ;
+        info = conform (T, Context) ;                               /* GB_transpose.c:968-975 */
+    }
     if (info != GrB_SUCCESS)
     {
-        gb200_result_free (&r) ;
+        /* the error contract of GB_transpose.c:22-30: a new C or a C transposed in place is freed and
+         * returned as NULL; an A transposed in place keeps its header (and, here, its content) */
+        if (r != NULL) gb200_result_free (&r) ;
         host_free (&T) ;
+        if (in_place_C) host_free (Chandle) ;
+        else if (!in_place_A) (*Chandle) = NULL ;
         return (info) ;
     }
     /* the device copy of A' serves the multiply that follows (residency cache on), unless the
      * reference's conform disagreed with the form T arrived in */
     if (T->p == p_fetched && (T->is_hyper ? 1 : 0) == f.is_hyper) adopt_result (&r, T, &f) ;
     else gb200_result_free (&r) ;
-    (*Chandle) = T ;
     __atomic_fetch_add (&g_transpose_calls, 1, __ATOMIC_RELAXED) ;
+    if (in_place_A)
+    {
+        /* as the bucket method in place of A (:936-944): the content of A is freed, T moved into its header */
+        return (transplant (A, ctype, &T, Context)) ;
+    }
+    if (in_place_C) host_free (Chandle) ;       /* :920-924: the input C goes, header included */
+    (*Chandle) = T ;
     return (GrB_SUCCESS) ;
 }
 

@@ -497,6 +497,36 @@ def test_transpose_seam(G, case, fmt, ctype):
         assert ref["is_hyper"] == (case[0] == "between_qsort")
 
 
+@pytest.mark.parametrize("held,exported", [("CSC", "CSR"), ("CSR", "CSC"), ("HyperCSC", "CSR"), ("CSR", "HyperCSC")])
+@pytest.mark.parametrize("type_", ["FP64", "INT16"])
+def test_format_change_in_place_on_device(G, held, exported, type_):
+    """A = A' in place of the header (GB_transpose (NULL, NULL, csc, A, NULL), GB_transpose.c:79-95): what
+    GxB_Matrix_export_<other format> runs before it hands the arrays out"""
+    A = gen.er(230, 310, 6000, 91, NP[type_])
+    out = []
+    for gpu in (False, True):
+        from parity import import_sp
+        a = import_sp(G, A, type_, held)
+        if not REF_ONLY:
+            G.shim_transpose_min(0)
+        G.use_gpu(gpu and not REF_ONLY)
+        before = 0 if REF_ONLY else G.shim_transpose_calls()
+        try:
+            out.append(G.matrix_export(a, exported))
+        finally:
+            G.use_gpu(False)
+            if not REF_ONLY:
+                G.shim_transpose_min(65536)
+        if gpu and not REF_ONLY:
+            assert G.shim_transpose_calls() - before == 1, "the GPU transpose did not run"
+    ref, got = out
+    for k in ref:
+        if isinstance(ref[k], np.ndarray):
+            assert np.array_equal(ref[k], got[k]), f"{k} differs"
+        else:
+            assert ref[k] == got[k], f"{k}: ref {ref[k]} got {got[k]}"
+
+
 @pytest.mark.parametrize("fmt,cfmt", [("CSR", "CSR"), ("CSC", "CSR"), ("HyperCSR", "CSC"), ("CSC", "HyperCSC")])
 def test_grb_transpose_with_mask_and_accum(G, fmt, cfmt):
     """GrB_transpose C<!M> += A' through the unmodified API (Source/GrB_transpose.c:98-108 -> GB_transpose)"""
